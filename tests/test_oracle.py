@@ -9,6 +9,17 @@ import mtn_oracle as O
 import golden_util as G
 
 
+@pytest.fixture(autouse=True)
+def _single_thread():
+    """The fixtures were generated single-threaded; MKL's multi-threaded GEMM
+    changes the fp32 reduction order (~1e-6), which would hide a real 1-ulp
+    restatement bug behind a tolerance.  One thread => bit-exact comparisons."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
+
 def test_kat_layernorm():
     z = G.load("kat.npz")
     y = O.layer_norm(G.t(z["ln_in"]), torch.ones(4), torch.zeros(4))
