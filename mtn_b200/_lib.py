@@ -1,0 +1,208 @@
+"""ctypes binding of ``libmtn_b200.so`` (C ABI declared in ``include/mtn_b200.h``).
+
+The product path has no fallback: if the shared library is missing or a call fails
+the caller gets an exception carrying ``mtn_last_error()``.  PyTorch is used only
+as the owner of device memory and streams -- tensors are passed as raw pointers.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
+ABI_VERSION = 1
+
+ACT_NONE, ACT_RELU = 0, 1
+
+
+class MtnError(RuntimeError):
+    pass
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int), ("W", C.c_void_p), ("ldw", C.c_int),
+                ("bias", C.c_void_p), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("act", C.c_int), ("addend", C.c_void_p), ("ld_add", C.c_int),
+                ("add_period", C.c_int), ("out_f32", C.c_void_p), ("ld32", C.c_int),
+                ("out_f16", C.c_void_p), ("ld16", C.c_int)]
+
+
+class AttnCoreArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int),
+                ("v", C.c_void_p), ("ldv", C.c_int), ("mask_bits", C.c_void_p),
+                ("mask_rows_q", C.c_int), ("B", C.c_int), ("h", C.c_int), ("Lq", C.c_int),
+                ("Lk", C.c_int), ("d_k", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int)]
+
+
+class AttnSiteArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("d", C.c_int), ("h", C.c_int),
+                ("x", C.c_void_p), ("x_out", C.c_void_p),
+                ("ln_a", C.c_void_p), ("ln_b", C.c_void_p), ("ln_eps", C.c_float),
+                ("w_q", C.c_void_p), ("b_q", C.c_void_p),
+                ("w_kv", C.c_void_p), ("b_kv", C.c_void_p),
+                ("w_o", C.c_void_p), ("b_o", C.c_void_p),
+                ("mem_f16", C.c_void_p),
+                ("kv", C.c_void_p), ("ld_kv", C.c_int), ("kv_k_col", C.c_int), ("kv_v_col", C.c_int),
+                ("mask_bits", C.c_void_p), ("mask_rows_q", C.c_int),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class FfnArgs(C.Structure):
+    _fields_ = [("rows", C.c_int), ("d", C.c_int), ("d_ff", C.c_int),
+                ("x", C.c_void_p), ("x_out", C.c_void_p),
+                ("ln_a", C.c_void_p), ("ln_b", C.c_void_p), ("ln_eps", C.c_float),
+                ("w_1", C.c_void_p), ("b_1", C.c_void_p), ("w_2", C.c_void_p), ("b_2", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+# every symbol include/mtn_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mtn_abi_version": (C.c_int, []),
+    "mtn_last_error": (C.c_char_p, []),
+    "mtn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_cast_f32_to_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
+    "mtn_mask_words": (C.c_int, [C.c_int]),
+    "mtn_mask_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mtn_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "mtn_attn_core_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
+    "mtn_attn_site_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mtn_attn_site_fwd": (C.c_int, [C.POINTER(AttnSiteArgs), C.c_void_p]),
+    "mtn_ffn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "mtn_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), C.c_void_p]),
+    "mtn_check_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "mtn_check_attn_core_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises MtnError when it has not been built --
+    there is deliberately no Python/PyTorch fallback for the hot path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise MtnError("%s not found: build it with `python -c 'import __graft_entry__ as g; "
+                           "g.build()'` or `make -C mtn_b200/csrc`" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.mtn_abi_version() != ABI_VERSION:
+            raise MtnError("ABI mismatch: library %d, binding %d" % (L.mtn_abi_version(), ABI_VERSION))
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MtnError("mtn_b200 error %d: %s" % (rc, lib().mtn_last_error().decode()))
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise MtnError("%s must be a CUDA tensor (the hot path has no CPU implementation)" % name)
+    if t.dtype != dtype:
+        raise MtnError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.stride(-1) != 1:
+        raise MtnError("%s must have unit stride in its last dimension" % name)
+
+
+# ------------------------------------------------------------------------------
+# thin tensor-level wrappers (used by mtn.py, engine.py and the tests)
+# ------------------------------------------------------------------------------
+def layernorm(x, a_2, b_2, eps, out_f32=None, out_f16=None):
+    """x: [..., d] f32 contiguous.  Writes into out_f32 / out_f16 (same shape)."""
+    _req(x, torch.float32, "x"); _req(a_2, torch.float32, "a_2"); _req(b_2, torch.float32, "b_2")
+    _req(out_f32, torch.float32, "out_f32"); _req(out_f16, torch.float16, "out_f16")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    assert x.is_contiguous() and (out_f32 is None or out_f32.is_contiguous()) and \
+        (out_f16 is None or out_f16.is_contiguous())
+    check(lib().mtn_layernorm_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), rows, d, ptr(out_f32),
+                                  ptr(out_f16), stream_ptr()))
+
+
+def cast_f16(src, dst=None):
+    """2-D (or flattened-to-2-D) f32 -> f16 copy; row strides are honoured."""
+    _req(src, torch.float32, "src")
+    s2 = src.reshape(-1, src.shape[-1]) if src.dim() != 2 else src
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.float16, device=src.device)
+    _req(dst, torch.float16, "dst")
+    d2 = dst.reshape(-1, dst.shape[-1]) if dst.dim() != 2 else dst
+    assert d2.shape == s2.shape
+    check(lib().mtn_cast_f32_to_f16(ptr(s2), s2.stride(0), ptr(d2), d2.stride(0), s2.shape[0],
+                                    s2.shape[1], stream_ptr()))
+    return dst
+
+
+def mask_words(Lk):
+    return lib().mtn_mask_words(int(Lk))
+
+
+def mask_pack(mask):
+    """mask: bool/uint8 [B, rows_q, Lk] (rows_q == 1 for key-padding masks) -> int32 bit words
+    [B, rows_q, words]."""
+    assert mask.dim() == 3 and mask.is_cuda
+    m8 = mask.to(torch.uint8).contiguous()
+    B, R, Lk = m8.shape
+    bits = torch.empty((B, R, mask_words(Lk)), dtype=torch.int32, device=mask.device)
+    check(lib().mtn_mask_pack(ptr(m8), B, R, Lk, ptr(bits), stream_ptr()))
+    return bits
+
+
+def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=None, out_f16=None,
+           _check_kernel=False):
+    """C = act(A W^T + bias) + addend.  A: [M, K] f16 (row stride allowed), W: [N, K] f16."""
+    _req(A, torch.float16, "A"); _req(W, torch.float16, "W"); _req(bias, torch.float32, "bias")
+    _req(addend, torch.float32, "addend"); _req(out_f32, torch.float32, "out_f32")
+    _req(out_f16, torch.float16, "out_f16")
+    assert A.dim() == 2 and W.dim() == 2 and A.shape[1] == W.shape[1]
+    a = LinearArgs()
+    a.A, a.lda, a.W, a.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.M, a.N, a.K, a.act = A.shape[0], W.shape[0], A.shape[1], act
+    if addend is not None:
+        assert addend.dim() == 2
+        a.addend, a.ld_add, a.add_period = addend.data_ptr(), addend.stride(0), int(add_period)
+    if out_f32 is not None:
+        assert out_f32.dim() == 2 and tuple(out_f32.shape) == (a.M, a.N)
+        a.out_f32, a.ld32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_f16 is not None:
+        assert out_f16.dim() == 2 and tuple(out_f16.shape) == (a.M, a.N)
+        a.out_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
+    fn = lib().mtn_check_linear_fwd if _check_kernel else lib().mtn_linear_fwd
+    check(fn(C.byref(a), stream_ptr()))
+
+
+def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False):
+    """q: [B*Lq, >=h*d_k] f16 view (row stride = leading dimension), k/v: [B*Lk, ...];
+    out: [B*Lq, >=h*d_k] f16.  mask_bits: output of mask_pack or None."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.float16, n)
+        assert t.dim() == 2
+    a = AttnCoreArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = (q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+                                         v.data_ptr(), v.stride(0))
+    if mask_bits is not None:
+        assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == B
+        assert mask_bits.shape[2] == mask_words(Lk)
+        a.mask_bits, a.mask_rows_q = mask_bits.data_ptr(), mask_bits.shape[1]
+    a.B, a.h, a.Lq, a.Lk, a.d_k = B, h, Lq, Lk, d_k
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
+    check(fn(C.byref(a), stream_ptr()))

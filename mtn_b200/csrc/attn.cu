@@ -1,0 +1,377 @@
+// Attention core on tcgen05:  O_h = softmax(mask(Q_h K_h^T / sqrt(d_k))) V_h
+//
+// Replaces attention() (mtn.py:221-231) and the head split / concat copies around it
+// (mtn.py:257, 265-266).  One CTA per (128-query tile, head, batch element):
+//   * Q, K, V head slices are fetched straight out of the packed projection buffers
+//     with 3-D TMA tensor maps (columns, sequence, batch) -- no transpose copies;
+//     out-of-range rows are zero-filled by TMA.
+//   * S = Q K^T (128 x 128 keys per tile) and O (128 x d_k) accumulate in tensor
+//     memory; tcgen05.mma is issued by one thread.
+//   * softmax is f32 with one thread per query row (TMEM lane == row): masked
+//     scores become the FINITE -1e9 of mtn.py:227, so a fully masked row yields the
+//     uniform average the reference produces; keys beyond Lk get -inf (weight 0).
+//   * P is rounded to f16, written to shared memory in the UMMA K-major 128B-swizzle
+//     layout and multiplied with V (MN-major operand) by the tensor core; the running
+//     max/sum rescale of O is done in TMEM (online softmax).
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2..5 softmax / epilogue.  K and V use separate single-slot buffers with their
+// own full/empty barriers so the next K tile streams in while softmax / PV run.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mtn {
+
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_QT = 128;  // queries per CTA (UMMA M)
+constexpr int ATT_KT = 128;  // keys per tile (UMMA N of the S MMA)
+
+template <int DK>
+struct AttnCfg {
+  static constexpr int ROWB = DK * 2;  // bytes per smem row of Q/K/V == swizzle span
+  static constexpr int Q_BYTES = ATT_QT * ROWB;
+  static constexpr int KV_BYTES = ATT_KT * ROWB;
+  static constexpr int P_BYTES = ATT_QT * ATT_KT * 2;  // two [128 x 64] f16 panels
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
+  static constexpr uint64_t SWZ = (DK == 64) ? SWZ_128B : SWZ_64B;
+  static constexpr uint32_t SBO = 8 * ROWB;  // 8-row swizzle atom
+  static constexpr uint32_t TMEM_COLS = 256;  // S: [0,128)  O: [128, 128+DK)
+  static constexpr uint32_t O_COL = 128;
+};
+
+struct AttnParams {
+  const uint32_t* mask_bits;
+  int mask_rows_q;
+  int mask_words;
+  int B, h, Lq, Lk;
+  float scale;
+  __half* out;
+  int ldo;
+};
+
+enum {
+  BAR_Q_FULL = 0, BAR_K_FULL, BAR_K_EMPTY, BAR_V_FULL, BAR_V_EMPTY, BAR_S_FULL, BAR_S_FREE,
+  BAR_P_FULL, BAR_PV_DONE, BAR_COUNT
+};
+
+template <int DK>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+    attn_core_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = AttnCfg<DK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sQ = base + C::OFF_Q, sK = base + C::OFF_K, sV = base + C::OFF_V, sP = base + C::OFF_P;
+  const uint32_t bars = base + C::OFF_BAR;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const uint32_t tmem_slot = bars + 8u * BAR_COUNT;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_BAR + 8 * BAR_COUNT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, hd = blockIdx.y, b = blockIdx.z;
+  const int nt = (p.Lk + ATT_KT - 1) / ATT_KT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < BAR_COUNT; ++i)
+      mbar_init(bar(i), (i == BAR_S_FREE || i == BAR_P_FULL) ? 128u : 1u);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + C::O_COL;
+
+  if (warp == 0) {
+    // -------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(BAR_Q_FULL), C::Q_BYTES);
+      tma_load_3d(sQ, &tmQ, bar(BAR_Q_FULL), hd * DK, qt * ATT_QT, b);
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(bar(BAR_K_EMPTY), ph ^ 1);
+        mbar_arrive_expect_tx(bar(BAR_K_FULL), C::KV_BYTES);
+        tma_load_3d(sK, &tmK, bar(BAR_K_FULL), hd * DK, j * ATT_KT, b);
+        mbar_wait(bar(BAR_V_EMPTY), ph ^ 1);
+        mbar_arrive_expect_tx(bar(BAR_V_FULL), C::KV_BYTES);
+        tma_load_3d(sV, &tmV, bar(BAR_V_FULL), hd * DK, j * ATT_KT, b);
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = make_idesc_f16(ATT_QT, ATT_KT, 0, 0);  // S = Q K^T, both K-major
+    constexpr uint32_t idesc_o = make_idesc_f16(ATT_QT, DK, 0, 1);      // O += P V,  V is MN-major
+    mbar_wait(bar(BAR_Q_FULL), 0);
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(bar(BAR_K_FULL), ph);
+      mbar_wait(bar(BAR_S_FREE), ph ^ 1);  // softmax has finished reading S of tile j-1
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dq = make_smem_desc(sQ, 16, C::SBO, C::SWZ);
+        const uint64_t dk = make_smem_desc(sK, 16, C::SBO, C::SWZ);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(bar(BAR_K_EMPTY));
+        tc_commit(bar(BAR_S_FULL));
+      }
+      __syncwarp();
+      mbar_wait(bar(BAR_V_FULL), ph);
+      mbar_wait(bar(BAR_P_FULL), ph);  // P_j is in shared memory, O has been rescaled
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < ATT_KT / 16; ++kk) {
+          // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row
+          const uint64_t dp = make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
+          // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
+          const uint64_t dv = make_smem_desc(sV + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
+          tc_mma_f16(tO, dp, dv, idesc_o, (j | kk) != 0);
+        }
+        tc_commit(bar(BAR_V_EMPTY));
+        tc_commit(bar(BAR_PV_DONE));
+      }
+      __syncwarp();
+    }
+  } else {
+    // -------------------------------------------------------------- softmax + epilogue
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;  // row inside the tile == TMEM lane
+    const int qi = qt * ATT_QT + row;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t* mrow = nullptr;
+    if (p.mask_bits != nullptr) {
+      const int mq = (p.mask_rows_q == 1) ? 0 : min(qi, p.Lq - 1);
+      mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
+    }
+    float m_run = -CUDART_INF_F, l_run = 0.f;
+    const uint32_t sw = (uint32_t)(row & 7);
+
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(bar(BAR_S_FULL), ph);
+      tc_fence_after();
+      // ---- pass 1: row maximum of the masked, scaled scores
+      float m_tile = -CUDART_INF_F;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int k0 = j * ATT_KT + c * 32;
+        const int nvalid = p.Lk - k0;  // keys of this chunk inside the sequence
+        const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + j * 4 + c) : 0xffffffffu;
+        uint32_t r[32];
+        tc_ld32(tS + lane_off + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]) * p.scale;
+          s = ((mw >> i) & 1u) ? s : -1e9f;
+          s = ((inb >> i) & 1u) ? s : -CUDART_INF_F;
+          m_tile = fmaxf(m_tile, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      // P buffer and O accumulator are in use by PV of the previous tile until it retires
+      if (j > 0) {
+        mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
+        tc_fence_after();
+      }
+      // ---- pass 2: p = exp(s - m), row sum, f16 P tile to shared memory
+      float l_tile = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int k0 = j * ATT_KT + c * 32;
+        const int nvalid = p.Lk - k0;
+        const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + j * 4 + c) : 0xffffffffu;
+        uint32_t r[32];
+        tc_ld32(tS + lane_off + c * 32, r);
+        tc_wait_ld();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]) * p.scale;
+          s = ((mw >> i) & 1u) ? s : -1e9f;
+          s = ((inb >> i) & 1u) ? s : -CUDART_INF_F;
+          e[i] = __expf(s - m_new);
+          l_tile += e[i];
+        }
+        const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * 128;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t chunk = (uint32_t)((c & 1) * 4 + t) ^ sw;  // 128B swizzle: 16-B chunk ^= row % 8
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + chunk * 16),
+                       "r"(pack_f16x2_sat(e[8 * t], e[8 * t + 1])), "r"(pack_f16x2_sat(e[8 * t + 2], e[8 * t + 3])),
+                       "r"(pack_f16x2_sat(e[8 * t + 4], e[8 * t + 5])), "r"(pack_f16x2_sat(e[8 * t + 6], e[8 * t + 7]))
+                       : "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(BAR_S_FREE));  // S may be overwritten by the next Q K^T
+      const float alpha = __expf(m_run - m_new);
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      if (j > 0) {
+        // rescale the running O accumulator in tensor memory
+#pragma unroll
+        for (int c = 0; c < DK / 32; ++c) {
+          uint32_t r[32];
+          tc_ld32(tO + lane_off + c * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tc_st32(tO + lane_off + c * 32, r);
+        }
+        tc_wait_st();
+      }
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+      tc_fence_before();
+      mbar_arrive(bar(BAR_P_FULL));
+    }
+    // ---- epilogue: O / l  -> f16, head hd's column slice of the output
+    mbar_wait(bar(BAR_PV_DONE), (nt - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+#pragma unroll
+    for (int c = 0; c < DK / 32; ++c) {
+      uint32_t r[32];
+      tc_ld32(tO + lane_off + c * 32, r);
+      tc_wait_ld();
+      if (qi < p.Lq) {
+        uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qi) * p.ldo + hd * DK + c * 32);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          o[t] = make_uint4(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l),
+                            pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l),
+                            pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l),
+                            pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int DK>
+static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
+  using C = AttnCfg<DK>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tc_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::TOTAL));
+    attr_set = true;
+  }
+  const TmSwizzle swz = DK == 64 ? TM_SWZ_128 : TM_SWZ_64;
+  const uint64_t cols = (uint64_t)a.h * DK;
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_3d_f16(&tq, a.q, cols, a.Lq, a.B, a.ldq, (uint64_t)a.Lq * a.ldq, DK, ATT_QT, swz);
+  if (rc) return rc;
+  rc = make_tmap_3d_f16(&tk, a.k, cols, a.Lk, a.B, a.ldk, (uint64_t)a.Lk * a.ldk, DK, ATT_KT, swz);
+  if (rc) return rc;
+  rc = make_tmap_3d_f16(&tv, a.v, cols, a.Lk, a.B, a.ldv, (uint64_t)a.Lk * a.ldv, DK, ATT_KT, swz);
+  if (rc) return rc;
+  AttnParams p{a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
+               1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo};
+  dim3 grid((a.Lq + ATT_QT - 1) / ATT_QT, a.h, a.B);
+  attn_core_tc_kernel<DK><<<grid, ATT_THREADS, C::TOTAL, st>>>(tq, tk, tv, p);
+  MTN_CHECK_CUDA(cudaGetLastError());
+  return MTN_OK;
+}
+
+static int validate_attn(const MtnAttnCoreArgs* a) {
+  MTN_REQUIRE(a && a->q && a->k && a->v && a->out, MTN_E_ARG, "attn_core: NULL pointer");
+  MTN_REQUIRE(a->B > 0 && a->h > 0 && a->Lq > 0 && a->Lk > 0, MTN_E_SHAPE, "attn_core: B=%d h=%d Lq=%d Lk=%d",
+              a->B, a->h, a->Lq, a->Lk);
+  MTN_REQUIRE(a->d_k == 32 || a->d_k == 64, MTN_E_SHAPE, "attn_core: d_k=%d (supported: 32, 64)", a->d_k);
+  MTN_REQUIRE(a->B <= 65535 && a->h <= 65535, MTN_E_SHAPE, "attn_core: grid too large");
+  const int w = a->h * a->d_k;
+  MTN_REQUIRE(a->ldq >= w && a->ldk >= w && a->ldv >= w && a->ldo >= w, MTN_E_SHAPE,
+              "attn_core: leading dimension smaller than h*d_k=%d", w);
+  MTN_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, MTN_E_ALIGN,
+              "attn_core: leading dimensions must be multiples of 8 elements");
+  MTN_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->out), MTN_E_ALIGN,
+              "attn_core: pointers must be 16-byte aligned");
+  MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,
+              "attn_core: mask_rows_q=%d must be 1 or Lq=%d", a->mask_rows_q, a->Lq);
+  return MTN_OK;
+}
+
+// ----------------------------------------------------------------------------
+// self-check kernel (tests only): one warp per (batch, head, query) row, same
+// arithmetic contract (f16 operands, f32 scores/softmax, P rounded to f16 for PV).
+// ----------------------------------------------------------------------------
+__global__ void attn_core_check_kernel(const __half* q, int ldq, const __half* k, int ldk, const __half* v,
+                                       int ldv, AttnParams p, int dk) {
+  extern __shared__ float sc[];  // Lk scores
+  const int qi = blockIdx.x, hd = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x;
+  const __half* qr = q + ((size_t)b * p.Lq + qi) * ldq + hd * dk;
+  const uint32_t* mrow = nullptr;
+  if (p.mask_bits) mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + (p.mask_rows_q == 1 ? 0 : qi)) * p.mask_words;
+  float mx = -CUDART_INF_F;
+  for (int j = lane; j < p.Lk; j += 32) {
+    const __half* kr = k + ((size_t)b * p.Lk + j) * ldk + hd * dk;
+    float s = 0.f;
+    for (int c = 0; c < dk; ++c) s = fmaf(__half2float(qr[c]), __half2float(kr[c]), s);
+    s *= p.scale;
+    if (mrow && !((mrow[j >> 5] >> (j & 31)) & 1u)) s = -1e9f;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < p.Lk; j += 32) {
+    const float e = __expf(sc[j] - mx);
+    sum += e;
+    sc[j] = __half2float(__float2half_rn(e));
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  for (int c = lane; c < dk; c += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < p.Lk; ++j)
+      acc = fmaf(sc[j], __half2float(v[((size_t)b * p.Lk + j) * ldv + hd * dk + c]), acc);
+    const uint32_t pk = pack_f16x2_sat(acc / sum, 0.f);
+    p.out[((size_t)b * p.Lq + qi) * p.ldo + hd * dk + c] = __ushort_as_half((unsigned short)(pk & 0xffff));
+  }
+}
+
+}  // namespace mtn
+
+extern "C" int mtn_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
+  int rc = mtn::validate_attn(a);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return a->d_k == 64 ? mtn::launch_attn<64>(*a, st) : mtn::launch_attn<32>(*a, st);
+}
+
+extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
+  int rc = mtn::validate_attn(a);
+  if (rc) return rc;
+  mtn::AttnParams p{a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
+                    1.0f / sqrtf((float)a->d_k), reinterpret_cast<__half*>(a->out), a->ldo};
+  dim3 grid(a->Lq, a->h, a->B);
+  mtn::attn_core_check_kernel<<<grid, 32, a->Lk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(a->q), a->ldq, reinterpret_cast<const __half*>(a->k), a->ldk,
+      reinterpret_cast<const __half*>(a->v), a->ldv, p, a->d_k);
+  MTN_CHECK_CUDA(cudaGetLastError());
+  return MTN_OK;
+}

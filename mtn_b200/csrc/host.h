@@ -1,0 +1,42 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and
+// TMA tensor-map construction (driver entry point resolved at run time, so the
+// library has no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mtn_b200.h"
+
+namespace mtn {
+
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+#define MTN_CHECK_CUDA(expr)                                                             \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return ::mtn::set_error(MTN_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define MTN_REQUIRE(cond, code, ...)                               \
+  do {                                                             \
+    if (!(cond)) return ::mtn::set_error(code, __VA_ARGS__);       \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+enum TmSwizzle { TM_SWZ_64 = 64, TM_SWZ_128 = 128 };
+
+// f16 tensor map, rank 2: dims {cols, rows}, row pitch ld (elements), box {box_cols, box_rows}.
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                     uint32_t box_cols, uint32_t box_rows, TmSwizzle swz);
+// rank 3: dims {cols, rows, batch}, strides {ld, rows_stride (elements)}; box {box_cols, box_rows, 1}.
+int make_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
+                     uint64_t ld, uint64_t batch_stride, uint32_t box_cols, uint32_t box_rows,
+                     TmSwizzle swz);
+
+}  // namespace mtn

@@ -1,0 +1,241 @@
+"""GPU tier, kernel level: every CUDA kernel of libmtn_b200.so called through the C ABI
+and compared with (a) the CPU oracle's arithmetic on the same inputs and (b) the
+on-device self-check kernels (same f16-operand arithmetic, so the tolerance is tight
+enough to expose any TMA / UMMA layout mistake).
+
+Tolerances: f16 operands have an 11-bit significand; outputs accumulated in f32.
+  vs check kernel (identical operand rounding): 2e-5 normwise (accumulation order only)
+  vs f32 oracle on f16-rounded operands:        2e-5 normwise (same)
+  f16 outputs add one output rounding:          6e-4 normwise
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+import mtn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DUMP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _dump(name, **arrs):
+    os.makedirs(DUMP, exist_ok=True)
+    np.savez(os.path.join(DUMP, name), **{k: v.detach().float().cpu().numpy() for k, v in arrs.items()})
+
+
+@pytest.fixture(scope="module")
+def L():
+    from mtn_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def dev(t):
+    return t.cuda()
+
+
+# ------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,d", [(1, 4), (7, 128), (33, 512), (5, 1024), (3, 96), (1000, 512)])
+def test_layernorm(L, rows, d):
+    g = torch.Generator().manual_seed(rows * 1000 + d)
+    x = torch.randn(rows, d, generator=g) * 3 + 1
+    a = 1 + 0.1 * torch.randn(d, generator=g)
+    b = 0.1 * torch.randn(d, generator=g)
+    if d == 4:
+        x = torch.tensor([[1., 2., 3., 4.]]); a = torch.ones(4); b = torch.zeros(4)
+    ref = O.layer_norm(x, a, b, 1e-6)
+    y32 = torch.empty(rows, d, device="cuda")
+    y16 = torch.empty(rows, d, device="cuda", dtype=torch.float16)
+    L.layernorm(dev(x), dev(a), dev(b), 1e-6, out_f32=y32, out_f16=y16)
+    torch.cuda.synchronize()
+    assert G.rel_err(y32.cpu(), ref) < 2e-6
+    assert G.rel_err(y16.float().cpu(), ref) < 6e-4
+    if d == 4:   # SURVEY 8c known answer
+        assert np.allclose(y32.cpu().numpy()[0], [-1.1618942, -0.3872980, 0.3872980, 1.1618942], atol=1e-6)
+
+
+def test_cast_and_mask_pack(L):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 72, generator=g) * 100
+    x[0, 0] = 1e6; x[0, 1] = -1e6
+    y = L.cast_f16(dev(x))
+    ref = x.clamp(-65504, 65504).half()
+    assert torch.equal(y.cpu(), ref)
+    x2 = torch.randn(5, 13, generator=g)           # scalar path
+    assert torch.equal(L.cast_f16(dev(x2)).cpu(), x2.half())
+    m = torch.rand(3, 5, 150, generator=g) > 0.4
+    bits = L.mask_pack(dev(m)).cpu()
+    W = L.mask_words(150)
+    assert W == 8 and bits.shape == (3, 5, 8)
+    ref_bits = torch.zeros(3, 5, W * 32, dtype=torch.bool)
+    ref_bits[:, :, :150] = m
+    got = ((bits.unsqueeze(-1) >> torch.arange(32, dtype=torch.int32)) & 1).bool().reshape(3, 5, -1)
+    assert torch.equal(got, ref_bits)
+
+
+# ------------------------------------------------------------------ linear
+LIN_CASES = [
+    # M,   N,    K,    act, addend, period, strided
+    (128, 128, 64, 0, False, 0, False),
+    (128, 64, 64, 0, False, 0, False),
+    (100, 192, 128, 0, False, 0, False),
+    (640, 512, 512, 0, True, 0, False),
+    (2048, 1536, 512, 0, False, 0, False),
+    (300, 2048, 512, 1, False, 0, False),
+    (300, 512, 2048, 0, True, 0, True),
+    (96, 128, 2048, 1, True, 16, False),
+    (1, 128, 128, 0, False, 0, False),
+]
+
+
+@pytest.mark.parametrize("M,N,K,act,add,period,strided", LIN_CASES)
+def test_linear(L, M, N, K, act, add, period, strided):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    lda = K + 64 if strided else K
+    Afull = (torch.randn(M, lda, generator=g)).half()
+    A = Afull[:, :K]
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, generator=g)
+    addend = torch.randn(period if period else M, N, generator=g) if add else None
+    ref = A.float().double() @ W.float().double().t() + bias.double()
+    if act:
+        ref = ref.clamp_min(0)
+    if add:
+        idx = torch.arange(M) % period if period else torch.arange(M)
+        ref = ref + addend[idx].double()
+    ref = ref.float()
+    Ad = dev(Afull)[:, :K]
+    out32 = torch.full((M, N), float("nan"), device="cuda")
+    ld16 = N + 8 if strided else N
+    out16_full = torch.zeros(M, ld16, device="cuda", dtype=torch.float16)
+    out16 = out16_full[:, :N]
+    chk32 = torch.empty(M, N, device="cuda")
+    kw = dict(bias=dev(bias), act=act, addend=dev(addend) if add else None, add_period=period)
+    L.linear(Ad, dev(W), out_f32=chk32, _check_kernel=True, **kw)
+    L.linear(Ad, dev(W), out_f32=out32, out_f16=out16, **kw)
+    torch.cuda.synchronize()
+    e_chk, e_ref = G.rel_err(out32.cpu(), chk32.cpu()), G.rel_err(out32.cpu(), ref)
+    if not (e_chk < 2e-5 and e_ref < 2e-5):
+        _dump("fail_linear_%d_%d_%d.npz" % (M, N, K), out=out32, chk=chk32, ref=ref, A=A, W=W)
+    assert G.rel_err(chk32.cpu(), ref) < 2e-5, "self-check kernel disagrees with the oracle"
+    assert e_chk < 2e-5 and e_ref < 2e-5, (e_chk, e_ref)
+    assert G.rel_err(out16.float().cpu(), ref) < 6e-4
+    if strided:
+        assert float(out16_full[:, N:].abs().sum()) == 0.0      # padding columns untouched
+
+
+def test_linear_pattern(L):
+    """Permutation-revealing inputs: C[m, n] = W[n, m % 64]."""
+    M, N, K = 128, 128, 64
+    A = torch.zeros(M, K); A[torch.arange(M), torch.arange(M) % K] = 1
+    W = (torch.arange(N).float().unsqueeze(1) + torch.arange(K).float().unsqueeze(0) / 128)
+    out = torch.empty(M, N, device="cuda")
+    L.linear(dev(A.half()), dev(W.half()), out_f32=out)
+    torch.cuda.synchronize()
+    ref = W.half().float()[:, torch.arange(M) % K].t()
+    if not torch.equal(out.cpu(), ref):
+        _dump("fail_linear_pattern.npz", out=out, ref=ref)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_linear_inplace_residual(L):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 200, 128, 128
+    A = torch.randn(M, K, generator=g).half(); W = (torch.randn(N, K, generator=g) / 11).half()
+    x = torch.randn(M, N, generator=g)
+    xd = dev(x)
+    L.linear(dev(A), dev(W), addend=xd, out_f32=xd)            # x += A W^T  (mtn.py:127)
+    torch.cuda.synchronize()
+    ref = (x.double() + A.double() @ W.double().t()).float()
+    assert G.rel_err(xd.cpu(), ref) < 2e-5
+
+
+def test_linear_rejects_bad_shapes(L):
+    A = torch.zeros(8, 48, device="cuda", dtype=torch.float16)
+    W = torch.zeros(64, 48, device="cuda", dtype=torch.float16)
+    with pytest.raises(L.MtnError, match="multiple of 64"):
+        L.linear(A, W, out_f32=torch.empty(8, 64, device="cuda"))
+
+
+# ------------------------------------------------------------------ attention core
+def _attn_ref(q, k, v, mask, h, dk):
+    """Oracle arithmetic (mtn.py:221-231 via mtn_oracle.attention) on the f16-rounded operands."""
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    qh = q.float().view(B, Lq, h, dk).transpose(1, 2)
+    kh = k.float().view(B, Lk, h, dk).transpose(1, 2)
+    vh = v.float().view(B, Lk, h, dk).transpose(1, 2)
+    o, _ = O.attention(qh, kh, vh, None if mask is None else mask.unsqueeze(1))
+    return o.transpose(1, 2).contiguous().view(B, Lq, h * dk)
+
+
+ATT_CASES = [
+    # B, h, Lq, Lk, dk, mask kind
+    (1, 1, 128, 128, 64, "none"),
+    (2, 2, 20, 37, 64, "keypad"),
+    (2, 3, 150, 150, 64, "causal"),
+    (2, 8, 64, 512, 64, "keypad"),
+    (1, 2, 256, 300, 64, "none"),
+    (1, 1, 128, 128, 32, "none"),
+    (2, 4, 8, 16, 32, "keypad"),
+    (2, 4, 8, 8, 32, "causal"),
+    (3, 4, 70, 200, 32, "keypad"),
+]
+
+
+@pytest.mark.parametrize("B,h,Lq,Lk,dk,kind", ATT_CASES)
+def test_attn_core(L, B, h, Lq, Lk, dk, kind):
+    g = torch.Generator().manual_seed(B * 1000 + Lq * 10 + Lk + dk)
+    d = h * dk
+    q = (torch.randn(B, Lq, d, generator=g) * 1.5).half()
+    k = (torch.randn(B, Lk, d, generator=g) * 1.5).half()
+    v = torch.randn(B, Lk, d, generator=g).half()
+    mask = None
+    if kind == "keypad":
+        mask = torch.ones(B, 1, Lk, dtype=torch.bool)
+        mask[B - 1, 0, Lk // 2:] = False
+        if B > 1:
+            mask[0, 0, :] = False                     # fully masked -> uniform average (mtn.py:227)
+    elif kind == "causal":
+        mask = O.subsequent_mask(Lq).expand(B, Lq, Lk).clone()
+        mask[B - 1, :, Lk - 3:] = False
+    ref = _attn_ref(q, k, v, mask, h, dk)
+    bits = L.mask_pack(dev(mask)) if mask is not None else None
+    # operands live inside a packed [Q|K|V]-style buffer to exercise leading dimensions
+    qd = torch.zeros(B * Lq, d + 64, device="cuda", dtype=torch.float16); qd[:, :d] = dev(q).view(-1, d)
+    kvd = torch.zeros(B * Lk, 2 * d, device="cuda", dtype=torch.float16)
+    kvd[:, :d] = dev(k).view(-1, d); kvd[:, d:] = dev(v).view(-1, d)
+    out = torch.zeros(B * Lq, d, device="cuda", dtype=torch.float16)
+    chk = torch.zeros(B * Lq, d, device="cuda", dtype=torch.float16)
+    args = (qd[:, :d], kvd[:, :d], kvd[:, d:], B, h, Lq, Lk, dk)
+    L.attn_core(*args, chk, mask_bits=bits, _check_kernel=True)
+    L.attn_core(*args, out, mask_bits=bits)
+    torch.cuda.synchronize()
+    o, c = out.float().cpu().view(B, Lq, d), chk.float().cpu().view(B, Lq, d)
+    e_chk, e_ref = G.rel_err(o, c), G.rel_err(o, ref)
+    if not (e_chk < 1e-3 and e_ref < 1e-3):
+        _dump("fail_attn_%d_%d_%d_%d_%d_%s.npz" % (B, h, Lq, Lk, dk, kind), out=o, chk=c, ref=ref)
+    assert G.rel_err(c, ref) < 1e-3, "self-check kernel disagrees with the oracle"
+    assert e_chk < 1e-3 and e_ref < 1e-3, (e_chk, e_ref)
+    if kind == "keypad" and B > 1:
+        # fully-masked batch element: every query row is the plain mean of V over ALL Lk keys
+        mean_v = v[0].float().view(Lk, h, dk).mean(0).reshape(1, d).expand(Lq, d)
+        assert G.rel_err(o[0], mean_v) < 2e-3
+
+
+def test_attn_kat(L):
+    """SURVEY 8c known answers, embedded in a d_k=32 head (extra dims zero)."""
+    z = G.load("kat.npz")
+    for name in ("allmasked", "lastmasked"):
+        q = torch.zeros(1, 1, 32); k = torch.zeros(1, 3, 32); v = torch.zeros(1, 3, 32)
+        s = 32 ** 0.5 / 2 ** 0.5       # the KAT uses d_k = 2: rescale q so scores match
+        q[0, :, :2] = G.t(z["attn_q"]) * s; k[0, :, :2] = G.t(z["attn_k"]); v[0, :, :2] = G.t(z["attn_v"])
+        mask = G.t(z["attn_%s_mask" % name]).view(1, 1, 3)
+        out = torch.zeros(1, 32, device="cuda", dtype=torch.float16)
+        L.attn_core(dev(q.half()).view(1, 32), dev(k.half()).view(3, 32), dev(v.half()).view(3, 32),
+                    1, 1, 1, 3, 32, out, mask_bits=L.mask_pack(dev(mask)))
+        torch.cuda.synchronize()
+        assert np.allclose(out.float().cpu().numpy()[0, :2], z["attn_%s_o" % name][0], atol=3e-3)
