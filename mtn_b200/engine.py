@@ -1,0 +1,279 @@
+"""Model-level execution of the MTN decoder cascade on the sm_100a kernels.
+
+``DecoderEngine.forward`` is what ``mtn.Decoder.forward`` (reference mtn.py:158-164)
+runs.  It exploits two structural facts of the reference's DecoderLayer
+(mtn.py:181-218) that the reference itself does not:
+
+1. **Static memories.**  his / cap / query / video memories are the same tensors in
+   every layer, so their K and V projections for ALL N layers are one wide GEMM per
+   memory ([B*L, d] x [d, N*2d]) instead of 2N small ones.
+2. **The Query-Aware Auto-Encoder branch never reads the target stream** (SURVEY 8a):
+   ae-self -> ae->video -> ae-FFN of every layer, and the K/V projections of its
+   outputs, depend only on the memories.  They are computed once per memory set
+   ("memory stage") and cached, so repeated ``model.decode`` calls of beam / greedy
+   search (data_utils.py:197-206) only pay for the target path.
+
+The target path per layer is then: LN -> [Q|K|V] GEMM -> core -> out-proj(+residual) for
+self-attention, and LN -> Q GEMM -> core (hoisted K/V) -> out-proj(+residual) for each
+memory, then the fused FFN; the residual stream stays f32, every tensor-core operand
+is f16 (see DESIGN.md "Precision").
+"""
+import torch
+
+from . import _lib
+
+
+def ensure_inference(module, x):
+    """The CUDA path implements the forward (eval) arithmetic.  Fail loudly instead of
+    silently producing tensors that autograd cannot differentiate or that lack dropout."""
+    if not x.is_cuda:
+        raise _lib.MtnError("mtn_b200 hot path needs CUDA tensors (no CPU implementation)")
+    if torch.is_grad_enabled() and (x.requires_grad or
+                                    (module is not None and module.training and
+                                     any(p.requires_grad for p in module.parameters()))):
+        raise NotImplementedError(
+            "mtn_b200: backward / training-mode dropout of the fused path is not implemented in "
+            "this round; call model.eval() and run under torch.no_grad()")
+
+
+class PackedWeights(object):
+    """Cache of tensor-core-ready (f16, concatenated) copies of nn.Parameters, rebuilt
+    when any source parameter is modified in place (``_version``) or re-assigned."""
+
+    def __init__(self):
+        self._key, self._val = None, None
+
+    def get(self, params, build):
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self._key:
+            self._val, self._key = build(), key
+        return self._val
+
+    def __deepcopy__(self, memo):
+        return PackedWeights()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, st):
+        self._key, self._val = None, None
+
+
+class _MemoryKey(object):
+    """Identity of a memory set.  Holds STRONG references to the tensors: while they are
+    alive the caching allocator cannot hand their storage to a different tensor, so
+    ``is`` + ``_version`` equality really means "same contents" (data_ptr alone would
+    alias across training-loop iterations)."""
+
+    def __init__(self, wkey, ae_features, tensors):
+        self.wkey, self.ae_features = wkey, ae_features
+        self.tensors = list(tensors)
+        self.versions = [None if t is None else t._version for t in self.tensors]
+
+    def matches(self, other):
+        return (other is not None and self.wkey == other.wkey and self.ae_features == other.ae_features
+                and len(self.tensors) == len(other.tensors)
+                and all(a is b for a, b in zip(self.tensors, other.tensors))
+                and self.versions == other.versions)
+
+
+class DecoderEngine(object):
+    def __init__(self, decoder):
+        self.dec = decoder
+        self._packed = PackedWeights()
+        self._mem_key, self._mem = None, None
+
+    # ------------------------------------------------------------------ weights
+    def weights(self):
+        dec = self.dec
+        params = list(dec.parameters())
+
+        def build():
+            f16 = lambda w: _lib.cast_f16(w.contiguous())
+            layers = dec.layers
+            M = len(layers[0].auto_encoder_vid_attn)
+            d = layers[0].size
+
+            def att(m):      # full per-site pack
+                w = [l.weight.data for l in m.linears]
+                b = [l.bias.data for l in m.linears]
+                return {"w_qkv": f16(torch.cat(w[:3], 0)), "b_qkv": torch.cat(b[:3], 0).contiguous(),
+                        "w_o": f16(w[3]), "b_o": b[3].contiguous(), "h": m.h, "d_k": m.d_k}
+
+            def hoist(mods):  # [N*2d, d]: layer l -> rows [l*2d, l*2d+d) = Wk_l, next d = Wv_l
+                w = torch.cat([torch.cat([m.linears[1].weight.data, m.linears[2].weight.data], 0)
+                               for m in mods], 0)
+                b = torch.cat([torch.cat([m.linears[1].bias.data, m.linears[2].bias.data], 0)
+                               for m in mods], 0)
+                return f16(w), b.contiguous()
+
+            def ffn(m):
+                return {"w_1": f16(m.w_1.weight.data), "b_1": m.w_1.bias.data.contiguous(),
+                        "w_2": f16(m.w_2.weight.data), "b_2": m.w_2.bias.data.contiguous()}
+
+            def ln(m):
+                return (m.a_2.data, m.b_2.data, m.eps)
+
+            W = {"M": M, "d": d, "N": len(layers), "layers": []}
+            W["kv_his"] = hoist([l.his_attn for l in layers])
+            W["kv_cap"] = hoist([l.cap_attn for l in layers])
+            W["kv_q"] = hoist([l.src_attn for l in layers])
+            W["kv_vid"] = [hoist([l.auto_encoder_vid_attn[i] for l in layers]) for i in range(M)]
+            for l in layers:
+                W["layers"].append({
+                    "self": att(l.self_attn), "his": att(l.his_attn), "cap": att(l.cap_attn),
+                    "src": att(l.src_attn),
+                    "ae_self": [att(m) for m in l.auto_encoder_self_attn],
+                    "ae_vid": [att(m) for m in l.auto_encoder_vid_attn],
+                    "ae_attn": [att(m) for m in l.auto_encoder_attn],
+                    "ae_ffn": [ffn(m) for m in l.auto_encoder_feed_forward],
+                    "ffn": ffn(l.feed_forward),
+                    "ln": [ln(s.norm) for s in l.sublayer],
+                })
+            W["norm"] = ln(dec.norm)
+            W["ae_norm"] = [ln(m) for m in dec.ae_norm]
+            return W
+
+        return self._packed.get(params, build)
+
+    # ------------------------------------------------------------------ building blocks
+    @staticmethod
+    def _attn_block(x, ln, A, B, Lq, Lk, q_w, q_b, kv, k_col, v_col, bits, xn16, qbuf, obuf):
+        """One pre-norm residual attention site, in place on the f32 stream ``x`` [B*Lq, d].
+        kv=None -> self-attention (q_w is the [3d, d] pack, K/V come out of the same GEMM)."""
+        d = x.shape[1]
+        _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
+        _lib.linear(xn16, q_w, q_b, out_f16=qbuf)
+        if kv is None:
+            q, k, v = qbuf[:, :d], qbuf[:, d:2 * d], qbuf[:, 2 * d:]
+        else:
+            q, k, v = qbuf, kv[:, k_col:k_col + d], kv[:, v_col:v_col + d]
+        _lib.attn_core(q, k, v, B, A["h"], Lq, Lk, A["d_k"], obuf, mask_bits=bits)
+        _lib.linear(obuf, A["w_o"], A["b_o"], addend=x, out_f32=x)
+
+    @staticmethod
+    def _ffn_block(x, ln, Fw, xn16, hid, out16=None):
+        _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
+        _lib.linear(xn16, Fw["w_1"], Fw["b_1"], act=_lib.ACT_RELU, out_f16=hid)
+        _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x, out_f32=x, out_f16=out16)
+
+    # ------------------------------------------------------------------ memory stage
+    def _memory_stage(self, W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask, ae_ft, ae_features):
+        dev = qm.device
+        d, N, M = W["d"], W["N"], W["M"]
+        B = qm.shape[0]
+        f16 = torch.float16
+
+        def hoisted(mem, wb):
+            m16 = _lib.cast_f16(mem.contiguous().view(-1, d))
+            out = torch.empty(m16.shape[0], N * 2 * d, dtype=f16, device=dev)
+            _lib.linear(m16, wb[0], wb[1], out_f16=out)
+            return out
+
+        def bits(mask, L):
+            if mask is None:
+                return None
+            if mask.shape[0] != B:
+                mask = mask.expand(B, -1, -1)
+            return _lib.mask_pack(mask)
+
+        S = {"H": his.shape[1], "C": cap.shape[1], "Q": qm.shape[1]}
+        S["kv_his"], S["kv_cap"], S["kv_q"] = hoisted(his, W["kv_his"]), hoisted(cap, W["kv_cap"]), hoisted(qm, W["kv_q"])
+        S["bits_his"], S["bits_cap"], S["bits_q"] = bits(his_mask, S["H"]), bits(cap_mask, S["C"]), bits(q_mask, S["Q"])
+        if ae_features in ("caption", "summary"):
+            ae_default, ae_bits = cap, S["bits_cap"]
+        elif ae_features == "query":
+            ae_default, ae_bits = qm, S["bits_q"]
+        else:
+            raise ValueError("auto_encoder_ft must be 'query', 'caption' or 'summary' "
+                             "(reference mtn.py:187-202 leaves ae_mask unbound otherwise)")
+        S["bits_ae"] = ae_bits
+        La = ae_default.shape[1]
+        S["La"] = La
+        rows = B * La
+        xn16 = torch.empty(rows, d, dtype=f16, device=dev)
+        qkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
+        obuf = torch.empty(rows, d, dtype=f16, device=dev)
+        dff = W["layers"][0]["ffn"]["w_1"].shape[0]
+        hid = torch.empty(rows, dff, dtype=f16, device=dev)
+        S["kv_ae"] = [[None] * M for _ in range(N)]
+        S["ae_out"] = []
+        for i in range(M):
+            Lv = vid_ft[i].shape[1]
+            kv_vid = hoisted(vid_ft[i], W["kv_vid"][i])
+            bits_vid = bits(vid_mask[i], Lv)
+            src = ae_ft[i] if isinstance(ae_ft, (list, tuple)) else (ae_ft if ae_ft is not None else ae_default)
+            ae = src.contiguous().view(rows, d).clone()          # f32 residual stream of the QAE branch
+            ae16 = torch.empty(rows, d, dtype=f16, device=dev)
+            for l in range(N):
+                Lw = W["layers"][l]
+                c0 = 4 + 4 * i
+                self._attn_block(ae, Lw["ln"][c0], Lw["ae_self"][i], B, La, La, Lw["ae_self"][i]["w_qkv"],
+                                 Lw["ae_self"][i]["b_qkv"], None, 0, 0, ae_bits, xn16, qkv, obuf)
+                A = Lw["ae_vid"][i]
+                self._attn_block(ae, Lw["ln"][c0 + 1], A, B, La, Lv, A["w_qkv"][:d], A["b_qkv"][:d], kv_vid,
+                                 l * 2 * d, l * 2 * d + d, bits_vid, xn16, qkv[:, :d], obuf)
+                self._ffn_block(ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], xn16, hid, out16=ae16)
+                # K/V of this layer's ae_i for the target stream's auto_encoder_attn[i] (mtn.py:215):
+                # the memory is the un-normed ae_i itself
+                A2 = Lw["ae_attn"][i]
+                kv = torch.empty(rows, 2 * d, dtype=f16, device=dev)
+                _lib.linear(ae16, A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=kv)
+                S["kv_ae"][l][i] = kv
+            out = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            nrm = W["ae_norm"][i]
+            _lib.layernorm(ae, nrm[0], nrm[1], nrm[2], out_f32=out)          # mtn.py:162-163
+            S["ae_out"].append(out.view(B, La, d))
+        return S
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, vid_ft, vid_mask, x, his, his_mask, cap, cap_mask, qm, q_mask, tgt_mask, ae_ft,
+                ae_features):
+        W = self.weights()
+        d, N, M = W["d"], W["N"], W["M"]
+        B, T, _ = x.shape
+        dev = x.device
+        key = _MemoryKey(self._packed._key, ae_features,
+                         list(vid_ft) + list(vid_mask) + [his, his_mask, cap, cap_mask, qm, q_mask] +
+                         (list(ae_ft) if isinstance(ae_ft, (list, tuple)) else [ae_ft]))
+        if not key.matches(self._mem_key):
+            self._mem = self._memory_stage(W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask,
+                                           ae_ft, ae_features)
+            self._mem_key = key
+        S = self._mem
+
+        rows = B * T
+        f16 = torch.float16
+        xs = x.contiguous().view(rows, d).clone()               # f32 residual stream (never aliases the input)
+        xn16 = torch.empty(rows, d, dtype=f16, device=dev)
+        qkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
+        obuf = torch.empty(rows, d, dtype=f16, device=dev)
+        dff = W["layers"][0]["ffn"]["w_1"].shape[0]
+        hid = torch.empty(rows, dff, dtype=f16, device=dev)
+        tm = tgt_mask
+        if tm is not None and tm.shape[0] != B:
+            tm = tm.expand(B, -1, -1)
+        bits_t = _lib.mask_pack(tm) if tm is not None else None
+        order = (("src", "kv_q", "bits_q", "Q"), ("cap", "kv_cap", "bits_cap", "C")) \
+            if ae_features in ("caption", "summary") else \
+            (("cap", "kv_cap", "bits_cap", "C"), ("src", "kv_q", "bits_q", "Q"))
+        for l in range(N):
+            Lw = W["layers"][l]
+            A = Lw["self"]
+            self._attn_block(xs, Lw["ln"][0], A, B, T, T, A["w_qkv"], A["b_qkv"], None, 0, 0, bits_t, xn16, qkv, obuf)
+            kc, vc = l * 2 * d, l * 2 * d + d
+            A = Lw["his"]
+            self._attn_block(xs, Lw["ln"][1], A, B, T, S["H"], A["w_qkv"][:d], A["b_qkv"][:d], S["kv_his"], kc, vc,
+                             S["bits_his"], xn16, qkv[:, :d], obuf)
+            for c, (name, kvn, bn, Ln) in enumerate(order):
+                A = Lw[name]
+                self._attn_block(xs, Lw["ln"][2 + c], A, B, T, S[Ln], A["w_qkv"][:d], A["b_qkv"][:d], S[kvn], kc, vc,
+                                 S[bn], xn16, qkv[:, :d], obuf)
+            for i in range(M):
+                A = Lw["ae_attn"][i]
+                self._attn_block(xs, Lw["ln"][7 + 4 * i], A, B, T, S["La"], A["w_qkv"][:d], A["b_qkv"][:d],
+                                 S["kv_ae"][l][i], 0, d, S["bits_ae"], xn16, qkv[:, :d], obuf)
+            self._ffn_block(xs, Lw["ln"][4 + 4 * M], Lw["ffn"], xn16, hid)
+        out = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=out)   # mtn.py:164
+        return out.view(B, T, d), list(S["ae_out"])
