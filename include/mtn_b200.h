@@ -81,7 +81,8 @@ int mtn_mask_pack(const uint8_t *mask_u8, int B, int rows_q, int Lk, uint32_t *b
  *         (mtn.py:127; add_period = 0 means row m) or the positional-encoding
  *         table (mtn.py:308; add_period = sequence length).  May alias out_f32.
  * Outputs: out_f32 [M, ld32] and/or out_f16 [M, ld16]; either may be NULL.
- * Constraints: K % 64 == 0, N % 64 == 0, 16-byte aligned rows.
+ * Constraints: K % 8 == 0, N % 8 == 0 (16-byte aligned rows); tails are zero-filled
+ * by TMA (K) / predicated in the epilogue (M, N).
  * tcgen05 (UMMA 128xBNx16, f16 in / f32 accumulate in TMEM), TMA-staged operands. */
 enum { MTN_ACT_NONE = 0, MTN_ACT_RELU = 1 };
 typedef struct MtnLinearArgs {

@@ -102,6 +102,24 @@ def check(rc):
         raise MtnError("mtn_b200 error %d: %s" % (rc, lib().mtn_last_error().decode()))
 
 
+# ------------------------------------------------------------------------------
+# optional per-launch trace (bench.py roofline leg): when TRACE is a list every kernel
+# wrapper appends {name, flops, bytes, start, end} with CUDA events around the launch.
+# ------------------------------------------------------------------------------
+TRACE = None
+
+
+def _launch(name, flops, nbytes, fn):
+    if TRACE is None:
+        return check(fn())
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn()
+    e.record()
+    TRACE.append({"name": name, "flops": flops, "bytes": nbytes, "start": s, "end": e})
+    check(rc)
+
+
 def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -132,8 +150,10 @@ def layernorm(x, a_2, b_2, eps, out_f32=None, out_f16=None):
     rows = x.numel() // d
     assert x.is_contiguous() and (out_f32 is None or out_f32.is_contiguous()) and \
         (out_f16 is None or out_f16.is_contiguous())
-    check(lib().mtn_layernorm_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), rows, d, ptr(out_f32),
-                                  ptr(out_f16), stream_ptr()))
+    nbytes = rows * d * (4 + (4 if out_f32 is not None else 0) + (2 if out_f16 is not None else 0))
+    _launch("layernorm", 0, nbytes,
+            lambda: lib().mtn_layernorm_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), rows, d, ptr(out_f32),
+                                            ptr(out_f16), stream_ptr()))
 
 
 def cast_f16(src, dst=None):
@@ -145,8 +165,9 @@ def cast_f16(src, dst=None):
     _req(dst, torch.float16, "dst")
     d2 = dst.reshape(-1, dst.shape[-1]) if dst.dim() != 2 else dst
     assert d2.shape == s2.shape
-    check(lib().mtn_cast_f32_to_f16(ptr(s2), s2.stride(0), ptr(d2), d2.stride(0), s2.shape[0],
-                                    s2.shape[1], stream_ptr()))
+    _launch("cast_f16", 0, s2.numel() * 6,
+            lambda: lib().mtn_cast_f32_to_f16(ptr(s2), s2.stride(0), ptr(d2), d2.stride(0), s2.shape[0],
+                                              s2.shape[1], stream_ptr()))
     return dst
 
 
@@ -161,7 +182,8 @@ def mask_pack(mask):
     m8 = mask.to(torch.uint8).contiguous()
     B, R, Lk = m8.shape
     bits = torch.empty((B, R, mask_words(Lk)), dtype=torch.int32, device=mask.device)
-    check(lib().mtn_mask_pack(ptr(m8), B, R, Lk, ptr(bits), stream_ptr()))
+    _launch("mask_pack", 0, m8.numel() + bits.numel() * 4,
+            lambda: lib().mtn_mask_pack(ptr(m8), B, R, Lk, ptr(bits), stream_ptr()))
     return bits
 
 
@@ -186,7 +208,10 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
         assert out_f16.dim() == 2 and tuple(out_f16.shape) == (a.M, a.N)
         a.out_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
     fn = lib().mtn_check_linear_fwd if _check_kernel else lib().mtn_linear_fwd
-    check(fn(C.byref(a), stream_ptr()))
+    nbytes = 2 * (a.M * a.K + a.N * a.K) + a.M * a.N * ((4 if out_f32 is not None else 0) +
+                                                        (2 if out_f16 is not None else 0) +
+                                                        (4 if addend is not None else 0))
+    _launch("linear", 2 * a.M * a.N * a.K, nbytes, lambda: fn(C.byref(a), stream_ptr()))
 
 
 def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False):
@@ -205,4 +230,5 @@ def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=Fal
     a.B, a.h, a.Lq, a.Lk, a.d_k = B, h, Lq, Lk, d_k
     a.out, a.ldo = out.data_ptr(), out.stride(0)
     fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
-    check(fn(C.byref(a), stream_ptr()))
+    _launch("attn_core", 4 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (2 * Lq + 2 * Lk),
+            lambda: fn(C.byref(a), stream_ptr()))

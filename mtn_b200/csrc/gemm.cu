@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(GEMM_THREADS)
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
-  const int nkb = K / BK;
+  const int nkb = (K + BK - 1) / BK;  // K tail: TMA zero-fills columns >= K
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -127,14 +127,16 @@ __global__ void __launch_bounds__(GEMM_THREADS)
       uint32_t r[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
       tc_wait_ld();
-      if (row_ok) {
-        const int col = n0 + c * 32;
+      const int col = n0 + c * 32;
+      const int nv = N - col;  // valid columns of this chunk (multiple of 8); >= 32 except in the N tail
+      if (row_ok && nv > 0) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (epi.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
+            if (j >= nv) break;
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col + j));
             v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(GEMM_THREADS)
         if (add_row != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
+            if (j >= nv) break;
             const float4 a4 = *reinterpret_cast<const float4*>(add_row + col + j);
             v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
           }
@@ -153,13 +156,14 @@ __global__ void __launch_bounds__(GEMM_THREADS)
         if (epi.out32 != nullptr) {
           float4* o = reinterpret_cast<float4*>(epi.out32 + (size_t)row * epi.ld32 + col);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nv) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (epi.out16 != nullptr) {
           uint4* o = reinterpret_cast<uint4*>(epi.out16 + (size_t)row * epi.ld16 + col);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pack_f16x2_sat(v[8 * j], v[8 * j + 1]), pack_f16x2_sat(v[8 * j + 2], v[8 * j + 3]),
+            if (8 * j < nv) o[j] = make_uint4(pack_f16x2_sat(v[8 * j], v[8 * j + 1]), pack_f16x2_sat(v[8 * j + 2], v[8 * j + 3]),
                               pack_f16x2_sat(v[8 * j + 4], v[8 * j + 5]), pack_f16x2_sat(v[8 * j + 6], v[8 * j + 7]));
         }
       }
@@ -189,7 +193,7 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
               reinterpret_cast<__half*>(a.out_f16), a.ld16};
-  dim3 grid(a.N / BN, (a.M + BM - 1) / BM);
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
   gemm_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, epi, a.M, a.N, a.K);
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;
@@ -198,8 +202,8 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
 static int validate_linear(const MtnLinearArgs* a) {
   MTN_REQUIRE(a != nullptr && a->A != nullptr && a->W != nullptr, MTN_E_ARG, "linear: NULL operand");
   MTN_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, MTN_E_SHAPE, "linear: M=%d N=%d K=%d", a->M, a->N, a->K);
-  MTN_REQUIRE(a->K % 64 == 0, MTN_E_SHAPE, "linear: K=%d must be a multiple of 64", a->K);
-  MTN_REQUIRE(a->N % 64 == 0, MTN_E_SHAPE, "linear: N=%d must be a multiple of 64", a->N);
+  MTN_REQUIRE(a->K % 8 == 0, MTN_E_SHAPE, "linear: K=%d must be a multiple of 8", a->K);
+  MTN_REQUIRE(a->N % 8 == 0, MTN_E_SHAPE, "linear: N=%d must be a multiple of 8", a->N);
   MTN_REQUIRE(a->lda >= a->K && a->ldw >= a->K && a->lda % 8 == 0 && a->ldw % 8 == 0, MTN_E_ALIGN,
               "linear: lda=%d ldw=%d must be >= K and multiples of 8", a->lda, a->ldw);
   MTN_REQUIRE(aligned16(a->A) && aligned16(a->W), MTN_E_ALIGN, "linear: A/W not 16-byte aligned");
@@ -246,7 +250,7 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
   int rc = mtn::validate_linear(a);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->N % 128 == 0) return mtn::launch_gemm<128, 3>(*a, st);
+  if (a->N > 64) return mtn::launch_gemm<128, 3>(*a, st);
   return mtn::launch_gemm<64, 4>(*a, st);
 }
 

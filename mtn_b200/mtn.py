@@ -407,9 +407,6 @@ class VideoEncoder(nn.Sequential):
         ensure_inference(self, ft)
         lin, pos = self[0], self[2]
         B, Lv, Fdim = ft.shape
-        if Fdim % 64 != 0 or lin.out_features % 64 != 0:
-            raise _lib.MtnError("video feature size %d / d_model %d must be multiples of 64" %
-                                (Fdim, lin.out_features))
         W = self._packed.get(list(lin.parameters()),
                              lambda: {"w": _lib.cast_f16(lin.weight.data.contiguous()), "b": lin.bias.data})
         x16 = _lib.cast_f16(ft.contiguous().float().view(B * Lv, Fdim))

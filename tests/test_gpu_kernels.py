@@ -88,6 +88,10 @@ LIN_CASES = [
     (300, 512, 2048, 0, True, 0, True),
     (96, 128, 2048, 1, True, 16, False),
     (1, 128, 128, 0, False, 0, False),
+    (70, 128, 32, 0, False, 0, False),      # K tail (K < 64): TMA zero fill
+    (70, 200, 136, 1, True, 0, False),      # N and K tails
+    (33, 3000, 512, 0, False, 0, False),    # vocabulary-sized N (generator, mtn.py:66)
+    (50, 40, 72, 0, False, 0, False),
 ]
 
 
@@ -154,9 +158,9 @@ def test_linear_inplace_residual(L):
 
 
 def test_linear_rejects_bad_shapes(L):
-    A = torch.zeros(8, 48, device="cuda", dtype=torch.float16)
-    W = torch.zeros(64, 48, device="cuda", dtype=torch.float16)
-    with pytest.raises(L.MtnError, match="multiple of 64"):
+    A = torch.zeros(8, 44, device="cuda", dtype=torch.float16)[:, :36]
+    W = torch.zeros(64, 44, device="cuda", dtype=torch.float16)[:, :36]
+    with pytest.raises(L.MtnError, match="multiple of 8"):
         L.linear(A, W, out_f32=torch.empty(8, 64, device="cuda"))
 
 
