@@ -11,9 +11,11 @@ import numpy as np
 import torch
 
 
-def subsequent_mask(size):
-    "Mask out subsequent positions: (1, size, size) bool, True on/below the diagonal."
-    return torch.tril(torch.ones(1, size, size, dtype=torch.bool))
+def subsequent_mask(size, device=None):
+    """Mask out subsequent positions: (1, size, size) bool, True on/below the diagonal.
+    ``device`` (an extension of the reference signature) builds it in place on the GPU so
+    that Batch construction is CUDA-graph capturable (no host->device copy)."""
+    return torch.tril(torch.ones(1, size, size, dtype=torch.bool, device=device))
 
 
 def _default_device(t):
@@ -59,7 +61,7 @@ class Batch:
     @staticmethod
     def make_std_mask(tgt, pad):
         "Hide padding and future words: (B, T, T)."
-        return (tgt != pad).unsqueeze(-2) & subsequent_mask(tgt.size(-1)).to(tgt.device)
+        return (tgt != pad).unsqueeze(-2) & subsequent_mask(tgt.size(-1), tgt.device)
 
 
 def encode(model, his, his_st, his_mask, cap, cap_mask, query, query_mask, video_features,
@@ -85,7 +87,7 @@ def greedy_decode(model, batch, max_len, start_symbol, pad_symbol=None):
     for _ in range(max_len - 1):
         out = model.decode(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask,
                            batch.cap_mask, batch.query_mask, ys,
-                           subsequent_mask(ys.size(1)).to(ys.device), ae_ft)
+                           subsequent_mask(ys.size(1), ys.device), ae_ft)
         prob = model.generator(out[0][:, -1])
         ys = torch.cat([ys, prob.argmax(dim=1, keepdim=True)], dim=1)
     return ys
@@ -108,7 +110,7 @@ def beam_search_decode(model, batch, max_len, start_symbol, unk_symbol, end_symb
         for out, lp, st in hyplist:
             output = model.decode(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask,
                                   batch.cap_mask, batch.query_mask, st,
-                                  subsequent_mask(st.size(1)).to(st.device), ae_ft)
+                                  subsequent_mask(st.size(1), st.device), ae_ft)
             logp = model.generator(output[0][:, -1])
             lp_vec = np.squeeze(logp.cpu().data.numpy() + lp)
             if l >= min_len:
