@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs the GPU test tiers in separate processes (a trapped kernel poisons its CUDA
 # context; isolation keeps the other tiers' results) with per-tier timeouts.
-# Usage (on the GPU box, via gpurun):  bash tools_gpu_check.sh [pytest -k expr]
+# Usage (on the GPU box, via gpurun):  bash tools/gpu_check.sh [pytest -k expr]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 run() { # name, timeout, args...
