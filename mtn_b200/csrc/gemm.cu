@@ -3,11 +3,11 @@
 // Replaces the nn.Linear call sites of the MTN hot path (mtn.py:256-258 Q/K/V
 // projections, :267 output projection, :280 FFN w_1/w_2, :35 video encoder).
 // A [M,K] and W [N,K] are both K-major f16, so the GEMM is the "TN" form UMMA
-// consumes directly: 128 x BN x 64 tiles are staged by TMA (128-byte swizzle) into
-// a STAGES-deep shared-memory ring, one elected thread issues 128xBNx16
-// tcgen05.mma (f32 accumulate in tensor memory) and four epilogue warps read the
-// accumulator back with tcgen05.ld (one thread per output row) and apply bias /
-// ReLU / residual-or-positional addend before storing f32 and/or f16.
+// consumes directly: 128 x BN x 64 tiles (BN = 256 or 128) are staged by TMA (128-byte
+// swizzle) into a STAGES-deep shared-memory ring, one elected thread issues 128xBNx16
+// tcgen05.mma (f32 accumulate in one of TWO tensor-memory buffers) and four epilogue
+// warps drain the other buffer with tcgen05.ld, apply bias / ReLU / residual-or-positional
+// addend and store f32 and/or f16 with line-coalesced accesses.  CTAs are persistent.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
@@ -31,48 +31,58 @@ struct GemmEpi {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 f16 = 128 B = one swizzle-128B row
 constexpr int GEMM_THREADS = 192;
+constexpr int STAGE_TILE_BYTES = 32 * 32 * 4;  // per-epilogue-warp 32x32 f32 transpose buffer
 
 template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;  // barriers + 1 KB alignment slack
+  static constexpr int XPOSE_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = XPOSE_OFF + 4 * STAGE_TILE_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 4;
+  static constexpr int TOTAL = BAR_OFF + 8 * NBARS + 16 + 1024;  // + tmem slot + 1 KB alignment slack
 };
 
+// Persistent kernel: each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so
+// the CTAs running at the same time share the same A row panels and the whole of W in L2).  The TMA
+// ring and the two TMEM accumulator buffers run across tile boundaries: while the epilogue warps drain
+// accumulator i the tensor core is already filling accumulator i+1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmEpi epi, int M, int N, int K) {
+                       const GemmEpi epi, int M, int N, int K, int tiles_n, int num_tiles) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t bar_base = base + L::BAR_OFF;
-  const uint32_t bar_tmem_full = bar_base + 8 * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8 * (2 * STAGES + 1);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * (2 * STAGES + 1));
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto bar_acc_full = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto bar_acc_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * L::NBARS;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * L::NBARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
   const int nkb = (K + BK - 1) / BK;  // K tail: TMA zero-fills columns >= K
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_base + 8 * s, 1);             // full[s]:  producer arrive + tx bytes
-      mbar_init(bar_base + 8 * (STAGES + s), 1);  // empty[s]: tcgen05.commit
+      mbar_init(bar_full(s), 1);   // producer arrive + tx bytes
+      mbar_init(bar_empty(s), 1);  // tcgen05.commit
     }
-    mbar_init(bar_tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);   // tcgen05.commit after the last k-block of a tile
+      mbar_init(bar_acc_empty(b), 4);  // one arrive per epilogue warp
+    }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -81,91 +91,114 @@ __global__ void __launch_bounds__(GEMM_THREADS)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1);
-        const uint32_t full = bar_base + 8 * s;
-        mbar_arrive_expect_tx(full, L::STAGE_BYTES);
-        const uint32_t sA = base + s * L::STAGE_BYTES;
-        tma_load_2d(sA, &tmA, full, kb * BK, m0);
-        tma_load_2d(sA + L::A_BYTES, &tmB, full, kb * BK, n0);
+      uint32_t it = 0;  // k-blocks issued so far (ring position across tiles)
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_empty(s), ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full(s), L::STAGE_BYTES);
+          const uint32_t sA = base + s * L::STAGE_BYTES;
+          tma_load_2d(sA, &tmA, bar_full(s), kb * BK, m0);
+          tma_load_2d(sA + L::A_BYTES, &tmB, bar_full(s), kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(bar_base + 8 * s, ph);
+    uint32_t it = 0, lt = 0;  // ring position, local tile counter
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1;
+      mbar_wait(bar_acc_empty(buf), ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sA = base + s * L::STAGE_BYTES;
-        const uint64_t da = make_smem_desc(sA, 16, 1024, SWZ_128B);
-        const uint64_t db = make_smem_desc(sA + L::A_BYTES, 16, 1024, SWZ_128B);
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(bar_full(s), (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = base + s * L::STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sA, 16, 1024, SWZ_128B);
+          const uint64_t db = make_smem_desc(sA + L::A_BYTES, 16, 1024, SWZ_128B);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the swizzled row = +2 encoded
-          tc_mma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-        tc_commit(bar_base + 8 * (STAGES + s));  // frees the stage when these MMAs retire
-        if (kb == nkb - 1) tc_commit(bar_tmem_full);
+          for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the swizzled row = +2 encoded
+            tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(bar_empty(s));  // frees the stage when these MMAs retire
+          if (kb == nkb - 1) tc_commit(bar_acc_full(buf));
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue
+    // TMEM gives each thread one accumulator ROW (32 columns per load).  Each warp transposes its
+    // 32x32 block through a private XOR-swizzled shared-memory tile so that global traffic is
+    // line-coalesced: 8 lanes cover 128 contiguous bytes of one row, a warp covers 4 rows.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(bar_tmem_full, 0);
-    tc_fence_after();
-    const bool row_ok = row < M;
-    const float* add_row = nullptr;
-    if (epi.addend != nullptr && row_ok)
-      add_row = epi.addend + (size_t)(epi.add_period > 0 ? row % epi.add_period : row) * epi.ld_add;
+    float4* xp = reinterpret_cast<float4*>(smem + L::XPOSE_OFF + q * STAGE_TILE_BYTES);
+    const int sub_r = lane >> 3, c4 = lane & 7;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      const uint32_t buf = lt & 1;
+      const int row0 = m0 + q * 32;
+      mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
-      tc_wait_ld();
-      const int col = n0 + c * 32;
-      const int nv = N - col;  // valid columns of this chunk (multiple of 8); >= 32 except in the N tail
-      if (row_ok && nv > 0) {
-        float v[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = n0 + c * 32 + c4 * 4;  // this lane's 4 columns in the coalesced phase
+        const bool col_ok = col < N;
+        float4 res[8];
+        if (epi.addend != nullptr) {  // issue the residual / positional loads before touching TMEM
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (epi.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j >= nv) break;
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          for (int i = 0; i < 8; ++i) {
+            const int r = row0 + i * 4 + sub_r;
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < M && col_ok)
+              res[i] = *reinterpret_cast<const float4*>(
+                  epi.addend + (size_t)(epi.add_period > 0 ? r % epi.add_period : r) * epi.ld_add + col);
           }
         }
-        if (epi.act == MTN_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        uint32_t acc[32];
+        tc_ld32(t_acc + c * 32, acc);
+        tc_wait_ld();
+        if (c == BN / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty(buf));
         }
-        if (add_row != nullptr) {
+        // bias + activation in the row-per-thread layout (bias address is warp-uniform -> broadcast)
+        const int cb = n0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j >= nv) break;
-            const float4 a4 = *reinterpret_cast<const float4*>(add_row + col + j);
-            v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+        for (int j = 0; j < 8; ++j) {
+          float4 v = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                 __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+          if (epi.bias != nullptr && cb + 4 * j < N) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4 * j));
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          }
+          if (epi.act == MTN_ACT_RELU) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+          xp[lane * 8 + (j ^ (lane & 7))] = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + sub_r;
+          const int r = row0 + rl;
+          float4 v = xp[rl * 8 + (c4 ^ (rl & 7))];
+          if (r < M && col_ok) {
+            if (epi.addend != nullptr) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+            if (epi.out32 != nullptr) *reinterpret_cast<float4*>(epi.out32 + (size_t)r * epi.ld32 + col) = v;
+            if (epi.out16 != nullptr)
+              *reinterpret_cast<uint2*>(epi.out16 + (size_t)r * epi.ld16 + col) =
+                  make_uint2(pack_f16x2_sat(v.x, v.y), pack_f16x2_sat(v.z, v.w));
           }
         }
-        if (epi.out32 != nullptr) {
-          float4* o = reinterpret_cast<float4*>(epi.out32 + (size_t)row * epi.ld32 + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (4 * j < nv) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (epi.out16 != nullptr) {
-          uint4* o = reinterpret_cast<uint4*>(epi.out16 + (size_t)row * epi.ld16 + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (8 * j < nv) o[j] = make_uint4(pack_f16x2_sat(v[8 * j], v[8 * j + 1]), pack_f16x2_sat(v[8 * j + 2], v[8 * j + 3]),
-                              pack_f16x2_sat(v[8 * j + 4], v[8 * j + 5]), pack_f16x2_sat(v[8 * j + 6], v[8 * j + 7]));
-        }
+        __syncwarp();
       }
     }
     tc_fence_before();
@@ -173,9 +206,11 @@ __global__ void __launch_bounds__(GEMM_THREADS)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
+
+static int g_num_sms = 0;
 
 template <int BN, int STAGES>
 static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
@@ -193,8 +228,11 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
               reinterpret_cast<__half*>(a.out_f16), a.ld16};
-  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
-  gemm_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, epi, a.M, a.N, a.K);
+  const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
+  const int num_tiles = tiles_n * tiles_m;
+  const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  gemm_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, epi, a.M, a.N, a.K, tiles_n,
+                                                                       num_tiles);
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;
 }
@@ -250,8 +288,16 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
   int rc = mtn::validate_linear(a);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->N > 64) return mtn::launch_gemm<128, 3>(*a, st);
-  return mtn::launch_gemm<64, 4>(*a, st);
+  if (mtn::g_num_sms == 0) {
+    int dev = 0, n = 0;
+    MTN_CHECK_CUDA(cudaGetDevice(&dev));
+    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    mtn::g_num_sms = n;
+  }
+  // 128x256 tiles halve the operand bytes per FLOP; use them when they still fill the machine.
+  const long tiles256 = (long)((a->N + 255) / 256) * ((a->M + 127) / 128);
+  if (a->N >= 256 && tiles256 >= mtn::g_num_sms) return mtn::launch_gemm<256, 4>(*a, st);
+  return mtn::launch_gemm<128, 6>(*a, st);
 }
 
 extern "C" int mtn_check_linear_fwd(const MtnLinearArgs* a, void* stream) {
