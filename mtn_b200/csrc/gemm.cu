@@ -9,8 +9,8 @@
 // warps drain the other buffer with tcgen05.ld, apply bias / ReLU / residual-or-positional
 // addend and store f32 and/or f16 with line-coalesced accesses.  CTAs are persistent.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (warp w may touch TMEM lanes 32*(w%4) .. +31; two warps per quarter).
 #include "common.cuh"
 #include "host.h"
 
@@ -30,7 +30,7 @@ struct GemmEpi {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 f16 = 128 B = one swizzle-128B row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STAGE_TILE_BYTES = 32 * 32 * 4;  // per-epilogue-warp 32x32 f32 transpose buffer
 
 template <int BN, int STAGES>
@@ -39,7 +39,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int XPOSE_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = XPOSE_OFF + 4 * STAGE_TILE_BYTES;
+  static constexpr int BAR_OFF = XPOSE_OFF + 8 * STAGE_TILE_BYTES;
   static constexpr int NBARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFF + 8 * NBARS + 16 + 1024;  // + tmem slot + 1 KB alignment slack
 };
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);   // tcgen05.commit after the last k-block of a tile
-      mbar_init(bar_acc_empty(b), 4);  // one arrive per epilogue warp
+      mbar_init(bar_acc_empty(b), 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -131,13 +131,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue (8 warps)
     // TMEM gives each thread one accumulator ROW (32 columns per load).  Each warp transposes its
-    // 32x32 block through a private XOR-swizzled shared-memory tile so that global traffic is
-    // line-coalesced: 8 lanes cover 128 contiguous bytes of one row, a warp covers 4 rows.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float4* xp = reinterpret_cast<float4*>(smem + L::XPOSE_OFF + q * STAGE_TILE_BYTES);
+    // 32x32 block through a private XOR-swizzled shared-memory tile so that all global traffic is
+    // line-coalesced (8 lanes cover 128 contiguous bytes of a row, a warp covers 4 rows), and all
+    // element-wise work (bias, ReLU, residual) happens in that coalesced layout with its global
+    // operands requested before the TMEM load.  Two warps share each TMEM lane quarter and take
+    // alternate 32-column chunks.
+    const int ew = warp - 2;
+    const int q = warp & 3;    // TMEM lane quarter this warp may access
+    const int half = ew >> 2;  // 0: even chunks, 1: odd chunks
+    float4* xp = reinterpret_cast<float4*>(smem + L::XPOSE_OFF + ew * STAGE_TILE_BYTES);
     const int sub_r = lane >> 3, c4 = lane & 7;
+    constexpr int NCHUNK = BN / 32;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
@@ -147,11 +153,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < NCHUNK; c += 2) {
         const int col = n0 + c * 32 + c4 * 4;  // this lane's 4 columns in the coalesced phase
         const bool col_ok = col < N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (epi.bias != nullptr && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
         float4 res[8];
-        if (epi.addend != nullptr) {  // issue the residual / positional loads before touching TMEM
+        if (epi.addend != nullptr) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = row0 + i * 4 + sub_r;
@@ -164,34 +172,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         uint32_t acc[32];
         tc_ld32(t_acc + c * 32, acc);
         tc_wait_ld();
-        if (c == BN / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        if (c + 2 >= NCHUNK) {  // this warp's last read of the accumulator: release its share of the buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty(buf));
         }
-        // bias + activation in the row-per-thread layout (bias address is warp-uniform -> broadcast)
-        const int cb = n0 + c * 32;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
-                                 __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-          if (epi.bias != nullptr && cb + 4 * j < N) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4 * j));
-            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          }
-          if (epi.act == MTN_ACT_RELU) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          }
-          xp[lane * 8 + (j ^ (lane & 7))] = v;
-        }
+        for (int j = 0; j < 8; ++j)
+          xp[lane * 8 + (j ^ (lane & 7))] =
+              make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                          __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + sub_r;
           const int r = row0 + rl;
           float4 v = xp[rl * 8 + (c4 ^ (rl & 7))];
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (epi.act == MTN_ACT_RELU) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+          if (epi.addend != nullptr) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
           if (r < M && col_ok) {
-            if (epi.addend != nullptr) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
             if (epi.out32 != nullptr) *reinterpret_cast<float4*>(epi.out32 + (size_t)r * epi.ld32 + col) = v;
             if (epi.out16 != nullptr)
               *reinterpret_cast<uint2*>(epi.out16 + (size_t)r * epi.ld16 + col) =
