@@ -158,11 +158,26 @@ class DecoderEngine(object):
         _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x, out_f32=x, out_f16=out16)
 
     # ------------------------------------------------------------------ memory stage
+    def _streams(self, M, dev):
+        if getattr(self, "_side", None) is None or len(self._side) != M or self._side_dev != dev:
+            self._side = [torch.cuda.Stream(device=dev) for _ in range(M)]
+            self._side_dev = dev
+        return self._side
+
     def _memory_stage(self, W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask, ae_ft, ae_features):
+        """Everything that does not depend on the target stream.  The text memories' hoisted K/V run
+        on the caller's stream; each modality's Query-Aware Auto-Encoder chain (all N layers) runs on
+        its own side stream, forked here and joined by ``forward`` -- the two chains and the target
+        path are independent latency-bound sequences of small kernels, so they overlap.  Every
+        buffer is allocated on the caller's stream; side streams only launch kernels.
+        ``S["ev"][l][i]`` fires when layer l's K/V of ae_i is ready for the target path."""
         dev = qm.device
         d, N, M = W["d"], W["N"], W["M"]
         B = qm.shape[0]
         f16 = torch.float16
+        main = torch.cuda.current_stream()
+        side = self._streams(M, dev)
+        dff = W["layers"][0]["ffn"]["w_1"].shape[0]
 
         def hoisted(mem, wb):
             m16 = _lib.cast_f16(mem.contiguous().view(-1, d))
@@ -170,7 +185,7 @@ class DecoderEngine(object):
             _lib.linear(m16, wb[0], wb[1], out_f16=out)
             return out
 
-        def bits(mask, L):
+        def bits(mask):
             if mask is None:
                 return None
             if mask.shape[0] != B:
@@ -178,52 +193,71 @@ class DecoderEngine(object):
             return _lib.mask_pack(mask)
 
         S = {"H": his.shape[1], "C": cap.shape[1], "Q": qm.shape[1]}
-        S["kv_his"], S["kv_cap"], S["kv_q"] = hoisted(his, W["kv_his"]), hoisted(cap, W["kv_cap"]), hoisted(qm, W["kv_q"])
-        S["bits_his"], S["bits_cap"], S["bits_q"] = bits(his_mask, S["H"]), bits(cap_mask, S["C"]), bits(q_mask, S["Q"])
         if ae_features in ("caption", "summary"):
-            ae_default, ae_bits = cap, S["bits_cap"]
+            ae_default = cap
         elif ae_features == "query":
-            ae_default, ae_bits = qm, S["bits_q"]
+            ae_default = qm
         else:
             raise ValueError("auto_encoder_ft must be 'query', 'caption' or 'summary' "
                              "(reference mtn.py:187-202 leaves ae_mask unbound otherwise)")
-        S["bits_ae"] = ae_bits
         La = ae_default.shape[1]
         S["La"] = La
         rows = B * La
-        xn16 = torch.empty(rows, d, dtype=f16, device=dev)
-        qkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
-        obuf = torch.empty(rows, d, dtype=f16, device=dev)
-        dff = W["layers"][0]["ffn"]["w_1"].shape[0]
-        hid = torch.empty(rows, dff, dtype=f16, device=dev)
-        S["kv_ae"] = [[None] * M for _ in range(N)]
-        S["ae_out"] = []
+        # ---- allocations + tiny prep on the caller's stream
+        S["bits_his"], S["bits_cap"], S["bits_q"] = bits(his_mask), bits(cap_mask), bits(q_mask)
+        ae_bits = S["bits_q"] if ae_features == "query" else S["bits_cap"]
+        S["bits_ae"] = ae_bits
+        mods = []
         for i in range(M):
             Lv = vid_ft[i].shape[1]
-            kv_vid = hoisted(vid_ft[i], W["kv_vid"][i])
-            bits_vid = bits(vid_mask[i], Lv)
             src = ae_ft[i] if isinstance(ae_ft, (list, tuple)) else (ae_ft if ae_ft is not None else ae_default)
-            ae = src.contiguous().view(rows, d).clone()          # f32 residual stream of the QAE branch
-            ae16 = torch.empty(rows, d, dtype=f16, device=dev)
-            for l in range(N):
-                Lw = W["layers"][l]
-                c0 = 4 + 4 * i
-                self._attn_block(ae, Lw["ln"][c0], Lw["ae_self"][i], B, La, La, Lw["ae_self"][i]["w_qkv"],
-                                 Lw["ae_self"][i]["b_qkv"], None, 0, 0, ae_bits, xn16, qkv, obuf)
-                A = Lw["ae_vid"][i]
-                self._attn_block(ae, Lw["ln"][c0 + 1], A, B, La, Lv, A["w_qkv"][:d], A["b_qkv"][:d], kv_vid,
-                                 l * 2 * d, l * 2 * d + d, bits_vid, xn16, qkv[:, :d], obuf)
-                self._ffn_block(ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], xn16, hid, out16=ae16)
-                # K/V of this layer's ae_i for the target stream's auto_encoder_attn[i] (mtn.py:215):
-                # the memory is the un-normed ae_i itself
-                A2 = Lw["ae_attn"][i]
-                kv = torch.empty(rows, 2 * d, dtype=f16, device=dev)
-                _lib.linear(ae16, A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=kv)
-                S["kv_ae"][l][i] = kv
-            out = torch.empty(rows, d, dtype=torch.float32, device=dev)
-            nrm = W["ae_norm"][i]
-            _lib.layernorm(ae, nrm[0], nrm[1], nrm[2], out_f32=out)          # mtn.py:162-163
-            S["ae_out"].append(out.view(B, La, d))
+            mods.append({
+                "Lv": Lv, "bits_vid": bits(vid_mask[i]),
+                "vid": vid_ft[i].contiguous().view(-1, d),
+                "vid16": torch.empty(B * Lv, d, dtype=f16, device=dev),
+                "kv_vid": torch.empty(B * Lv, N * 2 * d, dtype=f16, device=dev),
+                "ae": src.contiguous().view(rows, d).clone(),        # f32 residual stream of the QAE branch
+                "ae16": torch.empty(rows, d, dtype=f16, device=dev),
+                "xn16": torch.empty(rows, d, dtype=f16, device=dev),
+                "qkv": torch.empty(rows, 3 * d, dtype=f16, device=dev),
+                "obuf": torch.empty(rows, d, dtype=f16, device=dev),
+                "hid": torch.empty(rows, dff, dtype=f16, device=dev),
+                "kv_ae": [torch.empty(rows, 2 * d, dtype=f16, device=dev) for _ in range(N)],
+                "out": torch.empty(rows, d, dtype=torch.float32, device=dev),
+            })
+        S["kv_ae"] = [[mods[i]["kv_ae"][l] for i in range(M)] for l in range(N)]
+        S["ev"] = [[torch.cuda.Event() for _ in range(M)] for _ in range(N)]
+        S["ae_out"] = [m["out"].view(B, La, d) for m in mods]
+        S["side"] = side
+        # ---- fork: one side stream per modality
+        for i in range(M):
+            side[i].wait_stream(main)
+            m = mods[i]
+            with torch.cuda.stream(side[i]):
+                _lib.cast_f16(m["vid"], m["vid16"])
+                _lib.linear(m["vid16"], W["kv_vid"][i][0], W["kv_vid"][i][1], out_f16=m["kv_vid"])
+                ae = m["ae"]
+                for l in range(N):
+                    Lw = W["layers"][l]
+                    c0 = 4 + 4 * i
+                    A = Lw["ae_self"][i]
+                    self._attn_block(ae, Lw["ln"][c0], A, B, La, La, A["w_qkv"], A["b_qkv"], None, 0, 0, ae_bits,
+                                     m["xn16"], m["qkv"], m["obuf"])
+                    A = Lw["ae_vid"][i]
+                    self._attn_block(ae, Lw["ln"][c0 + 1], A, B, La, m["Lv"], A["w_qkv"][:d], A["b_qkv"][:d],
+                                     m["kv_vid"], l * 2 * d, l * 2 * d + d, m["bits_vid"], m["xn16"],
+                                     m["qkv"][:, :d], m["obuf"])
+                    self._ffn_block(ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], m["xn16"], m["hid"], out16=m["ae16"])
+                    # K/V of this layer's ae_i for the target stream's auto_encoder_attn[i] (mtn.py:215):
+                    # the memory is the un-normed ae_i itself
+                    A2 = Lw["ae_attn"][i]
+                    _lib.linear(m["ae16"], A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=m["kv_ae"][l])
+                    S["ev"][l][i].record(side[i])
+                nrm = W["ae_norm"][i]
+                _lib.layernorm(ae, nrm[0], nrm[1], nrm[2], out_f32=m["out"])          # mtn.py:162-163
+        # ---- text memories on the caller's stream (overlaps with the side streams)
+        S["kv_his"], S["kv_cap"], S["kv_q"] = hoisted(his, W["kv_his"]), hoisted(cap, W["kv_cap"]), hoisted(qm, W["kv_q"])
+        S["_keep"] = mods
         return S
 
     # ------------------------------------------------------------------ forward
@@ -236,11 +270,14 @@ class DecoderEngine(object):
         key = _MemoryKey(self._packed._key, ae_features,
                          list(vid_ft) + list(vid_mask) + [his, his_mask, cap, cap_mask, qm, q_mask] +
                          (list(ae_ft) if isinstance(ae_ft, (list, tuple)) else [ae_ft]))
-        if not key.matches(self._mem_key):
+        fresh = not key.matches(self._mem_key)
+        if fresh:
+            self._mem_key, self._mem = None, None
             self._mem = self._memory_stage(W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask,
                                            ae_ft, ae_features)
             self._mem_key = key
         S = self._mem
+        main = torch.cuda.current_stream()
 
         rows = B * T
         f16 = torch.float16
@@ -270,10 +307,15 @@ class DecoderEngine(object):
                 self._attn_block(xs, Lw["ln"][2 + c], A, B, T, S[Ln], A["w_qkv"][:d], A["b_qkv"][:d], S[kvn], kc, vc,
                                  S[bn], xn16, qkv[:, :d], obuf)
             for i in range(M):
+                if fresh:
+                    main.wait_event(S["ev"][l][i])          # layer l's K/V of ae_i (side stream i)
                 A = Lw["ae_attn"][i]
                 self._attn_block(xs, Lw["ln"][7 + 4 * i], A, B, T, S["La"], A["w_qkv"][:d], A["b_qkv"][:d],
                                  S["kv_ae"][l][i], 0, d, S["bits_ae"], xn16, qkv[:, :d], obuf)
             self._ffn_block(xs, Lw["ln"][4 + 4 * M], Lw["ffn"], xn16, hid)
         out = torch.empty(rows, d, dtype=torch.float32, device=dev)
         _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=out)   # mtn.py:164
+        if fresh:
+            for st in S["side"]:                                 # join (also required for graph capture)
+                main.wait_stream(st)
         return out.view(B, T, d), list(S["ae_out"])
