@@ -107,9 +107,15 @@ def check(rc):
 # wrapper appends {name, flops, bytes, start, end} with CUDA events around the launch.
 # ------------------------------------------------------------------------------
 TRACE = None
+# when RECORD is a list, every launch also appends (name, flops, bytes, relaunch) where relaunch()
+# re-issues the identical kernel on the current stream -- bench.py replays the launches of one
+# kernel type back to back inside a CUDA graph to time them without host gaps.
+RECORD = None
 
 
 def _launch(name, flops, nbytes, fn):
+    if RECORD is not None:
+        RECORD.append((name, flops, nbytes, lambda: check(fn())))
     if TRACE is None:
         return check(fn())
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

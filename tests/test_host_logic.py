@@ -1,0 +1,169 @@
+"""CPU tier: host-side logic of the drop-in boundary (no kernels run)."""
+import copy
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import mtn_oracle as O
+from mtn_b200 import mtn, data_utils, engine, _lib, parallel
+
+
+CFG = {"N": 2, "d_model": 64, "d_ff": 128, "h": 2, "vocab": 40, "ft_sizes": [24, 16],
+       "auto_encoder_ft": "query", "diff_encoder": True}
+
+
+def small_model(seed=0):
+    torch.manual_seed(seed)
+    return mtn.make_model(40, 40, N=2, d_model=64, d_ff=128, h=2, ft_sizes=[24, 16], diff_encoder=True,
+                          auto_encoder_ft="query")
+
+
+def test_state_dict_contract():
+    """Same keys and shapes as the reference; the oracle's key set was checked against
+    the live reference in test_oracle.py."""
+    sd = small_model().state_dict()
+    ref = O.init_state_dict(CFG, 0)
+    assert set(sd) == set(ref)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    assert "decoder.layers.0.src_attn.linears.0.weight" in sd       # q_attn is stored as src_attn
+    assert "vid_encoder.1.2.pe" in sd and "vid_encoder.0.0.weight" in sd
+
+
+def test_make_model_seed_parity_with_reference():
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present")
+    warnings.simplefilter("ignore")
+    ref_mtn, _ = ref_loader.load()
+    torch.manual_seed(11)
+    a = ref_mtn.make_model(40, 40, N=2, d_model=64, d_ff=128, h=2, ft_sizes=[24, 16], diff_encoder=True,
+                           auto_encoder_ft="query").state_dict()
+    b = small_model(11).state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_batch_masks_match_oracle():
+    inp = O.synth_inputs(CFG, B=4, Q=7, C=9, H=15, T=6, Lv=[11, 5], seed=2)
+    m = O.make_masks(inp["query"], inp["his"], inp["cap"], inp["trg"], inp["fts"], 1)
+    b = data_utils.Batch(inp["query"], inp["his"], None, [f.permute(1, 0, 2).numpy() for f in inp["fts"]],
+                         inp["cap"], inp["trg"], inp["trg_y"], 1)
+    dev = b.fts[0].device
+    for k in ("query_mask", "his_mask", "cap_mask", "trg_mask"):
+        assert torch.equal(getattr(b, k).cpu(), m[k]), k
+    for i in range(2):
+        assert torch.equal(b.fts_mask[i].cpu(), m["fts_mask"][i])
+        assert torch.equal(b.fts[i].cpu(), m["fts"][i])
+    assert int(b.ntokens) == int((inp["trg_y"] != 1).sum())
+    assert torch.equal(data_utils.subsequent_mask(5), O.subsequent_mask(5))
+    assert dev.type in ("cpu", "cuda")
+
+
+def test_hot_path_has_no_cpu_fallback():
+    model = small_model().eval()
+    x = torch.zeros(2, 3, 64)
+    with torch.no_grad():
+        for fn in (lambda: model.decoder.norm(x), lambda: model.decoder.layers[0].self_attn(x, x, x),
+                   lambda: model.decoder.layers[0].feed_forward(x),
+                   lambda: mtn.attention(torch.zeros(1, 2, 3, 32), torch.zeros(1, 2, 3, 32),
+                                         torch.zeros(1, 2, 3, 32))):
+            with pytest.raises(_lib.MtnError, match="CUDA"):
+                fn()
+
+
+def test_training_mode_is_rejected_not_silently_wrong():
+    model = small_model().train()
+    with pytest.raises((NotImplementedError, _lib.MtnError)):
+        model.decoder.norm(torch.zeros(2, 64, requires_grad=True))
+
+
+def test_packed_weight_cache_invalidation():
+    pw = engine.PackedWeights()
+    p = torch.nn.Parameter(torch.ones(4))
+    calls = []
+    build = lambda: calls.append(1) or len(calls)
+    assert pw.get([p], build) == 1 and pw.get([p], build) == 1
+    with torch.no_grad():
+        p.add_(1.0)                      # optimizer step bumps _version
+    assert pw.get([p], build) == 2
+    assert copy.deepcopy(pw)._key is None and pickle.loads(pickle.dumps(pw))._val is None
+
+
+def test_memory_key_identity():
+    a, b = torch.zeros(3), torch.zeros(3)
+    k1 = engine._MemoryKey(("w",), "query", [a, None])
+    assert k1.matches(engine._MemoryKey(("w",), "query", [a, None]))
+    assert not k1.matches(engine._MemoryKey(("w",), "query", [b, None]))       # equal values, other tensor
+    assert not k1.matches(engine._MemoryKey(("w",), "caption", [a, None]))
+    assert not k1.matches(None)
+    a.add_(1)
+    assert not engine._MemoryKey(("w",), "query", [a, None]).matches(k1)       # in-place update
+
+
+def test_model_pickles_like_the_reference_checkpoints():
+    """train.py:217 does torch.save(model); the classes must round-trip (engine caches dropped)."""
+    model = small_model()
+    model.decoder._engine = object()
+    m2 = pickle.loads(pickle.dumps(model))
+    assert m2.decoder._engine is None
+    assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), m2.state_dict().values()))
+
+
+class FakeModel(object):
+    """Deterministic stand-in with the encode/decode/generator protocol (no kernels): the next-token
+    distribution depends only on the prefix, so search logic can be compared exactly."""
+    V = 12
+
+    def encode(self, *a, **k):
+        return [torch.zeros(1)] * 5
+
+    def decode(self, vid, his, cap, q, fm, hm, cm, qm, tgt, tgt_mask, ae):
+        g = torch.Generator().manual_seed(int((tgt[0] * torch.arange(1, tgt.shape[1] + 1)).sum()))
+        return (torch.randn(tgt.shape[0], tgt.shape[1], self.V, generator=g), [])
+
+    def generator(self, x):
+        return torch.log_softmax(x * 3, dim=-1)
+
+
+class FakeBatch(object):
+    fts = fts_mask = cap = cap_mask = his = his_st = his_mask = query_mask = None
+    query = torch.zeros(1, 3, dtype=torch.long)
+
+
+def test_beam_search_matches_reference_rules():
+    import ref_loader
+    mine = data_utils.beam_search_decode(FakeModel(), FakeBatch(), 6, 2, 0, 3, 1, beam=3, penalty=1.0, nbest=3)
+    assert len(mine[0]) == 3 and mine[1] is not None
+    assert all(0 not in h and 3 not in h for h, _ in mine[0])       # <unk>/<eos> never expanded
+    if ref_loader.available():
+        warnings.simplefilter("ignore")
+        _, ref_du = ref_loader.load()
+        ref = ref_du.beam_search_decode(FakeModel(), FakeBatch(), 6, 2, 0, 3, 1, beam=3, penalty=1.0, nbest=3)
+        assert [list(map(int, h)) for h, _ in ref[0]] == [list(map(int, h)) for h, _ in mine[0]]
+        assert np.allclose([s for _, s in ref[0]], [s for _, s in mine[0]])
+        assert np.isclose(ref[1], mine[1])
+
+
+def test_greedy_decode_semantics():
+    ys = data_utils.greedy_decode(FakeModel(), FakeBatch(), 5, 2)
+    assert ys.shape == (1, 5) and int(ys[0, 0]) == 2
+    m = FakeModel()
+    t = torch.tensor([[2]])
+    for i in range(4):
+        nxt = m.generator(m.decode(*[None] * 8, t, None, None)[0][:, -1]).argmax(-1, keepdim=True)
+        t = torch.cat([t, nxt], 1)
+    assert torch.equal(t, ys)
+
+
+def test_shard_range_partitions():
+    for n, w in ((256, 8), (16, 4), (10, 4), (3, 8)):
+        spans = [parallel.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    assert parallel.shard_range(256, 3, 8) == (96, 128)             # cfg3: rows [32r, 32r+32)
