@@ -113,9 +113,9 @@ TRACE = None
 RECORD = None
 
 
-def _launch(name, flops, nbytes, fn):
-    if RECORD is not None:
-        RECORD.append((name, flops, nbytes, lambda: check(fn())))
+def _launch(name, flops, nbytes, fn, keep=()):
+    if RECORD is not None:      # `keep` pins the operand tensors for as long as the closure lives
+        RECORD.append((name, flops, nbytes, lambda: check(fn()), keep))
     if TRACE is None:
         return check(fn())
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -159,7 +159,8 @@ def layernorm(x, a_2, b_2, eps, out_f32=None, out_f16=None):
     nbytes = rows * d * (4 + (4 if out_f32 is not None else 0) + (2 if out_f16 is not None else 0))
     _launch("layernorm", 0, nbytes,
             lambda: lib().mtn_layernorm_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), rows, d, ptr(out_f32),
-                                            ptr(out_f16), stream_ptr()))
+                                            ptr(out_f16), stream_ptr()),
+            keep=(x, a_2, b_2, out_f32, out_f16))
 
 
 def cast_f16(src, dst=None):
@@ -173,7 +174,7 @@ def cast_f16(src, dst=None):
     assert d2.shape == s2.shape
     _launch("cast_f16", 0, s2.numel() * 6,
             lambda: lib().mtn_cast_f32_to_f16(ptr(s2), s2.stride(0), ptr(d2), d2.stride(0), s2.shape[0],
-                                              s2.shape[1], stream_ptr()))
+                                              s2.shape[1], stream_ptr()), keep=(s2, d2))
     return dst
 
 
@@ -189,7 +190,7 @@ def mask_pack(mask):
     B, R, Lk = m8.shape
     bits = torch.empty((B, R, mask_words(Lk)), dtype=torch.int32, device=mask.device)
     _launch("mask_pack", 0, m8.numel() + bits.numel() * 4,
-            lambda: lib().mtn_mask_pack(ptr(m8), B, R, Lk, ptr(bits), stream_ptr()))
+            lambda: lib().mtn_mask_pack(ptr(m8), B, R, Lk, ptr(bits), stream_ptr()), keep=(m8, bits))
     return bits
 
 
@@ -217,7 +218,8 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
     nbytes = 2 * (a.M * a.K + a.N * a.K) + a.M * a.N * ((4 if out_f32 is not None else 0) +
                                                         (2 if out_f16 is not None else 0) +
                                                         (4 if addend is not None else 0))
-    _launch("linear", 2 * a.M * a.N * a.K, nbytes, lambda: fn(C.byref(a), stream_ptr()))
+    _launch("linear", 2 * a.M * a.N * a.K, nbytes, lambda: fn(C.byref(a), stream_ptr()),
+            keep=(A, W, bias, addend, out_f32, out_f16))
 
 
 def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False):
@@ -237,4 +239,4 @@ def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=Fal
     a.out, a.ldo = out.data_ptr(), out.stride(0)
     fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
     _launch("attn_core", 4 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (2 * Lq + 2 * Lk),
-            lambda: fn(C.byref(a), stream_ptr()))
+            lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits))
