@@ -26,14 +26,15 @@ namespace mtn {
 
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_QT = 128;  // queries per CTA (UMMA M)
-constexpr int ATT_KT = 128;  // keys per tile (UMMA N of the S MMA)
 
-template <int DK>
+// KT = keys per tile (UMMA N of the S MMA): 128, or 64 for short memories (Lk <= 64: caption /
+// query / auto-encoder sites) where a 128-key tile would be half padding.
+template <int DK, int ATT_KT>
 struct AttnCfg {
   static constexpr int ROWB = DK * 2;  // bytes per smem row of Q/K/V == swizzle span
   static constexpr int Q_BYTES = ATT_QT * ROWB;
   static constexpr int KV_BYTES = ATT_KT * ROWB;
-  static constexpr int P_BYTES = ATT_QT * ATT_KT * 2;  // two [128 x 64] f16 panels
+  static constexpr int P_BYTES = ATT_QT * ATT_KT * 2;  // [128 x 64] f16 panels (KT/64 of them)
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_BYTES;
@@ -61,11 +62,17 @@ enum {
   BAR_P_FULL, BAR_PV_DONE, BAR_COUNT
 };
 
-template <int DK>
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DK, int ATT_KT>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
     attn_core_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using C = AttnCfg<DK>;
+  using C = AttnCfg<DK, ATT_KT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -158,8 +165,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       const int mq = (p.mask_rows_q == 1) ? 0 : min(qi, p.Lq - 1);
       mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
     }
+    // Softmax runs in the log2 domain: t = s * (scale * log2 e); masked t = -1e9 * log2 e (the
+    // reference's finite -1e9, mtn.py:227); p = 2^(t - m).  Chunks (32 keys) whose keys are all
+    // kept and in range -- the common case -- take a select-free fast path.
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float c1 = p.scale * LOG2E;
+    const float t_masked = -1e9f * LOG2E;
     float m_run = -CUDART_INF_F, l_run = 0.f;
     const uint32_t sw = (uint32_t)(row & 7);
+    constexpr int NCH = ATT_KT / 32;
 
     for (int j = 0; j < nt; ++j) {
       const uint32_t ph = j & 1;
@@ -168,20 +182,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       // ---- pass 1: row maximum of the masked, scaled scores
       float m_tile = -CUDART_INF_F;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         const int k0 = j * ATT_KT + c * 32;
-        const int nvalid = p.Lk - k0;  // keys of this chunk inside the sequence
-        const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + j * 4 + c) : 0xffffffffu;
+        const int nvalid = p.Lk - k0;  // keys of this chunk inside the sequence (warp-uniform)
+        if (nvalid <= 0) break;
+        const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+        const uint32_t mw = (mrow != nullptr) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
         uint32_t r[32];
         tc_ld32(tS + lane_off + c * 32, r);
         tc_wait_ld();
+        if ((mw & inb) == 0xffffffffu) {
+          float mx = __uint_as_float(r[0]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]) * p.scale;
-          s = ((mw >> i) & 1u) ? s : -1e9f;
-          s = ((inb >> i) & 1u) ? s : -CUDART_INF_F;
-          m_tile = fmaxf(m_tile, s);
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          m_tile = fmaxf(m_tile, mx * c1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = __uint_as_float(r[i]) * c1;
+            t = ((mw >> i) & 1u) ? t : t_masked;
+            t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+            m_tile = fmaxf(m_tile, t);
+          }
         }
       }
       const float m_new = fmaxf(m_run, m_tile);
@@ -190,25 +212,38 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
         tc_fence_after();
       }
-      // ---- pass 2: p = exp(s - m), row sum, f16 P tile to shared memory
+      // ---- pass 2: p = 2^(t - m), row sum, f16 P tile to shared memory
       float l_tile = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         const int k0 = j * ATT_KT + c * 32;
         const int nvalid = p.Lk - k0;
         const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + j * 4 + c) : 0xffffffffu;
-        uint32_t r[32];
-        tc_ld32(tS + lane_off + c * 32, r);
-        tc_wait_ld();
+        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
         float e[32];
+        if (nvalid > 0) {  // warp-uniform
+          uint32_t r[32];
+          tc_ld32(tS + lane_off + c * 32, r);
+          tc_wait_ld();
+          if ((mw & inb) == 0xffffffffu) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]) * p.scale;
-          s = ((mw >> i) & 1u) ? s : -1e9f;
-          s = ((inb >> i) & 1u) ? s : -CUDART_INF_F;
-          e[i] = __expf(s - m_new);
-          l_tile += e[i];
+            for (int i = 0; i < 32; ++i) {
+              e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c1, -m_new));
+              l_tile += e[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float t = __uint_as_float(r[i]) * c1;
+              t = ((mw >> i) & 1u) ? t : t_masked;
+              t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+              e[i] = ex2_approx(t - m_new);
+              l_tile += e[i];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) e[i] = 0.f;
         }
         const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * 128;
 #pragma unroll
@@ -222,7 +257,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       }
       tc_fence_before();
       mbar_arrive(bar(BAR_S_FREE));  // S may be overwritten by the next Q K^T
-      const float alpha = __expf(m_run - m_new);
+      const float alpha = ex2_approx(m_run - m_new);
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
       if (j > 0) {
@@ -270,12 +305,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   }
 }
 
-template <int DK>
+template <int DK, int ATT_KT>
 static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
-  using C = AttnCfg<DK>;
+  using C = AttnCfg<DK, ATT_KT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tc_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tc_kernel<DK, ATT_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::TOTAL));
     attr_set = true;
   }
@@ -291,7 +326,7 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   AttnParams p{a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
                1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo};
   dim3 grid((a.Lq + ATT_QT - 1) / ATT_QT, a.h, a.B);
-  attn_core_tc_kernel<DK><<<grid, ATT_THREADS, C::TOTAL, st>>>(tq, tk, tv, p);
+  attn_core_tc_kernel<DK, ATT_KT><<<grid, ATT_THREADS, C::TOTAL, st>>>(tq, tk, tv, p);
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;
 }
@@ -360,7 +395,8 @@ extern "C" int mtn_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
   int rc = mtn::validate_attn(a);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return a->d_k == 64 ? mtn::launch_attn<64>(*a, st) : mtn::launch_attn<32>(*a, st);
+  if (a->Lk <= 64) return a->d_k == 64 ? mtn::launch_attn<64, 64>(*a, st) : mtn::launch_attn<32, 64>(*a, st);
+  return a->d_k == 64 ? mtn::launch_attn<64, 128>(*a, st) : mtn::launch_attn<32, 128>(*a, st);
 }
 
 extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
