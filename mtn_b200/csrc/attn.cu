@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   const int qt = blockIdx.x, hd = blockIdx.y, b = blockIdx.z;
   const int nt = (p.Lk + ATT_KT - 1) / ATT_KT;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tS = tmem_base, tO = tmem_base + C::O_COL;
+  pdl_wait();
 
   if (warp == 0) {
     // -------------------------------------------------------------- TMA producer
@@ -326,8 +328,7 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   AttnParams p{a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
                1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo};
   dim3 grid((a.Lq + ATT_QT - 1) / ATT_QT, a.h, a.B);
-  attn_core_tc_kernel<DK, ATT_KT><<<grid, ATT_THREADS, C::TOTAL, st>>>(tq, tk, tv, p);
-  MTN_CHECK_CUDA(cudaGetLastError());
+  MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, p));
   return MTN_OK;
 }
 

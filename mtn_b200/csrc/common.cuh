@@ -61,6 +61,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch (PDL).  Every kernel calls pdl_launch_dependents() first -- once all
+// of its CTAs are resident the next kernel of the stream may start and run its prologue (barrier
+// init, TMEM allocation, descriptor prefetch) -- and pdl_wait() before its first global-memory
+// access, which blocks until the preceding kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA / TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int lane = threadIdx.x & 31;
   const int nkb = (K + BK - 1) / BK;  // K tail: TMA zero-fills columns >= K
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel; global memory is touched below
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -233,9 +235,8 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
   const int num_tiles = tiles_n * tiles_m;
   const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  gemm_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, epi, a.M, a.N, a.K, tiles_n,
-                                                                       num_tiles);
-  MTN_CHECK_CUDA(cudaGetLastError());
+  MTN_CHECK_CUDA(launch_kernel(gemm_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, st, tmA,
+                               tmB, epi, a.M, a.N, a.K, tiles_n, num_tiles));
   return MTN_OK;
 }
 

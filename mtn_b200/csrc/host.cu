@@ -1,11 +1,21 @@
 #include "host.h"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mtn {
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTN_B200_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256)
                           const float* __restrict__ b2, float eps, int rows, float* __restrict__ y32,
                           __half* __restrict__ y16) {
   constexpr int D = 128 * VPL;
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(256)
 __global__ void layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ a2,
                                          const float* __restrict__ b2, float eps, int rows, int d,
                                          float* __restrict__ y32, __half* __restrict__ y16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -94,6 +98,8 @@ __global__ void layernorm_generic_kernel(const float* __restrict__ x, const floa
 // ----------------------------------------------------------------------------
 __global__ void cast_f16_vec8_kernel(const float* __restrict__ src, int ld_src, __half* __restrict__ dst,
                                      int ld_dst, int rows, int cols8) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * cols8) return;
   const int r = (int)(i / cols8), c = (int)(i % cols8) * 8;
@@ -105,6 +111,8 @@ __global__ void cast_f16_vec8_kernel(const float* __restrict__ src, int ld_src, 
 }
 __global__ void cast_f16_scalar_kernel(const float* __restrict__ src, int ld_src, __half* __restrict__ dst,
                                        int ld_dst, int rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * cols) return;
   const int r = (int)(i / cols), c = (int)(i % cols);
@@ -117,6 +125,8 @@ __global__ void cast_f16_scalar_kernel(const float* __restrict__ src, int ld_src
 // ----------------------------------------------------------------------------
 __global__ void mask_pack_kernel(const uint8_t* __restrict__ m, int nrows, int Lk, int words,
                                  uint32_t* __restrict__ bits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (size_t)nrows * words) return;
   const int row = (int)(w / words), word = (int)(w % words);
@@ -139,11 +149,11 @@ extern "C" int mtn_layernorm_fwd(const float* x, const float* a_2, const float* 
   dim3 grid((rows + wpb - 1) / wpb);
   const bool vec = (d % 128 == 0) && d <= 1024 && aligned16(x) && aligned16(a_2) && aligned16(b_2) &&
                    (!y_f32 || aligned16(y_f32)) && (!y_f16 || aligned16(y_f16));
-  if (vec && d == 128) layernorm_rows_kernel<1><<<grid, 32 * wpb, 0, st>>>(x, a_2, b_2, eps, rows, y_f32, y16);
-  else if (vec && d == 256) layernorm_rows_kernel<2><<<grid, 32 * wpb, 0, st>>>(x, a_2, b_2, eps, rows, y_f32, y16);
-  else if (vec && d == 512) layernorm_rows_kernel<4><<<grid, 32 * wpb, 0, st>>>(x, a_2, b_2, eps, rows, y_f32, y16);
-  else if (vec && d == 1024) layernorm_rows_kernel<8><<<grid, 32 * wpb, 0, st>>>(x, a_2, b_2, eps, rows, y_f32, y16);
-  else layernorm_generic_kernel<<<grid, 32 * wpb, 0, st>>>(x, a_2, b_2, eps, rows, d, y_f32, y16);
+  if (vec && d == 128) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<1>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
+  else if (vec && d == 256) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<2>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
+  else if (vec && d == 512) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<4>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
+  else if (vec && d == 1024) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<8>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
+  else MTN_CHECK_CUDA(launch_kernel(layernorm_generic_kernel, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, d, y_f32, y16));
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;
 }
@@ -158,10 +168,12 @@ extern "C" int mtn_cast_f32_to_f16(const float* src, int ld_src, void* dst, int 
   __half* d16 = reinterpret_cast<__half*>(dst);
   if (cols % 8 == 0 && ld_src % 4 == 0 && ld_dst % 8 == 0 && aligned16(src) && aligned16(dst)) {
     const size_t n = (size_t)rows * (cols / 8);
-    cast_f16_vec8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, ld_src, d16, ld_dst, rows, cols / 8);
+    MTN_CHECK_CUDA(launch_kernel(cast_f16_vec8_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, src, ld_src, d16,
+                                 ld_dst, rows, cols / 8));
   } else {
     const size_t n = (size_t)rows * cols;
-    cast_f16_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, ld_src, d16, ld_dst, rows, cols);
+    MTN_CHECK_CUDA(launch_kernel(cast_f16_scalar_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, src, ld_src,
+                                 d16, ld_dst, rows, cols));
   }
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;
@@ -175,8 +187,8 @@ extern "C" int mtn_mask_pack(const uint8_t* mask_u8, int B, int rows_q, int Lk, 
   MTN_REQUIRE(B > 0 && rows_q > 0 && Lk > 0, MTN_E_SHAPE, "mask_pack: B=%d rows_q=%d Lk=%d", B, rows_q, Lk);
   const int words = mtn_mask_words(Lk);
   const size_t nw = (size_t)B * rows_q * words;
-  mask_pack_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      mask_u8, B * rows_q, Lk, words, bits);
+  MTN_CHECK_CUDA(launch_kernel(mask_pack_kernel, dim3((unsigned)((nw + 7) / 8)), dim3(256), 0,
+                               static_cast<cudaStream_t>(stream), mask_u8, B * rows_q, Lk, words, bits));
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;
 }
