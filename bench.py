@@ -378,4 +378,11 @@ def main():
 
 
 if __name__ == "__main__":
+    # The contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its version
+    # banner there) are pointed at stderr for the duration of the run; print() keeps the real stdout.
+    sys.stdout.flush()
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real, "w")
     main()
+    sys.stdout.flush()
