@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.cpu_batch),
+            "config": workload_config(args, args.batch),
             "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "first %d dialogues of the batch per step, %d steps" % (args.cpu_batch, args.steps)},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

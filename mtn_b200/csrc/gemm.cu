@@ -11,6 +11,8 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..9 = epilogue (warp w may touch TMEM lanes 32*(w%4) .. +31; two warps per quarter).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -48,7 +50,13 @@ struct GemmSmem {
 // the CTAs running at the same time share the same A row panels and the whole of W in L2).  The TMA
 // ring and the two TMEM accumulator buffers run across tile boundaries: while the epilogue warps drain
 // accumulator i the tensor core is already filling accumulator i+1.
-template <int BN, int STAGES>
+//
+// CL > 1: thread-block clusters of CL CTAs along M.  The CTAs of a cluster work on the same n-block and
+// CL consecutive m-blocks at the same time; each loads 1/CL of the W tile and TMA-multicasts it to all of
+// them, so W crosses L2->SM once per cluster instead of once per CTA (the 128xBN tiles are L2-bandwidth
+// bound otherwise).  A slot is refilled only after every CTA of the cluster has consumed it: the MMA
+// warp's tcgen05.commit arrives on the "empty" barrier of all CL CTAs (multicast commit).
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmEpi epi, int M, int N, int K, int tiles_n, int num_tiles) {
@@ -68,6 +76,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkb = (K + BK - 1) / BK;  // K tail: TMA zero-fills columns >= K
+  // num_tiles counts cluster-level "super tiles" (CL m-blocks x 1 n-block); this CTA takes m-block
+  // (mg * CL + rank) of each.  Out-of-range m-blocks still take part in the multicast and barriers:
+  // their A rows are zero-filled by TMA and their stores are predicated off.
+  const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int first_tile = blockIdx.x / CL, tile_stride = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -75,7 +89,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full(s), 1);   // producer arrive + tx bytes
-      mbar_init(bar_empty(s), 1);  // tcgen05.commit
+      mbar_init(bar_empty(s), CL);  // tcgen05.commit of every CTA in the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);   // tcgen05.commit after the last k-block of a tile
@@ -83,9 +97,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     mbar_fence_init();
   }
+  __syncwarp();  // cluster barriers are .aligned: every warp must arrive converged
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers must exist before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();  // everything above overlapped the previous kernel; global memory is touched below
@@ -94,23 +109,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;  // k-blocks issued so far (ring position across tiles)
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      for (int t = first_tile; t < num_tiles; t += tile_stride) {
+        const int m0 = ((t / tiles_n) * CL + rank) * BM, n0 = (t % tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty(s), ((it / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full(s), L::STAGE_BYTES);
           const uint32_t sA = base + s * L::STAGE_BYTES;
           tma_load_2d(sA, &tmA, bar_full(s), kb * BK, m0);
-          tma_load_2d(sA + L::A_BYTES, &tmB, bar_full(s), kb * BK, n0);
+          if (CL == 1) {
+            tma_load_2d(sA + L::A_BYTES, &tmB, bar_full(s), kb * BK, n0);
+          } else {  // my 1/CL of the W tile, delivered to every CTA of the cluster
+            constexpr int SL = BN / CL;
+            tma_load_2d_mc(sA + L::A_BYTES + rank * (SL * BK * 2), &tmB, bar_full(s), kb * BK, n0 + rank * SL, kMask);
+          }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
     uint32_t it = 0, lt = 0;  // ring position, local tile counter
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+    for (int t = first_tile; t < num_tiles; t += tile_stride, ++lt) {
       const uint32_t buf = lt & 1;
       mbar_wait(bar_acc_empty(buf), ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
@@ -126,7 +147,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the swizzled row = +2 encoded
             tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          tc_commit(bar_empty(s));  // frees the stage when these MMAs retire
+          if (CL == 1) tc_commit(bar_empty(s));  // frees the stage when these MMAs retire
+          else tc_commit_mc(bar_empty(s), kMask);
           if (kb == nkb - 1) tc_commit(bar_acc_full(buf));
         }
         __syncwarp();
@@ -147,8 +169,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int sub_r = lane >> 3, c4 = lane & 7;
     constexpr int NCHUNK = BN / 32;
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
-      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+    for (int t = first_tile; t < num_tiles; t += tile_stride, ++lt) {
+      const int m0 = ((t / tiles_n) * CL + rank) * BM, n0 = (t % tiles_n) * BN;
       const uint32_t buf = lt & 1;
       const int row0 = m0 + q * 32;
       mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
@@ -207,7 +229,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     tc_fence_before();
   }
-  __syncthreads();
+  // no CTA may leave while a peer can still multicast into its shared memory / arrive on its barriers
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
@@ -216,27 +239,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
 static int g_num_sms = 0;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES>,
+  static int max_clusters = 0;  // co-resident clusters (1 CTA per SM)
+  if (max_clusters == 0) {
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
+    if (CL == 1) {
+      max_clusters = g_num_sms;
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(g_num_sms / CL * CL);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = L::TOTAL;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int n = 0;
+      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL>, &cfg));
+      MTN_REQUIRE(n > 0, MTN_E_CUDA, "linear: no cluster of %d CTAs fits on this device", CL);
+      max_clusters = n;
+    }
   }
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d_f16(&tmA, a.A, a.K, a.M, a.lda, BK, BM, TM_SWZ_128);
   if (rc) return rc;
-  rc = make_tmap_2d_f16(&tmB, a.W, a.K, a.N, a.ldw, BK, BN, TM_SWZ_128);
+  rc = make_tmap_2d_f16(&tmB, a.W, a.K, a.N, a.ldw, BK, BN / CL, TM_SWZ_128);
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
               reinterpret_cast<__half*>(a.out_f16), a.ld16};
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
-  const int num_tiles = tiles_n * tiles_m;
-  const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  MTN_CHECK_CUDA(launch_kernel(gemm_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, st, tmA,
-                               tmB, epi, a.M, a.N, a.K, tiles_n, num_tiles));
+  const int num_super = tiles_n * ((tiles_m + CL - 1) / CL);
+  const int clusters = num_super < max_clusters ? num_super : max_clusters;
+  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL>, dim3(clusters * CL), dim3(GEMM_THREADS),
+                                       L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K, tiles_n, num_super));
   return MTN_OK;
 }
 
@@ -298,9 +336,17 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
     mtn::g_num_sms = n;
   }
   // 128x256 tiles halve the operand bytes per FLOP; use them when they still fill the machine.
-  const long tiles256 = (long)((a->N + 255) / 256) * ((a->M + 127) / 128);
-  if (a->N >= 256 && tiles256 >= mtn::g_num_sms) return mtn::launch_gemm<256, 4>(*a, st);
-  return mtn::launch_gemm<128, 6>(*a, st);
+  // Clusters of 2 CTAs along M share each W tile through TMA multicast (MTN_B200_CLUSTER=1 disables).
+  static int cl = -1;
+  if (cl < 0) {
+    const char* e = getenv("MTN_B200_CLUSTER");
+    cl = e ? atoi(e) : 2;
+  }
+  const int tiles_m = (a->M + 127) / 128;
+  const long tiles256 = (long)((a->N + 255) / 256) * tiles_m;
+  const bool big = a->N >= 256 && tiles256 >= mtn::g_num_sms;
+  if (cl >= 2 && tiles_m >= 2) return big ? mtn::launch_gemm<256, 4, 2>(*a, st) : mtn::launch_gemm<128, 6, 2>(*a, st);
+  return big ? mtn::launch_gemm<256, 4, 1>(*a, st) : mtn::launch_gemm<128, 6, 1>(*a, st);
 }
 
 extern "C" int mtn_check_linear_fwd(const MtnLinearArgs* a, void* stream) {
