@@ -225,12 +225,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
 // ---------------------------------------------------------------------------
 // numeric helpers
 // ---------------------------------------------------------------------------
-// f32 pair -> packed f16x2, round-to-nearest-even, saturating (no inf from overflow).
+// f32 pair -> packed f16x2 (lo in bits 0-15), round-to-nearest-even, saturating to +-65504
+// (one F2FP.SATFINITE instruction; overflow never produces inf).
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
-  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 }  // namespace mtn

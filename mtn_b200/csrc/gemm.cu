@@ -166,31 +166,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int q = warp & 3;    // TMEM lane quarter this warp may access
     const int half = ew >> 2;  // 0: even chunks, 1: odd chunks
     float4* xp = reinterpret_cast<float4*>(smem + L::XPOSE_OFF + ew * STAGE_TILE_BYTES);
-    const int sub_r = lane >> 3, c4 = lane & 7;
+    const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
+    // shared-memory slots of the transpose tile (float4 units); (row & 7) == sub_r for every row this lane reads
+    const int wr_base = lane * 8, wr_sw = lane & 7;
+    const int rd0 = sub_r * 8 + ((2 * c8) ^ sub_r), rd1 = sub_r * 8 + ((2 * c8 + 1) ^ sub_r);
     uint32_t lt = 0;
     for (int t = first_tile; t < num_tiles; t += tile_stride, ++lt) {
       const int m0 = ((t / tiles_n) * CL + rank) * BM, n0 = (t % tiles_n) * BN;
       const uint32_t buf = lt & 1;
-      const int row0 = m0 + q * 32;
+      const int row0 = m0 + q * 32 + sub_r;  // this lane's first row; the others are +8, +16, +24
+      // per-row element offsets, hoisted out of the chunk loop
+      size_t off32[4], off16[4], offad[4];
+      bool row_ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row0 + i * 8;
+        row_ok[i] = r < M;
+        off32[i] = (size_t)r * epi.ld32;
+        off16[i] = (size_t)r * epi.ld16;
+        offad[i] = (size_t)(epi.add_period > 0 ? r % epi.add_period : r) * epi.ld_add;
+      }
       mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
-        const int col = n0 + c * 32 + c4 * 4;  // this lane's 4 columns in the coalesced phase
-        const bool col_ok = col < N;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (epi.bias != nullptr && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+        const int col = n0 + c * 32 + c8 * 8;  // this lane's 8 columns in the coalesced phase
+        const bool col_ok = col < N;           // N % 8 == 0: all 8 or none
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (epi.bias != nullptr && col_ok) {
+          b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+          b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + col + 4));
+        }
         float4 res[8];
-        if (epi.addend != nullptr) {
+        if (epi.addend != nullptr) {  // residual / positional operand: requested before touching TMEM
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = row0 + i * 4 + sub_r;
-            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < M && col_ok)
-              res[i] = *reinterpret_cast<const float4*>(
-                  epi.addend + (size_t)(epi.add_period > 0 ? r % epi.add_period : r) * epi.ld_add + col);
+          for (int i = 0; i < 4; ++i) {
+            res[2 * i] = res[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok[i] && col_ok) {
+              const float4* ap = reinterpret_cast<const float4*>(epi.addend + offad[i] + col);
+              res[2 * i] = ap[0];
+              res[2 * i + 1] = ap[1];
+            }
           }
         }
         uint32_t acc[32];
@@ -203,28 +221,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          xp[lane * 8 + (j ^ (lane & 7))] =
-              make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
-                          __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+          xp[wr_base + (j ^ wr_sw)] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                                  __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
         __syncwarp();
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + sub_r;
-          const int r = row0 + rl;
-          float4 v = xp[rl * 8 + (c4 ^ (rl & 7))];
-          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          if (epi.act == MTN_ACT_RELU) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          }
-          if (epi.addend != nullptr) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-          if (r < M && col_ok) {
-            if (epi.out32 != nullptr) *reinterpret_cast<float4*>(epi.out32 + (size_t)r * epi.ld32 + col) = v;
-            if (epi.out16 != nullptr)
-              *reinterpret_cast<uint2*>(epi.out16 + (size_t)r * epi.ld16 + col) =
-                  make_uint2(pack_f16x2_sat(v.x, v.y), pack_f16x2_sat(v.z, v.w));
-          }
+        for (int i = 0; i < 4; ++i) {  // all shared-memory reads first (independent of the global stores below)
+          v[2 * i] = xp[i * 64 + rd0];
+          v[2 * i + 1] = xp[i * 64 + rd1];
         }
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 x0 = v[2 * i], x1 = v[2 * i + 1];
+          x0.x += b0.x; x0.y += b0.y; x0.z += b0.z; x0.w += b0.w;
+          x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
+          if (epi.act == MTN_ACT_RELU) {
+            x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
+            x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
+          }
+          if (epi.addend != nullptr) {
+            x0.x += res[2 * i].x; x0.y += res[2 * i].y; x0.z += res[2 * i].z; x0.w += res[2 * i].w;
+            x1.x += res[2 * i + 1].x; x1.y += res[2 * i + 1].y; x1.z += res[2 * i + 1].z; x1.w += res[2 * i + 1].w;
+          }
+          if (row_ok[i] && col_ok) {
+            if (epi.out32 != nullptr) {
+              float4* o = reinterpret_cast<float4*>(epi.out32 + off32[i] + col);
+              o[0] = x0;
+              o[1] = x1;
+            }
+            if (epi.out16 != nullptr)
+              *reinterpret_cast<uint4*>(epi.out16 + off16[i] + col) =
+                  make_uint4(pack_f16x2_sat(x0.x, x0.y), pack_f16x2_sat(x0.z, x0.w), pack_f16x2_sat(x1.x, x1.y),
+                             pack_f16x2_sat(x1.z, x1.w));
+          }
+        }
       }
     }
     tc_fence_before();
