@@ -367,7 +367,9 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
     mtn::g_num_sms = n;
   }
   // 128x256 tiles halve the operand bytes per FLOP; use them when they still fill the machine.
-  // Clusters of 2 CTAs along M share each W tile through TMA multicast (MTN_B200_CLUSTER=1 disables).
+  // Wide GEMMs with many waves additionally run as clusters of 2 CTAs along M that share each W tile
+  // through TMA multicast (measured +3 %; on the small single-wave GEMMs clusters only constrain
+  // placement next to the other streams' kernels, so they stay unclustered).  MTN_B200_CLUSTER=1 disables.
   static int cl = -1;
   if (cl < 0) {
     const char* e = getenv("MTN_B200_CLUSTER");
@@ -376,7 +378,7 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
   const int tiles_m = (a->M + 127) / 128;
   const long tiles256 = (long)((a->N + 255) / 256) * tiles_m;
   const bool big = a->N >= 256 && tiles256 >= mtn::g_num_sms;
-  if (cl >= 2 && tiles_m >= 2) return big ? mtn::launch_gemm<256, 4, 2>(*a, st) : mtn::launch_gemm<128, 6, 2>(*a, st);
+  if (cl >= 2 && big && tiles256 >= 4L * mtn::g_num_sms) return mtn::launch_gemm<256, 4, 2>(*a, st);
   return big ? mtn::launch_gemm<256, 4, 1>(*a, st) : mtn::launch_gemm<128, 6, 1>(*a, st);
 }
 
