@@ -56,6 +56,29 @@ const char *mtn_last_error(void);
 int mtn_layernorm_fwd(const float *x, const float *a_2, const float *b_2, float eps,
                       int rows, int d, float *y_f32, void *y_f16, void *stream);
 
+/* ---- embeddings ----------------------------------------------
+ * Replaces Embeddings.forward (mtn.py:288-289) + PositionalEncoding.forward (mtn.py:307-309)
+ * and, when a_2/b_2 are given, the Encoder's per-stream LayerNorm (mtn.py:91, :96):
+ *     y[r, :] = LN?( lut[ids[r], :] * scale + pe[r % L, :] )
+ * ids: [rows] int64 (rows = B*L, position = r % L), lut: [vocab, d] f32, pe: [>=L, d] f32.   */
+int mtn_embed_fwd(const int64_t *ids, const float *lut, const float *pe, int rows, int L, int d,
+                  int vocab, float scale, const float *a_2, const float *b_2, float eps,
+                  float *y_f32, void *y_f16, void *stream);
+
+/* ---- video-feature preparation (boundary: Batch, data_utils.py:28-30) ----------------
+ * ft: [frames, F] f32 raw features.  mask[frame] = any(ft[frame, :] != 1.0) (all-ones frames are
+ * padding); padded frames are zeroed; output as f16 (video-encoder operand) and/or f32.        */
+int mtn_feature_prep_fwd(const float *ft, int frames, int F, uint8_t *mask, void *out_f16,
+                         float *out_f32, void *stream);
+
+/* ---- generator tail ---------------------------------------------
+ * Replaces F.log_softmax(proj(x), -1) (mtn.py:68-69) after mtn_linear_fwd produced the logits,
+ * and the arg-max of greedy decoding (data_utils.py:183).  x: [rows, ldx] f32, first V columns
+ * are the vocabulary; y (may alias x, may be NULL) receives log-probabilities; argmax (may be
+ * NULL) the first maximal index per row.                                                      */
+int mtn_log_softmax_fwd(const float *x, int ldx, int rows, int V, float *y, int ldy,
+                        int64_t *argmax, void *stream);
+
 /* ---- casts / packing -----------------------------------------------------------
  * dst[r, c] = (f16) src[r, c]  (round-to-nearest-even, saturating to +-65504).
  * Used to pack nn.Linear weights once per parameter version and to convert module

@@ -62,6 +62,11 @@ SYMBOLS = {
     "mtn_last_error": (C.c_char_p, []),
     "mtn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_embed_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_feature_prep_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_log_softmax_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
     "mtn_cast_f32_to_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p]),
     "mtn_mask_words": (C.c_int, [C.c_int]),
@@ -240,3 +245,46 @@ def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=Fal
     fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
     _launch("attn_core", 4 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (2 * Lq + 2 * Lk),
             lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits))
+
+
+def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None):
+    """ids: [B, L] int64; lut: [vocab, d] f32; pe: [>=L, d] f32 (the table, 2-D).  Returns / fills
+    [B, L, d] = LN?(lut[ids] * scale + pe[:L]);  ln = (a_2, b_2, eps) or None."""
+    assert ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_cuda
+    _req(lut, torch.float32, "lut"); _req(pe, torch.float32, "pe")
+    _req(out_f32, torch.float32, "out_f32"); _req(out_f16, torch.float16, "out_f16")
+    B, L = ids.shape
+    d = lut.shape[1]
+    idc = ids.contiguous()
+    assert pe.dim() == 2 and pe.shape[0] >= L and pe.is_contiguous() and lut.is_contiguous()
+    a2, b2, eps = ln if ln is not None else (None, None, 0.0)
+    _launch("embed", 0, B * L * d * (8 + (4 if out_f32 is not None else 0) + (2 if out_f16 is not None else 0)),
+            lambda: lib().mtn_embed_fwd(ptr(idc), ptr(lut), ptr(pe), B * L, L, d, lut.shape[0], float(scale), ptr(a2),
+                                        ptr(b2), float(eps), ptr(out_f32), ptr(out_f16), stream_ptr()),
+            keep=(idc, lut, pe, a2, b2, out_f32, out_f16))
+
+
+def feature_prep(ft, out_f16=None, out_f32=None):
+    """ft: [B, L, F] f32 raw features -> (mask bool [B, 1, L], out).  Frames that are all 1.0 are padding
+    (data_utils.py:29) and are zeroed (data_utils.py:30)."""
+    _req(ft, torch.float32, "ft")
+    ftc = ft.contiguous()
+    B, L, F = ftc.shape
+    mask = torch.empty(B, 1, L, dtype=torch.bool, device=ft.device)
+    if out_f16 is None and out_f32 is None:
+        out_f16 = torch.empty(B, L, F, dtype=torch.float16, device=ft.device)
+    _launch("feature_prep", 0, B * L * F * (4 + (2 if out_f16 is not None else 0) + (4 if out_f32 is not None else 0)),
+            lambda: lib().mtn_feature_prep_fwd(ptr(ftc), B * L, F, ptr(mask), ptr(out_f16), ptr(out_f32), stream_ptr()),
+            keep=(ftc, mask, out_f16, out_f32))
+    return mask, (out_f16 if out_f16 is not None else out_f32)
+
+
+def log_softmax(x, V, out=None, argmax=None):
+    """x: [rows, ld>=V] f32 logits.  out: [rows, V] f32 log-probs (or None); argmax: [rows] int64 (or None)."""
+    _req(x, torch.float32, "x"); _req(out, torch.float32, "out")
+    assert x.dim() == 2 and (out is None or (out.dim() == 2 and out.shape[0] == x.shape[0]))
+    assert argmax is None or (argmax.dtype == torch.int64 and argmax.is_contiguous())
+    _launch("log_softmax", 0, x.shape[0] * V * 8,
+            lambda: lib().mtn_log_softmax_fwd(ptr(x), x.stride(0), x.shape[0], V, ptr(out),
+                                              out.stride(0) if out is not None else 0, ptr(argmax), stream_ptr()),
+            keep=(x, out, argmax))

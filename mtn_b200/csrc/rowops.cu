@@ -136,6 +136,154 @@ __global__ void mask_pack_kernel(const uint8_t* __restrict__ m, int nrows, int L
   if ((threadIdx.x & 31) == 0) bits[w] = b;
 }
 
+// ----------------------------------------------------------------------------
+// Embedding * sqrt(d) + positional encoding (+ optional stream LayerNorm), one warp per token.
+// Replaces Embeddings.forward (mtn.py:288-289), PositionalEncoding.forward (mtn.py:307-309) and,
+// when a_2 != NULL, the Encoder's per-stream LayerNorm (mtn.py:91/96) in one pass.
+// ----------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+    embed_rows_kernel(const long long* __restrict__ ids, const float* __restrict__ lut, const float* __restrict__ pe,
+                      int rows, int L, int vocab, float scale, const float* __restrict__ a2,
+                      const float* __restrict__ b2, float eps, float* __restrict__ y32, __half* __restrict__ y16) {
+  constexpr int D = 128 * VPL;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  long long id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);  // clamp instead of faulting on a bad id
+  const float4* er = reinterpret_cast<const float4*>(lut + (size_t)id * D);
+  const float4* pr = reinterpret_cast<const float4*>(pe + (size_t)(row % L) * D);
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 e = __ldg(er + lane + 32 * i), p = __ldg(pr + lane + 32 * i);
+    v[i] = make_float4(e.x * scale + p.x, e.y * scale + p.y, e.z * scale + p.z, e.w * scale + p.w);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  float inv = 1.f;
+  if (a2 != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / D);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    inv = 1.f / (sqrtf(ss * (1.f / (D - 1))) + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 o = v[i];
+    if (a2 != nullptr) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(a2) + c4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(b2) + c4);
+      o = make_float4(a.x * o.x * inv + b.x, a.y * o.y * inv + b.y, a.z * o.z * inv + b.z, a.w * o.w * inv + b.w);
+    }
+    if (y32) reinterpret_cast<float4*>(y32 + (size_t)row * D)[c4] = o;
+    if (y16)
+      reinterpret_cast<uint2*>(y16 + (size_t)row * D)[c4] = make_uint2(pack_f16x2_sat(o.x, o.y), pack_f16x2_sat(o.z, o.w));
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Video-feature preparation, one warp per frame: a frame whose F elements are all exactly 1.0 is
+// padding (data_utils.py:29) and is zeroed (data_utils.py:30); the surviving frames are converted to
+// the f16 tensor-core operand of the video encoder.  One read of the raw features instead of the
+// reference's compare / reduce / multiply passes plus a cast.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    feature_prep_kernel(const float* __restrict__ ft, int frames, int F, uint8_t* __restrict__ mask,
+                        __half* __restrict__ out16, float* __restrict__ out32) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= frames) return;
+  const int lane = threadIdx.x & 31;
+  const float4* fr = reinterpret_cast<const float4*>(ft + (size_t)row * F);
+  const int n4 = F >> 2;
+  bool any = false;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = __ldg(fr + i);
+    any |= (v.x != 1.f) | (v.y != 1.f) | (v.z != 1.f) | (v.w != 1.f);
+  }
+  const bool keep = __any_sync(0xffffffffu, any);
+  if (lane == 0) mask[row] = keep ? 1 : 0;
+  for (int i = lane; i < n4; i += 32) {  // second pass hits L1/L2 (a frame is at most 8 KB)
+    float4 v = __ldg(fr + i);
+    if (!keep) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (out16)
+      reinterpret_cast<uint2*>(out16 + (size_t)row * F)[i] = make_uint2(pack_f16x2_sat(v.x, v.y), pack_f16x2_sat(v.z, v.w));
+    if (out32) reinterpret_cast<float4*>(out32 + (size_t)row * F)[i] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Row-wise log-softmax over the first V columns (Generator, mtn.py:68-69) and row arg-max
+// (greedy decoding, data_utils.py:183).  One 128-thread block per row.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_128(float v, bool is_max, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+#pragma unroll
+  for (int w = 1; w < 4; ++w) r = is_max ? fmaxf(r, sh[w]) : r + sh[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(128)
+    log_softmax_rows_kernel(const float* __restrict__ x, int ldx, int V, float* __restrict__ y, int ldy,
+                            long long* __restrict__ argmax) {
+  __shared__ float sh[4];
+  __shared__ int shi[4];
+  pdl_launch_dependents();
+  pdl_wait();
+  const float* xr = x + (size_t)blockIdx.x * ldx;
+  float mx = -3.4e38f;
+  int mi = 0;
+  for (int i = threadIdx.x; i < V; i += 128) {
+    const float v = xr[i];
+    if (v > mx) { mx = v; mi = i; }
+  }
+  if (argmax != nullptr) {  // first maximal index, like torch.max / argmax
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float tv = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int ti = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (tv > mx || (tv == mx && ti < mi)) { mx = tv; mi = ti; }
+    }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = mx; shi[threadIdx.x >> 5] = mi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float bv = sh[0]; int bi = shi[0];
+      for (int w = 1; w < 4; ++w) if (sh[w] > bv || (sh[w] == bv && shi[w] < bi)) { bv = sh[w]; bi = shi[w]; }
+      argmax[blockIdx.x] = bi;
+    }
+    __syncthreads();
+  }
+  const float m = block_reduce_128(mx, true, sh);
+  if (y == nullptr) return;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += 128) s += __expf(xr[i] - m);
+  const float lse = m + __logf(block_reduce_128(s, false, sh));
+  float* yr = y + (size_t)blockIdx.x * ldy;
+  for (int i = threadIdx.x; i < V; i += 128) yr[i] = xr[i] - lse;
+}
+
 }  // namespace mtn
 
 extern "C" int mtn_layernorm_fwd(const float* x, const float* a_2, const float* b_2, float eps, int rows,
@@ -190,5 +338,47 @@ extern "C" int mtn_mask_pack(const uint8_t* mask_u8, int B, int rows_q, int Lk, 
   MTN_CHECK_CUDA(launch_kernel(mask_pack_kernel, dim3((unsigned)((nw + 7) / 8)), dim3(256), 0,
                                static_cast<cudaStream_t>(stream), mask_u8, B * rows_q, Lk, words, bits));
   MTN_CHECK_CUDA(cudaGetLastError());
+  return MTN_OK;
+}
+
+extern "C" int mtn_embed_fwd(const int64_t* ids, const float* lut, const float* pe, int rows, int L, int d, int vocab,
+                             float scale, const float* a_2, const float* b_2, float eps, float* y_f32, void* y_f16,
+                             void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(ids && lut && pe && (y_f32 || y_f16), MTN_E_ARG, "embed: NULL pointer");
+  MTN_REQUIRE((a_2 == nullptr) == (b_2 == nullptr), MTN_E_ARG, "embed: a_2 and b_2 must be given together");
+  MTN_REQUIRE(rows > 0 && L > 0 && vocab > 0, MTN_E_SHAPE, "embed: rows=%d L=%d vocab=%d", rows, L, vocab);
+  MTN_REQUIRE(d == 128 || d == 256 || d == 512 || d == 1024, MTN_E_SHAPE, "embed: d=%d (supported: 128, 256, 512, 1024)", d);
+  MTN_REQUIRE(aligned16(lut) && aligned16(pe) && (!y_f32 || aligned16(y_f32)) && (!y_f16 || aligned16(y_f16)) &&
+                  (!a_2 || (aligned16(a_2) && aligned16(b_2))), MTN_E_ALIGN, "embed: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* y16 = reinterpret_cast<__half*>(y_f16);
+  const long long* ids64 = reinterpret_cast<const long long*>(ids);
+  dim3 grid((rows + 7) / 8), block(256);
+#define MTN_EMBED(V) MTN_CHECK_CUDA(launch_kernel(embed_rows_kernel<V>, grid, block, 0, st, ids64, lut, pe, rows, L, vocab, scale, a_2, b_2, eps, y_f32, y16))
+  if (d == 128) MTN_EMBED(1); else if (d == 256) MTN_EMBED(2); else if (d == 512) MTN_EMBED(4); else MTN_EMBED(8);
+#undef MTN_EMBED
+  return MTN_OK;
+}
+
+extern "C" int mtn_feature_prep_fwd(const float* ft, int frames, int F, uint8_t* mask, void* out_f16, float* out_f32,
+                                    void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(ft && mask && (out_f16 || out_f32), MTN_E_ARG, "feature_prep: NULL pointer");
+  MTN_REQUIRE(frames > 0 && F > 0 && F % 4 == 0, MTN_E_SHAPE, "feature_prep: frames=%d F=%d (F %% 4 == 0)", frames, F);
+  MTN_REQUIRE(aligned16(ft) && (!out_f16 || aligned16(out_f16)) && (!out_f32 || aligned16(out_f32)) && (F % 8 == 0 || !out_f16),
+              MTN_E_ALIGN, "feature_prep: alignment");
+  MTN_CHECK_CUDA(launch_kernel(feature_prep_kernel, dim3((frames + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                               ft, frames, F, mask, reinterpret_cast<__half*>(out_f16), out_f32));
+  return MTN_OK;
+}
+
+extern "C" int mtn_log_softmax_fwd(const float* x, int ldx, int rows, int V, float* y, int ldy, int64_t* argmax,
+                                   void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(x && (y || argmax), MTN_E_ARG, "log_softmax: NULL pointer");
+  MTN_REQUIRE(rows > 0 && V > 0 && ldx >= V && (!y || ldy >= V), MTN_E_SHAPE, "log_softmax: rows=%d V=%d ldx=%d ldy=%d", rows, V, ldx, ldy);
+  MTN_CHECK_CUDA(launch_kernel(log_softmax_rows_kernel, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), x, ldx, V,
+                               y, ldy, reinterpret_cast<long long*>(argmax)));
   return MTN_OK;
 }

@@ -38,9 +38,16 @@ class Batch:
             dev = _default_device(query)
             permuted = [(torch.from_numpy(ft) if isinstance(ft, np.ndarray) else ft).float().to(dev)
                         .permute(1, 0, 2) for ft in fts]
-            self.fts_mask = [(torch.sum(ft != 1, dim=2) != 0).unsqueeze(-2) for ft in permuted]
-            self.fts = [ft * self.fts_mask[i].squeeze(1).unsqueeze(-1).float()
-                        for i, ft in enumerate(permuted)]
+            if dev.type == "cuda" and all(ft.shape[2] % 8 == 0 for ft in permuted):
+                # one pass per modality: padding mask + zeroing + f16 operand of the video encoder
+                from . import _lib
+                prepped = [_lib.feature_prep(ft) for ft in permuted]
+                self.fts_mask = [m for m, _ in prepped]
+                self.fts = [f for _, f in prepped]          # f16 on the CUDA path (f32 in the reference)
+            else:
+                self.fts_mask = [(torch.sum(ft != 1, dim=2) != 0).unsqueeze(-2) for ft in permuted]
+                self.fts = [ft * self.fts_mask[i].squeeze(1).unsqueeze(-1).float()
+                            for i, ft in enumerate(permuted)]
         else:
             self.fts = None
             self.fts_mask = None
@@ -88,8 +95,12 @@ def greedy_decode(model, batch, max_len, start_symbol, pad_symbol=None):
         out = model.decode(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask,
                            batch.cap_mask, batch.query_mask, ys,
                            subsequent_mask(ys.size(1), ys.device), ae_ft)
-        prob = model.generator(out[0][:, -1])
-        ys = torch.cat([ys, prob.argmax(dim=1, keepdim=True)], dim=1)
+        last = out[0][:, -1]
+        if hasattr(model.generator, "argmax"):
+            nxt = model.generator.argmax(last).unsqueeze(1)
+        else:
+            nxt = model.generator(last).argmax(dim=1, keepdim=True)
+        ys = torch.cat([ys, nxt.to(ys.dtype)], dim=1)
     return ys
 
 

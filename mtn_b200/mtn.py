@@ -354,14 +354,45 @@ class Encoder(nn.Module):
 
 
 class Generator(nn.Module):
-    """Reference mtn.py:62-69 (stays PyTorch this round)."""
+    """Reference mtn.py:62-69: log_softmax(proj(x)).  SURVEY 8f row f2: the projection runs on the
+    tcgen05 linear kernel (vocabulary padded to a multiple of 8 rows), followed by a row
+    log-softmax kernel; ``argmax`` skips the log-softmax for greedy decoding (data_utils.py:183)."""
 
     def __init__(self, d_model, vocab):
         super(Generator, self).__init__()
         self.proj = nn.Linear(d_model, vocab)
+        self._packed = PackedWeights()
+
+    def _logits(self, x):
+        V, d = self.proj.weight.shape
+        V8 = (V + 7) // 8 * 8
+
+        def build():
+            w = torch.zeros(V8, d, dtype=torch.float32, device=self.proj.weight.device)
+            w[:V] = self.proj.weight.data
+            b = torch.zeros(V8, dtype=torch.float32, device=w.device)
+            b[:V] = self.proj.bias.data
+            return {"w": _lib.cast_f16(w), "b": b}
+        W = self._packed.get(list(self.proj.parameters()), build)
+        x16 = _lib.cast_f16(x.contiguous().float().view(-1, d))
+        logits = torch.empty(x16.shape[0], V8, dtype=torch.float32, device=x.device)
+        _lib.linear(x16, W["w"], W["b"], out_f32=logits)
+        return logits, V
 
     def forward(self, x):
-        return F.log_softmax(self.proj(x), dim=-1)
+        ensure_inference(self, x)
+        logits, V = self._logits(x)
+        out = torch.empty(logits.shape[0], V, dtype=torch.float32, device=x.device)
+        _lib.log_softmax(logits, V, out=out)
+        return out.view(*x.shape[:-1], V)
+
+    def argmax(self, x):
+        """argmax_v log_softmax(proj(x))[..., v] without materialising the log-probabilities."""
+        ensure_inference(self, x)
+        logits, V = self._logits(x)
+        idx = torch.empty(logits.shape[0], dtype=torch.int64, device=x.device)
+        _lib.log_softmax(logits, V, argmax=idx)
+        return idx.view(*x.shape[:-1])
 
 
 class Embeddings(nn.Module):
@@ -409,7 +440,10 @@ class VideoEncoder(nn.Sequential):
         B, Lv, Fdim = ft.shape
         W = self._packed.get(list(lin.parameters()),
                              lambda: {"w": _lib.cast_f16(lin.weight.data.contiguous()), "b": lin.bias.data})
-        x16 = _lib.cast_f16(ft.contiguous().float().view(B * Lv, Fdim))
+        if ft.dtype == torch.float16:      # Batch already produced the masked f16 operand (feature_prep kernel)
+            x16 = ft.contiguous().view(B * Lv, Fdim)
+        else:
+            x16 = _lib.cast_f16(ft.contiguous().float().view(B * Lv, Fdim))
         out = torch.empty(B * Lv, lin.out_features, dtype=torch.float32, device=ft.device)
         _lib.linear(x16, W["w"], W["b"], act=_lib.ACT_RELU, addend=pos.pe[0, :Lv], add_period=Lv,
                     out_f32=out)
@@ -447,8 +481,42 @@ class EncoderDecoder(nn.Module):
     def vid_encode(self, video_features, video_features_mask, encoded_query=None):
         return [self.vid_encoder[i](ft) for i, ft in enumerate(video_features)]
 
+    def _embed(self, seq, ids, norm=None):
+        """``seq`` = nn.Sequential(Embeddings, PositionalEncoding) applied to ids, optionally followed by
+        the Encoder's stream LayerNorm ``norm`` -- one fused kernel."""
+        emb, pos = seq[0], seq[1]
+        ensure_inference(self, emb.lut.weight.data)
+        B, L = ids.shape
+        out = torch.empty(B, L, emb.d_model, dtype=torch.float32, device=ids.device)
+        ln = None if norm is None else (norm.a_2.data, norm.b_2.data, norm.eps)
+        _lib.embed(ids, emb.lut.weight.data, pos.pe[0], math.sqrt(emb.d_model), ln=ln, out_f32=out)
+        return out
+
+    def _fused_embed_ok(self):
+        return (isinstance(self.query_embed, nn.Sequential) and len(self.query_embed) == 2 and
+                isinstance(self.query_embed[0], Embeddings) and self.query_embed[0].d_model in (128, 256, 512, 1024)
+                and self.query_embed[0].lut.weight.is_cuda)
+
     def encode(self, query, query_mask, his=None, his_mask=None, cap=None, cap_mask=None, vid=None,
                vid_mask=None):
+        if self._fused_embed_ok():
+            # same streams / LayerNorm order as Encoder.forward (mtn.py:83-101): query, vid_0.., cap, his, ae_0..
+            nrm, M = self.query_encoder.norm, len(vid)
+            q_mem = self._embed(self.query_embed, query, nrm[0])
+            vid_mem = [nrm[1 + i](v) for i, v in enumerate(self.vid_encode(vid, vid_mask))]
+            cap_mem = self._embed(self.query_embed, cap, nrm[1 + M])
+            his_mem = self._embed(self.query_embed, his, nrm[2 + M])
+            if not self.diff_encoder:
+                return [q_mem, vid_mem, cap_mem, his_mem, None]
+            if self.auto_encoder_ft in ('caption', 'summary'):
+                ft = cap
+            elif self.auto_encoder_ft == 'query':
+                ft = query
+            else:
+                raise ValueError("auto_encoder_ft must be 'query', 'caption' or 'summary'")
+            ae_mem = [self._embed(self.auto_encoder_embed[i] if self.auto_encoder_embed is not None
+                                  else self.query_embed, ft, nrm[3 + M + i]) for i in range(M)]
+            return [q_mem, vid_mem, cap_mem, his_mem, ae_mem]
         if self.diff_encoder:
             if self.auto_encoder_ft in ('caption', 'summary'):
                 ft = cap
@@ -469,7 +537,8 @@ class EncoderDecoder(nn.Module):
 
     def decode(self, encoded_vid_features, his_memory, cap_memory, query_memory, vid_features_mask,
                his_mask, cap_mask, query_mask, tgt, tgt_mask, auto_encoded_ft):
-        return self.decoder(encoded_vid_features, vid_features_mask, self.tgt_embed(tgt), his_memory,
+        x = self._embed(self.tgt_embed, tgt) if self._fused_embed_ok() else self.tgt_embed(tgt)
+        return self.decoder(encoded_vid_features, vid_features_mask, x, his_memory,
                             his_mask, cap_memory, cap_mask, query_memory, query_mask, tgt_mask,
                             auto_encoded_ft, self.auto_encoder_ft)
 

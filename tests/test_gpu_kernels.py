@@ -243,3 +243,70 @@ def test_attn_kat(L):
                     1, 1, 1, 3, 32, out, mask_bits=L.mask_pack(dev(mask)))
         torch.cuda.synchronize()
         assert np.allclose(out.float().cpu().numpy()[0, :2], z["attn_%s_o" % name][0], atol=3e-3)
+
+
+# ------------------------------------------------------------------ next rows: f1/f2/f4 kernels
+@pytest.mark.parametrize("d,with_ln", [(128, False), (512, True), (1024, True), (256, False)])
+def test_embed(L, d, with_ln):
+    g = torch.Generator().manual_seed(d)
+    V, B, Ls = 50, 3, 11
+    sd = {"e.0.lut.weight": torch.randn(V, d, generator=g), "e.1.pe": O.sinusoid_pe(d)}
+    ids = torch.randint(0, V, (B, Ls), generator=g)
+    ref = O.embed(sd, "e.", ids, d)
+    a = 1 + 0.1 * torch.randn(d, generator=g); b = 0.1 * torch.randn(d, generator=g)
+    if with_ln:
+        ref = O.layer_norm(ref, a, b, 1e-6)
+    out = torch.empty(B, Ls, d, device="cuda")
+    out16 = torch.empty(B, Ls, d, device="cuda", dtype=torch.float16)
+    L.embed(dev(ids), dev(sd["e.0.lut.weight"]), dev(sd["e.1.pe"][0]), d ** 0.5,
+            ln=(dev(a), dev(b), 1e-6) if with_ln else None, out_f32=out, out_f16=out16)
+    torch.cuda.synchronize()
+    assert G.rel_err(out.cpu(), ref) < 2e-6
+    assert G.rel_err(out16.float().cpu(), ref) < 6e-4
+
+
+def test_feature_prep(L):
+    g = torch.Generator().manual_seed(3)
+    ft = torch.randn(4, 37, 128, generator=g)
+    ft[1, 20:] = 1.0; ft[3, :] = 1.0; ft[2, 5, :64] = 1.0       # partial ones are NOT padding
+    m = O.make_masks(torch.zeros(4, 1, dtype=torch.long), torch.zeros(4, 1, dtype=torch.long),
+                     torch.zeros(4, 1, dtype=torch.long), None, [ft], 1)
+    mask, out16 = L.feature_prep(dev(ft))
+    out32 = torch.empty(4, 37, 128, device="cuda")
+    mask2, _ = L.feature_prep(dev(ft), out_f32=out32)
+    torch.cuda.synchronize()
+    assert torch.equal(mask.cpu(), m["fts_mask"][0]) and torch.equal(mask2.cpu(), m["fts_mask"][0])
+    assert torch.equal(out32.cpu(), m["fts"][0])
+    assert torch.equal(out16.cpu(), m["fts"][0].half())
+
+
+@pytest.mark.parametrize("rows,V", [(5, 3000), (33, 100), (2, 7)])
+def test_log_softmax_argmax(L, rows, V):
+    g = torch.Generator().manual_seed(V)
+    ld = (V + 7) // 8 * 8
+    x = torch.randn(rows, ld, generator=g) * 4
+    x[0, 1] = x[0, 2] = 50.0                         # tie -> first index
+    xd = dev(x)
+    out = torch.empty(rows, V, device="cuda"); idx = torch.empty(rows, dtype=torch.int64, device="cuda")
+    L.log_softmax(xd, V, out=out, argmax=idx)
+    torch.cuda.synchronize()
+    ref = torch.log_softmax(x[:, :V].double(), -1).float()
+    assert float((out.cpu() - ref).abs().max()) < 2e-5
+    assert torch.equal(idx.cpu(), x[:, :V].argmax(-1))
+    assert int(idx[0]) == 1
+
+
+def test_generator_module(L):
+    from mtn_b200 import mtn
+    g = torch.Generator().manual_seed(1)
+    sd = {"generator.proj.weight": torch.randn(100, 128, generator=g) * 0.2, "generator.proj.bias": torch.randn(100, generator=g)}
+    gen = mtn.Generator(128, 100)
+    gen.load_state_dict({"proj.weight": sd["generator.proj.weight"], "proj.bias": sd["generator.proj.bias"]})
+    gen = gen.cuda().eval()
+    x = torch.randn(2, 9, 128, generator=g)
+    ref = O.generator(sd, x)
+    with torch.no_grad():
+        out = gen(dev(x)); am = gen.argmax(dev(x))
+    assert out.shape == (2, 9, 100)
+    assert float((out.cpu() - ref).abs().max()) < 2e-2          # f16 operands: abs error on log-probs
+    assert float((am.cpu() == ref.argmax(-1)).float().mean()) >= 0.9
