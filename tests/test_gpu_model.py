@@ -148,7 +148,7 @@ def test_layer_path_equals_engine_path_and_oracle(M):
         out_e, ae_e = model.forward(b)
         q, vid, cap, his, ae0 = model.encode(b.query, b.query_mask, b.his, b.his_mask, b.cap, b.cap_mask,
                                              b.fts, b.fts_mask)
-        x = model.tgt_embed(b.trg)
+        x = model._embed(model.tgt_embed, b.trg)      # same fused embedding kernel as model.decode
         aes = ae0
         for layer in model.decoder.layers:
             x, aes = layer(x, cap, b.cap_mask, his, b.his_mask, q, b.query_mask, b.trg_mask, vid, b.fts_mask,
