@@ -236,3 +236,40 @@ def test_loud_failures(M):
     ln = ln.cuda().train()
     with pytest.raises(NotImplementedError):
         ln(torch.zeros(2, 128, device="cuda", requires_grad=True))
+
+
+def test_cfg4_decode_graphs_token_exact(M, cfg2_model):
+    """BASELINE configs[3]: batched greedy decoding with the 6-layer d=512 model, 10-turn history (H=256),
+    target length 20 -- CUDA-graph decoder vs eager greedy_decode (bit-identical schedule) and vs the CPU
+    oracle's full-recompute greedy on 2 dialogues (token-exact; generator scaled x8 for realistic margins,
+    SURVEY 8d cfg4)."""
+    mtn, du = M
+    from mtn_b200.graph import GraphedGreedyDecoder
+    cfg, model = cfg2_model
+    w0 = model.generator.proj.weight.data.clone()
+    model.generator.proj.weight.data.mul_(8.0)
+    try:
+        B, steps = 8, 20
+        inp = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=4, Lv=[512, 256], seed=77)
+        d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
+             if k in ("query", "his", "cap", "fts")}
+        dec = GraphedGreedyDecoder(model, d, steps)
+        ys_g = dec.decode().clone()
+        b = du.Batch(d["query"], d["his"], None, [f.permute(1, 0, 2) for f in d["fts"]], d["cap"], None, None, 1)
+        with torch.no_grad():
+            ys_e = du.greedy_decode(model, b, steps, 2)
+        assert torch.equal(ys_g, ys_e)
+        # second batch through the same graphs (static buffers refreshed)
+        inp2 = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=4, Lv=[512, 256], seed=78)
+        dec.copy_inputs({k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp2.items()})
+        ys2 = dec.decode().clone()
+        assert not torch.equal(ys2, ys_g)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        sel = [0, 2]
+        ref = O.greedy_decode(sd, cfg, inp["query"][sel], inp["his"][sel], inp["cap"][sel],
+                              [f[sel] for f in inp["fts"]], steps)
+        agree = (ys_g[sel].cpu() == ref).float().mean().item()
+        print("cfg4 greedy tokens vs oracle:", ys_g[sel].cpu().tolist(), ref.tolist())
+        assert torch.equal(ys_g[sel].cpu(), ref), agree
+    finally:
+        model.generator.proj.weight.data.copy_(w0)
