@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--rot", type=int, default=4, help="distinct input batches rotated through")
     ap.add_argument("--cpu-batch", type=int, default=4, help="dialogues in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the auxiliary greedy-decode (configs[3]) leg")
+    ap.add_argument("--decode-batch", type=int, default=64)
+    ap.add_argument("--decode-len", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -347,6 +350,39 @@ def main():
     if ln:
         breakdown["layernorm"]["hbm_frac"] = round(ln["bytes"] / (ln["ms"] * 1e-3) / 1e9 / hbm, 3)
 
+    # ------------------------------------------------------------- auxiliary: greedy decode (configs[3])
+    # batch 64 dialogues, 10-turn history (H=256), target length 20, CUDA-graph decoder; timed end to end
+    # per dialogue batch: pinned-host inputs -> device, prefill (encode + memory stage) + 19 steps, tokens -> host.
+    decode = None
+    if not args.no_decode:
+        from mtn_b200.graph import GraphedGreedyDecoder
+        del graphs, slots
+        torch.cuda.empty_cache()
+        Bd, Ld = args.decode_batch, args.decode_len
+        dh = [O.synth_inputs(CFG, B=Bd, Q=SHAPE["Q"], C=SHAPE["C"], H=SHAPE["H"], T=4, Lv=SHAPE["Lv"],
+                             seed=5000 + 10 * rank + r) for r in range(2)]
+        dh = [{k: (pin(v) if torch.is_tensor(v) else [pin(f) for f in v]) for k, v in h.items()
+               if k in ("query", "his", "cap", "fts")} for h in dh]
+        dec = GraphedGreedyDecoder(model, {k: (v.to(dev) if torch.is_tensor(v) else [f.to(dev) for f in v])
+                                           for k, v in dh[0].items()}, Ld)
+        toks_host = torch.empty(Bd, Ld, dtype=torch.int64).pin_memory()
+        reps = 5
+        for i in range(2):
+            dec.copy_inputs(dh[i % 2]); toks_host.copy_(dec.decode(), non_blocking=True)
+        barrier()
+        e0.record()
+        for i in range(reps):
+            dec.copy_inputs(dh[i % 2])
+            toks_host.copy_(dec.decode(), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_dec = max_over_ranks(e0.elapsed_time(e1)) / reps
+        decode = {"workload": "BASELINE configs[3]: greedy decode, batch %d/GPU, 10-turn history (H=256), target len %d, "
+                              "N=6 d=512; memory stage once per batch, %d graph-replayed steps" % (Bd, Ld, Ld - 1),
+                  "generated_tokens_per_s": sum_over_ranks(Bd * (Ld - 1)) / (ms_dec * 1e-3), "ms_per_batch": ms_dec,
+                  "includes": "H2D of ids+features, encode, memory stage, all steps, D2H of tokens"}
+        del dec
+
     # ------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -371,7 +407,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "tokens_per_step_per_gpu": sum(ntok) / len(ntok),
                 "model_tflops": fl * world / (ms / args.steps * 1e-3) / 1e12, "gflop_per_step_per_gpu": fl / 1e9,
-                "kernel_breakdown_one_step": breakdown}
+                "kernel_breakdown_one_step": breakdown, "decode": decode}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
