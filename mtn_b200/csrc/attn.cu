@@ -35,8 +35,8 @@ struct AttnCfg {
   static constexpr int Q_BYTES = ATT_QT * ROWB;
   static constexpr int KV_BYTES = ATT_KT * ROWB;
   static constexpr int P_BYTES = ATT_QT * ATT_KT * 2;  // [128 x 64] f16 panels (KT/64 of them)
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_Q = 0;  // two Q buffers: the next work item's queries load during this one
+  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_BYTES;
   static constexpr int OFF_P = OFF_V + KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
@@ -48,6 +48,7 @@ struct AttnCfg {
 };
 
 struct AttnParams {
+  int n_items, nqt;  // work items = B * h * nqt, ordered (b, head, q-tile) with the q-tile fastest
   const uint32_t* mask_bits;
   int mask_rows_q;
   int mask_words;
@@ -58,8 +59,8 @@ struct AttnParams {
 };
 
 enum {
-  BAR_Q_FULL = 0, BAR_K_FULL, BAR_K_EMPTY, BAR_V_FULL, BAR_V_EMPTY, BAR_S_FULL, BAR_S_FREE,
-  BAR_P_FULL, BAR_PV_DONE, BAR_COUNT
+  BAR_Q_FULL = 0 /* +1 */, BAR_Q_EMPTY = 2 /* +1 */, BAR_K_FULL = 4, BAR_K_EMPTY, BAR_V_FULL, BAR_V_EMPTY,
+  BAR_S_FULL, BAR_S_FREE, BAR_P_FULL, BAR_PV_DONE, BAR_COUNT
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -85,8 +86,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, hd = blockIdx.y, b = blockIdx.z;
   const int nt = (p.Lk + ATT_KT - 1) / ATT_KT;
+  // Persistent CTA: work items it = blockIdx.x, += gridDim.x.  All barrier phases run on global
+  // counters (item counter `n` for the Q buffers, tile counter `g` for everything else), so the
+  // producer streams the next item's Q / K / V while the current item is still in softmax / PV.
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -108,194 +111,211 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   if (warp == 0) {
     // -------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar(BAR_Q_FULL), C::Q_BYTES);
-      tma_load_3d(sQ, &tmQ, bar(BAR_Q_FULL), hd * DK, qt * ATT_QT, b);
-      for (int j = 0; j < nt; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(bar(BAR_K_EMPTY), ph ^ 1);
-        mbar_arrive_expect_tx(bar(BAR_K_FULL), C::KV_BYTES);
-        tma_load_3d(sK, &tmK, bar(BAR_K_FULL), hd * DK, j * ATT_KT, b);
-        mbar_wait(bar(BAR_V_EMPTY), ph ^ 1);
-        mbar_arrive_expect_tx(bar(BAR_V_FULL), C::KV_BYTES);
-        tma_load_3d(sV, &tmV, bar(BAR_V_FULL), hd * DK, j * ATT_KT, b);
+      uint32_t n = 0, g = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++n) {
+        const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
+        const uint32_t qb = n & 1;
+        mbar_wait(bar(BAR_Q_EMPTY + qb), ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar(BAR_Q_FULL + qb), C::Q_BYTES);
+        tma_load_3d(sQ + qb * C::Q_BYTES, &tmQ, bar(BAR_Q_FULL + qb), hd * DK, qt * ATT_QT, b);
+        for (int j = 0; j < nt; ++j, ++g) {
+          const uint32_t ph = g & 1;
+          mbar_wait(bar(BAR_K_EMPTY), ph ^ 1);
+          mbar_arrive_expect_tx(bar(BAR_K_FULL), C::KV_BYTES);
+          tma_load_3d(sK, &tmK, bar(BAR_K_FULL), hd * DK, j * ATT_KT, b);
+          mbar_wait(bar(BAR_V_EMPTY), ph ^ 1);
+          mbar_arrive_expect_tx(bar(BAR_V_FULL), C::KV_BYTES);
+          tma_load_3d(sV, &tmV, bar(BAR_V_FULL), hd * DK, j * ATT_KT, b);
+        }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc_s = make_idesc_f16(ATT_QT, ATT_KT, 0, 0);  // S = Q K^T, both K-major
     constexpr uint32_t idesc_o = make_idesc_f16(ATT_QT, DK, 0, 1);      // O += P V,  V is MN-major
-    mbar_wait(bar(BAR_Q_FULL), 0);
-    for (int j = 0; j < nt; ++j) {
-      const uint32_t ph = j & 1;
-      mbar_wait(bar(BAR_K_FULL), ph);
-      mbar_wait(bar(BAR_S_FREE), ph ^ 1);  // softmax has finished reading S of tile j-1
-      tc_fence_after();
-      if (lane == 0) {
-        const uint64_t dq = make_smem_desc(sQ, 16, C::SBO, C::SWZ);
-        const uint64_t dk = make_smem_desc(sK, 16, C::SBO, C::SWZ);
+    uint32_t n = 0, g = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++n) {
+      const uint32_t qb = n & 1;
+      mbar_wait(bar(BAR_Q_FULL + qb), (n >> 1) & 1);
+      for (int j = 0; j < nt; ++j, ++g) {
+        const uint32_t ph = g & 1;
+        mbar_wait(bar(BAR_K_FULL), ph);
+        mbar_wait(bar(BAR_S_FREE), ph ^ 1);  // softmax has finished reading S of the previous tile
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t dq = make_smem_desc(sQ + qb * C::Q_BYTES, 16, C::SBO, C::SWZ);
+          const uint64_t dk = make_smem_desc(sK, 16, C::SBO, C::SWZ);
 #pragma unroll
-        for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        tc_commit(bar(BAR_K_EMPTY));
-        tc_commit(bar(BAR_S_FULL));
-      }
-      __syncwarp();
-      mbar_wait(bar(BAR_V_FULL), ph);
-      mbar_wait(bar(BAR_P_FULL), ph);  // P_j is in shared memory, O has been rescaled
-      tc_fence_after();
-      if (lane == 0) {
-#pragma unroll
-        for (int kk = 0; kk < ATT_KT / 16; ++kk) {
-          // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row
-          const uint64_t dp = make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
-          // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
-          const uint64_t dv = make_smem_desc(sV + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
-          tc_mma_f16(tO, dp, dv, idesc_o, (j | kk) != 0);
+          for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          tc_commit(bar(BAR_K_EMPTY));
+          tc_commit(bar(BAR_S_FULL));
+          if (j == nt - 1) tc_commit(bar(BAR_Q_EMPTY + qb));  // last use of this item's queries
         }
-        tc_commit(bar(BAR_V_EMPTY));
-        tc_commit(bar(BAR_PV_DONE));
+        __syncwarp();
+        mbar_wait(bar(BAR_V_FULL), ph);
+        mbar_wait(bar(BAR_P_FULL), ph);  // P_j is in shared memory, O has been rescaled
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int kk = 0; kk < ATT_KT / 16; ++kk) {
+            // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row
+            const uint64_t dp = make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
+            // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
+            const uint64_t dv = make_smem_desc(sV + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
+            tc_mma_f16(tO, dp, dv, idesc_o, (j | kk) != 0);
+          }
+          tc_commit(bar(BAR_V_EMPTY));
+          tc_commit(bar(BAR_PV_DONE));
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // -------------------------------------------------------------- softmax + epilogue
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;  // row inside the tile == TMEM lane
-    const int qi = qt * ATT_QT + row;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-    const uint32_t* mrow = nullptr;
-    if (p.mask_bits != nullptr) {
-      const int mq = (p.mask_rows_q == 1) ? 0 : min(qi, p.Lq - 1);
-      mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
-    }
     // Softmax runs in the log2 domain: t = s * (scale * log2 e); masked t = -1e9 * log2 e (the
     // reference's finite -1e9, mtn.py:227); p = 2^(t - m).  Chunks (32 keys) whose keys are all
     // kept and in range -- the common case -- take a select-free fast path.
     constexpr float LOG2E = 1.4426950408889634f;
     const float c1 = p.scale * LOG2E;
     const float t_masked = -1e9f * LOG2E;
-    float m_run = -CUDART_INF_F, l_run = 0.f;
     const uint32_t sw = (uint32_t)(row & 7);
     constexpr int NCH = ATT_KT / 32;
+    uint32_t g = 0;
 
-    for (int j = 0; j < nt; ++j) {
-      const uint32_t ph = j & 1;
-      mbar_wait(bar(BAR_S_FULL), ph);
-      tc_fence_after();
-      // ---- pass 1: row maximum of the masked, scaled scores
-      float m_tile = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        const int k0 = j * ATT_KT + c * 32;
-        const int nvalid = p.Lk - k0;  // keys of this chunk inside the sequence (warp-uniform)
-        if (nvalid <= 0) break;
-        const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-        const uint32_t mw = (mrow != nullptr) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
-        uint32_t r[32];
-        tc_ld32(tS + lane_off + c * 32, r);
-        tc_wait_ld();
-        if ((mw & inb) == 0xffffffffu) {
-          float mx = __uint_as_float(r[0]);
-#pragma unroll
-          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          m_tile = fmaxf(m_tile, mx * c1);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t = __uint_as_float(r[i]) * c1;
-            t = ((mw >> i) & 1u) ? t : t_masked;
-            t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-            m_tile = fmaxf(m_tile, t);
-          }
-        }
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
+      const int qi = qt * ATT_QT + row;
+      const uint32_t* mrow = nullptr;
+      if (p.mask_bits != nullptr) {
+        const int mq = (p.mask_rows_q == 1) ? 0 : min(qi, p.Lq - 1);
+        mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
       }
-      const float m_new = fmaxf(m_run, m_tile);
-      // P buffer and O accumulator are in use by PV of the previous tile until it retires
-      if (j > 0) {
-        mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
+      float m_run = -CUDART_INF_F, l_run = 0.f;
+
+      for (int j = 0; j < nt; ++j, ++g) {
+        const uint32_t ph = g & 1;
+        mbar_wait(bar(BAR_S_FULL), ph);
         tc_fence_after();
-      }
-      // ---- pass 2: p = 2^(t - m), row sum, f16 P tile to shared memory
-      float l_tile = 0.f;
+        // ---- pass 1: row maximum of the masked, scaled scores
+        float m_tile = -CUDART_INF_F;
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        const int k0 = j * ATT_KT + c * 32;
-        const int nvalid = p.Lk - k0;
-        const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
-        float e[32];
-        if (nvalid > 0) {  // warp-uniform
+        for (int c = 0; c < NCH; ++c) {
+          const int k0 = j * ATT_KT + c * 32;
+          const int nvalid = p.Lk - k0;  // keys of this chunk inside the sequence (warp-uniform)
+          if (nvalid <= 0) break;
+          const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+          const uint32_t mw = (mrow != nullptr) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
           uint32_t r[32];
           tc_ld32(tS + lane_off + c * 32, r);
           tc_wait_ld();
           if ((mw & inb) == 0xffffffffu) {
+            float mx = __uint_as_float(r[0]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c1, -m_new));
-              l_tile += e[i];
-            }
+            for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            m_tile = fmaxf(m_tile, mx * c1);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               float t = __uint_as_float(r[i]) * c1;
               t = ((mw >> i) & 1u) ? t : t_masked;
               t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-              e[i] = ex2_approx(t - m_new);
-              l_tile += e[i];
+              m_tile = fmaxf(m_tile, t);
             }
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) e[i] = 0.f;
         }
-        const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * 128;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t chunk = (uint32_t)((c & 1) * 4 + t) ^ sw;  // 128B swizzle: 16-B chunk ^= row % 8
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + chunk * 16),
-                       "r"(pack_f16x2_sat(e[8 * t], e[8 * t + 1])), "r"(pack_f16x2_sat(e[8 * t + 2], e[8 * t + 3])),
-                       "r"(pack_f16x2_sat(e[8 * t + 4], e[8 * t + 5])), "r"(pack_f16x2_sat(e[8 * t + 6], e[8 * t + 7]))
-                       : "memory");
+        const float m_new = fmaxf(m_run, m_tile);
+        // P buffer and O accumulator are in use by PV of the previous tile of this item until it
+        // retires (across items the epilogue below has already waited for the last PV)
+        if (j > 0) {
+          mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
+          tc_fence_after();
         }
+        // ---- pass 2: p = 2^(t - m), row sum, f16 P tile to shared memory
+        float l_tile = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const int k0 = j * ATT_KT + c * 32;
+          const int nvalid = p.Lk - k0;
+          const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+          const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
+          float e[32];
+          if (nvalid > 0) {  // warp-uniform
+            uint32_t r[32];
+            tc_ld32(tS + lane_off + c * 32, r);
+            tc_wait_ld();
+            if ((mw & inb) == 0xffffffffu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c1, -m_new));
+                l_tile += e[i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float t = __uint_as_float(r[i]) * c1;
+                t = ((mw >> i) & 1u) ? t : t_masked;
+                t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+                e[i] = ex2_approx(t - m_new);
+                l_tile += e[i];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] = 0.f;
+          }
+          const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * 128;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t chunk = (uint32_t)((c & 1) * 4 + t) ^ sw;  // 128B swizzle: 16-B chunk ^= row % 8
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + chunk * 16),
+                         "r"(pack_f16x2_sat(e[8 * t], e[8 * t + 1])), "r"(pack_f16x2_sat(e[8 * t + 2], e[8 * t + 3])),
+                         "r"(pack_f16x2_sat(e[8 * t + 4], e[8 * t + 5])), "r"(pack_f16x2_sat(e[8 * t + 6], e[8 * t + 7]))
+                         : "memory");
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar(BAR_S_FREE));  // S may be overwritten by the next Q K^T
+        const float alpha = ex2_approx(m_run - m_new);
+        l_run = l_run * alpha + l_tile;
+        m_run = m_new;
+        if (j > 0) {
+          // rescale the running O accumulator in tensor memory
+#pragma unroll
+          for (int c = 0; c < DK / 32; ++c) {
+            uint32_t r[32];
+            tc_ld32(tO + lane_off + c * 32, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tc_st32(tO + lane_off + c * 32, r);
+          }
+          tc_wait_st();
+        }
+        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+        tc_fence_before();
+        mbar_arrive(bar(BAR_P_FULL));
       }
-      tc_fence_before();
-      mbar_arrive(bar(BAR_S_FREE));  // S may be overwritten by the next Q K^T
-      const float alpha = ex2_approx(m_run - m_new);
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
-      if (j > 0) {
-        // rescale the running O accumulator in tensor memory
+      // ---- epilogue: O / l  -> f16, head hd's column slice of the output
+      mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
 #pragma unroll
-        for (int c = 0; c < DK / 32; ++c) {
-          uint32_t r[32];
-          tc_ld32(tO + lane_off + c * 32, r);
-          tc_wait_ld();
+      for (int c = 0; c < DK / 32; ++c) {
+        uint32_t r[32];
+        tc_ld32(tO + lane_off + c * 32, r);
+        tc_wait_ld();
+        if (qi < p.Lq) {
+          uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qi) * p.ldo + hd * DK + c * 32);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tc_st32(tO + lane_off + c * 32, r);
+          for (int t = 0; t < 4; ++t)
+            o[t] = make_uint4(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l),
+                              pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l),
+                              pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l),
+                              pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l));
         }
-        tc_wait_st();
-      }
-      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
-      tc_fence_before();
-      mbar_arrive(bar(BAR_P_FULL));
-    }
-    // ---- epilogue: O / l  -> f16, head hd's column slice of the output
-    mbar_wait(bar(BAR_PV_DONE), (nt - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.f / l_run;
-#pragma unroll
-    for (int c = 0; c < DK / 32; ++c) {
-      uint32_t r[32];
-      tc_ld32(tO + lane_off + c * 32, r);
-      tc_wait_ld();
-      if (qi < p.Lq) {
-        uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qi) * p.ldo + hd * DK + c * 32);
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          o[t] = make_uint4(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l),
-                            pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l),
-                            pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l),
-                            pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l));
       }
     }
     tc_fence_before();
@@ -325,9 +345,18 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_3d_f16(&tv, a.v, cols, a.Lk, a.B, a.ldv, (uint64_t)a.Lk * a.ldv, DK, ATT_KT, swz);
   if (rc) return rc;
-  AttnParams p{a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
+  const int nqt = (a.Lq + ATT_QT - 1) / ATT_QT;
+  const int n_items = nqt * a.h * a.B;
+  AttnParams p{n_items, nqt, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
                1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo};
-  dim3 grid((a.Lq + ATT_QT - 1) / ATT_QT, a.h, a.B);
+  static int slots = 0;  // resident CTAs: 2 per SM
+  if (slots == 0) {
+    int dev = 0, n = 0;
+    MTN_CHECK_CUDA(cudaGetDevice(&dev));
+    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    slots = 2 * n;
+  }
+  dim3 grid(n_items < slots ? n_items : slots);
   MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, p));
   return MTN_OK;
 }
@@ -337,7 +366,6 @@ static int validate_attn(const MtnAttnCoreArgs* a) {
   MTN_REQUIRE(a->B > 0 && a->h > 0 && a->Lq > 0 && a->Lk > 0, MTN_E_SHAPE, "attn_core: B=%d h=%d Lq=%d Lk=%d",
               a->B, a->h, a->Lq, a->Lk);
   MTN_REQUIRE(a->d_k == 32 || a->d_k == 64, MTN_E_SHAPE, "attn_core: d_k=%d (supported: 32, 64)", a->d_k);
-  MTN_REQUIRE(a->B <= 65535 && a->h <= 65535, MTN_E_SHAPE, "attn_core: grid too large");
   const int w = a->h * a->d_k;
   MTN_REQUIRE(a->ldq >= w && a->ldk >= w && a->ldv >= w && a->ldo >= w, MTN_E_SHAPE,
               "attn_core: leading dimension smaller than h*d_k=%d", w);
@@ -403,7 +431,7 @@ extern "C" int mtn_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
 extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
   int rc = mtn::validate_attn(a);
   if (rc) return rc;
-  mtn::AttnParams p{a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
+  mtn::AttnParams p{0, 0, a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
                     1.0f / sqrtf((float)a->d_k), reinterpret_cast<__half*>(a->out), a->ldo};
   dim3 grid(a->Lq, a->h, a->B);
   mtn::attn_core_check_kernel<<<grid, 32, a->Lk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(

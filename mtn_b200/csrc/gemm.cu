@@ -377,7 +377,12 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
   }
   const int tiles_m = (a->M + 127) / 128;
   const long tiles256 = (long)((a->N + 255) / 256) * tiles_m;
-  const bool big = a->N >= 256 && tiles256 >= mtn::g_num_sms;
+  static int big_pct = -1;  // 128x256 tiles once they fill this percentage of the SMs
+  if (big_pct < 0) {
+    const char* e = getenv("MTN_B200_BIG_PCT");
+    big_pct = e ? atoi(e) : 40;
+  }
+  const bool big = a->N >= 256 && tiles256 * 100 >= (long)big_pct * mtn::g_num_sms;
   if (cl >= 2 && big && tiles256 >= 4L * mtn::g_num_sms) return mtn::launch_gemm<256, 4, 2>(*a, st);
   return big ? mtn::launch_gemm<256, 4, 1>(*a, st) : mtn::launch_gemm<128, 6, 1>(*a, st);
 }
