@@ -194,6 +194,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
       }
       float m_run = -CUDART_INF_F, l_run = 0.f;
+      if (qt * ATT_QT + q4 * 32 >= p.Lq) {
+        // every query row of this warp is padding (Lq <= 64 sites use half of the 128-row tile): skip the
+        // softmax work, keep the barrier protocol alive.  The P rows of these queries stay whatever is in
+        // shared memory; they only feed O rows that are never stored.
+        for (int j = 0; j < nt; ++j, ++g) {
+          const uint32_t ph = g & 1;
+          mbar_wait(bar(BAR_S_FULL), ph);
+          if (j > 0) mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
+          mbar_arrive(bar(BAR_S_FREE));
+          mbar_arrive(bar(BAR_P_FULL));
+        }
+        mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
+        continue;
+      }
 
       for (int j = 0; j < nt; ++j, ++g) {
         const uint32_t ph = g & 1;
@@ -212,10 +226,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           tc_ld32(tS + lane_off + c * 32, r);
           tc_wait_ld();
           if ((mw & inb) == 0xffffffffu) {
-            float mx = __uint_as_float(r[0]);
+            float mx[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
 #pragma unroll
-            for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-            m_tile = fmaxf(m_tile, mx * c1);
+            for (int i = 4; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));  // 4 independent chains
+            m_tile = fmaxf(m_tile, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           tc_fence_after();
         }
         // ---- pass 2: p = 2^(t - m), row sum, f16 P tile to shared memory
-        float l_tile = 0.f;
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent partial row sums
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
           const int k0 = j * ATT_KT + c * 32;
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c1, -m_new));
-                l_tile += e[i];
+                l4[i & 3] += e[i];
               }
             } else {
 #pragma unroll
@@ -259,7 +273,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
                 t = ((mw >> i) & 1u) ? t : t_masked;
                 t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
                 e[i] = ex2_approx(t - m_new);
-                l_tile += e[i];
+                l4[i & 3] += e[i];
               }
             }
           } else {
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         tc_fence_before();
         mbar_arrive(bar(BAR_S_FREE));  // S may be overwritten by the next Q K^T
         const float alpha = ex2_approx(m_run - m_new);
-        l_run = l_run * alpha + l_tile;
+        l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
         if (j > 0) {
           // rescale the running O accumulator in tensor memory
