@@ -222,6 +222,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           if (nvalid <= 0) break;
           const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
           const uint32_t mw = (mrow != nullptr) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
+          // chunk with no kept key for ANY row of the warp (padding tail of a key-padding mask):
+          // every in-range score is the constant -1e9, nothing to read from TMEM
+          if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
+            m_tile = fmaxf(m_tile, t_masked);
+            continue;
+          }
           uint32_t r[32];
           tc_ld32(tS + lane_off + c * 32, r);
           tc_wait_ld();
@@ -256,7 +262,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
           const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
           float e[32];
-          if (nvalid > 0) {  // warp-uniform
+          if (nvalid > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
+            // all in-range keys masked for every row of the warp: p = 2^(-1e9 log2e - m) is one value
+            // per row (0 unless the whole row has been masked so far, then 1 -> uniform average)
+            const float pm = ex2_approx(t_masked - m_new);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] = ((inb >> i) & 1u) ? pm : 0.f;
+            l4[0] += pm * (float)__popc(inb);
+          } else if (nvalid > 0) {  // warp-uniform
             uint32_t r[32];
             tc_ld32(tS + lane_off + c * 32, r);
             tc_wait_ld();
