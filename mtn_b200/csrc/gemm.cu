@@ -32,16 +32,16 @@ struct GemmEpi {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 f16 = 128 B = one swizzle-128B row
-// threads = TMA warp + MMA warp + EW epilogue warps (EW = 8: one resident CTA per SM, EW = 4: two)
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STAGE_TILE_BYTES = 32 * 32 * 4;  // per-epilogue-warp 32x32 f32 transpose buffer
 
-template <int BN, int STAGES, int EW>
+template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int XPOSE_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = XPOSE_OFF + EW * STAGE_TILE_BYTES;
+  static constexpr int BAR_OFF = XPOSE_OFF + 8 * STAGE_TILE_BYTES;
   static constexpr int NBARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFF + 8 * NBARS + 16 + 1024;  // + tmem slot + 1 KB alignment slack
 };
@@ -56,16 +56,11 @@ struct GemmSmem {
 // them, so W crosses L2->SM once per cluster instead of once per CTA (the 128xBN tiles are L2-bandwidth
 // bound otherwise).  A slot is refilled only after every CTA of the cluster has consumed it: the MMA
 // warp's tcgen05.commit arrives on the "empty" barrier of all CL CTAs (multicast commit).
-//
-// EW = 4, STAGES = 2 is the small-problem configuration: ~97 KB of shared memory and 2 x BN TMEM columns
-// let TWO CTAs share an SM, so a single-wave GEMM (one tile per CTA, nothing for the accumulator
-// double-buffering to overlap) overlaps one CTA's epilogue with the other's mainloop, and under
-// programmatic dependent launch the next kernel's CTAs start as soon as a slot frees up.
-template <int BN, int STAGES, int CL, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2)
+template <int BN, int STAGES, int CL>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmEpi epi, int M, int N, int K, int tiles_n, int num_tiles) {
-  using L = GemmSmem<BN, STAGES, EW>;
+  using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
@@ -98,7 +93,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);   // tcgen05.commit after the last k-block of a tile
-      mbar_init(bar_acc_empty(b), EW);  // one arrive per epilogue warp
+      mbar_init(bar_acc_empty(b), 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -169,8 +164,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2)
     // alternate 32-column chunks.
     const int ew = warp - 2;
     const int q = warp & 3;    // TMEM lane quarter this warp may access
-    const int half = ew >> 2;  // EW = 8: warps 0-3 take even chunks, 4-7 odd ones; EW = 4: all chunks
-    constexpr int CSTEP = EW / 4;
+    const int half = ew >> 2;  // 0: even chunks, 1: odd chunks
     float4* xp = reinterpret_cast<float4*>(smem + L::XPOSE_OFF + ew * STAGE_TILE_BYTES);
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
@@ -197,7 +191,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2)
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = half; c < NCHUNK; c += CSTEP) {
+      for (int c = half; c < NCHUNK; c += 2) {
         const int col = n0 + c * 32 + c8 * 8;  // this lane's 8 columns in the coalesced phase
         const bool col_ok = col < N;           // N % 8 == 0: all 8 or none
         float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
@@ -220,7 +214,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2)
         uint32_t acc[32];
         tc_ld32(t_acc + c * 32, acc);
         tc_wait_ld();
-        if (c + CSTEP >= NCHUNK) {  // this warp's last read of the accumulator: release its share of the buffer
+        if (c + 2 >= NCHUNK) {  // this warp's last read of the accumulator: release its share of the buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty(buf));
@@ -276,16 +270,15 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2)
 
 static int g_num_sms = 0;
 
-template <int BN, int STAGES, int CL, int EW>
+template <int BN, int STAGES, int CL>
 static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES, EW>;
-  constexpr int GEMM_THREADS = 64 + 32 * EW;
+  using L = GemmSmem<BN, STAGES>;
   static int max_clusters = 0;  // co-resident clusters (1 CTA per SM)
   if (max_clusters == 0) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL, EW>,
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     if (CL == 1) {
-      max_clusters = g_num_sms * (EW == 8 ? 1 : 2);
+      max_clusters = g_num_sms;
     } else {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(g_num_sms / CL * CL);
@@ -296,7 +289,7 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
       attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       int n = 0;
-      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL, EW>, &cfg));
+      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL>, &cfg));
       MTN_REQUIRE(n > 0, MTN_E_CUDA, "linear: no cluster of %d CTAs fits on this device", CL);
       max_clusters = n;
     }
@@ -311,7 +304,7 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
   const int num_super = tiles_n * ((tiles_m + CL - 1) / CL);
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
-  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, EW>, dim3(clusters * CL), dim3(GEMM_THREADS),
+  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL>, dim3(clusters * CL), dim3(GEMM_THREADS),
                                        L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K, tiles_n, num_super));
   return MTN_OK;
 }
@@ -390,15 +383,8 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
     big_pct = e ? atoi(e) : 40;
   }
   const bool big = a->N >= 256 && tiles256 * 100 >= (long)big_pct * mtn::g_num_sms;
-  if (cl >= 2 && big && tiles256 >= 4L * mtn::g_num_sms) return mtn::launch_gemm<256, 4, 2, 8>(*a, st);
-  static int small_mode = -1;  // single-wave problems: two light CTAs per SM (MTN_B200_SMALL=0 disables)
-  if (small_mode < 0) {
-    const char* e = getenv("MTN_B200_SMALL");
-    small_mode = e ? atoi(e) : 1;
-  }
-  const long tiles128 = (long)((a->N + 127) / 128) * tiles_m;
-  if (small_mode && tiles128 <= 2L * mtn::g_num_sms) return mtn::launch_gemm<128, 2, 1, 4>(*a, st);
-  return big ? mtn::launch_gemm<256, 4, 1, 8>(*a, st) : mtn::launch_gemm<128, 6, 1, 8>(*a, st);
+  if (cl >= 2 && big && tiles256 >= 4L * mtn::g_num_sms) return mtn::launch_gemm<256, 4, 2>(*a, st);
+  return big ? mtn::launch_gemm<256, 4, 1>(*a, st) : mtn::launch_gemm<128, 6, 1>(*a, st);
 }
 
 extern "C" int mtn_check_linear_fwd(const MtnLinearArgs* a, void* stream) {
