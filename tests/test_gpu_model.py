@@ -273,3 +273,41 @@ def test_cfg4_decode_graphs_token_exact(M, cfg2_model):
         assert torch.equal(ys_g[sel].cpu(), ref), agree
     finally:
         model.generator.proj.weight.data.copy_(w0)
+
+
+def test_cfg5_family_d1024_h16(M):
+    """BASELINE configs[4] architecture family (d_model=1024, h=16 -> d_k=64, d_ff=4096, video_len=1024) at
+    N=1 and a small batch so the CPU oracle finishes in seconds."""
+    mtn, du = M
+    cfg = {"N": 1, "d_model": 1024, "d_ff": 4096, "h": 16, "vocab": 120, "ft_sizes": [2048, 128],
+           "auto_encoder_ft": "query", "diff_encoder": True}
+    sd = O.init_state_dict(cfg, 31)
+    model = build(mtn, cfg, sd)
+    inp = O.synth_inputs(cfg, B=2, Q=64, C=64, H=256, T=20, Lv=[1024, 256], seed=6)
+    ref_out, ref_ae = O.forward(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["fts"])
+    with torch.no_grad():
+        out, ae = model.forward(make_batch(du, inp))
+    e = [G.rel_err(out.cpu(), ref_out), G.rel_err(ae[0].cpu(), ref_ae[0]), G.rel_err(ae[1].cpu(), ref_ae[1])]
+    print("cfg5 family rel err:", e)
+    assert max(e) <= TOL, e
+
+
+def test_edge_shapes(M):
+    """Edge cases of the domain: batch 1; a first-turn dialogue whose history is the single <blank> token
+    (data_handler.py:113-114 -> fully masked keys -> uniform softmax); target length 1 (first decode step);
+    a single video frame; sequence lengths that are not multiples of any tile size."""
+    mtn, du = M
+    cfg = {"N": 2, "d_model": 128, "d_ff": 512, "h": 4, "vocab": 70, "ft_sizes": [64, 128],
+           "auto_encoder_ft": "query", "diff_encoder": True}
+    sd = O.init_state_dict(cfg, 13)
+    model = build(mtn, cfg, sd)
+    for (B, Q, C, H, T, Lv) in ((1, 5, 3, 1, 1, [1, 2]), (2, 1, 1, 1, 2, [3, 1]), (3, 67, 33, 129, 131, [257, 65])):
+        inp = O.synth_inputs(cfg, B=B, Q=Q, C=C, H=H, T=T, Lv=Lv, seed=B * 7 + T)
+        if H == 1:
+            inp["his"][:] = 1                      # <blank> only
+        ref_out, ref_ae = O.forward(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["fts"])
+        with torch.no_grad():
+            out, ae = model.forward(make_batch(du, inp))
+        e = [G.rel_err(out.cpu(), ref_out), G.rel_err(ae[0].cpu(), ref_ae[0]), G.rel_err(ae[1].cpu(), ref_ae[1])]
+        print((B, Q, C, H, T, Lv), e)
+        assert max(e) <= TOL, ((B, Q, C, H, T, Lv), e)
