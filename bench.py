@@ -107,6 +107,19 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def traffic_from_profiles(n_launches):
+    """DRAM bytes per launch of the linear kernel from the committed ncu capture of the same step
+    (profiles/rNN_gemm_traffic.json, written by tools/summarize_profiles.py); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))
+    if not files:
+        return None
+    t = json.load(open(files[-1]))
+    per_launch = (t["dram_bytes_read"] + t["dram_bytes_write"]) / max(1, t["launches"])
+    return {"dram_bytes_per_launch_avg": per_launch, "launches_in_capture": t["launches"],
+            "launches_in_this_run": n_launches, "source": t["source"]}
+
+
 def synth(O, B, T, seed):
     return O.synth_inputs(CFG, B=B, Q=SHAPE["Q"], C=SHAPE["C"], H=SHAPE["H"], T=T, Lv=SHAPE["Lv"], seed=seed)
 
@@ -337,7 +350,7 @@ def main():
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (f16 and bf16 share the tensor rate)"
                 if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
-                "traffic": None,
+                "traffic": traffic_from_profiles(lin["n"]),
                 "flops_per_launch_avg": lin["flops"] / lin["n"], "us_per_launch_avg": lin["ms"] * 1e3 / lin["n"],
                 "note": "algorithmic 2MNK of the step's linear launches / CUDA-event time of those launches "
                         "replayed back to back in one CUDA graph"}
