@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MTN_B200_ABI_VERSION 2
+#define MTN_B200_ABI_VERSION 1
 
 enum {
   MTN_OK = 0,
@@ -117,15 +117,6 @@ typedef struct MtnLinearArgs {
   const float *addend; int ld_add; int add_period;
   float *out_f32; int ld32;
   void *out_f16; int ld16;
-  /* Optional fused LayerNorm of the NEXT sublayer (mtn.py:111-114 as called from mtn.py:127): when
-   * ln_out_f16 != NULL (requires N == d, out_f32 contiguous) the kernel also writes
-   * ln_out_f16[m, :] = f16( LN(out_f32[m, :]; ln_a, ln_b, ln_eps) ), [M, N] contiguous -- the operand of
-   * the next projection -- so no separate mtn_layernorm_fwd launch is needed.  ln_counters: device
-   * array of ceil(M/128) uint32, zero before the first use; the kernel leaves it zeroed, so it can be
-   * shared by consecutive launches on ONE stream (use one array per stream).                     */
-  const float *ln_a, *ln_b; float ln_eps;
-  void *ln_out_f16;
-  unsigned int *ln_counters;
 } MtnLinearArgs;
 int mtn_linear_fwd(const MtnLinearArgs *args, void *stream);
 

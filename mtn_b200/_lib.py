@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 1
 
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -25,9 +25,7 @@ class LinearArgs(C.Structure):
                 ("bias", C.c_void_p), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("act", C.c_int), ("addend", C.c_void_p), ("ld_add", C.c_int),
                 ("add_period", C.c_int), ("out_f32", C.c_void_p), ("ld32", C.c_int),
-                ("out_f16", C.c_void_p), ("ld16", C.c_int),
-                ("ln_a", C.c_void_p), ("ln_b", C.c_void_p), ("ln_eps", C.c_float),
-                ("ln_out_f16", C.c_void_p), ("ln_counters", C.c_void_p)]
+                ("out_f16", C.c_void_p), ("ld16", C.c_int)]
 
 
 class AttnCoreArgs(C.Structure):
@@ -202,10 +200,8 @@ def mask_pack(mask):
 
 
 def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=None, out_f16=None,
-           ln=None, ln_out_f16=None, ln_counters=None, _check_kernel=False):
-    """C = act(A W^T + bias) + addend.  A: [M, K] f16 (row stride allowed), W: [N, K] f16.
-    ln=(a_2, b_2, eps) + ln_out_f16 [M, N] f16 + ln_counters (int32 zeros, >= ceil(M/128)): also emit
-    the next sublayer's LayerNorm of out_f32 (fused; see include/mtn_b200.h)."""
+           _check_kernel=False):
+    """C = act(A W^T + bias) + addend.  A: [M, K] f16 (row stride allowed), W: [N, K] f16."""
     _req(A, torch.float16, "A"); _req(W, torch.float16, "W"); _req(bias, torch.float32, "bias")
     _req(addend, torch.float32, "addend"); _req(out_f32, torch.float32, "out_f32")
     _req(out_f16, torch.float16, "out_f16")
@@ -223,19 +219,12 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
     if out_f16 is not None:
         assert out_f16.dim() == 2 and tuple(out_f16.shape) == (a.M, a.N)
         a.out_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
-    if ln_out_f16 is not None:
-        _req(ln_out_f16, torch.float16, "ln_out_f16")
-        assert ln is not None and ln_counters is not None and out_f32 is not None
-        assert ln_out_f16.is_contiguous() and tuple(ln_out_f16.shape) == (a.M, a.N) and out_f32.is_contiguous()
-        assert ln_counters.dtype == torch.int32 and ln_counters.numel() * 128 >= a.M
-        a.ln_a, a.ln_b, a.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), float(ln[2])
-        a.ln_out_f16, a.ln_counters = ln_out_f16.data_ptr(), ln_counters.data_ptr()
     fn = lib().mtn_check_linear_fwd if _check_kernel else lib().mtn_linear_fwd
     nbytes = 2 * (a.M * a.K + a.N * a.K) + a.M * a.N * ((4 if out_f32 is not None else 0) +
                                                         (2 if out_f16 is not None else 0) +
                                                         (4 if addend is not None else 0))
     _launch("linear", 2 * a.M * a.N * a.K, nbytes, lambda: fn(C.byref(a), stream_ptr()),
-            keep=(A, W, bias, addend, out_f32, out_f16, ln, ln_out_f16, ln_counters))
+            keep=(A, W, bias, addend, out_f32, out_f16))
 
 
 def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False):

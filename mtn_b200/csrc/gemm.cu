@@ -28,52 +28,9 @@ struct GemmEpi {
   int ld32;
   __half* out16;
   int ld16;
-  // fused "next LayerNorm" (see MtnLinearArgs.ln_out_f16)
-  const float* ln_a;
-  const float* ln_b;
-  float ln_eps;
-  __half* ln_out16;
-  unsigned int* ln_counters;
 };
 
 constexpr int BM = 128;
-
-// LayerNorm (mtn.py:111-114) of one row held as VPL float4 per lane of a warp -- the same arithmetic as
-// layernorm_rows_kernel (two-pass variance, eps on std).  Rows were written by other CTAs: read through L2.
-template <int VPL>
-__device__ __forceinline__ void ln_row_to_f16(const float* __restrict__ xrow, const float* __restrict__ a2,
-                                              const float* __restrict__ b2, float eps, __half* __restrict__ yrow,
-                                              int lane) {
-  constexpr int D = 128 * VPL;
-  float4 v[VPL];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i] = __ldcg(reinterpret_cast<const float4*>(xrow) + lane + 32 * i);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.f / D);
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-    ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float inv = 1.f / (sqrtf(ss * (1.f / (D - 1))) + eps);
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c4 = lane + 32 * i;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(a2) + c4);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(b2) + c4);
-    reinterpret_cast<uint2*>(yrow)[c4] =
-        make_uint2(pack_f16x2_sat(a.x * v[i].x * inv + b.x, a.y * v[i].y * inv + b.y),
-                   pack_f16x2_sat(a.z * v[i].z * inv + b.z, a.w * v[i].w * inv + b.w));
-  }
-}
 constexpr int BK = 64;  // 64 f16 = 128 B = one swizzle-128B row
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STAGE_TILE_BYTES = 32 * 32 * 4;  // per-epilogue-warp 32x32 f32 transpose buffer
@@ -86,7 +43,7 @@ struct GemmSmem {
   static constexpr int XPOSE_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = XPOSE_OFF + 8 * STAGE_TILE_BYTES;
   static constexpr int NBARS = 2 * STAGES + 4;
-  static constexpr int TOTAL = BAR_OFF + 8 * NBARS + 16 + 1024;  // + tmem slot, LN flag + 1 KB alignment slack
+  static constexpr int TOTAL = BAR_OFF + 8 * NBARS + 16 + 1024;  // + tmem slot + 1 KB alignment slack
 };
 
 // Persistent kernel: each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so
@@ -300,37 +257,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
         }
       }
-      if (epi.ln_out16 != nullptr) {
-        // Fused next-sublayer LayerNorm: N == d, so the n-tiles of one m-block together hold complete rows
-        // of the updated residual stream.  Every CTA publishes its tile (fence + counter); the CTA that
-        // arrives last normalises the 128 rows -- no waiting, hence no deadlock, and the result does not
-        // depend on which CTA is last.  The counter resets itself for the next launch on this stream.
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps of this CTA
-        uint32_t* flag = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * L::NBARS + 8);
-        const int mblk = m0 / BM;
-        if (ew == 0 && lane == 0) {
-          const unsigned prev = atomicAdd(epi.ln_counters + mblk, 1u);
-          const bool last = (prev == (unsigned)tiles_n - 1u);
-          if (last) epi.ln_counters[mblk] = 0u;
-          *flag = last ? 1u : 0u;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (*reinterpret_cast<volatile uint32_t*>(flag) != 0u) {
-          __threadfence();
-          for (int rr = ew; rr < BM; rr += 8) {
-            const int r = m0 + rr;
-            if (r >= M) break;
-            const float* xrow = epi.out32 + (size_t)r * epi.ld32;
-            __half* yrow = epi.ln_out16 + (size_t)r * N;
-            if (N == 512) ln_row_to_f16<4>(xrow, epi.ln_a, epi.ln_b, epi.ln_eps, yrow, lane);
-            else if (N == 1024) ln_row_to_f16<8>(xrow, epi.ln_a, epi.ln_b, epi.ln_eps, yrow, lane);
-            else if (N == 256) ln_row_to_f16<2>(xrow, epi.ln_a, epi.ln_b, epi.ln_eps, yrow, lane);
-            else ln_row_to_f16<1>(xrow, epi.ln_a, epi.ln_b, epi.ln_eps, yrow, lane);
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // flag is reused by the next tile
-      }
     }
     tc_fence_before();
   }
@@ -374,8 +300,7 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
   rc = make_tmap_2d_f16(&tmB, a.W, a.K, a.N, a.ldw, BK, BN / CL, TM_SWZ_128);
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
-              reinterpret_cast<__half*>(a.out_f16), a.ld16, a.ln_a, a.ln_b, a.ln_eps,
-              reinterpret_cast<__half*>(a.ln_out_f16), a.ln_counters};
+              reinterpret_cast<__half*>(a.out_f16), a.ld16};
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
   const int num_super = tiles_n * ((tiles_m + CL - 1) / CL);
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
@@ -404,14 +329,6 @@ static int validate_linear(const MtnLinearArgs* a) {
     MTN_REQUIRE(aligned16(a->addend) && a->ld_add % 4 == 0 && a->ld_add >= a->N && a->add_period >= 0,
                 MTN_E_ALIGN, "linear: addend alignment / ld_add=%d", a->ld_add);
   if (a->bias) MTN_REQUIRE(aligned16(a->bias), MTN_E_ALIGN, "linear: bias not 16-byte aligned");
-  if (a->ln_out_f16) {
-    MTN_REQUIRE(a->ln_a && a->ln_b && a->ln_counters && a->out_f32, MTN_E_ARG,
-                "linear: fused LayerNorm needs ln_a, ln_b, ln_counters and out_f32");
-    MTN_REQUIRE(a->N == 128 || a->N == 256 || a->N == 512 || a->N == 1024, MTN_E_SHAPE,
-                "linear: fused LayerNorm needs N == d in {128, 256, 512, 1024}, got %d", a->N);
-    MTN_REQUIRE(a->ld32 == a->N && aligned16(a->ln_a) && aligned16(a->ln_b) && aligned16(a->ln_out_f16), MTN_E_ALIGN,
-                "linear: fused LayerNorm needs contiguous out_f32 rows (ld32 == N) and 16-byte aligned pointers");
-  }
   return MTN_OK;
 }
 
@@ -474,8 +391,7 @@ extern "C" int mtn_check_linear_fwd(const MtnLinearArgs* a, void* stream) {
   int rc = mtn::validate_linear(a);
   if (rc) return rc;
   mtn::GemmEpi epi{a->bias, a->act, a->addend, a->ld_add, a->add_period, a->out_f32, a->ld32,
-                   reinterpret_cast<__half*>(a->out_f16), a->ld16, nullptr, nullptr, 0.f, nullptr, nullptr};
-  MTN_REQUIRE(a->ln_out_f16 == nullptr, MTN_E_ARG, "check_linear: fused LayerNorm is not part of the check kernel");
+                   reinterpret_cast<__half*>(a->out_f16), a->ld16};
   dim3 grid((a->N + 127) / 128, a->M);
   mtn::gemm_f16_check_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(a->A), a->lda, reinterpret_cast<const __half*>(a->W), a->ldw, epi,

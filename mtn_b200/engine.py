@@ -137,48 +137,27 @@ class DecoderEngine(object):
         return self._packed.get(params, build)
 
     # ------------------------------------------------------------------ building blocks
-    # A "block" is one pre-norm residual sublayer.  ``xn16`` holds LN(x) for the block on entry (f16); the
-    # block's last GEMM adds the residual in place on the f32 stream ``x`` and -- ``next_ln`` given --
-    # also emits LN_next(x) into ``xn16`` for the following block (fused in the GEMM epilogue: the CTA
-    # that completes a 128-row block last normalises it), so LayerNorm costs no launch of its own.
     @staticmethod
-    def _attn_block(x, A, B, Lq, Lk, q_w, q_b, kv, k_col, v_col, bits, xn16, qbuf, obuf, next_ln, ctr):
-        """kv=None -> self-attention (q_w is the [3d, d] pack, K/V come out of the same GEMM)."""
+    def _attn_block(x, ln, A, B, Lq, Lk, q_w, q_b, kv, k_col, v_col, bits, xn16, qbuf, obuf):
+        """One pre-norm residual attention site, in place on the f32 stream ``x`` [B*Lq, d].
+        kv=None -> self-attention (q_w is the [3d, d] pack, K/V come out of the same GEMM)."""
         d = x.shape[1]
+        _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
         _lib.linear(xn16, q_w, q_b, out_f16=qbuf)
         if kv is None:
             q, k, v = qbuf[:, :d], qbuf[:, d:2 * d], qbuf[:, 2 * d:]
         else:
             q, k, v = qbuf, kv[:, k_col:k_col + d], kv[:, v_col:v_col + d]
         _lib.attn_core(q, k, v, B, A["h"], Lq, Lk, A["d_k"], obuf, mask_bits=bits)
-        _lib.linear(obuf, A["w_o"], A["b_o"], addend=x, out_f32=x, ln=next_ln,
-                    ln_out_f16=xn16 if next_ln is not None else None, ln_counters=ctr)
+        _lib.linear(obuf, A["w_o"], A["b_o"], addend=x, out_f32=x)
 
     @staticmethod
-    def _ffn_block(x, Fw, xn16, hid, next_ln, ctr, out16=None):
+    def _ffn_block(x, ln, Fw, xn16, hid, out16=None):
+        _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
         _lib.linear(xn16, Fw["w_1"], Fw["b_1"], act=_lib.ACT_RELU, out_f16=hid)
-        _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x, out_f32=x, out_f16=out16, ln=next_ln,
-                    ln_out_f16=xn16 if next_ln is not None else None, ln_counters=ctr)
-
-    @staticmethod
-    def _run_blocks(x, xn16, blocks, ctr, fuse):
-        """blocks: list of (ln, fn) with fn(next_ln).  With ``fuse`` the first LayerNorm is a kernel of its
-        own and every later one rides on the previous block's last GEMM; without it (d not in
-        {128,256,512,1024}) every block is preceded by a LayerNorm launch."""
-        for i, (ln, fn) in enumerate(blocks):
-            if i == 0 or not fuse:
-                _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
-            nxt = blocks[i + 1][0] if (fuse and i + 1 < len(blocks)) else None
-            fn(nxt)
+        _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x, out_f32=x, out_f16=out16)
 
     # ------------------------------------------------------------------ memory stage
-    def _counters(self, slot, dev):
-        """Per-stream m-block counters of the fused LayerNorm (zero between launches by construction)."""
-        c = getattr(self, "_ctr", None)
-        if c is None or c.device != dev or c.shape[0] <= slot:
-            self._ctr = c = torch.zeros(max(8, slot + 1), 4096, dtype=torch.int32, device=dev)
-        return c[slot]
-
     def _streams(self, M, dev):
         if getattr(self, "_side", None) is None or len(self._side) != M or self._side_dev != dev:
             self._side = [torch.cuda.Stream(device=dev) for _ in range(M)]
@@ -199,7 +178,6 @@ class DecoderEngine(object):
         main = torch.cuda.current_stream()
         side = self._streams(M, dev)
         dff = W["layers"][0]["ffn"]["w_1"].shape[0]
-        fuse = d in (128, 256, 512, 1024)
 
         def hoisted(mem, wb):
             m16 = _lib.cast_f16(mem.contiguous().view(-1, d))
@@ -246,7 +224,6 @@ class DecoderEngine(object):
                 "hid": torch.empty(rows, dff, dtype=f16, device=dev),
                 "kv_ae": [torch.empty(rows, 2 * d, dtype=f16, device=dev) for _ in range(N)],
                 "out": torch.empty(rows, d, dtype=torch.float32, device=dev),
-                "ctr": self._counters(1 + i, dev),
             })
         S["kv_ae"] = [[mods[i]["kv_ae"][l] for i in range(M)] for l in range(N)]
         S["ev"] = [[torch.cuda.Event() for _ in range(M)] for _ in range(N)]
@@ -260,28 +237,22 @@ class DecoderEngine(object):
                 _lib.cast_f16(m["vid"], m["vid16"])
                 _lib.linear(m["vid16"], W["kv_vid"][i][0], W["kv_vid"][i][1], out_f16=m["kv_vid"])
                 ae = m["ae"]
-                blocks = []
                 for l in range(N):
                     Lw = W["layers"][l]
                     c0 = 4 + 4 * i
                     A = Lw["ae_self"][i]
-                    blocks.append((Lw["ln"][c0], lambda nxt, A=A: self._attn_block(
-                        ae, A, B, La, La, A["w_qkv"], A["b_qkv"], None, 0, 0, ae_bits, m["xn16"], m["qkv"],
-                        m["obuf"], nxt, m["ctr"])))
+                    self._attn_block(ae, Lw["ln"][c0], A, B, La, La, A["w_qkv"], A["b_qkv"], None, 0, 0, ae_bits,
+                                     m["xn16"], m["qkv"], m["obuf"])
                     A = Lw["ae_vid"][i]
-                    blocks.append((Lw["ln"][c0 + 1], lambda nxt, A=A, l=l: self._attn_block(
-                        ae, A, B, La, m["Lv"], A["w_qkv"][:d], A["b_qkv"][:d], m["kv_vid"], l * 2 * d,
-                        l * 2 * d + d, m["bits_vid"], m["xn16"], m["qkv"][:, :d], m["obuf"], nxt, m["ctr"])))
-
-                    def ffn_and_kv(nxt, Lw=Lw, l=l):
-                        self._ffn_block(ae, Lw["ae_ffn"][i], m["xn16"], m["hid"], nxt, m["ctr"], out16=m["ae16"])
-                        # K/V of this layer's ae_i for the target stream's auto_encoder_attn[i] (mtn.py:215):
-                        # the memory is the un-normed ae_i itself
-                        A2 = Lw["ae_attn"][i]
-                        _lib.linear(m["ae16"], A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=m["kv_ae"][l])
-                        S["ev"][l][i].record(side[i])
-                    blocks.append((Lw["ln"][c0 + 2], ffn_and_kv))
-                self._run_blocks(ae, m["xn16"], blocks, m["ctr"], fuse)
+                    self._attn_block(ae, Lw["ln"][c0 + 1], A, B, La, m["Lv"], A["w_qkv"][:d], A["b_qkv"][:d],
+                                     m["kv_vid"], l * 2 * d, l * 2 * d + d, m["bits_vid"], m["xn16"],
+                                     m["qkv"][:, :d], m["obuf"])
+                    self._ffn_block(ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], m["xn16"], m["hid"], out16=m["ae16"])
+                    # K/V of this layer's ae_i for the target stream's auto_encoder_attn[i] (mtn.py:215):
+                    # the memory is the un-normed ae_i itself
+                    A2 = Lw["ae_attn"][i]
+                    _lib.linear(m["ae16"], A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=m["kv_ae"][l])
+                    S["ev"][l][i].record(side[i])
                 nrm = W["ae_norm"][i]
                 _lib.layernorm(ae, nrm[0], nrm[1], nrm[2], out_f32=m["out"])          # mtn.py:162-163
         # ---- text memories on the caller's stream (overlaps with the side streams)
@@ -323,35 +294,25 @@ class DecoderEngine(object):
         order = (("src", "kv_q", "bits_q", "Q"), ("cap", "kv_cap", "bits_cap", "C")) \
             if ae_features in ("caption", "summary") else \
             (("cap", "kv_cap", "bits_cap", "C"), ("src", "kv_q", "bits_q", "Q"))
-        ctr = self._counters(0, dev)
-        fuse = d in (128, 256, 512, 1024) and rows <= 4096 * 128
-        blocks = []
         for l in range(N):
             Lw = W["layers"][l]
             A = Lw["self"]
-            blocks.append((Lw["ln"][0], lambda nxt, A=A: self._attn_block(
-                xs, A, B, T, T, A["w_qkv"], A["b_qkv"], None, 0, 0, bits_t, xn16, qkv, obuf, nxt, ctr)))
+            self._attn_block(xs, Lw["ln"][0], A, B, T, T, A["w_qkv"], A["b_qkv"], None, 0, 0, bits_t, xn16, qkv, obuf)
             kc, vc = l * 2 * d, l * 2 * d + d
             A = Lw["his"]
-            blocks.append((Lw["ln"][1], lambda nxt, A=A, kc=kc, vc=vc: self._attn_block(
-                xs, A, B, T, S["H"], A["w_qkv"][:d], A["b_qkv"][:d], S["kv_his"], kc, vc, S["bits_his"], xn16,
-                qkv[:, :d], obuf, nxt, ctr)))
+            self._attn_block(xs, Lw["ln"][1], A, B, T, S["H"], A["w_qkv"][:d], A["b_qkv"][:d], S["kv_his"], kc, vc,
+                             S["bits_his"], xn16, qkv[:, :d], obuf)
             for c, (name, kvn, bn, Ln) in enumerate(order):
                 A = Lw[name]
-                blocks.append((Lw["ln"][2 + c], lambda nxt, A=A, kc=kc, vc=vc, kvn=kvn, bn=bn, Ln=Ln: self._attn_block(
-                    xs, A, B, T, S[Ln], A["w_qkv"][:d], A["b_qkv"][:d], S[kvn], kc, vc, S[bn], xn16, qkv[:, :d],
-                    obuf, nxt, ctr)))
+                self._attn_block(xs, Lw["ln"][2 + c], A, B, T, S[Ln], A["w_qkv"][:d], A["b_qkv"][:d], S[kvn], kc, vc,
+                                 S[bn], xn16, qkv[:, :d], obuf)
             for i in range(M):
+                if fresh:
+                    main.wait_event(S["ev"][l][i])          # layer l's K/V of ae_i (side stream i)
                 A = Lw["ae_attn"][i]
-
-                def ae_site(nxt, A=A, l=l, i=i):
-                    if fresh:
-                        main.wait_event(S["ev"][l][i])          # layer l's K/V of ae_i (side stream i)
-                    self._attn_block(xs, A, B, T, S["La"], A["w_qkv"][:d], A["b_qkv"][:d], S["kv_ae"][l][i], 0, d,
-                                     S["bits_ae"], xn16, qkv[:, :d], obuf, nxt, ctr)
-                blocks.append((Lw["ln"][7 + 4 * i], ae_site))
-            blocks.append((Lw["ln"][4 + 4 * M], lambda nxt, Lw=Lw: self._ffn_block(xs, Lw["ffn"], xn16, hid, nxt, ctr)))
-        self._run_blocks(xs, xn16, blocks, ctr, fuse)
+                self._attn_block(xs, Lw["ln"][7 + 4 * i], A, B, T, S["La"], A["w_qkv"][:d], A["b_qkv"][:d],
+                                 S["kv_ae"][l][i], 0, d, S["bits_ae"], xn16, qkv[:, :d], obuf)
+            self._ffn_block(xs, Lw["ln"][4 + 4 * M], Lw["ffn"], xn16, hid)
         out = torch.empty(rows, d, dtype=torch.float32, device=dev)
         _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=out)   # mtn.py:164
         if fresh:

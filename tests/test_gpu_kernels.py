@@ -310,25 +310,3 @@ def test_generator_module(L):
     assert out.shape == (2, 9, 100)
     assert float((out.cpu() - ref).abs().max()) < 2e-2          # f16 operands: abs error on log-probs
     assert float((am.cpu() == ref.argmax(-1)).float().mean()) >= 0.9
-
-
-@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (8192, 512, 512), (130, 128, 64), (1000, 1024, 256)])
-def test_linear_fused_next_layernorm(L, M, N, K):
-    """out-proj + residual + the NEXT sublayer's LayerNorm in one launch (last CTA of an m-block normalises)."""
-    g = torch.Generator().manual_seed(M + N)
-    A = torch.randn(M, K, generator=g).half(); W = (torch.randn(N, K, generator=g) / K ** 0.5).half()
-    bias = torch.randn(N, generator=g); x = torch.randn(M, N, generator=g) * 2 + 0.3
-    a2 = 1 + 0.1 * torch.randn(N, generator=g); b2 = 0.1 * torch.randn(N, generator=g)
-    xd = dev(x)
-    xn = torch.zeros(M, N, device="cuda", dtype=torch.float16)
-    ctr = torch.zeros(4096, dtype=torch.int32, device="cuda")
-    for rep in range(2):        # second launch checks that the counters reset themselves
-        xd.copy_(dev(x))
-        L.linear(dev(A), dev(W), dev(bias), addend=xd, out_f32=xd, ln=(dev(a2), dev(b2), 1e-6), ln_out_f16=xn,
-                 ln_counters=ctr)
-        torch.cuda.synchronize()
-        ref_x = (x.double() + A.double() @ W.double().t() + bias.double()).float()
-        assert G.rel_err(xd.cpu(), ref_x) < 2e-5
-        ref_ln = O.layer_norm(xd.cpu(), a2, b2, 1e-6)        # LN of exactly what the kernel wrote
-        assert G.rel_err(xn.float().cpu(), ref_ln) < 6e-4
-        assert int(ctr.abs().sum()) == 0
