@@ -27,24 +27,29 @@ namespace mtn {
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_QT = 128;  // queries per CTA (UMMA M)
 
-// KT = keys per tile (UMMA N of the S MMA): 128, or 64 for short memories (Lk <= 64: caption /
-// query / auto-encoder sites) where a 128-key tile would be half padding.
+// KT = keys per tile (UMMA N of the S MMA): 96, or 64 for short memories (Lk <= 64: caption / query /
+// auto-encoder sites).  96 rather than 128 so that TWO S accumulators plus O fit in 256 TMEM columns
+// (2 x 96 + 64): the tensor core computes Q K^T of tile j+1 while the softmax warps are still on tile j,
+// and two CTAs still share an SM.
 template <int DK, int ATT_KT>
 struct AttnCfg {
   static constexpr int ROWB = DK * 2;  // bytes per smem row of Q/K/V == swizzle span
   static constexpr int Q_BYTES = ATT_QT * ROWB;
   static constexpr int KV_BYTES = ATT_KT * ROWB;
-  static constexpr int P_BYTES = ATT_QT * ATT_KT * 2;  // [128 x 64] f16 panels (KT/64 of them)
-  static constexpr int OFF_Q = 0;  // two Q buffers: the next work item's queries load during this one
-  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = OFF_V + KV_BYTES;
+  static constexpr int P_PANELS = (ATT_KT + 63) / 64;
+  static constexpr int P_BYTES = P_PANELS * ATT_QT * 128;  // [128 x 64] f16 panels, K-major, 128B swizzle
+  static constexpr int OFF_Q = 0;                       // two Q buffers (next work item's queries)
+  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;     // two K buffers (next tile's keys)
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
+  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
+  static constexpr int TOTAL = OFF_BAR + 192 + 1024;
   static constexpr uint64_t SWZ = (DK == 64) ? SWZ_128B : SWZ_64B;
   static constexpr uint32_t SBO = 8 * ROWB;  // 8-row swizzle atom
-  static constexpr uint32_t TMEM_COLS = 256;  // S: [0,128)  O: [128, 128+DK)
-  static constexpr uint32_t O_COL = 128;
+  static constexpr uint32_t TMEM_COLS = 256;  // S0: [0,KT)  S1: [KT,2KT)  O: [2KT, 2KT+DK)
+  static constexpr uint32_t O_COL = 2 * ATT_KT;
+  static_assert(2 * ATT_KT + DK <= 256, "TMEM budget");
+  static_assert((KV_BYTES % 1024) == 0 || DK == 32, "K/V buffers must stay swizzle-atom aligned");
 };
 
 struct AttnParams {
@@ -58,9 +63,10 @@ struct AttnParams {
   int ldo;
 };
 
-enum {
-  BAR_Q_FULL = 0 /* +1 */, BAR_Q_EMPTY = 2 /* +1 */, BAR_K_FULL = 4, BAR_K_EMPTY, BAR_V_FULL, BAR_V_EMPTY,
-  BAR_S_FULL, BAR_S_FREE, BAR_P_FULL, BAR_PV_DONE, BAR_COUNT
+enum {  // "+1": two barriers, one per buffer
+  BAR_Q_FULL = 0 /* +1 */, BAR_Q_EMPTY = 2 /* +1 */, BAR_K_FULL = 4 /* +1 */, BAR_K_EMPTY = 6 /* +1 */,
+  BAR_V_FULL = 8, BAR_V_EMPTY, BAR_S_FULL = 10 /* +1 */, BAR_S_FREE = 12 /* +1 */, BAR_P_FULL = 14, BAR_PV_DONE,
+  BAR_COUNT
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     for (int i = 0; i < BAR_COUNT; ++i)
-      mbar_init(bar(i), (i == BAR_S_FREE || i == BAR_P_FULL) ? 128u : 1u);
+      mbar_init(bar(i), (i == BAR_S_FREE || i == BAR_S_FREE + 1 || i == BAR_P_FULL) ? 128u : 1u);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base, tO = tmem_base + C::O_COL;
+  const uint32_t tO = tmem_base + C::O_COL;  // S buffers: tmem_base + (g & 1) * KT
   pdl_wait();
 
   if (warp == 0) {
@@ -119,10 +125,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         mbar_arrive_expect_tx(bar(BAR_Q_FULL + qb), C::Q_BYTES);
         tma_load_3d(sQ + qb * C::Q_BYTES, &tmQ, bar(BAR_Q_FULL + qb), hd * DK, qt * ATT_QT, b);
         for (int j = 0; j < nt; ++j, ++g) {
-          const uint32_t ph = g & 1;
-          mbar_wait(bar(BAR_K_EMPTY), ph ^ 1);
-          mbar_arrive_expect_tx(bar(BAR_K_FULL), C::KV_BYTES);
-          tma_load_3d(sK, &tmK, bar(BAR_K_FULL), hd * DK, j * ATT_KT, b);
+          const uint32_t ph = g & 1, kb = g & 1, kph = (g >> 1) & 1;
+          mbar_wait(bar(BAR_K_EMPTY + kb), kph ^ 1);
+          mbar_arrive_expect_tx(bar(BAR_K_FULL + kb), C::KV_BYTES);
+          tma_load_3d(sK + kb * C::KV_BYTES, &tmK, bar(BAR_K_FULL + kb), hd * DK, j * ATT_KT, b);
           mbar_wait(bar(BAR_V_EMPTY), ph ^ 1);
           mbar_arrive_expect_tx(bar(BAR_V_FULL), C::KV_BYTES);
           tma_load_3d(sV, &tmV, bar(BAR_V_FULL), hd * DK, j * ATT_KT, b);
@@ -133,42 +139,48 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     // -------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc_s = make_idesc_f16(ATT_QT, ATT_KT, 0, 0);  // S = Q K^T, both K-major
     constexpr uint32_t idesc_o = make_idesc_f16(ATT_QT, DK, 0, 1);      // O += P V,  V is MN-major
-    uint32_t n = 0, g = 0;
-    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++n) {
-      const uint32_t qb = n & 1;
-      mbar_wait(bar(BAR_Q_FULL + qb), (n >> 1) & 1);
-      for (int j = 0; j < nt; ++j, ++g) {
-        const uint32_t ph = g & 1;
-        mbar_wait(bar(BAR_K_FULL), ph);
-        mbar_wait(bar(BAR_S_FREE), ph ^ 1);  // softmax has finished reading S of the previous tile
-        tc_fence_after();
-        if (lane == 0) {
-          const uint64_t dq = make_smem_desc(sQ + qb * C::Q_BYTES, 16, C::SBO, C::SWZ);
-          const uint64_t dk = make_smem_desc(sK, 16, C::SBO, C::SWZ);
+    const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)my_items * (uint32_t)nt;  // tiles of this CTA, all items
+    // Q K^T runs ONE tile ahead of P V (it only needs the keys and a free S buffer), so the scores of
+    // tile g+1 -- possibly the first tile of the next work item -- are ready when the softmax warps
+    // finish tile g.
+    auto issue_qk = [&](uint32_t g) {
+      const uint32_t n = g / nt, j = g % nt, qb = n & 1, sb = g & 1, ph2 = (g >> 1) & 1;
+      if (j == 0) mbar_wait(bar(BAR_Q_FULL + qb), (n >> 1) & 1);
+      mbar_wait(bar(BAR_K_FULL + sb), ph2);
+      mbar_wait(bar(BAR_S_FREE + sb), ph2 ^ 1);  // softmax has finished reading this S buffer (tile g-2)
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dq = make_smem_desc(sQ + qb * C::Q_BYTES, 16, C::SBO, C::SWZ);
+        const uint64_t dk = make_smem_desc(sK + sb * C::KV_BYTES, 16, C::SBO, C::SWZ);
 #pragma unroll
-          for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          tc_commit(bar(BAR_K_EMPTY));
-          tc_commit(bar(BAR_S_FULL));
-          if (j == nt - 1) tc_commit(bar(BAR_Q_EMPTY + qb));  // last use of this item's queries
-        }
-        __syncwarp();
-        mbar_wait(bar(BAR_V_FULL), ph);
-        mbar_wait(bar(BAR_P_FULL), ph);  // P_j is in shared memory, O has been rescaled
-        tc_fence_after();
-        if (lane == 0) {
-#pragma unroll
-          for (int kk = 0; kk < ATT_KT / 16; ++kk) {
-            // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row
-            const uint64_t dp = make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
-            // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
-            const uint64_t dv = make_smem_desc(sV + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
-            tc_mma_f16(tO, dp, dv, idesc_o, (j | kk) != 0);
-          }
-          tc_commit(bar(BAR_V_EMPTY));
-          tc_commit(bar(BAR_PV_DONE));
-        }
-        __syncwarp();
+        for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tmem_base + sb * ATT_KT, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(bar(BAR_K_EMPTY + sb));
+        tc_commit(bar(BAR_S_FULL + sb));
+        if (j == (uint32_t)nt - 1) tc_commit(bar(BAR_Q_EMPTY + qb));  // last use of this item's queries
       }
+      __syncwarp();
+    };
+    if (total > 0) issue_qk(0);
+    for (uint32_t g = 0; g < total; ++g) {
+      if (g + 1 < total) issue_qk(g + 1);
+      const uint32_t ph = g & 1, j = g % nt;
+      mbar_wait(bar(BAR_V_FULL), ph);
+      mbar_wait(bar(BAR_P_FULL), ph);  // P_g is in shared memory, O has been rescaled
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < ATT_KT / 16; ++kk) {
+          // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row
+          const uint64_t dp = make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
+          // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
+          const uint64_t dv = make_smem_desc(sV + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
+          tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
+        }
+        tc_commit(bar(BAR_V_EMPTY));
+        tc_commit(bar(BAR_PV_DONE));
+      }
+      __syncwarp();
     }
   } else {
     // -------------------------------------------------------------- softmax + epilogue
@@ -200,9 +212,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         // shared memory; they only feed O rows that are never stored.
         for (int j = 0; j < nt; ++j, ++g) {
           const uint32_t ph = g & 1;
-          mbar_wait(bar(BAR_S_FULL), ph);
+          mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
           if (j > 0) mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
-          mbar_arrive(bar(BAR_S_FREE));
+          mbar_arrive(bar(BAR_S_FREE + ph));
           mbar_arrive(bar(BAR_P_FULL));
         }
         mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
@@ -211,7 +223,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 
       for (int j = 0; j < nt; ++j, ++g) {
         const uint32_t ph = g & 1;
-        mbar_wait(bar(BAR_S_FULL), ph);
+        const uint32_t tS = tmem_base + ph * ATT_KT;  // S buffer of this tile
+        mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
         tc_fence_after();
         // ---- pass 1: row maximum of the masked, scaled scores
         float m_tile = -CUDART_INF_F;
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           }
         }
         tc_fence_before();
-        mbar_arrive(bar(BAR_S_FREE));  // S may be overwritten by the next Q K^T
+        mbar_arrive(bar(BAR_S_FREE + ph));  // this S buffer may be overwritten by Q K^T of tile g+2
         const float alpha = ex2_approx(m_run - m_new);
         l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
@@ -452,7 +465,7 @@ extern "C" int mtn_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->Lk <= 64) return a->d_k == 64 ? mtn::launch_attn<64, 64>(*a, st) : mtn::launch_attn<32, 64>(*a, st);
-  return a->d_k == 64 ? mtn::launch_attn<64, 128>(*a, st) : mtn::launch_attn<32, 128>(*a, st);
+  return a->d_k == 64 ? mtn::launch_attn<64, 96>(*a, st) : mtn::launch_attn<32, 96>(*a, st);
 }
 
 extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
