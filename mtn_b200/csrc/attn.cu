@@ -226,44 +226,35 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         const uint32_t tS = tmem_base + ph * ATT_KT;  // S buffer of this tile
         mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
         tc_fence_after();
-        // ---- load the whole score tile into registers with ONE wait: a TMEM load costs a few hundred
-        // cycles of latency, and issuing the chunks back to back overlaps them (measured with in-kernel
-        // timestamps: per-chunk load+wait dominated both softmax passes).  The S buffer is released at once.
-        uint32_t r[NCH][32];
-        uint32_t keep[NCH], inb[NCH];
-        bool skip[NCH];  // warp-uniform: no kept in-range key for any row of the warp -> constant score
-#pragma unroll
+        // ---- pass 1: row maximum of the masked, scaled scores
+        float m_tile = -CUDART_INF_F;
+#pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
           const int k0 = j * ATT_KT + c * 32;
           const int nvalid = p.Lk - k0;  // keys of this chunk inside the sequence (warp-uniform)
-          inb[c] = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-          const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
-          keep[c] = mw & inb[c];
-          skip[c] = __all_sync(0xffffffffu, keep[c] == 0u);
-          if (!skip[c]) tc_ld32(tS + lane_off + c * 32, r[c]);
-        }
-        tc_wait_ld();
-        tc_fence_before();
-        mbar_arrive(bar(BAR_S_FREE + ph));  // this S buffer may be overwritten by Q K^T of tile g+2
-        // ---- row maximum of the masked, scaled scores
-        float m_tile = -CUDART_INF_F;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          if (inb[c] == 0u) continue;  // chunk entirely past the end of the sequence
-          if (skip[c]) {
+          if (nvalid <= 0) break;
+          const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+          const uint32_t mw = (mrow != nullptr) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
+          // chunk with no kept key for ANY row of the warp (padding tail of a key-padding mask):
+          // every in-range score is the constant -1e9, nothing to read from TMEM
+          if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
             m_tile = fmaxf(m_tile, t_masked);
-          } else if (keep[c] == 0xffffffffu) {
-            float mx[4] = {__uint_as_float(r[c][0]), __uint_as_float(r[c][1]), __uint_as_float(r[c][2]),
-                           __uint_as_float(r[c][3])};
+            continue;
+          }
+          uint32_t r[32];
+          tc_ld32(tS + lane_off + c * 32, r);
+          tc_wait_ld();
+          if ((mw & inb) == 0xffffffffu) {
+            float mx[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
 #pragma unroll
-            for (int i = 4; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[c][i]));  // 4 independent chains
+            for (int i = 4; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));  // 4 independent chains
             m_tile = fmaxf(m_tile, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float t = __uint_as_float(r[c][i]) * c1;
-              t = ((keep[c] >> i) & 1u) ? t : t_masked;
-              t = ((inb[c] >> i) & 1u) ? t : -CUDART_INF_F;
+              float t = __uint_as_float(r[i]) * c1;
+              t = ((mw >> i) & 1u) ? t : t_masked;
+              t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
               m_tile = fmaxf(m_tile, t);
             }
           }
@@ -275,36 +266,45 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
           tc_fence_after();
         }
-        // ---- p = 2^(t - m), row sum, f16 P tile to shared memory
+        // ---- pass 2: p = 2^(t - m), row sum, f16 P tile to shared memory
         float l4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent partial row sums
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
+          const int k0 = j * ATT_KT + c * 32;
+          const int nvalid = p.Lk - k0;
+          const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+          const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
           float e[32];
-          if (inb[c] == 0u) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) e[i] = 0.f;
-          } else if (skip[c]) {
+          if (nvalid > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
             // all in-range keys masked for every row of the warp: p = 2^(-1e9 log2e - m) is one value
             // per row (0 unless the whole row has been masked so far, then 1 -> uniform average)
             const float pm = ex2_approx(t_masked - m_new);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) e[i] = ((inb[c] >> i) & 1u) ? pm : 0.f;
-            l4[0] += pm * (float)__popc(inb[c]);
-          } else if (keep[c] == 0xffffffffu) {
+            for (int i = 0; i < 32; ++i) e[i] = ((inb >> i) & 1u) ? pm : 0.f;
+            l4[0] += pm * (float)__popc(inb);
+          } else if (nvalid > 0) {  // warp-uniform
+            uint32_t r[32];
+            tc_ld32(tS + lane_off + c * 32, r);
+            tc_wait_ld();
+            if ((mw & inb) == 0xffffffffu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              e[i] = ex2_approx(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
-              l4[i & 3] += e[i];
+              for (int i = 0; i < 32; ++i) {
+                e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c1, -m_new));
+                l4[i & 3] += e[i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float t = __uint_as_float(r[i]) * c1;
+                t = ((mw >> i) & 1u) ? t : t_masked;
+                t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+                e[i] = ex2_approx(t - m_new);
+                l4[i & 3] += e[i];
+              }
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float t = __uint_as_float(r[c][i]) * c1;
-              t = ((keep[c] >> i) & 1u) ? t : t_masked;
-              t = ((inb[c] >> i) & 1u) ? t : -CUDART_INF_F;
-              e[i] = ex2_approx(t - m_new);
-              l4[i & 3] += e[i];
-            }
+            for (int i = 0; i < 32; ++i) e[i] = 0.f;
           }
           const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * 128;
 #pragma unroll
@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
                          : "memory");
           }
         }
+        tc_fence_before();
+        mbar_arrive(bar(BAR_S_FREE + ph));  // this S buffer may be overwritten by Q K^T of tile g+2
         const float alpha = ex2_approx(m_run - m_new);
         l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
