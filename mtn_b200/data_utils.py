@@ -104,49 +104,67 @@ def greedy_decode(model, batch, max_len, start_symbol, pad_symbol=None):
     return ys
 
 
+class _BeamPool(object):
+    """The reference's per-step hypothesis pool (data_utils.py:223-234): grows to ``width`` entries, then a
+    candidate only enters by REPLACING the current worst entry (first minimal score), and the first
+    candidate that does not beat the worst ends the expansion of that hypothesis."""
+
+    def __init__(self, width):
+        self.width, self.entries, self.worst = width, [], 0
+
+    def _refresh_worst(self):
+        self.worst = min(range(len(self.entries)), key=lambda i: self.entries[i][1])
+
+    def offer(self, entry):
+        """entry = (tokens, score, prefix).  False <=> the pool is full and the entry was rejected."""
+        if len(self.entries) < self.width:
+            self.entries.append(entry)
+            if len(self.entries) == self.width:
+                self._refresh_worst()
+            return True
+        if self.entries[self.worst][1] < entry[1]:
+            self.entries[self.worst] = entry
+            self._refresh_worst()
+            return True
+        return False
+
+
 def beam_search_decode(model, batch, max_len, start_symbol, unk_symbol, end_symbol, pad_symbol, beam=5,
                        penalty=1.0, nbest=5, min_len=1):
-    """Same search rules as the reference (data_utils.py:188-242): batch-1, hypotheses are
-    expanded best-first skipping <unk>/<eos>, an argmin-replacement beam, EOS hypotheses
-    scored lp + penalty*(len+1) once l >= min_len, n-best sorted by score."""
+    """Beam search with the reference's rules (data_utils.py:188-242): batch of one dialogue; each live
+    hypothesis is expanded best-token-first, never with <unk> or <eos>; from step ``min_len`` on every live
+    hypothesis also contributes a finished candidate scored ``logp[eos] + penalty * (len + 1)``; the n-best
+    finished candidates and the best finished score are returned.  Every ``model.decode`` call after the
+    first reuses the engine's cached memory stage (hoisted K/V, QAE branch)."""
     his_mem, cap_mem, q_mem, vid_mem, ae_ft = _encode_batch(model, batch)
-    q = batch.query
-    ds = torch.full((1, 1), start_symbol, dtype=q.dtype, device=q.device)
-    hyplist = [([], 0., ds)]
-    best_state = None
-    comp_hyplist = []
-    for l in range(max_len):
-        new_hyplist = []
-        argmin = 0
-        for out, lp, st in hyplist:
-            output = model.decode(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask,
-                                  batch.cap_mask, batch.query_mask, st,
-                                  subsequent_mask(st.size(1), st.device), ae_ft)
-            logp = model.generator(output[0][:, -1])
-            lp_vec = np.squeeze(logp.cpu().data.numpy() + lp)
-            if l >= min_len:
-                new_lp = lp_vec[end_symbol] + penalty * (len(out) + 1)
-                comp_hyplist.append((out, new_lp))
-                if best_state is None or best_state < new_lp:
-                    best_state = new_lp
-            for o in np.argsort(lp_vec)[::-1]:
-                if o == unk_symbol or o == end_symbol:
+    ids = batch.query
+
+    def next_logp(prefix):
+        dec = model.decode(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask, batch.cap_mask,
+                           batch.query_mask, prefix, subsequent_mask(prefix.size(1), prefix.device), ae_ft)
+        dec = dec[0] if isinstance(dec, (tuple, list)) else dec
+        return np.squeeze(model.generator(dec[:, -1]).cpu().data.numpy())
+
+    def extend(prefix, token):
+        return torch.cat([prefix, torch.full((1, 1), int(token), dtype=ids.dtype, device=ids.device)], dim=1)
+
+    live = [([], 0., torch.full((1, 1), start_symbol, dtype=ids.dtype, device=ids.device))]
+    finished, best_finished = [], None
+    for step in range(max_len):
+        pool = _BeamPool(beam)
+        for tokens, score, prefix in live:
+            scores = next_logp(prefix) + score
+            if step >= min_len:
+                done = scores[end_symbol] + penalty * (len(tokens) + 1)
+                finished.append((tokens, done))
+                if best_finished is None or best_finished < done:
+                    best_finished = done
+            for tok in np.argsort(scores)[::-1]:
+                if tok == unk_symbol or tok == end_symbol:
                     continue
-                new_lp = lp_vec[o]
-                if len(new_hyplist) == beam:
-                    if new_hyplist[argmin][1] < new_lp:
-                        new_st = torch.cat([st, torch.full((1, 1), int(o), dtype=q.dtype, device=q.device)], dim=1)
-                        new_hyplist[argmin] = (out + [o], new_lp, new_st)
-                        argmin = min(enumerate(new_hyplist), key=lambda h: h[1][1])[0]
-                    else:
-                        break
-                else:
-                    new_st = torch.cat([st, torch.full((1, 1), int(o), dtype=q.dtype, device=q.device)], dim=1)
-                    new_hyplist.append((out + [o], new_lp, new_st))
-                    if len(new_hyplist) == beam:
-                        argmin = min(enumerate(new_hyplist), key=lambda h: h[1][1])[0]
-        hyplist = new_hyplist
-    if len(comp_hyplist) > 0:
-        maxhyps = sorted(comp_hyplist, key=lambda h: -h[1])[:nbest]
-        return maxhyps, best_state
+                if not pool.offer((tokens + [tok], scores[tok], extend(prefix, tok))):
+                    break
+        live = pool.entries
+    if finished:
+        return sorted(finished, key=lambda h: -h[1])[:nbest], best_finished
     return [([], 0)], None
