@@ -166,6 +166,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int q = warp & 3;    // TMEM lane quarter this warp may access
     const int half = ew >> 2;  // 0: even chunks, 1: odd chunks
     float4* xp = reinterpret_cast<float4*>(smem + L::XPOSE_OFF + ew * STAGE_TILE_BYTES);
+    // In-place residual (x += A W^T + b, the common SublayerConnection case): the add is done by L2
+    // reductions (red.global.add.v4.f32) -- the 16 MB residual read that makes these launches
+    // L2-bandwidth bound disappears and each element still receives exactly one f32 add.
+    const bool red_add = epi.addend != nullptr && epi.addend == epi.out32 && epi.add_period == 0 &&
+                         epi.ld_add == epi.ld32 && epi.out16 == nullptr;
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
     // shared-memory slots of the transpose tile (float4 units); (row & 7) == sub_r for every row this lane reads
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + col + 4));
         }
         float4 res[8];
-        if (epi.addend != nullptr) {  // residual / positional operand: requested before touching TMEM
+        if (epi.addend != nullptr && !red_add) {  // residual / positional operand: requested before touching TMEM
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             res[2 * i] = res[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -240,12 +245,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
             x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
           }
-          if (epi.addend != nullptr) {
+          if (epi.addend != nullptr && !red_add) {
             x0.x += res[2 * i].x; x0.y += res[2 * i].y; x0.z += res[2 * i].z; x0.w += res[2 * i].w;
             x1.x += res[2 * i + 1].x; x1.y += res[2 * i + 1].y; x1.z += res[2 * i + 1].z; x1.w += res[2 * i + 1].w;
           }
           if (row_ok[i] && col_ok) {
-            if (epi.out32 != nullptr) {
+            if (red_add) {
+              float* o = epi.out32 + off32[i] + col;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x0.x), "f"(x0.y), "f"(x0.z),
+                           "f"(x0.w)
+                           : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(x1.x), "f"(x1.y),
+                           "f"(x1.z), "f"(x1.w)
+                           : "memory");
+            } else if (epi.out32 != nullptr) {
               float4* o = reinterpret_cast<float4*>(epi.out32 + off32[i] + col);
               o[0] = x0;
               o[1] = x1;
