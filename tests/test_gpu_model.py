@@ -311,3 +311,41 @@ def test_edge_shapes(M):
         e = [G.rel_err(out.cpu(), ref_out), G.rel_err(ae[0].cpu(), ref_ae[0]), G.rel_err(ae[1].cpu(), ref_ae[1])]
         print((B, Q, C, H, T, Lv), e)
         assert max(e) <= TOL, ((B, Q, C, H, T, Lv), e)
+
+
+def test_c_abi_site_with_hoisted_kv(M):
+    """mtn_attn_site_fwd with K/V hoisted out of the layer loop (the `kv` argument): project the memory
+    once with mtn_linear_fwd into a [B*Lk, 2d] buffer, then run the site on it; must equal the site that
+    projects the memory itself, and the reference golden."""
+    import ctypes as C
+    mtn, _ = M
+    from mtn_b200 import _lib
+    z = G.load("site_d128.npz")
+    sub, att, ff = _site_modules(mtn, z)
+    d, h = 128, int(z["h"])
+    x, mem, km = G.t(z["x"]).cuda(), G.t(z["mem"]).cuda(), G.t(z["kmask"]).cuda()
+    B, Lq, Lk = x.shape[0], x.shape[1], mem.shape[1]
+    W = att._weights()
+    mem16 = _lib.cast_f16(mem.contiguous().view(-1, d))
+    pad = 64                                             # K at column 64, V at column 64 + d of a wider buffer
+    kv = torch.zeros(B * Lk, pad + 2 * d, dtype=torch.float16, device="cuda")
+    _lib.linear(mem16, W["w_qkv"][d:], W["b_qkv"][d:], out_f16=kv[:, pad:])
+    bits = _lib.mask_pack(km)
+    out = torch.empty_like(x)
+    a = _lib.AttnSiteArgs()
+    a.B, a.Lq, a.Lk, a.d, a.h = B, Lq, Lk, d, h
+    a.x, a.x_out = x.data_ptr(), out.data_ptr()
+    a.ln_a, a.ln_b, a.ln_eps = sub.norm.a_2.data_ptr(), sub.norm.b_2.data_ptr(), sub.norm.eps
+    wq, bq = W["w_qkv"][:d], W["b_qkv"][:d]
+    a.w_q, a.b_q, a.w_o, a.b_o = wq.data_ptr(), bq.data_ptr(), W["w_o"].data_ptr(), W["b_o"].data_ptr()
+    a.kv, a.ld_kv, a.kv_k_col, a.kv_v_col = kv.data_ptr(), kv.stride(0), pad, pad + d
+    a.mask_bits, a.mask_rows_q = bits.data_ptr(), bits.shape[1]
+    n = _lib.lib().mtn_attn_site_workspace_bytes(B, Lq, Lk, d)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    a.workspace, a.workspace_bytes = ws.data_ptr(), n
+    _lib.check(_lib.lib().mtn_attn_site_fwd(C.byref(a), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert G.rel_err(out.cpu(), G.t(z["y_cross"])) <= TOL
+    a.workspace_bytes = 1024                             # too small -> error code, not a crash
+    rc = _lib.lib().mtn_attn_site_fwd(C.byref(a), _lib.stream_ptr())
+    assert rc == -3 and b"workspace" in _lib.lib().mtn_last_error()
