@@ -165,9 +165,11 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, B):
-    return {"workload": "MTN EncoderDecoder.forward, BASELINE configs[1]: N=6 d_model=512 h=8 d_ff=2048, "
-                        "batch=%d/GPU, query=caption=64, history=256, I3D 2048-d x512 + VGGish 128-d x256, "
-                        "target len %d, ragged padding" % (B, args.tgt_len),
+    return {"workload": "MTN EncoderDecoder.forward, BASELINE configs[%s]: N=%d d_model=%d h=%d d_ff=%d, "
+                        "batch=%d/GPU, query=caption=64, history=256, I3D 2048-d x%d + VGGish 128-d x%d, "
+                        "target len %d, ragged padding" % ("1" if args.preset == "cfg2" else "4", CFG["N"], CFG["d_model"],
+                                                           CFG["h"], CFG["d_ff"], B, SHAPE["Lv"][0], SHAPE["Lv"][1],
+                                                           args.tgt_len),
             "global_batch": B * args.gpus, "tgt_len": args.tgt_len, "parallelism": "dp%d (independent dialogue "
             "batches per GPU, no data-path collective in forward)" % args.gpus,
             "l2": "inputs rotate over %d distinct batches per GPU (> L2 working set: features alone are 138 MB "
@@ -184,12 +186,22 @@ def main():
     ap.add_argument("--batch", type=int, default=SHAPE["B"])
     ap.add_argument("--rot", type=int, default=4, help="distinct input batches rotated through")
     ap.add_argument("--cpu-batch", type=int, default=4, help="dialogues in the CPU-baseline sample")
+    ap.add_argument("--preset", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 = BASELINE configs[1] (the metric's config, default); cfg5 = configs[4] stress config "
+                         "(N=12 d=1024 h=16 d_ff=4096, video_len=1024, batch 4/GPU) for roofline captures")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the auxiliary greedy-decode (configs[3]) leg")
     ap.add_argument("--decode-batch", type=int, default=64)
     ap.add_argument("--decode-len", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.preset == "cfg5":
+        CFG.update({"N": 12, "d_model": 1024, "d_ff": 4096, "h": 16})
+        SHAPE.update({"B": 4, "Lv": [1024, 256]})
+        if args.batch == 32:
+            args.batch = 4
+        global METRIC
+        METRIC = "decoder tokens/sec at d_model=1024 h=16 L=12 (forward, stress config)"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

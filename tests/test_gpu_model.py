@@ -349,3 +349,31 @@ def test_c_abi_site_with_hoisted_kv(M):
     a.workspace_bytes = 1024                             # too small -> error code, not a crash
     rc = _lib.lib().mtn_attn_site_fwd(C.byref(a), _lib.stream_ptr())
     assert rc == -3 and b"workspace" in _lib.lib().mtn_last_error()
+
+
+def test_attention_function_and_numpy_batch(M):
+    """mtn.attention (mtn.py:221-231 signature, (B,h,L,d_k) views) and Batch built from the reference's
+    numpy (L, B, F) feature arrays (data_utils.py:28)."""
+    mtn, du = M
+    g = torch.Generator().manual_seed(2)
+    B, h, Lq, Lk, dk = 2, 4, 9, 21, 32
+    q = torch.randn(B, Lq, h * dk, generator=g); k = torch.randn(B, Lk, h * dk, generator=g)
+    v = torch.randn(B, Lk, h * dk, generator=g)
+    mask = torch.ones(B, 1, Lk, dtype=torch.bool); mask[1, 0, 15:] = False
+    split = lambda t, L: t.view(B, L, h, dk).transpose(1, 2)
+    ref, _ = O.attention(split(q.half().float(), Lq), split(k.half().float(), Lk), split(v.half().float(), Lk),
+                         mask.unsqueeze(1))
+    with torch.no_grad():
+        out, p = mtn.attention(split(q.cuda(), Lq), split(k.cuda(), Lk), split(v.cuda(), Lk), mask.cuda().unsqueeze(1))
+    assert p is None and out.shape == (B, h, Lq, dk)
+    assert G.rel_err(out.cpu(), ref) < 1e-3
+    cfg = {"vocab": 30, "ft_sizes": [64, 16]}
+    inp = O.synth_inputs(cfg, B=3, Q=4, C=4, H=5, T=4, Lv=[7, 5], seed=1)
+    np_fts = [f.permute(1, 0, 2).contiguous().numpy() for f in inp["fts"]]          # (L, B, F) numpy
+    b = du.Batch(inp["query"].cuda(), inp["his"].cuda(), None, np_fts, inp["cap"].cuda(), inp["trg"].cuda(),
+                 inp["trg_y"].cuda(), 1)
+    m = O.make_masks(inp["query"], inp["his"], inp["cap"], inp["trg"], inp["fts"], 1)
+    for i in range(2):
+        assert b.fts[i].is_cuda and torch.equal(b.fts_mask[i].cpu(), m["fts_mask"][i])
+        assert torch.equal(b.fts[i].float().cpu(), m["fts"][i].half().float())
+    assert torch.equal(b.trg_mask.cpu(), m["trg_mask"])
