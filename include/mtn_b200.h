@@ -79,6 +79,18 @@ int mtn_feature_prep_fwd(const float *ft, int frames, int F, uint8_t *mask, void
 int mtn_log_softmax_fwd(const float *x, int ldx, int rows, int V, float *y, int ldy,
                         int64_t *argmax, void *stream);
 
+/* ---- label-smoothed loss (forward) -----------------------------------
+ * Replaces LabelSmoothing.forward (label_smoothing.py:20-32: smoothed one-hot target, padding column
+ * zeroed, padding rows zeroed with the reference's index-sum quirk) + nn.KLDivLoss(sum) applied to
+ * log_softmax(logits), computed per row from the logits (or from log-probabilities -- same formula):
+ *     loss[0] (+)= scale * sum_rows KL(true_dist_r || softmax(logits_r))
+ * `accumulate` != 0 adds to loss[0] (main loss + lambda * auto-encoder losses, data_utils.py:133-151);
+ * `scale` carries 1/norm.  Deterministic (fixed-order reductions).  target: [rows] int64.            */
+size_t mtn_label_smoothing_workspace_bytes(int rows);
+int mtn_label_smoothing_loss_fwd(const float *logits, int ld, int rows, int V, const int64_t *target,
+                                 int64_t padding_idx, float smoothing, float scale, int accumulate,
+                                 float *loss, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- casts / packing -----------------------------------------------------------
  * dst[r, c] = (f16) src[r, c]  (round-to-nearest-even, saturating to +-65504).
  * Used to pack nn.Linear weights once per parameter version and to convert module

@@ -67,6 +67,9 @@ SYMBOLS = {
     "mtn_feature_prep_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_log_softmax_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p]),
+    "mtn_label_smoothing_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "mtn_label_smoothing_loss_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_float,
+                                               C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mtn_cast_f32_to_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p]),
     "mtn_mask_words": (C.c_int, [C.c_int]),
@@ -288,3 +291,19 @@ def log_softmax(x, V, out=None, argmax=None):
             lambda: lib().mtn_log_softmax_fwd(ptr(x), x.stride(0), x.shape[0], V, ptr(out),
                                               out.stride(0) if out is not None else 0, ptr(argmax), stream_ptr()),
             keep=(x, out, argmax))
+
+
+def label_smoothing_loss(logits, V, target, padding_idx, smoothing, loss, scale=1.0, accumulate=False):
+    """loss[0] (+)= scale * KL-sum of the label-smoothed target vs softmax(logits[:, :V]) (label_smoothing.py:20-32).
+    logits: [rows, ld >= V] f32 (logits or log-probs); target: [rows] int64; loss: 1-element f32 tensor."""
+    _req(logits, torch.float32, "logits"); _req(loss, torch.float32, "loss")
+    assert logits.dim() == 2 and target.dtype == torch.int64 and target.is_cuda and target.numel() == logits.shape[0]
+    tc = target.contiguous()
+    rows = logits.shape[0]
+    nbytes = lib().mtn_label_smoothing_workspace_bytes(rows)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+    _launch("label_smoothing", 0, rows * V * 8,
+            lambda: lib().mtn_label_smoothing_loss_fwd(ptr(logits), logits.stride(0), rows, V, ptr(tc), int(padding_idx),
+                                                       float(smoothing), float(scale), 1 if accumulate else 0, ptr(loss),
+                                                       ptr(ws), nbytes, stream_ptr()),
+            keep=(logits, tc, loss, ws))

@@ -341,6 +341,114 @@ extern "C" int mtn_mask_pack(const uint8_t* mask_u8, int B, int rows_q, int Lk, 
   return MTN_OK;
 }
 
+namespace mtn {
+// ----------------------------------------------------------------------------
+// Label-smoothed KL loss (label_smoothing.py:20-32 + nn.KLDivLoss(sum)) straight from logits, without
+// materialising log-probabilities or the dense target distribution.  Row r, target y, padding column p,
+// s = smoothing / (V - 2), conf = 1 - smoothing, logp_v = z_v - lse:
+//   y != p :  conf (log conf - logp_y) + s [ (V-2) log s - (sum_v logp_v - logp_y - logp_p) ]
+//   y == p :  0 if padding rows are zeroed, else  s [ (V-1) log s - (sum_v logp_v - logp_p) ]
+// "Padding rows are zeroed" reproduces the reference's quirk: only if the SUM OF THE INDICES of the padding
+// rows is > 0 (label_smoothing.py:26-30: a lone padding target in row 0 is not zeroed).
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pad_index_sum_kernel(const long long* __restrict__ tgt, int rows, long long pad,
+                                                             unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long sh[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  unsigned long long acc = 0;
+  for (int r = threadIdx.x; r < rows; r += 1024) acc += (tgt[r] == pad) ? (unsigned long long)r : 0ull;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 32; ++w) t += sh[w];
+    *out = t;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    label_smoothing_rows_kernel(const float* __restrict__ z, int ldz, int V, const long long* __restrict__ tgt,
+                                long long pad, float smoothing, const unsigned long long* __restrict__ pad_index_sum,
+                                float* __restrict__ row_loss) {
+  __shared__ float sh[4];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.x;
+  const float* zr = z + (size_t)r * ldz;
+  const long long y = tgt[r];
+  float mx = -3.4e38f, sum = 0.f;
+  for (int i = threadIdx.x; i < V; i += 128) {
+    const float v = zr[i];
+    mx = fmaxf(mx, v);
+    sum += v;
+  }
+  const float m = block_reduce_128(mx, true, sh);
+  const float zsum = block_reduce_128(sum, false, sh);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < V; i += 128) se += __expf(zr[i] - m);
+  const float lse = m + __logf(block_reduce_128(se, false, sh));
+  if (threadIdx.x != 0) return;
+  const float s = smoothing / (float)(V - 2), conf = 1.f - smoothing;
+  const float sum_logp = zsum - (float)V * lse;
+  const float logp_p = zr[pad] - lse;
+  const float s_log_s = s > 0.f ? __logf(s) : 0.f;
+  float loss;
+  if (y != pad) {
+    const float logp_y = zr[y] - lse;
+    loss = (conf > 0.f ? conf * (__logf(conf) - logp_y) : 0.f) +
+           (s > 0.f ? s * ((float)(V - 2) * s_log_s - (sum_logp - logp_y - logp_p)) : 0.f);
+  } else if (*pad_index_sum > 0ull) {
+    loss = 0.f;
+  } else {
+    loss = s > 0.f ? s * ((float)(V - 1) * s_log_s - (sum_logp - logp_p)) : 0.f;
+  }
+  row_loss[r] = loss;
+}
+
+// deterministic (fixed-order) sum of n floats, scaled: out[0] (+)= scale * sum
+__global__ void __launch_bounds__(1024) sum_scaled_kernel(const float* __restrict__ x, int n, float scale, int accumulate,
+                                                          float* __restrict__ out) {
+  __shared__ float sh[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += x[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += sh[w];
+    out[0] = (accumulate ? out[0] : 0.f) + scale * t;
+  }
+}
+}  // namespace mtn
+
+extern "C" size_t mtn_label_smoothing_workspace_bytes(int rows) { return 256 + (size_t)rows * 4; }
+
+extern "C" int mtn_label_smoothing_loss_fwd(const float* logits, int ld, int rows, int V, const int64_t* target,
+                                            int64_t padding_idx, float smoothing, float scale, int accumulate,
+                                            float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(logits && target && loss, MTN_E_ARG, "label_smoothing: NULL pointer");
+  MTN_REQUIRE(rows > 0 && V > 2 && ld >= V && padding_idx >= 0 && padding_idx < V, MTN_E_SHAPE,
+              "label_smoothing: rows=%d V=%d ld=%d padding_idx=%lld", rows, V, ld, (long long)padding_idx);
+  MTN_REQUIRE(workspace && workspace_bytes >= mtn_label_smoothing_workspace_bytes(rows) && aligned16(workspace),
+              MTN_E_WORKSPACE, "label_smoothing: workspace too small or misaligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* flag = reinterpret_cast<unsigned long long*>(workspace);
+  float* row_loss = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 256);
+  const long long* t64 = reinterpret_cast<const long long*>(target);
+  MTN_CHECK_CUDA(launch_kernel(pad_index_sum_kernel, dim3(1), dim3(1024), 0, st, t64, rows, (long long)padding_idx, flag));
+  MTN_CHECK_CUDA(launch_kernel(label_smoothing_rows_kernel, dim3(rows), dim3(128), 0, st, logits, ld, V, t64,
+                               (long long)padding_idx, smoothing, (const unsigned long long*)flag, row_loss));
+  MTN_CHECK_CUDA(launch_kernel(sum_scaled_kernel, dim3(1), dim3(1024), 0, st, (const float*)row_loss, rows, scale,
+                               accumulate, loss));
+  return MTN_OK;
+}
+
 extern "C" int mtn_embed_fwd(const int64_t* ids, const float* lut, const float* pe, int rows, int L, int d, int vocab,
                              float scale, const float* a_2, const float* b_2, float eps, float* y_f32, void* y_f16,
                              void* stream) {

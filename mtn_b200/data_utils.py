@@ -71,6 +71,32 @@ class Batch:
         return (tgt != pad).unsqueeze(-2) & subsequent_mask(tgt.size(-1), tgt.device)
 
 
+class SimpleLossCompute:
+    """Evaluation half of the reference's SimpleLossCompute (data_utils.py:123-156): main loss / norm plus
+    l * sum_i auto-encoder loss_i / ae_norm (every stream through ``generator`` unless ``ae_generator`` is
+    given), returned as ``loss * norm`` like the reference.  The generator's logits feed the fused
+    label-smoothing kernel directly.  Training (``opt`` given) needs the backward kernels: not implemented."""
+
+    def __init__(self, generator, ae_generator, criterion, opt=None, l=1.0):
+        if opt is not None:
+            raise NotImplementedError("mtn_b200: training (loss.backward / optimizer step) is not implemented "
+                                      "in this round; use opt=None for evaluation (train.py:204-209)")
+        self.generator, self.ae_generator, self.criterion, self.opt, self.l = generator, ae_generator, criterion, opt, l
+
+    def __call__(self, x, y, norm, ae_x=None, ae_y=None, ae_norm=None):
+        total = torch.zeros(1, dtype=torch.float32, device=x.device)
+        logits, V = self.generator._logits(x)
+        self.criterion.from_logits(logits, V, y, scale=1.0 / float(norm), out=total)
+        if ae_x is not None:
+            streams = ae_x if isinstance(ae_x, (list, tuple)) else [ae_x]
+            for i, ae_in in enumerate(streams):
+                gen = self.generator if self.ae_generator is None else (
+                    self.ae_generator[i] if isinstance(ae_x, (list, tuple)) else self.ae_generator)
+                lg, Vg = gen._logits(ae_in)
+                self.criterion.from_logits(lg, Vg, ae_y, scale=self.l / float(ae_norm), out=total, accumulate=True)
+        return total.item() * float(norm)
+
+
 def encode(model, his, his_st, his_mask, cap, cap_mask, query, query_mask, video_features,
            video_features_mask):
     q_mem, vid_mem, cap_mem, his_mem, ae_ft = model.encode(query, query_mask, his, his_mask, cap,

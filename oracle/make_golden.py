@@ -202,6 +202,22 @@ def main():
               trg=inp["trg"].numpy(), trg_y=inp["trg_y"].numpy(), ft0=inp["fts"][0].numpy(),
               ft1=inp["fts"][1].numpy(), out=out3.numpy(), ae0=ae3[0].numpy(), ae1=ae3[1].numpy())
     np.savez_compressed(os.path.join(OUT, "mini512.npz"), **md)
+    # ---- label smoothing (label_smoothing.py) incl. the padding-row index-sum quirk
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_label_smoothing", os.path.join(ref_loader.ref_dir(), "label_smoothing.py"))
+    ref_ls = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref_ls)
+    g = torch.Generator().manual_seed(8)
+    ls = {}
+    for name, tgt in (("mixed", [5, 1, 7, 1, 2, 9]), ("quirk_pad_row0_only", [1, 4, 6, 3, 2, 8]), ("nopad", [5, 3, 7, 4, 2, 9])):
+        logp = torch.log_softmax(torch.randn(6, 12, generator=g) * 2, -1)
+        crit = ref_ls.LabelSmoothing(size=12, padding_idx=1, smoothing=0.1)
+        ls[name + "/logp"] = logp.numpy(); ls[name + "/target"] = np.array(tgt, np.int64)
+        ls[name + "/loss"] = np.float32(crit(logp, torch.tensor(tgt)).item())
+    crit0 = ref_ls.LabelSmoothing(size=12, padding_idx=1, smoothing=0.0)
+    ls["nosmooth/logp"] = ls["mixed/logp"]; ls["nosmooth/target"] = ls["mixed/target"]
+    ls["nosmooth/loss"] = np.float32(crit0(torch.from_numpy(ls["mixed/logp"]), torch.from_numpy(ls["mixed/target"])).item())
+    np.savez(os.path.join(OUT, "label_smoothing.npz"), **ls)
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

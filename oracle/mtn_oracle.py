@@ -212,6 +212,33 @@ def generator(sd, x):
     return torch.log_softmax(linear(x, sd["generator.proj.weight"], sd["generator.proj.bias"]), dim=-1)
 
 
+def label_smoothing_loss(logp, target, size, padding_idx, smoothing):
+    """label_smoothing.py:20-32 + nn.KLDivLoss(size_average=False): sum over rows of KL(true_dist || exp(logp)).
+    true_dist: smoothing/(size-2) everywhere, 1-smoothing at the target, 0 in the padding column; rows whose
+    target is padding are zeroed ONLY IF the sum of their row indices is > 0 (the reference tests
+    ``mask.sum() > 0`` on the index tensor, label_smoothing.py:26-30)."""
+    assert logp.shape[1] == size
+    t = torch.full_like(logp, smoothing / (size - 2))
+    t.scatter_(1, target.unsqueeze(1), 1.0 - smoothing)
+    t[:, padding_idx] = 0
+    idx = torch.nonzero(target == padding_idx)
+    if idx.sum() > 0 and len(idx) > 0:
+        t.index_fill_(0, idx.squeeze(1), 0.0)
+    return torch.nn.functional.kl_div(logp, t, reduction="sum")
+
+
+def simple_loss(sd, cfg, out, trg_y, ae_out, ae_y, pad=1, smoothing=0.1, lam=1.0):
+    """data_utils.py:132-156 (evaluation, opt=None): returns loss * norm like the reference."""
+    V = sd["generator.proj.weight"].shape[0]
+    norm = (trg_y != pad).sum().float()
+    loss = label_smoothing_loss(generator(sd, out).reshape(-1, V), trg_y.reshape(-1), V, pad, smoothing) / norm
+    ae_norm = (ae_y != pad).sum().float()
+    for a in ae_out:
+        loss = loss + lam * label_smoothing_loss(generator(sd, a).reshape(-1, V), ae_y.reshape(-1), V, pad,
+                                                 smoothing) / ae_norm
+    return float(loss) * float(norm)
+
+
 def greedy_decode(sd, cfg, query, his, cap, fts, max_len, sos=2, pad=1):
     """The *intended* semantics of data_utils.py:162-186, using the working call
     form of data_utils.py:202-210 (the reference's greedy_decode raises TypeError;

@@ -310,3 +310,39 @@ def test_generator_module(L):
     assert out.shape == (2, 9, 100)
     assert float((out.cpu() - ref).abs().max()) < 2e-2          # f16 operands: abs error on log-probs
     assert float((am.cpu() == ref.argmax(-1)).float().mean()) >= 0.9
+
+
+@pytest.mark.parametrize("name,smoothing", [("mixed", 0.1), ("quirk_pad_row0_only", 0.1), ("nopad", 0.1), ("nosmooth", 0.0)])
+def test_label_smoothing_kernel_vs_reference_golden(L, name, smoothing):
+    z = G.load("label_smoothing.npz")
+    logp, tgt = G.t(z[name + "/logp"]), G.t(z[name + "/target"])
+    loss = torch.zeros(1, device="cuda")
+    L.label_smoothing_loss(dev(logp), 12, dev(tgt), 1, smoothing, loss)
+    raw = logp + 3.7                                    # un-normalised logits give the same loss
+    loss2 = torch.full((1,), 5.0, device="cuda")
+    L.label_smoothing_loss(dev(raw), 12, dev(tgt), 1, smoothing, loss2, scale=0.5, accumulate=True)
+    torch.cuda.synchronize()
+    ref = float(z[name + "/loss"])
+    assert abs(float(loss) - ref) <= 2e-5 * max(1.0, abs(ref))
+    assert abs(float(loss2) - (5.0 + 0.5 * ref)) <= 2e-5 * max(1.0, abs(ref))
+
+
+def test_simple_loss_compute_eval(L):
+    """SimpleLossCompute (data_utils.py:123-156, opt=None) on the fused generator + label-smoothing path vs the oracle."""
+    from mtn_b200 import mtn, data_utils, label_smoothing
+    g = torch.Generator().manual_seed(4)
+    V, d = 96, 128
+    sd = {"generator.proj.weight": torch.randn(V, d, generator=g) * 0.3, "generator.proj.bias": torch.randn(V, generator=g)}
+    gen = mtn.Generator(d, V); gen.load_state_dict({"proj.weight": sd["generator.proj.weight"], "proj.bias": sd["generator.proj.bias"]})
+    gen = gen.cuda().eval()
+    out = torch.randn(3, 7, d, generator=g); ae = [torch.randn(3, 5, d, generator=g) for _ in range(2)]
+    trg_y = torch.randint(2, V, (3, 7), generator=g); trg_y[1, 4:] = 1
+    qy = torch.randint(2, V, (3, 5), generator=g); qy[2, 3:] = 1
+    ref = O.simple_loss(sd, {}, out, trg_y, ae, qy)
+    crit = label_smoothing.LabelSmoothing(size=V, padding_idx=1, smoothing=0.1)
+    lc = data_utils.SimpleLossCompute(gen, None, crit, opt=None)
+    with torch.no_grad():
+        got = lc(dev(out), dev(trg_y), (trg_y != 1).sum(), [dev(a) for a in ae], dev(qy), (qy != 1).sum())
+    assert abs(got - ref) <= 2e-3 * abs(ref), (got, ref)        # f16 generator operands
+    with pytest.raises(NotImplementedError):
+        data_utils.SimpleLossCompute(gen, None, crit, opt=object())

@@ -145,3 +145,12 @@ def test_live_reference_bitexact():
     assert all(torch.equal(a, b_) for a, b_ in zip(ae, ae_r))
     # state_dict key contract
     assert set(sd.keys()) == set(model.state_dict().keys())
+
+
+@pytest.mark.parametrize("name,smoothing", [("mixed", 0.1), ("quirk_pad_row0_only", 0.1), ("nopad", 0.1), ("nosmooth", 0.0)])
+def test_label_smoothing_golden(name, smoothing):
+    """oracle.label_smoothing_loss vs the reference's LabelSmoothing (label_smoothing.py), including the quirk that a
+    lone padding target in row 0 is NOT zeroed."""
+    z = G.load("label_smoothing.npz")
+    loss = O.label_smoothing_loss(G.t(z[name + "/logp"]), G.t(z[name + "/target"]), 12, 1, smoothing)
+    assert abs(float(loss) - float(z[name + "/loss"])) <= 1e-6 * max(1.0, abs(float(z[name + "/loss"])))

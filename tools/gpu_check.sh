@@ -9,7 +9,7 @@ run() { # name, timeout, args...
   timeout $t python -m pytest -q -m gpu --no-header -p no:cacheprovider "$@" > gpurun_out/$name.log 2>&1
   echo "== $name exit $?"; tail -n 25 gpurun_out/$name.log
 }
-run ln_cast 300 tests/test_gpu_kernels.py -k "layernorm or cast or embed or feature or softmax or generator"
+run ln_cast 300 tests/test_gpu_kernels.py -k "layernorm or cast or embed or feature or softmax or generator or label or simple_loss"
 run linear 600 tests/test_gpu_kernels.py -k "linear"
 run attn 600 tests/test_gpu_kernels.py -k "attn"
 for f in "$@"; do run extra_$(basename $f .py) 900 $f; done
