@@ -419,6 +419,22 @@ def main():
         cpu = {"value": int((sub["trg_y"] != 1).sum()) / sec, "unit": "tokens/s", "cores": torch.get_num_threads(),
                "kind": "port", "sample": "oracle forward on the first %d dialogues of batch 0, median of 5 (%.2f s each)"
                % (args.cpu_batch, sec)}
+        # context only: the same port (stock PyTorch eager ops, f32, what the reference would run on a GPU) on
+        # this B200, full batch -- the reference ships no GPU kernels of its own.
+        try:
+            sdg = {k: v.to(dev) for k, v in sd.items()}
+            fullg = {k: (v.to(dev) if torch.is_tensor(v) else [f.to(dev) for f in v]) for k, v in host[0].items()}
+            run = lambda: O.forward(sdg, CFG, fullg["query"], fullg["his"], fullg["cap"], fullg["trg"], fullg["fts"])
+            run(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            cpu["gpu_eager_port_tokens_per_s"] = ntok[0] / ((time.perf_counter() - t0) / 3)
+            cpu["gpu_eager_port_note"] = "oracle port in stock PyTorch eager f32 on the same GPU, full batch (context)"
+            del sdg, fullg
+        except Exception as e:       # context number only
+            cpu["gpu_eager_port_note"] = "failed: %r" % (e,)
 
     if rank == 0:
         fl = flops_forward(B, T)

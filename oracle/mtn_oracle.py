@@ -191,7 +191,7 @@ def make_masks(query, his, cap, trg, fts, pad):
         "cap_mask": (cap != pad).unsqueeze(-2),
     }
     if trg is not None:
-        m["trg_mask"] = (trg != pad).unsqueeze(-2) & subsequent_mask(trg.shape[-1])
+        m["trg_mask"] = (trg != pad).unsqueeze(-2) & subsequent_mask(trg.shape[-1]).to(trg.device)
     m["fts_mask"] = [(torch.sum(ft != 1, dim=2) != 0).unsqueeze(-2) for ft in fts]
     m["fts"] = [ft * m["fts_mask"][i].squeeze(1).unsqueeze(-1).float() for i, ft in enumerate(fts)]
     return m
