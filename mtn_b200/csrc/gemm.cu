@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // L2-bandwidth bound disappears and each element still receives exactly one f32 add.
     const bool red_add = epi.addend != nullptr && epi.addend == epi.out32 && epi.add_period == 0 &&
                          epi.ld_add == epi.ld32 && epi.out16 == nullptr;
+    const bool f16_only = epi.out16 != nullptr && epi.out32 == nullptr && epi.addend == nullptr;
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
     // shared-memory slots of the transpose tile (float4 units); (row & 7) == sub_r for every row this lane reads
@@ -197,6 +198,56 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
+        if (f16_only) {
+          // f16-only outputs (Q/K/V projections, FFN hidden: most of the FLOPs): bias + activation in the
+          // row-per-thread layout, round to f16 BEFORE the transpose -- half the shared-memory traffic of the
+          // f32 path, and shared-memory bandwidth is what the epilogue and the mainloop compete for.
+          const int cb = n0 + c * 32;
+          float4 bb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // warp-uniform addresses: broadcast loads, issued before the TMEM load
+            bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (epi.bias != nullptr && cb + 4 * j < N) bb[j] = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4 * j));
+          }
+          uint32_t acc[32];
+          tc_ld32(t_acc + c * 32, acc);
+          tc_wait_ld();
+          if (c + 2 >= NCHUNK) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v0 = __uint_as_float(acc[4 * j]) + bb[j].x, v1 = __uint_as_float(acc[4 * j + 1]) + bb[j].y;
+            float v2 = __uint_as_float(acc[4 * j + 2]) + bb[j].z, v3 = __uint_as_float(acc[4 * j + 3]) + bb[j].w;
+            if (epi.act == MTN_ACT_RELU) {
+              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+            }
+            pk[2 * j] = pack_f16x2_sat(v0, v1);
+            pk[2 * j + 1] = pack_f16x2_sat(v2, v3);
+          }
+          // [32 rows x 64 B] tile, 16-B slots XOR-swizzled by (row >> 1) & 3: conflict-free both ways
+          uint4* hp = reinterpret_cast<uint4*>(xp);
+          const int wsw = (lane >> 1) & 3;
+#pragma unroll
+          for (int sI = 0; sI < 4; ++sI)
+            hp[lane * 4 + (sI ^ wsw)] = make_uint4(pk[4 * sI], pk[4 * sI + 1], pk[4 * sI + 2], pk[4 * sI + 3]);
+          __syncwarp();
+          uint4 hv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + sub_r;
+            hv[i] = hp[rl * 4 + (c8 ^ ((rl >> 1) & 3))];
+          }
+          __syncwarp();
+          const int colh = cb + c8 * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (row_ok[i] && colh < N) *reinterpret_cast<uint4*>(epi.out16 + off16[i] + colh) = hv[i];
+          continue;
+        }
         const int col = n0 + c * 32 + c8 * 8;  // this lane's 8 columns in the coalesced phase
         const bool col_ok = col < N;           // N % 8 == 0: all 8 or none
         float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
