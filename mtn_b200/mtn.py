@@ -25,7 +25,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib
 from .engine import DecoderEngine, PackedWeights, ensure_inference

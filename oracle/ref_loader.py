@@ -61,7 +61,6 @@ def load():
                             "torchtext.datasets": tt_ds})
     # The reference's module names (mtn, data_utils) are imported under private
     # aliases so they can never shadow the product package.
-    import importlib.util
     saved = {k: sys.modules.get(k) for k in ("mtn", "data_utils")}
     sys.path.insert(0, d)
     try:
