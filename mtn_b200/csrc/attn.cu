@@ -43,7 +43,10 @@ struct AttnCfg {
   static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
   static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 192 + 1024;
+  // At most TWO CTAs may share an SM (2 x 256 TMEM columns): the request is padded above a third of the
+  // shared memory so a third CTA can never be co-resident and sit in tcgen05.alloc behind a persistent peer.
+  static constexpr int NEEDED = OFF_BAR + 192 + 1024;
+  static constexpr int TOTAL = NEEDED > 78 * 1024 ? NEEDED : 78 * 1024;
   static constexpr uint64_t SWZ = (DK == 64) ? SWZ_128B : SWZ_64B;
   static constexpr uint32_t SBO = 8 * ROWB;  // 8-row swizzle atom
   static constexpr uint32_t TMEM_COLS = 256;  // S0: [0,KT)  S1: [KT,2KT)  O: [2KT, 2KT+DK)
