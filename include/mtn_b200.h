@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MTN_B200_ABI_VERSION 1
+#define MTN_B200_ABI_VERSION 2
 
 enum {
   MTN_OK = 0,
@@ -55,6 +55,10 @@ const char *mtn_last_error(void);
  * NULL; this is the tensor-core operand for the following projection).            */
 int mtn_layernorm_fwd(const float *x, const float *a_2, const float *b_2, float eps,
                       int rows, int d, float *y_f32, void *y_f16, void *stream);
+/* Grouped variant: a_2 / b_2 are [groups, d]; row r is normalised with parameter set r / rows_per_group
+ * (one launch for the same sublayer of several independent streams).                                 */
+int mtn_layernorm_grouped_fwd(const float *x, const float *a_2, const float *b_2, float eps, int rows,
+                              int d, int rows_per_group, float *y_f32, void *y_f16, void *stream);
 
 /* ---- embeddings ----------------------------------------------
  * Replaces Embeddings.forward (mtn.py:288-289) + PositionalEncoding.forward (mtn.py:307-309)
@@ -129,6 +133,12 @@ typedef struct MtnLinearArgs {
   const float *addend; int ld_add; int add_period;
   float *out_f32; int ld32;
   void *out_f16; int ld16;
+  /* Strided batch (ABI v2): `batch` > 1 runs that many independent problems of identical shape in ONE
+   * launch; problem b uses A + b*stride_A, W + b*stride_W, bias + b*stride_bias, addend + b*stride_add,
+   * out_f32 + b*stride_out_f32, out_f16 + b*stride_out_f16 (strides in ELEMENTS).  Used to run the two
+   * video modalities' Query-Aware Auto-Encoder projections (same shapes, different weights) together. */
+  int batch;
+  long long stride_A, stride_W, stride_bias, stride_add, stride_out_f32, stride_out_f16;
 } MtnLinearArgs;
 int mtn_linear_fwd(const MtnLinearArgs *args, void *stream);
 

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -25,7 +25,10 @@ class LinearArgs(C.Structure):
                 ("bias", C.c_void_p), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("act", C.c_int), ("addend", C.c_void_p), ("ld_add", C.c_int),
                 ("add_period", C.c_int), ("out_f32", C.c_void_p), ("ld32", C.c_int),
-                ("out_f16", C.c_void_p), ("ld16", C.c_int)]
+                ("out_f16", C.c_void_p), ("ld16", C.c_int),
+                ("batch", C.c_int), ("stride_A", C.c_longlong), ("stride_W", C.c_longlong),
+                ("stride_bias", C.c_longlong), ("stride_add", C.c_longlong), ("stride_out_f32", C.c_longlong),
+                ("stride_out_f16", C.c_longlong)]
 
 
 class AttnCoreArgs(C.Structure):
@@ -70,6 +73,8 @@ SYMBOLS = {
     "mtn_label_smoothing_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mtn_label_smoothing_loss_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_float,
                                                C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mtn_layernorm_grouped_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_cast_f32_to_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p]),
     "mtn_mask_words": (C.c_int, [C.c_int]),
@@ -156,8 +161,9 @@ def _req(t, dtype, name):
 # ------------------------------------------------------------------------------
 # thin tensor-level wrappers (used by mtn.py, engine.py and the tests)
 # ------------------------------------------------------------------------------
-def layernorm(x, a_2, b_2, eps, out_f32=None, out_f16=None):
-    """x: [..., d] f32 contiguous.  Writes into out_f32 / out_f16 (same shape)."""
+def layernorm(x, a_2, b_2, eps, out_f32=None, out_f16=None, rows_per_group=None):
+    """x: [..., d] f32 contiguous.  Writes into out_f32 / out_f16 (same shape).
+    rows_per_group: a_2 / b_2 are [groups, d] and row r uses parameter set r // rows_per_group."""
     _req(x, torch.float32, "x"); _req(a_2, torch.float32, "a_2"); _req(b_2, torch.float32, "b_2")
     _req(out_f32, torch.float32, "out_f32"); _req(out_f16, torch.float16, "out_f16")
     d = x.shape[-1]
@@ -165,9 +171,11 @@ def layernorm(x, a_2, b_2, eps, out_f32=None, out_f16=None):
     assert x.is_contiguous() and (out_f32 is None or out_f32.is_contiguous()) and \
         (out_f16 is None or out_f16.is_contiguous())
     nbytes = rows * d * (4 + (4 if out_f32 is not None else 0) + (2 if out_f16 is not None else 0))
+    rpg = rows if rows_per_group is None else int(rows_per_group)
+    assert a_2.is_contiguous() and b_2.is_contiguous() and a_2.numel() * rpg >= rows * d
     _launch("layernorm", 0, nbytes,
-            lambda: lib().mtn_layernorm_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), rows, d, ptr(out_f32),
-                                            ptr(out_f16), stream_ptr()),
+            lambda: lib().mtn_layernorm_grouped_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), rows, d, rpg, ptr(out_f32),
+                                                    ptr(out_f16), stream_ptr()),
             keep=(x, a_2, b_2, out_f32, out_f16))
 
 
@@ -307,3 +315,34 @@ def label_smoothing_loss(logits, V, target, padding_idx, smoothing, loss, scale=
                                                        float(smoothing), float(scale), 1 if accumulate else 0, ptr(loss),
                                                        ptr(ws), nbytes, stream_ptr()),
             keep=(logits, tc, loss, ws))
+
+
+def linear_batched(A, W, bias=None, act=ACT_NONE, addend=None, out_f32=None, out_f16=None):
+    """`batch` independent problems of one shape in ONE launch (strided batch): A [b, M, K] f16, W [b, N, K] f16,
+    bias [b, N] f32, addend / out_f32 [b, M, N] f32, out_f16 [b, M, N] f16.  The last dimension must have unit
+    stride; rows and batch may be strided views (e.g. a column block of a packed [b, M, 3d] buffer)."""
+    for t, dt, n in ((A, torch.float16, "A"), (W, torch.float16, "W"), (bias, torch.float32, "bias"),
+                     (addend, torch.float32, "addend"), (out_f32, torch.float32, "out_f32"), (out_f16, torch.float16, "out_f16")):
+        _req(t, dt, n)
+    assert A.dim() == 3 and W.dim() == 3 and A.shape[0] == W.shape[0] and A.shape[2] == W.shape[2]
+    a = LinearArgs()
+    a.batch, a.M, a.N, a.K, a.act = A.shape[0], A.shape[1], W.shape[1], A.shape[2], act
+    a.A, a.lda, a.stride_A = A.data_ptr(), A.stride(1), A.stride(0)
+    a.W, a.ldw, a.stride_W = W.data_ptr(), W.stride(1), W.stride(0)
+    if bias is not None:
+        assert tuple(bias.shape) == (a.batch, a.N)
+        a.bias, a.stride_bias = bias.data_ptr(), bias.stride(0)
+    if addend is not None:
+        assert tuple(addend.shape) == (a.batch, a.M, a.N)
+        a.addend, a.ld_add, a.stride_add = addend.data_ptr(), addend.stride(1), addend.stride(0)
+    if out_f32 is not None:
+        assert tuple(out_f32.shape) == (a.batch, a.M, a.N)
+        a.out_f32, a.ld32, a.stride_out_f32 = out_f32.data_ptr(), out_f32.stride(1), out_f32.stride(0)
+    if out_f16 is not None:
+        assert tuple(out_f16.shape) == (a.batch, a.M, a.N)
+        a.out_f16, a.ld16, a.stride_out_f16 = out_f16.data_ptr(), out_f16.stride(1), out_f16.stride(0)
+    nbytes = a.batch * (2 * (a.M * a.K + a.N * a.K) + a.M * a.N * ((4 if out_f32 is not None else 0) +
+                                                                      (2 if out_f16 is not None else 0) +
+                                                                      (4 if addend is not None else 0)))
+    _launch("linear", 2 * a.batch * a.M * a.N * a.K, nbytes, lambda: lib().mtn_linear_fwd(C.byref(a), stream_ptr()),
+            keep=(A, W, bias, addend, out_f32, out_f16))

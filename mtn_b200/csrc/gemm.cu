@@ -28,6 +28,8 @@ struct GemmEpi {
   int ld32;
   __half* out16;
   int ld16;
+  // strided batch (element strides between consecutive problems; batch == 1: unused)
+  long long s_bias, s_add, s_out32, s_out16;
 };
 
 constexpr int BM = 128;
@@ -59,7 +61,7 @@ struct GemmSmem {
 template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmEpi epi, int M, int N, int K, int tiles_n, int num_tiles) {
+                       const GemmEpi epi0, int M, int N, int K, int tiles_n, int tiles_per_batch, int num_tiles) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -110,18 +112,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       uint32_t it = 0;  // k-blocks issued so far (ring position across tiles)
       for (int t = first_tile; t < num_tiles; t += tile_stride) {
-        const int m0 = ((t / tiles_n) * CL + rank) * BM, n0 = (t % tiles_n) * BN;
+        const int bt = t / tiles_per_batch, tl = t % tiles_per_batch;  // problem of the strided batch, tile in it
+        const int m0 = ((tl / tiles_n) * CL + rank) * BM, n0 = (tl % tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty(s), ((it / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full(s), L::STAGE_BYTES);
           const uint32_t sA = base + s * L::STAGE_BYTES;
-          tma_load_2d(sA, &tmA, bar_full(s), kb * BK, m0);
+          tma_load_3d(sA, &tmA, bar_full(s), kb * BK, m0, bt);
           if (CL == 1) {
-            tma_load_2d(sA + L::A_BYTES, &tmB, bar_full(s), kb * BK, n0);
+            tma_load_3d(sA + L::A_BYTES, &tmB, bar_full(s), kb * BK, n0, bt);
           } else {  // my 1/CL of the W tile, delivered to every CTA of the cluster
             constexpr int SL = BN / CL;
-            tma_load_2d_mc(sA + L::A_BYTES + rank * (SL * BK * 2), &tmB, bar_full(s), kb * BK, n0 + rank * SL, kMask);
+            tma_load_3d_mc(sA + L::A_BYTES + rank * (SL * BK * 2), &tmB, bar_full(s), kb * BK, n0 + rank * SL, bt, kMask);
           }
         }
       }
@@ -169,9 +172,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // In-place residual (x += A W^T + b, the common SublayerConnection case): the add is done by L2
     // reductions (red.global.add.v4.f32) -- the 16 MB residual read that makes these launches
     // L2-bandwidth bound disappears and each element still receives exactly one f32 add.
-    const bool red_add = epi.addend != nullptr && epi.addend == epi.out32 && epi.add_period == 0 &&
-                         epi.ld_add == epi.ld32 && epi.out16 == nullptr;
-    const bool f16_only = epi.out16 != nullptr && epi.out32 == nullptr && epi.addend == nullptr;
+    const bool red_add = epi0.addend != nullptr && epi0.addend == epi0.out32 && epi0.add_period == 0 &&
+                         epi0.ld_add == epi0.ld32 && epi0.out16 == nullptr && epi0.s_add == epi0.s_out32;
+    const bool f16_only = epi0.out16 != nullptr && epi0.out32 == nullptr && epi0.addend == nullptr;
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
     // shared-memory slots of the transpose tile (float4 units); (row & 7) == sub_r for every row this lane reads
@@ -179,7 +182,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int rd0 = sub_r * 8 + ((2 * c8) ^ sub_r), rd1 = sub_r * 8 + ((2 * c8 + 1) ^ sub_r);
     uint32_t lt = 0;
     for (int t = first_tile; t < num_tiles; t += tile_stride, ++lt) {
-      const int m0 = ((t / tiles_n) * CL + rank) * BM, n0 = (t % tiles_n) * BN;
+      const int bt = t / tiles_per_batch, tl = t % tiles_per_batch;
+      const int m0 = ((tl / tiles_n) * CL + rank) * BM, n0 = (tl % tiles_n) * BN;
+      GemmEpi epi = epi0;  // this problem's operands
+      if (bt > 0) {
+        if (epi.bias) epi.bias += bt * epi.s_bias;
+        if (epi.addend) epi.addend += bt * epi.s_add;
+        if (epi.out32) epi.out32 += bt * epi.s_out32;
+        if (epi.out16) epi.out16 += bt * epi.s_out16;
+      }
       const uint32_t buf = lt & 1;
       const int row0 = m0 + q * 32 + sub_r;  // this lane's first row; the others are +8, +16, +24
       // per-row element offsets, hoisted out of the chunk loop
@@ -358,18 +369,22 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
       max_clusters = n;
     }
   }
+  const int batch = a.batch > 1 ? a.batch : 1;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d_f16(&tmA, a.A, a.K, a.M, a.lda, BK, BM, TM_SWZ_128);
+  int rc = make_tmap_3d_f16(&tmA, a.A, a.K, a.M, batch, a.lda, batch > 1 ? (uint64_t)a.stride_A : (uint64_t)a.M * a.lda, BK,
+                            BM, TM_SWZ_128);
   if (rc) return rc;
-  rc = make_tmap_2d_f16(&tmB, a.W, a.K, a.N, a.ldw, BK, BN / CL, TM_SWZ_128);
+  rc = make_tmap_3d_f16(&tmB, a.W, a.K, a.N, batch, a.ldw, batch > 1 ? (uint64_t)a.stride_W : (uint64_t)a.N * a.ldw, BK,
+                        BN / CL, TM_SWZ_128);
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
-              reinterpret_cast<__half*>(a.out_f16), a.ld16};
+              reinterpret_cast<__half*>(a.out_f16), a.ld16, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
-  const int num_super = tiles_n * ((tiles_m + CL - 1) / CL);
+  const int tiles_per_batch = tiles_n * ((tiles_m + CL - 1) / CL);
+  const int num_super = tiles_per_batch * batch;
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
   MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL>, dim3(clusters * CL), dim3(GEMM_THREADS),
-                                       L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K, tiles_n, num_super));
+                                       L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K, tiles_n, tiles_per_batch, num_super));
   return MTN_OK;
 }
 
@@ -393,6 +408,13 @@ static int validate_linear(const MtnLinearArgs* a) {
     MTN_REQUIRE(aligned16(a->addend) && a->ld_add % 4 == 0 && a->ld_add >= a->N && a->add_period >= 0,
                 MTN_E_ALIGN, "linear: addend alignment / ld_add=%d", a->ld_add);
   if (a->bias) MTN_REQUIRE(aligned16(a->bias), MTN_E_ALIGN, "linear: bias not 16-byte aligned");
+  if (a->batch > 1) {
+    MTN_REQUIRE(a->stride_A % 8 == 0 && a->stride_W % 8 == 0 && a->stride_A > 0 && a->stride_W > 0 &&
+                    a->stride_bias % 4 == 0 && a->stride_add % 4 == 0 && a->stride_out_f32 % 4 == 0 &&
+                    a->stride_out_f16 % 8 == 0,
+                MTN_E_ALIGN, "linear: batch strides must keep every problem 16-byte aligned");
+    MTN_REQUIRE(a->batch <= 65535, MTN_E_SHAPE, "linear: batch=%d", a->batch);
+  }
   return MTN_OK;
 }
 
@@ -440,7 +462,7 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
     cl = e ? atoi(e) : 2;
   }
   const int tiles_m = (a->M + 127) / 128;
-  const long tiles256 = (long)((a->N + 255) / 256) * tiles_m;
+  const long tiles256 = (long)((a->N + 255) / 256) * tiles_m * (a->batch > 1 ? a->batch : 1);
   static int big_pct = -1;  // 128x256 tiles once they fill this percentage of the SMs
   if (big_pct < 0) {
     const char* e = getenv("MTN_B200_BIG_PCT");
@@ -455,7 +477,8 @@ extern "C" int mtn_check_linear_fwd(const MtnLinearArgs* a, void* stream) {
   int rc = mtn::validate_linear(a);
   if (rc) return rc;
   mtn::GemmEpi epi{a->bias, a->act, a->addend, a->ld_add, a->add_period, a->out_f32, a->ld32,
-                   reinterpret_cast<__half*>(a->out_f16), a->ld16};
+                   reinterpret_cast<__half*>(a->out_f16), a->ld16, 0, 0, 0, 0};
+  MTN_REQUIRE(a->batch <= 1, MTN_E_ARG, "check_linear: the check kernel is not batched");
   dim3 grid((a->N + 127) / 128, a->M);
   mtn::gemm_f16_check_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(a->A), a->lda, reinterpret_cast<const __half*>(a->W), a->ldw, epi,

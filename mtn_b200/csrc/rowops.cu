@@ -16,13 +16,15 @@ namespace mtn {
 template <int VPL>  // float4 per lane: d = 128 * VPL
 __global__ void __launch_bounds__(256)
     layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ a2,
-                          const float* __restrict__ b2, float eps, int rows, float* __restrict__ y32,
-                          __half* __restrict__ y16) {
+                          const float* __restrict__ b2, float eps, int rows, int rows_per_group,
+                          float* __restrict__ y32, __half* __restrict__ y16) {
   constexpr int D = 128 * VPL;
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  a2 += (size_t)(row / rows_per_group) * D;  // parameter set of this row's stream
+  b2 += (size_t)(row / rows_per_group) * D;
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
   float4 v[VPL];
@@ -288,19 +290,29 @@ __global__ void __launch_bounds__(128)
 
 extern "C" int mtn_layernorm_fwd(const float* x, const float* a_2, const float* b_2, float eps, int rows,
                                  int d, float* y_f32, void* y_f16, void* stream) {
+  return mtn_layernorm_grouped_fwd(x, a_2, b_2, eps, rows, d, rows, y_f32, y_f16, stream);
+}
+
+extern "C" int mtn_layernorm_grouped_fwd(const float* x, const float* a_2, const float* b_2, float eps, int rows,
+                                         int d, int rows_per_group, float* y_f32, void* y_f16, void* stream) {
   using namespace mtn;
   MTN_REQUIRE(x && a_2 && b_2 && (y_f32 || y_f16), MTN_E_ARG, "layernorm: NULL pointer");
-  MTN_REQUIRE(rows > 0 && d > 1, MTN_E_SHAPE, "layernorm: rows=%d d=%d", rows, d);
+  MTN_REQUIRE(rows > 0 && d > 1 && rows_per_group > 0, MTN_E_SHAPE, "layernorm: rows=%d d=%d rows_per_group=%d", rows, d,
+              rows_per_group);
+  const bool grouped = rows_per_group < rows;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __half* y16 = reinterpret_cast<__half*>(y_f16);
   const int wpb = 8;  // warps (= rows) per block
   dim3 grid((rows + wpb - 1) / wpb);
+  MTN_REQUIRE(!grouped || (d == 128 || d == 256 || d == 512 || d == 1024), MTN_E_SHAPE,
+              "layernorm: grouped variant needs d in {128, 256, 512, 1024}, got %d", d);
   const bool vec = (d % 128 == 0) && d <= 1024 && aligned16(x) && aligned16(a_2) && aligned16(b_2) &&
                    (!y_f32 || aligned16(y_f32)) && (!y_f16 || aligned16(y_f16));
-  if (vec && d == 128) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<1>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
-  else if (vec && d == 256) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<2>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
-  else if (vec && d == 512) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<4>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
-  else if (vec && d == 1024) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<8>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, y_f32, y16));
+  MTN_REQUIRE(!grouped || vec, MTN_E_ALIGN, "layernorm: grouped variant needs 16-byte aligned pointers");
+  if (vec && d == 128) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<1>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, rows_per_group, y_f32, y16));
+  else if (vec && d == 256) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<2>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, rows_per_group, y_f32, y16));
+  else if (vec && d == 512) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<4>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, rows_per_group, y_f32, y16));
+  else if (vec && d == 1024) MTN_CHECK_CUDA(launch_kernel(layernorm_rows_kernel<8>, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, rows_per_group, y_f32, y16));
   else MTN_CHECK_CUDA(launch_kernel(layernorm_generic_kernel, grid, dim3(32 * wpb), 0, st, x, a_2, b_2, eps, rows, d, y_f32, y16));
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;

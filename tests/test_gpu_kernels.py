@@ -346,3 +346,28 @@ def test_simple_loss_compute_eval(L):
     assert abs(got - ref) <= 2e-3 * abs(ref), (got, ref)        # f16 generator operands
     with pytest.raises(NotImplementedError):
         data_utils.SimpleLossCompute(gen, None, crit, opt=object())
+
+
+def test_linear_batched_and_grouped_layernorm(L):
+    """Strided-batch GEMM (two problems, one launch) incl. in-place residual and a column-block output view, and the
+    grouped LayerNorm (parameter set per row group) -- the primitives that run the two video modalities' QAE chains
+    together."""
+    g = torch.Generator().manual_seed(12)
+    b, M, N, K = 2, 300, 512, 256
+    A = torch.randn(b, M, K, generator=g).half(); W = (torch.randn(b, N, K, generator=g) / 16).half()
+    bias = torch.randn(b, N, generator=g); x = torch.randn(b, M, N, generator=g)
+    ref = torch.stack([(A[i].double() @ W[i].double().t() + bias[i].double()) for i in range(b)])
+    xd = dev(x)
+    L.linear_batched(dev(A), dev(W), dev(bias), addend=xd, out_f32=xd)                 # x += A W^T + b, per problem
+    wide = torch.zeros(b, M, 3 * N, device="cuda", dtype=torch.float16)
+    L.linear_batched(dev(A), dev(W), dev(bias), act=L.ACT_RELU, out_f16=wide[:, :, N:2 * N])
+    torch.cuda.synchronize()
+    assert G.rel_err(xd.cpu(), (x.double() + ref).float()) < 2e-5
+    assert G.rel_err(wide[:, :, N:2 * N].float().cpu(), ref.clamp_min(0).float()) < 6e-4
+    assert float(wide[:, :, :N].abs().sum()) == 0 and float(wide[:, :, 2 * N:].abs().sum()) == 0
+    a2 = 1 + 0.1 * torch.randn(b, N, generator=g); b2 = 0.1 * torch.randn(b, N, generator=g)
+    y = torch.empty(b * M, N, device="cuda", dtype=torch.float16)
+    L.layernorm(xd.view(b * M, N), dev(a2), dev(b2), 1e-6, out_f16=y, rows_per_group=M)
+    torch.cuda.synchronize()
+    ref_ln = torch.cat([O.layer_norm(xd[i].cpu(), a2[i], b2[i], 1e-6) for i in range(b)])
+    assert G.rel_err(y.float().cpu(), ref_ln) < 6e-4
