@@ -78,6 +78,9 @@ class _MemoryKey(object):
 
 
 class DecoderEngine(object):
+    # run the modalities' QAE chains as strided-batch launches (MTN_B200_QAE_BATCHED=0: one chain per stream)
+    qae_batched = __import__("os").environ.get("MTN_B200_QAE_BATCHED", "1") != "0"
+
     def __init__(self, decoder):
         self.dec = decoder
         self._packed = PackedWeights()
@@ -132,6 +135,25 @@ class DecoderEngine(object):
                 })
             W["norm"] = ln(dec.norm)
             W["ae_norm"] = [ln(m) for m in dec.ae_norm]
+            if M > 1:
+                # modality-stacked copies for the batched Query-Aware Auto-Encoder chain: problem i of a
+                # strided-batch GEMM / parameter set i of a grouped LayerNorm is modality i
+                st = lambda ts: torch.stack(list(ts), 0).contiguous()
+                lnst = lambda ls: (st(t[0] for t in ls), st(t[1] for t in ls), ls[0][2])
+                for l, Lw in enumerate(W["layers"]):
+                    Lw["qae"] = {
+                        "ln_self": lnst([Lw["ln"][4 + 4 * i] for i in range(M)]),
+                        "ln_vid": lnst([Lw["ln"][5 + 4 * i] for i in range(M)]),
+                        "ln_ffn": lnst([Lw["ln"][6 + 4 * i] for i in range(M)]),
+                        "self_w_qkv": st(a["w_qkv"] for a in Lw["ae_self"]), "self_b_qkv": st(a["b_qkv"] for a in Lw["ae_self"]),
+                        "self_w_o": st(a["w_o"] for a in Lw["ae_self"]), "self_b_o": st(a["b_o"] for a in Lw["ae_self"]),
+                        "vid_w_q": st(a["w_qkv"][:d] for a in Lw["ae_vid"]), "vid_b_q": st(a["b_qkv"][:d] for a in Lw["ae_vid"]),
+                        "vid_w_o": st(a["w_o"] for a in Lw["ae_vid"]), "vid_b_o": st(a["b_o"] for a in Lw["ae_vid"]),
+                        "ffn_w_1": st(f["w_1"] for f in Lw["ae_ffn"]), "ffn_b_1": st(f["b_1"] for f in Lw["ae_ffn"]),
+                        "ffn_w_2": st(f["w_2"] for f in Lw["ae_ffn"]), "ffn_b_2": st(f["b_2"] for f in Lw["ae_ffn"]),
+                        "kv_w": st(a["w_qkv"][d:] for a in Lw["ae_attn"]), "kv_b": st(a["b_qkv"][d:] for a in Lw["ae_attn"]),
+                    }
+                W["ae_norm_stacked"] = lnst(W["ae_norm"])
             return W
 
         return self._packed.get(params, build)
@@ -163,6 +185,71 @@ class DecoderEngine(object):
             self._side = [torch.cuda.Stream(device=dev) for _ in range(M)]
             self._side_dev = dev
         return self._side
+
+    def _qae_batched(self, W, S, mods, side, main, B, La, rows, ae_bits):
+        """Both (all) modalities' Query-Aware Auto-Encoder chains in lockstep on one side stream: every
+        projection is ONE strided-batch GEMM over the modalities (same shapes, different weights), every
+        LayerNorm one grouped launch, the ae-self attention one launch over M*B "dialogues"; only the
+        ae->video attention stays per modality (different video lengths).  13 launches per layer instead of 26,
+        and each fills the machine twice as well."""
+        d, N, M = W["d"], W["N"], W["M"]
+        dev = mods[0]["ae"].device
+        f16 = torch.float16
+        dff = W["layers"][0]["ffn"]["w_1"].shape[0]
+        A0 = W["layers"][0]["ae_self"][0]
+        h, dk = A0["h"], A0["d_k"]
+        R = M * rows
+        ae = torch.stack([m["ae"] for m in mods], 0)                         # [M, rows, d] f32 residual streams
+        xn16 = torch.empty(M, rows, d, dtype=f16, device=dev)
+        qkv = torch.empty(M, rows, 3 * d, dtype=f16, device=dev)
+        obuf = torch.empty(M, rows, d, dtype=f16, device=dev)
+        hid = torch.empty(M, rows, dff, dtype=f16, device=dev)
+        ae16 = torch.empty(M, rows, d, dtype=f16, device=dev)
+        kv_ae = [torch.empty(M, rows, 2 * d, dtype=f16, device=dev) for _ in range(N)]
+        out = torch.empty(M, rows, d, dtype=torch.float32, device=dev)
+        bits_rep = ae_bits.repeat(M, 1, 1).contiguous() if ae_bits is not None else None
+        S["kv_ae"] = [[kv_ae[l][i] for i in range(M)] for l in range(N)]
+        evs = [torch.cuda.Event() for _ in range(N)]
+        S["ev"] = [[evs[l]] * M for l in range(N)]
+        S["ae_out"] = [out[i].view(B, La, d) for i in range(M)]
+        S["side"] = side
+        S["_keep_b"] = (ae, xn16, qkv, obuf, hid, ae16, kv_ae, out, bits_rep)
+        for i in range(M):                                                   # hoisted video K/V, one stream each
+            side[i].wait_stream(main)
+            with torch.cuda.stream(side[i]):
+                m = mods[i]
+                _lib.cast_f16(m["vid"], m["vid16"])
+                _lib.linear(m["vid16"], W["kv_vid"][i][0], W["kv_vid"][i][1], out_f16=m["kv_vid"])
+        for i in range(1, M):
+            side[0].wait_stream(side[i])
+        with torch.cuda.stream(side[0]):
+            flat = lambda t: t.view(R, t.shape[-1])
+            for l in range(N):
+                Q = W["layers"][l]["qae"]
+                kc, vc = l * 2 * d, l * 2 * d + d
+                ln = Q["ln_self"]
+                _lib.layernorm(flat(ae), ln[0], ln[1], ln[2], out_f16=flat(xn16), rows_per_group=rows)
+                _lib.linear_batched(xn16, Q["self_w_qkv"], Q["self_b_qkv"], out_f16=qkv)
+                q2 = flat(qkv)
+                _lib.attn_core(q2[:, :d], q2[:, d:2 * d], q2[:, 2 * d:], M * B, h, La, La, dk, flat(obuf), mask_bits=bits_rep)
+                _lib.linear_batched(obuf, Q["self_w_o"], Q["self_b_o"], addend=ae, out_f32=ae)
+                ln = Q["ln_vid"]
+                _lib.layernorm(flat(ae), ln[0], ln[1], ln[2], out_f16=flat(xn16), rows_per_group=rows)
+                _lib.linear_batched(xn16, Q["vid_w_q"], Q["vid_b_q"], out_f16=qkv[:, :, :d])
+                for i in range(M):
+                    m = mods[i]
+                    _lib.attn_core(qkv[i][:, :d], m["kv_vid"][:, kc:kc + d], m["kv_vid"][:, vc:vc + d], B, h, La, m["Lv"],
+                                   dk, obuf[i], mask_bits=m["bits_vid"])
+                _lib.linear_batched(obuf, Q["vid_w_o"], Q["vid_b_o"], addend=ae, out_f32=ae)
+                ln = Q["ln_ffn"]
+                _lib.layernorm(flat(ae), ln[0], ln[1], ln[2], out_f16=flat(xn16), rows_per_group=rows)
+                _lib.linear_batched(xn16, Q["ffn_w_1"], Q["ffn_b_1"], act=_lib.ACT_RELU, out_f16=hid)
+                _lib.linear_batched(hid, Q["ffn_w_2"], Q["ffn_b_2"], addend=ae, out_f32=ae, out_f16=ae16)
+                # K/V of this layer's ae_i for the target stream's auto_encoder_attn[i] (mtn.py:215)
+                _lib.linear_batched(ae16, Q["kv_w"], Q["kv_b"], out_f16=kv_ae[l])
+                evs[l].record(side[0])
+            ln = W["ae_norm_stacked"]
+            _lib.layernorm(flat(ae), ln[0], ln[1], ln[2], out_f32=flat(out), rows_per_group=rows)   # mtn.py:162-163
 
     def _memory_stage(self, W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask, ae_ft, ae_features):
         """Everything that does not depend on the target stream.  The text memories' hoisted K/V run
@@ -225,6 +312,11 @@ class DecoderEngine(object):
                 "kv_ae": [torch.empty(rows, 2 * d, dtype=f16, device=dev) for _ in range(N)],
                 "out": torch.empty(rows, d, dtype=torch.float32, device=dev),
             })
+        if M > 1 and self.qae_batched and d in (128, 256, 512, 1024):
+            self._qae_batched(W, S, mods, side, main, B, La, rows, ae_bits)
+            S["kv_his"], S["kv_cap"], S["kv_q"] = hoisted(his, W["kv_his"]), hoisted(cap, W["kv_cap"]), hoisted(qm, W["kv_q"])
+            S["_keep"] = mods
+            return S
         S["kv_ae"] = [[mods[i]["kv_ae"][l] for i in range(M)] for l in range(N)]
         S["ev"] = [[torch.cuda.Event() for _ in range(M)] for _ in range(N)]
         S["ae_out"] = [m["out"].view(B, La, d) for m in mods]
