@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MTN_B200_ABI_VERSION 2
+#define MTN_B200_ABI_VERSION 3
 
 enum {
   MTN_OK = 0,
@@ -139,6 +139,9 @@ typedef struct MtnLinearArgs {
    * video modalities' Query-Aware Auto-Encoder projections (same shapes, different weights) together. */
   int batch;
   long long stride_A, stride_W, stride_bias, stride_add, stride_out_f32, stride_out_f16;
+  /* ABI v3: out_f16 receives the value BEFORE the addend (video encoder in training: relu(.) without the
+   * positional term is what the ReLU backward needs).                                                  */
+  int out16_pre_add;
 } MtnLinearArgs;
 int mtn_linear_fwd(const MtnLinearArgs *args, void *stream);
 
@@ -162,6 +165,9 @@ typedef struct MtnAttnCoreArgs {
   const uint32_t *mask_bits; int mask_rows_q;
   int B, h, Lq, Lk, d_k;
   void *out; int ldo;
+  /* ABI v3 (training): optional [B, h, Lq, 2] f32 -- per query row {row maximum of the masked scaled scores
+   * in the log2 domain, 1 / softmax denominator}; saved for mtn_attn_core_bwd.  NULL: not written.       */
+  float *stats;
 } MtnAttnCoreArgs;
 int mtn_attn_core_fwd(const MtnAttnCoreArgs *args, void *stream);
 
@@ -205,6 +211,143 @@ typedef struct MtnFfnArgs {
 } MtnFfnArgs;
 size_t mtn_ffn_workspace_bytes(int rows, int d, int d_ff);
 int mtn_ffn_fwd(const MtnFfnArgs *args, void *stream);
+
+
+/* =====================================================================================================
+ * BACKWARD (training) entry points -- ABI v3.  The reference trains through torch.autograd (train.py:33-39,
+ * data_utils.py:152-155 loss.backward()); these are the gradients of the entry points above, bound by
+ * mtn_b200/train_engine.py behind one autograd.Function per reference module.
+ *
+ * Gradient scaling: tensor-core operands of the backward GEMMs are f16.  A backward pass multiplies the
+ * incoming gradient by a power of two S picked on the device (mtn_grad_absmax + mtn_grad_scale -> {S, 1/S}),
+ * keeps intermediates scaled, and un-scales every result in the kernel that produces it.  `scale` / `alpha`
+ * below are DEVICE pointers to those scalars (NULL = 1), so a whole step stays CUDA-graph capturable.
+ * ===================================================================================================== */
+
+/* ---- general tensor-core GEMM ----------------------------------------------------------------------
+ *   C[m, n] = act( alpha * sum_k A(m, k) B(n, k) + bias[n] ) [* (relu_mask[m, n] > 0)] + addend[.., n]
+ * A(m, k) = A[m*lda + k] (a_mn = 0, "K-major") or A[k*lda + m] (a_mn = 1, "MN-major"); B likewise.
+ * (0,0) is the forward linear, (0,1) its data gradient, (1,1) its weight gradient.  accumulate != 0:
+ * out_f32 += alpha * A B^T with split-K over the CTAs (atomic f32 adds; bias / act / addend not allowed). */
+typedef struct MtnGemmArgs {
+  const void *A; int lda; int a_mn;
+  const void *B; int ldb; int b_mn;
+  int M, N, K;
+  const float *alpha;
+  const float *bias; int act;
+  const void *relu_mask; int ld_mask;
+  const float *addend; int ld_add; int add_period;
+  int accumulate;
+  float *out_f32; int ld32;
+  void *out_f16; int ld16; int out16_pre_add;
+  int batch;
+  long long stride_A, stride_B, stride_bias, stride_add, stride_out_f32, stride_out_f16;
+} MtnGemmArgs;
+int mtn_gemm_f16(const MtnGemmArgs *args, void *stream);
+int mtn_check_gemm_f16(const MtnGemmArgs *args, void *stream);   /* tests only */
+
+/* ---- linear backward (autograd of nn.Linear, mtn.py:256-258, 267, 280, 35, 68) -------------------------
+ * dgrad:  dX[M, K] = alpha * dY[M, N] W[N, K]  (* (relu_mask > 0): gradient through the ReLU that produced
+ *         X, mtn.py:280) (+ addend).  W is read in its forward [out, in] layout.
+ * wgrad:  dW[N, K] += alpha * dY[M, N]^T X[M, K]  (f32, atomically accumulated: the caller zeroes or keeps
+ *         the running .grad).  dY and X are read in their forward row-major layouts.                      */
+typedef struct MtnLinearDgradArgs {
+  const void *dY; int lddy;            /* f16 [M, N] */
+  const void *W; int ldw;              /* f16 [N, K] */
+  int M, N, K;
+  const float *alpha;
+  const void *relu_mask; int ld_mask;  /* f16 [M, K] or NULL */
+  const float *addend; int ld_add;     /* f32 [M, K] or NULL */
+  float *dX_f32; int ld32;
+  void *dX_f16; int ld16;
+  int batch;
+  long long stride_dY, stride_W, stride_add, stride_dX_f32, stride_dX_f16;
+} MtnLinearDgradArgs;
+int mtn_linear_dgrad(const MtnLinearDgradArgs *args, void *stream);
+
+typedef struct MtnLinearWgradArgs {
+  const void *dY; int lddy;            /* f16 [M, N] */
+  const void *X; int ldx;              /* f16 [M, K] */
+  int M, N, K;
+  const float *alpha;
+  float *dW; int lddw;                 /* f32 [N, K] += */
+  int batch;
+  long long stride_dY, stride_X, stride_dW;
+} MtnLinearWgradArgs;
+int mtn_linear_wgrad(const MtnLinearWgradArgs *args, void *stream);
+
+/* ---- operand cast + bias gradient ------------------------------------------------------------------
+ * dst_f16[r, c] = f16( src[r, c] * scale  [0 where relu_mask[r, c] <= 0] )      (dst_f16 may be NULL)
+ * colsum[c]    += alpha * sum_r (the same values in f32)                         (colsum may be NULL)
+ * src is f32 (src_is_f16 = 0) or f16.  cols % 8 == 0.  The bias gradient of every nn.Linear on the path. */
+int mtn_cast_colsum(const void *src, int src_is_f16, int ld_src, void *dst_f16, int ld_dst,
+                    const void *relu_mask, int ld_mask, int rows, int cols, const float *scale,
+                    const float *alpha, float *colsum, void *stream);
+
+/* ---- gradient scale ---------------------------------------------------------------------------------
+ * mtn_grad_absmax folds max|x| into *slot (a zero-initialised uint32 in device memory; may be called for
+ * several tensors); mtn_grad_scale turns it into scale2 = {S, 1/S}, S = 2^k with absmax*S in [128, 256)
+ * (S = 1 for an all-zero or non-finite gradient) and resets the slot.                                   */
+int mtn_grad_absmax(const float *x, size_t n, uint32_t *slot, void *stream);
+int mtn_grad_scale(uint32_t *slot, float *scale2, void *stream);
+/* y = (accumulate ? y : 0) + x * alpha[0]: un-scales an input gradient leaving the backward pass.  n % 4 == 0. */
+int mtn_scale_f32(const float *x, const float *alpha, float *y, size_t n, int accumulate, void *stream);
+
+/* ---- LayerNorm backward (autograd of mtn.py:111-114) --------------------------------------------------
+ * dx = dres + dLN/dx(dy * dy_scale);  da_2 += param_alpha * sum_rows dy' (x - mean)/(std + eps);
+ * db_2 += param_alpha * sum_rows dy'.  dres may be NULL or alias dx (residual-stream gradient in place). */
+typedef struct MtnLayerNormBwdArgs {
+  const float *x; const float *a_2; float eps;
+  int rows, d;
+  const float *dy; const float *dy_scale;
+  const float *dres; float *dx;
+  float *da_2; float *db_2; const float *param_alpha;
+} MtnLayerNormBwdArgs;
+int mtn_layernorm_bwd(const MtnLayerNormBwdArgs *args, void *stream);
+
+/* ---- embedding backward (autograd of mtn_embed_fwd) ---------------------------------------------------
+ * dy: gradient of the (optionally stream-normalised) embedding output; the pre-norm value is recomputed.
+ * dlut[ids[r], :] += param_alpha * scale * dpre[r, :] (atomic); da_2 / db_2 as in mtn_layernorm_bwd.      */
+typedef struct MtnEmbedBwdArgs {
+  const int64_t *ids; const float *lut; const float *pe;
+  int rows, L, d, vocab; float scale;
+  const float *a_2; float eps;
+  const float *dy;
+  float *dlut; float *da_2; float *db_2; const float *param_alpha;
+} MtnEmbedBwdArgs;
+int mtn_embed_bwd(const MtnEmbedBwdArgs *args, void *stream);
+
+/* ---- attention core backward (autograd of attention(), mtn.py:221-231) -----------------------------------
+ * delta[b, h, q] = sum_c dO[row, h*d_k + c] * O[row, h*d_k + c]  (mtn_attn_delta), then
+ *   dV = P^T dO,  dS = P (dO V^T - delta) / sqrt(d_k) [0 where masked],  dQ = dS K,  dK = dS^T Q
+ * with P recomputed from q, k, mask and the forward's `stats`.  dq is f32 and ACCUMULATED atomically over the
+ * key tiles (zero it first); dk / dv are f16, head h in columns [h*d_k, (h+1)*d_k).                      */
+int mtn_attn_delta(const void *dO, int lddo, const void *O, int ldo, int B, int Lq, int h, int d_k,
+                   float *delta, void *stream);
+typedef struct MtnAttnCoreBwdArgs {
+  const void *q; int ldq;
+  const void *k; int ldk;
+  const void *v; int ldv;
+  const void *dO; int lddo;
+  const float *stats; const float *delta;
+  const uint32_t *mask_bits; int mask_rows_q;
+  int B, h, Lq, Lk, d_k;
+  float *dq; int lddq;
+  void *dk; int lddk;
+  void *dv; int lddv;
+} MtnAttnCoreBwdArgs;
+int mtn_attn_core_bwd(const MtnAttnCoreBwdArgs *args, void *stream);
+
+/* ---- generator tail / criterion backward ------------------------------------------------------------
+ * log-softmax (mtn.py:68-69):  dz = dy - exp(y) * sum_v dy;  columns [V, lddz) of dz are zeroed.
+ * label smoothing (label_smoothing.py:20-32 + KLDivLoss(sum)) from logits or log-probabilities z:
+ *   dz_v = gscale * gout[0] * (T_r softmax(z)_v - t_v)   (t = smoothed target row, T_r its sum);
+ * gout: device scalar (upstream gradient) or NULL.  workspace: >= 256 bytes.                               */
+int mtn_log_softmax_bwd(const float *y, int ldy, const float *dy, int lddy, int rows, int V, float *dz,
+                        int lddz, void *stream);
+int mtn_label_smoothing_loss_bwd(const float *z, int ld, int rows, int V, const int64_t *target,
+                                 int64_t padding_idx, float smoothing, float gscale, const float *gout,
+                                 float *dz, int lddz, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- on-device self-check kernels (tests only) ---------------------------------
  * Plain one-thread-per-output CUDA kernels with the same f16-operand / f32-accumulate

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -28,14 +28,68 @@ class LinearArgs(C.Structure):
                 ("out_f16", C.c_void_p), ("ld16", C.c_int),
                 ("batch", C.c_int), ("stride_A", C.c_longlong), ("stride_W", C.c_longlong),
                 ("stride_bias", C.c_longlong), ("stride_add", C.c_longlong), ("stride_out_f32", C.c_longlong),
+                ("stride_out_f16", C.c_longlong), ("out16_pre_add", C.c_int)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int), ("a_mn", C.c_int),
+                ("B", C.c_void_p), ("ldb", C.c_int), ("b_mn", C.c_int),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("alpha", C.c_void_p), ("bias", C.c_void_p), ("act", C.c_int),
+                ("relu_mask", C.c_void_p), ("ld_mask", C.c_int),
+                ("addend", C.c_void_p), ("ld_add", C.c_int), ("add_period", C.c_int),
+                ("accumulate", C.c_int), ("out_f32", C.c_void_p), ("ld32", C.c_int),
+                ("out_f16", C.c_void_p), ("ld16", C.c_int), ("out16_pre_add", C.c_int),
+                ("batch", C.c_int), ("stride_A", C.c_longlong), ("stride_B", C.c_longlong),
+                ("stride_bias", C.c_longlong), ("stride_add", C.c_longlong), ("stride_out_f32", C.c_longlong),
                 ("stride_out_f16", C.c_longlong)]
+
+
+class LinearDgradArgs(C.Structure):
+    _fields_ = [("dY", C.c_void_p), ("lddy", C.c_int), ("W", C.c_void_p), ("ldw", C.c_int),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("alpha", C.c_void_p),
+                ("relu_mask", C.c_void_p), ("ld_mask", C.c_int), ("addend", C.c_void_p), ("ld_add", C.c_int),
+                ("dX_f32", C.c_void_p), ("ld32", C.c_int), ("dX_f16", C.c_void_p), ("ld16", C.c_int),
+                ("batch", C.c_int), ("stride_dY", C.c_longlong), ("stride_W", C.c_longlong),
+                ("stride_add", C.c_longlong), ("stride_dX_f32", C.c_longlong), ("stride_dX_f16", C.c_longlong)]
+
+
+class LinearWgradArgs(C.Structure):
+    _fields_ = [("dY", C.c_void_p), ("lddy", C.c_int), ("X", C.c_void_p), ("ldx", C.c_int),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("alpha", C.c_void_p),
+                ("dW", C.c_void_p), ("lddw", C.c_int),
+                ("batch", C.c_int), ("stride_dY", C.c_longlong), ("stride_X", C.c_longlong),
+                ("stride_dW", C.c_longlong)]
+
+
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("a_2", C.c_void_p), ("eps", C.c_float), ("rows", C.c_int), ("d", C.c_int),
+                ("dy", C.c_void_p), ("dy_scale", C.c_void_p), ("dres", C.c_void_p), ("dx", C.c_void_p),
+                ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p)]
+
+
+class EmbedBwdArgs(C.Structure):
+    _fields_ = [("ids", C.c_void_p), ("lut", C.c_void_p), ("pe", C.c_void_p),
+                ("rows", C.c_int), ("L", C.c_int), ("d", C.c_int), ("vocab", C.c_int), ("scale", C.c_float),
+                ("a_2", C.c_void_p), ("eps", C.c_float), ("dy", C.c_void_p),
+                ("dlut", C.c_void_p), ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p)]
+
+
+class AttnCoreBwdArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int),
+                ("v", C.c_void_p), ("ldv", C.c_int), ("dO", C.c_void_p), ("lddo", C.c_int),
+                ("stats", C.c_void_p), ("delta", C.c_void_p),
+                ("mask_bits", C.c_void_p), ("mask_rows_q", C.c_int),
+                ("B", C.c_int), ("h", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("d_k", C.c_int),
+                ("dq", C.c_void_p), ("lddq", C.c_int), ("dk", C.c_void_p), ("lddk", C.c_int),
+                ("dv", C.c_void_p), ("lddv", C.c_int)]
 
 
 class AttnCoreArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int),
                 ("v", C.c_void_p), ("ldv", C.c_int), ("mask_bits", C.c_void_p),
                 ("mask_rows_q", C.c_int), ("B", C.c_int), ("h", C.c_int), ("Lq", C.c_int),
-                ("Lk", C.c_int), ("d_k", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int)]
+                ("Lk", C.c_int), ("d_k", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int), ("stats", C.c_void_p)]
 
 
 class AttnSiteArgs(C.Structure):
@@ -87,6 +141,26 @@ SYMBOLS = {
     "mtn_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), C.c_void_p]),
     "mtn_check_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "mtn_check_attn_core_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
+    # ---- backward (ABI v3)
+    "mtn_gemm_f16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "mtn_check_gemm_f16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "mtn_linear_dgrad": (C.c_int, [C.POINTER(LinearDgradArgs), C.c_void_p]),
+    "mtn_linear_wgrad": (C.c_int, [C.POINTER(LinearWgradArgs), C.c_void_p]),
+    "mtn_cast_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_grad_absmax": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "mtn_grad_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_scale_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "mtn_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdArgs), C.c_void_p]),
+    "mtn_embed_bwd": (C.c_int, [C.POINTER(EmbedBwdArgs), C.c_void_p]),
+    "mtn_attn_delta": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p]),
+    "mtn_attn_core_bwd": (C.c_int, [C.POINTER(AttnCoreBwdArgs), C.c_void_p]),
+    "mtn_log_softmax_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_void_p]),
+    "mtn_label_smoothing_loss_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_float,
+                                               C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                               C.c_void_p]),
 }
 
 _lib = None
@@ -211,7 +285,7 @@ def mask_pack(mask):
 
 
 def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=None, out_f16=None,
-           _check_kernel=False):
+           _check_kernel=False, out16_pre_add=False):
     """C = act(A W^T + bias) + addend.  A: [M, K] f16 (row stride allowed), W: [N, K] f16."""
     _req(A, torch.float16, "A"); _req(W, torch.float16, "W"); _req(bias, torch.float32, "bias")
     _req(addend, torch.float32, "addend"); _req(out_f32, torch.float32, "out_f32")
@@ -230,6 +304,7 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
     if out_f16 is not None:
         assert out_f16.dim() == 2 and tuple(out_f16.shape) == (a.M, a.N)
         a.out_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
+    a.out16_pre_add = 1 if out16_pre_add else 0
     fn = lib().mtn_check_linear_fwd if _check_kernel else lib().mtn_linear_fwd
     nbytes = 2 * (a.M * a.K + a.N * a.K) + a.M * a.N * ((4 if out_f32 is not None else 0) +
                                                         (2 if out_f16 is not None else 0) +
@@ -238,7 +313,7 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
             keep=(A, W, bias, addend, out_f32, out_f16))
 
 
-def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False):
+def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False, stats=None):
     """q: [B*Lq, >=h*d_k] f16 view (row stride = leading dimension), k/v: [B*Lk, ...];
     out: [B*Lq, >=h*d_k] f16.  mask_bits: output of mask_pack or None."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
@@ -253,9 +328,13 @@ def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=Fal
         a.mask_bits, a.mask_rows_q = mask_bits.data_ptr(), mask_bits.shape[1]
     a.B, a.h, a.Lq, a.Lk, a.d_k = B, h, Lq, Lk, d_k
     a.out, a.ldo = out.data_ptr(), out.stride(0)
+    if stats is not None:      # [B, h, Lq, 2] f32 softmax statistics for the backward pass
+        _req(stats, torch.float32, "stats")
+        assert stats.is_contiguous() and stats.numel() == B * h * Lq * 2
+        a.stats = stats.data_ptr()
     fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
     _launch("attn_core", 4 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (2 * Lq + 2 * Lk),
-            lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits))
+            lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits, stats))
 
 
 def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None):
@@ -346,3 +425,218 @@ def linear_batched(A, W, bias=None, act=ACT_NONE, addend=None, out_f32=None, out
                                                                       (4 if addend is not None else 0)))
     _launch("linear", 2 * a.batch * a.M * a.N * a.K, nbytes, lambda: lib().mtn_linear_fwd(C.byref(a), stream_ptr()),
             keep=(A, W, bias, addend, out_f32, out_f16))
+
+
+# ------------------------------------------------------------------------------
+# backward wrappers (ABI v3).  `scale2` is a 2-element f32 device tensor {S, 1/S} from grad_scale(); wrappers
+# take views of it (scale2[0:1] / scale2[1:2]) or None as `scale` / `alpha` device scalars.
+# ------------------------------------------------------------------------------
+def gemm(A, B, M, N, K, a_mn=False, b_mn=False, alpha=None, bias=None, act=ACT_NONE, relu_mask=None, addend=None,
+         add_period=0, accumulate=False, out_f32=None, out_f16=None, _check_kernel=False):
+    """General tensor-core GEMM (see MtnGemmArgs); 2-D operands, row strides honoured."""
+    _req(A, torch.float16, "A"); _req(B, torch.float16, "B"); _req(alpha, torch.float32, "alpha")
+    _req(bias, torch.float32, "bias"); _req(relu_mask, torch.float16, "relu_mask"); _req(addend, torch.float32, "addend")
+    _req(out_f32, torch.float32, "out_f32"); _req(out_f16, torch.float16, "out_f16")
+    a = GemmArgs()
+    a.A, a.lda, a.a_mn = A.data_ptr(), A.stride(0), 1 if a_mn else 0
+    a.B, a.ldb, a.b_mn = B.data_ptr(), B.stride(0), 1 if b_mn else 0
+    a.M, a.N, a.K, a.act = M, N, K, act
+    assert tuple(A.shape) == ((K, M) if a_mn else (M, K)) and tuple(B.shape) == ((K, N) if b_mn else (N, K))
+    a.alpha = alpha.data_ptr() if alpha is not None else None
+    a.bias = bias.data_ptr() if bias is not None else None
+    if relu_mask is not None:
+        a.relu_mask, a.ld_mask = relu_mask.data_ptr(), relu_mask.stride(0)
+    if addend is not None:
+        a.addend, a.ld_add, a.add_period = addend.data_ptr(), addend.stride(0), int(add_period)
+    a.accumulate = 1 if accumulate else 0
+    if out_f32 is not None:
+        assert tuple(out_f32.shape) == (M, N)
+        a.out_f32, a.ld32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_f16 is not None:
+        assert tuple(out_f16.shape) == (M, N)
+        a.out_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
+    fn = lib().mtn_check_gemm_f16 if _check_kernel else lib().mtn_gemm_f16
+    _launch("gemm", 2 * M * N * K, 2 * (M * K + N * K) + M * N * 4, lambda: fn(C.byref(a), stream_ptr()),
+            keep=(A, B, alpha, bias, relu_mask, addend, out_f32, out_f16))
+
+
+def linear_dgrad(dY, W, alpha=None, relu_mask=None, addend=None, out_f32=None, out_f16=None):
+    """dX = alpha * dY W (* relu_mask > 0) (+ addend).  dY: [M, N] f16, W: [N, K] f16 (forward layout)."""
+    _req(dY, torch.float16, "dY"); _req(W, torch.float16, "W"); _req(alpha, torch.float32, "alpha")
+    _req(relu_mask, torch.float16, "relu_mask"); _req(addend, torch.float32, "addend")
+    _req(out_f32, torch.float32, "out_f32"); _req(out_f16, torch.float16, "out_f16")
+    assert dY.dim() == 2 and W.dim() == 2 and dY.shape[1] == W.shape[0]
+    a = LinearDgradArgs()
+    a.dY, a.lddy, a.W, a.ldw = dY.data_ptr(), dY.stride(0), W.data_ptr(), W.stride(0)
+    a.M, a.N, a.K = dY.shape[0], W.shape[0], W.shape[1]
+    a.alpha = alpha.data_ptr() if alpha is not None else None
+    if relu_mask is not None:
+        assert tuple(relu_mask.shape) == (a.M, a.K)
+        a.relu_mask, a.ld_mask = relu_mask.data_ptr(), relu_mask.stride(0)
+    if addend is not None:
+        assert tuple(addend.shape) == (a.M, a.K)
+        a.addend, a.ld_add = addend.data_ptr(), addend.stride(0)
+    if out_f32 is not None:
+        assert tuple(out_f32.shape) == (a.M, a.K)
+        a.dX_f32, a.ld32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_f16 is not None:
+        assert tuple(out_f16.shape) == (a.M, a.K)
+        a.dX_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
+    nbytes = 2 * (a.M * a.N + a.N * a.K) + a.M * a.K * ((4 if out_f32 is not None else 0) + (2 if out_f16 is not None else 0))
+    _launch("linear_dgrad", 2 * a.M * a.N * a.K, nbytes, lambda: lib().mtn_linear_dgrad(C.byref(a), stream_ptr()),
+            keep=(dY, W, alpha, relu_mask, addend, out_f32, out_f16))
+
+
+def linear_wgrad(dY, X, dW, alpha=None):
+    """dW += alpha * dY^T X.  dY: [M, N] f16, X: [M, K] f16, dW: [N, K] f32 (row stride honoured)."""
+    _req(dY, torch.float16, "dY"); _req(X, torch.float16, "X"); _req(dW, torch.float32, "dW")
+    _req(alpha, torch.float32, "alpha")
+    assert dY.dim() == 2 and X.dim() == 2 and dY.shape[0] == X.shape[0] and tuple(dW.shape) == (dY.shape[1], X.shape[1])
+    a = LinearWgradArgs()
+    a.dY, a.lddy, a.X, a.ldx = dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0)
+    a.M, a.N, a.K = dY.shape[0], dY.shape[1], X.shape[1]
+    a.alpha = alpha.data_ptr() if alpha is not None else None
+    a.dW, a.lddw = dW.data_ptr(), dW.stride(0)
+    _launch("linear_wgrad", 2 * a.M * a.N * a.K, 2 * a.M * (a.N + a.K) + 8 * a.N * a.K,
+            lambda: lib().mtn_linear_wgrad(C.byref(a), stream_ptr()), keep=(dY, X, dW, alpha))
+
+
+def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mask=None):
+    """dst_f16 = f16(src * scale [masked]); colsum += alpha * column sums.  src: 2-D f32 or f16."""
+    assert src.dim() == 2 and src.is_cuda and src.dtype in (torch.float32, torch.float16) and src.stride(1) == 1
+    _req(dst_f16, torch.float16, "dst_f16"); _req(colsum, torch.float32, "colsum"); _req(scale, torch.float32, "scale")
+    _req(alpha, torch.float32, "alpha"); _req(relu_mask, torch.float16, "relu_mask")
+    rows, cols = src.shape
+    assert dst_f16 is None or tuple(dst_f16.shape) == (rows, cols)
+    assert colsum is None or (colsum.is_contiguous() and colsum.numel() == cols)
+    esz = 2 if src.dtype == torch.float16 else 4
+    _launch("cast_colsum", 0, rows * cols * (esz + (2 if dst_f16 is not None else 0)),
+            lambda: lib().mtn_cast_colsum(ptr(src), 1 if src.dtype == torch.float16 else 0, src.stride(0), ptr(dst_f16),
+                                          dst_f16.stride(0) if dst_f16 is not None else 0, ptr(relu_mask),
+                                          relu_mask.stride(0) if relu_mask is not None else 0, rows, cols, ptr(scale),
+                                          ptr(alpha), ptr(colsum), stream_ptr()),
+            keep=(src, dst_f16, colsum, scale, alpha, relu_mask))
+
+
+_SCALE_SLOTS = {}
+
+
+def grad_scale(tensors):
+    """{S, 1/S} (2-element f32 device tensor) for the f32 gradient tensors `tensors`: S = 2^k with
+    max|g| * S in [128, 256).  No host synchronisation."""
+    dev = tensors[0].device
+    slot = _SCALE_SLOTS.get(dev)
+    if slot is None:
+        slot = _SCALE_SLOTS[dev] = torch.zeros(4, dtype=torch.int32, device=dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    for t in tensors:
+        _req(t, torch.float32, "grad")
+        tc = t if t.is_contiguous() else t.contiguous()
+        assert tc.numel() % 4 == 0
+        _launch("grad_absmax", 0, tc.numel() * 4,
+                lambda tc=tc: lib().mtn_grad_absmax(ptr(tc), tc.numel(), ptr(slot), stream_ptr()), keep=(tc, slot))
+    _launch("grad_scale", 0, 16, lambda: lib().mtn_grad_scale(ptr(slot), ptr(out), stream_ptr()), keep=(slot, out))
+    return out
+
+
+def scale_f32(x, alpha, y, accumulate=False):
+    """y = (accumulate ? y : 0) + x * alpha (alpha: 1-element f32 device tensor or None)."""
+    _req(x, torch.float32, "x"); _req(y, torch.float32, "y"); _req(alpha, torch.float32, "alpha")
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel() and x.numel() % 4 == 0
+    _launch("scale_f32", 0, x.numel() * (12 if accumulate else 8),
+            lambda: lib().mtn_scale_f32(ptr(x), ptr(alpha), ptr(y), x.numel(), 1 if accumulate else 0, stream_ptr()),
+            keep=(x, alpha, y))
+
+
+def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale=None, param_alpha=None):
+    """dx = dres + dLN(dy * dy_scale); da_2 / db_2 += param_alpha * (...).  x, dy, dx: [rows, d] f32 contiguous."""
+    for t, n in ((x, "x"), (a_2, "a_2"), (dy, "dy"), (dx, "dx"), (dres, "dres"), (da_2, "da_2"), (db_2, "db_2"),
+                 (dy_scale, "dy_scale"), (param_alpha, "param_alpha")):
+        _req(t, torch.float32, n)
+    d = x.shape[-1]
+    rows = x.numel() // d
+    assert x.is_contiguous() and dy.is_contiguous() and dx.is_contiguous() and (dres is None or dres.is_contiguous())
+    assert dy.numel() == x.numel() and dx.numel() == x.numel()
+    a = LayerNormBwdArgs()
+    a.x, a.a_2, a.eps, a.rows, a.d = x.data_ptr(), a_2.data_ptr(), float(eps), rows, d
+    a.dy = dy.data_ptr()
+    a.dy_scale = dy_scale.data_ptr() if dy_scale is not None else None
+    a.dres = dres.data_ptr() if dres is not None else None
+    a.dx = dx.data_ptr()
+    a.da_2 = da_2.data_ptr() if da_2 is not None else None
+    a.db_2 = db_2.data_ptr() if db_2 is not None else None
+    a.param_alpha = param_alpha.data_ptr() if param_alpha is not None else None
+    _launch("layernorm_bwd", 0, rows * d * (12 + (4 if dres is not None else 0)),
+            lambda: lib().mtn_layernorm_bwd(C.byref(a), stream_ptr()),
+            keep=(x, a_2, dy, dx, dres, da_2, db_2, dy_scale, param_alpha))
+
+
+def embed_bwd(ids, lut, pe, scale, dy, dlut, ln=None, da_2=None, db_2=None, param_alpha=None):
+    """Backward of embed(): dlut[ids] += scale * dpre (atomic), LN parameter gradients when ln is given."""
+    assert ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_cuda
+    _req(lut, torch.float32, "lut"); _req(pe, torch.float32, "pe"); _req(dy, torch.float32, "dy")
+    _req(dlut, torch.float32, "dlut")
+    B, L = ids.shape
+    d = lut.shape[1]
+    idc = ids.contiguous()
+    assert dy.is_contiguous() and dy.numel() == B * L * d and dlut.is_contiguous() and dlut.shape == lut.shape
+    a = EmbedBwdArgs()
+    a.ids, a.lut, a.pe = idc.data_ptr(), lut.data_ptr(), pe.data_ptr()
+    a.rows, a.L, a.d, a.vocab, a.scale = B * L, L, d, lut.shape[0], float(scale)
+    if ln is not None:
+        a.a_2, a.eps = ln[0].data_ptr(), float(ln[2])
+        a.da_2, a.db_2 = da_2.data_ptr(), db_2.data_ptr()
+    a.dy, a.dlut = dy.data_ptr(), dlut.data_ptr()
+    a.param_alpha = param_alpha.data_ptr() if param_alpha is not None else None
+    _launch("embed_bwd", 0, B * L * d * 16, lambda: lib().mtn_embed_bwd(C.byref(a), stream_ptr()),
+            keep=(idc, lut, pe, dy, dlut, ln, da_2, db_2, param_alpha))
+
+
+def attn_delta(dO, O, B, Lq, h, d_k, delta):
+    _req(dO, torch.float16, "dO"); _req(O, torch.float16, "O"); _req(delta, torch.float32, "delta")
+    assert delta.is_contiguous() and delta.numel() == B * h * Lq
+    _launch("attn_delta", 0, B * Lq * h * d_k * 4,
+            lambda: lib().mtn_attn_delta(ptr(dO), dO.stride(0), ptr(O), O.stride(0), B, Lq, h, d_k, ptr(delta),
+                                         stream_ptr()), keep=(dO, O, delta))
+
+
+def attn_core_bwd(q, k, v, dO, stats, delta, B, h, Lq, Lk, d_k, dq, dk, dv, mask_bits=None):
+    """q/k/v/dO: f16 2-D views (row stride = leading dimension); stats [B,h,Lq,2], delta [B,h,Lq] f32;
+    dq: f32 [B*Lq, >= h*d_k] ACCUMULATED (zero it first); dk/dv: f16 [B*Lk, >= h*d_k] written."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (dO, "dO"), (dk, "dk"), (dv, "dv")):
+        _req(t, torch.float16, n)
+        assert t.dim() == 2
+    _req(stats, torch.float32, "stats"); _req(delta, torch.float32, "delta"); _req(dq, torch.float32, "dq")
+    a = AttnCoreBwdArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0)
+    a.dO, a.lddo = dO.data_ptr(), dO.stride(0)
+    a.stats, a.delta = stats.data_ptr(), delta.data_ptr()
+    if mask_bits is not None:
+        assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == B
+        a.mask_bits, a.mask_rows_q = mask_bits.data_ptr(), mask_bits.shape[1]
+    a.B, a.h, a.Lq, a.Lk, a.d_k = B, h, Lq, Lk, d_k
+    a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0)
+    _launch("attn_core_bwd", 10 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (4 * Lq + 4 * Lk),
+            lambda: lib().mtn_attn_core_bwd(C.byref(a), stream_ptr()),
+            keep=(q, k, v, dO, stats, delta, dq, dk, dv, mask_bits))
+
+
+def log_softmax_bwd(y, dy, V, dz):
+    """dz[:, :V] = dy - exp(y) * rowsum(dy); dz[:, V:] = 0.  y, dy: [rows, >=V] f32; dz: [rows, ld] f32."""
+    _req(y, torch.float32, "y"); _req(dy, torch.float32, "dy"); _req(dz, torch.float32, "dz")
+    rows = y.shape[0]
+    _launch("log_softmax_bwd", 0, rows * V * 12,
+            lambda: lib().mtn_log_softmax_bwd(ptr(y), y.stride(0), ptr(dy), dy.stride(0), rows, V, ptr(dz), dz.stride(0),
+                                              stream_ptr()), keep=(y, dy, dz))
+
+
+def label_smoothing_loss_bwd(z, V, target, padding_idx, smoothing, dz, gscale=1.0, gout=None):
+    """dz = gscale * gout * d(label-smoothed KL sum)/dz for logits or log-probs z [rows, ld >= V]."""
+    _req(z, torch.float32, "z"); _req(dz, torch.float32, "dz"); _req(gout, torch.float32, "gout")
+    tc = target.contiguous()
+    rows = z.shape[0]
+    ws = torch.empty(256, dtype=torch.uint8, device=z.device)
+    _launch("label_smoothing_bwd", 0, rows * V * 8,
+            lambda: lib().mtn_label_smoothing_loss_bwd(ptr(z), z.stride(0), rows, V, ptr(tc), int(padding_idx),
+                                                       float(smoothing), float(gscale), ptr(gout), ptr(dz), dz.stride(0),
+                                                       ptr(ws), 256, stream_ptr()), keep=(z, tc, dz, gout, ws))

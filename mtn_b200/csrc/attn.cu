@@ -64,6 +64,7 @@ struct AttnParams {
   float scale;
   __half* out;
   int ldo;
+  float2* stats;  // optional [B, h, Lq] {row maximum (log2 domain), 1 / row sum}: saved for the backward pass
 };
 
 enum {  // "+1": two barriers, one per buffer
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.f / l_run;
+      if (p.stats != nullptr && qi < p.Lq) p.stats[((size_t)b * p.h + hd) * p.Lq + qi] = make_float2(m_run, inv_l);
 #pragma unroll
       for (int c = 0; c < DK / 32; ++c) {
         uint32_t r[32];
@@ -391,7 +393,7 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   const int nqt = (a.Lq + ATT_QT - 1) / ATT_QT;
   const int n_items = nqt * a.h * a.B;
   AttnParams p{n_items, nqt, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
-               1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo};
+               1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo, reinterpret_cast<float2*>(a.stats)};
   static int slots = 0;  // resident CTAs: 2 per SM
   if (slots == 0) {
     int dev = 0, n = 0;
@@ -475,7 +477,7 @@ extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
   int rc = mtn::validate_attn(a);
   if (rc) return rc;
   mtn::AttnParams p{0, 0, a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
-                    1.0f / sqrtf((float)a->d_k), reinterpret_cast<__half*>(a->out), a->ldo};
+                    1.0f / sqrtf((float)a->d_k), reinterpret_cast<__half*>(a->out), a->ldo, nullptr};
   dim3 grid(a->Lq, a->h, a->B);
   mtn::attn_core_check_kernel<<<grid, 32, a->Lk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(a->q), a->ldq, reinterpret_cast<const __half*>(a->k), a->ldk,

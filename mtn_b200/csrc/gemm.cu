@@ -11,6 +11,13 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..9 = epilogue (warp w may touch TMEM lanes 32*(w%4) .. +31; two warps per quarter).
+//
+// The same kernel is the backward of those call sites (mtn_linear_dgrad / mtn_linear_wgrad): an operand
+// may be "MN-major" (stored [k, mn], mn contiguous), which UMMA consumes through the transpose bits of the
+// instruction descriptor, so   dX = dY W   reads W in its forward [out, in] layout and   dW = dY^T X
+// reads dY and X in their forward [rows, features] layouts -- no transposed copies exist anywhere.
+// Weight gradients (small output, long contraction) run split-K: the contraction is cut over CTAs and the
+// partial tiles are accumulated into the f32 gradient with L2 reductions (red.global.add).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -28,6 +35,11 @@ struct GemmEpi {
   int ld32;
   __half* out16;
   int ld16;
+  const float* alpha;      // device scalar multiplied into the accumulator first (NULL: 1)
+  const __half* relu_mask; // [M, ld_mask] forward activation: result zeroed where it is <= 0 (ReLU backward)
+  int ld_mask;
+  int accumulate;          // out32 += result (red.global.add), required for split-K
+  int out16_pre_add;       // out16 receives the value BEFORE the addend (video encoder: relu(.) without PE)
   // strided batch (element strides between consecutive problems; batch == 1: unused)
   long long s_bias, s_add, s_out32, s_out16;
 };
@@ -58,10 +70,16 @@ struct GemmSmem {
 // them, so W crosses L2->SM once per cluster instead of once per CTA (the 128xBN tiles are L2-bandwidth
 // bound otherwise).  A slot is refilled only after every CTA of the cluster has consumed it: the MMA
 // warp's tcgen05.commit arrives on the "empty" barrier of all CL CTAs (multicast commit).
-template <int BN, int STAGES, int CL>
+//
+// A_MN / B_MN: the operand is MN-major.  Its 64-row k-block is then staged as (BM or BN)/64 TMA boxes of
+// [64 k-rows x 64 mn-columns] (128-byte swizzled rows), i.e. the canonical UMMA MN-major layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = 8192 B (next 64 mn), SBO = 1024 B (next 8 k).
+// ksplit > 1: tile index also enumerates contraction slices of kb_per_split k-blocks (split-K).
+template <int BN, int STAGES, int CL, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmEpi epi0, int M, int N, int K, int tiles_n, int tiles_per_batch, int num_tiles) {
+                       const GemmEpi epi0, int M, int N, int K, int tiles_n, int tiles_per_batch, int num_tiles,
+                       int tiles_mn, int kb_per_split) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -77,7 +95,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nkb = (K + BK - 1) / BK;  // K tail: TMA zero-fills columns >= K
+  const int nkb_all = (K + BK - 1) / BK;  // K tail: TMA zero-fills columns >= K
+  static_assert(CL == 1 || (A_MN == 0 && B_MN == 0), "multicast path is K-major only");
+  // k-block range of tile-in-batch index tl (split-K slice tl / tiles_mn)
+  auto kb_range = [&](int tl, int& kb0, int& kb1) {
+    kb0 = (tl / tiles_mn) * kb_per_split;
+    kb1 = min(nkb_all, kb0 + kb_per_split);
+  };
   // num_tiles counts cluster-level "super tiles" (CL m-blocks x 1 n-block); this CTA takes m-block
   // (mg * CL + rank) of each.  Out-of-range m-blocks still take part in the multicast and barriers:
   // their A rows are zero-filled by TMA and their stores are predicated off.
@@ -113,14 +137,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint32_t it = 0;  // k-blocks issued so far (ring position across tiles)
       for (int t = first_tile; t < num_tiles; t += tile_stride) {
         const int bt = t / tiles_per_batch, tl = t % tiles_per_batch;  // problem of the strided batch, tile in it
-        const int m0 = ((tl / tiles_n) * CL + rank) * BM, n0 = (tl % tiles_n) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int tmn = tl % tiles_mn;
+        const int m0 = ((tmn / tiles_n) * CL + rank) * BM, n0 = (tmn % tiles_n) * BN;
+        int kb0, kb1;
+        kb_range(tl, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty(s), ((it / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full(s), L::STAGE_BYTES);
           const uint32_t sA = base + s * L::STAGE_BYTES;
-          tma_load_3d(sA, &tmA, bar_full(s), kb * BK, m0, bt);
-          if (CL == 1) {
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_3d(sA + j * 8192, &tmA, bar_full(s), m0 + 64 * j, kb * BK, bt);
+          } else {
+            tma_load_3d(sA, &tmA, bar_full(s), kb * BK, m0, bt);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(sA + L::A_BYTES + j * 8192, &tmB, bar_full(s), n0 + 64 * j, kb * BK, bt);
+          } else if (CL == 1) {
             tma_load_3d(sA + L::A_BYTES, &tmB, bar_full(s), kb * BK, n0, bt);
           } else {  // my 1/CL of the W tile, delivered to every CTA of the cluster
             constexpr int SL = BN / CL;
@@ -132,27 +168,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, A_MN, B_MN);
     uint32_t it = 0, lt = 0;  // ring position, local tile counter
     for (int t = first_tile; t < num_tiles; t += tile_stride, ++lt) {
       const uint32_t buf = lt & 1;
       mbar_wait(bar_acc_empty(buf), ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
+      int kb0, kb1;
+      kb_range(t % tiles_per_batch, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(bar_full(s), (it / STAGES) & 1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = base + s * L::STAGE_BYTES;
-          const uint64_t da = make_smem_desc(sA, 16, 1024, SWZ_128B);
-          const uint64_t db = make_smem_desc(sA + L::A_BYTES, 16, 1024, SWZ_128B);
+          // K-major: +32 B along K inside the swizzled row (= +2 encoded) per 16-wide k-step.
+          // MN-major: a k-step is 16 k-rows of 128 B = +2048 B (= +128 encoded).
+          const uint64_t da = A_MN ? make_smem_desc(sA, 8192, 1024, SWZ_128B) : make_smem_desc(sA, 16, 1024, SWZ_128B);
+          const uint64_t db = B_MN ? make_smem_desc(sA + L::A_BYTES, 8192, 1024, SWZ_128B)
+                                   : make_smem_desc(sA + L::A_BYTES, 16, 1024, SWZ_128B);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the swizzled row = +2 encoded
-            tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_f16(d_tmem, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, ((kb - kb0) | k) != 0);
           if (CL == 1) tc_commit(bar_empty(s));  // frees the stage when these MMAs retire
           else tc_commit_mc(bar_empty(s), kMask);
-          if (kb == nkb - 1) tc_commit(bar_acc_full(buf));
+          if (kb == kb1 - 1) tc_commit(bar_acc_full(buf));
         }
         __syncwarp();
       }
@@ -172,9 +213,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // In-place residual (x += A W^T + b, the common SublayerConnection case): the add is done by L2
     // reductions (red.global.add.v4.f32) -- the 16 MB residual read that makes these launches
     // L2-bandwidth bound disappears and each element still receives exactly one f32 add.
-    const bool red_add = epi0.addend != nullptr && epi0.addend == epi0.out32 && epi0.add_period == 0 &&
-                         epi0.ld_add == epi0.ld32 && epi0.out16 == nullptr && epi0.s_add == epi0.s_out32;
-    const bool f16_only = epi0.out16 != nullptr && epi0.out32 == nullptr && epi0.addend == nullptr;
+    const bool red_add = epi0.accumulate != 0 ||
+                         (epi0.addend != nullptr && epi0.addend == epi0.out32 && epi0.add_period == 0 &&
+                          epi0.ld_add == epi0.ld32 && epi0.out16 == nullptr && epi0.s_add == epi0.s_out32);
+    const bool has_add = epi0.addend != nullptr && epi0.accumulate == 0;
+    const bool f16_only = epi0.out16 != nullptr && epi0.out32 == nullptr && epi0.addend == nullptr &&
+                          epi0.relu_mask == nullptr;
+    const float alpha = epi0.alpha != nullptr ? __ldg(epi0.alpha) : 1.f;
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
     // shared-memory slots of the transpose tile (float4 units); (row & 7) == sub_r for every row this lane reads
@@ -182,8 +227,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int rd0 = sub_r * 8 + ((2 * c8) ^ sub_r), rd1 = sub_r * 8 + ((2 * c8 + 1) ^ sub_r);
     uint32_t lt = 0;
     for (int t = first_tile; t < num_tiles; t += tile_stride, ++lt) {
-      const int bt = t / tiles_per_batch, tl = t % tiles_per_batch;
-      const int m0 = ((tl / tiles_n) * CL + rank) * BM, n0 = (tl % tiles_n) * BN;
+      const int bt = t / tiles_per_batch, tmn = (t % tiles_per_batch) % tiles_mn;
+      const int m0 = ((tmn / tiles_n) * CL + rank) * BM, n0 = (tmn % tiles_n) * BN;
       GemmEpi epi = epi0;  // this problem's operands
       if (bt > 0) {
         if (epi.bias) epi.bias += bt * epi.s_bias;
@@ -194,7 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t buf = lt & 1;
       const int row0 = m0 + q * 32 + sub_r;  // this lane's first row; the others are +8, +16, +24
       // per-row element offsets, hoisted out of the chunk loop
-      size_t off32[4], off16[4], offad[4];
+      size_t off32[4], off16[4], offad[4], offmk[4];
       bool row_ok[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -202,6 +247,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         row_ok[i] = r < M;
         off32[i] = (size_t)r * epi.ld32;
         off16[i] = (size_t)r * epi.ld16;
+        offmk[i] = (size_t)r * epi.ld_mask;
         offad[i] = (size_t)(epi.add_period > 0 ? r % epi.add_period : r) * epi.ld_add;
       }
       mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
@@ -231,8 +277,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float v0 = __uint_as_float(acc[4 * j]) + bb[j].x, v1 = __uint_as_float(acc[4 * j + 1]) + bb[j].y;
-            float v2 = __uint_as_float(acc[4 * j + 2]) + bb[j].z, v3 = __uint_as_float(acc[4 * j + 3]) + bb[j].w;
+            float v0 = fmaf(__uint_as_float(acc[4 * j]), alpha, bb[j].x), v1 = fmaf(__uint_as_float(acc[4 * j + 1]), alpha, bb[j].y);
+            float v2 = fmaf(__uint_as_float(acc[4 * j + 2]), alpha, bb[j].z), v3 = fmaf(__uint_as_float(acc[4 * j + 3]), alpha, bb[j].w);
             if (epi.act == MTN_ACT_RELU) {
               v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
             }
@@ -267,7 +313,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + col + 4));
         }
         float4 res[8];
-        if (epi.addend != nullptr && !red_add) {  // residual / positional operand: requested before touching TMEM
+        uint4 mk[4];
+        if (epi.relu_mask != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            mk[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok[i] && col_ok) mk[i] = *reinterpret_cast<const uint4*>(epi.relu_mask + offmk[i] + col);
+          }
+        }
+        if (has_add && !red_add) {  // residual / positional operand: requested before touching TMEM
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             res[2 * i] = res[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -301,13 +355,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 x0 = v[2 * i], x1 = v[2 * i + 1];
-          x0.x += b0.x; x0.y += b0.y; x0.z += b0.z; x0.w += b0.w;
-          x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
+          x0.x = fmaf(x0.x, alpha, b0.x); x0.y = fmaf(x0.y, alpha, b0.y); x0.z = fmaf(x0.z, alpha, b0.z); x0.w = fmaf(x0.w, alpha, b0.w);
+          x1.x = fmaf(x1.x, alpha, b1.x); x1.y = fmaf(x1.y, alpha, b1.y); x1.z = fmaf(x1.z, alpha, b1.z); x1.w = fmaf(x1.w, alpha, b1.w);
           if (epi.act == MTN_ACT_RELU) {
             x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
             x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
           }
-          if (epi.addend != nullptr && !red_add) {
+          if (epi.relu_mask != nullptr) {  // ReLU backward: keep the gradient where the forward activation was > 0
+            const __half2* hm = reinterpret_cast<const __half2*>(&mk[i]);
+            const float2 m0_ = __half22float2(hm[0]), m1_ = __half22float2(hm[1]), m2_ = __half22float2(hm[2]),
+                         m3_ = __half22float2(hm[3]);
+            x0.x = m0_.x > 0.f ? x0.x : 0.f; x0.y = m0_.y > 0.f ? x0.y : 0.f;
+            x0.z = m1_.x > 0.f ? x0.z : 0.f; x0.w = m1_.y > 0.f ? x0.w : 0.f;
+            x1.x = m2_.x > 0.f ? x1.x : 0.f; x1.y = m2_.y > 0.f ? x1.y : 0.f;
+            x1.z = m3_.x > 0.f ? x1.z : 0.f; x1.w = m3_.y > 0.f ? x1.w : 0.f;
+          }
+          uint4 pre16 = make_uint4(0u, 0u, 0u, 0u);
+          if (epi.out16_pre_add)
+            pre16 = make_uint4(pack_f16x2_sat(x0.x, x0.y), pack_f16x2_sat(x0.z, x0.w), pack_f16x2_sat(x1.x, x1.y),
+                               pack_f16x2_sat(x1.z, x1.w));
+          if (has_add && !red_add) {
             x0.x += res[2 * i].x; x0.y += res[2 * i].y; x0.z += res[2 * i].z; x0.w += res[2 * i].w;
             x1.x += res[2 * i + 1].x; x1.y += res[2 * i + 1].y; x1.z += res[2 * i + 1].z; x1.w += res[2 * i + 1].w;
           }
@@ -327,8 +394,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
             if (epi.out16 != nullptr)
               *reinterpret_cast<uint4*>(epi.out16 + off16[i] + col) =
-                  make_uint4(pack_f16x2_sat(x0.x, x0.y), pack_f16x2_sat(x0.z, x0.w), pack_f16x2_sat(x1.x, x1.y),
-                             pack_f16x2_sat(x1.z, x1.w));
+                  epi.out16_pre_add ? pre16
+                                    : make_uint4(pack_f16x2_sat(x0.x, x0.y), pack_f16x2_sat(x0.z, x0.w),
+                                                 pack_f16x2_sat(x1.x, x1.y), pack_f16x2_sat(x1.z, x1.w));
           }
         }
       }
@@ -345,12 +413,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
 static int g_num_sms = 0;
 
-template <int BN, int STAGES, int CL>
-static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
+static int ensure_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    MTN_CHECK_CUDA(cudaGetDevice(&dev));
+    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = n;
+  }
+  return MTN_OK;
+}
+
+// Tensor map of one operand.  K-major: dims {K, MN, batch}, box {64, box_mn}.  MN-major: dims {MN, K, batch},
+// box {64 mn-columns, 64 k-rows} (the kernel issues box_mn / 64 of them per k-block).
+static int make_operand_map(CUtensorMap* tm, const void* p, int mn_major, int MN, int K, int ld, int batch,
+                            long long stride, int box_mn) {
+  if (mn_major)
+    return make_tmap_3d_f16(tm, p, MN, K, batch, ld, batch > 1 ? (uint64_t)stride : (uint64_t)K * ld, 64, BK, TM_SWZ_128);
+  return make_tmap_3d_f16(tm, p, K, MN, batch, ld, batch > 1 ? (uint64_t)stride : (uint64_t)MN * ld, BK, box_mn, TM_SWZ_128);
+}
+
+template <int BN, int STAGES, int CL, int A_MN, int B_MN>
+static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   static int max_clusters = 0;  // co-resident clusters (1 CTA per SM)
   if (max_clusters == 0) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL>,
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     if (CL == 1) {
       max_clusters = g_num_sms;
@@ -364,94 +451,90 @@ static int launch_gemm(const MtnLinearArgs& a, cudaStream_t st) {
       attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       int n = 0;
-      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL>, &cfg));
-      MTN_REQUIRE(n > 0, MTN_E_CUDA, "linear: no cluster of %d CTAs fits on this device", CL);
+      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN>, &cfg));
+      MTN_REQUIRE(n > 0, MTN_E_CUDA, "gemm: no cluster of %d CTAs fits on this device", CL);
       max_clusters = n;
     }
   }
   const int batch = a.batch > 1 ? a.batch : 1;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_3d_f16(&tmA, a.A, a.K, a.M, batch, a.lda, batch > 1 ? (uint64_t)a.stride_A : (uint64_t)a.M * a.lda, BK,
-                            BM, TM_SWZ_128);
+  int rc = make_operand_map(&tmA, a.A, A_MN, a.M, a.K, a.lda, batch, a.stride_A, BM);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tmB, a.W, a.K, a.N, batch, a.ldw, batch > 1 ? (uint64_t)a.stride_W : (uint64_t)a.N * a.ldw, BK,
-                        BN / CL, TM_SWZ_128);
+  rc = make_operand_map(&tmB, a.B, B_MN, a.N, a.K, a.ldb, batch, a.stride_B, BN / CL);
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
-              reinterpret_cast<__half*>(a.out_f16), a.ld16, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
+              reinterpret_cast<__half*>(a.out_f16), a.ld16, a.alpha, reinterpret_cast<const __half*>(a.relu_mask),
+              a.ld_mask, a.accumulate, a.out16_pre_add,
+              a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
-  const int tiles_per_batch = tiles_n * ((tiles_m + CL - 1) / CL);
+  const int tiles_mn = tiles_n * ((tiles_m + CL - 1) / CL);
+  // split-K (accumulating outputs only): cut the contraction so that the launch fills the machine about twice
+  const int nkb = (a.K + BK - 1) / BK;
+  int kb_per_split = nkb;
+  if (a.accumulate) {
+    const long want = (2L * max_clusters + (long)tiles_mn * batch - 1) / ((long)tiles_mn * batch);  // slices wanted
+    long per = (nkb + want - 1) / (want > 0 ? want : 1);
+    if (per < 4) per = nkb < 4 ? nkb : 4;  // at least 4 k-blocks (256 contraction rows) per slice
+    kb_per_split = (int)per;
+  }
+  const int ksplit = (nkb + kb_per_split - 1) / kb_per_split;
+  const int tiles_per_batch = tiles_mn * ksplit;
   const int num_super = tiles_per_batch * batch;
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
-  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL>, dim3(clusters * CL), dim3(GEMM_THREADS),
-                                       L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K, tiles_n, tiles_per_batch, num_super));
+  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN>, dim3(clusters * CL),
+                                       dim3(GEMM_THREADS), L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K,
+                                       tiles_n, tiles_per_batch, num_super, tiles_mn, kb_per_split));
   return MTN_OK;
 }
 
-static int validate_linear(const MtnLinearArgs* a) {
-  MTN_REQUIRE(a != nullptr && a->A != nullptr && a->W != nullptr, MTN_E_ARG, "linear: NULL operand");
-  MTN_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, MTN_E_SHAPE, "linear: M=%d N=%d K=%d", a->M, a->N, a->K);
-  MTN_REQUIRE(a->K % 8 == 0, MTN_E_SHAPE, "linear: K=%d must be a multiple of 8", a->K);
-  MTN_REQUIRE(a->N % 8 == 0, MTN_E_SHAPE, "linear: N=%d must be a multiple of 8", a->N);
-  MTN_REQUIRE(a->lda >= a->K && a->ldw >= a->K && a->lda % 8 == 0 && a->ldw % 8 == 0, MTN_E_ALIGN,
-              "linear: lda=%d ldw=%d must be >= K and multiples of 8", a->lda, a->ldw);
-  MTN_REQUIRE(aligned16(a->A) && aligned16(a->W), MTN_E_ALIGN, "linear: A/W not 16-byte aligned");
-  MTN_REQUIRE(a->out_f32 != nullptr || a->out_f16 != nullptr, MTN_E_ARG, "linear: no output");
-  MTN_REQUIRE(a->act == MTN_ACT_NONE || a->act == MTN_ACT_RELU, MTN_E_ARG, "linear: act=%d", a->act);
+static int validate_gemm(const MtnGemmArgs* a) {
+  MTN_REQUIRE(a != nullptr && a->A != nullptr && a->B != nullptr, MTN_E_ARG, "gemm: NULL operand");
+  MTN_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, MTN_E_SHAPE, "gemm: M=%d N=%d K=%d", a->M, a->N, a->K);
+  MTN_REQUIRE(a->N % 8 == 0, MTN_E_SHAPE, "gemm: N=%d must be a multiple of 8", a->N);
+  // 16-byte aligned rows of every operand: the contiguous extent must be a multiple of 8 elements
+  MTN_REQUIRE((a->a_mn ? a->M : a->K) % 8 == 0, MTN_E_SHAPE, "gemm: contiguous extent of A (%s=%d) must be a multiple of 8",
+              a->a_mn ? "M" : "K", a->a_mn ? a->M : a->K);
+  MTN_REQUIRE(a->b_mn || a->K % 8 == 0, MTN_E_SHAPE, "gemm: K=%d must be a multiple of 8", a->K);
+  MTN_REQUIRE(a->lda >= (a->a_mn ? a->M : a->K) && a->ldb >= (a->b_mn ? a->N : a->K) && a->lda % 8 == 0 &&
+                  a->ldb % 8 == 0,
+              MTN_E_ALIGN, "gemm: lda=%d ldb=%d must cover the contiguous extent and be multiples of 8", a->lda, a->ldb);
+  MTN_REQUIRE(aligned16(a->A) && aligned16(a->B), MTN_E_ALIGN, "gemm: A/B not 16-byte aligned");
+  MTN_REQUIRE(a->out_f32 != nullptr || a->out_f16 != nullptr, MTN_E_ARG, "gemm: no output");
+  MTN_REQUIRE(a->act == MTN_ACT_NONE || a->act == MTN_ACT_RELU, MTN_E_ARG, "gemm: act=%d", a->act);
   if (a->out_f32)
     MTN_REQUIRE(aligned16(a->out_f32) && a->ld32 % 4 == 0 && a->ld32 >= a->N, MTN_E_ALIGN,
-                "linear: out_f32 alignment / ld32=%d", a->ld32);
+                "gemm: out_f32 alignment / ld32=%d", a->ld32);
   if (a->out_f16)
     MTN_REQUIRE(aligned16(a->out_f16) && a->ld16 % 8 == 0 && a->ld16 >= a->N, MTN_E_ALIGN,
-                "linear: out_f16 alignment / ld16=%d", a->ld16);
+                "gemm: out_f16 alignment / ld16=%d", a->ld16);
   if (a->addend)
     MTN_REQUIRE(aligned16(a->addend) && a->ld_add % 4 == 0 && a->ld_add >= a->N && a->add_period >= 0,
-                MTN_E_ALIGN, "linear: addend alignment / ld_add=%d", a->ld_add);
-  if (a->bias) MTN_REQUIRE(aligned16(a->bias), MTN_E_ALIGN, "linear: bias not 16-byte aligned");
+                MTN_E_ALIGN, "gemm: addend alignment / ld_add=%d", a->ld_add);
+  if (a->bias) MTN_REQUIRE(aligned16(a->bias), MTN_E_ALIGN, "gemm: bias not 16-byte aligned");
+  if (a->relu_mask)
+    MTN_REQUIRE(aligned16(a->relu_mask) && a->ld_mask % 8 == 0 && a->ld_mask >= a->N, MTN_E_ALIGN,
+                "gemm: relu_mask alignment / ld_mask=%d", a->ld_mask);
+  if (a->accumulate)
+    MTN_REQUIRE(a->out_f32 != nullptr && a->out_f16 == nullptr && a->bias == nullptr && a->addend == nullptr &&
+                    a->act == MTN_ACT_NONE && a->relu_mask == nullptr,
+                MTN_E_ARG, "gemm: accumulate takes only alpha and out_f32");
   if (a->batch > 1) {
-    MTN_REQUIRE(a->stride_A % 8 == 0 && a->stride_W % 8 == 0 && a->stride_A > 0 && a->stride_W > 0 &&
+    MTN_REQUIRE(a->stride_A % 8 == 0 && a->stride_B % 8 == 0 && a->stride_A > 0 && a->stride_B > 0 &&
                     a->stride_bias % 4 == 0 && a->stride_add % 4 == 0 && a->stride_out_f32 % 4 == 0 &&
                     a->stride_out_f16 % 8 == 0,
-                MTN_E_ALIGN, "linear: batch strides must keep every problem 16-byte aligned");
-    MTN_REQUIRE(a->batch <= 65535, MTN_E_SHAPE, "linear: batch=%d", a->batch);
+                MTN_E_ALIGN, "gemm: batch strides must keep every problem 16-byte aligned");
+    MTN_REQUIRE(a->batch <= 65535, MTN_E_SHAPE, "gemm: batch=%d", a->batch);
+    MTN_REQUIRE(a->relu_mask == nullptr, MTN_E_ARG, "gemm: relu_mask is not batched");
   }
   return MTN_OK;
 }
 
-// ----------------------------------------------------------------------------
-// self-check kernel (tests only): one thread per output element, same arithmetic
-// contract (f16 operands, f32 accumulate, same epilogue order).
-// ----------------------------------------------------------------------------
-__global__ void gemm_f16_check_kernel(const __half* A, int lda, const __half* W, int ldw, GemmEpi epi,
-                                      int M, int N, int K) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = blockIdx.y;
-  if (n >= N || m >= M) return;
-  float acc = 0.f;
-  for (int k = 0; k < K; ++k)
-    acc = fmaf(__half2float(A[(size_t)m * lda + k]), __half2float(W[(size_t)n * ldw + k]), acc);
-  if (epi.bias) acc += epi.bias[n];
-  if (epi.act == MTN_ACT_RELU) acc = fmaxf(acc, 0.f);
-  if (epi.addend) acc += epi.addend[(size_t)(epi.add_period > 0 ? m % epi.add_period : m) * epi.ld_add + n];
-  if (epi.out32) epi.out32[(size_t)m * epi.ld32 + n] = acc;
-  if (epi.out16) {
-    const uint32_t p = pack_f16x2_sat(acc, 0.f);
-    epi.out16[(size_t)m * epi.ld16 + n] = __ushort_as_half((unsigned short)(p & 0xffff));
-  }
-}
-
-}  // namespace mtn
-
-extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
-  int rc = mtn::validate_linear(a);
+static int run_gemm(const MtnGemmArgs* a, void* stream) {
+  int rc = validate_gemm(a);
+  if (rc) return rc;
+  rc = ensure_sms();
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mtn::g_num_sms == 0) {
-    int dev = 0, n = 0;
-    MTN_CHECK_CUDA(cudaGetDevice(&dev));
-    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    mtn::g_num_sms = n;
-  }
   // 128x256 tiles halve the operand bytes per FLOP; use them when they still fill the machine.
   // Wide GEMMs with many waves additionally run as clusters of 2 CTAs along M that share each W tile
   // through TMA multicast (measured +3 %; on the small single-wave GEMMs clusters only constrain
@@ -468,21 +551,127 @@ extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
     const char* e = getenv("MTN_B200_BIG_PCT");
     big_pct = e ? atoi(e) : 40;
   }
-  const bool big = a->N >= 256 && tiles256 * 100 >= (long)big_pct * mtn::g_num_sms;
-  if (cl >= 2 && big && tiles256 >= 4L * mtn::g_num_sms) return mtn::launch_gemm<256, 4, 2>(*a, st);
-  return big ? mtn::launch_gemm<256, 4, 1>(*a, st) : mtn::launch_gemm<128, 6, 1>(*a, st);
+  // split-K launches fill the machine through their slices: always the wide tile when N allows
+  const bool big = a->N >= 256 && (a->accumulate || tiles256 * 100 >= (long)big_pct * g_num_sms);
+  const int form = (a->a_mn ? 2 : 0) | (a->b_mn ? 1 : 0);
+  switch (form) {
+    case 0:
+      if (cl >= 2 && big && !a->accumulate && tiles256 >= 4L * g_num_sms) return launch_gemm<256, 4, 2, 0, 0>(*a, st);
+      return big ? launch_gemm<256, 4, 1, 0, 0>(*a, st) : launch_gemm<128, 6, 1, 0, 0>(*a, st);
+    case 1:
+      return big ? launch_gemm<256, 4, 1, 0, 1>(*a, st) : launch_gemm<128, 6, 1, 0, 1>(*a, st);
+    case 3:
+      return big ? launch_gemm<256, 4, 1, 1, 1>(*a, st) : launch_gemm<128, 6, 1, 1, 1>(*a, st);
+    default:
+      return set_error(MTN_E_ARG, "gemm: the (A MN-major, B K-major) form is not instantiated");
+  }
+}
+
+static MtnGemmArgs from_linear(const MtnLinearArgs& a) {
+  MtnGemmArgs g = {};
+  g.A = a.A; g.lda = a.lda; g.B = a.W; g.ldb = a.ldw;
+  g.M = a.M; g.N = a.N; g.K = a.K;
+  g.bias = a.bias; g.act = a.act;
+  g.addend = a.addend; g.ld_add = a.ld_add; g.add_period = a.add_period;
+  g.out_f32 = a.out_f32; g.ld32 = a.ld32; g.out_f16 = a.out_f16; g.ld16 = a.ld16;
+  g.out16_pre_add = a.out16_pre_add;
+  g.batch = a.batch; g.stride_A = a.stride_A; g.stride_B = a.stride_W; g.stride_bias = a.stride_bias;
+  g.stride_add = a.stride_add; g.stride_out_f32 = a.stride_out_f32; g.stride_out_f16 = a.stride_out_f16;
+  return g;
+}
+
+// ----------------------------------------------------------------------------
+// self-check kernel (tests only): one thread per output element, same arithmetic
+// contract (f16 operands, f32 accumulate, same epilogue order).
+// ----------------------------------------------------------------------------
+__global__ void gemm_f16_check_kernel(const __half* A, int lda, int a_mn, const __half* B, int ldb, int b_mn,
+                                      GemmEpi epi, int M, int N, int K) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float av = __half2float(a_mn ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]);
+    const float bv = __half2float(b_mn ? B[(size_t)k * ldb + n] : B[(size_t)n * ldb + k]);
+    acc = fmaf(av, bv, acc);
+  }
+  if (epi.alpha) acc *= epi.alpha[0];
+  if (epi.bias) acc += epi.bias[n];
+  if (epi.act == MTN_ACT_RELU) acc = fmaxf(acc, 0.f);
+  if (epi.relu_mask && !(__half2float(epi.relu_mask[(size_t)m * epi.ld_mask + n]) > 0.f)) acc = 0.f;
+  const float pre = acc;
+  if (epi.addend && !epi.accumulate)
+    acc += epi.addend[(size_t)(epi.add_period > 0 ? m % epi.add_period : m) * epi.ld_add + n];
+  if (epi.out32) {
+    if (epi.accumulate) epi.out32[(size_t)m * epi.ld32 + n] += acc;
+    else epi.out32[(size_t)m * epi.ld32 + n] = acc;
+  }
+  if (epi.out16) {
+    const uint32_t p = pack_f16x2_sat(epi.out16_pre_add ? pre : acc, 0.f);
+    epi.out16[(size_t)m * epi.ld16 + n] = __ushort_as_half((unsigned short)(p & 0xffff));
+  }
+}
+
+static int run_check_gemm(const MtnGemmArgs* a, void* stream) {
+  int rc = validate_gemm(a);
+  if (rc) return rc;
+  GemmEpi epi{a->bias, a->act, a->addend, a->ld_add, a->add_period, a->out_f32, a->ld32,
+              reinterpret_cast<__half*>(a->out_f16), a->ld16, a->alpha, reinterpret_cast<const __half*>(a->relu_mask),
+              a->ld_mask, a->accumulate, a->out16_pre_add, 0, 0, 0, 0};
+  MTN_REQUIRE(a->batch <= 1, MTN_E_ARG, "check_gemm: the check kernel is not batched");
+  dim3 grid((a->N + 127) / 128, a->M);
+  gemm_f16_check_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(a->A), a->lda, a->a_mn, reinterpret_cast<const __half*>(a->B), a->ldb, a->b_mn,
+      epi, a->M, a->N, a->K);
+  MTN_CHECK_CUDA(cudaGetLastError());
+  return MTN_OK;
+}
+
+}  // namespace mtn
+
+extern "C" int mtn_gemm_f16(const MtnGemmArgs* a, void* stream) { return mtn::run_gemm(a, stream); }
+extern "C" int mtn_check_gemm_f16(const MtnGemmArgs* a, void* stream) { return mtn::run_check_gemm(a, stream); }
+
+extern "C" int mtn_linear_fwd(const MtnLinearArgs* a, void* stream) {
+  MTN_REQUIRE(a != nullptr, MTN_E_ARG, "linear: NULL args");
+  const MtnGemmArgs g = mtn::from_linear(*a);
+  return mtn::run_gemm(&g, stream);
 }
 
 extern "C" int mtn_check_linear_fwd(const MtnLinearArgs* a, void* stream) {
-  int rc = mtn::validate_linear(a);
-  if (rc) return rc;
-  mtn::GemmEpi epi{a->bias, a->act, a->addend, a->ld_add, a->add_period, a->out_f32, a->ld32,
-                   reinterpret_cast<__half*>(a->out_f16), a->ld16, 0, 0, 0, 0};
-  MTN_REQUIRE(a->batch <= 1, MTN_E_ARG, "check_linear: the check kernel is not batched");
-  dim3 grid((a->N + 127) / 128, a->M);
-  mtn::gemm_f16_check_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(a->A), a->lda, reinterpret_cast<const __half*>(a->W), a->ldw, epi,
-      a->M, a->N, a->K);
-  MTN_CHECK_CUDA(cudaGetLastError());
-  return MTN_OK;
+  MTN_REQUIRE(a != nullptr, MTN_E_ARG, "linear: NULL args");
+  const MtnGemmArgs g = mtn::from_linear(*a);
+  return mtn::run_check_gemm(&g, stream);
+}
+
+// dX[M, K] = alpha * (dY[M, N] W[N, K])  (optionally masked by the forward ReLU output): the contraction runs
+// over the layer's OUTPUT features, W is read in its forward [out, in] layout as an MN-major operand.
+extern "C" int mtn_linear_dgrad(const MtnLinearDgradArgs* a, void* stream) {
+  MTN_REQUIRE(a != nullptr, MTN_E_ARG, "linear_dgrad: NULL args");
+  MtnGemmArgs g = {};
+  g.A = a->dY; g.lda = a->lddy; g.a_mn = 0;
+  g.B = a->W; g.ldb = a->ldw; g.b_mn = 1;
+  g.M = a->M; g.N = a->K; g.K = a->N;
+  g.alpha = a->alpha;
+  g.relu_mask = a->relu_mask; g.ld_mask = a->ld_mask;
+  g.addend = a->addend; g.ld_add = a->ld_add;
+  g.out_f32 = a->dX_f32; g.ld32 = a->ld32; g.out_f16 = a->dX_f16; g.ld16 = a->ld16;
+  g.batch = a->batch; g.stride_A = a->stride_dY; g.stride_B = a->stride_W;
+  g.stride_add = a->stride_add; g.stride_out_f32 = a->stride_dX_f32; g.stride_out_f16 = a->stride_dX_f16;
+  return mtn::run_gemm(&g, stream);
+}
+
+// dW[N, K] += alpha * (dY[M, N]^T X[M, K]): both operands MN-major (forward layouts), contraction over the
+// M rows, split-K with red.global.add accumulation into the f32 gradient.
+extern "C" int mtn_linear_wgrad(const MtnLinearWgradArgs* a, void* stream) {
+  MTN_REQUIRE(a != nullptr, MTN_E_ARG, "linear_wgrad: NULL args");
+  MtnGemmArgs g = {};
+  g.A = a->dY; g.lda = a->lddy; g.a_mn = 1;
+  g.B = a->X; g.ldb = a->ldx; g.b_mn = 1;
+  g.M = a->N; g.N = a->K; g.K = a->M;
+  g.alpha = a->alpha;
+  g.accumulate = 1;
+  g.out_f32 = a->dW; g.ld32 = a->lddw;
+  g.batch = a->batch; g.stride_A = a->stride_dY; g.stride_B = a->stride_X; g.stride_out_f32 = a->stride_dW;
+  return mtn::run_gemm(&g, stream);
 }

@@ -71,29 +71,63 @@ class Batch:
         return (tgt != pad).unsqueeze(-2) & subsequent_mask(tgt.size(-1), tgt.device)
 
 
+class NoamOpt:
+    """Learning-rate schedule wrapper of the reference (data_utils.py:92-117; train.py:190-191 builds it around
+    torch.optim.Adam): rate = factor * d_model^-0.5 * min(step^-0.5, step * warmup^-1.5).  Host logic only."""
+
+    def __init__(self, model_size, factor, warmup, optimizer):
+        self.optimizer = optimizer
+        self._step = 0
+        self.warmup = warmup
+        self.factor = factor
+        self.model_size = model_size
+        self._rate = 0
+
+    def step(self):
+        self._step += 1
+        rate = self.rate()
+        for p in self.optimizer.param_groups:
+            p['lr'] = rate
+        self._rate = rate
+        self.optimizer.step()
+
+    def rate(self, step=None):
+        if step is None:
+            step = self._step
+        return self.factor * (self.model_size ** (-0.5) * min(step ** (-0.5), step * self.warmup ** (-1.5)))
+
+
 class SimpleLossCompute:
-    """Evaluation half of the reference's SimpleLossCompute (data_utils.py:123-156): main loss / norm plus
+    """The reference's SimpleLossCompute (data_utils.py:123-156): main loss / norm plus
     l * sum_i auto-encoder loss_i / ae_norm (every stream through ``generator`` unless ``ae_generator`` is
-    given), returned as ``loss * norm`` like the reference.  The generator's logits feed the fused
-    label-smoothing kernel directly.  Training (``opt`` given) needs the backward kernels: not implemented."""
+    given); with ``opt`` it also runs ``loss.backward()``, ``opt.step()`` and ``opt.optimizer.zero_grad()``
+    (data_utils.py:152-155).  Returns ``loss * norm`` like the reference.  The generator's logits feed the
+    fused label-smoothing kernel directly (no (rows, vocab) log-prob tensor, no dense target distribution);
+    in training the same two steps are autograd Functions backed by the backward kernels."""
 
     def __init__(self, generator, ae_generator, criterion, opt=None, l=1.0):
-        if opt is not None:
-            raise NotImplementedError("mtn_b200: training (loss.backward / optimizer step) is not implemented "
-                                      "in this round; use opt=None for evaluation (train.py:204-209)")
         self.generator, self.ae_generator, self.criterion, self.opt, self.l = generator, ae_generator, criterion, opt, l
 
-    def __call__(self, x, y, norm, ae_x=None, ae_y=None, ae_norm=None):
-        total = torch.zeros(1, dtype=torch.float32, device=x.device)
+    def loss(self, x, y, norm, ae_x=None, ae_y=None, ae_norm=None):
+        """The normalised loss as a 0-d tensor (differentiable when autograd is recording); no host sync when
+        ``norm`` / ``ae_norm`` are Python numbers."""
         logits, V = self.generator._logits(x)
-        self.criterion.from_logits(logits, V, y, scale=1.0 / float(norm), out=total)
+        total = self.criterion.from_logits(logits, V, y, scale=1.0 / float(norm))
         if ae_x is not None:
             streams = ae_x if isinstance(ae_x, (list, tuple)) else [ae_x]
             for i, ae_in in enumerate(streams):
                 gen = self.generator if self.ae_generator is None else (
                     self.ae_generator[i] if isinstance(ae_x, (list, tuple)) else self.ae_generator)
                 lg, Vg = gen._logits(ae_in)
-                self.criterion.from_logits(lg, Vg, ae_y, scale=self.l / float(ae_norm), out=total, accumulate=True)
+                total = total + self.criterion.from_logits(lg, Vg, ae_y, scale=self.l / float(ae_norm))
+        return total
+
+    def __call__(self, x, y, norm, ae_x=None, ae_y=None, ae_norm=None):
+        total = self.loss(x, y, norm, ae_x, ae_y, ae_norm)
+        if self.opt is not None:
+            total.backward()
+            self.opt.step()
+            self.opt.optimizer.zero_grad()
         return total.item() * float(norm)
 
 

@@ -27,6 +27,13 @@ class LabelSmoothing(nn.Module):
 
     def from_logits(self, logits, V, target, scale=1.0, out=None, accumulate=False):
         """logits: [rows, ld >= V] (raw generator logits or log-probs -- the loss formula is the same)."""
+        if torch.is_grad_enabled() and logits.requires_grad:      # training: criterion + its backward kernel
+            from . import autograd as AG
+            z = logits.float() if logits.dtype != torch.float32 else logits
+            val = AG.LabelSmoothingFn.apply(z, target, V, self.padding_idx, self.smoothing, float(scale))
+            if out is None:
+                return val
+            return out + val if accumulate else val
         ensure_inference(None, logits)
         loss = out if out is not None else torch.zeros(1, dtype=torch.float32, device=logits.device)
         _lib.label_smoothing_loss(logits.float() if logits.dtype != torch.float32 else logits, V,

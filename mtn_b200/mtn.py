@@ -27,7 +27,9 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import autograd as AG
 from .engine import DecoderEngine, PackedWeights, ensure_inference
+from .train_engine import DecoderTrainer
 
 
 def clones(module, N):
@@ -48,6 +50,10 @@ class LayerNorm(nn.Module):
         self.eps = eps
 
     def forward(self, x):
+        if AG.recording(self, x):            # training: mtn_layernorm_fwd + mtn_layernorm_bwd
+            if not x.is_cuda:
+                raise _lib.MtnError("mtn_b200 hot path needs CUDA tensors (no CPU implementation)")
+            return AG.LayerNormFn.apply(x, self.a_2, self.b_2, self.eps)
         ensure_inference(self, x)
         xc = x.contiguous().float()
         y = torch.empty_like(xc)
@@ -304,6 +310,7 @@ class Decoder(nn.Module):
         for ft_size in ft_sizes:
             self.ae_norm.append(LayerNorm(layer.size))
         self._engine = None
+        self._trainer = None
 
     @property
     def engine(self):
@@ -311,13 +318,33 @@ class Decoder(nn.Module):
             self._engine = DecoderEngine(self)
         return self._engine
 
+    @property
+    def trainer(self):
+        if getattr(self, "_trainer", None) is None:
+            self._trainer = DecoderTrainer(self)
+        return self._trainer
+
     def __getstate__(self):          # torch.save(model) (train.py:217): engines are rebuilt lazily
         st = self.__dict__.copy()
         st["_engine"] = None
+        st["_trainer"] = None
         return st
 
     def forward(self, vid_ft, vid_mask, x, his_memory, his_mask, cap_memory, cap_mask, query_memory,
                 query_mask, tgt_mask, auto_encoded_ft, auto_encoded_features):
+        ae_in = list(auto_encoded_ft) if isinstance(auto_encoded_ft, (list, tuple)) else \
+            ([auto_encoded_ft] if auto_encoded_ft is not None else [])
+        if AG.recording(self, x, his_memory, cap_memory, query_memory, *(list(vid_ft) + ae_in)):
+            # training (train.py:33): one autograd.Function for the whole cascade, hand-written backward
+            if not x.is_cuda:
+                raise _lib.MtnError("mtn_b200 hot path needs CUDA tensors (no CPU implementation)")
+            AG.require_no_dropout(self)
+            meta = {"vid_mask": list(vid_mask), "his_mask": his_mask, "cap_mask": cap_mask, "q_mask": query_mask,
+                    "tgt_mask": tgt_mask, "ae_features": auto_encoded_features,
+                    "ae_list": isinstance(auto_encoded_ft, (list, tuple))}
+            res = AG.DecoderFn.apply(self.trainer, meta, len(vid_ft), len(ae_in), x, his_memory, cap_memory,
+                                     query_memory, *(list(vid_ft) + ae_in + self.trainer.param_list()))
+            return res[0], list(res[1:])
         ensure_inference(self, x)
         return self.engine.forward(vid_ft, vid_mask, x, his_memory, his_mask, cap_memory, cap_mask,
                                    query_memory, query_mask, tgt_mask, auto_encoded_ft,
@@ -362,7 +389,7 @@ class Generator(nn.Module):
         self.proj = nn.Linear(d_model, vocab)
         self._packed = PackedWeights()
 
-    def _logits(self, x):
+    def _logits(self, x, log_probs=False):
         V, d = self.proj.weight.shape
         V8 = (V + 7) // 8 * 8
 
@@ -373,12 +400,17 @@ class Generator(nn.Module):
             b[:V] = self.proj.bias.data
             return {"w": _lib.cast_f16(w), "b": b}
         W = self._packed.get(list(self.proj.parameters()), build)
+        if AG.recording(self, x):       # training: projection (+ log-softmax) with its backward kernels
+            return AG.ProjectFn.apply(x, self.proj.weight, self.proj.bias, W["w"], W["b"], V, log_probs), V
         x16 = _lib.cast_f16(x.contiguous().float().view(-1, d))
         logits = torch.empty(x16.shape[0], V8, dtype=torch.float32, device=x.device)
         _lib.linear(x16, W["w"], W["b"], out_f32=logits)
         return logits, V
 
     def forward(self, x):
+        if AG.recording(self, x):
+            y, V = self._logits(x, log_probs=True)
+            return y.view(*x.shape[:-1], V)
         ensure_inference(self, x)
         logits, V = self._logits(x)
         out = torch.empty(logits.shape[0], V, dtype=torch.float32, device=x.device)
@@ -434,7 +466,6 @@ class VideoEncoder(nn.Sequential):
         self._packed = PackedWeights()
 
     def forward(self, ft):
-        ensure_inference(self, ft)
         lin, pos = self[0], self[2]
         B, Lv, Fdim = ft.shape
         W = self._packed.get(list(lin.parameters()),
@@ -442,7 +473,12 @@ class VideoEncoder(nn.Sequential):
         if ft.dtype == torch.float16:      # Batch already produced the masked f16 operand (feature_prep kernel)
             x16 = ft.contiguous().view(B * Lv, Fdim)
         else:
-            x16 = _lib.cast_f16(ft.contiguous().float().view(B * Lv, Fdim))
+            x16 = _lib.cast_f16(ft.detach().contiguous().float().view(B * Lv, Fdim))
+        if AG.recording(self):             # training: the features are data, only W / b receive gradients
+            AG.require_no_dropout(self)
+            out = AG.VideoEncoderFn.apply(x16, lin.weight, lin.bias, W["w"], pos.pe[0, :Lv], Lv)
+            return out.view(B, Lv, -1)
+        ensure_inference(self, ft)
         out = torch.empty(B * Lv, lin.out_features, dtype=torch.float32, device=ft.device)
         _lib.linear(x16, W["w"], W["b"], act=_lib.ACT_RELU, addend=pos.pe[0, :Lv], add_period=Lv,
                     out_f32=out)
@@ -484,6 +520,11 @@ class EncoderDecoder(nn.Module):
         """``seq`` = nn.Sequential(Embeddings, PositionalEncoding) applied to ids, optionally followed by
         the Encoder's stream LayerNorm ``norm`` -- one fused kernel."""
         emb, pos = seq[0], seq[1]
+        if AG.recording(seq) or (norm is not None and AG.recording(norm)):
+            AG.require_no_dropout(seq)
+            return AG.EmbedFn.apply(ids, emb.lut.weight, pos.pe[0], math.sqrt(emb.d_model),
+                                    None if norm is None else norm.a_2, None if norm is None else norm.b_2,
+                                    0.0 if norm is None else norm.eps)
         ensure_inference(self, emb.lut.weight.data)
         B, L = ids.shape
         out = torch.empty(B, L, emb.d_model, dtype=torch.float32, device=ids.device)

@@ -1,0 +1,441 @@
+"""Training execution of the MTN decoder cascade: forward with a tape, hand-written backward.
+
+``DecoderTrainer.apply`` is what ``mtn.Decoder.forward`` (reference mtn.py:158-164) runs when autograd is
+recording.  The whole N-layer cascade (reference mtn.py:181-218 per layer) is ONE ``torch.autograd.Function``:
+its forward launches the same sm_100a kernels as the inference engine and keeps, per SublayerConnection, the
+f32 residual input, the f16 LayerNorm output, the f16 Q/K/V and attention outputs and the softmax statistics;
+its backward walks that tape in reverse and launches the backward kernels of ``include/mtn_b200.h`` (ABI v3):
+
+  out-projection / w_2 : dY -> f16 (+ bias gradient, one pass)  ->  dgrad GEMM, split-K wgrad GEMM
+  attention core       : delta = rowsum(dO * O);  tcgen05 backward kernel (dQ f32 accumulate, dK / dV f16)
+  Q / QKV / w_1        : dgrad + wgrad GEMMs (ReLU mask in the dgrad epilogue)
+  LayerNorm            : row kernel, residual-stream gradient updated in place
+  hoisted memory K/V   : every layer writes its dK / dV columns into ONE [rows, N*2d] buffer per memory;
+                         one wide dgrad + one wgrad per memory at the end.
+
+All intermediate gradients are multiplied by a power of two S chosen on the device from the incoming gradient
+(``_lib.grad_scale``) so that the f16 tensor-core operands do not underflow; every result leaving the Function
+(parameter and input gradients) is multiplied by 1/S in the kernel that produces it.  No host synchronisation,
+so forward + backward can be captured in a CUDA graph.
+
+PyTorch autograd only connects this Function with the embedding / encoder / generator Functions around it
+(``mtn_b200/autograd.py``); no arithmetic of the path runs in PyTorch.
+"""
+import torch
+
+from . import _lib
+from .engine import PackedWeights
+
+
+class _Arena(object):
+    """One flat f32 buffer (a single memset) carved into gradient views."""
+
+    def __init__(self, n, device):
+        self.buf = torch.zeros(n, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for s in shape:
+            n *= s
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 3) // 4 * 4
+        return v
+
+
+class DecoderTrainer(object):
+    def __init__(self, decoder):
+        self.dec = decoder
+        self._packed = PackedWeights()
+
+    # ------------------------------------------------------------------ parameters
+    def param_list(self):
+        return list(self.dec.parameters())
+
+    def weights(self):
+        """Tensor-core (f16) packs of the decoder's parameters, rebuilt when a parameter changes."""
+        return self.dec.engine.weights()
+
+    # ------------------------------------------------------------------ forward building blocks (taped)
+    @staticmethod
+    def _attn_fwd(tape, x_in, ln, A, B, Lq, Lk, kv, k_col, v_col, bits, names):
+        """One pre-norm residual attention site (mtn.py:125-127 around :248-267).  kv=None: self-attention."""
+        rows, d = x_in.shape
+        dev = x_in.device
+        f16 = torch.float16
+        xn16 = torch.empty(rows, d, dtype=f16, device=dev)
+        _lib.layernorm(x_in, ln[0], ln[1], ln[2], out_f16=xn16)
+        if kv is None:
+            qbuf = torch.empty(rows, 3 * d, dtype=f16, device=dev)
+            _lib.linear(xn16, A["w_qkv"], A["b_qkv"], out_f16=qbuf)
+            q, k, v = qbuf[:, :d], qbuf[:, d:2 * d], qbuf[:, 2 * d:]
+        else:
+            qbuf = torch.empty(rows, d, dtype=f16, device=dev)
+            _lib.linear(xn16, A["w_qkv"][:d], A["b_qkv"][:d], out_f16=qbuf)
+            q, k, v = qbuf, kv[:, k_col:k_col + d], kv[:, v_col:v_col + d]
+        o16 = torch.empty(rows, d, dtype=f16, device=dev)
+        stats = torch.empty(B, A["h"], Lq, 2, dtype=torch.float32, device=dev)
+        _lib.attn_core(q, k, v, B, A["h"], Lq, Lk, A["d_k"], o16, mask_bits=bits, stats=stats)
+        x_out = torch.empty_like(x_in)
+        _lib.linear(o16, A["w_o"], A["b_o"], addend=x_in, out_f32=x_out)
+        tape.append(("attn", dict(x_in=x_in, ln=ln, A=A, B=B, Lq=Lq, Lk=Lk, self_attn=kv is None, xn16=xn16, q=q, k=k,
+                                  v=v, o16=o16, stats=stats, bits=bits, names=names)))
+        return x_out
+
+    @staticmethod
+    def _ffn_fwd(tape, x_in, ln, Fw, names, want16=False):
+        rows, d = x_in.shape
+        dev = x_in.device
+        f16 = torch.float16
+        xn16 = torch.empty(rows, d, dtype=f16, device=dev)
+        _lib.layernorm(x_in, ln[0], ln[1], ln[2], out_f16=xn16)
+        hid = torch.empty(rows, Fw["w_1"].shape[0], dtype=f16, device=dev)
+        _lib.linear(xn16, Fw["w_1"], Fw["b_1"], act=_lib.ACT_RELU, out_f16=hid)
+        x_out = torch.empty_like(x_in)
+        out16 = torch.empty(rows, d, dtype=f16, device=dev) if want16 else None
+        _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x_in, out_f32=x_out, out_f16=out16)
+        tape.append(("ffn", dict(x_in=x_in, ln=ln, Fw=Fw, xn16=xn16, hid=hid, names=names)))
+        return x_out, out16
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, vid_ft, vid_mask, x, his, his_mask, cap, cap_mask, qm, q_mask, tgt_mask, ae_ft, ae_features):
+        """Returns (out [B,T,d], [ae_out_i [B,La,d]], ctx) with ctx the tape for ``backward``."""
+        W = self.weights()
+        d, N, M = W["d"], W["N"], W["M"]
+        B, T, _ = x.shape
+        dev = x.device
+        f16 = torch.float16
+        if ae_features in ("caption", "summary"):
+            ae_default = cap
+        elif ae_features == "query":
+            ae_default = qm
+        else:
+            raise ValueError("auto_encoder_ft must be 'query', 'caption' or 'summary' "
+                             "(reference mtn.py:187-202 leaves ae_mask unbound otherwise)")
+        La = ae_default.shape[1]
+
+        def bits(mask, Bm=B):
+            if mask is None:
+                return None
+            if mask.dim() == 4:
+                mask = mask[:, 0]
+            if mask.shape[0] != Bm:
+                mask = mask.expand(Bm, -1, -1)
+            return _lib.mask_pack(mask)
+
+        def hoisted(mem, wb):
+            m32 = mem.contiguous().view(-1, d)
+            m16 = _lib.cast_f16(m32)
+            out = torch.empty(m16.shape[0], N * 2 * d, dtype=f16, device=dev)
+            _lib.linear(m16, wb[0], wb[1], out_f16=out)
+            return m16, out
+
+        ctx = {"W": W, "B": B, "T": T, "La": La, "ae_features": ae_features, "ae_shared": None}
+        his16, kv_his = hoisted(his, W["kv_his"])
+        cap16, kv_cap = hoisted(cap, W["kv_cap"])
+        q16, kv_q = hoisted(qm, W["kv_q"])
+        b_his, b_cap, b_q = bits(his_mask), bits(cap_mask), bits(q_mask)
+        b_ae = b_q if ae_features == "query" else b_cap
+        ctx["mem16"] = {"his": his16, "cap": cap16, "src": q16}
+        ctx["mem_shape"] = {"his": his.shape, "cap": cap.shape, "src": qm.shape}
+
+        # ---- Query-Aware Auto-Encoder branch (mtn.py:209-213), all layers, per modality
+        qae_tapes, kv_ae, ae16s, ae_outs, vid16s = [], [], [], [], []
+        if isinstance(ae_ft, (list, tuple)):
+            ctx["ae_shared"] = None
+        else:
+            ctx["ae_shared"] = "given" if ae_ft is not None else ("src" if ae_features == "query" else "cap")
+        for i in range(M):
+            Lv = vid_ft[i].shape[1]
+            v16, kv_vid = hoisted(vid_ft[i], W["kv_vid"][i])
+            vid16s.append(v16)
+            b_vid = bits(vid_mask[i])
+            src = ae_ft[i] if isinstance(ae_ft, (list, tuple)) else (ae_ft if ae_ft is not None else ae_default)
+            ae = src.contiguous().view(B * La, d)
+            tape, kvs, a16s = [], [], []
+            for l in range(N):
+                Lw = W["layers"][l]
+                c0 = 4 + 4 * i
+                ae = self._attn_fwd(tape, ae, Lw["ln"][c0], Lw["ae_self"][i], B, La, La, None, 0, 0, b_ae,
+                                    ("ae_self", l, i, c0))
+                ae = self._attn_fwd(tape, ae, Lw["ln"][c0 + 1], Lw["ae_vid"][i], B, La, Lv, kv_vid, l * 2 * d,
+                                    l * 2 * d + d, b_vid, ("ae_vid", l, i, c0 + 1))
+                ae, a16 = self._ffn_fwd(tape, ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], ("ae_ffn", l, i, c0 + 2), want16=True)
+                A2 = Lw["ae_attn"][i]
+                kv = torch.empty(B * La, 2 * d, dtype=f16, device=dev)
+                _lib.linear(a16, A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=kv)
+                kvs.append(kv)
+                a16s.append(a16)
+            out = torch.empty(B * La, d, dtype=torch.float32, device=dev)
+            nrm = W["ae_norm"][i]
+            _lib.layernorm(ae, nrm[0], nrm[1], nrm[2], out_f32=out)
+            tape.append(("norm", dict(x_in=ae, ln=nrm, names=("ae_norm", i))))
+            qae_tapes.append(tape)
+            kv_ae.append(kvs)
+            ae16s.append(a16s)
+            ae_outs.append(out.view(B, La, d))
+        ctx["qae_tapes"], ctx["ae16"], ctx["vid16"] = qae_tapes, ae16s, vid16s
+
+        # ---- target path
+        tm = tgt_mask
+        if tm is not None and tm.dim() == 4:
+            tm = tm[:, 0]
+        if tm is not None and tm.shape[0] != B:
+            tm = tm.expand(B, -1, -1)
+        bits_t = _lib.mask_pack(tm) if tm is not None else None
+        order = (("src", kv_q, b_q, qm.shape[1]), ("cap", kv_cap, b_cap, cap.shape[1])) \
+            if ae_features in ("caption", "summary") else \
+            (("cap", kv_cap, b_cap, cap.shape[1]), ("src", kv_q, b_q, qm.shape[1]))
+        tape = []
+        xs = x.contiguous().view(B * T, d)
+        for l in range(N):
+            Lw = W["layers"][l]
+            kc, vc = l * 2 * d, l * 2 * d + d
+            xs = self._attn_fwd(tape, xs, Lw["ln"][0], Lw["self"], B, T, T, None, 0, 0, bits_t, ("self", l, 0, 0))
+            xs = self._attn_fwd(tape, xs, Lw["ln"][1], Lw["his"], B, T, his.shape[1], kv_his, kc, vc, b_his,
+                                ("his", l, 0, 1))
+            for c, (name, kvm, bm, Lm) in enumerate(order):
+                xs = self._attn_fwd(tape, xs, Lw["ln"][2 + c], Lw[name], B, T, Lm, kvm, kc, vc, bm, (name, l, 0, 2 + c))
+            for i in range(M):
+                xs = self._attn_fwd(tape, xs, Lw["ln"][7 + 4 * i], Lw["ae_attn"][i], B, T, La, kv_ae[i][l], 0, d, b_ae,
+                                    ("ae_attn", l, i, 7 + 4 * i))
+            xs, _ = self._ffn_fwd(tape, xs, Lw["ln"][4 + 4 * M], Lw["ffn"], ("ffn", l, 0, 4 + 4 * M))
+        out = torch.empty(B * T, d, dtype=torch.float32, device=dev)
+        _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=out)
+        tape.append(("norm", dict(x_in=xs, ln=W["norm"], names=("norm",))))
+        ctx["tape"] = tape
+        return out.view(B, T, d), ae_outs, ctx
+
+    # ------------------------------------------------------------------ gradient buffers
+    def _grad_views(self, dev):
+        """Flat gradient arena carved so that every GEMM of the backward writes one contiguous block:
+        [Wq;Wk;Wv] per self-attention-like module, all layers' [Wk_l;Wv_l] per hoisted memory.
+        Returns (G, per_param) with per_param: id(parameter) -> view."""
+        dec = self.dec
+        layers = dec.layers
+        N = len(layers)
+        M = len(layers[0].auto_encoder_vid_attn)
+        d = layers[0].size
+        total = sum((p.numel() + 3) // 4 * 4 for p in dec.parameters())
+        ar = _Arena(total, dev)
+        G, per = {}, {}
+
+        def lin_views(m, idx, w, b):
+            per[id(m.linears[idx].weight)], per[id(m.linears[idx].bias)] = w, b
+
+        def packed_qkv(key, mods):      # modules whose q, k, v projections are used together: [3d, d]
+            for l, m in mods:
+                w, b = ar.take(3 * d, d), ar.take(3 * d)
+                G[(key, l, "wqkv")], G[(key, l, "bqkv")] = w, b
+                for j in range(3):
+                    lin_views(m, j, w[j * d:(j + 1) * d], b[j * d:(j + 1) * d])
+                wo, bo = ar.take(d, d), ar.take(d)
+                G[(key, l, "wo")], G[(key, l, "bo")] = wo, bo
+                lin_views(m, 3, wo, bo)
+
+        def hoisted(key, mods):         # [N*2d, d]: layer l -> rows [l*2d, l*2d+d) = Wk_l, next d = Wv_l
+            w, b = ar.take(N * 2 * d, d), ar.take(N * 2 * d)
+            G[(key, "wkv")], G[(key, "bkv")] = w, b
+            for l, m in mods:
+                lin_views(m, 1, w[l * 2 * d:l * 2 * d + d], b[l * 2 * d:l * 2 * d + d])
+                lin_views(m, 2, w[l * 2 * d + d:(l + 1) * 2 * d], b[l * 2 * d + d:(l + 1) * 2 * d])
+                wq, bq, wo, bo = ar.take(d, d), ar.take(d), ar.take(d, d), ar.take(d)
+                G[(key, l, "wq")], G[(key, l, "bq")], G[(key, l, "wo")], G[(key, l, "bo")] = wq, bq, wo, bo
+                lin_views(m, 0, wq, bq)
+                lin_views(m, 3, wo, bo)
+
+        def ffn(key, mods):
+            for l, m in mods:
+                dff = m.w_1.weight.shape[0]
+                w1, b1, w2, b2 = ar.take(dff, d), ar.take(dff), ar.take(d, dff), ar.take(d)
+                G[(key, l, "w1")], G[(key, l, "b1")], G[(key, l, "w2")], G[(key, l, "b2")] = w1, b1, w2, b2
+                per[id(m.w_1.weight)], per[id(m.w_1.bias)] = w1, b1
+                per[id(m.w_2.weight)], per[id(m.w_2.bias)] = w2, b2
+
+        packed_qkv(("self", 0), [(l, L.self_attn) for l, L in enumerate(layers)])
+        hoisted(("his", 0), [(l, L.his_attn) for l, L in enumerate(layers)])
+        hoisted(("cap", 0), [(l, L.cap_attn) for l, L in enumerate(layers)])
+        hoisted(("src", 0), [(l, L.src_attn) for l, L in enumerate(layers)])
+        ffn(("ffn", 0), [(l, L.feed_forward) for l, L in enumerate(layers)])
+        for i in range(M):
+            packed_qkv(("ae_self", i), [(l, L.auto_encoder_self_attn[i]) for l, L in enumerate(layers)])
+            hoisted(("ae_vid", i), [(l, L.auto_encoder_vid_attn[i]) for l, L in enumerate(layers)])
+            packed_qkv(("ae_attn", i), [(l, L.auto_encoder_attn[i]) for l, L in enumerate(layers)])
+            ffn(("ae_ffn", i), [(l, L.auto_encoder_feed_forward[i]) for l, L in enumerate(layers)])
+        for l, L in enumerate(layers):
+            for c, s in enumerate(L.sublayer):
+                a, b = ar.take(d), ar.take(d)
+                G[("ln", l, c)] = (a, b)
+                per[id(s.norm.a_2)], per[id(s.norm.b_2)] = a, b
+        a, b = ar.take(d), ar.take(d)
+        G[("norm",)] = (a, b)
+        per[id(dec.norm.a_2)], per[id(dec.norm.b_2)] = a, b
+        for i, m in enumerate(dec.ae_norm):
+            a, b = ar.take(d), ar.take(d)
+            G[("ae_norm", i)] = (a, b)
+            per[id(m.a_2)], per[id(m.b_2)] = a, b
+        return G, per
+
+    # ------------------------------------------------------------------ backward building blocks
+    @staticmethod
+    def _ln_bwd(t, dy, dres, dx, gab, invS, dy_scale=None):
+        ln = t["ln"]
+        _lib.layernorm_bwd(t["x_in"], ln[0], ln[2], dy, dx, dres=dres, da_2=gab[0], db_2=gab[1], dy_scale=dy_scale,
+                           param_alpha=invS)
+
+    def _attn_bwd(self, t, dx, G, invS, dkv):
+        """dx: [rows, d] f32 scaled residual-stream gradient at the site's OUTPUT; updated in place to the
+        gradient at its input.  dkv: (dk view, dv view) f16 destination for cross sites (hoisted columns)."""
+        A = t["A"]
+        B, Lq, Lk, h, dk_ = t["B"], t["Lq"], t["Lk"], A["h"], A["d_k"]
+        rows, d = dx.shape
+        dev = dx.device
+        f16 = torch.float16
+        key, l, i, c = t["names"]
+        gk = (key, i)
+        # ---- output projection (mtn.py:267) + residual (mtn.py:127)
+        dx16 = torch.empty(rows, d, dtype=f16, device=dev)
+        _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS)
+        do16 = torch.empty(rows, d, dtype=f16, device=dev)
+        _lib.linear_dgrad(dx16, A["w_o"], out_f16=do16)
+        _lib.linear_wgrad(dx16, t["o16"], G[(gk, l, "wo")], alpha=invS)
+        # ---- attention core
+        delta = torch.empty(B, h, Lq, dtype=torch.float32, device=dev)
+        _lib.attn_delta(do16, t["o16"], B, Lq, h, dk_, delta)
+        dq32 = torch.zeros(rows, d, dtype=torch.float32, device=dev)
+        if t["self_attn"]:
+            dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
+            dkd, dvd = dqkv[:, d:2 * d], dqkv[:, 2 * d:]
+        else:
+            dkd, dvd = dkv
+        _lib.attn_core_bwd(t["q"], t["k"], t["v"], do16, t["stats"], delta, B, h, Lq, Lk, dk_, dq32, dkd, dvd,
+                           mask_bits=t["bits"])
+        # ---- Q (or QKV) projection
+        dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        if t["self_attn"]:
+            gb = G[(gk, l, "bqkv")]
+            _lib.cast_colsum(dq32, dst_f16=dqkv[:, :d], colsum=gb[:d], alpha=invS)
+            _lib.cast_colsum(dqkv[:, d:], colsum=gb[d:], alpha=invS)
+            _lib.linear_dgrad(dqkv, A["w_qkv"], out_f32=dxn)
+            _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS)
+        else:
+            dq16 = torch.empty(rows, d, dtype=f16, device=dev)
+            wq_key, bq_key = ("wq", "bq") if (gk, l, "wq") in G else ("wqkv", "bqkv")
+            gw, gb = G[(gk, l, wq_key)], G[(gk, l, bq_key)]
+            _lib.cast_colsum(dq32, dst_f16=dq16, colsum=gb[:d], alpha=invS)
+            _lib.linear_dgrad(dq16, A["w_qkv"][:d], out_f32=dxn)
+            _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS)
+        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS)
+
+    def _ffn_bwd(self, t, dx, G, invS):
+        Fw = t["Fw"]
+        rows, d = dx.shape
+        dev = dx.device
+        f16 = torch.float16
+        key, l, i, c = t["names"]
+        gk = (key, i)
+        dx16 = torch.empty(rows, d, dtype=f16, device=dev)
+        _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS)
+        dhid = torch.empty(rows, Fw["w_1"].shape[0], dtype=f16, device=dev)
+        _lib.linear_dgrad(dx16, Fw["w_2"], relu_mask=t["hid"], out_f16=dhid)        # through the ReLU (mtn.py:280)
+        _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS)
+        _lib.cast_colsum(dhid, colsum=G[(gk, l, "b1")], alpha=invS)
+        dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        _lib.linear_dgrad(dhid, Fw["w_1"], out_f32=dxn)
+        _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS)
+        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, ctx, g_out, g_ae):
+        """g_out: [B,T,d] f32 or None; g_ae: list of [B,La,d] f32 or None.  Returns (input_grads, per_param) with
+        input_grads = dict(x, his, cap, src, vid=[...], ae=[...] or None)."""
+        W = ctx["W"]
+        d, N, M = W["d"], W["N"], W["M"]
+        B, T, La = ctx["B"], ctx["T"], ctx["La"]
+        tape = ctx["tape"]
+        dev = tape[0][1]["x_in"].device
+        f16 = torch.float16
+        G, per = self._grad_views(dev)
+        if g_out is None:
+            g_out = torch.zeros(B, T, d, dtype=torch.float32, device=dev)
+        g_ae = [g if g is not None else torch.zeros(B, La, d, dtype=torch.float32, device=dev) for g in g_ae]
+        g_out = g_out.contiguous().float()
+        g_ae = [g.contiguous().float() for g in g_ae]
+        S2 = _lib.grad_scale([g_out] + g_ae)
+        S, invS = S2[0:1], S2[1:2]
+
+        # hoisted dK/dV destinations, one per memory: every layer fills its own columns
+        rows_mem = {k: v.shape[0] for k, v in ctx["mem16"].items()}
+        dkv_mem = {k: torch.empty(r, N * 2 * d, dtype=f16, device=dev) for k, r in rows_mem.items()}
+        dkv_vid = [torch.empty(v.shape[0], N * 2 * d, dtype=f16, device=dev) for v in ctx["vid16"]]
+        dkv_ae = [[torch.empty(B * La, 2 * d, dtype=f16, device=dev) for _ in range(N)] for _ in range(M)]
+
+        # ---- target path, last sublayer first
+        kind, t = tape[-1]
+        dx = torch.empty(B * T, d, dtype=torch.float32, device=dev)
+        self._ln_bwd(t, g_out.view(B * T, d), None, dx, G[("norm",)], invS, dy_scale=S)        # mtn.py:164
+        for kind, t in reversed(tape[:-1]):
+            if kind == "ffn":
+                self._ffn_bwd(t, dx, G, invS)
+                continue
+            key, l, i, c = t["names"]
+            if key == "self":
+                dkv = None
+            elif key == "ae_attn":
+                buf = dkv_ae[i][l]
+                dkv = (buf[:, :d], buf[:, d:])
+            else:
+                buf = dkv_mem[key]
+                dkv = (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d])
+            self._attn_bwd(t, dx, G, invS, dkv)
+        grads = {"x": self._unscale(dx, invS).view(B, T, d)}
+
+        # ---- Query-Aware Auto-Encoder branch
+        grads["ae"], grads["vid"] = [], []
+        for i in range(M):
+            qt = ctx["qae_tapes"][i]
+            kind, t = qt[-1]
+            dae = torch.empty(B * La, d, dtype=torch.float32, device=dev)
+            self._ln_bwd(t, g_ae[i].view(B * La, d), None, dae, G[("ae_norm", i)], invS, dy_scale=S)  # mtn.py:162-163
+            for kind, t in reversed(qt[:-1]):
+                key, l, _, c = t["names"]
+                if kind == "ffn":
+                    # the layer's output ae_i^l is also the memory of the target's auto_encoder_attn[i] (mtn.py:215):
+                    # add the gradient that came back through its K/V projection
+                    A2 = W["layers"][l]["ae_attn"][i]
+                    gk = ("ae_attn", i)
+                    _lib.cast_colsum(dkv_ae[i][l], colsum=G[(gk, l, "bqkv")][d:], alpha=invS)
+                    _lib.linear_dgrad(dkv_ae[i][l], A2["w_qkv"][d:], addend=dae, out_f32=dae)
+                    _lib.linear_wgrad(dkv_ae[i][l], ctx["ae16"][i][l], G[(gk, l, "wqkv")][d:], alpha=invS)
+                    self._ffn_bwd(t, dae, G, invS)
+                elif key == "ae_vid":
+                    buf = dkv_vid[i]
+                    self._attn_bwd(t, dae, G, invS, (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d]))
+                else:
+                    self._attn_bwd(t, dae, G, invS, None)
+            grads["ae"].append(self._unscale(dae, invS).view(B, La, d))
+            # hoisted video K/V projection of modality i
+            gk = ("ae_vid", i)
+            grads["vid"].append(self._mem_bwd(dkv_vid[i], ctx["vid16"][i], W["kv_vid"][i][0], G[(gk, "wkv")], G[(gk, "bkv")],
+                                              invS))
+        for name in ("his", "cap", "src"):
+            gk = (name, 0)
+            grads[name] = self._mem_bwd(dkv_mem[name], ctx["mem16"][name], W["kv_" + ("q" if name == "src" else name)][0],
+                                        G[(gk, "wkv")], G[(gk, "bkv")], invS).view(ctx["mem_shape"][name])
+        return grads, per
+
+    @staticmethod
+    def _unscale(dx, invS):
+        """An input gradient leaves the Function: multiply by 1/S."""
+        out = torch.empty_like(dx)
+        _lib.scale_f32(dx, invS, out)
+        return out
+
+    @staticmethod
+    def _mem_bwd(dkv, mem16, w_kv, gw, gb, invS):
+        """Backward of a hoisted memory K/V projection: bias gradient, weight gradient, memory gradient."""
+        _lib.cast_colsum(dkv, colsum=gb, alpha=invS)
+        _lib.linear_wgrad(dkv, mem16, gw, alpha=invS)
+        dmem = torch.empty(mem16.shape[0], mem16.shape[1], dtype=torch.float32, device=dkv.device)
+        _lib.linear_dgrad(dkv, w_kv, alpha=invS, out_f32=dmem)
+        return dmem
