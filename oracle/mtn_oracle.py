@@ -239,6 +239,31 @@ def simple_loss(sd, cfg, out, trg_y, ae_out, ae_y, pad=1, smoothing=0.1, lam=1.0
     return float(loss) * float(norm)
 
 
+def loss_and_grads(sd, cfg, query, his, cap, trg, trg_y, fts, pad=1, smoothing=0.1, lam=1.0):
+    """One training step's loss and parameter gradients with dropout disabled: train.py:33-39 (forward, loss on
+    the decoder output AND on every auto-encoder stream against the un-shifted query ids, normalised by
+    ntokens / ntokens_query) + data_utils.py:132-152 (loss.backward()).  Plain torch autograd through the
+    functional restatement above.  Returns (loss / 1, {name: grad}) -- the loss is the NORMALISED one that is
+    differentiated (the reference returns loss * norm)."""
+    p = {k: (v.clone().requires_grad_(True) if not k.endswith(".pe") else v) for k, v in sd.items()}
+    m = make_masks(query, his, cap, trg, fts, pad)
+    q_mem, vid_mem, cap_mem, his_mem, ae_mem = encode(p, cfg, query, his, cap, m["fts"])
+    x = embed(p, "tgt_embed.", trg, cfg["d_model"])
+    out, ae_out = decoder(p, cfg, vid_mem, m["fts_mask"], x, his_mem, m["his_mask"], cap_mem, m["cap_mask"], q_mem,
+                          m["query_mask"], m["trg_mask"], ae_mem)
+    V = p["generator.proj.weight"].shape[0]
+    norm = (trg_y != pad).sum().float()
+    loss = label_smoothing_loss(generator(p, out).reshape(-1, V), trg_y.reshape(-1), V, pad, smoothing) / norm
+    ae_y = query if cfg.get("auto_encoder_ft", "query") == "query" else cap          # train.py:34-39
+    ae_norm = (ae_y != pad).sum().float()
+    for a in ae_out:
+        loss = loss + lam * label_smoothing_loss(generator(p, a).reshape(-1, V), ae_y.reshape(-1), V, pad,
+                                                 smoothing) / ae_norm
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items() if not k.endswith(".pe")}
+    return float(loss.detach()), grads
+
+
 def greedy_decode(sd, cfg, query, his, cap, fts, max_len, sos=2, pad=1):
     """The *intended* semantics of data_utils.py:162-186, using the working call
     form of data_utils.py:202-210 (the reference's greedy_decode raises TypeError;

@@ -1,0 +1,328 @@
+"""GPU tier, backward kernels (ABI v3) through the C ABI, compared with torch autograd through the CPU oracle's
+arithmetic on the same (f16-rounded where the kernel rounds) operands, and -- model level -- with the gradients of
+the unmodified reference (golden digest) and of the oracle's training step.
+
+Tolerances (normwise ||g - ref|| / ||ref|| unless noted):
+  GEMM forms vs on-device check kernel (identical rounding)  2e-5
+  row kernels (f32 arithmetic)                                1e-5
+  attention backward (P and dS rounded to f16 for the MMAs)   3e-3
+  model-level parameter gradients (f16 operands end to end)   2e-2 per tensor, 5e-3 for the loss
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+import mtn_oracle as O
+from test_oracle_grads import check_against_digest, golden_grad_case, grad_errors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from mtn_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def dev(t):
+    return t.cuda()
+
+
+def rnd16(t):
+    return t.half().float()
+
+
+# ------------------------------------------------------------------ general GEMM: operand forms, split-K, epilogue
+GEMM_CASES = [
+    # M, N, K, a_mn, b_mn
+    (200, 264, 136, 0, 0), (200, 264, 136, 0, 1), (200, 264, 136, 1, 1),
+    (128, 64, 64, 0, 1), (128, 64, 64, 1, 1), (520, 512, 2048, 0, 1), (512, 512, 4100, 1, 1),
+    (2048, 512, 777, 1, 1), (104, 512, 333, 1, 1), (64, 2048, 192, 0, 1),
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", GEMM_CASES)
+def test_gemm_forms_vs_check_kernel(L, M, N, K, a_mn, b_mn):
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K + a_mn + 2 * b_mn)
+    A = (torch.randn((K, M) if a_mn else (M, K), generator=g)).half().cuda()
+    B = (torch.randn((K, N) if b_mn else (N, K), generator=g)).half().cuda()
+    Af = A.float().t() if a_mn else A.float()
+    Bf = B.float().t() if b_mn else B.float()
+    ref = Af @ Bf.t()
+    alpha = torch.tensor([0.5], device="cuda")
+    out, chk = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    L.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, alpha=alpha, out_f32=out)
+    L.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, alpha=alpha, out_f32=chk, _check_kernel=True)
+    torch.cuda.synchronize()
+    assert G.rel_err(out.cpu(), chk.cpu()) < 2e-5, "layout bug (vs on-device check kernel)"
+    assert G.rel_err(out.cpu(), 0.5 * ref.cpu()) < 2e-5
+    # split-K accumulation on top of existing contents
+    acc = torch.full((M, N), 3.0, device="cuda")
+    L.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, alpha=alpha, accumulate=True, out_f32=acc)
+    torch.cuda.synchronize()
+    assert G.rel_err((acc - 3.0).cpu(), 0.5 * ref.cpu()) < 5e-5
+
+
+def test_gemm_relu_mask_and_pre_add(L):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 300, 256, 192
+    A, B = torch.randn(M, K, generator=g).half().cuda(), torch.randn(K, N, generator=g).half().cuda()
+    mask = torch.randn(M, N, generator=g).relu().half().cuda()
+    out16 = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    L.gemm(A, B, M, N, K, b_mn=True, relu_mask=mask, out_f16=out16)
+    ref = (A.float() @ B.float()) * (mask.float() > 0)
+    assert G.rel_err(out16.float().cpu(), ref.cpu()) < 6e-4
+    # forward linear: out16 = relu(.) before the positional addend, out32 after it
+    W = torch.randn(N, K, generator=g).half().cuda()
+    bias, pe = torch.randn(N, generator=g).cuda(), torch.randn(50, N, generator=g).cuda()
+    o32, o16 = torch.empty(M, N, device="cuda"), torch.empty(M, N, dtype=torch.float16, device="cuda")
+    L.linear(A, W, bias, act=L.ACT_RELU, addend=pe, add_period=50, out_f32=o32, out_f16=o16, out16_pre_add=True)
+    pre = (A.float() @ W.float().t() + bias).relu()
+    assert G.rel_err(o16.float().cpu(), pre.cpu()) < 6e-4
+    assert G.rel_err(o32.cpu(), (pre + pe.repeat(6, 1)).cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(77, 128, 128), (8192, 512, 512), (2048, 2048, 512), (640, 3000, 512)])
+def test_linear_dgrad_wgrad_vs_autograd(L, M, N, K):
+    """y = x W^T: dX = dY W, dW = dY^T X on f16-rounded operands, incl. the device-side gradient scale."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = rnd16(torch.randn(M, K, generator=g))
+    w = rnd16(torch.randn(N, K, generator=g) * 0.05)
+    dy = torch.randn(M, N, generator=g) * 1e-6            # tiny gradients: would underflow f16 unscaled
+    dy32 = dy.cuda()
+    S2 = L.grad_scale([dy32])
+    S = float(S2[0])
+    assert 128.0 <= float(dy.abs().max()) * S < 256.0 and abs(float(S2[1]) * S - 1) < 1e-6
+    dy16 = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    L.cast_colsum(dy32, dst_f16=dy16, colsum=db, scale=S2[0:1], alpha=S2[1:2])
+    dyr = dy16.float().cpu() / S                            # what the tensor core sees, un-scaled
+    assert G.rel_err(dyr, dy) < 6e-4
+    assert G.rel_err(db.cpu(), dy.sum(0)) < 1e-4
+    dx = torch.empty(M, K, device="cuda")
+    L.linear_dgrad(dy16, w.half().cuda(), alpha=S2[1:2], out_f32=dx)
+    dW = torch.zeros(N, K, device="cuda")
+    L.linear_wgrad(dy16, x.half().cuda(), dW, alpha=S2[1:2])
+    torch.cuda.synchronize()
+    assert G.rel_err(dx.cpu(), dyr @ w) < 3e-5
+    assert G.rel_err(dW.cpu(), dyr.t() @ x) < 3e-5
+
+
+# ------------------------------------------------------------------ row kernels
+@pytest.mark.parametrize("rows,d", [(1, 4), (7, 128), (33, 512), (5, 1024), (3, 96), (5000, 512)])
+def test_layernorm_bwd(L, rows, d):
+    g = torch.Generator().manual_seed(rows * 100 + d)
+    x = (torch.randn(rows, d, generator=g) * 3 + 1).requires_grad_(True)
+    a = (1 + 0.1 * torch.randn(d, generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(d, generator=g)).requires_grad_(True)
+    dy = torch.randn(rows, d, generator=g)
+    dres = torch.randn(rows, d, generator=g)
+    O.layer_norm(x, a, b, 1e-6).backward(dy)
+    dx = dres.clone().cuda()
+    da, db = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    L.layernorm_bwd(dev(x.detach()), dev(a.detach()), 1e-6, dev(dy), dx, dres=dx, da_2=da, db_2=db)
+    torch.cuda.synchronize()
+    assert G.rel_err(dx.cpu() - dres, x.grad) < 1e-5
+    assert G.rel_err(da.cpu(), a.grad) < 2e-5 and G.rel_err(db.cpu(), b.grad) < 2e-5
+    # scaled entry: dy * S in, parameter gradients / S out
+    S2 = torch.tensor([64.0, 1 / 64.0], device="cuda")
+    dx2 = torch.empty(rows, d, device="cuda")
+    da.zero_(); db.zero_()
+    L.layernorm_bwd(dev(x.detach()), dev(a.detach()), 1e-6, dev(dy), dx2, da_2=da, db_2=db, dy_scale=S2[0:1],
+                    param_alpha=S2[1:2])
+    assert G.rel_err(dx2.cpu() / 64.0, x.grad) < 1e-5 and G.rel_err(da.cpu(), a.grad) < 2e-5
+
+
+def test_cast_colsum_scale_f32_delta(L):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(333, 520, generator=g)
+    m = torch.randn(333, 520, generator=g).half()
+    y16 = torch.empty(333, 520, dtype=torch.float16, device="cuda")
+    cs = torch.ones(520, device="cuda")
+    sc, al = torch.tensor([4.0], device="cuda"), torch.tensor([0.25], device="cuda")
+    L.cast_colsum(dev(x), dst_f16=y16, colsum=cs, scale=sc, alpha=al, relu_mask=dev(m))
+    ref = x * 4 * (m.float() > 0)
+    assert torch.equal(y16.cpu(), ref.half())
+    assert G.rel_err(cs.cpu() - 1, ref.sum(0) * 0.25) < 1e-5
+    cs2 = torch.zeros(520, device="cuda")
+    L.cast_colsum(y16, colsum=cs2)                              # f16 source, column sums only
+    assert G.rel_err(cs2.cpu(), y16.float().cpu().sum(0)) < 1e-5
+    out = torch.ones(333 * 520, device="cuda")
+    L.scale_f32(dev(x).view(-1), al, out, accumulate=True)
+    assert G.rel_err(out.cpu(), 1 + 0.25 * x.reshape(-1)) < 1e-6
+    # attention row term
+    B, Lq, h, dk = 3, 37, 8, 64
+    dO, Ot = torch.randn(B * Lq, h * dk, generator=g).half(), torch.randn(B * Lq, h * dk, generator=g).half()
+    delta = torch.empty(B, h, Lq, device="cuda")
+    L.attn_delta(dev(dO), dev(Ot), B, Lq, h, dk, delta)
+    ref = (dO.float() * Ot.float()).view(B, Lq, h, dk).sum(-1).permute(0, 2, 1)
+    assert G.rel_err(delta.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("with_ln", [True, False])
+def test_embed_bwd(L, with_ln):
+    g = torch.Generator().manual_seed(17)
+    V, d, B, Lq = 50, 128, 4, 9
+    ids = torch.randint(0, V, (B, Lq), generator=g)
+    lut = torch.randn(V, d, generator=g).requires_grad_(True)
+    pe = O.sinusoid_pe(d)[0, :64].contiguous()
+    a = (1 + 0.1 * torch.randn(d, generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(d, generator=g)).requires_grad_(True)
+    dy = torch.randn(B, Lq, d, generator=g)
+    y = lut[ids] * (d ** 0.5) + pe[:Lq]
+    if with_ln:
+        y = O.layer_norm(y, a, b, 1e-6)
+    y.backward(dy)
+    dlut = torch.zeros(V, d, device="cuda")
+    da, db = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    L.embed_bwd(dev(ids), dev(lut.detach()), dev(pe), d ** 0.5, dev(dy), dlut,
+                ln=(dev(a.detach()), None, 1e-6) if with_ln else None, da_2=da if with_ln else None,
+                db_2=db if with_ln else None)
+    torch.cuda.synchronize()
+    assert G.rel_err(dlut.cpu(), lut.grad) < 1e-5
+    if with_ln:
+        assert G.rel_err(da.cpu(), a.grad) < 2e-5 and G.rel_err(db.cpu(), b.grad) < 2e-5
+
+
+def test_log_softmax_and_label_smoothing_bwd(L):
+    g = torch.Generator().manual_seed(23)
+    rows, V, V8 = 40, 203, 208
+    z = (torch.randn(rows, V, generator=g) * 2).requires_grad_(True)
+    dy = torch.randn(rows, V, generator=g)
+    y = torch.log_softmax(z, -1)
+    y.backward(dy)
+    dz = torch.full((rows, V8), 7.0, device="cuda")
+    L.log_softmax_bwd(dev(y.detach()), dev(dy), V, dz)
+    assert G.rel_err(dz[:, :V].cpu(), z.grad) < 1e-5 and float(dz[:, V:].abs().max()) == 0
+    for tgt_case in ("mixed", "lone_pad_row0"):
+        tgt = torch.randint(2, V, (rows,), generator=g)
+        if tgt_case == "mixed":
+            tgt[5] = 1; tgt[17] = 1
+        else:
+            tgt[0] = 1                              # index sum 0: the reference does NOT zero this row
+        z2 = torch.randn(rows, V, generator=g).requires_grad_(True)
+        loss = O.label_smoothing_loss(torch.log_softmax(z2, -1), tgt, V, 1, 0.1) * 0.37
+        loss.backward()
+        zp = torch.zeros(rows, V8)
+        zp[:, :V] = z2.detach()
+        dz2 = torch.empty(rows, V8, device="cuda")
+        gout = torch.tensor([2.0], device="cuda")
+        L.label_smoothing_loss_bwd(dev(zp), V, dev(tgt), 1, 0.1, dz2, gscale=0.37 / 2.0, gout=gout)
+        assert G.rel_err(dz2[:, :V].cpu(), z2.grad) < 2e-5, tgt_case
+        assert float(dz2[:, V:].abs().max()) == 0
+
+
+# ------------------------------------------------------------------ attention core backward
+ATT_CASES = [
+    # B, h, Lq, Lk, dk, mask kind
+    (2, 4, 8, 16, 32, "keypad"), (2, 8, 64, 64, 64, "keypad"), (3, 8, 130, 300, 64, "keypad"),
+    (2, 8, 256, 256, 64, "causal"), (2, 4, 20, 20, 32, "causal"), (2, 8, 40, 512, 64, "none"),
+    (2, 8, 33, 70, 64, "allmasked_row"), (1, 8, 256, 512, 64, "keypad"),
+]
+
+
+def _attn_ref(q, k, v, mask, B, h, Lq, Lk, dk):
+    """autograd through the oracle's attention on (B, h, L, dk) views of the f16-rounded operands."""
+    def heads(t, Lx):
+        return t.view(B, Lx, h, dk).transpose(1, 2)
+    o, _ = O.attention(heads(q, Lq), heads(k, Lk), heads(v, Lk), None if mask is None else mask.unsqueeze(1))
+    return o.transpose(1, 2).reshape(B * Lq, h * dk)
+
+
+@pytest.mark.parametrize("B,h,Lq,Lk,dk,kind", ATT_CASES)
+def test_attn_core_bwd_vs_autograd(L, B, h, Lq, Lk, dk, kind):
+    g = torch.Generator().manual_seed(B * 1000 + Lq * 10 + Lk)
+    d = h * dk
+    q = rnd16(torch.randn(B * Lq, d, generator=g)).requires_grad_(True)
+    k = rnd16(torch.randn(B * Lk, d, generator=g)).requires_grad_(True)
+    v = rnd16(torch.randn(B * Lk, d, generator=g)).requires_grad_(True)
+    mask = None
+    if kind == "keypad":
+        mask = torch.ones(B, 1, Lk, dtype=torch.bool)
+        for b in range(1, B):
+            mask[b, 0, int(Lk * 0.6) + b:] = False
+    elif kind == "causal":
+        mask = O.subsequent_mask(Lq).expand(B, -1, -1).clone()
+        mask[B - 1, :, Lk - 3:] = False
+    elif kind == "allmasked_row":
+        mask = torch.ones(B, 1, Lk, dtype=torch.bool)
+        mask[1] = False                                   # every key masked: uniform softmax, dQ = dK = 0, dV != 0
+    o = _attn_ref(q, k, v, mask, B, h, Lq, Lk, dk)
+    dO = rnd16(torch.randn(B * Lq, d, generator=g))
+    o.backward(dO)
+    # --- device
+    q16, k16, v16, dO16 = (t.detach().half().cuda() for t in (q, k, v, dO))
+    bits = L.mask_pack(mask.cuda()) if mask is not None else None
+    o16 = torch.empty(B * Lq, d, dtype=torch.float16, device="cuda")
+    stats = torch.empty(B, h, Lq, 2, device="cuda")
+    L.attn_core(q16, k16, v16, B, h, Lq, Lk, dk, o16, mask_bits=bits, stats=stats)
+    assert G.rel_err(o16.float().cpu(), o.detach()) < 1e-3
+    delta = torch.empty(B, h, Lq, device="cuda")
+    L.attn_delta(dO16, o16, B, Lq, h, dk, delta)
+    dq = torch.zeros(B * Lq, d, device="cuda")
+    dk_ = torch.full((B * Lk, d), 9.0, dtype=torch.float16, device="cuda")
+    dv_ = torch.full((B * Lk, d), 9.0, dtype=torch.float16, device="cuda")
+    L.attn_core_bwd(q16, k16, v16, dO16, stats, delta, B, h, Lq, Lk, dk, dq, dk_, dv_, mask_bits=bits)
+    torch.cuda.synchronize()
+    errs = (G.rel_err(dq.cpu(), q.grad), G.rel_err(dk_.float().cpu(), k.grad), G.rel_err(dv_.float().cpu(), v.grad))
+    print("attn bwd %s: dq %.2e dk %.2e dv %.2e" % ((B, h, Lq, Lk, dk, kind), *errs))
+    assert max(errs) < 3e-3, errs
+    if kind == "allmasked_row":
+        assert float(dq[Lq:2 * Lq].abs().max()) == 0 and float(dk_[Lk:2 * Lk].abs().max()) == 0
+        assert float(dv_[Lk:2 * Lk].abs().max()) > 0
+
+
+# ------------------------------------------------------------------ model level
+def _train_grads(mtn, du, cfg, sd, inp, smoothing=0.1):
+    from mtn_b200 import label_smoothing
+    model = mtn.make_model(cfg["vocab"], cfg["vocab"], N=cfg["N"], d_model=cfg["d_model"], d_ff=cfg["d_ff"], h=cfg["h"],
+                           dropout=0.1, ft_sizes=cfg["ft_sizes"], diff_encoder=True, auto_encoder_ft="query")
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g = lambda t: t.cuda()
+    b = du.Batch(g(inp["query"]), g(inp["his"]), None, [g(f).permute(1, 0, 2).contiguous() for f in inp["fts"]],
+                 g(inp["cap"]), g(inp["trg"]), g(inp["trg_y"]), 1)
+    out, ae = model.forward(b)                                                    # train.py:33
+    crit = label_smoothing.LabelSmoothing(size=cfg["vocab"], padding_idx=1, smoothing=smoothing)
+    lc = du.SimpleLossCompute(model.generator, None, crit, opt=None)
+    loss = lc.loss(out, b.trg_y, int(b.ntokens), ae, b.query, int((b.query != 1).sum()))   # train.py:37-39
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss), {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+
+
+def test_training_step_vs_reference_golden_gradients():
+    """BASELINE configs[0] family (N=1, d=128, h=4, d_k=32), ragged batch with an all-pad history row: loss and every
+    parameter gradient against the UNMODIFIED reference's training step (digest) and the oracle's autograd."""
+    from mtn_b200 import mtn, data_utils
+    z, cfg, sd, inp = golden_grad_case()
+    loss, grads = _train_grads(mtn, data_utils, cfg, sd, inp)
+    norm = float((inp["trg_y"] != 1).sum())
+    assert abs(loss * norm - float(z["loss_times_norm"])) <= 5e-3 * abs(float(z["loss_times_norm"]))
+    oloss, og = O.loss_and_grads(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"])
+    errs = grad_errors(grads, og)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print("train step d=128: loss %.6f vs %.6f; worst grad errors: %s" % (loss, oloss, worst))
+    assert max(errs.values()) < 2e-2, worst
+    check_against_digest(z, grads, 2e-2)
+
+
+def test_training_step_d512_vs_oracle():
+    """cfg2 family (N=2, d=512, h=8, d_k=64), ragged batch."""
+    from mtn_b200 import mtn, data_utils
+    cfg = {"N": 2, "d_model": 512, "d_ff": 2048, "h": 8, "vocab": 200, "ft_sizes": [2048, 128],
+           "auto_encoder_ft": "query", "diff_encoder": True}
+    sd = O.init_state_dict(cfg, 3)
+    inp = O.synth_inputs(cfg, B=4, Q=16, C=24, H=70, T=12, Lv=[140, 40], seed=5)
+    loss, grads = _train_grads(mtn, data_utils, cfg, sd, inp)
+    oloss, og = O.loss_and_grads(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"])
+    errs = grad_errors(grads, og)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print("train step d=512: loss %.6f vs %.6f; worst grad errors: %s" % (loss, oloss, worst))
+    assert abs(loss - oloss) <= 5e-3 * abs(oloss)
+    assert max(errs.values()) < 2e-2, worst

@@ -233,9 +233,11 @@ def test_loud_failures(M):
     ln = mtn.LayerNorm(128)
     with pytest.raises(Exception, match="CUDA"):
         ln(torch.zeros(2, 128))                     # CPU tensor: no fallback
-    ln = ln.cuda().train()
+    # modules without a backward kernel binding refuse to record instead of returning graph-less tensors
+    mha = mtn.MultiHeadedAttention(4, 128).cuda().train()
+    x = torch.zeros(2, 3, 128, device="cuda", requires_grad=True)
     with pytest.raises(NotImplementedError):
-        ln(torch.zeros(2, 128, device="cuda", requires_grad=True))
+        mha(x, x, x)
 
 
 def test_cfg4_decode_graphs_token_exact(M, cfg2_model):

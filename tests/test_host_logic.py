@@ -76,10 +76,13 @@ def test_hot_path_has_no_cpu_fallback():
                 fn()
 
 
-def test_training_mode_is_rejected_not_silently_wrong():
+def test_training_on_cpu_is_rejected_not_silently_wrong():
     model = small_model().train()
     with pytest.raises((NotImplementedError, _lib.MtnError)):
-        model.decoder.norm(torch.zeros(2, 64, requires_grad=True))
+        model.decoder.norm(torch.zeros(2, 64, requires_grad=True))      # no CPU implementation, no fallback
+    with pytest.raises((NotImplementedError, _lib.MtnError)):           # module-level MHA has no backward binding
+        x = torch.zeros(1, 2, 64, requires_grad=True)
+        model.decoder.layers[0].self_attn(x, x, x)
 
 
 def test_packed_weight_cache_invalidation():
