@@ -417,7 +417,7 @@ class DecoderTrainer(object):
             # hoisted video K/V projection of modality i
             gk = ("ae_vid", i)
             grads["vid"].append(self._mem_bwd(dkv_vid[i], ctx["vid16"][i], W["kv_vid"][i][0], G[(gk, "wkv")], G[(gk, "bkv")],
-                                              invS))
+                                              invS).view(B, -1, d))
         for name in ("his", "cap", "src"):
             gk = (name, 0)
             grads[name] = self._mem_bwd(dkv_mem[name], ctx["mem16"][name], W["kv_" + ("q" if name == "src" else name)][0],

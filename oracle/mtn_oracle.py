@@ -264,6 +264,39 @@ def loss_and_grads(sd, cfg, query, his, cap, trg, trg_y, fts, pad=1, smoothing=0
     return float(loss.detach()), grads
 
 
+class _Linear16(torch.autograd.Function):
+    """nn.Linear with the arithmetic CONTRACT of the sm_100a GEMM kernels and none of their code: operands rounded
+    to f16 (forward: x, W; backward: dy scaled by a power of two, x, W), f32 accumulation."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x16, w16 = x.half().float(), w.half().float()
+        ctx.save_for_backward(x16, w16)
+        return x16 @ w16.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w16 = ctx.saved_tensors
+        s = 2.0 ** (8 - math.frexp(float(dy.abs().max()) + 1e-300)[1])
+        dy16 = (dy * s).half().float() / s
+        dw = dy16.reshape(-1, dy16.shape[-1]).t() @ x16.reshape(-1, x16.shape[-1])
+        return dy16 @ w16, dw, dy.reshape(-1, dy.shape[-1]).sum(0)
+
+
+class f16_operand_linears(object):
+    """Context manager: inside it every ``linear`` of this module rounds its operands like the tensor-core kernels
+    do.  Used by the tests to separate "precision of the operand format" from "bug" in gradient comparisons."""
+
+    def __enter__(self):
+        global linear
+        self._orig = linear
+        linear = lambda x, w, b: _Linear16.apply(x, w, b)
+
+    def __exit__(self, *exc):
+        global linear
+        linear = self._orig
+
+
 def greedy_decode(sd, cfg, query, his, cap, fts, max_len, sos=2, pad=1):
     """The *intended* semantics of data_utils.py:162-186, using the working call
     form of data_utils.py:202-210 (the reference's greedy_decode raises TypeError;

@@ -6,7 +6,10 @@ Tolerances (normwise ||g - ref|| / ||ref|| unless noted):
   GEMM forms vs on-device check kernel (identical rounding)  2e-5
   row kernels (f32 arithmetic)                                1e-5
   attention backward (P and dS rounded to f16 for the MMAs)   3e-3
-  model-level parameter gradients (f16 operands end to end)   2e-2 per tensor, 5e-3 for the loss
+  model-level parameter gradients vs the f32 reference: 3e-2 per tensor, median 8e-3 -- the floor of f16 (11-bit
+  significand, = TF32) GEMM operands, measured WITHOUT any kernel by tools/f16_grad_precision.py (median 4.9e-3, max
+  2.0e-2 for the d=512 case below).  The largest per-ENTRY deviations come from ReLU activations within rounding
+  distance of zero (the mask flips), which is why the digest's sampled entries get a wider bar than the norms.
 """
 import numpy as np
 import pytest
@@ -296,6 +299,17 @@ def _train_grads(mtn, du, cfg, sd, inp, smoothing=0.1):
     return float(loss), {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
 
 
+def _vs_f16_contract(grads, args, tag):
+    """Against the oracle whose linears round their operands to f16 like the kernels (same arithmetic contract, no
+    shared code): what is left is accumulation order and the attention core's P / dS rounding."""
+    with O.f16_operand_linears():
+        _, g16 = O.loss_and_grads(*args)
+    errs = grad_errors(grads, g16)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print("train step %s vs f16-operand oracle: median %.2e worst %s" % (tag, float(np.median(list(errs.values()))), worst))
+    assert max(errs.values()) < 3e-2, worst     # two f16-operand implementations differ by rounding noise of the same size
+
+
 def test_training_step_vs_reference_golden_gradients():
     """BASELINE configs[0] family (N=1, d=128, h=4, d_k=32), ragged batch with an all-pad history row: loss and every
     parameter gradient against the UNMODIFIED reference's training step (digest) and the oracle's autograd."""
@@ -307,9 +321,11 @@ def test_training_step_vs_reference_golden_gradients():
     oloss, og = O.loss_and_grads(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"])
     errs = grad_errors(grads, og)
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
-    print("train step d=128: loss %.6f vs %.6f; worst grad errors: %s" % (loss, oloss, worst))
-    assert max(errs.values()) < 2e-2, worst
-    check_against_digest(z, grads, 2e-2)
+    print("train step d=128: loss %.6f vs %.6f; median %.2e worst grad errors: %s"
+          % (loss, oloss, float(np.median(list(errs.values()))), worst))
+    assert max(errs.values()) < 3e-2 and float(np.median(list(errs.values()))) < 8e-3, worst
+    check_against_digest(z, grads, 8e-2)
+    _vs_f16_contract(grads, (sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"]), "d=128")
 
 
 def test_training_step_d512_vs_oracle():
@@ -323,6 +339,8 @@ def test_training_step_d512_vs_oracle():
     oloss, og = O.loss_and_grads(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"])
     errs = grad_errors(grads, og)
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
-    print("train step d=512: loss %.6f vs %.6f; worst grad errors: %s" % (loss, oloss, worst))
+    print("train step d=512: loss %.6f vs %.6f; median %.2e worst grad errors: %s"
+          % (loss, oloss, float(np.median(list(errs.values()))), worst))
     assert abs(loss - oloss) <= 5e-3 * abs(oloss)
-    assert max(errs.values()) < 2e-2, worst
+    assert max(errs.values()) < 3e-2 and float(np.median(list(errs.values()))) < 8e-3, worst
+    _vs_f16_contract(grads, (sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"]), "d=512")

@@ -27,7 +27,13 @@ def grad_errors(grads, ref):
     for k, r in ref.items():
         r = r.detach().double().cpu()
         g = grads[k].detach().double().cpu()
-        out[k] = float((g - r).norm() / max(float(r.norm()), floor * np.sqrt(r.numel())))
+        den = max(float(r.norm()), floor * np.sqrt(r.numel()))
+        if k.endswith("linears.1.bias"):
+            # the key-projection bias has an analytically ZERO gradient (softmax is invariant to a per-query
+            # constant); what every implementation returns is rounding noise -- measure it against its sibling,
+            # the value-projection bias gradient
+            den = max(den, float(ref[k.replace("linears.1.bias", "linears.2.bias")].double().norm()))
+        out[k] = float((g - r).norm() / den)
     return out
 
 
