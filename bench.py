@@ -227,6 +227,7 @@ def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over
                         "gbs": round(sum(r[2] for r in mine) / (msk * 1e-3) / 1e9, 1)}
             del g
         res["kernel_breakdown_one_step"] = kt
+        n_launches = len(rec)
         del rec
         for i in range(3):
             run(i)
@@ -241,7 +242,7 @@ def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over
         tokens = sum_over_ranks(sum(ntok[i % args.rot] for i in range(args.train_steps)) / args.train_steps)
         res.update({"tokens_per_s": tokens / (ms * 1e-3), "ms_per_step": ms, "steps": args.train_steps,
                     "mode": "eager launches" if args.train_eager else "CUDA graph replay (one launch per step)",
-                    "launches_per_step": len(rec), "launches_by_kernel": per, "params": n_params,
+                    "launches_per_step": n_launches, "launches_by_kernel": per, "params": n_params,
                     "allreduce_bytes_per_step": ts.flat.numel() * 4 if world > 1 else 0,
                     "loss": float(loss), "model_tflops": 3 * flops_forward(args.batch, args.tgt_len) * world / (ms * 1e-3) / 1e12,
                     "normaliser_note": "loss normalised by the global token counts of rotation slot 0 (fixed in the "

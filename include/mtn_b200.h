@@ -290,6 +290,8 @@ int mtn_cast_colsum(const void *src, int src_is_f16, int ld_src, void *dst_f16, 
  * (S = 1 for an all-zero or non-finite gradient) and resets the slot.                                   */
 int mtn_grad_absmax(const float *x, size_t n, uint32_t *slot, void *stream);
 int mtn_grad_scale(uint32_t *slot, float *scale2, void *stream);
+/* Stream-ordered zero fill (cudaMemsetAsync) of a gradient accumulation buffer. */
+int mtn_zero(void *p, size_t bytes, void *stream);
 /* y = (accumulate ? y : 0) + x * alpha[0]: un-scales an input gradient leaving the backward pass.  n % 4 == 0. */
 int mtn_scale_f32(const float *x, const float *alpha, float *y, size_t n, int accumulate, void *stream);
 

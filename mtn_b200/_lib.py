@@ -150,6 +150,7 @@ SYMBOLS = {
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_grad_absmax": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mtn_grad_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "mtn_scale_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "mtn_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdArgs), C.c_void_p]),
     "mtn_embed_bwd": (C.c_int, [C.POINTER(EmbedBwdArgs), C.c_void_p]),
@@ -213,8 +214,31 @@ def _launch(name, flops, nbytes, fn, keep=()):
     check(rc)
 
 
+# Launch-stream override: kernels go to STREAM (a torch.cuda.Stream) while PyTorch's current stream -- and with it
+# the caching allocator's pool -- stays the caller's.  Buffers are therefore always allocated stream-ordered on the
+# caller's stream and side streams only launch kernels (the engines join every side stream before they return).
+STREAM = None
+
+
+class on_stream(object):
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        global STREAM
+        self.prev, STREAM = STREAM, self.stream
+
+    def __exit__(self, *exc):
+        global STREAM
+        STREAM = self.prev
+
+
+def launch_stream():
+    return STREAM if STREAM is not None else torch.cuda.current_stream()
+
+
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(launch_stream().cuda_stream)
 
 
 def ptr(t):
@@ -537,6 +561,14 @@ def grad_scale(tensors):
                 lambda tc=tc: lib().mtn_grad_absmax(ptr(tc), tc.numel(), ptr(slot), stream_ptr()), keep=(tc, slot))
     _launch("grad_scale", 0, 16, lambda: lib().mtn_grad_scale(ptr(slot), ptr(out), stream_ptr()), keep=(slot, out))
     return out
+
+
+def zero(t):
+    """Stream-ordered zero fill of a contiguous tensor on the launch stream."""
+    assert t.is_contiguous() and t.is_cuda
+    n = t.numel() * t.element_size()
+    _launch("zero", 0, n, lambda: lib().mtn_zero(ptr(t), n, stream_ptr()), keep=(t,))
+    return t
 
 
 def scale_f32(x, alpha, y, accumulate=False):

@@ -208,7 +208,7 @@ __global__ void layernorm_bwd_generic_kernel(const LnBwdParams p, int d) {
 // colsum[c] += alpha * sum_rows (src * scale [masked]).  TIn = float or __half; dst16 / colsum optional.
 // Block (32 x 8): 32 eight-column vectors x 8 row lanes, ROWS_PER_BLOCK rows per block.
 // ----------------------------------------------------------------------------
-constexpr int CC_ROWS_PER_BLOCK = 64;
+constexpr int CC_ROWS_PER_BLOCK = 32;
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
@@ -236,24 +236,33 @@ __global__ void __launch_bounds__(256)
   const float sc = scale ? __ldg(scale) : 1.f;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int r_end = active ? min(rows, (int)(blockIdx.y + 1) * CC_ROWS_PER_BLOCK) : 0;
-  for (int r = blockIdx.y * CC_ROWS_PER_BLOCK + threadIdx.y; r < r_end; r += 8) {
-    float v[8];
-    load8(src + (size_t)r * ld_src + 8 * vc, v);
-    if (relu_mask != nullptr) {
-      float m[8];
-      load8(relu_mask + (size_t)r * ld_mask + 8 * vc, m);
+  const int r0 = blockIdx.y * CC_ROWS_PER_BLOCK + threadIdx.y;
+  constexpr int U = CC_ROWS_PER_BLOCK / 8;  // rows per thread, all loads issued before any use
+  float v[U][8], m[U][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+  for (int u = 0; u < U; ++u) {
+    const int r = r0 + 8 * u;
+    if (r < r_end) {
+      load8(src + (size_t)r * ld_src + 8 * vc, v[u]);
+      if (relu_mask != nullptr) load8(relu_mask + (size_t)r * ld_mask + 8 * vc, m[u]);
     }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int r = r0 + 8 * u;
+    if (r >= r_end) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[j] *= sc;
-      acc[j] += v[j];
+      float x = v[u][j];
+      if (relu_mask != nullptr) x = m[u][j] > 0.f ? x : 0.f;
+      x *= sc;
+      v[u][j] = x;
+      acc[j] += x;
     }
     if (dst != nullptr)
       *reinterpret_cast<uint4*>(dst + (size_t)r * ld_dst + 8 * vc) =
-          make_uint4(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3]), pack_f16x2_sat(v[4], v[5]),
-                     pack_f16x2_sat(v[6], v[7]));
+          make_uint4(pack_f16x2_sat(v[u][0], v[u][1]), pack_f16x2_sat(v[u][2], v[u][3]), pack_f16x2_sat(v[u][4], v[u][5]),
+                     pack_f16x2_sat(v[u][6], v[u][7]));
   }
   if (colsum != nullptr) {
     const float al = alpha ? __ldg(alpha) : 1.f;
@@ -547,6 +556,13 @@ extern "C" int mtn_grad_absmax(const float* x, size_t n, uint32_t* slot, void* s
   if (blocks > 1184) blocks = 1184;
   MTN_CHECK_CUDA(launch_kernel(absmax_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), x, n4,
                                reinterpret_cast<unsigned*>(slot)));
+  return MTN_OK;
+}
+
+extern "C" int mtn_zero(void* p, size_t bytes, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(p != nullptr, MTN_E_ARG, "zero: NULL pointer");
+  MTN_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream)));
   return MTN_OK;
 }
 

@@ -18,6 +18,13 @@ All intermediate gradients are multiplied by a power of two S chosen on the devi
 (parameter and input gradients) is multiplied by 1/S in the kernel that produces it.  No host synchronisation,
 so forward + backward can be captured in a CUDA graph.
 
+Streams.  Forward: each modality's Query-Aware Auto-Encoder chain (target-independent, mtn.py:209-213) runs on its
+own side stream next to the target path, as in the inference engine.  Backward: the target chain is the critical
+path on the caller's stream; every weight-gradient GEMM (nothing downstream reads it) goes to a dedicated stream,
+and each modality's QAE chain runs on its side stream as soon as the target layer that feeds it is done.  Side
+streams only LAUNCH: every buffer is allocated stream-ordered on the caller's stream and kept alive until the
+streams are joined at the end of the pass.
+
 PyTorch autograd only connects this Function with the embedding / encoder / generator Functions around it
 (``mtn_b200/autograd.py``); no arithmetic of the path runs in PyTorch.
 """
@@ -47,6 +54,14 @@ class DecoderTrainer(object):
     def __init__(self, decoder):
         self.dec = decoder
         self._packed = PackedWeights()
+
+    # ------------------------------------------------------------------ streams
+    def _streams(self, M, dev):
+        if getattr(self, "_side", None) is None or len(self._side) != M or self._side_dev != dev:
+            self._side = [torch.cuda.Stream(device=dev) for _ in range(M)]
+            self._wstream = torch.cuda.Stream(device=dev)
+            self._side_dev = dev
+        return self._side, self._wstream
 
     # ------------------------------------------------------------------ parameters
     def param_list(self):
@@ -131,13 +146,18 @@ class DecoderTrainer(object):
             return m16, out
 
         ctx = {"W": W, "B": B, "T": T, "La": La, "ae_features": ae_features, "ae_shared": None}
-        his16, kv_his = hoisted(his, W["kv_his"])
-        cap16, kv_cap = hoisted(cap, W["kv_cap"])
-        q16, kv_q = hoisted(qm, W["kv_q"])
+        main = torch.cuda.current_stream()
+        side, _ = self._streams(M, dev)
         b_his, b_cap, b_q = bits(his_mask), bits(cap_mask), bits(q_mask)
         b_ae = b_q if ae_features == "query" else b_cap
-        ctx["mem16"] = {"his": his16, "cap": cap16, "src": q16}
-        ctx["mem_shape"] = {"his": his.shape, "cap": cap.shape, "src": qm.shape}
+        b_vids = [bits(vid_mask[i]) for i in range(M)]
+        vid_c = [v.contiguous() for v in vid_ft]
+        ae_src = []
+        for i in range(M):
+            src = ae_ft[i] if isinstance(ae_ft, (list, tuple)) else (ae_ft if ae_ft is not None else ae_default)
+            ae_src.append(src.contiguous().view(B * La, d))
+        for st in side:                     # fork: everything above (mask packing, input copies) is visible
+            st.wait_stream(main)
 
         # ---- Query-Aware Auto-Encoder branch (mtn.py:209-213), all layers, per modality
         qae_tapes, kv_ae, ae16s, ae_outs, vid16s = [], [], [], [], []
@@ -145,38 +165,45 @@ class DecoderTrainer(object):
             ctx["ae_shared"] = None
         else:
             ctx["ae_shared"] = "given" if ae_ft is not None else ("src" if ae_features == "query" else "cap")
+        ev_ae = [[torch.cuda.Event() for _ in range(M)] for _ in range(N)]
         for i in range(M):
-            Lv = vid_ft[i].shape[1]
-            v16, kv_vid = hoisted(vid_ft[i], W["kv_vid"][i])
-            vid16s.append(v16)
-            b_vid = bits(vid_mask[i])
-            src = ae_ft[i] if isinstance(ae_ft, (list, tuple)) else (ae_ft if ae_ft is not None else ae_default)
-            ae = src.contiguous().view(B * La, d)
-            tape, kvs, a16s = [], [], []
-            for l in range(N):
-                Lw = W["layers"][l]
-                c0 = 4 + 4 * i
-                ae = self._attn_fwd(tape, ae, Lw["ln"][c0], Lw["ae_self"][i], B, La, La, None, 0, 0, b_ae,
-                                    ("ae_self", l, i, c0))
-                ae = self._attn_fwd(tape, ae, Lw["ln"][c0 + 1], Lw["ae_vid"][i], B, La, Lv, kv_vid, l * 2 * d,
-                                    l * 2 * d + d, b_vid, ("ae_vid", l, i, c0 + 1))
-                ae, a16 = self._ffn_fwd(tape, ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], ("ae_ffn", l, i, c0 + 2), want16=True)
-                A2 = Lw["ae_attn"][i]
-                kv = torch.empty(B * La, 2 * d, dtype=f16, device=dev)
-                _lib.linear(a16, A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=kv)
-                kvs.append(kv)
-                a16s.append(a16)
-            out = torch.empty(B * La, d, dtype=torch.float32, device=dev)
-            nrm = W["ae_norm"][i]
-            _lib.layernorm(ae, nrm[0], nrm[1], nrm[2], out_f32=out)
-            tape.append(("norm", dict(x_in=ae, ln=nrm, names=("ae_norm", i))))
-            qae_tapes.append(tape)
-            kv_ae.append(kvs)
-            ae16s.append(a16s)
-            ae_outs.append(out.view(B, La, d))
+            with _lib.on_stream(side[i]):
+                Lv = vid_ft[i].shape[1]
+                v16, kv_vid = hoisted(vid_c[i], W["kv_vid"][i])
+                vid16s.append(v16)
+                b_vid = b_vids[i]
+                ae = ae_src[i]
+                tape, kvs, a16s = [], [], []
+                for l in range(N):
+                    Lw = W["layers"][l]
+                    c0 = 4 + 4 * i
+                    ae = self._attn_fwd(tape, ae, Lw["ln"][c0], Lw["ae_self"][i], B, La, La, None, 0, 0, b_ae,
+                                        ("ae_self", l, i, c0))
+                    ae = self._attn_fwd(tape, ae, Lw["ln"][c0 + 1], Lw["ae_vid"][i], B, La, Lv, kv_vid, l * 2 * d,
+                                        l * 2 * d + d, b_vid, ("ae_vid", l, i, c0 + 1))
+                    ae, a16 = self._ffn_fwd(tape, ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], ("ae_ffn", l, i, c0 + 2), want16=True)
+                    A2 = Lw["ae_attn"][i]
+                    kv = torch.empty(B * La, 2 * d, dtype=f16, device=dev)
+                    _lib.linear(a16, A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=kv)
+                    kvs.append(kv)
+                    a16s.append(a16)
+                    ev_ae[l][i].record(side[i])      # layer l's K/V of ae_i is ready for the target path
+                out = torch.empty(B * La, d, dtype=torch.float32, device=dev)
+                nrm = W["ae_norm"][i]
+                _lib.layernorm(ae, nrm[0], nrm[1], nrm[2], out_f32=out)
+                tape.append(("norm", dict(x_in=ae, ln=nrm, names=("ae_norm", i))))
+                qae_tapes.append(tape)
+                kv_ae.append(kvs)
+                ae16s.append(a16s)
+                ae_outs.append(out.view(B, La, d))
         ctx["qae_tapes"], ctx["ae16"], ctx["vid16"] = qae_tapes, ae16s, vid16s
 
-        # ---- target path
+        # ---- text memories' hoisted K/V and the target path on the caller's stream
+        his16, kv_his = hoisted(his, W["kv_his"])
+        cap16, kv_cap = hoisted(cap, W["kv_cap"])
+        q16, kv_q = hoisted(qm, W["kv_q"])
+        ctx["mem16"] = {"his": his16, "cap": cap16, "src": q16}
+        ctx["mem_shape"] = {"his": his.shape, "cap": cap.shape, "src": qm.shape}
         tm = tgt_mask
         if tm is not None and tm.dim() == 4:
             tm = tm[:, 0]
@@ -197,6 +224,7 @@ class DecoderTrainer(object):
             for c, (name, kvm, bm, Lm) in enumerate(order):
                 xs = self._attn_fwd(tape, xs, Lw["ln"][2 + c], Lw[name], B, T, Lm, kvm, kc, vc, bm, (name, l, 0, 2 + c))
             for i in range(M):
+                main.wait_event(ev_ae[l][i])
                 xs = self._attn_fwd(tape, xs, Lw["ln"][7 + 4 * i], Lw["ae_attn"][i], B, T, La, kv_ae[i][l], 0, d, b_ae,
                                     ("ae_attn", l, i, 7 + 4 * i))
             xs, _ = self._ffn_fwd(tape, xs, Lw["ln"][4 + 4 * M], Lw["ffn"], ("ffn", l, 0, 4 + 4 * M))
@@ -204,6 +232,8 @@ class DecoderTrainer(object):
         _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=out)
         tape.append(("norm", dict(x_in=xs, ln=W["norm"], names=("norm",))))
         ctx["tape"] = tape
+        for st in side:                     # join
+            main.wait_stream(st)
         return out.view(B, T, d), ae_outs, ctx
 
     # ------------------------------------------------------------------ gradient buffers
@@ -277,15 +307,32 @@ class DecoderTrainer(object):
         return G, per
 
     # ------------------------------------------------------------------ backward building blocks
+    # `wq` collects the weight-gradient GEMMs of a site as closures: nothing downstream reads them, so `_flush`
+    # launches them on the dedicated wgrad stream once the site's operands are complete.
     @staticmethod
-    def _ln_bwd(t, dy, dres, dx, gab, invS, dy_scale=None):
+    def _ln_bwd(t, dy, dres, dx, gab, invS, dy_scale=None, dx_alpha=None):
         ln = t["ln"]
         _lib.layernorm_bwd(t["x_in"], ln[0], ln[2], dy, dx, dres=dres, da_2=gab[0], db_2=gab[1], dy_scale=dy_scale,
                            param_alpha=invS)
 
-    def _attn_bwd(self, t, dx, G, invS, dkv):
+    def _flush(self, bk, wq):
+        """Launch the collected weight-gradient GEMMs on the wgrad stream, after everything issued so far on the
+        launch stream (their operands).  The closures keep their operand tensors alive until the final join."""
+        if not wq:
+            return
+        ev = torch.cuda.Event()
+        ev.record(_lib.launch_stream())
+        bk["ws"].wait_event(ev)
+        with _lib.on_stream(bk["ws"]):
+            for fn in wq:
+                fn()
+        bk["keep"].extend(wq)
+        del wq[:]
+
+    def _attn_bwd(self, bk, t, dx, dkv):
         """dx: [rows, d] f32 scaled residual-stream gradient at the site's OUTPUT; updated in place to the
         gradient at its input.  dkv: (dk view, dv view) f16 destination for cross sites (hoisted columns)."""
+        G, invS, wq = bk["G"], bk["invS"], []
         A = t["A"]
         B, Lq, Lk, h, dk_ = t["B"], t["Lq"], t["Lk"], A["h"], A["d_k"]
         rows, d = dx.shape
@@ -298,11 +345,11 @@ class DecoderTrainer(object):
         _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS)
         do16 = torch.empty(rows, d, dtype=f16, device=dev)
         _lib.linear_dgrad(dx16, A["w_o"], out_f16=do16)
-        _lib.linear_wgrad(dx16, t["o16"], G[(gk, l, "wo")], alpha=invS)
+        wq.append(lambda: _lib.linear_wgrad(dx16, t["o16"], G[(gk, l, "wo")], alpha=invS))
         # ---- attention core
         delta = torch.empty(B, h, Lq, dtype=torch.float32, device=dev)
         _lib.attn_delta(do16, t["o16"], B, Lq, h, dk_, delta)
-        dq32 = torch.zeros(rows, d, dtype=torch.float32, device=dev)
+        dq32 = _lib.zero(torch.empty(rows, d, dtype=torch.float32, device=dev))
         if t["self_attn"]:
             dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
             dkd, dvd = dqkv[:, d:2 * d], dqkv[:, 2 * d:]
@@ -317,17 +364,20 @@ class DecoderTrainer(object):
             _lib.cast_colsum(dq32, dst_f16=dqkv[:, :d], colsum=gb[:d], alpha=invS)
             _lib.cast_colsum(dqkv[:, d:], colsum=gb[d:], alpha=invS)
             _lib.linear_dgrad(dqkv, A["w_qkv"], out_f32=dxn)
-            _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS)
+            wq.append(lambda: _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS))
         else:
             dq16 = torch.empty(rows, d, dtype=f16, device=dev)
             wq_key, bq_key = ("wq", "bq") if (gk, l, "wq") in G else ("wqkv", "bqkv")
             gw, gb = G[(gk, l, wq_key)], G[(gk, l, bq_key)]
             _lib.cast_colsum(dq32, dst_f16=dq16, colsum=gb[:d], alpha=invS)
             _lib.linear_dgrad(dq16, A["w_qkv"][:d], out_f32=dxn)
-            _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS)
+            wq.append(lambda: _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS))
+        self._flush(bk, wq)
         self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS)
+        bk["keep"].append((dq32, delta, do16, dxn))
 
-    def _ffn_bwd(self, t, dx, G, invS):
+    def _ffn_bwd(self, bk, t, dx):
+        G, invS, wq = bk["G"], bk["invS"], []
         Fw = t["Fw"]
         rows, d = dx.shape
         dev = dx.device
@@ -338,23 +388,43 @@ class DecoderTrainer(object):
         _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS)
         dhid = torch.empty(rows, Fw["w_1"].shape[0], dtype=f16, device=dev)
         _lib.linear_dgrad(dx16, Fw["w_2"], relu_mask=t["hid"], out_f16=dhid)        # through the ReLU (mtn.py:280)
-        _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS)
-        _lib.cast_colsum(dhid, colsum=G[(gk, l, "b1")], alpha=invS)
+        wq.append(lambda: _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS))
+        wq.append(lambda: _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS))
+        wq.append(lambda: _lib.cast_colsum(dhid, colsum=G[(gk, l, "b1")], alpha=invS))   # bias gradient: off the critical path too
+        self._flush(bk, wq)
         dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
         _lib.linear_dgrad(dhid, Fw["w_1"], out_f32=dxn)
-        _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS)
         self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS)
+        bk["keep"].append(dxn)
+
+    def _mem_bwd(self, bk, dkv, mem16, w_kv, gw, gb):
+        """Backward of a hoisted memory K/V projection: bias gradient, weight gradient, memory gradient."""
+        invS = bk["invS"]
+        wq = [lambda: _lib.cast_colsum(dkv, colsum=gb, alpha=invS), lambda: _lib.linear_wgrad(dkv, mem16, gw, alpha=invS)]
+        self._flush(bk, wq)
+        dmem = torch.empty(mem16.shape[0], mem16.shape[1], dtype=torch.float32, device=dkv.device)
+        _lib.linear_dgrad(dkv, w_kv, alpha=invS, out_f32=dmem)
+        return dmem
+
+    @staticmethod
+    def _unscale(dx, invS):
+        """An input gradient leaves the Function: multiply by 1/S."""
+        out = torch.empty_like(dx)
+        _lib.scale_f32(dx, invS, out)
+        return out
 
     # ------------------------------------------------------------------ backward
     def backward(self, ctx, g_out, g_ae):
         """g_out: [B,T,d] f32 or None; g_ae: list of [B,La,d] f32 or None.  Returns (input_grads, per_param) with
-        input_grads = dict(x, his, cap, src, vid=[...], ae=[...] or None)."""
+        input_grads = dict(x, his, cap, src, vid=[...], ae=[...])."""
         W = ctx["W"]
         d, N, M = W["d"], W["N"], W["M"]
         B, T, La = ctx["B"], ctx["T"], ctx["La"]
         tape = ctx["tape"]
         dev = tape[0][1]["x_in"].device
         f16 = torch.float16
+        main = torch.cuda.current_stream()
+        side, ws = self._streams(M, dev)
         G, per = self._grad_views(dev)
         if g_out is None:
             g_out = torch.zeros(B, T, d, dtype=torch.float32, device=dev)
@@ -363,20 +433,24 @@ class DecoderTrainer(object):
         g_ae = [g.contiguous().float() for g in g_ae]
         S2 = _lib.grad_scale([g_out] + g_ae)
         S, invS = S2[0:1], S2[1:2]
+        bk = {"G": G, "invS": invS, "ws": ws, "keep": []}
 
         # hoisted dK/dV destinations, one per memory: every layer fills its own columns
         rows_mem = {k: v.shape[0] for k, v in ctx["mem16"].items()}
         dkv_mem = {k: torch.empty(r, N * 2 * d, dtype=f16, device=dev) for k, r in rows_mem.items()}
         dkv_vid = [torch.empty(v.shape[0], N * 2 * d, dtype=f16, device=dev) for v in ctx["vid16"]]
         dkv_ae = [[torch.empty(B * La, 2 * d, dtype=f16, device=dev) for _ in range(N)] for _ in range(M)]
+        ev_kv = [[torch.cuda.Event() for _ in range(M)] for _ in range(N)]
+        for st in side + [ws]:              # fork: gradient arena zeroed, scale computed
+            st.wait_stream(main)
 
-        # ---- target path, last sublayer first
+        # ---- target path (critical path, caller's stream), last sublayer first
         kind, t = tape[-1]
         dx = torch.empty(B * T, d, dtype=torch.float32, device=dev)
         self._ln_bwd(t, g_out.view(B * T, d), None, dx, G[("norm",)], invS, dy_scale=S)        # mtn.py:164
         for kind, t in reversed(tape[:-1]):
             if kind == "ffn":
-                self._ffn_bwd(t, dx, G, invS)
+                self._ffn_bwd(bk, t, dx)
                 continue
             key, l, i, c = t["names"]
             if key == "self":
@@ -387,55 +461,50 @@ class DecoderTrainer(object):
             else:
                 buf = dkv_mem[key]
                 dkv = (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d])
-            self._attn_bwd(t, dx, G, invS, dkv)
+            self._attn_bwd(bk, t, dx, dkv)
+            if key == "ae_attn":
+                ev_kv[l][i].record(main)    # dK/dV of layer l's ae_i memory are complete: its QAE chain may proceed
         grads = {"x": self._unscale(dx, invS).view(B, T, d)}
-
-        # ---- Query-Aware Auto-Encoder branch
-        grads["ae"], grads["vid"] = [], []
-        for i in range(M):
-            qt = ctx["qae_tapes"][i]
-            kind, t = qt[-1]
-            dae = torch.empty(B * La, d, dtype=torch.float32, device=dev)
-            self._ln_bwd(t, g_ae[i].view(B * La, d), None, dae, G[("ae_norm", i)], invS, dy_scale=S)  # mtn.py:162-163
-            for kind, t in reversed(qt[:-1]):
-                key, l, _, c = t["names"]
-                if kind == "ffn":
-                    # the layer's output ae_i^l is also the memory of the target's auto_encoder_attn[i] (mtn.py:215):
-                    # add the gradient that came back through its K/V projection
-                    A2 = W["layers"][l]["ae_attn"][i]
-                    gk = ("ae_attn", i)
-                    _lib.cast_colsum(dkv_ae[i][l], colsum=G[(gk, l, "bqkv")][d:], alpha=invS)
-                    _lib.linear_dgrad(dkv_ae[i][l], A2["w_qkv"][d:], addend=dae, out_f32=dae)
-                    _lib.linear_wgrad(dkv_ae[i][l], ctx["ae16"][i][l], G[(gk, l, "wqkv")][d:], alpha=invS)
-                    self._ffn_bwd(t, dae, G, invS)
-                elif key == "ae_vid":
-                    buf = dkv_vid[i]
-                    self._attn_bwd(t, dae, G, invS, (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d]))
-                else:
-                    self._attn_bwd(t, dae, G, invS, None)
-            grads["ae"].append(self._unscale(dae, invS).view(B, La, d))
-            # hoisted video K/V projection of modality i
-            gk = ("ae_vid", i)
-            grads["vid"].append(self._mem_bwd(dkv_vid[i], ctx["vid16"][i], W["kv_vid"][i][0], G[(gk, "wkv")], G[(gk, "bkv")],
-                                              invS).view(B, -1, d))
         for name in ("his", "cap", "src"):
             gk = (name, 0)
-            grads[name] = self._mem_bwd(dkv_mem[name], ctx["mem16"][name], W["kv_" + ("q" if name == "src" else name)][0],
-                                        G[(gk, "wkv")], G[(gk, "bkv")], invS).view(ctx["mem_shape"][name])
+            grads[name] = self._mem_bwd(bk, dkv_mem[name], ctx["mem16"][name],
+                                        W["kv_" + ("q" if name == "src" else name)][0], G[(gk, "wkv")],
+                                        G[(gk, "bkv")]).view(ctx["mem_shape"][name])
+
+        # ---- Query-Aware Auto-Encoder branch: one side stream per modality
+        grads["ae"], grads["vid"] = [], []
+        for i in range(M):
+            with _lib.on_stream(side[i]):
+                qt = ctx["qae_tapes"][i]
+                kind, t = qt[-1]
+                dae = torch.empty(B * La, d, dtype=torch.float32, device=dev)
+                self._ln_bwd(t, g_ae[i].view(B * La, d), None, dae, G[("ae_norm", i)], invS, dy_scale=S)   # mtn.py:162-163
+                for kind, t in reversed(qt[:-1]):
+                    key, l, _, c = t["names"]
+                    if kind == "ffn":
+                        # the layer's output ae_i^l is also the memory of the target's auto_encoder_attn[i]
+                        # (mtn.py:215): add the gradient that came back through its K/V projection
+                        side[i].wait_event(ev_kv[l][i])
+                        A2 = W["layers"][l]["ae_attn"][i]
+                        gk = ("ae_attn", i)
+                        buf, a16 = dkv_ae[i][l], ctx["ae16"][i][l]
+                        gw, gb = G[(gk, l, "wqkv")][d:], G[(gk, l, "bqkv")][d:]
+                        _lib.linear_dgrad(buf, A2["w_qkv"][d:], addend=dae, out_f32=dae)
+                        self._flush(bk, [lambda buf=buf, gb=gb: _lib.cast_colsum(buf, colsum=gb, alpha=invS),
+                                         lambda buf=buf, a16=a16, gw=gw: _lib.linear_wgrad(buf, a16, gw, alpha=invS)])
+                        self._ffn_bwd(bk, t, dae)
+                    elif key == "ae_vid":
+                        buf = dkv_vid[i]
+                        self._attn_bwd(bk, t, dae, (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d]))
+                    else:
+                        self._attn_bwd(bk, t, dae, None)
+                grads["ae"].append(self._unscale(dae, invS).view(B, La, d))
+                bk["keep"].append(dae)
+                gk = ("ae_vid", i)              # hoisted video K/V projection of modality i
+                grads["vid"].append(self._mem_bwd(bk, dkv_vid[i], ctx["vid16"][i], W["kv_vid"][i][0], G[(gk, "wkv")],
+                                                  G[(gk, "bkv")]).view(B, -1, d))
+        for st in side + [ws]:              # join
+            main.wait_stream(st)
+        bk["keep"].append((dkv_mem, dkv_vid, dkv_ae, dx, g_out, g_ae, S2))
+        ctx["_bwd_keep"] = bk["keep"]       # released with the tape by the caller, after the join has been enqueued
         return grads, per
-
-    @staticmethod
-    def _unscale(dx, invS):
-        """An input gradient leaves the Function: multiply by 1/S."""
-        out = torch.empty_like(dx)
-        _lib.scale_f32(dx, invS, out)
-        return out
-
-    @staticmethod
-    def _mem_bwd(dkv, mem16, w_kv, gw, gb, invS):
-        """Backward of a hoisted memory K/V projection: bias gradient, weight gradient, memory gradient."""
-        _lib.cast_colsum(dkv, colsum=gb, alpha=invS)
-        _lib.linear_wgrad(dkv, mem16, gw, alpha=invS)
-        dmem = torch.empty(mem16.shape[0], mem16.shape[1], dtype=torch.float32, device=dkv.device)
-        _lib.linear_dgrad(dkv, w_kv, alpha=invS, out_f32=dmem)
-        return dmem
