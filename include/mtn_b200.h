@@ -304,6 +304,9 @@ typedef struct MtnLayerNormBwdArgs {
   const float *dy; const float *dy_scale;
   const float *dres; float *dx;
   float *da_2; float *db_2; const float *param_alpha;
+  /* optional fused outputs for the NEXT backward step (the sublayer whose output x is): an f16 copy of dx (its
+   * GEMM operand) and dx_colsum[c] += param_alpha * sum_rows dx[:, c] (its output-bias gradient)            */
+  void *dx_f16; float *dx_colsum;
 } MtnLayerNormBwdArgs;
 int mtn_layernorm_bwd(const MtnLayerNormBwdArgs *args, void *stream);
 

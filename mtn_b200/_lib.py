@@ -65,7 +65,8 @@ class LinearWgradArgs(C.Structure):
 class LayerNormBwdArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("a_2", C.c_void_p), ("eps", C.c_float), ("rows", C.c_int), ("d", C.c_int),
                 ("dy", C.c_void_p), ("dy_scale", C.c_void_p), ("dres", C.c_void_p), ("dx", C.c_void_p),
-                ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p)]
+                ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p),
+                ("dx_f16", C.c_void_p), ("dx_colsum", C.c_void_p)]
 
 
 class EmbedBwdArgs(C.Structure):
@@ -580,7 +581,8 @@ def scale_f32(x, alpha, y, accumulate=False):
             keep=(x, alpha, y))
 
 
-def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale=None, param_alpha=None):
+def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale=None, param_alpha=None, dx_f16=None,
+                  dx_colsum=None):
     """dx = dres + dLN(dy * dy_scale); da_2 / db_2 += param_alpha * (...).  x, dy, dx: [rows, d] f32 contiguous."""
     for t, n in ((x, "x"), (a_2, "a_2"), (dy, "dy"), (dx, "dx"), (dres, "dres"), (da_2, "da_2"), (db_2, "db_2"),
                  (dy_scale, "dy_scale"), (param_alpha, "param_alpha")):
@@ -598,9 +600,16 @@ def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale
     a.da_2 = da_2.data_ptr() if da_2 is not None else None
     a.db_2 = db_2.data_ptr() if db_2 is not None else None
     a.param_alpha = param_alpha.data_ptr() if param_alpha is not None else None
-    _launch("layernorm_bwd", 0, rows * d * (12 + (4 if dres is not None else 0)),
+    _req(dx_f16, torch.float16, "dx_f16"); _req(dx_colsum, torch.float32, "dx_colsum")
+    if dx_f16 is not None:
+        assert dx_f16.is_contiguous() and dx_f16.numel() == x.numel()
+        a.dx_f16 = dx_f16.data_ptr()
+    if dx_colsum is not None:
+        assert dx_colsum.is_contiguous() and dx_colsum.numel() == d
+        a.dx_colsum = dx_colsum.data_ptr()
+    _launch("layernorm_bwd", 0, rows * d * (12 + (4 if dres is not None else 0) + (2 if dx_f16 is not None else 0)),
             lambda: lib().mtn_layernorm_bwd(C.byref(a), stream_ptr()),
-            keep=(x, a_2, dy, dx, dres, da_2, db_2, dy_scale, param_alpha))
+            keep=(x, a_2, dy, dx, dres, da_2, db_2, dy_scale, param_alpha, dx_f16, dx_colsum))
 
 
 def embed_bwd(ids, lut, pe, scale, dy, dlut, ln=None, da_2=None, db_2=None, param_alpha=None):

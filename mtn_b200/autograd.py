@@ -231,5 +231,7 @@ class DecoderFn(Function):
             g_ae_in = [tot] if ctx.n_ae == 1 else []
         params = ctx.trainer.param_list()
         assert len(params) == ctx.n_params
+        # per is None: the gradients were accumulated straight into the attached .grad arena
+        pg = tuple(per[id(p)] for p in params) if per is not None else (None,) * len(params)
         return (None, None, None, None, grads["x"], grads["his"], g_cap, g_qm) + tuple(grads["vid"]) + \
-            tuple(g_ae_in) + tuple(per[id(p)] for p in params)
+            tuple(g_ae_in) + pg

@@ -42,6 +42,8 @@ struct LnBwdParams {
   float* dlut;
   float* da; float* db;
   float eps; int rows; int has_ln;
+  __half* dx16;   // optional f16 copy of dx: the operand of the next backward GEMM
+  float* colsum;  // optional: += param_alpha * sum_rows dx  (bias gradient of the layer whose output this is)
 };
 
 template <int VPL, bool EMBED>
@@ -53,9 +55,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float dys = p.dy_scale ? __ldg(p.dy_scale) : 1.f;
   const float pal = p.param_alpha ? __ldg(p.param_alpha) : 1.f;
-  float4 da_acc[VPL], db_acc[VPL];
+  float4 da_acc[VPL], db_acc[VPL], cs_acc[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) da_acc[i] = db_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < VPL; ++i) da_acc[i] = db_acc[i] = cs_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int row = blockIdx.x * 8 + warp; row < p.rows; row += gridDim.x * 8) {
     float4 c[VPL], g[VPL];
@@ -143,19 +145,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         dxr[lane + 32 * i] = o;
+        if (p.dx16 != nullptr)
+          reinterpret_cast<uint2*>(p.dx16 + (size_t)row * D)[lane + 32 * i] =
+              make_uint2(pack_f16x2_sat(o.x, o.y), pack_f16x2_sat(o.z, o.w));
+        cs_acc[i].x += o.x; cs_acc[i].y += o.y; cs_acc[i].z += o.z; cs_acc[i].w += o.w;
       }
     }
   }
-  if (!p.has_ln || p.da == nullptr) return;
   // block reduction of the parameter-gradient partials (8 warps), then one atomic per column
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? p.da : (pass == 1 ? p.db : p.colsum);
+    if (dst == nullptr || (pass < 2 && !p.has_ln)) continue;  // uniform over the block
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
-      reinterpret_cast<float4*>(red + warp * D)[lane + 32 * i] = pass == 0 ? da_acc[i] : db_acc[i];
+      reinterpret_cast<float4*>(red + warp * D)[lane + 32 * i] = pass == 0 ? da_acc[i] : (pass == 1 ? db_acc[i] : cs_acc[i]);
     __syncthreads();
-    float* dst = pass == 0 ? p.da : p.db;
     for (int col = threadIdx.x; col < D; col += 256) {
       float t = 0.f;
 #pragma unroll
@@ -208,7 +214,7 @@ __global__ void layernorm_bwd_generic_kernel(const LnBwdParams p, int d) {
 // colsum[c] += alpha * sum_rows (src * scale [masked]).  TIn = float or __half; dst16 / colsum optional.
 // Block (32 x 8): 32 eight-column vectors x 8 row lanes, ROWS_PER_BLOCK rows per block.
 // ----------------------------------------------------------------------------
-constexpr int CC_ROWS_PER_BLOCK = 32;
+constexpr int CC_ROWS_PER_BLOCK = 64;
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
@@ -237,11 +243,13 @@ __global__ void __launch_bounds__(256)
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int r_end = active ? min(rows, (int)(blockIdx.y + 1) * CC_ROWS_PER_BLOCK) : 0;
   const int r0 = blockIdx.y * CC_ROWS_PER_BLOCK + threadIdx.y;
-  constexpr int U = CC_ROWS_PER_BLOCK / 8;  // rows per thread, all loads issued before any use
+  constexpr int U = 4;  // rows per thread and batch: all loads of a batch are issued before any use
   float v[U][8], m[U][8];
+#pragma unroll 1
+  for (int rb = r0; rb < r_end; rb += 8 * U) {
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int r = r0 + 8 * u;
+    const int r = rb + 8 * u;
     if (r < r_end) {
       load8(src + (size_t)r * ld_src + 8 * vc, v[u]);
       if (relu_mask != nullptr) load8(relu_mask + (size_t)r * ld_mask + 8 * vc, m[u]);
@@ -249,7 +257,7 @@ __global__ void __launch_bounds__(256)
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int r = r0 + 8 * u;
+    const int r = rb + 8 * u;
     if (r >= r_end) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -263,6 +271,7 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<uint4*>(dst + (size_t)r * ld_dst + 8 * vc) =
           make_uint4(pack_f16x2_sat(v[u][0], v[u][1]), pack_f16x2_sat(v[u][2], v[u][3]), pack_f16x2_sat(v[u][4], v[u][5]),
                      pack_f16x2_sat(v[u][6], v[u][7]));
+  }
   }
   if (colsum != nullptr) {
     const float al = alpha ? __ldg(alpha) : 1.f;
@@ -473,6 +482,7 @@ extern "C" int mtn_layernorm_bwd(const MtnLayerNormBwdArgs* a, void* stream) {
   LnBwdParams p = {};
   p.x = a->x; p.a2 = a->a_2; p.dy = a->dy; p.dy_scale = a->dy_scale; p.param_alpha = a->param_alpha;
   p.dres = a->dres; p.dx = a->dx; p.da = a->da_2; p.db = a->db_2; p.eps = a->eps; p.rows = a->rows; p.has_ln = 1;
+  p.dx16 = reinterpret_cast<__half*>(a->dx_f16); p.colsum = a->dx_colsum;
   const int d = a->d;
   const bool vec = (d == 128 || d == 256 || d == 512 || d == 1024) && aligned16(a->x) && aligned16(a->a_2) &&
                    aligned16(a->dy) && aligned16(a->dx) && (!a->dres || aligned16(a->dres));
@@ -488,7 +498,11 @@ extern "C" int mtn_layernorm_bwd(const MtnLayerNormBwdArgs* a, void* stream) {
   else if (vec && d == 256) MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<2, false>, dim3(blocks), dim3(256), 0, st, p));
   else if (vec && d == 512) MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<4, false>, dim3(blocks), dim3(256), 0, st, p));
   else if (vec && d == 1024) MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<8, false>, dim3(blocks), dim3(256), 0, st, p));
-  else MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_generic_kernel, dim3((a->rows + 7) / 8), dim3(256), 0, st, p, d));
+  else {
+    MTN_REQUIRE(a->dx_f16 == nullptr && a->dx_colsum == nullptr, MTN_E_SHAPE,
+                "layernorm_bwd: dx_f16 / dx_colsum need d in {128, 256, 512, 1024} and 16-byte aligned pointers");
+    MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_generic_kernel, dim3((a->rows + 7) / 8), dim3(256), 0, st, p, d));
+  }
   return MTN_OK;
 }
 

@@ -35,10 +35,10 @@ from .engine import PackedWeights
 
 
 class _Arena(object):
-    """One flat f32 buffer (a single memset) carved into gradient views."""
+    """A flat buffer carved into views (every view starts 16-byte aligned)."""
 
-    def __init__(self, n, device):
-        self.buf = torch.zeros(n, dtype=torch.float32, device=device)
+    def __init__(self, buf):
+        self.buf = buf
         self.off = 0
 
     def take(self, *shape):
@@ -46,7 +46,7 @@ class _Arena(object):
         for s in shape:
             n *= s
         v = self.buf[self.off:self.off + n].view(*shape)
-        self.off += (n + 3) // 4 * 4
+        self.off += (n + 7) // 8 * 8
         return v
 
 
@@ -54,6 +54,8 @@ class DecoderTrainer(object):
     def __init__(self, decoder):
         self.dec = decoder
         self._packed = PackedWeights()
+        self._arena = None          # flat f32 parameter arena + f16 operand arena (same layout)
+        self._grad = None           # optional persistent gradient arena (same layout) backing every .grad
 
     # ------------------------------------------------------------------ streams
     def _streams(self, M, dev):
@@ -67,9 +69,93 @@ class DecoderTrainer(object):
     def param_list(self):
         return list(self.dec.parameters())
 
+    def arena_numel(self):
+        return sum((p.numel() + 7) // 8 * 8 for p in self.dec.parameters())
+
+    def _ensure_arena(self):
+        """Flat parameter arena: every decoder parameter's storage becomes a view of ONE f32 buffer laid out like
+        the gradient arena ([Wq;Wk;Wv] contiguous per self-attention-like module, every layer's [Wk_l;Wv_l] of a
+        hoisted memory contiguous).  The f16 tensor-core operands of ALL parameters are then one cast kernel over
+        the arena, and every packed operand (w_qkv, hoisted K/V weights, ...) is a view -- no torch.cat, no
+        per-tensor casts.  state_dict keys / values are unchanged (parameters stay separate nn.Parameters)."""
+        params = self.param_list()
+        dev = params[0].device
+        ar = self._arena
+        if ar is not None and ar["dev"] == dev and all(p.data_ptr() == v.data_ptr() for p, v in zip(params, ar["views"])):
+            return ar
+        n = self.arena_numel()
+        flat32 = torch.zeros(n, dtype=torch.float32, device=dev)
+        P, per = self._carve(flat32)
+        views = []
+        with torch.no_grad():
+            for p in params:
+                v = per[id(p)]
+                v.copy_(p.data)
+                p.data = v
+                views.append(v)
+        flat16 = torch.empty(n, dtype=torch.float16, device=dev)
+        H, _ = self._carve(flat16)
+        self._arena = {"dev": dev, "flat32": flat32, "flat16": flat16, "P": P, "H": H, "views": views, "W": self._build_W(P, H)}
+        self._packed._key = None
+        return self._arena
+
+    def _build_W(self, P, H):
+        """The engine's weight dictionary (same structure as DecoderEngine.weights()) out of arena views: f16
+        operands from H, f32 biases / LayerNorm parameters from P."""
+        dec = self.dec
+        layers = dec.layers
+        M = len(layers[0].auto_encoder_vid_attn)
+        d = layers[0].size
+
+        def packed(key, l, m):
+            return {"w_qkv": H[(key, l, "wqkv")], "b_qkv": P[(key, l, "bqkv")], "w_o": H[(key, l, "wo")],
+                    "b_o": P[(key, l, "bo")], "h": m.h, "d_k": m.d_k}
+
+        def hoisted_site(key, l, m):     # only the query projection is used per site ([:d] of a [d, d] view is itself)
+            return {"w_qkv": H[(key, l, "wq")], "b_qkv": P[(key, l, "bq")], "w_o": H[(key, l, "wo")],
+                    "b_o": P[(key, l, "bo")], "h": m.h, "d_k": m.d_k}
+
+        def ffn(key, l):
+            return {"w_1": H[(key, l, "w1")], "b_1": P[(key, l, "b1")], "w_2": H[(key, l, "w2")], "b_2": P[(key, l, "b2")]}
+
+        W = {"M": M, "d": d, "N": len(layers), "layers": []}
+        for name, key in (("kv_his", ("his", 0)), ("kv_cap", ("cap", 0)), ("kv_q", ("src", 0))):
+            W[name] = (H[(key, "wkv")], P[(key, "bkv")])
+        W["kv_vid"] = [(H[(("ae_vid", i), "wkv")], P[(("ae_vid", i), "bkv")]) for i in range(M)]
+        for l, L in enumerate(layers):
+            W["layers"].append({
+                "self": packed(("self", 0), l, L.self_attn),
+                "his": hoisted_site(("his", 0), l, L.his_attn), "cap": hoisted_site(("cap", 0), l, L.cap_attn),
+                "src": hoisted_site(("src", 0), l, L.src_attn),
+                "ae_self": [packed(("ae_self", i), l, L.auto_encoder_self_attn[i]) for i in range(M)],
+                "ae_vid": [hoisted_site(("ae_vid", i), l, L.auto_encoder_vid_attn[i]) for i in range(M)],
+                "ae_attn": [packed(("ae_attn", i), l, L.auto_encoder_attn[i]) for i in range(M)],
+                "ae_ffn": [ffn(("ae_ffn", i), l) for i in range(M)],
+                "ffn": ffn(("ffn", 0), l),
+                "ln": [(P[("ln", l, c)][0], P[("ln", l, c)][1], s.norm.eps) for c, s in enumerate(L.sublayer)],
+            })
+        W["norm"] = (P[("norm",)][0], P[("norm",)][1], dec.norm.eps)
+        W["ae_norm"] = [(P[("ae_norm", i)][0], P[("ae_norm", i)][1], m.eps) for i, m in enumerate(dec.ae_norm)]
+        return W
+
     def weights(self):
-        """Tensor-core (f16) packs of the decoder's parameters, rebuilt when a parameter changes."""
-        return self.dec.engine.weights()
+        """Tensor-core (f16) operands of the decoder's parameters: ONE cast kernel over the parameter arena,
+        re-run when a parameter changed (optimizer step, load_state_dict)."""
+        ar = self._ensure_arena()
+
+        def build():
+            n = ar["flat32"].numel()
+            _lib.cast_f16(ar["flat32"].view(-1, 8), ar["flat16"].view(-1, 8))
+            return ar["W"]
+        return self._packed.get(self.param_list(), build)
+
+    def attach_grads(self, buf):
+        """Back every decoder parameter's ``.grad`` by a view of `buf` (f32, arena_numel() elements, arena layout):
+        the backward then accumulates straight into it -- no per-parameter autograd accumulation kernels."""
+        G, per = self._carve(buf)
+        for p in self.param_list():
+            p.grad = per[id(p)]
+        self._grad = {"buf": buf, "G": G, "per": per}
 
     # ------------------------------------------------------------------ forward building blocks (taped)
     @staticmethod
@@ -238,7 +324,18 @@ class DecoderTrainer(object):
 
     # ------------------------------------------------------------------ gradient buffers
     def _grad_views(self, dev):
-        """Flat gradient arena carved so that every GEMM of the backward writes one contiguous block:
+        """(G, per_param, direct): the gradient arena for one backward.  With ``attach_grads`` and every .grad
+        still being its view, gradients accumulate directly (direct=True, the Function returns None for the
+        parameters); otherwise a fresh zeroed arena whose views are handed to autograd."""
+        g = self._grad
+        if g is not None and g["buf"].device == dev and all(
+                p.grad is not None and p.grad.data_ptr() == g["per"][id(p)].data_ptr() for p in self.param_list()):
+            return g["G"], g["per"], True
+        G, per = self._carve(torch.zeros(self.arena_numel(), dtype=torch.float32, device=dev))
+        return G, per, False
+
+    def _carve(self, buf):
+        """Carve a flat buffer in the arena layout, so that every GEMM of the backward writes one contiguous block:
         [Wq;Wk;Wv] per self-attention-like module, all layers' [Wk_l;Wv_l] per hoisted memory.
         Returns (G, per_param) with per_param: id(parameter) -> view."""
         dec = self.dec
@@ -246,8 +343,7 @@ class DecoderTrainer(object):
         N = len(layers)
         M = len(layers[0].auto_encoder_vid_attn)
         d = layers[0].size
-        total = sum((p.numel() + 3) // 4 * 4 for p in dec.parameters())
-        ar = _Arena(total, dev)
+        ar = _Arena(buf)
         G, per = {}, {}
 
         def lin_views(m, idx, w, b):
@@ -310,10 +406,13 @@ class DecoderTrainer(object):
     # `wq` collects the weight-gradient GEMMs of a site as closures: nothing downstream reads them, so `_flush`
     # launches them on the dedicated wgrad stream once the site's operands are complete.
     @staticmethod
-    def _ln_bwd(t, dy, dres, dx, gab, invS, dy_scale=None, dx_alpha=None):
+    def _ln_bwd(t, dy, dres, dx, gab, invS, dy_scale=None, nxt=None):
+        """nxt = (dx16, bias_grad) of the sublayer processed next: the LayerNorm kernel also emits the f16 copy of
+        the updated residual gradient (that sublayer's GEMM operand) and its column sums (its output-bias gradient)."""
         ln = t["ln"]
         _lib.layernorm_bwd(t["x_in"], ln[0], ln[2], dy, dx, dres=dres, da_2=gab[0], db_2=gab[1], dy_scale=dy_scale,
-                           param_alpha=invS)
+                           param_alpha=invS, dx_f16=None if nxt is None else nxt[0],
+                           dx_colsum=None if nxt is None else nxt[1])
 
     def _flush(self, bk, wq):
         """Launch the collected weight-gradient GEMMs on the wgrad stream, after everything issued so far on the
@@ -329,9 +428,10 @@ class DecoderTrainer(object):
         bk["keep"].extend(wq)
         del wq[:]
 
-    def _attn_bwd(self, bk, t, dx, dkv):
+    def _attn_bwd(self, bk, t, dx, dkv, dx16=None, nxt=None):
         """dx: [rows, d] f32 scaled residual-stream gradient at the site's OUTPUT; updated in place to the
-        gradient at its input.  dkv: (dk view, dv view) f16 destination for cross sites (hoisted columns)."""
+        gradient at its input.  dkv: (dk view, dv view) f16 destination for cross sites (hoisted columns).
+        dx16: f16 copy of dx if the previous LayerNorm backward already produced it (and the b_o gradient)."""
         G, invS, wq = bk["G"], bk["invS"], []
         A = t["A"]
         B, Lq, Lk, h, dk_ = t["B"], t["Lq"], t["Lk"], A["h"], A["d_k"]
@@ -341,8 +441,9 @@ class DecoderTrainer(object):
         key, l, i, c = t["names"]
         gk = (key, i)
         # ---- output projection (mtn.py:267) + residual (mtn.py:127)
-        dx16 = torch.empty(rows, d, dtype=f16, device=dev)
-        _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS)
+        if dx16 is None:
+            dx16 = torch.empty(rows, d, dtype=f16, device=dev)
+            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS)
         do16 = torch.empty(rows, d, dtype=f16, device=dev)
         _lib.linear_dgrad(dx16, A["w_o"], out_f16=do16)
         wq.append(lambda: _lib.linear_wgrad(dx16, t["o16"], G[(gk, l, "wo")], alpha=invS))
@@ -373,10 +474,10 @@ class DecoderTrainer(object):
             _lib.linear_dgrad(dq16, A["w_qkv"][:d], out_f32=dxn)
             wq.append(lambda: _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS))
         self._flush(bk, wq)
-        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS)
+        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS, nxt=nxt)
         bk["keep"].append((dq32, delta, do16, dxn))
 
-    def _ffn_bwd(self, bk, t, dx):
+    def _ffn_bwd(self, bk, t, dx, dx16=None, nxt=None):
         G, invS, wq = bk["G"], bk["invS"], []
         Fw = t["Fw"]
         rows, d = dx.shape
@@ -384,8 +485,9 @@ class DecoderTrainer(object):
         f16 = torch.float16
         key, l, i, c = t["names"]
         gk = (key, i)
-        dx16 = torch.empty(rows, d, dtype=f16, device=dev)
-        _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS)
+        if dx16 is None:
+            dx16 = torch.empty(rows, d, dtype=f16, device=dev)
+            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS)
         dhid = torch.empty(rows, Fw["w_1"].shape[0], dtype=f16, device=dev)
         _lib.linear_dgrad(dx16, Fw["w_2"], relu_mask=t["hid"], out_f16=dhid)        # through the ReLU (mtn.py:280)
         wq.append(lambda: _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS))
@@ -394,7 +496,7 @@ class DecoderTrainer(object):
         self._flush(bk, wq)
         dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
         _lib.linear_dgrad(dhid, Fw["w_1"], out_f32=dxn)
-        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS)
+        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS, nxt=nxt)
         bk["keep"].append(dxn)
 
     def _mem_bwd(self, bk, dkv, mem16, w_kv, gw, gb):
@@ -425,7 +527,7 @@ class DecoderTrainer(object):
         f16 = torch.float16
         main = torch.cuda.current_stream()
         side, ws = self._streams(M, dev)
-        G, per = self._grad_views(dev)
+        G, per, direct = self._grad_views(dev)
         if g_out is None:
             g_out = torch.zeros(B, T, d, dtype=torch.float32, device=dev)
         g_ae = [g if g is not None else torch.zeros(B, La, d, dtype=torch.float32, device=dev) for g in g_ae]
@@ -445,12 +547,26 @@ class DecoderTrainer(object):
             st.wait_stream(main)
 
         # ---- target path (critical path, caller's stream), last sublayer first
+        def bias_of(entry):                 # output-bias gradient of a taped sublayer
+            knd, tt = entry
+            key, l, i, c = tt["names"]
+            return G[((key, i), l, "bo" if knd == "attn" else "b2")]
+
+        def handoff(seq, k, rows, fused=lambda entry: True):
+            """(dx16, bias gradient) the LayerNorm backward of seq[k] should produce for seq[k+1], or None."""
+            if k + 1 >= len(seq) or not fused(seq[k + 1]):
+                return None
+            return (torch.empty(rows, d, dtype=f16, device=dev), bias_of(seq[k + 1]))
+
         kind, t = tape[-1]
+        seq = list(reversed(tape[:-1]))
         dx = torch.empty(B * T, d, dtype=torch.float32, device=dev)
-        self._ln_bwd(t, g_out.view(B * T, d), None, dx, G[("norm",)], invS, dy_scale=S)        # mtn.py:164
-        for kind, t in reversed(tape[:-1]):
+        nxt = handoff(seq, -1, B * T)
+        self._ln_bwd(t, g_out.view(B * T, d), None, dx, G[("norm",)], invS, dy_scale=S, nxt=nxt)        # mtn.py:164
+        for k, (kind, t) in enumerate(seq):
+            dx16, nxt = (nxt[0] if nxt is not None else None), handoff(seq, k, B * T)
             if kind == "ffn":
-                self._ffn_bwd(bk, t, dx)
+                self._ffn_bwd(bk, t, dx, dx16, nxt)
                 continue
             key, l, i, c = t["names"]
             if key == "self":
@@ -461,7 +577,7 @@ class DecoderTrainer(object):
             else:
                 buf = dkv_mem[key]
                 dkv = (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d])
-            self._attn_bwd(bk, t, dx, dkv)
+            self._attn_bwd(bk, t, dx, dkv, dx16, nxt)
             if key == "ae_attn":
                 ev_kv[l][i].record(main)    # dK/dV of layer l's ae_i memory are complete: its QAE chain may proceed
         grads = {"x": self._unscale(dx, invS).view(B, T, d)}
@@ -477,9 +593,13 @@ class DecoderTrainer(object):
             with _lib.on_stream(side[i]):
                 qt = ctx["qae_tapes"][i]
                 kind, t = qt[-1]
+                seq = list(reversed(qt[:-1]))
+                not_ffn = lambda entry: entry[0] != "ffn"    # an FFN's input gradient gets the K/V term added first
                 dae = torch.empty(B * La, d, dtype=torch.float32, device=dev)
+                nxt = None
                 self._ln_bwd(t, g_ae[i].view(B * La, d), None, dae, G[("ae_norm", i)], invS, dy_scale=S)   # mtn.py:162-163
-                for kind, t in reversed(qt[:-1]):
+                for k, (kind, t) in enumerate(seq):
+                    dx16, nxt = (nxt[0] if nxt is not None else None), handoff(seq, k, B * La, not_ffn)
                     key, l, _, c = t["names"]
                     if kind == "ffn":
                         # the layer's output ae_i^l is also the memory of the target's auto_encoder_attn[i]
@@ -492,12 +612,13 @@ class DecoderTrainer(object):
                         _lib.linear_dgrad(buf, A2["w_qkv"][d:], addend=dae, out_f32=dae)
                         self._flush(bk, [lambda buf=buf, gb=gb: _lib.cast_colsum(buf, colsum=gb, alpha=invS),
                                          lambda buf=buf, a16=a16, gw=gw: _lib.linear_wgrad(buf, a16, gw, alpha=invS)])
-                        self._ffn_bwd(bk, t, dae)
+                        self._ffn_bwd(bk, t, dae, None, nxt)
                     elif key == "ae_vid":
                         buf = dkv_vid[i]
-                        self._attn_bwd(bk, t, dae, (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d]))
+                        self._attn_bwd(bk, t, dae, (buf[:, l * 2 * d:l * 2 * d + d], buf[:, l * 2 * d + d:(l + 1) * 2 * d]),
+                                       dx16, nxt)
                     else:
-                        self._attn_bwd(bk, t, dae, None)
+                        self._attn_bwd(bk, t, dae, None, dx16, nxt)
                 grads["ae"].append(self._unscale(dae, invS).view(B, La, d))
                 bk["keep"].append(dae)
                 gk = ("ae_vid", i)              # hoisted video K/V projection of modality i
@@ -507,4 +628,4 @@ class DecoderTrainer(object):
             main.wait_stream(st)
         bk["keep"].append((dkv_mem, dkv_vid, dkv_ae, dx, g_out, g_ae, S2))
         ctx["_bwd_keep"] = bk["keep"]       # released with the tape by the caller, after the join has been enqueued
-        return grads, per
+        return grads, (None if direct else per)

@@ -20,14 +20,22 @@ from .label_smoothing import LabelSmoothing
 
 
 def flatten_grads(model):
-    """Back every parameter's .grad by a view of one flat f32 buffer (zeroed).  Returns the buffer."""
-    params = [p for p in model.parameters() if p.requires_grad]
-    total = sum((p.numel() + 3) // 4 * 4 for p in params)
-    flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
-    off = 0
-    for p in params:
+    """Back every parameter's .grad by a view of one flat f32 buffer (zeroed) -- the buffer of the single gradient
+    all-reduce.  The decoder's segment uses the training engine's arena layout, so its backward kernels accumulate
+    straight into it.  Returns the buffer."""
+    dec = getattr(model, "decoder", None)
+    tr = dec.trainer if dec is not None and hasattr(dec, "trainer") else None
+    dec_ids = set(id(p) for p in dec.parameters()) if tr is not None else set()
+    rest = [p for p in model.parameters() if p.requires_grad and id(p) not in dec_ids]
+    n_dec = tr.arena_numel() if tr is not None else 0
+    total = n_dec + sum((p.numel() + 7) // 8 * 8 for p in rest)
+    flat = torch.zeros(total, dtype=torch.float32, device=next(model.parameters()).device)
+    if tr is not None:
+        tr.attach_grads(flat[:n_dec])
+    off = n_dec
+    for p in rest:
         p.grad = flat[off:off + p.numel()].view_as(p)
-        off += (p.numel() + 3) // 4 * 4
+        off += (p.numel() + 7) // 8 * 8
     return flat
 
 

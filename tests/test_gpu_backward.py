@@ -136,6 +136,13 @@ def test_layernorm_bwd(L, rows, d):
     L.layernorm_bwd(dev(x.detach()), dev(a.detach()), 1e-6, dev(dy), dx2, da_2=da, db_2=db, dy_scale=S2[0:1],
                     param_alpha=S2[1:2])
     assert G.rel_err(dx2.cpu() / 64.0, x.grad) < 1e-5 and G.rel_err(da.cpu(), a.grad) < 2e-5
+    if d in (128, 512, 1024):      # fused hand-off to the next backward step: f16 copy of dx and its column sums
+        dx3, dx16 = dres.clone().cuda(), torch.empty(rows, d, dtype=torch.float16, device="cuda")
+        cs = torch.ones(d, device="cuda")
+        L.layernorm_bwd(dev(x.detach()), dev(a.detach()), 1e-6, dev(dy), dx3, dres=dx3, dx_f16=dx16, dx_colsum=cs,
+                        param_alpha=S2[1:2])
+        assert torch.equal(dx3, dx) and torch.equal(dx16, dx.half())
+        assert G.rel_err(cs.cpu() - 1, dx.cpu().sum(0) / 64.0) < 2e-5
 
 
 def test_cast_colsum_scale_f32_delta(L):
