@@ -69,6 +69,13 @@ int mtn_embed_fwd(const int64_t *ids, const float *lut, const float *pe, int row
                   int vocab, float scale, const float *a_2, const float *b_2, float eps,
                   float *y_f32, void *y_f16, void *stream);
 
+/* Training variant: PositionalEncoding's dropout (mtn.py:309) applied to lut*scale + pe BEFORE the stream
+ * LayerNorm; element index = r * d + c (see MtnLinearArgs for the RNG contract).                              */
+int mtn_embed_dropout_fwd(const int64_t *ids, const float *lut, const float *pe, int rows, int L, int d,
+                          int vocab, float scale, const float *a_2, const float *b_2, float eps,
+                          float *y_f32, void *y_f16, const void *drop_seed, uint32_t drop_site,
+                          uint32_t drop_thresh, void *stream);
+
 /* ---- video-feature preparation (boundary: Batch, data_utils.py:28-30) ----------------
  * ft: [frames, F] f32 raw features.  mask[frame] = any(ft[frame, :] != 1.0) (all-ones frames are
  * padding); padded frames are zeroed; output as f16 (video-encoder operand) and/or f32.        */
@@ -142,6 +149,13 @@ typedef struct MtnLinearArgs {
   /* ABI v3: out_f16 receives the value BEFORE the addend (video encoder in training: relu(.) without the
    * positional term is what the ReLU backward needs).                                                  */
   int out16_pre_add;
+  /* ABI v3, training-mode dropout of the result (nn.Dropout of SublayerConnection mtn.py:127, of the FFN hidden
+   * layer mtn.py:280, of PositionalEncoding mtn.py:309): element (m, n) is kept iff the 16 random bits that
+   * Philox-4x32-10(counter = ((m*N + n) >> 3, drop_site), key = *drop_seed) assigns to it are >= drop_thresh
+   * (= round(p * 65536)); kept elements are multiplied by 1/(1 - drop_thresh/65536).  Applied after the
+   * activation and BEFORE the addend (drop_after_add = 0) or after it (1).  drop_seed: device pointer to a
+   * 64-bit seed, NULL = no dropout.  The backward kernels regenerate the same decisions from (seed, site).  */
+  const void *drop_seed; uint32_t drop_site, drop_thresh; int drop_after_add;
 } MtnLinearArgs;
 int mtn_linear_fwd(const MtnLinearArgs *args, void *stream);
 
@@ -168,6 +182,11 @@ typedef struct MtnAttnCoreArgs {
   /* ABI v3 (training): optional [B, h, Lq, 2] f32 -- per query row {row maximum of the masked scaled scores
    * in the log2 domain, 1 / softmax denominator}; saved for mtn_attn_core_bwd.  NULL: not written.       */
   float *stats;
+  /* ABI v3, training-mode dropout of the probabilities (mtn.py:229-230): P[b, head, q, k] is kept iff the 16 random
+   * bits Philox-4x32-10(counter = ((((b*h + head)*Lq + q) * Lk32 + k) >> 3, drop_site), key = *drop_seed), Lk32 =
+   * Lk rounded up to 32, assigns to it are >= drop_thresh; kept probabilities are multiplied by
+   * 1/(1 - drop_thresh/65536).  The softmax normalisation is unaffected.  drop_seed NULL = no dropout.        */
+  const void *drop_seed; uint32_t drop_site, drop_thresh;
 } MtnAttnCoreArgs;
 int mtn_attn_core_fwd(const MtnAttnCoreArgs *args, void *stream);
 
@@ -242,6 +261,8 @@ typedef struct MtnGemmArgs {
   void *out_f16; int ld16; int out16_pre_add;
   int batch;
   long long stride_A, stride_B, stride_bias, stride_add, stride_out_f32, stride_out_f16;
+  float mask_scale;                   /* multiplies what passes relu_mask (0 = 1) */
+  const void *drop_seed; uint32_t drop_site, drop_thresh; int drop_after_add;   /* see MtnLinearArgs */
 } MtnGemmArgs;
 int mtn_gemm_f16(const MtnGemmArgs *args, void *stream);
 int mtn_check_gemm_f16(const MtnGemmArgs *args, void *stream);   /* tests only */
@@ -257,6 +278,7 @@ typedef struct MtnLinearDgradArgs {
   int M, N, K;
   const float *alpha;
   const void *relu_mask; int ld_mask;  /* f16 [M, K] or NULL */
+  float mask_scale;                    /* multiplies what passes the mask: 1/(1-p) of a dropout after the ReLU (0 = 1) */
   const float *addend; int ld_add;     /* f32 [M, K] or NULL */
   float *dX_f32; int ld32;
   void *dX_f16; int ld16;
@@ -282,7 +304,10 @@ int mtn_linear_wgrad(const MtnLinearWgradArgs *args, void *stream);
  * src is f32 (src_is_f16 = 0) or f16.  cols % 8 == 0.  The bias gradient of every nn.Linear on the path. */
 int mtn_cast_colsum(const void *src, int src_is_f16, int ld_src, void *dst_f16, int ld_dst,
                     const void *relu_mask, int ld_mask, int rows, int cols, const float *scale,
-                    const float *alpha, float *colsum, void *stream);
+                    const float *alpha, float *colsum, const void *drop_seed, uint32_t drop_site,
+                    uint32_t drop_thresh, void *stream);
+/* (drop_*: the values are additionally thinned by the dropout of the linear layer's output they are the
+ * gradient of -- see MtnLinearArgs; element index = r * cols + c.)                                        */
 
 /* ---- gradient scale ---------------------------------------------------------------------------------
  * mtn_grad_absmax folds max|x| into *slot (a zero-initialised uint32 in device memory; may be called for
@@ -290,6 +315,8 @@ int mtn_cast_colsum(const void *src, int src_is_f16, int ld_src, void *dst_f16, 
  * (S = 1 for an all-zero or non-finite gradient) and resets the slot.                                   */
 int mtn_grad_absmax(const float *x, size_t n, uint32_t *slot, void *stream);
 int mtn_grad_scale(uint32_t *slot, float *scale2, void *stream);
+/* *seed += 1 on the stream (the captured training step bumps the dropout seed once per replay). */
+int mtn_seed_bump(uint64_t *seed, void *stream);
 /* Stream-ordered zero fill (cudaMemsetAsync) of a gradient accumulation buffer. */
 int mtn_zero(void *p, size_t bytes, void *stream);
 /* y = (accumulate ? y : 0) + x * alpha[0]: un-scales an input gradient leaving the backward pass.  n % 4 == 0. */
@@ -307,6 +334,7 @@ typedef struct MtnLayerNormBwdArgs {
   /* optional fused outputs for the NEXT backward step (the sublayer whose output x is): an f16 copy of dx (its
    * GEMM operand) and dx_colsum[c] += param_alpha * sum_rows dx[:, c] (its output-bias gradient)            */
   void *dx_f16; float *dx_colsum;
+  const void *drop_seed; uint32_t drop_site, drop_thresh;   /* dropout applied to dx_f16 / dx_colsum only */
 } MtnLayerNormBwdArgs;
 int mtn_layernorm_bwd(const MtnLayerNormBwdArgs *args, void *stream);
 
@@ -319,6 +347,7 @@ typedef struct MtnEmbedBwdArgs {
   const float *a_2; float eps;
   const float *dy;
   float *dlut; float *da_2; float *db_2; const float *param_alpha;
+  const void *drop_seed; uint32_t drop_site, drop_thresh;   /* the forward's dropout (mtn_embed_dropout_fwd) */
 } MtnEmbedBwdArgs;
 int mtn_embed_bwd(const MtnEmbedBwdArgs *args, void *stream);
 
@@ -340,6 +369,7 @@ typedef struct MtnAttnCoreBwdArgs {
   float *dq; int lddq;
   void *dk; int lddk;
   void *dv; int lddv;
+  const void *drop_seed; uint32_t drop_site, drop_thresh;   /* the forward's probability dropout (regenerated) */
 } MtnAttnCoreBwdArgs;
 int mtn_attn_core_bwd(const MtnAttnCoreBwdArgs *args, void *stream);
 

@@ -28,7 +28,9 @@ class LinearArgs(C.Structure):
                 ("out_f16", C.c_void_p), ("ld16", C.c_int),
                 ("batch", C.c_int), ("stride_A", C.c_longlong), ("stride_W", C.c_longlong),
                 ("stride_bias", C.c_longlong), ("stride_add", C.c_longlong), ("stride_out_f32", C.c_longlong),
-                ("stride_out_f16", C.c_longlong), ("out16_pre_add", C.c_int)]
+                ("stride_out_f16", C.c_longlong), ("out16_pre_add", C.c_int),
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32),
+                ("drop_after_add", C.c_int)]
 
 
 class GemmArgs(C.Structure):
@@ -42,13 +44,16 @@ class GemmArgs(C.Structure):
                 ("out_f16", C.c_void_p), ("ld16", C.c_int), ("out16_pre_add", C.c_int),
                 ("batch", C.c_int), ("stride_A", C.c_longlong), ("stride_B", C.c_longlong),
                 ("stride_bias", C.c_longlong), ("stride_add", C.c_longlong), ("stride_out_f32", C.c_longlong),
-                ("stride_out_f16", C.c_longlong)]
+                ("stride_out_f16", C.c_longlong), ("mask_scale", C.c_float),
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32),
+                ("drop_after_add", C.c_int)]
 
 
 class LinearDgradArgs(C.Structure):
     _fields_ = [("dY", C.c_void_p), ("lddy", C.c_int), ("W", C.c_void_p), ("ldw", C.c_int),
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("alpha", C.c_void_p),
-                ("relu_mask", C.c_void_p), ("ld_mask", C.c_int), ("addend", C.c_void_p), ("ld_add", C.c_int),
+                ("relu_mask", C.c_void_p), ("ld_mask", C.c_int), ("mask_scale", C.c_float),
+                ("addend", C.c_void_p), ("ld_add", C.c_int),
                 ("dX_f32", C.c_void_p), ("ld32", C.c_int), ("dX_f16", C.c_void_p), ("ld16", C.c_int),
                 ("batch", C.c_int), ("stride_dY", C.c_longlong), ("stride_W", C.c_longlong),
                 ("stride_add", C.c_longlong), ("stride_dX_f32", C.c_longlong), ("stride_dX_f16", C.c_longlong)]
@@ -66,14 +71,16 @@ class LayerNormBwdArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("a_2", C.c_void_p), ("eps", C.c_float), ("rows", C.c_int), ("d", C.c_int),
                 ("dy", C.c_void_p), ("dy_scale", C.c_void_p), ("dres", C.c_void_p), ("dx", C.c_void_p),
                 ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p),
-                ("dx_f16", C.c_void_p), ("dx_colsum", C.c_void_p)]
+                ("dx_f16", C.c_void_p), ("dx_colsum", C.c_void_p),
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32)]
 
 
 class EmbedBwdArgs(C.Structure):
     _fields_ = [("ids", C.c_void_p), ("lut", C.c_void_p), ("pe", C.c_void_p),
                 ("rows", C.c_int), ("L", C.c_int), ("d", C.c_int), ("vocab", C.c_int), ("scale", C.c_float),
                 ("a_2", C.c_void_p), ("eps", C.c_float), ("dy", C.c_void_p),
-                ("dlut", C.c_void_p), ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p)]
+                ("dlut", C.c_void_p), ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p),
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32)]
 
 
 class AttnCoreBwdArgs(C.Structure):
@@ -83,14 +90,16 @@ class AttnCoreBwdArgs(C.Structure):
                 ("mask_bits", C.c_void_p), ("mask_rows_q", C.c_int),
                 ("B", C.c_int), ("h", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("d_k", C.c_int),
                 ("dq", C.c_void_p), ("lddq", C.c_int), ("dk", C.c_void_p), ("lddk", C.c_int),
-                ("dv", C.c_void_p), ("lddv", C.c_int)]
+                ("dv", C.c_void_p), ("lddv", C.c_int),
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32)]
 
 
 class AttnCoreArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int),
                 ("v", C.c_void_p), ("ldv", C.c_int), ("mask_bits", C.c_void_p),
                 ("mask_rows_q", C.c_int), ("B", C.c_int), ("h", C.c_int), ("Lq", C.c_int),
-                ("Lk", C.c_int), ("d_k", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int), ("stats", C.c_void_p)]
+                ("Lk", C.c_int), ("d_k", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int), ("stats", C.c_void_p),
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32)]
 
 
 class AttnSiteArgs(C.Structure):
@@ -148,7 +157,12 @@ SYMBOLS = {
     "mtn_linear_dgrad": (C.c_int, [C.POINTER(LinearDgradArgs), C.c_void_p]),
     "mtn_linear_wgrad": (C.c_int, [C.POINTER(LinearWgradArgs), C.c_void_p]),
     "mtn_cast_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                  C.c_void_p]),
+    "mtn_embed_dropout_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                        C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                        C.c_uint32, C.c_void_p]),
+    "mtn_seed_bump": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mtn_grad_absmax": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mtn_grad_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -310,7 +324,7 @@ def mask_pack(mask):
 
 
 def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=None, out_f16=None,
-           _check_kernel=False, out16_pre_add=False):
+           _check_kernel=False, out16_pre_add=False, drop=None, drop_after_add=False):
     """C = act(A W^T + bias) + addend.  A: [M, K] f16 (row stride allowed), W: [N, K] f16."""
     _req(A, torch.float16, "A"); _req(W, torch.float16, "W"); _req(bias, torch.float32, "bias")
     _req(addend, torch.float32, "addend"); _req(out_f32, torch.float32, "out_f32")
@@ -330,15 +344,17 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
         assert out_f16.dim() == 2 and tuple(out_f16.shape) == (a.M, a.N)
         a.out_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
     a.out16_pre_add = 1 if out16_pre_add else 0
+    _set_drop(a, drop)
+    a.drop_after_add = 1 if drop_after_add else 0
     fn = lib().mtn_check_linear_fwd if _check_kernel else lib().mtn_linear_fwd
     nbytes = 2 * (a.M * a.K + a.N * a.K) + a.M * a.N * ((4 if out_f32 is not None else 0) +
                                                         (2 if out_f16 is not None else 0) +
                                                         (4 if addend is not None else 0))
     _launch("linear", 2 * a.M * a.N * a.K, nbytes, lambda: fn(C.byref(a), stream_ptr()),
-            keep=(A, W, bias, addend, out_f32, out_f16))
+            keep=(A, W, bias, addend, out_f32, out_f16, drop))
 
 
-def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False, stats=None):
+def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False, stats=None, drop=None):
     """q: [B*Lq, >=h*d_k] f16 view (row stride = leading dimension), k/v: [B*Lk, ...];
     out: [B*Lq, >=h*d_k] f16.  mask_bits: output of mask_pack or None."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
@@ -357,12 +373,13 @@ def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=Fal
         _req(stats, torch.float32, "stats")
         assert stats.is_contiguous() and stats.numel() == B * h * Lq * 2
         a.stats = stats.data_ptr()
+    _set_drop(a, drop)
     fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
     _launch("attn_core", 4 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (2 * Lq + 2 * Lk),
-            lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits, stats))
+            lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits, stats, drop))
 
 
-def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None):
+def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None, drop=None):
     """ids: [B, L] int64; lut: [vocab, d] f32; pe: [>=L, d] f32 (the table, 2-D).  Returns / fills
     [B, L, d] = LN?(lut[ids] * scale + pe[:L]);  ln = (a_2, b_2, eps) or None."""
     assert ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_cuda
@@ -374,9 +391,11 @@ def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None):
     assert pe.dim() == 2 and pe.shape[0] >= L and pe.is_contiguous() and lut.is_contiguous()
     a2, b2, eps = ln if ln is not None else (None, None, 0.0)
     _launch("embed", 0, B * L * d * (8 + (4 if out_f32 is not None else 0) + (2 if out_f16 is not None else 0)),
-            lambda: lib().mtn_embed_fwd(ptr(idc), ptr(lut), ptr(pe), B * L, L, d, lut.shape[0], float(scale), ptr(a2),
-                                        ptr(b2), float(eps), ptr(out_f32), ptr(out_f16), stream_ptr()),
-            keep=(idc, lut, pe, a2, b2, out_f32, out_f16))
+            lambda: lib().mtn_embed_dropout_fwd(ptr(idc), ptr(lut), ptr(pe), B * L, L, d, lut.shape[0], float(scale), ptr(a2),
+                                                ptr(b2), float(eps), ptr(out_f32), ptr(out_f16),
+                                                ptr(drop[0]) if drop else None, drop[1] if drop else 0,
+                                                drop[2] if drop else 0, stream_ptr()),
+            keep=(idc, lut, pe, a2, b2, out_f32, out_f16, drop))
 
 
 def feature_prep(ft, out_f16=None, out_f32=None):
@@ -453,11 +472,37 @@ def linear_batched(A, W, bias=None, act=ACT_NONE, addend=None, out_f32=None, out
 
 
 # ------------------------------------------------------------------------------
+# dropout: a `drop` argument is None or a tuple (seed, site, thresh): `seed` a 1-element int64 device tensor read by
+# the kernels (so a captured step can bump it), `site` the number of the dropout application inside one forward
+# pass, `thresh` = round(p * 65536).  The backward kernels get the SAME tuple and regenerate the decisions.
+# ------------------------------------------------------------------------------
+def drop_cfg(seed, site, p):
+    """(seed, site, thresh) for probability p, or None when p == 0."""
+    th = int(round(float(p) * 65536.0))
+    if th <= 0:
+        return None
+    if th >= 65536:
+        raise MtnError("dropout probability %g must be < 1" % p)
+    assert seed.dtype == torch.int64 and seed.is_cuda and seed.numel() == 1
+    return (seed, int(site), th)
+
+
+def _set_drop(a, drop):
+    if drop is not None:
+        a.drop_seed, a.drop_site, a.drop_thresh = drop[0].data_ptr(), drop[1], drop[2]
+
+
+def seed_bump(seed):
+    _launch("seed_bump", 0, 16, lambda: lib().mtn_seed_bump(ptr(seed), stream_ptr()), keep=(seed,))
+
+
+# ------------------------------------------------------------------------------
 # backward wrappers (ABI v3).  `scale2` is a 2-element f32 device tensor {S, 1/S} from grad_scale(); wrappers
 # take views of it (scale2[0:1] / scale2[1:2]) or None as `scale` / `alpha` device scalars.
 # ------------------------------------------------------------------------------
 def gemm(A, B, M, N, K, a_mn=False, b_mn=False, alpha=None, bias=None, act=ACT_NONE, relu_mask=None, addend=None,
-         add_period=0, accumulate=False, out_f32=None, out_f16=None, _check_kernel=False):
+         add_period=0, accumulate=False, out_f32=None, out_f16=None, _check_kernel=False, mask_scale=0.0, drop=None,
+         drop_after_add=False):
     """General tensor-core GEMM (see MtnGemmArgs); 2-D operands, row strides honoured."""
     _req(A, torch.float16, "A"); _req(B, torch.float16, "B"); _req(alpha, torch.float32, "alpha")
     _req(bias, torch.float32, "bias"); _req(relu_mask, torch.float16, "relu_mask"); _req(addend, torch.float32, "addend")
@@ -480,12 +525,15 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, alpha=None, bias=None, act=ACT_N
     if out_f16 is not None:
         assert tuple(out_f16.shape) == (M, N)
         a.out_f16, a.ld16 = out_f16.data_ptr(), out_f16.stride(0)
+    a.mask_scale = float(mask_scale)
+    _set_drop(a, drop)
+    a.drop_after_add = 1 if drop_after_add else 0
     fn = lib().mtn_check_gemm_f16 if _check_kernel else lib().mtn_gemm_f16
     _launch("gemm", 2 * M * N * K, 2 * (M * K + N * K) + M * N * 4, lambda: fn(C.byref(a), stream_ptr()),
             keep=(A, B, alpha, bias, relu_mask, addend, out_f32, out_f16))
 
 
-def linear_dgrad(dY, W, alpha=None, relu_mask=None, addend=None, out_f32=None, out_f16=None):
+def linear_dgrad(dY, W, alpha=None, relu_mask=None, addend=None, out_f32=None, out_f16=None, mask_scale=0.0):
     """dX = alpha * dY W (* relu_mask > 0) (+ addend).  dY: [M, N] f16, W: [N, K] f16 (forward layout)."""
     _req(dY, torch.float16, "dY"); _req(W, torch.float16, "W"); _req(alpha, torch.float32, "alpha")
     _req(relu_mask, torch.float16, "relu_mask"); _req(addend, torch.float32, "addend")
@@ -498,6 +546,7 @@ def linear_dgrad(dY, W, alpha=None, relu_mask=None, addend=None, out_f32=None, o
     if relu_mask is not None:
         assert tuple(relu_mask.shape) == (a.M, a.K)
         a.relu_mask, a.ld_mask = relu_mask.data_ptr(), relu_mask.stride(0)
+    a.mask_scale = float(mask_scale)
     if addend is not None:
         assert tuple(addend.shape) == (a.M, a.K)
         a.addend, a.ld_add = addend.data_ptr(), addend.stride(0)
@@ -526,7 +575,7 @@ def linear_wgrad(dY, X, dW, alpha=None):
             lambda: lib().mtn_linear_wgrad(C.byref(a), stream_ptr()), keep=(dY, X, dW, alpha))
 
 
-def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mask=None):
+def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mask=None, drop=None):
     """dst_f16 = f16(src * scale [masked]); colsum += alpha * column sums.  src: 2-D f32 or f16."""
     assert src.dim() == 2 and src.is_cuda and src.dtype in (torch.float32, torch.float16) and src.stride(1) == 1
     _req(dst_f16, torch.float16, "dst_f16"); _req(colsum, torch.float32, "colsum"); _req(scale, torch.float32, "scale")
@@ -539,8 +588,9 @@ def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mas
             lambda: lib().mtn_cast_colsum(ptr(src), 1 if src.dtype == torch.float16 else 0, src.stride(0), ptr(dst_f16),
                                           dst_f16.stride(0) if dst_f16 is not None else 0, ptr(relu_mask),
                                           relu_mask.stride(0) if relu_mask is not None else 0, rows, cols, ptr(scale),
-                                          ptr(alpha), ptr(colsum), stream_ptr()),
-            keep=(src, dst_f16, colsum, scale, alpha, relu_mask))
+                                          ptr(alpha), ptr(colsum), ptr(drop[0]) if drop else None,
+                                          drop[1] if drop else 0, drop[2] if drop else 0, stream_ptr()),
+            keep=(src, dst_f16, colsum, scale, alpha, relu_mask, drop))
 
 
 _SCALE_SLOTS = {}
@@ -582,7 +632,7 @@ def scale_f32(x, alpha, y, accumulate=False):
 
 
 def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale=None, param_alpha=None, dx_f16=None,
-                  dx_colsum=None):
+                  dx_colsum=None, drop=None):
     """dx = dres + dLN(dy * dy_scale); da_2 / db_2 += param_alpha * (...).  x, dy, dx: [rows, d] f32 contiguous."""
     for t, n in ((x, "x"), (a_2, "a_2"), (dy, "dy"), (dx, "dx"), (dres, "dres"), (da_2, "da_2"), (db_2, "db_2"),
                  (dy_scale, "dy_scale"), (param_alpha, "param_alpha")):
@@ -607,12 +657,13 @@ def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale
     if dx_colsum is not None:
         assert dx_colsum.is_contiguous() and dx_colsum.numel() == d
         a.dx_colsum = dx_colsum.data_ptr()
+    _set_drop(a, drop)
     _launch("layernorm_bwd", 0, rows * d * (12 + (4 if dres is not None else 0) + (2 if dx_f16 is not None else 0)),
             lambda: lib().mtn_layernorm_bwd(C.byref(a), stream_ptr()),
-            keep=(x, a_2, dy, dx, dres, da_2, db_2, dy_scale, param_alpha, dx_f16, dx_colsum))
+            keep=(x, a_2, dy, dx, dres, da_2, db_2, dy_scale, param_alpha, dx_f16, dx_colsum, drop))
 
 
-def embed_bwd(ids, lut, pe, scale, dy, dlut, ln=None, da_2=None, db_2=None, param_alpha=None):
+def embed_bwd(ids, lut, pe, scale, dy, dlut, ln=None, da_2=None, db_2=None, param_alpha=None, drop=None):
     """Backward of embed(): dlut[ids] += scale * dpre (atomic), LN parameter gradients when ln is given."""
     assert ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_cuda
     _req(lut, torch.float32, "lut"); _req(pe, torch.float32, "pe"); _req(dy, torch.float32, "dy")
@@ -629,8 +680,9 @@ def embed_bwd(ids, lut, pe, scale, dy, dlut, ln=None, da_2=None, db_2=None, para
         a.da_2, a.db_2 = da_2.data_ptr(), db_2.data_ptr()
     a.dy, a.dlut = dy.data_ptr(), dlut.data_ptr()
     a.param_alpha = param_alpha.data_ptr() if param_alpha is not None else None
+    _set_drop(a, drop)
     _launch("embed_bwd", 0, B * L * d * 16, lambda: lib().mtn_embed_bwd(C.byref(a), stream_ptr()),
-            keep=(idc, lut, pe, dy, dlut, ln, da_2, db_2, param_alpha))
+            keep=(idc, lut, pe, dy, dlut, ln, da_2, db_2, param_alpha, drop))
 
 
 def attn_delta(dO, O, B, Lq, h, d_k, delta):
@@ -641,7 +693,7 @@ def attn_delta(dO, O, B, Lq, h, d_k, delta):
                                          stream_ptr()), keep=(dO, O, delta))
 
 
-def attn_core_bwd(q, k, v, dO, stats, delta, B, h, Lq, Lk, d_k, dq, dk, dv, mask_bits=None):
+def attn_core_bwd(q, k, v, dO, stats, delta, B, h, Lq, Lk, d_k, dq, dk, dv, mask_bits=None, drop=None):
     """q/k/v/dO: f16 2-D views (row stride = leading dimension); stats [B,h,Lq,2], delta [B,h,Lq] f32;
     dq: f32 [B*Lq, >= h*d_k] ACCUMULATED (zero it first); dk/dv: f16 [B*Lk, >= h*d_k] written."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (dO, "dO"), (dk, "dk"), (dv, "dv")):
@@ -657,9 +709,10 @@ def attn_core_bwd(q, k, v, dO, stats, delta, B, h, Lq, Lk, d_k, dq, dk, dv, mask
         a.mask_bits, a.mask_rows_q = mask_bits.data_ptr(), mask_bits.shape[1]
     a.B, a.h, a.Lq, a.Lk, a.d_k = B, h, Lq, Lk, d_k
     a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0)
+    _set_drop(a, drop)
     _launch("attn_core_bwd", 10 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (4 * Lq + 4 * Lk),
             lambda: lib().mtn_attn_core_bwd(C.byref(a), stream_ptr()),
-            keep=(q, k, v, dO, stats, delta, dq, dk, dv, mask_bits))
+            keep=(q, k, v, dO, stats, delta, dq, dk, dv, mask_bits, drop))
 
 
 def log_softmax_bwd(y, dy, V, dz):

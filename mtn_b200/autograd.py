@@ -21,17 +21,25 @@ def recording(module, *tensors):
     return module is not None and any(p.requires_grad for p in module.parameters())
 
 
-def require_no_dropout(module):
-    """Training-mode dropout (mtn.py:127, :230, :280, :309) is not implemented in the fused kernels yet: fail
-    loudly instead of silently training without it."""
-    if module is None or not module.training:
-        return
-    for m in module.modules():
-        if isinstance(m, torch.nn.Dropout) and m.p > 0:
-            raise NotImplementedError(
-                "mtn_b200: training-mode dropout (p=%g) is not implemented in the fused kernels; set every "
-                "nn.Dropout.p to 0 (e.g. `for m in model.modules(): m.p = 0 if isinstance(m, nn.Dropout) else ...`) "
-                "or call model.eval()" % m.p)
+# ---- dropout seed: one 64-bit counter per device, in device memory so that a captured training step advances it
+_SEEDS = {}
+
+
+def manual_seed(seed, device=None):
+    """Seed of the fused dropout (every training-mode forward draws a fresh value from this counter)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _SEEDS[dev] = torch.tensor([int(seed)], dtype=torch.int64, device=dev)
+
+
+def next_seed(device):
+    """Snapshot of the device's dropout counter for ONE forward pass (its backward regenerates the same decisions),
+    then advance the counter.  Two tiny stream-ordered ops: CUDA-graph capturable, no host synchronisation."""
+    dev = torch.device(device)
+    if dev not in _SEEDS:
+        manual_seed(0x6d746e, dev)
+    snap = _SEEDS[dev].clone()
+    _lib.seed_bump(_SEEDS[dev])
+    return snap
 
 
 def _linear_bwd(dy32, x16, w16, want_dx=True):
@@ -79,11 +87,12 @@ class EmbedFn(Function):
     """Embeddings * sqrt(d) + positional encoding (+ the Encoder's stream LayerNorm), mtn_embed_fwd / _bwd."""
 
     @staticmethod
-    def forward(ctx, ids, lut, pe, scale, a_2, b_2, eps):
+    def forward(ctx, ids, lut, pe, scale, a_2, b_2, eps, p_drop=0.0):
         B, L = ids.shape
         out = torch.empty(B, L, lut.shape[1], dtype=torch.float32, device=ids.device)
         ln = None if a_2 is None else (a_2, b_2, eps)
-        _lib.embed(ids, lut, pe, scale, ln=ln, out_f32=out)
+        ctx.drop = _lib.drop_cfg(next_seed(ids.device), 0, p_drop) if p_drop > 0 else None   # mtn.py:309
+        _lib.embed(ids, lut, pe, scale, ln=ln, out_f32=out, drop=ctx.drop)
         ctx.save_for_backward(ids, lut, pe, a_2)
         ctx.scale, ctx.eps = scale, eps
         return out
@@ -98,21 +107,22 @@ class EmbedFn(Function):
         if a_2 is not None:
             da, db = torch.zeros_like(a_2), torch.zeros_like(a_2)
             ln = (a_2, None, ctx.eps)
-        _lib.embed_bwd(ids, lut, pe, ctx.scale, dyc, dlut, ln=ln, da_2=da, db_2=db)
-        return None, dlut, None, None, da, db, None
+        _lib.embed_bwd(ids, lut, pe, ctx.scale, dyc, dlut, ln=ln, da_2=da, db_2=db, drop=ctx.drop)
+        return None, dlut, None, None, da, db, None, None
 
 
 class VideoEncoderFn(Function):
     """relu(ft W^T + b) + pe[t] (mtn.py:377-379) as one fused GEMM; the f16 ReLU output is kept as the mask."""
 
     @staticmethod
-    def forward(ctx, ft16, weight, bias, w16, pe, Lv):
+    def forward(ctx, ft16, weight, bias, w16, pe, Lv, p_drop=0.0):
         rows = ft16.shape[0]
         d = weight.shape[0]
         out = torch.empty(rows, d, dtype=torch.float32, device=ft16.device)
         relu16 = torch.empty(rows, d, dtype=torch.float16, device=ft16.device)
+        ctx.drop = _lib.drop_cfg(next_seed(ft16.device), 0, p_drop) if p_drop > 0 else None   # mtn.py:309, after + pe
         _lib.linear(ft16, w16, bias, act=_lib.ACT_RELU, addend=pe, add_period=Lv, out_f32=out, out_f16=relu16,
-                    out16_pre_add=True)
+                    out16_pre_add=True, drop=ctx.drop, drop_after_add=True)
         ctx.save_for_backward(ft16, relu16)
         ctx.wshape = weight.shape
         return out
@@ -126,10 +136,10 @@ class VideoEncoderFn(Function):
         S, invS = S2[0:1], S2[1:2]
         dpre16 = torch.empty_like(relu16)
         db = torch.zeros(ctx.wshape[0], dtype=torch.float32, device=dev)
-        _lib.cast_colsum(dyc, dst_f16=dpre16, colsum=db, scale=S, alpha=invS, relu_mask=relu16)
+        _lib.cast_colsum(dyc, dst_f16=dpre16, colsum=db, scale=S, alpha=invS, relu_mask=relu16, drop=ctx.drop)
         dW = torch.zeros(ctx.wshape, dtype=torch.float32, device=dev)
         _lib.linear_wgrad(dpre16, ft16, dW, alpha=invS)
-        return None, dW, db, None, None, None
+        return None, dW, db, None, None, None, None
 
 
 class ProjectFn(Function):
@@ -201,10 +211,11 @@ class DecoderFn(Function):
         else:
             ae_ft = ae[0] if n_ae == 1 else None
         f = lambda t: t.contiguous().float()
+        seed = next_seed(x.device) if trainer.dec.training else None
         out, ae_outs, tape = trainer.forward([f(v) for v in vid], meta["vid_mask"], f(x), f(his), meta["his_mask"],
                                              f(cap), meta["cap_mask"], f(qm), meta["q_mask"], meta["tgt_mask"],
                                              [f(a) for a in ae_ft] if isinstance(ae_ft, list) else
-                                             (f(ae_ft) if ae_ft is not None else None), meta["ae_features"])
+                                             (f(ae_ft) if ae_ft is not None else None), meta["ae_features"], seed=seed)
         ctx.trainer, ctx.tape, ctx.n_vid, ctx.n_ae, ctx.ae_list = trainer, tape, n_vid, n_ae, meta["ae_list"]
         ctx.n_params = len(tensors) - 4 - n_vid - n_ae
         return (out,) + tuple(ae_outs)

@@ -65,6 +65,8 @@ struct AttnParams {
   __half* out;
   int ldo;
   float2* stats;  // optional [B, h, Lq] {row maximum (log2 domain), 1 / row sum}: saved for the backward pass
+  DropCfg drop;   // dropout of the probabilities (mtn.py:229-230): element index ((b*h + head)*Lq + q) * Lk32 + key
+  int Lk32;       // Lk rounded up to a multiple of 32
 };
 
 enum {  // "+1": two barriers, one per buffer
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     const uint32_t sw = (uint32_t)(row & 7);
     constexpr int NCH = ATT_KT / 32;
     uint32_t g = 0;
+    const unsigned long long dseed = p.drop.seed != nullptr ? __ldg(p.drop.seed) : 0ull;
 
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
@@ -310,6 +313,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 #pragma unroll
             for (int i = 0; i < 32; ++i) e[i] = 0.f;
           }
+          if (p.drop.seed != nullptr && nvalid > 0) {
+            // dropout AFTER the softmax: the row sum above keeps every key, only the P V operand is thinned
+            const unsigned long long e0 =
+                ((((unsigned long long)b * p.h + hd) * p.Lq + min(qi, p.Lq - 1)) * p.Lk32 + k0) >> 3;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t kb = drop_keep8(p.drop, dseed, e0 + t);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) e[8 * t + u] = ((kb >> u) & 1u) ? e[8 * t + u] * p.drop.inv_keep : 0.f;
+            }
+          }
           const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * 128;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -393,7 +407,10 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   const int nqt = (a.Lq + ATT_QT - 1) / ATT_QT;
   const int n_items = nqt * a.h * a.B;
   AttnParams p{n_items, nqt, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
-               1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo, reinterpret_cast<float2*>(a.stats)};
+               1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo, reinterpret_cast<float2*>(a.stats),
+               DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
+                       a.drop_seed ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
+               (a.Lk + 31) / 32 * 32};
   static int slots = 0;  // resident CTAs: 2 per SM
   if (slots == 0) {
     int dev = 0, n = 0;
@@ -420,6 +437,7 @@ static int validate_attn(const MtnAttnCoreArgs* a) {
               "attn_core: pointers must be 16-byte aligned");
   MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,
               "attn_core: mask_rows_q=%d must be 1 or Lq=%d", a->mask_rows_q, a->Lq);
+  MTN_REQUIRE(a->drop_thresh < 65536u, MTN_E_ARG, "attn_core: drop_thresh=%u", a->drop_thresh);
   return MTN_OK;
 }
 
@@ -477,7 +495,8 @@ extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
   int rc = mtn::validate_attn(a);
   if (rc) return rc;
   mtn::AttnParams p{0, 0, a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
-                    1.0f / sqrtf((float)a->d_k), reinterpret_cast<__half*>(a->out), a->ldo, nullptr};
+                    1.0f / sqrtf((float)a->d_k), reinterpret_cast<__half*>(a->out), a->ldo, nullptr,
+                    mtn::DropCfg{nullptr, 0, 0, 1.f}, 0};
   dim3 grid(a->Lq, a->h, a->B);
   mtn::attn_core_check_kernel<<<grid, 32, a->Lk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(a->q), a->ldq, reinterpret_cast<const __half*>(a->k), a->ldk,

@@ -61,6 +61,8 @@ struct AttnBwdParams {
   float* dq; int lddq;
   __half* dk; int lddk;
   __half* dv; int lddv;
+  DropCfg drop;  // the forward's dropout of the probabilities, regenerated
+  int Lk32;
 };
 
 enum { ABAR_KV_FULL = 0, ABAR_QDO_FULL = 1 /* +1 */, ABAR_QDO_EMPTY = 3 /* +1 */, ABAR_S_FULL = 5, ABAR_P_FULL, ABAR_G_DONE,
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const float t_masked = -1e9f * LOG2E;
     const uint32_t sw = (uint32_t)(row & 7);
     const size_t bh = (size_t)b * p.h + hd;
+    const unsigned long long dseed = p.drop.seed != nullptr ? __ldg(p.drop.seed) : 0ull;
 
     auto drain_dq = [&](int i) {  // dQ tile i (TMEM buffer i & 1) -> f32 global accumulation
       if (half * 32 < DK) {
@@ -239,17 +242,26 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
           tc_ld32(tmem_base + C::COL_S + lane_off + c * 32, s);
           tc_ld32(tmem_base + C::COL_DP + lane_off + c * 32, d);
           tc_wait_ld();
+          uint32_t dropk = 0xffffffffu;  // keep decisions of this row's 32 keys (P dropout of the forward)
+          if (p.drop.seed != nullptr) {
+            const unsigned long long e0 = (((unsigned long long)bh * p.Lq + min(qi, p.Lq - 1)) * p.Lk32 + k0) >> 3;
+            dropk = 0u;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dropk |= drop_keep8(p.drop, dseed, e0 + t) << (8 * t);
+          }
+          const float ik = p.drop.inv_keep;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             float pv[2], dv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const bool keep = (mw >> (j + u)) & 1u, in = (inb >> (j + u)) & 1u;
+              const float dm = ((dropk >> (j + u)) & 1u) ? ik : 0.f;   // dropout mask / keep probability
               float t = __uint_as_float(s[j + u]) * c1;
               t = keep ? t : t_masked;
               const float pr = (valid && in) ? ex2_approx_b(t - m_row) * inv_l : 0.f;
-              pv[u] = pr;
-              dv[u] = (keep && in) ? pr * (__uint_as_float(d[j + u]) - delta) * p.scale : 0.f;
+              pv[u] = pr * dm;                                            // dropped P feeds dV = P_drop^T dO
+              dv[u] = (keep && in) ? pr * (__uint_as_float(d[j + u]) * dm - delta) * p.scale : 0.f;
             }
             pk_p[j >> 1] = pack_f16x2_sat(pv[0], pv[1]);
             pk_d[j >> 1] = pack_f16x2_sat(dv[0], dv[1]);
@@ -328,7 +340,10 @@ static int launch_attn_bwd(const MtnAttnCoreBwdArgs& a, cudaStream_t st) {
   if (rc) return rc;
   AttnBwdParams p{a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk, 1.0f / sqrtf((float)DK),
                   reinterpret_cast<const float2*>(a.stats), a.delta, a.dq, a.lddq,
-                  reinterpret_cast<__half*>(a.dk), a.lddk, reinterpret_cast<__half*>(a.dv), a.lddv};
+                  reinterpret_cast<__half*>(a.dk), a.lddk, reinterpret_cast<__half*>(a.dv), a.lddv,
+                  DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
+                          a.drop_seed ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
+                  (a.Lk + 31) / 32 * 32};
   dim3 grid((a.Lk + AB_T - 1) / AB_T, a.h, a.B);
   MTN_CHECK_CUDA(launch_kernel(attn_core_bwd_tc_kernel<DK>, grid, dim3(AB_THREADS), C::TOTAL, st, tq, tk, tv, tdo, p));
   return MTN_OK;
@@ -354,6 +369,7 @@ extern "C" int mtn_attn_core_bwd(const MtnAttnCoreBwdArgs* a, void* stream) {
               MTN_E_ALIGN, "attn_core_bwd: pointers must be 16-byte aligned");
   MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,
               "attn_core_bwd: mask_rows_q=%d must be 1 or Lq=%d", a->mask_rows_q, a->Lq);
+  MTN_REQUIRE(a->drop_thresh < 65536u, MTN_E_ARG, "attn_core_bwd: drop_thresh=%u", a->drop_thresh);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return a->d_k == 64 ? launch_attn_bwd<64>(*a, st) : launch_attn_bwd<32>(*a, st);
 }

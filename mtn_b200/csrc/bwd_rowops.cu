@@ -44,6 +44,8 @@ struct LnBwdParams {
   float eps; int rows; int has_ln;
   __half* dx16;   // optional f16 copy of dx: the operand of the next backward GEMM
   float* colsum;  // optional: += param_alpha * sum_rows dx  (bias gradient of the layer whose output this is)
+  DropCfg drop;   // !EMBED: dropout of the sublayer output that dx16 / colsum flow into (mtn.py:127), applied to
+                  // them only.  EMBED: dropout of the embedding (mtn.py:309), applied before the scatter.
 };
 
 template <int VPL, bool EMBED>
@@ -55,6 +57,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float dys = p.dy_scale ? __ldg(p.dy_scale) : 1.f;
   const float pal = p.param_alpha ? __ldg(p.param_alpha) : 1.f;
+  const unsigned long long dseed = p.drop.seed ? __ldg(p.drop.seed) : 0ull;
+  // keep decisions of this lane's float4 number i of `row` (columns 4*(lane+32i) .. +3): 4 bits
+  auto keep4 = [&](int row, int i) -> uint32_t {
+    if (p.drop.seed == nullptr) return 0xfu;
+    const int c4 = lane + 32 * i;
+    return (drop_keep8(p.drop, dseed, (unsigned long long)row * (D / 8) + (c4 >> 1)) >> (4 * (c4 & 1))) & 0xfu;
+  };
   float4 da_acc[VPL], db_acc[VPL], cs_acc[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) da_acc[i] = db_acc[i] = cs_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -73,6 +82,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
         const float4 e = __ldg(er + lane + 32 * i), q = __ldg(pr + lane + 32 * i);
         c[i] = make_float4(e.x * p.emb_scale + q.x, e.y * p.emb_scale + q.y, e.z * p.emb_scale + q.z,
                            e.w * p.emb_scale + q.w);
+        const uint32_t kb = keep4(row, i);
+        const float ik = p.drop.inv_keep;
+        c[i] = make_float4((kb & 1u) ? c[i].x * ik : 0.f, (kb & 2u) ? c[i].y * ik : 0.f, (kb & 4u) ? c[i].z * ik : 0.f,
+                           (kb & 8u) ? c[i].w * ik : 0.f);
       }
     } else {
       const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)row * D);
@@ -130,11 +143,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
       for (int i = 0; i < VPL; ++i) dxv[i] = g[i];
     }
     if (EMBED) {
-      const float f = p.emb_scale * pal;
       float* gr = p.dlut + (size_t)id * D;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
-        red_add_v4(gr + 4 * (lane + 32 * i), make_float4(dxv[i].x * f, dxv[i].y * f, dxv[i].z * f, dxv[i].w * f));
+      for (int i = 0; i < VPL; ++i) {
+        const uint32_t kb = keep4(row, i);
+        const float f = p.emb_scale * pal * p.drop.inv_keep;   // inv_keep == 1 without dropout
+        red_add_v4(gr + 4 * (lane + 32 * i), make_float4((kb & 1u) ? dxv[i].x * f : 0.f, (kb & 2u) ? dxv[i].y * f : 0.f,
+                                                         (kb & 4u) ? dxv[i].z * f : 0.f, (kb & 8u) ? dxv[i].w * f : 0.f));
+      }
     } else {
       float4* dxr = reinterpret_cast<float4*>(p.dx + (size_t)row * D);
 #pragma unroll
@@ -145,6 +161,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         dxr[lane + 32 * i] = o;
+        if (p.dx16 != nullptr || p.colsum != nullptr) {
+          const uint32_t kb = keep4(row, i);
+          const float ik = p.drop.inv_keep;
+          o = make_float4((kb & 1u) ? o.x * ik : 0.f, (kb & 2u) ? o.y * ik : 0.f, (kb & 4u) ? o.z * ik : 0.f,
+                          (kb & 8u) ? o.w * ik : 0.f);
+        }
         if (p.dx16 != nullptr)
           reinterpret_cast<uint2*>(p.dx16 + (size_t)row * D)[lane + 32 * i] =
               make_uint2(pack_f16x2_sat(o.x, o.y), pack_f16x2_sat(o.z, o.w));
@@ -234,9 +256,11 @@ template <typename TIn>
 __global__ void __launch_bounds__(256)
     cast_colsum_kernel(const TIn* __restrict__ src, int ld_src, __half* __restrict__ dst, int ld_dst,
                        const __half* __restrict__ relu_mask, int ld_mask, int rows, int vcols,
-                       const float* __restrict__ scale, const float* __restrict__ alpha, float* __restrict__ colsum) {
+                       const float* __restrict__ scale, const float* __restrict__ alpha, float* __restrict__ colsum,
+                       const DropCfg drop) {
   pdl_launch_dependents();
   pdl_wait();
+  const unsigned long long dseed = drop.seed ? __ldg(drop.seed) : 0ull;
   const int vc = blockIdx.x * 32 + threadIdx.x;
   const bool active = vc < vcols;
   const float sc = scale ? __ldg(scale) : 1.f;
@@ -259,10 +283,12 @@ __global__ void __launch_bounds__(256)
   for (int u = 0; u < U; ++u) {
     const int r = rb + 8 * u;
     if (r >= r_end) continue;
+    const uint32_t kb = drop.seed ? drop_keep8(drop, dseed, (unsigned long long)r * vcols + vc) : 0xffu;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float x = v[u][j];
       if (relu_mask != nullptr) x = m[u][j] > 0.f ? x : 0.f;
+      x = ((kb >> j) & 1u) ? x * drop.inv_keep : 0.f;
       x *= sc;
       v[u][j] = x;
       acc[j] += x;
@@ -329,6 +355,12 @@ __global__ void grad_scale_kernel(unsigned* __restrict__ slot, float* __restrict
   }
   out[0] = S;
   out[1] = 1.f / S;
+}
+
+__global__ void seed_bump_kernel(unsigned long long* seed) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *seed += 1ull;
 }
 
 // y = (accumulate ? y : 0) + x * alpha: un-scaling of an input gradient that leaves the backward pass
@@ -483,6 +515,9 @@ extern "C" int mtn_layernorm_bwd(const MtnLayerNormBwdArgs* a, void* stream) {
   p.x = a->x; p.a2 = a->a_2; p.dy = a->dy; p.dy_scale = a->dy_scale; p.param_alpha = a->param_alpha;
   p.dres = a->dres; p.dx = a->dx; p.da = a->da_2; p.db = a->db_2; p.eps = a->eps; p.rows = a->rows; p.has_ln = 1;
   p.dx16 = reinterpret_cast<__half*>(a->dx_f16); p.colsum = a->dx_colsum;
+  MTN_REQUIRE(a->drop_thresh < 65536u, MTN_E_ARG, "layernorm_bwd: drop_thresh=%u", a->drop_thresh);
+  p.drop = DropCfg{reinterpret_cast<const unsigned long long*>(a->drop_seed), a->drop_site, a->drop_thresh,
+                   a->drop_seed ? 1.f / (1.f - a->drop_thresh / 65536.f) : 1.f};
   const int d = a->d;
   const bool vec = (d == 128 || d == 256 || d == 512 || d == 1024) && aligned16(a->x) && aligned16(a->a_2) &&
                    aligned16(a->dy) && aligned16(a->dx) && (!a->dres || aligned16(a->dres));
@@ -499,7 +534,7 @@ extern "C" int mtn_layernorm_bwd(const MtnLayerNormBwdArgs* a, void* stream) {
   else if (vec && d == 512) MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<4, false>, dim3(blocks), dim3(256), 0, st, p));
   else if (vec && d == 1024) MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_kernel<8, false>, dim3(blocks), dim3(256), 0, st, p));
   else {
-    MTN_REQUIRE(a->dx_f16 == nullptr && a->dx_colsum == nullptr, MTN_E_SHAPE,
+    MTN_REQUIRE(a->dx_f16 == nullptr && a->dx_colsum == nullptr && a->drop_seed == nullptr, MTN_E_SHAPE,
                 "layernorm_bwd: dx_f16 / dx_colsum need d in {128, 256, 512, 1024} and 16-byte aligned pointers");
     MTN_CHECK_CUDA(launch_kernel(layernorm_bwd_generic_kernel, dim3((a->rows + 7) / 8), dim3(256), 0, st, p, d));
   }
@@ -522,6 +557,9 @@ extern "C" int mtn_embed_bwd(const MtnEmbedBwdArgs* a, void* stream) {
   p.ids = reinterpret_cast<const long long*>(a->ids); p.lut = a->lut; p.pe = a->pe; p.L = a->L; p.vocab = a->vocab;
   p.emb_scale = a->scale; p.a2 = a->a_2; p.dy = a->dy; p.dy_scale = nullptr; p.param_alpha = a->param_alpha;
   p.dlut = a->dlut; p.da = a->da_2; p.db = a->db_2; p.eps = a->eps; p.rows = a->rows; p.has_ln = a->a_2 != nullptr;
+  MTN_REQUIRE(a->drop_thresh < 65536u, MTN_E_ARG, "embed_bwd: drop_thresh=%u", a->drop_thresh);
+  p.drop = DropCfg{reinterpret_cast<const unsigned long long*>(a->drop_seed), a->drop_site, a->drop_thresh,
+                   a->drop_seed ? 1.f / (1.f - a->drop_thresh / 65536.f) : 1.f};
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -539,8 +577,12 @@ extern "C" int mtn_embed_bwd(const MtnEmbedBwdArgs* a, void* stream) {
 
 extern "C" int mtn_cast_colsum(const void* src, int src_is_f16, int ld_src, void* dst_f16, int ld_dst,
                                const void* relu_mask, int ld_mask, int rows, int cols, const float* scale,
-                               const float* alpha, float* colsum, void* stream) {
+                               const float* alpha, float* colsum, const void* drop_seed, uint32_t drop_site,
+                               uint32_t drop_thresh, void* stream) {
   using namespace mtn;
+  MTN_REQUIRE(drop_thresh < 65536u, MTN_E_ARG, "cast_colsum: drop_thresh=%u", drop_thresh);
+  const DropCfg drop{reinterpret_cast<const unsigned long long*>(drop_seed), drop_site, drop_thresh,
+                     drop_seed ? 1.f / (1.f - drop_thresh / 65536.f) : 1.f};
   MTN_REQUIRE(src && (dst_f16 || colsum), MTN_E_ARG, "cast_colsum: NULL pointer");
   MTN_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ld_src >= cols && ld_src % 8 == 0, MTN_E_SHAPE,
               "cast_colsum: rows=%d cols=%d ld_src=%d (cols and ld must be multiples of 8)", rows, cols, ld_src);
@@ -554,10 +596,10 @@ extern "C" int mtn_cast_colsum(const void* src, int src_is_f16, int ld_src, void
   const __half* mk = reinterpret_cast<const __half*>(relu_mask);
   if (src_is_f16)
     MTN_CHECK_CUDA(launch_kernel(cast_colsum_kernel<__half>, grid, block, 0, st, reinterpret_cast<const __half*>(src), ld_src,
-                                 d16, ld_dst, mk, ld_mask, rows, vcols, scale, alpha, colsum));
+                                 d16, ld_dst, mk, ld_mask, rows, vcols, scale, alpha, colsum, drop));
   else
     MTN_CHECK_CUDA(launch_kernel(cast_colsum_kernel<float>, grid, block, 0, st, reinterpret_cast<const float*>(src), ld_src,
-                                 d16, ld_dst, mk, ld_mask, rows, vcols, scale, alpha, colsum));
+                                 d16, ld_dst, mk, ld_mask, rows, vcols, scale, alpha, colsum, drop));
   return MTN_OK;
 }
 
@@ -570,6 +612,14 @@ extern "C" int mtn_grad_absmax(const float* x, size_t n, uint32_t* slot, void* s
   if (blocks > 1184) blocks = 1184;
   MTN_CHECK_CUDA(launch_kernel(absmax_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), x, n4,
                                reinterpret_cast<unsigned*>(slot)));
+  return MTN_OK;
+}
+
+extern "C" int mtn_seed_bump(uint64_t* seed, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(seed != nullptr, MTN_E_ARG, "seed_bump: NULL pointer");
+  MTN_CHECK_CUDA(launch_kernel(seed_bump_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream),
+                               reinterpret_cast<unsigned long long*>(seed)));
   return MTN_OK;
 }
 

@@ -242,4 +242,43 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
   return r;
 }
 
+
+// ---------------------------------------------------------------------------
+// dropout: counter-based RNG (Philox-4x32-10), regenerated -- never stored -- by the backward kernels.
+// One Philox call yields 8 x 16 random bits = the keep decisions of 8 CONSECUTIVE elements of a site's
+// logical [rows, cols] output: element e = row * cols + col, counter = (e >> 3, site), key = seed.
+// The seed lives in device memory (the CUDA-graph-captured step bumps it with a kernel), `site` numbers the
+// dropout applications of one forward pass.  thresh = round(p * 65536): keep <=> r16 >= thresh.
+// ---------------------------------------------------------------------------
+struct DropCfg {
+  const unsigned long long* seed;  // NULL: dropout disabled
+  uint32_t site;
+  uint32_t thresh;
+  float inv_keep;  // 1 / (1 - thresh / 65536)
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// bit j of the result: keep element (8 * idx8 + j)
+__device__ __forceinline__ uint32_t drop_keep8(const DropCfg& d, unsigned long long seed, unsigned long long idx8) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx8, (uint32_t)(idx8 >> 32), d.site, 0x6d746e62u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m |= ((w[j] & 0xffffu) >= d.thresh ? 1u : 0u) << (2 * j);
+    m |= ((w[j] >> 16) >= d.thresh ? 1u : 0u) << (2 * j + 1);
+  }
+  return m;
+}
+
 }  // namespace mtn

@@ -40,6 +40,9 @@ struct GemmEpi {
   int ld_mask;
   int accumulate;          // out32 += result (red.global.add), required for split-K
   int out16_pre_add;       // out16 receives the value BEFORE the addend (video encoder: relu(.) without PE)
+  float mask_scale;        // multiplies the elements that pass relu_mask (1/(1-p) of the dropout after the ReLU); 0 = 1
+  DropCfg drop;            // dropout of the result (element index = row * N + col)
+  int drop_after_add;      // 0: before the addend (SublayerConnection, mtn.py:127)  1: after it (PositionalEncoding, mtn.py:309)
   // strided batch (element strides between consecutive problems; batch == 1: unused)
   long long s_bias, s_add, s_out32, s_out16;
 };
@@ -220,6 +223,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool f16_only = epi0.out16 != nullptr && epi0.out32 == nullptr && epi0.addend == nullptr &&
                           epi0.relu_mask == nullptr;
     const float alpha = epi0.alpha != nullptr ? __ldg(epi0.alpha) : 1.f;
+    const unsigned long long drop_seed = epi0.drop.seed != nullptr ? __ldg(epi0.drop.seed) : 0ull;
+    const float mscale = epi0.mask_scale != 0.f ? epi0.mask_scale : 1.f;
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
     // shared-memory slots of the transpose tile (float4 units); (row & 7) == sub_r for every row this lane reads
@@ -275,12 +280,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (lane == 0) mbar_arrive(bar_acc_empty(buf));
           }
           uint32_t pk[16];
+          uint32_t keep8 = 0xffu;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float v0 = fmaf(__uint_as_float(acc[4 * j]), alpha, bb[j].x), v1 = fmaf(__uint_as_float(acc[4 * j + 1]), alpha, bb[j].y);
             float v2 = fmaf(__uint_as_float(acc[4 * j + 2]), alpha, bb[j].z), v3 = fmaf(__uint_as_float(acc[4 * j + 3]), alpha, bb[j].w);
             if (epi.act == MTN_ACT_RELU) {
               v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+            }
+            if (epi.drop.seed != nullptr) {  // this thread's row, columns cb + 4j .. +3: half of an 8-element group
+              if ((j & 1) == 0) keep8 = drop_keep8(epi.drop, drop_seed, ((unsigned long long)(m0 + q * 32 + lane) * N + cb + 4 * j) >> 3);
+              const uint32_t kb = keep8 >> (4 * (j & 1));
+              v0 = (kb & 1u) ? v0 * epi.drop.inv_keep : 0.f; v1 = (kb & 2u) ? v1 * epi.drop.inv_keep : 0.f;
+              v2 = (kb & 4u) ? v2 * epi.drop.inv_keep : 0.f; v3 = (kb & 8u) ? v3 * epi.drop.inv_keep : 0.f;
             }
             pk[2 * j] = pack_f16x2_sat(v0, v1);
             pk[2 * j + 1] = pack_f16x2_sat(v2, v3);
@@ -365,11 +377,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const __half2* hm = reinterpret_cast<const __half2*>(&mk[i]);
             const float2 m0_ = __half22float2(hm[0]), m1_ = __half22float2(hm[1]), m2_ = __half22float2(hm[2]),
                          m3_ = __half22float2(hm[3]);
-            x0.x = m0_.x > 0.f ? x0.x : 0.f; x0.y = m0_.y > 0.f ? x0.y : 0.f;
-            x0.z = m1_.x > 0.f ? x0.z : 0.f; x0.w = m1_.y > 0.f ? x0.w : 0.f;
-            x1.x = m2_.x > 0.f ? x1.x : 0.f; x1.y = m2_.y > 0.f ? x1.y : 0.f;
-            x1.z = m3_.x > 0.f ? x1.z : 0.f; x1.w = m3_.y > 0.f ? x1.w : 0.f;
+            x0.x = m0_.x > 0.f ? x0.x * mscale : 0.f; x0.y = m0_.y > 0.f ? x0.y * mscale : 0.f;
+            x0.z = m1_.x > 0.f ? x0.z * mscale : 0.f; x0.w = m1_.y > 0.f ? x0.w * mscale : 0.f;
+            x1.x = m2_.x > 0.f ? x1.x * mscale : 0.f; x1.y = m2_.y > 0.f ? x1.y * mscale : 0.f;
+            x1.z = m3_.x > 0.f ? x1.z * mscale : 0.f; x1.w = m3_.y > 0.f ? x1.w * mscale : 0.f;
           }
+          uint32_t keep8 = 0xffu;
+          if (epi.drop.seed != nullptr)
+            keep8 = drop_keep8(epi.drop, drop_seed, ((unsigned long long)(row0 + i * 8) * N + col) >> 3);
+          auto apply_drop = [&]() {
+            const float ik = epi.drop.inv_keep;
+            x0.x = (keep8 & 1u) ? x0.x * ik : 0.f; x0.y = (keep8 & 2u) ? x0.y * ik : 0.f;
+            x0.z = (keep8 & 4u) ? x0.z * ik : 0.f; x0.w = (keep8 & 8u) ? x0.w * ik : 0.f;
+            x1.x = (keep8 & 16u) ? x1.x * ik : 0.f; x1.y = (keep8 & 32u) ? x1.y * ik : 0.f;
+            x1.z = (keep8 & 64u) ? x1.z * ik : 0.f; x1.w = (keep8 & 128u) ? x1.w * ik : 0.f;
+          };
+          if (epi.drop.seed != nullptr && !epi.drop_after_add) apply_drop();
           uint4 pre16 = make_uint4(0u, 0u, 0u, 0u);
           if (epi.out16_pre_add)
             pre16 = make_uint4(pack_f16x2_sat(x0.x, x0.y), pack_f16x2_sat(x0.z, x0.w), pack_f16x2_sat(x1.x, x1.y),
@@ -378,6 +401,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             x0.x += res[2 * i].x; x0.y += res[2 * i].y; x0.z += res[2 * i].z; x0.w += res[2 * i].w;
             x1.x += res[2 * i + 1].x; x1.y += res[2 * i + 1].y; x1.z += res[2 * i + 1].z; x1.w += res[2 * i + 1].w;
           }
+          if (epi.drop.seed != nullptr && epi.drop_after_add) apply_drop();
           if (row_ok[i] && col_ok) {
             if (red_add) {
               float* o = epi.out32 + off32[i] + col;
@@ -464,8 +488,10 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
               reinterpret_cast<__half*>(a.out_f16), a.ld16, a.alpha, reinterpret_cast<const __half*>(a.relu_mask),
-              a.ld_mask, a.accumulate, a.out16_pre_add,
-              a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
+              a.ld_mask, a.accumulate, a.out16_pre_add, a.mask_scale,
+              DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
+                      a.drop_thresh ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
+              a.drop_after_add, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
   const int tiles_mn = tiles_n * ((tiles_m + CL - 1) / CL);
   // split-K (accumulating outputs only): cut the contraction so that the launch fills the machine about twice
@@ -514,6 +540,9 @@ static int validate_gemm(const MtnGemmArgs* a) {
   if (a->relu_mask)
     MTN_REQUIRE(aligned16(a->relu_mask) && a->ld_mask % 8 == 0 && a->ld_mask >= a->N, MTN_E_ALIGN,
                 "gemm: relu_mask alignment / ld_mask=%d", a->ld_mask);
+  if (a->drop_seed != nullptr)
+    MTN_REQUIRE(a->drop_thresh < 65536u && a->batch <= 1 && !a->accumulate, MTN_E_ARG,
+                "gemm: dropout needs thresh < 65536, no batch, no accumulate");
   if (a->accumulate)
     MTN_REQUIRE(a->out_f32 != nullptr && a->out_f16 == nullptr && a->bias == nullptr && a->addend == nullptr &&
                     a->act == MTN_ACT_NONE && a->relu_mask == nullptr,
@@ -575,6 +604,7 @@ static MtnGemmArgs from_linear(const MtnLinearArgs& a) {
   g.addend = a.addend; g.ld_add = a.ld_add; g.add_period = a.add_period;
   g.out_f32 = a.out_f32; g.ld32 = a.ld32; g.out_f16 = a.out_f16; g.ld16 = a.ld16;
   g.out16_pre_add = a.out16_pre_add;
+  g.drop_seed = a.drop_seed; g.drop_site = a.drop_site; g.drop_thresh = a.drop_thresh; g.drop_after_add = a.drop_after_add;
   g.batch = a.batch; g.stride_A = a.stride_A; g.stride_B = a.stride_W; g.stride_bias = a.stride_bias;
   g.stride_add = a.stride_add; g.stride_out_f32 = a.stride_out_f32; g.stride_out_f16 = a.stride_out_f16;
   return g;
@@ -598,10 +628,14 @@ __global__ void gemm_f16_check_kernel(const __half* A, int lda, int a_mn, const 
   if (epi.alpha) acc *= epi.alpha[0];
   if (epi.bias) acc += epi.bias[n];
   if (epi.act == MTN_ACT_RELU) acc = fmaxf(acc, 0.f);
-  if (epi.relu_mask && !(__half2float(epi.relu_mask[(size_t)m * epi.ld_mask + n]) > 0.f)) acc = 0.f;
+  if (epi.relu_mask) acc = (__half2float(epi.relu_mask[(size_t)m * epi.ld_mask + n]) > 0.f) ? acc * (epi.mask_scale != 0.f ? epi.mask_scale : 1.f) : 0.f;
   const float pre = acc;
+  bool keep = true;
+  if (epi.drop.seed) keep = (drop_keep8(epi.drop, epi.drop.seed[0], ((unsigned long long)m * N + n) >> 3) >> (n & 7)) & 1u;
+  if (epi.drop.seed && !epi.drop_after_add) acc = keep ? acc * epi.drop.inv_keep : 0.f;
   if (epi.addend && !epi.accumulate)
     acc += epi.addend[(size_t)(epi.add_period > 0 ? m % epi.add_period : m) * epi.ld_add + n];
+  if (epi.drop.seed && epi.drop_after_add) acc = keep ? acc * epi.drop.inv_keep : 0.f;
   if (epi.out32) {
     if (epi.accumulate) epi.out32[(size_t)m * epi.ld32 + n] += acc;
     else epi.out32[(size_t)m * epi.ld32 + n] = acc;
@@ -617,7 +651,10 @@ static int run_check_gemm(const MtnGemmArgs* a, void* stream) {
   if (rc) return rc;
   GemmEpi epi{a->bias, a->act, a->addend, a->ld_add, a->add_period, a->out_f32, a->ld32,
               reinterpret_cast<__half*>(a->out_f16), a->ld16, a->alpha, reinterpret_cast<const __half*>(a->relu_mask),
-              a->ld_mask, a->accumulate, a->out16_pre_add, 0, 0, 0, 0};
+              a->ld_mask, a->accumulate, a->out16_pre_add, a->mask_scale,
+              DropCfg{reinterpret_cast<const unsigned long long*>(a->drop_seed), a->drop_site, a->drop_thresh,
+                      a->drop_thresh ? 1.f / (1.f - a->drop_thresh / 65536.f) : 1.f},
+              a->drop_after_add, 0, 0, 0, 0};
   MTN_REQUIRE(a->batch <= 1, MTN_E_ARG, "check_gemm: the check kernel is not batched");
   dim3 grid((a->N + 127) / 128, a->M);
   gemm_f16_check_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -653,7 +690,7 @@ extern "C" int mtn_linear_dgrad(const MtnLinearDgradArgs* a, void* stream) {
   g.B = a->W; g.ldb = a->ldw; g.b_mn = 1;
   g.M = a->M; g.N = a->K; g.K = a->N;
   g.alpha = a->alpha;
-  g.relu_mask = a->relu_mask; g.ld_mask = a->ld_mask;
+  g.relu_mask = a->relu_mask; g.ld_mask = a->ld_mask; g.mask_scale = a->mask_scale;
   g.addend = a->addend; g.ld_add = a->ld_add;
   g.out_f32 = a->dX_f32; g.ld32 = a->ld32; g.out_f16 = a->dX_f16; g.ld16 = a->ld16;
   g.batch = a->batch; g.stride_A = a->stride_dY; g.stride_B = a->stride_W;

@@ -147,10 +147,12 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
     embed_rows_kernel(const long long* __restrict__ ids, const float* __restrict__ lut, const float* __restrict__ pe,
                       int rows, int L, int vocab, float scale, const float* __restrict__ a2,
-                      const float* __restrict__ b2, float eps, float* __restrict__ y32, __half* __restrict__ y16) {
+                      const float* __restrict__ b2, float eps, float* __restrict__ y32, __half* __restrict__ y16,
+                      const DropCfg drop) {
   constexpr int D = 128 * VPL;
   pdl_launch_dependents();
   pdl_wait();
+  const unsigned long long dseed = drop.seed ? __ldg(drop.seed) : 0ull;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -164,6 +166,13 @@ __global__ void __launch_bounds__(256)
   for (int i = 0; i < VPL; ++i) {
     const float4 e = __ldg(er + lane + 32 * i), p = __ldg(pr + lane + 32 * i);
     v[i] = make_float4(e.x * scale + p.x, e.y * scale + p.y, e.z * scale + p.z, e.w * scale + p.w);
+    if (drop.seed != nullptr) {  // PositionalEncoding's dropout (mtn.py:309), before the stream LayerNorm
+      const int c4 = lane + 32 * i;
+      const uint32_t kb = drop_keep8(drop, dseed, (unsigned long long)row * (D / 8) + (c4 >> 1)) >> (4 * (c4 & 1));
+      const float ik = drop.inv_keep;
+      v[i] = make_float4((kb & 1u) ? v[i].x * ik : 0.f, (kb & 2u) ? v[i].y * ik : 0.f, (kb & 4u) ? v[i].z * ik : 0.f,
+                         (kb & 8u) ? v[i].w * ik : 0.f);
+    }
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   float inv = 1.f;
@@ -464,7 +473,17 @@ extern "C" int mtn_label_smoothing_loss_fwd(const float* logits, int ld, int row
 extern "C" int mtn_embed_fwd(const int64_t* ids, const float* lut, const float* pe, int rows, int L, int d, int vocab,
                              float scale, const float* a_2, const float* b_2, float eps, float* y_f32, void* y_f16,
                              void* stream) {
+  return mtn_embed_dropout_fwd(ids, lut, pe, rows, L, d, vocab, scale, a_2, b_2, eps, y_f32, y_f16, nullptr, 0, 0, stream);
+}
+
+extern "C" int mtn_embed_dropout_fwd(const int64_t* ids, const float* lut, const float* pe, int rows, int L, int d,
+                                     int vocab, float scale, const float* a_2, const float* b_2, float eps, float* y_f32,
+                                     void* y_f16, const void* drop_seed, uint32_t drop_site, uint32_t drop_thresh,
+                                     void* stream) {
   using namespace mtn;
+  MTN_REQUIRE(drop_thresh < 65536u, MTN_E_ARG, "embed: drop_thresh=%u", drop_thresh);
+  const DropCfg drop{reinterpret_cast<const unsigned long long*>(drop_seed), drop_site, drop_thresh,
+                     drop_seed ? 1.f / (1.f - drop_thresh / 65536.f) : 1.f};
   MTN_REQUIRE(ids && lut && pe && (y_f32 || y_f16), MTN_E_ARG, "embed: NULL pointer");
   MTN_REQUIRE((a_2 == nullptr) == (b_2 == nullptr), MTN_E_ARG, "embed: a_2 and b_2 must be given together");
   MTN_REQUIRE(rows > 0 && L > 0 && vocab > 0, MTN_E_SHAPE, "embed: rows=%d L=%d vocab=%d", rows, L, vocab);
@@ -475,7 +494,7 @@ extern "C" int mtn_embed_fwd(const int64_t* ids, const float* lut, const float* 
   __half* y16 = reinterpret_cast<__half*>(y_f16);
   const long long* ids64 = reinterpret_cast<const long long*>(ids);
   dim3 grid((rows + 7) / 8), block(256);
-#define MTN_EMBED(V) MTN_CHECK_CUDA(launch_kernel(embed_rows_kernel<V>, grid, block, 0, st, ids64, lut, pe, rows, L, vocab, scale, a_2, b_2, eps, y_f32, y16))
+#define MTN_EMBED(V) MTN_CHECK_CUDA(launch_kernel(embed_rows_kernel<V>, grid, block, 0, st, ids64, lut, pe, rows, L, vocab, scale, a_2, b_2, eps, y_f32, y16, drop))
   if (d == 128) MTN_EMBED(1); else if (d == 256) MTN_EMBED(2); else if (d == 512) MTN_EMBED(4); else MTN_EMBED(8);
 #undef MTN_EMBED
   return MTN_OK;

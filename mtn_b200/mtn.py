@@ -338,7 +338,6 @@ class Decoder(nn.Module):
             # training (train.py:33): one autograd.Function for the whole cascade, hand-written backward
             if not x.is_cuda:
                 raise _lib.MtnError("mtn_b200 hot path needs CUDA tensors (no CPU implementation)")
-            AG.require_no_dropout(self)
             meta = {"vid_mask": list(vid_mask), "his_mask": his_mask, "cap_mask": cap_mask, "q_mask": query_mask,
                     "tgt_mask": tgt_mask, "ae_features": auto_encoded_features,
                     "ae_list": isinstance(auto_encoded_ft, (list, tuple))}
@@ -475,8 +474,8 @@ class VideoEncoder(nn.Sequential):
         else:
             x16 = _lib.cast_f16(ft.detach().contiguous().float().view(B * Lv, Fdim))
         if AG.recording(self):             # training: the features are data, only W / b receive gradients
-            AG.require_no_dropout(self)
-            out = AG.VideoEncoderFn.apply(x16, lin.weight, lin.bias, W["w"], pos.pe[0, :Lv], Lv)
+            out = AG.VideoEncoderFn.apply(x16, lin.weight, lin.bias, W["w"], pos.pe[0, :Lv], Lv,
+                                          pos.dropout.p if self.training else 0.0)
             return out.view(B, Lv, -1)
         ensure_inference(self, ft)
         out = torch.empty(B * Lv, lin.out_features, dtype=torch.float32, device=ft.device)
@@ -521,10 +520,9 @@ class EncoderDecoder(nn.Module):
         the Encoder's stream LayerNorm ``norm`` -- one fused kernel."""
         emb, pos = seq[0], seq[1]
         if AG.recording(seq) or (norm is not None and AG.recording(norm)):
-            AG.require_no_dropout(seq)
             return AG.EmbedFn.apply(ids, emb.lut.weight, pos.pe[0], math.sqrt(emb.d_model),
                                     None if norm is None else norm.a_2, None if norm is None else norm.b_2,
-                                    0.0 if norm is None else norm.eps)
+                                    0.0 if norm is None else norm.eps, pos.dropout.p if seq.training else 0.0)
         ensure_inference(self, emb.lut.weight.data)
         B, L = ids.shape
         out = torch.empty(B, L, emb.d_model, dtype=torch.float32, device=ids.device)

@@ -109,14 +109,15 @@ class DecoderTrainer(object):
 
         def packed(key, l, m):
             return {"w_qkv": H[(key, l, "wqkv")], "b_qkv": P[(key, l, "bqkv")], "w_o": H[(key, l, "wo")],
-                    "b_o": P[(key, l, "bo")], "h": m.h, "d_k": m.d_k}
+                    "b_o": P[(key, l, "bo")], "h": m.h, "d_k": m.d_k, "mod": m}
 
         def hoisted_site(key, l, m):     # only the query projection is used per site ([:d] of a [d, d] view is itself)
             return {"w_qkv": H[(key, l, "wq")], "b_qkv": P[(key, l, "bq")], "w_o": H[(key, l, "wo")],
-                    "b_o": P[(key, l, "bo")], "h": m.h, "d_k": m.d_k}
+                    "b_o": P[(key, l, "bo")], "h": m.h, "d_k": m.d_k, "mod": m}
 
-        def ffn(key, l):
-            return {"w_1": H[(key, l, "w1")], "b_1": P[(key, l, "b1")], "w_2": H[(key, l, "w2")], "b_2": P[(key, l, "b2")]}
+        def ffn(key, l, m):
+            return {"w_1": H[(key, l, "w1")], "b_1": P[(key, l, "b1")], "w_2": H[(key, l, "w2")], "b_2": P[(key, l, "b2")],
+                    "mod": m}
 
         W = {"M": M, "d": d, "N": len(layers), "layers": []}
         for name, key in (("kv_his", ("his", 0)), ("kv_cap", ("cap", 0)), ("kv_q", ("src", 0))):
@@ -130,8 +131,9 @@ class DecoderTrainer(object):
                 "ae_self": [packed(("ae_self", i), l, L.auto_encoder_self_attn[i]) for i in range(M)],
                 "ae_vid": [hoisted_site(("ae_vid", i), l, L.auto_encoder_vid_attn[i]) for i in range(M)],
                 "ae_attn": [packed(("ae_attn", i), l, L.auto_encoder_attn[i]) for i in range(M)],
-                "ae_ffn": [ffn(("ae_ffn", i), l) for i in range(M)],
-                "ffn": ffn(("ffn", 0), l),
+                "ae_ffn": [ffn(("ae_ffn", i), l, L.auto_encoder_feed_forward[i]) for i in range(M)],
+                "ffn": ffn(("ffn", 0), l, L.feed_forward),
+                "sub": L.sublayer,
                 "ln": [(P[("ln", l, c)][0], P[("ln", l, c)][1], s.norm.eps) for c, s in enumerate(L.sublayer)],
             })
         W["norm"] = (P[("norm",)][0], P[("norm",)][1], dec.norm.eps)
@@ -159,8 +161,19 @@ class DecoderTrainer(object):
 
     # ------------------------------------------------------------------ forward building blocks (taped)
     @staticmethod
-    def _attn_fwd(tape, x_in, ln, A, B, Lq, Lk, kv, k_col, v_col, bits, names):
-        """One pre-norm residual attention site (mtn.py:125-127 around :248-267).  kv=None: self-attention."""
+    def _drop(dr, p):
+        """Next dropout site of this forward pass: (seed, site, thresh) or None (eval mode / p == 0)."""
+        if dr is None or p <= 0:
+            return None
+        dr["site"] += 1
+        return _lib.drop_cfg(dr["seed"], dr["site"], p)
+
+    @classmethod
+    def _attn_fwd(cls, tape, x_in, ln, A, B, Lq, Lk, kv, k_col, v_col, bits, names, dr=None, p_sub=0.0):
+        """One pre-norm residual attention site (mtn.py:125-127 around :248-267).  kv=None: self-attention.
+        Training: dropout of the probabilities (mtn.py:230) and of the sublayer output (mtn.py:127)."""
+        drop_p = cls._drop(dr, A["mod"].dropout.p)
+        drop_o = cls._drop(dr, p_sub)
         rows, d = x_in.shape
         dev = x_in.device
         f16 = torch.float16
@@ -176,32 +189,38 @@ class DecoderTrainer(object):
             q, k, v = qbuf, kv[:, k_col:k_col + d], kv[:, v_col:v_col + d]
         o16 = torch.empty(rows, d, dtype=f16, device=dev)
         stats = torch.empty(B, A["h"], Lq, 2, dtype=torch.float32, device=dev)
-        _lib.attn_core(q, k, v, B, A["h"], Lq, Lk, A["d_k"], o16, mask_bits=bits, stats=stats)
+        _lib.attn_core(q, k, v, B, A["h"], Lq, Lk, A["d_k"], o16, mask_bits=bits, stats=stats, drop=drop_p)
         x_out = torch.empty_like(x_in)
-        _lib.linear(o16, A["w_o"], A["b_o"], addend=x_in, out_f32=x_out)
+        _lib.linear(o16, A["w_o"], A["b_o"], addend=x_in, out_f32=x_out, drop=drop_o)
         tape.append(("attn", dict(x_in=x_in, ln=ln, A=A, B=B, Lq=Lq, Lk=Lk, self_attn=kv is None, xn16=xn16, q=q, k=k,
-                                  v=v, o16=o16, stats=stats, bits=bits, names=names)))
+                                  v=v, o16=o16, stats=stats, bits=bits, names=names, drop_p=drop_p, drop_o=drop_o)))
         return x_out
 
-    @staticmethod
-    def _ffn_fwd(tape, x_in, ln, Fw, names, want16=False):
+    @classmethod
+    def _ffn_fwd(cls, tape, x_in, ln, Fw, names, want16=False, dr=None, p_sub=0.0):
+        drop_h = cls._drop(dr, Fw["mod"].dropout.p)          # dropout of relu(w_1 x) (mtn.py:280)
+        drop_o = cls._drop(dr, p_sub)                        # dropout of the sublayer output (mtn.py:127)
         rows, d = x_in.shape
         dev = x_in.device
         f16 = torch.float16
         xn16 = torch.empty(rows, d, dtype=f16, device=dev)
         _lib.layernorm(x_in, ln[0], ln[1], ln[2], out_f16=xn16)
         hid = torch.empty(rows, Fw["w_1"].shape[0], dtype=f16, device=dev)
-        _lib.linear(xn16, Fw["w_1"], Fw["b_1"], act=_lib.ACT_RELU, out_f16=hid)
+        _lib.linear(xn16, Fw["w_1"], Fw["b_1"], act=_lib.ACT_RELU, out_f16=hid, drop=drop_h)
         x_out = torch.empty_like(x_in)
         out16 = torch.empty(rows, d, dtype=f16, device=dev) if want16 else None
-        _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x_in, out_f32=x_out, out_f16=out16)
-        tape.append(("ffn", dict(x_in=x_in, ln=ln, Fw=Fw, xn16=xn16, hid=hid, names=names)))
+        _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x_in, out_f32=x_out, out_f16=out16, drop=drop_o)
+        tape.append(("ffn", dict(x_in=x_in, ln=ln, Fw=Fw, xn16=xn16, hid=hid, names=names, drop_h=drop_h, drop_o=drop_o)))
         return x_out, out16
 
     # ------------------------------------------------------------------ forward
-    def forward(self, vid_ft, vid_mask, x, his, his_mask, cap, cap_mask, qm, q_mask, tgt_mask, ae_ft, ae_features):
-        """Returns (out [B,T,d], [ae_out_i [B,La,d]], ctx) with ctx the tape for ``backward``."""
+    def forward(self, vid_ft, vid_mask, x, his, his_mask, cap, cap_mask, qm, q_mask, tgt_mask, ae_ft, ae_features,
+                seed=None):
+        """Returns (out [B,T,d], [ae_out_i [B,La,d]], ctx) with ctx the tape for ``backward``.
+        seed: 1-element int64 device tensor -- the dropout seed of THIS pass (training mode); None: no dropout."""
         W = self.weights()
+        dr = {"seed": seed, "site": 0} if (seed is not None and self.dec.training) else None
+        psub = lambda l, c: (W["layers"][l]["sub"][c].dropout.p if dr is not None else 0.0)
         d, N, M = W["d"], W["N"], W["M"]
         B, T, _ = x.shape
         dev = x.device
@@ -264,10 +283,11 @@ class DecoderTrainer(object):
                     Lw = W["layers"][l]
                     c0 = 4 + 4 * i
                     ae = self._attn_fwd(tape, ae, Lw["ln"][c0], Lw["ae_self"][i], B, La, La, None, 0, 0, b_ae,
-                                        ("ae_self", l, i, c0))
+                                        ("ae_self", l, i, c0), dr, psub(l, c0))
                     ae = self._attn_fwd(tape, ae, Lw["ln"][c0 + 1], Lw["ae_vid"][i], B, La, Lv, kv_vid, l * 2 * d,
-                                        l * 2 * d + d, b_vid, ("ae_vid", l, i, c0 + 1))
-                    ae, a16 = self._ffn_fwd(tape, ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], ("ae_ffn", l, i, c0 + 2), want16=True)
+                                        l * 2 * d + d, b_vid, ("ae_vid", l, i, c0 + 1), dr, psub(l, c0 + 1))
+                    ae, a16 = self._ffn_fwd(tape, ae, Lw["ln"][c0 + 2], Lw["ae_ffn"][i], ("ae_ffn", l, i, c0 + 2), want16=True,
+                                            dr=dr, p_sub=psub(l, c0 + 2))
                     A2 = Lw["ae_attn"][i]
                     kv = torch.empty(B * La, 2 * d, dtype=f16, device=dev)
                     _lib.linear(a16, A2["w_qkv"][d:], A2["b_qkv"][d:], out_f16=kv)
@@ -304,16 +324,19 @@ class DecoderTrainer(object):
         for l in range(N):
             Lw = W["layers"][l]
             kc, vc = l * 2 * d, l * 2 * d + d
-            xs = self._attn_fwd(tape, xs, Lw["ln"][0], Lw["self"], B, T, T, None, 0, 0, bits_t, ("self", l, 0, 0))
+            xs = self._attn_fwd(tape, xs, Lw["ln"][0], Lw["self"], B, T, T, None, 0, 0, bits_t, ("self", l, 0, 0), dr,
+                                psub(l, 0))
             xs = self._attn_fwd(tape, xs, Lw["ln"][1], Lw["his"], B, T, his.shape[1], kv_his, kc, vc, b_his,
-                                ("his", l, 0, 1))
+                                ("his", l, 0, 1), dr, psub(l, 1))
             for c, (name, kvm, bm, Lm) in enumerate(order):
-                xs = self._attn_fwd(tape, xs, Lw["ln"][2 + c], Lw[name], B, T, Lm, kvm, kc, vc, bm, (name, l, 0, 2 + c))
+                xs = self._attn_fwd(tape, xs, Lw["ln"][2 + c], Lw[name], B, T, Lm, kvm, kc, vc, bm, (name, l, 0, 2 + c), dr,
+                                    psub(l, 2 + c))
             for i in range(M):
                 main.wait_event(ev_ae[l][i])
                 xs = self._attn_fwd(tape, xs, Lw["ln"][7 + 4 * i], Lw["ae_attn"][i], B, T, La, kv_ae[i][l], 0, d, b_ae,
-                                    ("ae_attn", l, i, 7 + 4 * i))
-            xs, _ = self._ffn_fwd(tape, xs, Lw["ln"][4 + 4 * M], Lw["ffn"], ("ffn", l, 0, 4 + 4 * M))
+                                    ("ae_attn", l, i, 7 + 4 * i), dr, psub(l, 7 + 4 * i))
+            xs, _ = self._ffn_fwd(tape, xs, Lw["ln"][4 + 4 * M], Lw["ffn"], ("ffn", l, 0, 4 + 4 * M), dr=dr,
+                                  p_sub=psub(l, 4 + 4 * M))
         out = torch.empty(B * T, d, dtype=torch.float32, device=dev)
         _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=out)
         tape.append(("norm", dict(x_in=xs, ln=W["norm"], names=("norm",))))
@@ -412,7 +435,7 @@ class DecoderTrainer(object):
         ln = t["ln"]
         _lib.layernorm_bwd(t["x_in"], ln[0], ln[2], dy, dx, dres=dres, da_2=gab[0], db_2=gab[1], dy_scale=dy_scale,
                            param_alpha=invS, dx_f16=None if nxt is None else nxt[0],
-                           dx_colsum=None if nxt is None else nxt[1])
+                           dx_colsum=None if nxt is None else nxt[1], drop=None if nxt is None else nxt[2])
 
     def _flush(self, bk, wq):
         """Launch the collected weight-gradient GEMMs on the wgrad stream, after everything issued so far on the
@@ -443,7 +466,7 @@ class DecoderTrainer(object):
         # ---- output projection (mtn.py:267) + residual (mtn.py:127)
         if dx16 is None:
             dx16 = torch.empty(rows, d, dtype=f16, device=dev)
-            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS)
+            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS, drop=t["drop_o"])
         do16 = torch.empty(rows, d, dtype=f16, device=dev)
         _lib.linear_dgrad(dx16, A["w_o"], out_f16=do16)
         wq.append(lambda: _lib.linear_wgrad(dx16, t["o16"], G[(gk, l, "wo")], alpha=invS))
@@ -457,7 +480,7 @@ class DecoderTrainer(object):
         else:
             dkd, dvd = dkv
         _lib.attn_core_bwd(t["q"], t["k"], t["v"], do16, t["stats"], delta, B, h, Lq, Lk, dk_, dq32, dkd, dvd,
-                           mask_bits=t["bits"])
+                           mask_bits=t["bits"], drop=t["drop_p"])
         # ---- Q (or QKV) projection
         dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
         if t["self_attn"]:
@@ -487,9 +510,12 @@ class DecoderTrainer(object):
         gk = (key, i)
         if dx16 is None:
             dx16 = torch.empty(rows, d, dtype=f16, device=dev)
-            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS)
+            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS, drop=t["drop_o"])
         dhid = torch.empty(rows, Fw["w_1"].shape[0], dtype=f16, device=dev)
-        _lib.linear_dgrad(dx16, Fw["w_2"], relu_mask=t["hid"], out_f16=dhid)        # through the ReLU (mtn.py:280)
+        # through the ReLU and the hidden dropout (mtn.py:280): the saved hidden activation is > 0 exactly where the
+        # unit was active AND kept; kept gradients are scaled by 1/(1-p)
+        ms = 1.0 / (1.0 - t["drop_h"][2] / 65536.0) if t["drop_h"] is not None else 0.0
+        _lib.linear_dgrad(dx16, Fw["w_2"], relu_mask=t["hid"], out_f16=dhid, mask_scale=ms)
         wq.append(lambda: _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS))
         wq.append(lambda: _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS))
         wq.append(lambda: _lib.cast_colsum(dhid, colsum=G[(gk, l, "b1")], alpha=invS))   # bias gradient: off the critical path too
@@ -556,7 +582,7 @@ class DecoderTrainer(object):
             """(dx16, bias gradient) the LayerNorm backward of seq[k] should produce for seq[k+1], or None."""
             if k + 1 >= len(seq) or not fused(seq[k + 1]):
                 return None
-            return (torch.empty(rows, d, dtype=f16, device=dev), bias_of(seq[k + 1]))
+            return (torch.empty(rows, d, dtype=f16, device=dev), bias_of(seq[k + 1]), seq[k + 1][1]["drop_o"])
 
         kind, t = tape[-1]
         seq = list(reversed(tape[:-1]))
