@@ -81,7 +81,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DK, int ATT_KT>
+template <int DK, int ATT_KT, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
     attn_core_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     const uint32_t sw = (uint32_t)(row & 7);
     constexpr int NCH = ATT_KT / 32;
     uint32_t g = 0;
-    const unsigned long long dseed = p.drop.seed != nullptr ? __ldg(p.drop.seed) : 0ull;
+    const unsigned long long dseed = (DROP && p.drop.seed != nullptr) ? __ldg(p.drop.seed) : 0ull;
 
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 #pragma unroll
             for (int i = 0; i < 32; ++i) e[i] = 0.f;
           }
-          if (p.drop.seed != nullptr && nvalid > 0) {
+          if (DROP && p.drop.seed != nullptr && nvalid > 0) {
             // dropout AFTER the softmax: the row sum above keeps every key, only the P V operand is thinned
             const unsigned long long e0 =
                 ((((unsigned long long)b * p.h + hd) * p.Lq + min(qi, p.Lq - 1)) * p.Lk32 + k0) >> 3;
@@ -386,12 +386,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   }
 }
 
-template <int DK, int ATT_KT>
+template <int DK, int ATT_KT, bool DROP>
 static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   using C = AttnCfg<DK, ATT_KT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tc_kernel<DK, ATT_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tc_kernel<DK, ATT_KT, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::TOTAL));
     attr_set = true;
   }
@@ -419,7 +419,7 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
     slots = 2 * n;
   }
   dim3 grid(n_items < slots ? n_items : slots);
-  MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, p));
+  MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT, DROP>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, p));
   return MTN_OK;
 }
 
@@ -487,8 +487,12 @@ extern "C" int mtn_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
   int rc = mtn::validate_attn(a);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->Lk <= 64) return a->d_k == 64 ? mtn::launch_attn<64, 64>(*a, st) : mtn::launch_attn<32, 64>(*a, st);
-  return a->d_k == 64 ? mtn::launch_attn<64, 96>(*a, st) : mtn::launch_attn<32, 96>(*a, st);
+  if (a->drop_seed != nullptr) {      // training: probability dropout compiled in
+    if (a->Lk <= 64) return a->d_k == 64 ? mtn::launch_attn<64, 64, true>(*a, st) : mtn::launch_attn<32, 64, true>(*a, st);
+    return a->d_k == 64 ? mtn::launch_attn<64, 96, true>(*a, st) : mtn::launch_attn<32, 96, true>(*a, st);
+  }
+  if (a->Lk <= 64) return a->d_k == 64 ? mtn::launch_attn<64, 64, false>(*a, st) : mtn::launch_attn<32, 64, false>(*a, st);
+  return a->d_k == 64 ? mtn::launch_attn<64, 96, false>(*a, st) : mtn::launch_attn<32, 96, false>(*a, st);
 }
 
 extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {

@@ -78,7 +78,9 @@ struct GemmSmem {
 // [64 k-rows x 64 mn-columns] (128-byte swizzled rows), i.e. the canonical UMMA MN-major layout
 // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = 8192 B (next 64 mn), SBO = 1024 B (next 8 k).
 // ksplit > 1: tile index also enumerates contraction slices of kb_per_split k-blocks (split-K).
-template <int BN, int STAGES, int CL, int A_MN, int B_MN>
+// DROP: compile the dropout of the result into the epilogue (training forward only; the inference kernels carry
+// none of its registers or branches).
+template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmEpi epi0, int M, int N, int K, int tiles_n, int tiles_per_batch, int num_tiles,
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                          (epi0.addend != nullptr && epi0.addend == epi0.out32 && epi0.add_period == 0 &&
                           epi0.ld_add == epi0.ld32 && epi0.out16 == nullptr && epi0.s_add == epi0.s_out32);
     const bool has_add = epi0.addend != nullptr && epi0.accumulate == 0;
+    constexpr bool MASKED = (A_MN == 0 && B_MN == 1);  // only the data-gradient form carries the ReLU-mask epilogue
     const bool f16_only = epi0.out16 != nullptr && epi0.out32 == nullptr && epi0.addend == nullptr &&
-                          epi0.relu_mask == nullptr;
+                          !(MASKED && epi0.relu_mask != nullptr);
     const float alpha = epi0.alpha != nullptr ? __ldg(epi0.alpha) : 1.f;
-    const unsigned long long drop_seed = epi0.drop.seed != nullptr ? __ldg(epi0.drop.seed) : 0ull;
+    const unsigned long long drop_seed = (DROP && epi0.drop.seed != nullptr) ? __ldg(epi0.drop.seed) : 0ull;
     const float mscale = epi0.mask_scale != 0.f ? epi0.mask_scale : 1.f;
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (epi.act == MTN_ACT_RELU) {
               v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
             }
-            if (epi.drop.seed != nullptr) {  // this thread's row, columns cb + 4j .. +3: half of an 8-element group
+            if (DROP && epi.drop.seed != nullptr) {  // this thread's row, columns cb + 4j .. +3: half of an 8-element group
               if ((j & 1) == 0) keep8 = drop_keep8(epi.drop, drop_seed, ((unsigned long long)(m0 + q * 32 + lane) * N + cb + 4 * j) >> 3);
               const uint32_t kb = keep8 >> (4 * (j & 1));
               v0 = (kb & 1u) ? v0 * epi.drop.inv_keep : 0.f; v1 = (kb & 2u) ? v1 * epi.drop.inv_keep : 0.f;
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         float4 res[8];
         uint4 mk[4];
-        if (epi.relu_mask != nullptr) {
+        if (MASKED && epi.relu_mask != nullptr) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             mk[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
             x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
           }
-          if (epi.relu_mask != nullptr) {  // ReLU backward: keep the gradient where the forward activation was > 0
+          if (MASKED && epi.relu_mask != nullptr) {  // ReLU backward: keep the gradient where the forward activation was > 0
             const __half2* hm = reinterpret_cast<const __half2*>(&mk[i]);
             const float2 m0_ = __half22float2(hm[0]), m1_ = __half22float2(hm[1]), m2_ = __half22float2(hm[2]),
                          m3_ = __half22float2(hm[3]);
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             x1.z = m3_.x > 0.f ? x1.z * mscale : 0.f; x1.w = m3_.y > 0.f ? x1.w * mscale : 0.f;
           }
           uint32_t keep8 = 0xffu;
-          if (epi.drop.seed != nullptr)
+          if (DROP && epi.drop.seed != nullptr)
             keep8 = drop_keep8(epi.drop, drop_seed, ((unsigned long long)(row0 + i * 8) * N + col) >> 3);
           auto apply_drop = [&]() {
             const float ik = epi.drop.inv_keep;
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             x1.x = (keep8 & 16u) ? x1.x * ik : 0.f; x1.y = (keep8 & 32u) ? x1.y * ik : 0.f;
             x1.z = (keep8 & 64u) ? x1.z * ik : 0.f; x1.w = (keep8 & 128u) ? x1.w * ik : 0.f;
           };
-          if (epi.drop.seed != nullptr && !epi.drop_after_add) apply_drop();
+          if (DROP && epi.drop.seed != nullptr && !epi.drop_after_add) apply_drop();
           uint4 pre16 = make_uint4(0u, 0u, 0u, 0u);
           if (epi.out16_pre_add)
             pre16 = make_uint4(pack_f16x2_sat(x0.x, x0.y), pack_f16x2_sat(x0.z, x0.w), pack_f16x2_sat(x1.x, x1.y),
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             x0.x += res[2 * i].x; x0.y += res[2 * i].y; x0.z += res[2 * i].z; x0.w += res[2 * i].w;
             x1.x += res[2 * i + 1].x; x1.y += res[2 * i + 1].y; x1.z += res[2 * i + 1].z; x1.w += res[2 * i + 1].w;
           }
-          if (epi.drop.seed != nullptr && epi.drop_after_add) apply_drop();
+          if (DROP && epi.drop.seed != nullptr && epi.drop_after_add) apply_drop();
           if (row_ok[i] && col_ok) {
             if (red_add) {
               float* o = epi.out32 + off32[i] + col;
@@ -456,12 +459,12 @@ static int make_operand_map(CUtensorMap* tm, const void* p, int mn_major, int MN
   return make_tmap_3d_f16(tm, p, K, MN, batch, ld, batch > 1 ? (uint64_t)stride : (uint64_t)MN * ld, BK, box_mn, TM_SWZ_128);
 }
 
-template <int BN, int STAGES, int CL, int A_MN, int B_MN>
+template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP = 0>
 static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   static int max_clusters = 0;  // co-resident clusters (1 CTA per SM)
   if (max_clusters == 0) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN>,
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     if (CL == 1) {
       max_clusters = g_num_sms;
@@ -475,7 +478,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
       attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       int n = 0;
-      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN>, &cfg));
+      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP>, &cfg));
       MTN_REQUIRE(n > 0, MTN_E_CUDA, "gemm: no cluster of %d CTAs fits on this device", CL);
       max_clusters = n;
     }
@@ -507,7 +510,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   const int tiles_per_batch = tiles_mn * ksplit;
   const int num_super = tiles_per_batch * batch;
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
-  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN>, dim3(clusters * CL),
+  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP>, dim3(clusters * CL),
                                        dim3(GEMM_THREADS), L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K,
                                        tiles_n, tiles_per_batch, num_super, tiles_mn, kb_per_split));
   return MTN_OK;
@@ -538,11 +541,11 @@ static int validate_gemm(const MtnGemmArgs* a) {
                 MTN_E_ALIGN, "gemm: addend alignment / ld_add=%d", a->ld_add);
   if (a->bias) MTN_REQUIRE(aligned16(a->bias), MTN_E_ALIGN, "gemm: bias not 16-byte aligned");
   if (a->relu_mask)
-    MTN_REQUIRE(aligned16(a->relu_mask) && a->ld_mask % 8 == 0 && a->ld_mask >= a->N, MTN_E_ALIGN,
-                "gemm: relu_mask alignment / ld_mask=%d", a->ld_mask);
+    MTN_REQUIRE(aligned16(a->relu_mask) && a->ld_mask % 8 == 0 && a->ld_mask >= a->N && !a->a_mn && a->b_mn, MTN_E_ALIGN,
+                "gemm: relu_mask (data-gradient form only) alignment / ld_mask=%d", a->ld_mask);
   if (a->drop_seed != nullptr)
-    MTN_REQUIRE(a->drop_thresh < 65536u && a->batch <= 1 && !a->accumulate, MTN_E_ARG,
-                "gemm: dropout needs thresh < 65536, no batch, no accumulate");
+    MTN_REQUIRE(a->drop_thresh < 65536u && a->batch <= 1 && !a->accumulate && !a->a_mn && !a->b_mn, MTN_E_ARG,
+                "gemm: dropout needs thresh < 65536, the forward (K-major) form, no batch, no accumulate");
   if (a->accumulate)
     MTN_REQUIRE(a->out_f32 != nullptr && a->out_f16 == nullptr && a->bias == nullptr && a->addend == nullptr &&
                     a->act == MTN_ACT_NONE && a->relu_mask == nullptr,
@@ -585,6 +588,7 @@ static int run_gemm(const MtnGemmArgs* a, void* stream) {
   const int form = (a->a_mn ? 2 : 0) | (a->b_mn ? 1 : 0);
   switch (form) {
     case 0:
+      if (a->drop_seed != nullptr) return big ? launch_gemm<256, 4, 1, 0, 0, 1>(*a, st) : launch_gemm<128, 6, 1, 0, 0, 1>(*a, st);
       if (cl >= 2 && big && !a->accumulate && tiles256 >= 4L * g_num_sms) return launch_gemm<256, 4, 2, 0, 0>(*a, st);
       return big ? launch_gemm<256, 4, 1, 0, 0>(*a, st) : launch_gemm<128, 6, 1, 0, 0>(*a, st);
     case 1:
