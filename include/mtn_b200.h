@@ -315,6 +315,15 @@ int mtn_cast_colsum(const void *src, int src_is_f16, int ld_src, void *dst_f16, 
  * (S = 1 for an all-zero or non-finite gradient) and resets the slot.                                   */
 int mtn_grad_absmax(const float *x, size_t n, uint32_t *slot, void *stream);
 int mtn_grad_scale(uint32_t *slot, float *scale2, void *stream);
+/* ---- fused Adam (optimizer of train.py:190-191 = torch.optim.Adam wrapped by NoamOpt) ------
+ * state: 8 f32 in device memory {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, t, -}.
+ * mtn_adam_advance: t += 1, refresh the bias corrections and, if noam_factor > 0, the learning rate of
+ *   data_utils.py:112-117: lr = factor * model_size^-0.5 * min(t^-0.5, t * warmup^-1.5).
+ * mtn_adam_step over a flat arena of n f32 parameters: torch.optim.Adam's update (no weight decay / amsgrad),
+ *   optionally p_f16 = f16(p) (the tensor-core operand arena) and g = 0, in one pass.                        */
+int mtn_adam_advance(float *state, float noam_factor, float model_size, float warmup, void *stream);
+int mtn_adam_step(float *p, float *g, float *m, float *v, void *p_f16, size_t n, const float *state,
+                  int zero_grad, void *stream);
 /* *seed += 1 on the stream (the captured training step bumps the dropout seed once per replay). */
 int mtn_seed_bump(uint64_t *seed, void *stream);
 /* Stream-ordered zero fill (cudaMemsetAsync) of a gradient accumulation buffer. */

@@ -163,6 +163,9 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                         C.c_uint32, C.c_void_p]),
     "mtn_seed_bump": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mtn_adam_advance": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "mtn_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                C.c_void_p]),
     "mtn_grad_absmax": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mtn_grad_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -490,6 +493,27 @@ def drop_cfg(seed, site, p):
 def _set_drop(a, drop):
     if drop is not None:
         a.drop_seed, a.drop_site, a.drop_thresh = drop[0].data_ptr(), drop[1], drop[2]
+
+
+def adam_advance(state, noam=None):
+    """state: 8-element f32 device tensor {lr, b1, b2, eps, bc1, bc2, step, -}; noam = (factor, model_size, warmup)."""
+    _req(state, torch.float32, "state")
+    f, ms, wu = noam if noam is not None else (0.0, 1.0, 1.0)
+    _launch("adam_advance", 0, 32, lambda: lib().mtn_adam_advance(ptr(state), float(f), float(ms), float(wu), stream_ptr()),
+            keep=(state,))
+
+
+def adam_step(p, g, m, v, state, p_f16=None, zero_grad=True):
+    """Fused Adam over flat f32 buffers (n % 4 == 0); optionally refreshes the f16 copy and zeroes the gradient."""
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (state, "state")):
+        _req(t, torch.float32, n)
+        assert t.is_contiguous()
+    _req(p_f16, torch.float16, "p_f16")
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n and (p_f16 is None or p_f16.numel() == n)
+    _launch("adam_step", 0, n * (28 + (4 if zero_grad else 0) + (2 if p_f16 is not None else 0)),
+            lambda: lib().mtn_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_f16), n, ptr(state), 1 if zero_grad else 0,
+                                        stream_ptr()), keep=(p, g, m, v, state, p_f16))
 
 
 def seed_bump(seed):

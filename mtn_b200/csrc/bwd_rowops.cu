@@ -357,6 +357,50 @@ __global__ void grad_scale_kernel(unsigned* __restrict__ slot, float* __restrict
   out[1] = 1.f / S;
 }
 
+// ----------------------------------------------------------------------------
+// Fused Adam over a flat parameter arena (torch.optim.Adam semantics, train.py:190-191):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// one pass: also refreshes the f16 tensor-core copy of the parameters and zeroes the gradient.  Hyper-parameters
+// live in device memory (state[8] = lr, b1, b2, eps, bc1, bc2, step, -) so that a captured step can advance them:
+// adam_advance_kernel increments the step, updates the bias corrections and, for the reference's NoamOpt schedule
+// (data_utils.py:92-117), the learning rate.
+// ----------------------------------------------------------------------------
+__global__ void adam_advance_kernel(float* st, float noam_factor, float model_size, float warmup) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float step = st[6] + 1.f;
+  st[6] = step;
+  st[4] = 1.f - powf(st[1], step);
+  st[5] = 1.f - powf(st[2], step);
+  if (noam_factor > 0.f) st[0] = noam_factor * (rsqrtf(model_size) * fminf(rsqrtf(step), step * powf(warmup, -1.5f)));
+}
+
+__global__ void __launch_bounds__(256)
+    adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                     __half* __restrict__ p16, size_t n4, const float* __restrict__ st, int zero_grad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float lr = __ldg(st), b1 = __ldg(st + 1), b2 = __ldg(st + 2), eps = __ldg(st + 3);
+  const float step_size = lr / __ldg(st + 4), inv_sqrt_bc2 = rsqrtf(__ldg(st + 5));
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    const float4 Gv = reinterpret_cast<const float4*>(g)[i];
+    float4 Mv = reinterpret_cast<float4*>(m)[i], Vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = &P.x; const float* gg = &Gv.x; float* mm = &Mv.x; float* vv = &Vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mm[j] = b1 * mm[j] + (1.f - b1) * gg[j];
+      vv[j] = b2 * vv[j] + (1.f - b2) * gg[j] * gg[j];
+      pp[j] -= step_size * mm[j] / (sqrtf(vv[j]) * inv_sqrt_bc2 + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = Mv;
+    reinterpret_cast<float4*>(v)[i] = Vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p16 != nullptr) reinterpret_cast<uint2*>(p16)[i] = make_uint2(pack_f16x2_sat(P.x, P.y), pack_f16x2_sat(P.z, P.w));
+  }
+}
+
 __global__ void seed_bump_kernel(unsigned long long* seed) {
   pdl_launch_dependents();
   pdl_wait();
@@ -612,6 +656,29 @@ extern "C" int mtn_grad_absmax(const float* x, size_t n, uint32_t* slot, void* s
   if (blocks > 1184) blocks = 1184;
   MTN_CHECK_CUDA(launch_kernel(absmax_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), x, n4,
                                reinterpret_cast<unsigned*>(slot)));
+  return MTN_OK;
+}
+
+extern "C" int mtn_adam_advance(float* state, float noam_factor, float model_size, float warmup, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(state != nullptr, MTN_E_ARG, "adam_advance: NULL pointer");
+  MTN_CHECK_CUDA(launch_kernel(adam_advance_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), state, noam_factor,
+                               model_size, warmup));
+  return MTN_OK;
+}
+
+extern "C" int mtn_adam_step(float* p, float* g, float* m, float* v, void* p_f16, size_t n, const float* state, int zero_grad,
+                             void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(p && g && m && v && state, MTN_E_ARG, "adam_step: NULL pointer");
+  MTN_REQUIRE(n > 0 && n % 4 == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) &&
+                  (!p_f16 || (reinterpret_cast<uintptr_t>(p_f16) & 7) == 0),
+              MTN_E_ALIGN, "adam_step: n=%zu must be a multiple of 4 and the buffers 16-byte aligned", n);
+  const size_t n4 = n / 4;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > 4736) blocks = 4736;
+  MTN_CHECK_CUDA(launch_kernel(adam_step_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g, m,
+                               v, reinterpret_cast<__half*>(p_f16), n4, state, zero_grad));
   return MTN_OK;
 }
 

@@ -497,13 +497,15 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
               a.drop_after_add, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
   const int tiles_mn = tiles_n * ((tiles_m + CL - 1) / CL);
-  // split-K (accumulating outputs only): cut the contraction so that the launch fills the machine about twice
+  // split-K (accumulating outputs only): cut the contraction so that the launch is ONE wave of CTAs -- every slice
+  // pays a full-tile red.add epilogue, so fewer, longer slices beat many short ones
   const int nkb = (a.K + BK - 1) / BK;
   int kb_per_split = nkb;
   if (a.accumulate) {
-    const long want = (2L * max_clusters + (long)tiles_mn * batch - 1) / ((long)tiles_mn * batch);  // slices wanted
-    long per = (nkb + want - 1) / (want > 0 ? want : 1);
-    if (per < 4) per = nkb < 4 ? nkb : 4;  // at least 4 k-blocks (256 contraction rows) per slice
+    long want = (long)max_clusters / ((long)tiles_mn * batch);  // slices per output tile
+    if (want < 1) want = 1;
+    long per = (nkb + want - 1) / want;
+    if (per < 2) per = nkb < 2 ? nkb : 2;
     kb_per_split = (int)per;
   }
   const int ksplit = (nkb + kb_per_split - 1) / kb_per_split;
@@ -583,8 +585,9 @@ static int run_gemm(const MtnGemmArgs* a, void* stream) {
     const char* e = getenv("MTN_B200_BIG_PCT");
     big_pct = e ? atoi(e) : 40;
   }
-  // split-K launches fill the machine through their slices: always the wide tile when N allows
-  const bool big = a->N >= 256 && (a->accumulate || tiles256 * 100 >= (long)big_pct * g_num_sms);
+  // split-K launches fill the machine through their slices; small outputs take 128x128 tiles (half the red.add
+  // bytes per slice, twice the slices' length), large ones the wide tile
+  const bool big = a->N >= 256 && (a->accumulate ? tiles256 * 2 >= g_num_sms : tiles256 * 100 >= (long)big_pct * g_num_sms);
   const int form = (a->a_mn ? 2 : 0) | (a->b_mn ? 1 : 0);
   switch (form) {
     case 0:

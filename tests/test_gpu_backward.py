@@ -351,3 +351,27 @@ def test_training_step_d512_vs_oracle():
     assert abs(loss - oloss) <= 5e-3 * abs(oloss)
     assert max(errs.values()) < 3e-2 and float(np.median(list(errs.values()))) < 8e-3, worst
     _vs_f16_contract(grads, (sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"]), "d=512")
+
+
+# ------------------------------------------------------------------ optimizer
+def test_fused_adam_matches_torch_adam_and_noam_schedule(L):
+    from mtn_b200.data_utils import NoamOpt
+    g = torch.Generator().manual_seed(31)
+    n = 4096 + 8
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone().cuda())
+    topt = NoamOpt(512, 1, 40, torch.optim.Adam([ref], lr=0, betas=(0.9, 0.98), eps=1e-9))     # train.py:190-191
+    p, m, v = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    p16 = torch.empty(n, dtype=torch.float16, device="cuda")
+    state = torch.tensor([0.0, 0.9, 0.98, 1e-9, 1.0, 1.0, 0.0, 0.0], device="cuda")
+    for it in range(5):
+        grad = torch.randn(n, generator=g).cuda() * (10.0 ** (it - 2))
+        ref.grad = grad.clone()
+        topt.step()
+        gbuf = grad.clone()
+        L.adam_advance(state, (1.0, 512.0, 40.0))
+        L.adam_step(p, gbuf, m, v, state, p_f16=p16, zero_grad=True)
+        assert abs(float(state[0]) - topt.rate()) <= 1e-6 * topt.rate()
+        assert float(gbuf.abs().max()) == 0.0
+        assert G.rel_err(p.cpu(), ref.detach().cpu()) < 2e-6, it
+        assert torch.equal(p16, p.half())

@@ -10,6 +10,8 @@ import subprocess
 import sys
 
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAGS = sys.argv[2:] or ["gemm_big", "gemm_small", "attn", "ln"]
+TRAIN = "train" in R
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
@@ -32,13 +34,15 @@ for (_, name, grid), d in per.items():
     a = agg.setdefault(short, {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
     a["n"] += 1; a["us"] += d.get("us", 0); a["rd"] += d.get("dram__bytes_read.sum", 0); a["wr"] += d.get("dram__bytes_write.sum", 0)
 tot = sum(a["us"] for a in agg.values())
-out = ["# %s: ncu launch list of one bench step (tools/profile_step.py: B=32, T=256; cold cache, serialised)" % R, "",
+out = ["# %s: ncu launch list of one %s (tools/%s: B=32, T=256; cold cache, serialised)"
+       % (R, "eager TRAINING step (forward + loss + backward + Adam, dropout 0.1)" if TRAIN else "bench step",
+          "profile_train_step.py" if TRAIN else "profile_step.py"), "",
        "| kernel | launches | total us | share | avg us | DRAM read MB | DRAM write MB |", "|---|---:|---:|---:|---:|---:|---:|"]
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
     out.append("| `%s` | %d | %.1f | %.1f%% | %.2f | %.1f | %.1f |" % (k[:70], a["n"], a["us"], 100 * a["us"] / tot, a["us"] / a["n"],
                                                                        a["rd"] / 1e6, a["wr"] / 1e6))
 out.append("| **total** | %d | %.1f | | | | |" % (sum(a["n"] for a in agg.values()), tot))
-ours = {k: a for k, a in agg.items() if not k.startswith("at::")}
+ours = {k: a for k, a in agg.items() if not (k.startswith("at::") or "at::native" in k or k.startswith("nccl"))}
 out += ["", "Kernels of this repo: %d launches, %.1f us (%.1f%% of the step's kernel time); the rest are PyTorch glue "
         "(mask construction in Batch, clone of the residual stream)." % (sum(a["n"] for a in ours.values()),
                                                                          sum(a["us"] for a in ours.values()),
@@ -58,7 +62,7 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct"]
 out = ["# %s: ncu --set full captures (key metrics; .ncu-rep files are scratch under gpurun_out/)" % R, ""]
-for tag in ("gemm_big", "gemm_small", "attn", "ln"):
+for tag in TAGS:
     rep = os.path.join(GO, "%s_%s.ncu-rep" % (R, tag))
     if not os.path.isfile(rep):
         continue
