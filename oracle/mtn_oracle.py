@@ -239,7 +239,7 @@ def simple_loss(sd, cfg, out, trg_y, ae_out, ae_y, pad=1, smoothing=0.1, lam=1.0
     return float(loss) * float(norm)
 
 
-def loss_and_grads(sd, cfg, query, his, cap, trg, trg_y, fts, pad=1, smoothing=0.1, lam=1.0):
+def loss_and_grads(sd, cfg, query, his, cap, trg, trg_y, fts, pad=1, smoothing=0.1, lam=1.0, norm=None, ae_norm=None):
     """One training step's loss and parameter gradients with dropout disabled: train.py:33-39 (forward, loss on
     the decoder output AND on every auto-encoder stream against the un-shifted query ids, normalised by
     ntokens / ntokens_query) + data_utils.py:132-152 (loss.backward()).  Plain torch autograd through the
@@ -252,10 +252,12 @@ def loss_and_grads(sd, cfg, query, his, cap, trg, trg_y, fts, pad=1, smoothing=0
     out, ae_out = decoder(p, cfg, vid_mem, m["fts_mask"], x, his_mem, m["his_mask"], cap_mem, m["cap_mask"], q_mem,
                           m["query_mask"], m["trg_mask"], ae_mem)
     V = p["generator.proj.weight"].shape[0]
-    norm = (trg_y != pad).sum().float()
-    loss = label_smoothing_loss(generator(p, out).reshape(-1, V), trg_y.reshape(-1), V, pad, smoothing) / norm
     ae_y = query if cfg.get("auto_encoder_ft", "query") == "query" else cap          # train.py:34-39
-    ae_norm = (ae_y != pad).sum().float()
+    # norm / ae_norm: token counts of THIS batch (the reference) unless the caller passes the global counts of a
+    # sharded batch (data parallelism)
+    norm = (trg_y != pad).sum().float() if norm is None else torch.tensor(float(norm))
+    ae_norm = (ae_y != pad).sum().float() if ae_norm is None else torch.tensor(float(ae_norm))
+    loss = label_smoothing_loss(generator(p, out).reshape(-1, V), trg_y.reshape(-1), V, pad, smoothing) / norm
     for a in ae_out:
         loss = loss + lam * label_smoothing_loss(generator(p, a).reshape(-1, V), ae_y.reshape(-1), V, pad,
                                                  smoothing) / ae_norm

@@ -40,3 +40,112 @@ def test_two_rank_sharding_and_reductions():
         assert tok == total                 # shards sum to the global token count on every rank
         assert tmax == 11.0                 # max over ranks
         assert n == 3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Data-parallel TRAINING recipe: shards + GLOBAL normalisers + ONE all-reduce(SUM) of the flat gradient
+# must equal the single-process gradient of the whole batch.  CPU tier: the recipe itself with the oracle's autograd
+# (world_size 2, gloo).  GPU tier (below): the same through TrainStep's kernels, two processes sharing one GPU (gloo
+# moves the CUDA gradient buffer through the host -- NCCL cannot put two ranks on one device).
+# ---------------------------------------------------------------------------------------------------------------
+CFG_DP = {"N": 1, "d_model": 128, "d_ff": 512, "h": 4, "vocab": 100, "ft_sizes": [2048, 128], "auto_encoder_ft": "query",
+          "diff_encoder": True}
+
+
+def _dp_oracle_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import mtn_oracle as O
+    from mtn_b200 import parallel
+    sd = O.init_state_dict(CFG_DP, 11)
+    full = O.synth_inputs(CFG_DP, B=4, Q=8, C=8, H=16, T=8, Lv=[16, 8], seed=5)
+    mine = parallel.shard_batch(full, rank, world)
+    ntok = parallel.global_tokens(mine["trg_y"], 1)
+    nq = parallel.all_sum(int((mine["query"] != 1).sum()))
+    _, g = O.loss_and_grads(sd, CFG_DP, mine["query"], mine["his"], mine["cap"], mine["trg"], mine["trg_y"], mine["fts"],
+                            norm=ntok, ae_norm=nq)
+    names = sorted(g)
+    flat = torch.cat([g[k].reshape(-1) for k in names])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)                      # the one gradient collective
+    if rank == 0:
+        _, gf = O.loss_and_grads(sd, CFG_DP, full["query"], full["his"], full["cap"], full["trg"], full["trg_y"], full["fts"])
+        ref = torch.cat([gf[k].reshape(-1) for k in names])
+        q.put(float((flat - ref).norm() / ref.norm()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_single_process_oracle():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 500
+    ps = [ctx.Process(target=_dp_oracle_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    err = q.get(timeout=300)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    assert err <= 1e-5, err                                          # SURVEY 8e equivalence bar
+
+
+def _dp_gpu_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mtn_oracle as O
+    from mtn_b200 import mtn, parallel
+    from mtn_b200.trainer import TrainStep
+    torch.cuda.set_device(0)
+    sd = O.init_state_dict(CFG_DP, 11)
+    full = O.synth_inputs(CFG_DP, B=4, Q=8, C=8, H=16, T=8, Lv=[16, 8], seed=5)
+
+    def grads_of(batch, ntok, nq, use_dist):
+        model = mtn.make_model(100, 100, N=1, d_model=128, d_ff=512, h=4, dropout=0.0, ft_sizes=[2048, 128],
+                               diff_encoder=True, auto_encoder_ft="query")
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        ts = TrainStep(model, 100, graph=False, optimizer=_NoOpt())
+        if not use_dist:
+            ts.world = 1
+        snap = {}
+        ts.opt.hook = lambda: snap.update(flat=ts.flat.clone())      # the gradient the optimizer would consume
+        ts.eager({k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in batch.items()}, ntok, nq)
+        return snap["flat"].cpu()
+
+    mine = parallel.shard_batch(full, rank, world)
+    ntok = parallel.global_tokens(mine["trg_y"], 1)
+    nq = parallel.all_sum(int((mine["query"] != 1).sum()))
+    g_dp = grads_of(mine, ntok, nq, True)
+    if rank == 0:
+        g_one = grads_of(full, int((full["trg_y"] != 1).sum()), int((full["query"] != 1).sum()), False)
+        q.put(float((g_dp - g_one).norm() / g_one.norm()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+class _NoOpt(object):
+    """Stand-in optimizer: records instead of updating (so both runs start from the same weights)."""
+    hook = None
+
+    def step(self):
+        if self.hook:
+            self.hook()
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_two_process_trainstep_allreduce_equals_single_process_gpu():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 13) % 500
+    ps = [ctx.Process(target=_dp_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    err = q.get(timeout=300)
+    [p.join(120) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    assert err <= 2e-3, err          # two f16-operand passes over different batch splits: rounding noise only
