@@ -375,3 +375,48 @@ def test_fused_adam_matches_torch_adam_and_noam_schedule(L):
         assert float(gbuf.abs().max()) == 0.0
         assert G.rel_err(p.cpu(), ref.detach().cpu()) < 2e-6, it
         assert torch.equal(p16, p.half())
+
+
+def test_reference_training_loop_three_steps_vs_oracle():
+    """The reference's own loop (train.py:28-39, 190-209): make_model, LabelSmoothing, NoamOpt(Adam), SimpleLossCompute
+    with opt -- driven exactly like train.py drives it, dropout 0 -- against the same three Adam steps taken with the
+    CPU oracle's gradients.  Checks the loss trajectory (so the parameters after each update) end to end."""
+    from mtn_b200 import mtn, data_utils, label_smoothing
+    z, cfg, sd, inp = golden_grad_case()
+    model = mtn.make_model(100, 100, N=1, d_model=128, d_ff=512, h=4, dropout=0.0, ft_sizes=[2048, 128], diff_encoder=True,
+                           auto_encoder_ft="query")
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    criterion = label_smoothing.LabelSmoothing(size=100, padding_idx=1, smoothing=0.1)
+    opt = data_utils.NoamOpt(128, 1, 4, torch.optim.Adam(model.parameters(), lr=0, betas=(0.9, 0.98), eps=1e-9))
+    lc = data_utils.SimpleLossCompute(model.generator, model.auto_encoder_generator, criterion, opt=opt, l=1.0)
+    g = lambda t: t.cuda()
+    b = data_utils.Batch(g(inp["query"]), g(inp["his"]), None, [g(f).permute(1, 0, 2).contiguous() for f in inp["fts"]],
+                         g(inp["cap"]), g(inp["trg"]), g(inp["trg_y"]), 1)
+    got = []
+    for _ in range(3):
+        out, ae_out = model.forward(b)                                              # train.py:33
+        ntokens_query = (b.query != 1).data.sum()                                   # train.py:38
+        got.append(float(lc(out, b.trg_y, b.ntokens, ae_out, b.query, ntokens_query)))    # train.py:39 (loss * norm)
+    # oracle: same optimizer on the state_dict tensors
+    psd = {k: v.clone() for k, v in sd.items()}
+    names = [k for k in psd if not k.endswith(".pe")]
+    params = [torch.nn.Parameter(psd[k]) for k in names]
+    oopt = data_utils.NoamOpt(128, 1, 4, torch.optim.Adam(params, lr=0, betas=(0.9, 0.98), eps=1e-9))
+    norm = float((inp["trg_y"] != 1).sum())
+    ref = []
+    for _ in range(3):
+        cur = dict(psd)
+        cur.update({k: p.data for k, p in zip(names, params)})
+        loss, grads = O.loss_and_grads(cur, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"])
+        for k, p in zip(names, params):
+            p.grad = grads[k]
+        oopt.step()
+        ref.append(loss * norm)
+    print("reference loop losses", got, "oracle", ref)
+    assert ref[2] < ref[0] and got[2] < got[0]
+    for a, r in zip(got, ref):
+        assert abs(a - r) <= 2e-3 * abs(r), (got, ref)
