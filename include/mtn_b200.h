@@ -364,7 +364,7 @@ int mtn_embed_bwd(const MtnEmbedBwdArgs *args, void *stream);
  * delta[b, h, q] = sum_c dO[row, h*d_k + c] * O[row, h*d_k + c]  (mtn_attn_delta), then
  *   dV = P^T dO,  dS = P (dO V^T - delta) / sqrt(d_k) [0 where masked],  dQ = dS K,  dK = dS^T Q
  * with P recomputed from q, k, mask and the forward's `stats`.  dq is f32 and ACCUMULATED atomically over the
- * key tiles (zero it first); dk / dv are f16, head h in columns [h*d_k, (h+1)*d_k).                      */
+ * key tiles (zero it first) -- or dq_f16 for Lk <= 128; dk / dv are f16, head h in columns [h*d_k, (h+1)*d_k). */
 int mtn_attn_delta(const void *dO, int lddo, const void *O, int ldo, int B, int Lq, int h, int d_k,
                    float *delta, void *stream);
 typedef struct MtnAttnCoreBwdArgs {
@@ -379,6 +379,9 @@ typedef struct MtnAttnCoreBwdArgs {
   void *dk; int lddk;
   void *dv; int lddv;
   const void *drop_seed; uint32_t drop_site, drop_thresh;   /* the forward's probability dropout (regenerated) */
+  /* Lk <= 128 (one key tile): dQ is complete inside one CTA -- pass dq = NULL and dq_f16 (f16 [B*Lq, lddq16]) to
+   * get it stored directly, without the f32 accumulation buffer.                                             */
+  void *dq_f16; int lddq16;
 } MtnAttnCoreBwdArgs;
 int mtn_attn_core_bwd(const MtnAttnCoreBwdArgs *args, void *stream);
 

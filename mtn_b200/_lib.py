@@ -91,7 +91,8 @@ class AttnCoreBwdArgs(C.Structure):
                 ("B", C.c_int), ("h", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("d_k", C.c_int),
                 ("dq", C.c_void_p), ("lddq", C.c_int), ("dk", C.c_void_p), ("lddk", C.c_int),
                 ("dv", C.c_void_p), ("lddv", C.c_int),
-                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32)]
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32),
+                ("dq_f16", C.c_void_p), ("lddq16", C.c_int)]
 
 
 class AttnCoreArgs(C.Structure):
@@ -719,11 +720,13 @@ def attn_delta(dO, O, B, Lq, h, d_k, delta):
 
 def attn_core_bwd(q, k, v, dO, stats, delta, B, h, Lq, Lk, d_k, dq, dk, dv, mask_bits=None, drop=None):
     """q/k/v/dO: f16 2-D views (row stride = leading dimension); stats [B,h,Lq,2], delta [B,h,Lq] f32;
-    dq: f32 [B*Lq, >= h*d_k] ACCUMULATED (zero it first); dk/dv: f16 [B*Lk, >= h*d_k] written."""
+    dq: f32 [B*Lq, >= h*d_k] ACCUMULATED (zero it first) -- or, for Lk <= 128, an f16 tensor written directly;
+    dk/dv: f16 [B*Lk, >= h*d_k] written."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (dO, "dO"), (dk, "dk"), (dv, "dv")):
         _req(t, torch.float16, n)
         assert t.dim() == 2
-    _req(stats, torch.float32, "stats"); _req(delta, torch.float32, "delta"); _req(dq, torch.float32, "dq")
+    _req(stats, torch.float32, "stats"); _req(delta, torch.float32, "delta")
+    assert dq.is_cuda and dq.dim() == 2 and dq.stride(1) == 1 and dq.dtype in (torch.float32, torch.float16)
     a = AttnCoreBwdArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0)
     a.dO, a.lddo = dO.data_ptr(), dO.stride(0)
@@ -732,7 +735,11 @@ def attn_core_bwd(q, k, v, dO, stats, delta, B, h, Lq, Lk, d_k, dq, dk, dv, mask
         assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == B
         a.mask_bits, a.mask_rows_q = mask_bits.data_ptr(), mask_bits.shape[1]
     a.B, a.h, a.Lq, a.Lk, a.d_k = B, h, Lq, Lk, d_k
-    a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0)
+    a.dk, a.lddk, a.dv, a.lddv = dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0)
+    if dq.dtype == torch.float16:
+        a.dq_f16, a.lddq16 = dq.data_ptr(), dq.stride(0)
+    else:
+        a.dq, a.lddq = dq.data_ptr(), dq.stride(0)
     _set_drop(a, drop)
     _launch("attn_core_bwd", 10 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (4 * Lq + 4 * Lk),
             lambda: lib().mtn_attn_core_bwd(C.byref(a), stream_ptr()),

@@ -59,6 +59,7 @@ struct AttnBwdParams {
   const float2* stats;
   const float* delta;
   float* dq; int lddq;
+  __half* dq16; int lddq16;  // single key tile (Lk <= 128): dQ is complete inside the CTA and stored as f16 directly
   __half* dk; int lddk;
   __half* dv; int lddv;
   DropCfg drop;  // the forward's dropout of the probabilities, regenerated
@@ -199,7 +200,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         uint32_t r[32];
         tc_ld32(tmem_base + C::COL_DQ + (i & 1) * DK + half * 32 + lane_off, r);
         tc_wait_ld();
-        if (qi < p.Lq) {
+        if (qi < p.Lq && p.dq16 != nullptr) {
+          uint4* o = reinterpret_cast<uint4*>(p.dq16 + ((size_t)b * p.Lq + qi) * p.lddq16 + hd * DK + half * 32);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            o[t] = make_uint4(pack_f16x2_sat(__uint_as_float(r[8 * t]), __uint_as_float(r[8 * t + 1])),
+                              pack_f16x2_sat(__uint_as_float(r[8 * t + 2]), __uint_as_float(r[8 * t + 3])),
+                              pack_f16x2_sat(__uint_as_float(r[8 * t + 4]), __uint_as_float(r[8 * t + 5])),
+                              pack_f16x2_sat(__uint_as_float(r[8 * t + 6]), __uint_as_float(r[8 * t + 7])));
+        } else if (qi < p.Lq) {
           float* o = p.dq + ((size_t)b * p.Lq + qi) * p.lddq + hd * DK + half * 32;
 #pragma unroll
           for (int t = 0; t < 8; ++t)
@@ -340,7 +349,7 @@ static int launch_attn_bwd(const MtnAttnCoreBwdArgs& a, cudaStream_t st) {
   if (rc) return rc;
   AttnBwdParams p{a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk, 1.0f / sqrtf((float)DK),
                   reinterpret_cast<const float2*>(a.stats), a.delta, a.dq, a.lddq,
-                  reinterpret_cast<__half*>(a.dk), a.lddk, reinterpret_cast<__half*>(a.dv), a.lddv,
+                  reinterpret_cast<__half*>(a.dq_f16), a.lddq16, reinterpret_cast<__half*>(a.dk), a.lddk, reinterpret_cast<__half*>(a.dv), a.lddv,
                   DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
                           a.drop_seed ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
                   (a.Lk + 31) / 32 * 32};
@@ -353,18 +362,21 @@ static int launch_attn_bwd(const MtnAttnCoreBwdArgs& a, cudaStream_t st) {
 
 extern "C" int mtn_attn_core_bwd(const MtnAttnCoreBwdArgs* a, void* stream) {
   using namespace mtn;
-  MTN_REQUIRE(a && a->q && a->k && a->v && a->dO && a->stats && a->delta && a->dq && a->dk && a->dv, MTN_E_ARG,
+  MTN_REQUIRE(a && a->q && a->k && a->v && a->dO && a->stats && a->delta && (a->dq || a->dq_f16) && a->dk && a->dv, MTN_E_ARG,
               "attn_core_bwd: NULL pointer");
+  MTN_REQUIRE((a->dq != nullptr) != (a->dq_f16 != nullptr), MTN_E_ARG, "attn_core_bwd: give exactly one of dq (f32, accumulated) and dq_f16");
+  MTN_REQUIRE(a->dq_f16 == nullptr || (a->Lk <= 128 && aligned16(a->dq_f16) && a->lddq16 % 8 == 0 && a->lddq16 >= a->h * a->d_k),
+              MTN_E_SHAPE, "attn_core_bwd: dq_f16 needs Lk <= 128 (one key tile), 16-byte alignment, lddq16 >= h*d_k");
   MTN_REQUIRE(a->B > 0 && a->B <= 65535 && a->h > 0 && a->h <= 65535 && a->Lq > 0 && a->Lk > 0, MTN_E_SHAPE,
               "attn_core_bwd: B=%d h=%d Lq=%d Lk=%d", a->B, a->h, a->Lq, a->Lk);
   MTN_REQUIRE(a->d_k == 32 || a->d_k == 64, MTN_E_SHAPE, "attn_core_bwd: d_k=%d (supported: 32, 64)", a->d_k);
   const int w = a->h * a->d_k;
-  MTN_REQUIRE(a->ldq >= w && a->ldk >= w && a->ldv >= w && a->lddo >= w && a->lddq >= w && a->lddk >= w && a->lddv >= w,
+  MTN_REQUIRE(a->ldq >= w && a->ldk >= w && a->ldv >= w && a->lddo >= w && (!a->dq || a->lddq >= w) && a->lddk >= w && a->lddv >= w,
               MTN_E_SHAPE, "attn_core_bwd: leading dimension smaller than h*d_k=%d", w);
   MTN_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->lddo % 8 == 0 && a->lddk % 8 == 0 &&
-                  a->lddv % 8 == 0 && a->lddq % 4 == 0,
+                  a->lddv % 8 == 0 && (!a->dq || a->lddq % 4 == 0),
               MTN_E_ALIGN, "attn_core_bwd: leading dimensions must keep rows 16-byte aligned");
-  MTN_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->dO) && aligned16(a->dq) &&
+  MTN_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->dO) && (!a->dq || aligned16(a->dq)) &&
                   aligned16(a->dk) && aligned16(a->dv) && (reinterpret_cast<uintptr_t>(a->stats) & 7) == 0,
               MTN_E_ALIGN, "attn_core_bwd: pointers must be 16-byte aligned");
   MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,

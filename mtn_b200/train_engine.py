@@ -473,27 +473,34 @@ class DecoderTrainer(object):
         # ---- attention core
         delta = torch.empty(B, h, Lq, dtype=torch.float32, device=dev)
         _lib.attn_delta(do16, t["o16"], B, Lq, h, dk_, delta)
-        dq32 = _lib.zero(torch.empty(rows, d, dtype=torch.float32, device=dev))
+        one_tile = Lk <= 128             # dQ complete inside one CTA: stored as f16 directly, no f32 accumulation buffer
         if t["self_attn"]:
             dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
-            dkd, dvd = dqkv[:, d:2 * d], dqkv[:, 2 * d:]
+            dq16, dkd, dvd = dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]
         else:
+            dq16 = torch.empty(rows, d, dtype=f16, device=dev)
             dkd, dvd = dkv
-        _lib.attn_core_bwd(t["q"], t["k"], t["v"], do16, t["stats"], delta, B, h, Lq, Lk, dk_, dq32, dkd, dvd,
-                           mask_bits=t["bits"], drop=t["drop_p"])
+        dq32 = None if one_tile else _lib.zero(torch.empty(rows, d, dtype=torch.float32, device=dev))
+        _lib.attn_core_bwd(t["q"], t["k"], t["v"], do16, t["stats"], delta, B, h, Lq, Lk, dk_, dq16 if one_tile else dq32,
+                           dkd, dvd, mask_bits=t["bits"], drop=t["drop_p"])
         # ---- Q (or QKV) projection
         dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
         if t["self_attn"]:
             gb = G[(gk, l, "bqkv")]
-            _lib.cast_colsum(dq32, dst_f16=dqkv[:, :d], colsum=gb[:d], alpha=invS)
-            _lib.cast_colsum(dqkv[:, d:], colsum=gb[d:], alpha=invS)
+            if one_tile:
+                _lib.cast_colsum(dqkv, colsum=gb, alpha=invS)
+            else:
+                _lib.cast_colsum(dq32, dst_f16=dq16, colsum=gb[:d], alpha=invS)
+                wq.append(lambda: _lib.cast_colsum(dqkv[:, d:], colsum=gb[d:], alpha=invS))   # off the critical path
             _lib.linear_dgrad(dqkv, A["w_qkv"], out_f32=dxn)
             wq.append(lambda: _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS))
         else:
-            dq16 = torch.empty(rows, d, dtype=f16, device=dev)
             wq_key, bq_key = ("wq", "bq") if (gk, l, "wq") in G else ("wqkv", "bqkv")
             gw, gb = G[(gk, l, wq_key)], G[(gk, l, bq_key)]
-            _lib.cast_colsum(dq32, dst_f16=dq16, colsum=gb[:d], alpha=invS)
+            if one_tile:
+                wq.append(lambda: _lib.cast_colsum(dq16, colsum=gb[:d], alpha=invS))      # bias gradient off the critical path
+            else:
+                _lib.cast_colsum(dq32, dst_f16=dq16, colsum=gb[:d], alpha=invS)
             _lib.linear_dgrad(dq16, A["w_qkv"][:d], out_f32=dxn)
             wq.append(lambda: _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS))
         self._flush(bk, wq)

@@ -282,6 +282,10 @@ def test_attn_core_bwd_vs_autograd(L, B, h, Lq, Lk, dk, kind):
     if kind == "allmasked_row":
         assert float(dq[Lq:2 * Lq].abs().max()) == 0 and float(dk_[Lk:2 * Lk].abs().max()) == 0
         assert float(dv_[Lk:2 * Lk].abs().max()) > 0
+    if Lk <= 128:          # one key tile: dQ can be stored as f16 directly (no f32 accumulation buffer)
+        dq16 = torch.full((B * Lq, d), 9.0, dtype=torch.float16, device="cuda")
+        L.attn_core_bwd(q16, k16, v16, dO16, stats, delta, B, h, Lq, Lk, dk, dq16, dk_, dv_, mask_bits=bits)
+        assert torch.equal(dq16, dq.half())
 
 
 # ------------------------------------------------------------------ model level
