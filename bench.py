@@ -176,6 +176,63 @@ def workload_config(args, B):
                   "per batch)" % args.rot}
 
 
+def site_roofline(dev, peak_tf):
+    """BASELINE metric, second half: the fused decoder cross-attention SITE at d_model=512, h=8, seq=256, video_len=512
+    (north_star; SURVEY 8d: projections 25.77 GF + core 8.59 GF = 34.36 GF at B=32) through the C-ABI site entry point
+    mtn_attn_site_fwd (LayerNorm + Q projection + K/V projection of the memory + attention core + output projection +
+    residual), replayed back to back in a CUDA graph; algorithmic FLOPs / CUDA-event time / measured tensor peak."""
+    import ctypes as C
+    from mtn_b200 import _lib
+    B, Lq, Lk, d, h = 32, 256, 512, 512, 8
+    g = torch.Generator(device="cpu").manual_seed(3)
+    r = lambda *shape: torch.randn(*shape, generator=g).to(dev)
+    x, out = r(B * Lq, d), torch.empty(B * Lq, d, device=dev)
+    mem16 = r(B * Lk, d).half()
+    w_q, w_kv, w_o = (r(d, d) * 0.04).half(), (r(2 * d, d) * 0.04).half(), (r(d, d) * 0.04).half()
+    b_q, b_kv, b_o, ln_a, ln_b = r(d) * 0.1, r(2 * d) * 0.1, r(d) * 0.1, 1 + 0.1 * r(d), 0.1 * r(d)
+    lens = torch.randint(Lk // 2, Lk + 1, (B,), generator=g)
+    mask = (torch.arange(Lk)[None, :] < lens[:, None]).view(B, 1, Lk).to(dev)
+    bits = _lib.mask_pack(mask)
+    a = _lib.AttnSiteArgs()
+    a.B, a.Lq, a.Lk, a.d, a.h = B, Lq, Lk, d, h
+    a.x, a.x_out = x.data_ptr(), out.data_ptr()
+    a.ln_a, a.ln_b, a.ln_eps = ln_a.data_ptr(), ln_b.data_ptr(), 1e-6
+    a.w_q, a.b_q, a.w_kv, a.b_kv, a.w_o, a.b_o = (w_q.data_ptr(), b_q.data_ptr(), w_kv.data_ptr(), b_kv.data_ptr(),
+                                                  w_o.data_ptr(), b_o.data_ptr())
+    a.mem_f16 = mem16.data_ptr()
+    a.mask_bits, a.mask_rows_q = bits.data_ptr(), 1
+    n = _lib.lib().mtn_attn_site_workspace_bytes(B, Lq, Lk, d)
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), n
+    call = lambda: _lib.check(_lib.lib().mtn_attn_site_fwd(C.byref(a), _lib.stream_ptr()))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        call(); call()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    reps = 20
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for _ in range(reps):
+            call()
+    gr.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        gr.replay()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (5 * reps)
+    proj, core = 4 * B * d * d * (Lq + Lk), 4 * B * Lq * Lk * d
+    tf = (proj + core) / (us * 1e-6) / 1e12
+    return {"workload": "mtn_attn_site_fwd: B=32 Lq=256 Lk=512 d=512 h=8, key-padding mask, memory K/V projected in the call "
+                        "(5 kernels: LayerNorm, Q GEMM, K/V GEMM, attention core, out-proj GEMM + residual)",
+            "gflop": (proj + core) / 1e9, "us_per_site": us, "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": tf / peak_tf, "bound": "tensor",
+            "note": "north_star target 0.70; the attention core itself is MUFU(exp)-bound at d_k = 64 (256 FLOP per "
+                    "exponential), see DESIGN.md section 4"}
+
+
 def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over_ranks, sum_over_ranks):
     """Tokens/s of one TRAINING step on the same workload: forward (train.py:33), label-smoothed loss on the decoder
     and both auto-encoder streams normalised by the global token counts (train.py:37-39), backward through the
@@ -227,6 +284,17 @@ def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over
                         "gbs": round(sum(r[2] for r in mine) / (msk * 1e-3) / 1e9, 1)}
             del g
         res["kernel_breakdown_one_step"] = kt
+        gemm_ms = sum(kt[k]["ms"] for k in ("linear", "linear_dgrad", "linear_wgrad") if k in kt)
+        gemm_fl = sum(r[1] for r in rec if r[0] in ("linear", "linear_dgrad", "linear_wgrad"))
+        pk = 1400.0
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", pk)
+        except Exception:
+            pass
+        res["roofline"] = {"bound": "tensor", "kernel": "gemm_f16_tc_kernel, all forward / dgrad / wgrad launches of one training step",
+                           "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
+                           "frac": gemm_fl / (gemm_ms * 1e-3) / 1e12 / pk, "launches": sum(kt[k]["launches"] for k in
+                                                                                          ("linear", "linear_dgrad", "linear_wgrad") if k in kt)}
         n_launches = len(rec)
         del rec
         for i in range(3):
@@ -451,6 +519,12 @@ def main():
                 "flops_per_launch_avg": lin["flops"] / lin["n"], "us_per_launch_avg": lin["ms"] * 1e3 / lin["n"],
                 "note": "algorithmic 2MNK of the step's linear launches / CUDA-event time of those launches "
                         "replayed back to back in one CUDA graph"}
+    site = None
+    if rank == 0:
+        try:
+            site = site_roofline(dev, peak_tf)
+        except Exception as e:
+            site = {"error": repr(e)[:300]}
     hbm = peaks.get("hbm_gbs", 6650.0)
     breakdown = {k: {"launches": v["n"], "ms": round(v["ms"], 4), "gflop": round(v["flops"] / 1e9, 2),
                      "mb": round(v["bytes"] / 1e6, 1),
@@ -539,7 +613,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches * args.steps, "launches_per_step": launches,
-                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "roofline": roofline, "attn_site_roofline": site, "cpu_baseline": cpu, "clocks": clocks,
                 "tokens_per_step_per_gpu": sum(ntok) / len(ntok),
                 "model_tflops": fl * world / (ms / args.steps * 1e-3) / 1e12, "gflop_per_step_per_gpu": fl / 1e9,
                 "kernel_breakdown_one_step": breakdown, "decode": decode, "train": train}
