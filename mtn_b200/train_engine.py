@@ -587,8 +587,8 @@ class DecoderTrainer(object):
 
         def handoff(seq, k, rows, fused=lambda entry: True):
             """(dx16, bias gradient) the LayerNorm backward of seq[k] should produce for seq[k+1], or None."""
-            if k + 1 >= len(seq) or not fused(seq[k + 1]):
-                return None
+            if k + 1 >= len(seq) or not fused(seq[k + 1]) or d not in (128, 256, 512, 1024):
+                return None        # (the vectorised LayerNorm backward that can emit the hand-off exists for these d)
             return (torch.empty(rows, d, dtype=f16, device=dev), bias_of(seq[k + 1]), seq[k + 1][1]["drop_o"])
 
         kind, t = tape[-1]
