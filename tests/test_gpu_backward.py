@@ -424,3 +424,49 @@ def test_reference_training_loop_three_steps_vs_oracle():
     assert ref[2] < ref[0] and got[2] < got[0]
     for a, r in zip(got, ref):
         assert abs(a - r) <= 2e-3 * abs(r), (got, ref)
+
+
+# ------------------------------------------------------------------ configuration variants of the training path
+VARIANTS = [
+    # auto_encoder_ft='caption': sublayers 2/3 swap, the QAE branch reads the caption (mtn.py:187-194), AE loss vs b.cap
+    ({"N": 1, "d_model": 128, "d_ff": 256, "h": 4, "vocab": 50, "ft_sizes": [64], "auto_encoder_ft": "caption",
+      "diff_encoder": True}, dict(B=3, Q=6, C=10, H=12, T=5, Lv=[17])),
+    # diff_encoder=False: the auto-encoder streams start from the query memory itself (mtn.py:200-201, 205-208): its
+    # gradient collects the K/V terms AND both streams' input gradients
+    ({"N": 2, "d_model": 128, "d_ff": 256, "h": 4, "vocab": 50, "ft_sizes": [64, 32], "auto_encoder_ft": "query",
+      "diff_encoder": False}, dict(B=3, Q=6, C=10, H=12, T=5, Lv=[17, 9])),
+    # the stress configuration's family: d_model=1024, h=16 (d_k = 64), multi-tile sequences
+    ({"N": 1, "d_model": 1024, "d_ff": 4096, "h": 16, "vocab": 120, "ft_sizes": [2048, 128], "auto_encoder_ft": "query",
+      "diff_encoder": True}, dict(B=2, Q=20, C=30, H=150, T=140, Lv=[300, 70])),
+]
+
+
+@pytest.mark.parametrize("cfg,shape", VARIANTS, ids=["caption", "shared_ae", "d1024"])
+def test_training_step_variants_vs_oracle(cfg, shape):
+    from mtn_b200 import mtn, data_utils, label_smoothing
+    sd = O.init_state_dict(cfg, 8)
+    inp = O.synth_inputs(cfg, seed=9, **shape)
+    model = mtn.make_model(cfg["vocab"], cfg["vocab"], N=cfg["N"], d_model=cfg["d_model"], d_ff=cfg["d_ff"], h=cfg["h"],
+                           dropout=0.0, ft_sizes=cfg["ft_sizes"], diff_encoder=cfg["diff_encoder"],
+                           auto_encoder_ft=cfg["auto_encoder_ft"])
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g = lambda t: t.cuda()
+    b = data_utils.Batch(g(inp["query"]), g(inp["his"]), None, [g(f).permute(1, 0, 2).contiguous() for f in inp["fts"]],
+                         g(inp["cap"]), g(inp["trg"]), g(inp["trg_y"]), 1)
+    out, ae = model.forward(b)
+    ae_y = b.cap if cfg["auto_encoder_ft"] == "caption" else b.query                 # train.py:34-39
+    lc = data_utils.SimpleLossCompute(model.generator, None, label_smoothing.LabelSmoothing(cfg["vocab"], 1, 0.1), opt=None)
+    loss = lc.loss(out, b.trg_y, int(b.ntokens), ae, ae_y, int((ae_y != 1).sum()))
+    loss.backward()
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+    oloss, og = O.loss_and_grads(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"])
+    errs = grad_errors(grads, og)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print("variant %s: loss %.5f vs %.5f; median %.2e worst %s" % (cfg["auto_encoder_ft"], float(loss.detach()), oloss,
+                                                                  float(np.median(list(errs.values()))), worst))
+    assert abs(float(loss.detach()) - oloss) <= 5e-3 * abs(oloss)
+    assert max(errs.values()) < 4e-2 and float(np.median(list(errs.values()))) < 1e-2, worst
