@@ -8,7 +8,10 @@
 // Masked scores are the constant -1e9 (mtn.py:227), so no gradient flows through them into Q / K, but their
 // probabilities (non-zero only in fully masked rows) still weight dV exactly as autograd does.
 //
-// One CTA per (128-key tile, head, batch element); it loops over 128-query tiles.  Per query tile the
+// Work item = (128-key tile, head, batch element); persistent CTAs (one per SM) walk the items and, per item, loop
+// over 128-query tiles.  All barrier phases run on per-CTA global counters (item counter for the double-buffered K/V
+// tiles, tile counter for everything else), so the producer streams the next item's K / V / Q / dO and the tensor
+// core computes its first scores while the current item is still in its gradient MMAs and drains.  Per query tile the
 // tensor core computes S and dP (both K-major operands, like the forward), 256 threads (one TMEM lane = one
 // query row, two warps per lane quarter splitting the key columns) turn them into P and dS, written as f16
 // to shared memory in the 128-byte-swizzled panel layout, and three more MMAs consume those panels:
@@ -35,9 +38,10 @@ struct AttnBwdCfg {
   static constexpr int ROWB = DK * 2;
   static constexpr int TILE = AB_T * ROWB;             // one 128-row operand tile
   static constexpr int PANEL = AB_T * 128;             // [128 rows x 64 f16] swizzled panel
-  static constexpr int OFF_K = 0;
+  static constexpr int OFF_K = 0;                      // two buffers of [K | V] (next item's keys / values)
   static constexpr int OFF_V = OFF_K + TILE;
-  static constexpr int OFF_Q = OFF_V + TILE;           // two buffers
+  static constexpr int KV_STRIDE = 2 * TILE;
+  static constexpr int OFF_Q = OFF_K + 2 * KV_STRIDE;  // two buffers
   static constexpr int OFF_DO = OFF_Q + 2 * TILE;      // two buffers
   static constexpr int OFF_P = OFF_DO + 2 * TILE;      // two panels (keys 0-63, 64-127)
   static constexpr int OFF_DS = OFF_P + 2 * PANEL;
@@ -52,6 +56,7 @@ struct AttnBwdCfg {
 };
 
 struct AttnBwdParams {
+  int n_items, nkt;  // work items = B * h * nkt, ordered (b, head, key tile) with the key tile fastest
   const uint32_t* mask_bits;
   int mask_rows_q, mask_words;
   int B, h, Lq, Lk;
@@ -66,8 +71,8 @@ struct AttnBwdParams {
   int Lk32;
 };
 
-enum { ABAR_KV_FULL = 0, ABAR_QDO_FULL = 1 /* +1 */, ABAR_QDO_EMPTY = 3 /* +1 */, ABAR_S_FULL = 5, ABAR_P_FULL, ABAR_G_DONE,
-       ABAR_COUNT };
+enum { ABAR_KV_FULL = 0 /* +1 */, ABAR_KV_EMPTY = 2 /* +1 */, ABAR_QDO_FULL = 4 /* +1 */, ABAR_QDO_EMPTY = 6 /* +1 */,
+       ABAR_S_FULL = 8, ABAR_P_FULL, ABAR_G_DONE, ABAR_COUNT };
 
 __device__ __forceinline__ float ex2_approx_b(float x) {
   float y;
@@ -94,8 +99,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, hd = blockIdx.y, b = blockIdx.z;
   const int nq = (p.Lq + AB_T - 1) / AB_T;
+  auto item_of = [&](int it, int& kt, int& hd, int& b) {
+    kt = it % p.nkt;
+    hd = (it / p.nkt) % p.h;
+    b = it / (p.nkt * p.h);
+  };
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
-    for (int i = 0; i < ABAR_COUNT; ++i) mbar_init(bar(i), i == ABAR_P_FULL ? 256u : 1u);
+    for (int i = 0; i < ABAR_COUNT; ++i) mbar_init(bar(i), i == ABAR_P_FULL ? 256u : 1u);  // P_FULL: all softmax threads
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -116,15 +125,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   if (warp == 0) {
     // -------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar(ABAR_KV_FULL), 2 * C::TILE);
-      tma_load_3d(sK, &tmK, bar(ABAR_KV_FULL), hd * DK, kt * AB_T, b);
-      tma_load_3d(sV, &tmV, bar(ABAR_KV_FULL), hd * DK, kt * AB_T, b);
-      for (int i = 0; i < nq; ++i) {
-        const uint32_t buf = i & 1;
-        mbar_wait(bar(ABAR_QDO_EMPTY + buf), ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(bar(ABAR_QDO_FULL + buf), 2 * C::TILE);
-        tma_load_3d(sQ + buf * C::TILE, &tmQ, bar(ABAR_QDO_FULL + buf), hd * DK, i * AB_T, b);
-        tma_load_3d(sDO + buf * C::TILE, &tmDO, bar(ABAR_QDO_FULL + buf), hd * DK, i * AB_T, b);
+      uint32_t n = 0, g = 0;  // items / query tiles issued so far by this CTA
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++n) {
+        int kt, hd, b;
+        item_of(it, kt, hd, b);
+        const uint32_t kb = n & 1;
+        mbar_wait(bar(ABAR_KV_EMPTY + kb), ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar(ABAR_KV_FULL + kb), 2 * C::TILE);
+        tma_load_3d(sK + kb * C::KV_STRIDE, &tmK, bar(ABAR_KV_FULL + kb), hd * DK, kt * AB_T, b);
+        tma_load_3d(sV + kb * C::KV_STRIDE, &tmV, bar(ABAR_KV_FULL + kb), hd * DK, kt * AB_T, b);
+        for (int i = 0; i < nq; ++i, ++g) {
+          const uint32_t buf = g & 1;
+          mbar_wait(bar(ABAR_QDO_EMPTY + buf), ((g >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar(ABAR_QDO_FULL + buf), 2 * C::TILE);
+          tma_load_3d(sQ + buf * C::TILE, &tmQ, bar(ABAR_QDO_FULL + buf), hd * DK, i * AB_T, b);
+          tma_load_3d(sDO + buf * C::TILE, &tmDO, bar(ABAR_QDO_FULL + buf), hd * DK, i * AB_T, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -134,31 +150,37 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     constexpr uint32_t idesc_q = make_idesc_f16(AB_T, DK, 0, 1);    // dQ = dS K
     const uint32_t tS = tmem_base + C::COL_S, tDP = tmem_base + C::COL_DP;
     const uint32_t tDV = tmem_base + C::COL_DV, tDK = tmem_base + C::COL_DK;
-    auto issue_scores = [&](int i) {  // lane 0 only; operands of tile i are resident
-      const uint32_t buf = i & 1;
-      const uint64_t dq = make_smem_desc(sQ + buf * C::TILE, 16, C::SBO, C::SWZ);
-      const uint64_t ddo = make_smem_desc(sDO + buf * C::TILE, 16, C::SBO, C::SWZ);
-      const uint64_t dk = make_smem_desc(sK, 16, C::SBO, C::SWZ);
-      const uint64_t dv = make_smem_desc(sV, 16, C::SBO, C::SWZ);
-#pragma unroll
-      for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-#pragma unroll
-      for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tDP, ddo + 2 * k, dv + 2 * k, idesc_s, k != 0);
-      tc_commit(bar(ABAR_S_FULL));
-    };
-    mbar_wait(bar(ABAR_KV_FULL), 0);
-    mbar_wait(bar(ABAR_QDO_FULL + 0), 0);
-    tc_fence_after();
-    if (lane == 0) issue_scores(0);
-    __syncwarp();
-    for (int i = 0; i < nq; ++i) {
-      const uint32_t buf = i & 1;
-      mbar_wait(bar(ABAR_P_FULL), i & 1);  // P_i / dS_i are in shared memory; S / dP and dQ[buf] may be overwritten
-      if (i + 1 < nq) mbar_wait(bar(ABAR_QDO_FULL + ((i + 1) & 1)), ((i + 1) >> 1) & 1);
+    const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)my_items * (uint32_t)nq;  // query tiles of this CTA, all items
+    // scores of global tile g (item g / nq, its query tile g % nq): whole warp waits for the operands, lane 0 issues
+    auto issue_scores = [&](uint32_t g) {
+      const uint32_t n = g / nq, buf = g & 1, kb = n & 1;
+      if (g % nq == 0) mbar_wait(bar(ABAR_KV_FULL + kb), (n >> 1) & 1);
+      mbar_wait(bar(ABAR_QDO_FULL + buf), (g >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
-        if (i + 1 < nq) issue_scores(i + 1);  // scores of the next tile first: its softmax overlaps the MMAs below
+        const uint64_t dq = make_smem_desc(sQ + buf * C::TILE, 16, C::SBO, C::SWZ);
+        const uint64_t ddo = make_smem_desc(sDO + buf * C::TILE, 16, C::SBO, C::SWZ);
+        const uint64_t dk = make_smem_desc(sK + kb * C::KV_STRIDE, 16, C::SBO, C::SWZ);
+        const uint64_t dv = make_smem_desc(sV + kb * C::KV_STRIDE, 16, C::SBO, C::SWZ);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tDP, ddo + 2 * k, dv + 2 * k, idesc_s, k != 0);
+        tc_commit(bar(ABAR_S_FULL));
+      }
+      __syncwarp();
+    };
+    if (total > 0) issue_scores(0);
+    for (uint32_t g = 0; g < total; ++g) {
+      const uint32_t n = g / nq, i = g % nq, buf = g & 1, kb = n & 1;
+      mbar_wait(bar(ABAR_P_FULL), g & 1);  // P_g / dS_g are in shared memory; S / dP and dQ[buf] may be overwritten
+      // scores of the next tile first (possibly the first tile of the NEXT item): its softmax overlaps the MMAs below
+      if (g + 1 < total) issue_scores(g + 1);
+      tc_fence_after();
+      if (lane == 0) {
         const uint32_t tDQ = tmem_base + C::COL_DQ + buf * DK;
+        const uint32_t sKb = sK + kb * C::KV_STRIDE;
 #pragma unroll
         for (int kk = 0; kk < AB_T / 16; ++kk) {  // contraction over the 128 queries, 16 per step
           // A: panel rows [16 kk, +16) (2048 B), both 64-key panels (LBO = panel stride), MN-major
@@ -167,16 +189,17 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
           // B: dO / Q rows [16 kk, +16), d_k contiguous (MN-major, one swizzle atom wide)
           const uint64_t bdo = make_smem_desc(sDO + buf * C::TILE + kk * 16 * C::ROWB, C::TILE, C::SBO, C::SWZ);
           const uint64_t bq = make_smem_desc(sQ + buf * C::TILE + kk * 16 * C::ROWB, C::TILE, C::SBO, C::SWZ);
-          tc_mma_f16(tDV, dp, bdo, idesc_g, (i | kk) != 0);
-          tc_mma_f16(tDK, dds, bq, idesc_g, (i | kk) != 0);
+          tc_mma_f16(tDV, dp, bdo, idesc_g, (i | (uint32_t)kk) != 0);
+          tc_mma_f16(tDK, dds, bq, idesc_g, (i | (uint32_t)kk) != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < AB_T / 16; ++kk) {  // contraction over the 128 keys
           const uint64_t ads = make_smem_desc(sDS + (kk >> 2) * C::PANEL + (kk & 3) * 32, 16, 1024, SWZ_128B);
-          const uint64_t bk = make_smem_desc(sK + kk * 16 * C::ROWB, C::TILE, C::SBO, C::SWZ);
+          const uint64_t bk = make_smem_desc(sKb + kk * 16 * C::ROWB, C::TILE, C::SBO, C::SWZ);
           tc_mma_f16(tDQ, ads, bk, idesc_q, kk != 0);
         }
         tc_commit(bar(ABAR_QDO_EMPTY + buf));
+        if (i == (uint32_t)nq - 1) tc_commit(bar(ABAR_KV_EMPTY + kb));  // last use of this item's keys / values
         tc_commit(bar(ABAR_G_DONE));
       }
       __syncwarp();
@@ -191,14 +214,19 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const float c1 = p.scale * LOG2E;
     const float t_masked = -1e9f * LOG2E;
     const uint32_t sw = (uint32_t)(row & 7);
-    const size_t bh = (size_t)b * p.h + hd;
     const unsigned long long dseed = p.drop.seed != nullptr ? __ldg(p.drop.seed) : 0ull;
+    uint32_t g = 0;  // query tiles processed so far by this CTA (all items): barrier phases and the dQ buffer index
 
-    auto drain_dq = [&](int i) {  // dQ tile i (TMEM buffer i & 1) -> f32 global accumulation
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+    int kt, hd, b;
+    item_of(it, kt, hd, b);
+    const size_t bh = (size_t)b * p.h + hd;
+
+    auto drain_dq = [&](uint32_t gt, int i) {  // dQ of query tile i (global tile gt, TMEM buffer gt & 1) -> global memory
       if (half * 32 < DK) {
         const int qi = i * AB_T + row;
         uint32_t r[32];
-        tc_ld32(tmem_base + C::COL_DQ + (i & 1) * DK + half * 32 + lane_off, r);
+        tc_ld32(tmem_base + C::COL_DQ + (gt & 1) * DK + half * 32 + lane_off, r);
         tc_wait_ld();
         if (qi < p.Lq && p.dq16 != nullptr) {
           uint4* o = reinterpret_cast<uint4*>(p.dq16 + ((size_t)b * p.Lq + qi) * p.lddq16 + hd * DK + half * 32);
@@ -220,7 +248,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       }
     };
 
-    for (int i = 0; i < nq; ++i) {
+    for (int i = 0; i < nq; ++i, ++g) {
       const int qi = i * AB_T + row;
       const bool valid = qi < p.Lq;
       float m_row = 0.f, inv_l = 0.f, delta = 0.f;
@@ -235,8 +263,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         const int mq = (p.mask_rows_q == 1) ? 0 : min(qi, p.Lq - 1);
         mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
       }
-      mbar_wait(bar(ABAR_S_FULL), i & 1);
-      if (i > 0) mbar_wait(bar(ABAR_G_DONE), (i - 1) & 1);  // the MMAs reading P / dS of tile i-1 have retired
+      mbar_wait(bar(ABAR_S_FULL), g & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -279,6 +306,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk_p[j] = pk_d[j] = 0u;
         }
+        // the panels are still being read by the gradient MMAs of the previous tile until G_DONE: the first chunk's
+        // TMEM loads, exponentials and dropout decisions above overlap them, only the stores wait
+        if (cc == 0 && g > 0) mbar_wait(bar(ABAR_G_DONE), (g - 1) & 1);
         const uint32_t off = (uint32_t)(c >> 1) * C::PANEL + row * 128;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -294,11 +324,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       fence_proxy_async_smem();  // panel stores (generic proxy) -> visible to the tensor core
       tc_fence_before();
       mbar_arrive(bar(ABAR_P_FULL));
-      if (i > 0) drain_dq(i - 1);  // overlaps the MMAs of tile i (they write the other dQ buffer)
+      if (i > 0) drain_dq(g - 1, i - 1);  // overlaps the MMAs of tile i (they write the other dQ buffer)
     }
-    mbar_wait(bar(ABAR_G_DONE), (nq - 1) & 1);
+    mbar_wait(bar(ABAR_G_DONE), (g - 1) & 1);  // g already counts this item's last tile
     tc_fence_after();
-    drain_dq(nq - 1);
+    drain_dq(g - 1, nq - 1);
     // ---- dV, dK: f16, head hd's column slice, keys of this tile
     if (half * 32 < DK) {
       const int key = kt * AB_T + row;
@@ -319,6 +349,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         }
       }
     }
+    }  // work items
     tc_fence_before();
   }
   __syncthreads();
@@ -347,13 +378,21 @@ static int launch_attn_bwd(const MtnAttnCoreBwdArgs& a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_3d_f16(&tdo, a.dO, cols, a.Lq, a.B, a.lddo, (uint64_t)a.Lq * a.lddo, DK, AB_T, swz);
   if (rc) return rc;
-  AttnBwdParams p{a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk, 1.0f / sqrtf((float)DK),
+  const int nkt = (a.Lk + AB_T - 1) / AB_T;
+  const int n_items = nkt * a.h * a.B;
+  AttnBwdParams p{n_items, nkt, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk, 1.0f / sqrtf((float)DK),
                   reinterpret_cast<const float2*>(a.stats), a.delta, a.dq, a.lddq,
                   reinterpret_cast<__half*>(a.dq_f16), a.lddq16, reinterpret_cast<__half*>(a.dk), a.lddk, reinterpret_cast<__half*>(a.dv), a.lddv,
                   DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
                           a.drop_seed ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
                   (a.Lk + 31) / 32 * 32};
-  dim3 grid((a.Lk + AB_T - 1) / AB_T, a.h, a.B);
+  static int sms = 0;  // persistent CTAs: one per SM (512 TMEM columns, ~193 KB shared memory each)
+  if (sms == 0) {
+    int dev = 0;
+    MTN_CHECK_CUDA(cudaGetDevice(&dev));
+    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  dim3 grid(n_items < sms ? n_items : sms);
   MTN_CHECK_CUDA(launch_kernel(attn_core_bwd_tc_kernel<DK>, grid, dim3(AB_THREADS), C::TOTAL, st, tq, tk, tv, tdo, p));
   return MTN_OK;
 }
