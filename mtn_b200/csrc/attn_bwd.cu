@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         }
         // the panels are still being read by the gradient MMAs of the previous tile until G_DONE: the first chunk's
         // TMEM loads, exponentials and dropout decisions above overlap them, only the stores wait
-        if (cc == 0 && g > 0) mbar_wait(bar(ABAR_G_DONE), (g - 1) & 1);
+        if (cc == 0 && g > 0) {
+          mbar_wait(bar(ABAR_G_DONE), (g - 1) & 1);
+          tc_fence_after();  // (also orders the dQ drain below after the MMAs that produced it)
+        }
         const uint32_t off = (uint32_t)(c >> 1) * C::PANEL + row * 128;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
