@@ -263,6 +263,7 @@ typedef struct MtnGemmArgs {
   long long stride_A, stride_B, stride_bias, stride_add, stride_out_f32, stride_out_f16;
   float mask_scale;                   /* multiplies what passes relu_mask (0 = 1) */
   const void *drop_seed; uint32_t drop_site, drop_thresh; int drop_after_add;   /* see MtnLinearArgs */
+  float *colsum_a;                    /* weight-gradient form only: colsum_a[m] += alpha * sum_k A(m, k) */
 } MtnGemmArgs;
 int mtn_gemm_f16(const MtnGemmArgs *args, void *stream);
 int mtn_check_gemm_f16(const MtnGemmArgs *args, void *stream);   /* tests only */
@@ -295,6 +296,8 @@ typedef struct MtnLinearWgradArgs {
   float *dW; int lddw;                 /* f32 [N, K] += */
   int batch;
   long long stride_dY, stride_X, stride_dW;
+  float *dbias;                        /* optional f32 [N] += alpha * column sums of dY (the bias gradient), computed
+                                        * by one extra MMA against a tile of ones inside the same kernel          */
 } MtnLinearWgradArgs;
 int mtn_linear_wgrad(const MtnLinearWgradArgs *args, void *stream);
 

@@ -46,7 +46,7 @@ class GemmArgs(C.Structure):
                 ("stride_bias", C.c_longlong), ("stride_add", C.c_longlong), ("stride_out_f32", C.c_longlong),
                 ("stride_out_f16", C.c_longlong), ("mask_scale", C.c_float),
                 ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32),
-                ("drop_after_add", C.c_int)]
+                ("drop_after_add", C.c_int), ("colsum_a", C.c_void_p)]
 
 
 class LinearDgradArgs(C.Structure):
@@ -64,7 +64,7 @@ class LinearWgradArgs(C.Structure):
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("alpha", C.c_void_p),
                 ("dW", C.c_void_p), ("lddw", C.c_int),
                 ("batch", C.c_int), ("stride_dY", C.c_longlong), ("stride_X", C.c_longlong),
-                ("stride_dW", C.c_longlong)]
+                ("stride_dW", C.c_longlong), ("dbias", C.c_void_p)]
 
 
 class LayerNormBwdArgs(C.Structure):
@@ -527,7 +527,7 @@ def seed_bump(seed):
 # ------------------------------------------------------------------------------
 def gemm(A, B, M, N, K, a_mn=False, b_mn=False, alpha=None, bias=None, act=ACT_NONE, relu_mask=None, addend=None,
          add_period=0, accumulate=False, out_f32=None, out_f16=None, _check_kernel=False, mask_scale=0.0, drop=None,
-         drop_after_add=False):
+         drop_after_add=False, colsum_a=None):
     """General tensor-core GEMM (see MtnGemmArgs); 2-D operands, row strides honoured."""
     _req(A, torch.float16, "A"); _req(B, torch.float16, "B"); _req(alpha, torch.float32, "alpha")
     _req(bias, torch.float32, "bias"); _req(relu_mask, torch.float16, "relu_mask"); _req(addend, torch.float32, "addend")
@@ -553,6 +553,10 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, alpha=None, bias=None, act=ACT_N
     a.mask_scale = float(mask_scale)
     _set_drop(a, drop)
     a.drop_after_add = 1 if drop_after_add else 0
+    if colsum_a is not None:
+        _req(colsum_a, torch.float32, "colsum_a")
+        assert colsum_a.is_contiguous() and colsum_a.numel() == M
+        a.colsum_a = colsum_a.data_ptr()
     fn = lib().mtn_check_gemm_f16 if _check_kernel else lib().mtn_gemm_f16
     _launch("gemm", 2 * M * N * K, 2 * (M * K + N * K) + M * N * 4, lambda: fn(C.byref(a), stream_ptr()),
             keep=(A, B, alpha, bias, relu_mask, addend, out_f32, out_f16))
@@ -586,8 +590,10 @@ def linear_dgrad(dY, W, alpha=None, relu_mask=None, addend=None, out_f32=None, o
             keep=(dY, W, alpha, relu_mask, addend, out_f32, out_f16))
 
 
-def linear_wgrad(dY, X, dW, alpha=None):
-    """dW += alpha * dY^T X.  dY: [M, N] f16, X: [M, K] f16, dW: [N, K] f32 (row stride honoured)."""
+def linear_wgrad(dY, X, dW, alpha=None, dbias=None):
+    """dW += alpha * dY^T X (and dbias += alpha * column sums of dY).  dY: [M, N] f16, X: [M, K] f16, dW: [N, K] f32
+    (row stride honoured), dbias: [N] f32 contiguous."""
+    _req(dbias, torch.float32, "dbias")
     _req(dY, torch.float16, "dY"); _req(X, torch.float16, "X"); _req(dW, torch.float32, "dW")
     _req(alpha, torch.float32, "alpha")
     assert dY.dim() == 2 and X.dim() == 2 and dY.shape[0] == X.shape[0] and tuple(dW.shape) == (dY.shape[1], X.shape[1])
@@ -596,8 +602,11 @@ def linear_wgrad(dY, X, dW, alpha=None):
     a.M, a.N, a.K = dY.shape[0], dY.shape[1], X.shape[1]
     a.alpha = alpha.data_ptr() if alpha is not None else None
     a.dW, a.lddw = dW.data_ptr(), dW.stride(0)
+    if dbias is not None:
+        assert dbias.is_contiguous() and dbias.numel() == a.N
+        a.dbias = dbias.data_ptr()
     _launch("linear_wgrad", 2 * a.M * a.N * a.K, 2 * a.M * (a.N + a.K) + 8 * a.N * a.K,
-            lambda: lib().mtn_linear_wgrad(C.byref(a), stream_ptr()), keep=(dY, X, dW, alpha))
+            lambda: lib().mtn_linear_wgrad(C.byref(a), stream_ptr()), keep=(dY, X, dW, alpha, dbias))
 
 
 def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mask=None, drop=None):

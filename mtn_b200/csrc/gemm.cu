@@ -40,6 +40,7 @@ struct GemmEpi {
   int ld_mask;
   int accumulate;          // out32 += result (red.global.add), required for split-K
   int out16_pre_add;       // out16 receives the value BEFORE the addend (video encoder: relu(.) without PE)
+  float* colsum_a;         // BIAS kernels: colsum_a[m] += alpha * sum_k A(m, k)  (the bias gradient of a wgrad GEMM)
   float mask_scale;        // multiplies the elements that pass relu_mask (1/(1-p) of the dropout after the ReLU); 0 = 1
   DropCfg drop;            // dropout of the result (element index = row * N + col)
   int drop_after_add;      // 0: before the addend (SublayerConnection, mtn.py:127)  1: after it (PositionalEncoding, mtn.py:309)
@@ -60,7 +61,9 @@ struct GemmSmem {
   static constexpr int XPOSE_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = XPOSE_OFF + 8 * STAGE_TILE_BYTES;
   static constexpr int NBARS = 2 * STAGES + 4;
-  static constexpr int TOTAL = BAR_OFF + 8 * NBARS + 16 + 1024;  // + tmem slot + 1 KB alignment slack
+  static constexpr int ONES_OFF = (BAR_OFF + 8 * NBARS + 16 + 255) / 256 * 256;  // 1 KB of f16 1.0 (bias-gradient MMA)
+  static constexpr int TOTAL = ONES_OFF + 1024 + 1024;  // + 1 KB alignment slack
+  static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
 // Persistent kernel: each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so
@@ -80,7 +83,10 @@ struct GemmSmem {
 // ksplit > 1: tile index also enumerates contraction slices of kb_per_split k-blocks (split-K).
 // DROP: compile the dropout of the result into the epilogue (training forward only; the inference kernels carry
 // none of its registers or branches).
-template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP>
+// BIAS: the weight-gradient form additionally accumulates the row sums of its A operand (dY^T), i.e. the bias
+// gradient, on the tensor core: one extra N=16 MMA per k-step against a constant tile of ones (any layout of an
+// all-ones tile is the same tile), 16 more TMEM columns per accumulator buffer, one atomic per output row.
+template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP, int BIAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmEpi epi0, int M, int N, int K, int tiles_n, int tiles_per_batch, int num_tiles,
@@ -129,7 +135,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     mbar_fence_init();
   }
   __syncwarp();  // cluster barriers are .aligned: every warp must arrive converged
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  static_assert(!BIAS || (A_MN == 1 && B_MN == 1 && 2 * BN + 64 <= 512), "BIAS: weight-gradient form, BN <= 128");
+  constexpr uint32_t TMEM_COLS = BIAS ? 512u : 2u * BN;
+  if (BIAS && warp == 2) {  // the constant ones tile
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + L::ONES_OFF);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ones[lane + 32 * i] = 0x3C003C00u;  // two f16 1.0
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers must exist before any multicast
   tc_fence_after();
@@ -180,6 +194,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(bar_acc_empty(buf), ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN;
+      const uint32_t d_bias = tmem_base + 2 * BN + buf * 32;  // BIAS: 16 columns used, 32 reserved per buffer
+      const bool first_n = ((t % tiles_per_batch) % tiles_mn) % tiles_n == 0;  // one n-tile per row block sums the rows
       int kb0, kb1;
       kb_range(t % tiles_per_batch, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -196,6 +212,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             tc_mma_f16(d_tmem, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, ((kb - kb0) | k) != 0);
+          if (BIAS && first_n) {
+            constexpr uint32_t idesc_b = make_idesc_f16(BM, 16, A_MN, 1);
+            const uint64_t dones = make_smem_desc(base + L::ONES_OFF, 128, 256, SWZ_NONE);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) tc_mma_f16(d_bias, da + (A_MN ? 128 : 2) * k, dones, idesc_b, ((kb - kb0) | k) != 0);
+          }
           if (CL == 1) tc_commit(bar_empty(s));  // frees the stage when these MMAs retire
           else tc_commit_mc(bar_empty(s), kMask);
           if (kb == kb1 - 1) tc_commit(bar_acc_full(buf));
@@ -261,6 +283,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      if (BIAS && epi.colsum_a != nullptr && n0 == 0 && half == 0) {  // row sums of A: the bias gradient
+        uint32_t rb[32];
+        tc_ld32(tmem_base + 2 * BN + buf * 32 + ((uint32_t)(q * 32) << 16), rb);
+        tc_wait_ld();
+        const int r = m0 + q * 32 + lane;
+        if (r < M) atomicAdd(epi.colsum_a + r, __uint_as_float(rb[0]) * alpha);
+      }
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
         if (f16_only) {
@@ -434,7 +463,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -459,12 +488,12 @@ static int make_operand_map(CUtensorMap* tm, const void* p, int mn_major, int MN
   return make_tmap_3d_f16(tm, p, K, MN, batch, ld, batch > 1 ? (uint64_t)stride : (uint64_t)MN * ld, BK, box_mn, TM_SWZ_128);
 }
 
-template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP = 0>
+template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP = 0, int BIAS = 0>
 static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   static int max_clusters = 0;  // co-resident clusters (1 CTA per SM)
   if (max_clusters == 0) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP>,
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP, BIAS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     if (CL == 1) {
       max_clusters = g_num_sms;
@@ -478,7 +507,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
       attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       int n = 0;
-      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP>, &cfg));
+      MTN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP, BIAS>, &cfg));
       MTN_REQUIRE(n > 0, MTN_E_CUDA, "gemm: no cluster of %d CTAs fits on this device", CL);
       max_clusters = n;
     }
@@ -491,7 +520,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
               reinterpret_cast<__half*>(a.out_f16), a.ld16, a.alpha, reinterpret_cast<const __half*>(a.relu_mask),
-              a.ld_mask, a.accumulate, a.out16_pre_add, a.mask_scale,
+              a.ld_mask, a.accumulate, a.out16_pre_add, a.colsum_a, a.mask_scale,
               DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
                       a.drop_thresh ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
               a.drop_after_add, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
@@ -512,7 +541,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   const int tiles_per_batch = tiles_mn * ksplit;
   const int num_super = tiles_per_batch * batch;
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
-  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP>, dim3(clusters * CL),
+  MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP, BIAS>, dim3(clusters * CL),
                                        dim3(GEMM_THREADS), L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K,
                                        tiles_n, tiles_per_batch, num_super, tiles_mn, kb_per_split));
   return MTN_OK;
@@ -548,6 +577,9 @@ static int validate_gemm(const MtnGemmArgs* a) {
   if (a->drop_seed != nullptr)
     MTN_REQUIRE(a->drop_thresh < 65536u && a->batch <= 1 && !a->accumulate && !a->a_mn && !a->b_mn, MTN_E_ARG,
                 "gemm: dropout needs thresh < 65536, the forward (K-major) form, no batch, no accumulate");
+  if (a->colsum_a != nullptr)
+    MTN_REQUIRE(a->a_mn && a->b_mn && a->accumulate && a->M % 8 == 0, MTN_E_ARG,
+                "gemm: colsum_a (bias gradient) belongs to the accumulating weight-gradient form");
   if (a->accumulate)
     MTN_REQUIRE(a->out_f32 != nullptr && a->out_f16 == nullptr && a->bias == nullptr && a->addend == nullptr &&
                     a->act == MTN_ACT_NONE && a->relu_mask == nullptr,
@@ -597,6 +629,13 @@ static int run_gemm(const MtnGemmArgs* a, void* stream) {
     case 1:
       return big ? launch_gemm<256, 4, 1, 0, 1>(*a, st) : launch_gemm<128, 6, 1, 0, 1>(*a, st);
     case 3:
+      if (a->colsum_a != nullptr) {
+        if (!big && a->batch <= 1) return launch_gemm<128, 6, 1, 1, 1, 0, 1>(*a, st);   // bias gradient on the tensor core
+        // wide tiles have no TMEM columns to spare: the row sums of A take a separate pass over it
+        rc = mtn_cast_colsum(a->A, 1, a->lda, nullptr, 0, nullptr, 0, a->K, a->M, nullptr, a->alpha, a->colsum_a, nullptr, 0, 0,
+                             stream);
+        if (rc) return rc;
+      }
       return big ? launch_gemm<256, 4, 1, 1, 1>(*a, st) : launch_gemm<128, 6, 1, 1, 1>(*a, st);
     default:
       return set_error(MTN_E_ARG, "gemm: the (A MN-major, B K-major) form is not instantiated");
@@ -632,6 +671,11 @@ __global__ void gemm_f16_check_kernel(const __half* A, int lda, int a_mn, const 
     const float bv = __half2float(b_mn ? B[(size_t)k * ldb + n] : B[(size_t)n * ldb + k]);
     acc = fmaf(av, bv, acc);
   }
+  if (epi.colsum_a != nullptr && n == 0) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += __half2float(a_mn ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]);
+    epi.colsum_a[m] += s * (epi.alpha ? epi.alpha[0] : 1.f);
+  }
   if (epi.alpha) acc *= epi.alpha[0];
   if (epi.bias) acc += epi.bias[n];
   if (epi.act == MTN_ACT_RELU) acc = fmaxf(acc, 0.f);
@@ -658,7 +702,7 @@ static int run_check_gemm(const MtnGemmArgs* a, void* stream) {
   if (rc) return rc;
   GemmEpi epi{a->bias, a->act, a->addend, a->ld_add, a->add_period, a->out_f32, a->ld32,
               reinterpret_cast<__half*>(a->out_f16), a->ld16, a->alpha, reinterpret_cast<const __half*>(a->relu_mask),
-              a->ld_mask, a->accumulate, a->out16_pre_add, a->mask_scale,
+              a->ld_mask, a->accumulate, a->out16_pre_add, a->colsum_a, a->mask_scale,
               DropCfg{reinterpret_cast<const unsigned long long*>(a->drop_seed), a->drop_site, a->drop_thresh,
                       a->drop_thresh ? 1.f / (1.f - a->drop_thresh / 65536.f) : 1.f},
               a->drop_after_add, 0, 0, 0, 0};
@@ -715,6 +759,7 @@ extern "C" int mtn_linear_wgrad(const MtnLinearWgradArgs* a, void* stream) {
   g.M = a->N; g.N = a->K; g.K = a->M;
   g.alpha = a->alpha;
   g.accumulate = 1;
+  g.colsum_a = a->dbias;
   g.out_f32 = a->dW; g.ld32 = a->lddw;
   g.batch = a->batch; g.stride_A = a->stride_dY; g.stride_B = a->stride_X; g.stride_out_f32 = a->stride_dW;
   return mtn::run_gemm(&g, stream);

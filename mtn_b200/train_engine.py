@@ -485,24 +485,20 @@ class DecoderTrainer(object):
                            dkd, dvd, mask_bits=t["bits"], drop=t["drop_p"])
         # ---- Q (or QKV) projection
         dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        # (bias gradients = column sums of the f16 gradient: computed inside the weight-gradient GEMM by one extra MMA
+        #  against a tile of ones, off the critical path)
         if t["self_attn"]:
-            gb = G[(gk, l, "bqkv")]
-            if one_tile:
-                _lib.cast_colsum(dqkv, colsum=gb, alpha=invS)
-            else:
-                _lib.cast_colsum(dq32, dst_f16=dq16, colsum=gb[:d], alpha=invS)
-                wq.append(lambda: _lib.cast_colsum(dqkv[:, d:], colsum=gb[d:], alpha=invS))   # off the critical path
+            if not one_tile:
+                _lib.cast_colsum(dq32, dst_f16=dq16)
             _lib.linear_dgrad(dqkv, A["w_qkv"], out_f32=dxn)
-            wq.append(lambda: _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS))
+            wq.append(lambda: _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS, dbias=G[(gk, l, "bqkv")]))
         else:
             wq_key, bq_key = ("wq", "bq") if (gk, l, "wq") in G else ("wqkv", "bqkv")
             gw, gb = G[(gk, l, wq_key)], G[(gk, l, bq_key)]
-            if one_tile:
-                wq.append(lambda: _lib.cast_colsum(dq16, colsum=gb[:d], alpha=invS))      # bias gradient off the critical path
-            else:
-                _lib.cast_colsum(dq32, dst_f16=dq16, colsum=gb[:d], alpha=invS)
+            if not one_tile:
+                _lib.cast_colsum(dq32, dst_f16=dq16)
             _lib.linear_dgrad(dq16, A["w_qkv"][:d], out_f32=dxn)
-            wq.append(lambda: _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS))
+            wq.append(lambda: _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS, dbias=gb[:d]))
         self._flush(bk, wq)
         self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS, nxt=nxt)
         bk["keep"].append((dq32, delta, do16, dxn))
@@ -524,8 +520,7 @@ class DecoderTrainer(object):
         ms = 1.0 / (1.0 - t["drop_h"][2] / 65536.0) if t["drop_h"] is not None else 0.0
         _lib.linear_dgrad(dx16, Fw["w_2"], relu_mask=t["hid"], out_f16=dhid, mask_scale=ms)
         wq.append(lambda: _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS))
-        wq.append(lambda: _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS))
-        wq.append(lambda: _lib.cast_colsum(dhid, colsum=G[(gk, l, "b1")], alpha=invS))   # bias gradient: off the critical path too
+        wq.append(lambda: _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS, dbias=G[(gk, l, "b1")]))
         self._flush(bk, wq)
         dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
         _lib.linear_dgrad(dhid, Fw["w_1"], out_f32=dxn)
@@ -535,7 +530,7 @@ class DecoderTrainer(object):
     def _mem_bwd(self, bk, dkv, mem16, w_kv, gw, gb):
         """Backward of a hoisted memory K/V projection: bias gradient, weight gradient, memory gradient."""
         invS = bk["invS"]
-        wq = [lambda: _lib.cast_colsum(dkv, colsum=gb, alpha=invS), lambda: _lib.linear_wgrad(dkv, mem16, gw, alpha=invS)]
+        wq = [lambda: _lib.linear_wgrad(dkv, mem16, gw, alpha=invS, dbias=gb)]
         self._flush(bk, wq)
         dmem = torch.empty(mem16.shape[0], mem16.shape[1], dtype=torch.float32, device=dkv.device)
         _lib.linear_dgrad(dkv, w_kv, alpha=invS, out_f32=dmem)
@@ -643,8 +638,7 @@ class DecoderTrainer(object):
                         buf, a16 = dkv_ae[i][l], ctx["ae16"][i][l]
                         gw, gb = G[(gk, l, "wqkv")][d:], G[(gk, l, "bqkv")][d:]
                         _lib.linear_dgrad(buf, A2["w_qkv"][d:], addend=dae, out_f32=dae)
-                        self._flush(bk, [lambda buf=buf, gb=gb: _lib.cast_colsum(buf, colsum=gb, alpha=invS),
-                                         lambda buf=buf, a16=a16, gw=gw: _lib.linear_wgrad(buf, a16, gw, alpha=invS)])
+                        self._flush(bk, [lambda buf=buf, a16=a16, gw=gw, gb=gb: _lib.linear_wgrad(buf, a16, gw, alpha=invS, dbias=gb)])
                         self._ffn_bwd(bk, t, dae, None, nxt)
                     elif key == "ae_vid":
                         buf = dkv_vid[i]
