@@ -107,12 +107,12 @@ def test_linear_dgrad_wgrad_vs_autograd(L, M, N, K):
     dx = torch.empty(M, K, device="cuda")
     L.linear_dgrad(dy16, w.half().cuda(), alpha=S2[1:2], out_f32=dx)
     dW = torch.zeros(N, K, device="cuda")
-    db2 = torch.ones(N, device="cuda")            # bias gradient from the same kernel (extra MMA against ones)
+    db2 = db.clone()                              # bias gradient from the same kernel (extra MMA against ones), accumulated
     L.linear_wgrad(dy16, x.half().cuda(), dW, alpha=S2[1:2], dbias=db2)
     torch.cuda.synchronize()
     assert G.rel_err(dx.cpu(), dyr @ w) < 3e-5
     assert G.rel_err(dW.cpu(), dyr.t() @ x) < 3e-5
-    assert G.rel_err(db2.cpu() - 1, dyr.sum(0)) < 3e-5
+    assert G.rel_err(db2.cpu(), db.cpu() + dyr.sum(0)) < 3e-5
 
 
 # ------------------------------------------------------------------ row kernels
