@@ -135,8 +135,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     mbar_fence_init();
   }
   __syncwarp();  // cluster barriers are .aligned: every warp must arrive converged
-  static_assert(!BIAS || (A_MN == 1 && B_MN == 1 && 2 * BN + 64 <= 512), "BIAS: weight-gradient form, BN <= 128");
-  constexpr uint32_t TMEM_COLS = BIAS ? 512u : 2u * BN;
+  static_assert(!BIAS || (A_MN == 1 && B_MN == 1 && BN == 128), "BIAS: weight-gradient form, BN = 128");
+  // BIAS kernels (one-wave split-K launches: a CTA rarely sees a second tile) keep ONE accumulator buffer, so that
+  // accumulator + row sums still fit 256 TMEM columns and two CTAs of consecutive launches can overlap on an SM (PDL)
+  constexpr uint32_t NBUF = BIAS ? 1u : 2u;
+  constexpr uint32_t TMEM_COLS = BIAS ? 256u : 2u * BN;
+  constexpr uint32_t BIAS_COL = BN;  // BIAS: columns [BN, BN + 16)
   if (BIAS && warp == 2) {  // the constant ones tile
     uint32_t* ones = reinterpret_cast<uint32_t*>(smem + L::ONES_OFF);
 #pragma unroll
@@ -190,11 +194,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     constexpr uint32_t idesc = make_idesc_f16(BM, BN, A_MN, B_MN);
     uint32_t it = 0, lt = 0;  // ring position, local tile counter
     for (int t = first_tile; t < num_tiles; t += tile_stride, ++lt) {
-      const uint32_t buf = lt & 1;
-      mbar_wait(bar_acc_empty(buf), ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      const uint32_t buf = lt % NBUF;
+      mbar_wait(bar_acc_empty(buf), ((lt / NBUF) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN;
-      const uint32_t d_bias = tmem_base + 2 * BN + buf * 32;  // BIAS: 16 columns used, 32 reserved per buffer
+      const uint32_t d_bias = tmem_base + BIAS_COL;
       const bool first_n = ((t % tiles_per_batch) % tiles_mn) % tiles_n == 0;  // one n-tile per row block sums the rows
       int kb0, kb1;
       kb_range(t % tiles_per_batch, kb0, kb1);
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (epi.out32) epi.out32 += bt * epi.s_out32;
         if (epi.out16) epi.out16 += bt * epi.s_out16;
       }
-      const uint32_t buf = lt & 1;
+      const uint32_t buf = lt % NBUF;
       const int row0 = m0 + q * 32 + sub_r;  // this lane's first row; the others are +8, +16, +24
       // per-row element offsets, hoisted out of the chunk loop
       size_t off32[4], off16[4], offad[4], offmk[4];
@@ -280,12 +284,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         offmk[i] = (size_t)r * epi.ld_mask;
         offad[i] = (size_t)(epi.add_period > 0 ? r % epi.add_period : r) * epi.ld_add;
       }
-      mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
+      mbar_wait(bar_acc_full(buf), (lt / NBUF) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       if (BIAS && epi.colsum_a != nullptr && n0 == 0 && half == 0) {  // row sums of A: the bias gradient
         uint32_t rb[32];
-        tc_ld32(tmem_base + 2 * BN + buf * 32 + ((uint32_t)(q * 32) << 16), rb);
+        tc_ld32(tmem_base + BIAS_COL + ((uint32_t)(q * 32) << 16), rb);
         tc_wait_ld();
         const int r = m0 + q * 32 + lane;
         if (r < M) atomicAdd(epi.colsum_a + r, __uint_as_float(rb[0]) * alpha);
