@@ -199,7 +199,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN;
       const uint32_t d_bias = tmem_base + BIAS_COL;
-      const bool first_n = ((t % tiles_per_batch) % tiles_mn) % tiles_n == 0;  // one n-tile per row block sums the rows
+      // BIAS: the n-tiles of a row block share the row-sum work -- tile j takes the k-blocks with kb % tiles_n == j
+      const int nidx = ((t % tiles_per_batch) % tiles_mn) % tiles_n;
+      bool bias_started = false;
       int kb0, kb1;
       kb_range(t % tiles_per_batch, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -216,11 +218,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             tc_mma_f16(d_tmem, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, ((kb - kb0) | k) != 0);
-          if (BIAS && first_n) {
+          if (BIAS && kb % tiles_n == nidx) {
             constexpr uint32_t idesc_b = make_idesc_f16(BM, 16, A_MN, 1);
             const uint64_t dones = make_smem_desc(base + L::ONES_OFF, 128, 256, SWZ_NONE);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) tc_mma_f16(d_bias, da + (A_MN ? 128 : 2) * k, dones, idesc_b, ((kb - kb0) | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_f16(d_bias, da + (A_MN ? 128 : 2) * k, dones, idesc_b, (bias_started || k != 0) ? 1u : 0u);
+            bias_started = true;
           }
           if (CL == 1) tc_commit(bar_empty(s));  // frees the stage when these MMAs retire
           else tc_commit_mc(bar_empty(s), kMask);
@@ -287,7 +291,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(bar_acc_full(buf), (lt / NBUF) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-      if (BIAS && epi.colsum_a != nullptr && n0 == 0 && half == 0) {  // row sums of A: the bias gradient
+      int bkb0, bkb1;
+      kb_range(t % tiles_per_batch, bkb0, bkb1);
+      const int nidx = tmn % tiles_n;
+      const bool has_bias = bkb0 + ((nidx - bkb0 % tiles_n) + tiles_n) % tiles_n < bkb1;  // this tile summed >= 1 k-block
+      if (BIAS && epi.colsum_a != nullptr && has_bias && half == 0) {  // partial row sums of A: the bias gradient
         uint32_t rb[32];
         tc_ld32(tmem_base + BIAS_COL + ((uint32_t)(q * 32) << 16), rb);
         tc_wait_ld();
