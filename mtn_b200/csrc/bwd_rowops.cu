@@ -255,7 +255,7 @@ __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
 template <typename TIn>
 __global__ void __launch_bounds__(256)
     cast_colsum_kernel(const TIn* __restrict__ src, int ld_src, __half* __restrict__ dst, int ld_dst,
-                       const __half* __restrict__ relu_mask, int ld_mask, int rows, int vcols,
+                       const __half* __restrict__ relu_mask, int ld_mask, int rows, int vcols, int rows_per_block,
                        const float* __restrict__ scale, const float* __restrict__ alpha, float* __restrict__ colsum,
                        const DropCfg drop) {
   pdl_launch_dependents();
@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(256)
   const bool active = vc < vcols;
   const float sc = scale ? __ldg(scale) : 1.f;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int r_end = active ? min(rows, (int)(blockIdx.y + 1) * CC_ROWS_PER_BLOCK) : 0;
-  const int r0 = blockIdx.y * CC_ROWS_PER_BLOCK + threadIdx.y;
+  const int r_end = active ? min(rows, (int)(blockIdx.y + 1) * rows_per_block) : 0;
+  const int r0 = blockIdx.y * rows_per_block + threadIdx.y;
   constexpr int U = 4;  // rows per thread and batch: all loads of a batch are issued before any use
   float v[U][8], m[U][8];
 #pragma unroll 1
@@ -635,15 +635,21 @@ extern "C" int mtn_cast_colsum(const void* src, int src_is_f16, int ld_src, void
               MTN_E_ALIGN, "cast_colsum: alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int vcols = cols / 8;
-  dim3 grid((vcols + 31) / 32, (rows + CC_ROWS_PER_BLOCK - 1) / CC_ROWS_PER_BLOCK), block(32, 8);
+  // rows per block: at least 64; large inputs get about 8 blocks per SM in total, so that the column-sum atomics per
+  // address stay in the tens (they serialise in L2) instead of rows / 64
+  const int gx = (vcols + 31) / 32;
+  int rpb = CC_ROWS_PER_BLOCK;
+  const int want_y = (8 * 148 + gx - 1) / gx;
+  if ((rows + rpb - 1) / rpb > want_y) rpb = ((rows + want_y - 1) / want_y + 31) / 32 * 32;
+  dim3 grid(gx, (rows + rpb - 1) / rpb), block(32, 8);
   __half* d16 = reinterpret_cast<__half*>(dst_f16);
   const __half* mk = reinterpret_cast<const __half*>(relu_mask);
   if (src_is_f16)
     MTN_CHECK_CUDA(launch_kernel(cast_colsum_kernel<__half>, grid, block, 0, st, reinterpret_cast<const __half*>(src), ld_src,
-                                 d16, ld_dst, mk, ld_mask, rows, vcols, scale, alpha, colsum, drop));
+                                 d16, ld_dst, mk, ld_mask, rows, vcols, rpb, scale, alpha, colsum, drop));
   else
     MTN_CHECK_CUDA(launch_kernel(cast_colsum_kernel<float>, grid, block, 0, st, reinterpret_cast<const float*>(src), ld_src,
-                                 d16, ld_dst, mk, ld_mask, rows, vcols, scale, alpha, colsum, drop));
+                                 d16, ld_dst, mk, ld_mask, rows, vcols, rpb, scale, alpha, colsum, drop));
   return MTN_OK;
 }
 
