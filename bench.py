@@ -107,11 +107,13 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def traffic_from_profiles(n_launches):
+def traffic_from_profiles(n_launches, train=False):
     """DRAM bytes per launch of the linear kernel from the committed ncu capture of the same step
-    (profiles/rNN_gemm_traffic.json, written by tools/summarize_profiles.py); None if absent."""
+    (profiles/rNN_gemm_traffic.json for the forward, rNN_train_gemm_traffic.json for the training step, written by
+    tools/summarize_profiles.py); None if absent."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json"))
+                   if ("_train_" in os.path.basename(f)) == train)
     if not files:
         return None
     t = json.load(open(files[-1]))
@@ -295,6 +297,7 @@ def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over
                            "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
                            "frac": gemm_fl / (gemm_ms * 1e-3) / 1e12 / pk, "launches": sum(kt[k]["launches"] for k in
                                                                                           ("linear", "linear_dgrad", "linear_wgrad") if k in kt)}
+        res["roofline"]["traffic"] = traffic_from_profiles(res["roofline"]["launches"], train=True)
         n_launches = len(rec)
         del rec
         for i in range(3):
