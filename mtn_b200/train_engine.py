@@ -1,15 +1,16 @@
 """Training execution of the MTN decoder cascade: forward with a tape, hand-written backward.
 
-``DecoderTrainer.apply`` is what ``mtn.Decoder.forward`` (reference mtn.py:158-164) runs when autograd is
-recording.  The whole N-layer cascade (reference mtn.py:181-218 per layer) is ONE ``torch.autograd.Function``:
+``autograd.DecoderFn`` (forward -> ``DecoderTrainer.forward``, backward -> ``DecoderTrainer.backward``) is what
+``mtn.Decoder.forward`` (reference mtn.py:158-164) runs when autograd is recording.  The whole N-layer cascade
+(reference mtn.py:181-218 per layer) is ONE ``torch.autograd.Function``:
 its forward launches the same sm_100a kernels as the inference engine and keeps, per SublayerConnection, the
 f32 residual input, the f16 LayerNorm output, the f16 Q/K/V and attention outputs and the softmax statistics;
 its backward walks that tape in reverse and launches the backward kernels of ``include/mtn_b200.h`` (ABI v3):
 
-  out-projection / w_2 : dY -> f16 (+ bias gradient, one pass)  ->  dgrad GEMM, split-K wgrad GEMM
-  attention core       : delta = rowsum(dO * O);  tcgen05 backward kernel (dQ f32 accumulate, dK / dV f16)
-  Q / QKV / w_1        : dgrad + wgrad GEMMs (ReLU mask in the dgrad epilogue)
-  LayerNorm            : row kernel, residual-stream gradient updated in place
+  out-projection / w_2 : dY as f16 (handed over by the previous LayerNorm backward)  ->  dgrad GEMM, split-K wgrad GEMM
+  attention core       : delta = rowsum(dO * O);  tcgen05 backward kernel (dQ f16 or f32-accumulated, dK / dV f16)
+  Q / QKV / w_1        : dgrad + wgrad GEMMs (ReLU mask in the dgrad epilogue, bias gradient inside the wgrad GEMM)
+  LayerNorm            : row kernel, residual-stream gradient updated in place, f16 copy + bias gradient for the next sublayer
   hoisted memory K/V   : every layer writes its dK / dV columns into ONE [rows, N*2d] buffer per memory;
                          one wide dgrad + one wgrad per memory at the end.
 
