@@ -81,6 +81,9 @@ int mtn_embed_dropout_fwd(const int64_t *ids, const float *lut, const float *pe,
  * padding); padded frames are zeroed; output as f16 (video-encoder operand) and/or f32.        */
 int mtn_feature_prep_fwd(const float *ft, int frames, int F, uint8_t *mask, void *out_f16,
                          float *out_f32, void *stream);
+/* Features stored as f16 on the host (half the upload; the rounding is the one mtn_feature_prep_fwd applies on the
+ * device, so everything downstream is bit-identical): same mask / zeroing, f16 in, f16 out.  F % 8 == 0.        */
+int mtn_feature_prep_f16_fwd(const void *ft_f16, int frames, int F, uint8_t *mask, void *out_f16, void *stream);
 
 /* ---- generator tail ---------------------------------------------
  * Replaces F.log_softmax(proj(x), -1) (mtn.py:68-69) after mtn_linear_fwd produced the logits,

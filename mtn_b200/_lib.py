@@ -133,6 +133,7 @@ SYMBOLS = {
     "mtn_embed_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_feature_prep_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtn_feature_prep_f16_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_log_softmax_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p]),
     "mtn_label_smoothing_workspace_bytes": (C.c_size_t, [C.c_int]),
@@ -405,10 +406,18 @@ def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None, drop=None):
 def feature_prep(ft, out_f16=None, out_f32=None):
     """ft: [B, L, F] f32 raw features -> (mask bool [B, 1, L], out).  Frames that are all 1.0 are padding
     (data_utils.py:29) and are zeroed (data_utils.py:30)."""
-    _req(ft, torch.float32, "ft")
     ftc = ft.contiguous()
     B, L, F = ftc.shape
     mask = torch.empty(B, 1, L, dtype=torch.bool, device=ft.device)
+    if ft.dtype == torch.float16:          # features stored / uploaded as f16: same result, half the bytes
+        _req(ft, torch.float16, "ft")
+        assert out_f32 is None
+        out_f16 = out_f16 if out_f16 is not None else torch.empty(B, L, F, dtype=torch.float16, device=ft.device)
+        _launch("feature_prep", 0, B * L * F * 4,
+                lambda: lib().mtn_feature_prep_f16_fwd(ptr(ftc), B * L, F, ptr(mask), ptr(out_f16), stream_ptr()),
+                keep=(ftc, mask, out_f16))
+        return mask, out_f16
+    _req(ft, torch.float32, "ft")
     if out_f16 is None and out_f32 is None:
         out_f16 = torch.empty(B, L, F, dtype=torch.float16, device=ft.device)
     _launch("feature_prep", 0, B * L * F * (4 + (2 if out_f16 is not None else 0) + (4 if out_f32 is not None else 0)),

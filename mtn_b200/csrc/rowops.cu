@@ -237,6 +237,29 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Same for features that were stored / uploaded as f16 (half the PCIe bytes; the f16 rounding is the one the
+// kernel above applies on the device, so the results are bit-identical): mask + zeroing, f16 in, f16 out.
+__global__ void __launch_bounds__(256)
+    feature_prep_f16_kernel(const __half* __restrict__ ft, int frames, int F, uint8_t* __restrict__ mask,
+                            __half* __restrict__ out16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= frames) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* fr = reinterpret_cast<const uint4*>(ft + (size_t)row * F);
+  const int n8 = F >> 3;
+  bool any = false;
+  for (int i = lane; i < n8; i += 32) {
+    const uint4 v = __ldg(fr + i);
+    any |= (v.x != 0x3C003C00u) | (v.y != 0x3C003C00u) | (v.z != 0x3C003C00u) | (v.w != 0x3C003C00u);  // f16 1.0 pairs
+  }
+  const bool keep = __any_sync(0xffffffffu, any);
+  if (lane == 0) mask[row] = keep ? 1 : 0;
+  for (int i = lane; i < n8; i += 32)
+    reinterpret_cast<uint4*>(out16 + (size_t)row * F)[i] = keep ? __ldg(fr + i) : make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ----------------------------------------------------------------------------
 // Row-wise log-softmax over the first V columns (Generator, mtn.py:68-69) and row arg-max
 // (greedy decoding, data_utils.py:183).  One 128-thread block per row.
@@ -497,6 +520,16 @@ extern "C" int mtn_embed_dropout_fwd(const int64_t* ids, const float* lut, const
 #define MTN_EMBED(V) MTN_CHECK_CUDA(launch_kernel(embed_rows_kernel<V>, grid, block, 0, st, ids64, lut, pe, rows, L, vocab, scale, a_2, b_2, eps, y_f32, y16, drop))
   if (d == 128) MTN_EMBED(1); else if (d == 256) MTN_EMBED(2); else if (d == 512) MTN_EMBED(4); else MTN_EMBED(8);
 #undef MTN_EMBED
+  return MTN_OK;
+}
+
+extern "C" int mtn_feature_prep_f16_fwd(const void* ft_f16, int frames, int F, uint8_t* mask, void* out_f16, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(ft_f16 && mask && out_f16, MTN_E_ARG, "feature_prep_f16: NULL pointer");
+  MTN_REQUIRE(frames > 0 && F > 0 && F % 8 == 0, MTN_E_SHAPE, "feature_prep_f16: frames=%d F=%d (F %% 8 == 0)", frames, F);
+  MTN_REQUIRE(aligned16(ft_f16) && aligned16(out_f16), MTN_E_ALIGN, "feature_prep_f16: alignment");
+  MTN_CHECK_CUDA(launch_kernel(feature_prep_f16_kernel, dim3((frames + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                               reinterpret_cast<const __half*>(ft_f16), frames, F, mask, reinterpret_cast<__half*>(out_f16)));
   return MTN_OK;
 }
 

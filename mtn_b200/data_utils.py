@@ -36,8 +36,10 @@ class Batch:
         self.his_st = his_st
         if fts is not None:
             dev = _default_device(query)
-            permuted = [(torch.from_numpy(ft) if isinstance(ft, np.ndarray) else ft).float().to(dev)
-                        .permute(1, 0, 2) for ft in fts]
+            def load(ft):      # f16 features (a loader that stores them as f16: half the upload) stay f16
+                t = torch.from_numpy(ft) if isinstance(ft, np.ndarray) else ft
+                return (t if t.dtype == torch.float16 and dev.type == "cuda" else t.float()).to(dev).permute(1, 0, 2)
+            permuted = [load(ft) for ft in fts]
             if dev.type == "cuda" and all(ft.shape[2] % 8 == 0 for ft in permuted):
                 # one pass per modality: padding mask + zeroing + f16 operand of the video encoder
                 from . import _lib

@@ -379,3 +379,25 @@ def test_attention_function_and_numpy_batch(M):
         assert b.fts[i].is_cuda and torch.equal(b.fts_mask[i].cpu(), m["fts_mask"][i])
         assert torch.equal(b.fts[i].float().cpu(), m["fts"][i].half().float())
     assert torch.equal(b.trg_mask.cpu(), m["trg_mask"])
+
+
+def test_f16_features_are_bit_identical_to_f32_features(M):
+    """Features handed to Batch as f16 (a loader storing them that way halves the upload): the f16 rounding is the one
+    the feature-preparation kernel applies to f32 features on the device, so masks and outputs must be bit-identical."""
+    mtn, du = M
+    cfg = dict(G.CFG1)
+    sd = O.init_state_dict(cfg, 5)
+    model = build(mtn, cfg, sd)
+    inp = O.synth_inputs(cfg, B=3, Q=8, C=8, H=16, T=8, Lv=[16, 8], seed=4)
+    g = lambda t: t.cuda()
+
+    def run(cast):
+        b = du.Batch(g(inp["query"]), g(inp["his"]), None, [cast(g(f)).permute(1, 0, 2).contiguous() for f in inp["fts"]],
+                     g(inp["cap"]), g(inp["trg"]), g(inp["trg_y"]), 1)
+        with torch.no_grad():
+            out, ae = model.forward(b)
+        return out, ae, b.fts_mask
+    o32, a32, m32 = run(lambda t: t)
+    o16, a16, m16 = run(lambda t: t.half())
+    assert torch.equal(o32, o16) and all(torch.equal(x, y) for x, y in zip(a32, a16))
+    assert all(torch.equal(x, y) for x, y in zip(m32, m16))
