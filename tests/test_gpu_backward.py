@@ -232,6 +232,9 @@ ATT_CASES = [
     (2, 4, 8, 16, 32, "keypad"), (2, 8, 64, 64, 64, "keypad"), (3, 8, 130, 300, 64, "keypad"),
     (2, 8, 256, 256, 64, "causal"), (2, 4, 20, 20, 32, "causal"), (2, 8, 40, 512, 64, "none"),
     (2, 8, 33, 70, 64, "allmasked_row"), (1, 8, 256, 512, 64, "keypad"),
+    (2, 8, 256, 64, 64, "keypad"),       # one key tile, two query tiles: dQ stored as f16 per tile
+    (24, 8, 130, 300, 64, "keypad"),     # 576 work items on 148 persistent CTAs: several items per CTA, double-buffered K/V
+    (40, 4, 70, 64, 32, "causal_sq"),    # 160 single-tile items, d_k = 32
 ]
 
 
@@ -258,6 +261,8 @@ def test_attn_core_bwd_vs_autograd(L, B, h, Lq, Lk, dk, kind):
     elif kind == "causal":
         mask = O.subsequent_mask(Lq).expand(B, -1, -1).clone()
         mask[B - 1, :, Lk - 3:] = False
+    elif kind == "causal_sq":            # rectangular "causal-like" mask (Lq != Lk): lower-triangular band
+        mask = (torch.arange(Lk)[None, :] <= torch.arange(Lq)[:, None] + 3).expand(B, -1, -1).clone()
     elif kind == "allmasked_row":
         mask = torch.ones(B, 1, Lk, dtype=torch.bool)
         mask[1] = False                                   # every key masked: uniform softmax, dQ = dK = 0, dV != 0
