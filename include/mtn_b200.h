@@ -267,6 +267,7 @@ typedef struct MtnGemmArgs {
   float mask_scale;                   /* multiplies what passes relu_mask (0 = 1) */
   const void *drop_seed; uint32_t drop_site, drop_thresh; int drop_after_add;   /* see MtnLinearArgs */
   float *colsum_a;                    /* weight-gradient form only: colsum_a[m] += alpha * sum_k A(m, k) */
+  int multimem;                       /* accumulate form: out_f32 / colsum_a are NVLS multicast addresses (see below) */
 } MtnGemmArgs;
 int mtn_gemm_f16(const MtnGemmArgs *args, void *stream);
 int mtn_check_gemm_f16(const MtnGemmArgs *args, void *stream);   /* tests only */
@@ -301,6 +302,11 @@ typedef struct MtnLinearWgradArgs {
   long long stride_dY, stride_X, stride_dW;
   float *dbias;                        /* optional f32 [N] += alpha * column sums of dY (the bias gradient), computed
                                         * by one extra MMA against a tile of ones inside the same kernel          */
+  /* Data-parallel training on an NVSwitch box: pass dW / dbias as addresses inside the NVLS MULTICAST mapping of
+   * the (symmetric) gradient buffer and set multimem = 1 -- the epilogue then issues multimem.red.add instead of
+   * red.add, the switch adds the tile into EVERY rank's gradient buffer, and the gradient all-reduce disappears as
+   * a separate step (one cross-GPU barrier before the optimizer replaces it).                                    */
+  int multimem;
 } MtnLinearWgradArgs;
 int mtn_linear_wgrad(const MtnLinearWgradArgs *args, void *stream);
 
@@ -311,7 +317,7 @@ int mtn_linear_wgrad(const MtnLinearWgradArgs *args, void *stream);
 int mtn_cast_colsum(const void *src, int src_is_f16, int ld_src, void *dst_f16, int ld_dst,
                     const void *relu_mask, int ld_mask, int rows, int cols, const float *scale,
                     const float *alpha, float *colsum, const void *drop_seed, uint32_t drop_site,
-                    uint32_t drop_thresh, void *stream);
+                    uint32_t drop_thresh, int multimem /* colsum is an NVLS multicast address */, void *stream);
 /* (drop_*: the values are additionally thinned by the dropout of the linear layer's output they are the
  * gradient of -- see MtnLinearArgs; element index = r * cols + c.)                                        */
 
@@ -350,6 +356,7 @@ typedef struct MtnLayerNormBwdArgs {
    * GEMM operand) and dx_colsum[c] += param_alpha * sum_rows dx[:, c] (its output-bias gradient)            */
   void *dx_f16; float *dx_colsum;
   const void *drop_seed; uint32_t drop_site, drop_thresh;   /* dropout applied to dx_f16 / dx_colsum only */
+  int multimem;                         /* da_2 / db_2 / dx_colsum are NVLS multicast addresses (see MtnLinearWgradArgs) */
 } MtnLayerNormBwdArgs;
 int mtn_layernorm_bwd(const MtnLayerNormBwdArgs *args, void *stream);
 

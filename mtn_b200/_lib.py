@@ -46,7 +46,7 @@ class GemmArgs(C.Structure):
                 ("stride_bias", C.c_longlong), ("stride_add", C.c_longlong), ("stride_out_f32", C.c_longlong),
                 ("stride_out_f16", C.c_longlong), ("mask_scale", C.c_float),
                 ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32),
-                ("drop_after_add", C.c_int), ("colsum_a", C.c_void_p)]
+                ("drop_after_add", C.c_int), ("colsum_a", C.c_void_p), ("multimem", C.c_int)]
 
 
 class LinearDgradArgs(C.Structure):
@@ -64,7 +64,7 @@ class LinearWgradArgs(C.Structure):
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("alpha", C.c_void_p),
                 ("dW", C.c_void_p), ("lddw", C.c_int),
                 ("batch", C.c_int), ("stride_dY", C.c_longlong), ("stride_X", C.c_longlong),
-                ("stride_dW", C.c_longlong), ("dbias", C.c_void_p)]
+                ("stride_dW", C.c_longlong), ("dbias", C.c_void_p), ("multimem", C.c_int)]
 
 
 class LayerNormBwdArgs(C.Structure):
@@ -72,7 +72,7 @@ class LayerNormBwdArgs(C.Structure):
                 ("dy", C.c_void_p), ("dy_scale", C.c_void_p), ("dres", C.c_void_p), ("dx", C.c_void_p),
                 ("da_2", C.c_void_p), ("db_2", C.c_void_p), ("param_alpha", C.c_void_p),
                 ("dx_f16", C.c_void_p), ("dx_colsum", C.c_void_p),
-                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32)]
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32), ("multimem", C.c_int)]
 
 
 class EmbedBwdArgs(C.Structure):
@@ -160,7 +160,7 @@ SYMBOLS = {
     "mtn_linear_wgrad": (C.c_int, [C.POINTER(LinearWgradArgs), C.c_void_p]),
     "mtn_cast_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
-                                  C.c_void_p]),
+                                  C.c_int, C.c_void_p]),
     "mtn_embed_dropout_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                         C.c_uint32, C.c_void_p]),
@@ -599,7 +599,7 @@ def linear_dgrad(dY, W, alpha=None, relu_mask=None, addend=None, out_f32=None, o
             keep=(dY, W, alpha, relu_mask, addend, out_f32, out_f16))
 
 
-def linear_wgrad(dY, X, dW, alpha=None, dbias=None):
+def linear_wgrad(dY, X, dW, alpha=None, dbias=None, mc=0):
     """dW += alpha * dY^T X (and dbias += alpha * column sums of dY).  dY: [M, N] f16, X: [M, K] f16, dW: [N, K] f32
     (row stride honoured), dbias: [N] f32 contiguous."""
     _req(dbias, torch.float32, "dbias")
@@ -610,15 +610,17 @@ def linear_wgrad(dY, X, dW, alpha=None, dbias=None):
     a.dY, a.lddy, a.X, a.ldx = dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0)
     a.M, a.N, a.K = dY.shape[0], dY.shape[1], X.shape[1]
     a.alpha = alpha.data_ptr() if alpha is not None else None
-    a.dW, a.lddw = dW.data_ptr(), dW.stride(0)
+    # mc: byte offset from the gradient buffer's local mapping to its NVLS multicast mapping (0: local accumulation)
+    a.dW, a.lddw = dW.data_ptr() + mc, dW.stride(0)
+    a.multimem = 1 if mc else 0
     if dbias is not None:
         assert dbias.is_contiguous() and dbias.numel() == a.N
-        a.dbias = dbias.data_ptr()
+        a.dbias = dbias.data_ptr() + mc
     _launch("linear_wgrad", 2 * a.M * a.N * a.K, 2 * a.M * (a.N + a.K) + 8 * a.N * a.K,
             lambda: lib().mtn_linear_wgrad(C.byref(a), stream_ptr()), keep=(dY, X, dW, alpha, dbias))
 
 
-def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mask=None, drop=None):
+def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mask=None, drop=None, mc=0):
     """dst_f16 = f16(src * scale [masked]); colsum += alpha * column sums.  src: 2-D f32 or f16."""
     assert src.dim() == 2 and src.is_cuda and src.dtype in (torch.float32, torch.float16) and src.stride(1) == 1
     _req(dst_f16, torch.float16, "dst_f16"); _req(colsum, torch.float32, "colsum"); _req(scale, torch.float32, "scale")
@@ -631,8 +633,10 @@ def cast_colsum(src, dst_f16=None, colsum=None, scale=None, alpha=None, relu_mas
             lambda: lib().mtn_cast_colsum(ptr(src), 1 if src.dtype == torch.float16 else 0, src.stride(0), ptr(dst_f16),
                                           dst_f16.stride(0) if dst_f16 is not None else 0, ptr(relu_mask),
                                           relu_mask.stride(0) if relu_mask is not None else 0, rows, cols, ptr(scale),
-                                          ptr(alpha), ptr(colsum), ptr(drop[0]) if drop else None,
-                                          drop[1] if drop else 0, drop[2] if drop else 0, stream_ptr()),
+                                          ptr(alpha), C.c_void_p(colsum.data_ptr() + mc) if colsum is not None else None,
+                                          ptr(drop[0]) if drop else None,
+                                          drop[1] if drop else 0, drop[2] if drop else 0, 1 if (mc and colsum is not None) else 0,
+                                          stream_ptr()),
             keep=(src, dst_f16, colsum, scale, alpha, relu_mask, drop))
 
 
@@ -675,7 +679,7 @@ def scale_f32(x, alpha, y, accumulate=False):
 
 
 def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale=None, param_alpha=None, dx_f16=None,
-                  dx_colsum=None, drop=None):
+                  dx_colsum=None, drop=None, mc=0):
     """dx = dres + dLN(dy * dy_scale); da_2 / db_2 += param_alpha * (...).  x, dy, dx: [rows, d] f32 contiguous."""
     for t, n in ((x, "x"), (a_2, "a_2"), (dy, "dy"), (dx, "dx"), (dres, "dres"), (da_2, "da_2"), (db_2, "db_2"),
                  (dy_scale, "dy_scale"), (param_alpha, "param_alpha")):
@@ -690,8 +694,9 @@ def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale
     a.dy_scale = dy_scale.data_ptr() if dy_scale is not None else None
     a.dres = dres.data_ptr() if dres is not None else None
     a.dx = dx.data_ptr()
-    a.da_2 = da_2.data_ptr() if da_2 is not None else None
-    a.db_2 = db_2.data_ptr() if db_2 is not None else None
+    a.da_2 = da_2.data_ptr() + mc if da_2 is not None else None
+    a.db_2 = db_2.data_ptr() + mc if db_2 is not None else None
+    a.multimem = 1 if mc else 0
     a.param_alpha = param_alpha.data_ptr() if param_alpha is not None else None
     _req(dx_f16, torch.float16, "dx_f16"); _req(dx_colsum, torch.float32, "dx_colsum")
     if dx_f16 is not None:
@@ -699,7 +704,7 @@ def layernorm_bwd(x, a_2, eps, dy, dx, dres=None, da_2=None, db_2=None, dy_scale
         a.dx_f16 = dx_f16.data_ptr()
     if dx_colsum is not None:
         assert dx_colsum.is_contiguous() and dx_colsum.numel() == d
-        a.dx_colsum = dx_colsum.data_ptr()
+        a.dx_colsum = dx_colsum.data_ptr() + mc
     _set_drop(a, drop)
     _launch("layernorm_bwd", 0, rows * d * (12 + (4 if dres is not None else 0) + (2 if dx_f16 is not None else 0)),
             lambda: lib().mtn_layernorm_bwd(C.byref(a), stream_ptr()),

@@ -44,6 +44,7 @@ struct LnBwdParams {
   float eps; int rows; int has_ln;
   __half* dx16;   // optional f16 copy of dx: the operand of the next backward GEMM
   float* colsum;  // optional: += param_alpha * sum_rows dx  (bias gradient of the layer whose output this is)
+  int multimem;   // da / db / colsum are NVLS multicast addresses (data-parallel gradient reduction in the switch)
   DropCfg drop;   // !EMBED: dropout of the sublayer output that dx16 / colsum flow into (mtn.py:127), applied to
                   // them only.  EMBED: dropout of the embedding (mtn.py:309), applied before the scatter.
 };
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += red[w * D + col];
-      atomicAdd(dst + col, t * pal);
+      grad_red_f32(dst + col, t * pal, p.multimem);
     }
   }
 }
@@ -225,8 +226,8 @@ __global__ void layernorm_bwd_generic_kernel(const LnBwdParams p, int d) {
     if (p.dres) o += p.dres[(size_t)row * d + i];
     p.dx[(size_t)row * d + i] = o;
     if (p.da) {
-      atomicAdd(p.da + i, dyv * c * inv * pal);
-      atomicAdd(p.db + i, dyv * pal);
+      grad_red_f32(p.da + i, dyv * c * inv * pal, p.multimem);
+      grad_red_f32(p.db + i, dyv * pal, p.multimem);
     }
   }
 }
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(256)
     cast_colsum_kernel(const TIn* __restrict__ src, int ld_src, __half* __restrict__ dst, int ld_dst,
                        const __half* __restrict__ relu_mask, int ld_mask, int rows, int vcols, int rows_per_block,
                        const float* __restrict__ scale, const float* __restrict__ alpha, float* __restrict__ colsum,
-                       const DropCfg drop) {
+                       const DropCfg drop, int multimem) {
   pdl_launch_dependents();
   pdl_wait();
   const unsigned long long dseed = drop.seed ? __ldg(drop.seed) : 0ull;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256)
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x][j];
-        atomicAdd(colsum + 8 * vc + j, t * al);
+        grad_red_f32(colsum + 8 * vc + j, t * al, multimem);
       }
     }
   }
@@ -558,7 +559,7 @@ extern "C" int mtn_layernorm_bwd(const MtnLayerNormBwdArgs* a, void* stream) {
   LnBwdParams p = {};
   p.x = a->x; p.a2 = a->a_2; p.dy = a->dy; p.dy_scale = a->dy_scale; p.param_alpha = a->param_alpha;
   p.dres = a->dres; p.dx = a->dx; p.da = a->da_2; p.db = a->db_2; p.eps = a->eps; p.rows = a->rows; p.has_ln = 1;
-  p.dx16 = reinterpret_cast<__half*>(a->dx_f16); p.colsum = a->dx_colsum;
+  p.dx16 = reinterpret_cast<__half*>(a->dx_f16); p.colsum = a->dx_colsum; p.multimem = a->multimem;
   MTN_REQUIRE(a->drop_thresh < 65536u, MTN_E_ARG, "layernorm_bwd: drop_thresh=%u", a->drop_thresh);
   p.drop = DropCfg{reinterpret_cast<const unsigned long long*>(a->drop_seed), a->drop_site, a->drop_thresh,
                    a->drop_seed ? 1.f / (1.f - a->drop_thresh / 65536.f) : 1.f};
@@ -622,7 +623,7 @@ extern "C" int mtn_embed_bwd(const MtnEmbedBwdArgs* a, void* stream) {
 extern "C" int mtn_cast_colsum(const void* src, int src_is_f16, int ld_src, void* dst_f16, int ld_dst,
                                const void* relu_mask, int ld_mask, int rows, int cols, const float* scale,
                                const float* alpha, float* colsum, const void* drop_seed, uint32_t drop_site,
-                               uint32_t drop_thresh, void* stream) {
+                               uint32_t drop_thresh, int multimem, void* stream) {
   using namespace mtn;
   MTN_REQUIRE(drop_thresh < 65536u, MTN_E_ARG, "cast_colsum: drop_thresh=%u", drop_thresh);
   const DropCfg drop{reinterpret_cast<const unsigned long long*>(drop_seed), drop_site, drop_thresh,
@@ -646,10 +647,10 @@ extern "C" int mtn_cast_colsum(const void* src, int src_is_f16, int ld_src, void
   const __half* mk = reinterpret_cast<const __half*>(relu_mask);
   if (src_is_f16)
     MTN_CHECK_CUDA(launch_kernel(cast_colsum_kernel<__half>, grid, block, 0, st, reinterpret_cast<const __half*>(src), ld_src,
-                                 d16, ld_dst, mk, ld_mask, rows, vcols, rpb, scale, alpha, colsum, drop));
+                                 d16, ld_dst, mk, ld_mask, rows, vcols, rpb, scale, alpha, colsum, drop, multimem));
   else
     MTN_CHECK_CUDA(launch_kernel(cast_colsum_kernel<float>, grid, block, 0, st, reinterpret_cast<const float*>(src), ld_src,
-                                 d16, ld_dst, mk, ld_mask, rows, vcols, rpb, scale, alpha, colsum, drop));
+                                 d16, ld_dst, mk, ld_mask, rows, vcols, rpb, scale, alpha, colsum, drop, multimem));
   return MTN_OK;
 }
 

@@ -244,6 +244,25 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
 
 
 // ---------------------------------------------------------------------------
+// gradient accumulation: local L2 reduction, or -- data-parallel training on an NVSwitch box -- a reduction on the
+// NVLS MULTICAST address of the gradient buffer: the switch adds the value into EVERY rank's copy, so the gradient
+// all-reduce happens inside the weight-gradient epilogues instead of as a separate collective.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void grad_red_v4(float* p, float a, float b, float c, float d, int multimem) {
+  if (multimem)
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+  else
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void grad_red_f32(float* p, float v, int multimem) {
+  if (multimem)
+    asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+  else
+    atomicAdd(p, v);
+}
+
+// ---------------------------------------------------------------------------
 // dropout: counter-based RNG (Philox-4x32-10), regenerated -- never stored -- by the backward kernels.
 // One Philox call yields 8 x 16 random bits = the keep decisions of 8 CONSECUTIVE elements of a site's
 // logical [rows, cols] output: element e = row * cols + col, counter = (e >> 3, site), key = seed.

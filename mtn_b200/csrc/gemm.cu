@@ -40,6 +40,7 @@ struct GemmEpi {
   int ld_mask;
   int accumulate;          // out32 += result (red.global.add), required for split-K
   int out16_pre_add;       // out16 receives the value BEFORE the addend (video encoder: relu(.) without PE)
+  int multimem;            // accumulate mode: out32 / colsum_a are NVLS multicast addresses (multimem.red)
   float* colsum_a;         // BIAS kernels: colsum_a[m] += alpha * sum_k A(m, k)  (the bias gradient of a wgrad GEMM)
   float mask_scale;        // multiplies the elements that pass relu_mask (1/(1-p) of the dropout after the ReLU); 0 = 1
   DropCfg drop;            // dropout of the result (element index = row * N + col)
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tc_ld32(tmem_base + BIAS_COL + ((uint32_t)(q * 32) << 16), rb);
         tc_wait_ld();
         const int r = m0 + q * 32 + lane;
-        if (r < M) atomicAdd(epi.colsum_a + r, __uint_as_float(rb[0]) * alpha);
+        if (r < M) grad_red_f32(epi.colsum_a + r, __uint_as_float(rb[0]) * alpha, epi.multimem);
       }
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
@@ -449,12 +450,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (row_ok[i] && col_ok) {
             if (red_add) {
               float* o = epi.out32 + off32[i] + col;
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x0.x), "f"(x0.y), "f"(x0.z),
-                           "f"(x0.w)
-                           : "memory");
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(x1.x), "f"(x1.y),
-                           "f"(x1.z), "f"(x1.w)
-                           : "memory");
+              const int mm = epi.accumulate ? epi.multimem : 0;
+              grad_red_v4(o, x0.x, x0.y, x0.z, x0.w, mm);
+              grad_red_v4(o + 4, x1.x, x1.y, x1.z, x1.w, mm);
             } else if (epi.out32 != nullptr) {
               float4* o = reinterpret_cast<float4*>(epi.out32 + off32[i] + col);
               o[0] = x0;
@@ -532,7 +530,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   if (rc) return rc;
   GemmEpi epi{a.bias, a.act, a.addend, a.ld_add, a.add_period, a.out_f32, a.ld32,
               reinterpret_cast<__half*>(a.out_f16), a.ld16, a.alpha, reinterpret_cast<const __half*>(a.relu_mask),
-              a.ld_mask, a.accumulate, a.out16_pre_add, a.colsum_a, a.mask_scale,
+              a.ld_mask, a.accumulate, a.out16_pre_add, a.multimem, a.colsum_a, a.mask_scale,
               DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
                       a.drop_thresh ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
               a.drop_after_add, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
@@ -589,6 +587,7 @@ static int validate_gemm(const MtnGemmArgs* a) {
   if (a->drop_seed != nullptr)
     MTN_REQUIRE(a->drop_thresh < 65536u && a->batch <= 1 && !a->accumulate && !a->a_mn && !a->b_mn, MTN_E_ARG,
                 "gemm: dropout needs thresh < 65536, the forward (K-major) form, no batch, no accumulate");
+  MTN_REQUIRE(!a->multimem || a->accumulate, MTN_E_ARG, "gemm: multimem belongs to the accumulating form");
   if (a->colsum_a != nullptr)
     MTN_REQUIRE(a->a_mn && a->b_mn && a->accumulate && a->M % 8 == 0, MTN_E_ARG,
                 "gemm: colsum_a (bias gradient) belongs to the accumulating weight-gradient form");
@@ -645,7 +644,7 @@ static int run_gemm(const MtnGemmArgs* a, void* stream) {
         if (!big && a->batch <= 1) return launch_gemm<128, 6, 1, 1, 1, 0, 1>(*a, st);   // bias gradient on the tensor core
         // wide tiles have no TMEM columns to spare: the row sums of A take a separate pass over it
         rc = mtn_cast_colsum(a->A, 1, a->lda, nullptr, 0, nullptr, 0, a->K, a->M, nullptr, a->alpha, a->colsum_a, nullptr, 0, 0,
-                             stream);
+                             a->multimem, stream);
         if (rc) return rc;
       }
       return big ? launch_gemm<256, 4, 1, 1, 1>(*a, st) : launch_gemm<128, 6, 1, 1, 1>(*a, st);
@@ -714,7 +713,7 @@ static int run_check_gemm(const MtnGemmArgs* a, void* stream) {
   if (rc) return rc;
   GemmEpi epi{a->bias, a->act, a->addend, a->ld_add, a->add_period, a->out_f32, a->ld32,
               reinterpret_cast<__half*>(a->out_f16), a->ld16, a->alpha, reinterpret_cast<const __half*>(a->relu_mask),
-              a->ld_mask, a->accumulate, a->out16_pre_add, a->colsum_a, a->mask_scale,
+              a->ld_mask, a->accumulate, a->out16_pre_add, 0, a->colsum_a, a->mask_scale,
               DropCfg{reinterpret_cast<const unsigned long long*>(a->drop_seed), a->drop_site, a->drop_thresh,
                       a->drop_thresh ? 1.f / (1.f - a->drop_thresh / 65536.f) : 1.f},
               a->drop_after_add, 0, 0, 0, 0};
@@ -772,6 +771,7 @@ extern "C" int mtn_linear_wgrad(const MtnLinearWgradArgs* a, void* stream) {
   g.alpha = a->alpha;
   g.accumulate = 1;
   g.colsum_a = a->dbias;
+  g.multimem = a->multimem;
   g.out_f32 = a->dW; g.ld32 = a->lddw;
   g.batch = a->batch; g.stride_A = a->stride_dY; g.stride_B = a->stride_X; g.stride_out_f32 = a->stride_dW;
   return mtn::run_gemm(&g, stream);

@@ -57,6 +57,7 @@ class DecoderTrainer(object):
         self._packed = PackedWeights()
         self._arena = None          # flat f32 parameter arena + f16 operand arena (same layout)
         self._grad = None           # optional persistent gradient arena (same layout) backing every .grad
+        self._mc = 0                # byte offset local -> NVLS multicast mapping of that arena (0: local accumulation)
 
     # ------------------------------------------------------------------ streams
     def _streams(self, M, dev):
@@ -152,9 +153,13 @@ class DecoderTrainer(object):
             return ar["W"]
         return self._packed.get(self.param_list(), build)
 
-    def attach_grads(self, buf):
+    def attach_grads(self, buf, multicast_offset=0):
         """Back every decoder parameter's ``.grad`` by a view of `buf` (f32, arena_numel() elements, arena layout):
-        the backward then accumulates straight into it -- no per-parameter autograd accumulation kernels."""
+        the backward then accumulates straight into it -- no per-parameter autograd accumulation kernels.
+        multicast_offset: `buf` is symmetric memory with an NVLS multicast mapping at data_ptr() + multicast_offset:
+        every gradient reduction of the backward then goes to the multicast address (multimem.red), i.e. into the
+        gradient buffers of ALL ranks -- the data-parallel all-reduce fused into the weight-gradient epilogues."""
+        self._mc = int(multicast_offset)
         G, per = self._carve(buf)
         for p in self.param_list():
             p.grad = per[id(p)]
@@ -430,13 +435,13 @@ class DecoderTrainer(object):
     # `wq` collects the weight-gradient GEMMs of a site as closures: nothing downstream reads them, so `_flush`
     # launches them on the dedicated wgrad stream once the site's operands are complete.
     @staticmethod
-    def _ln_bwd(t, dy, dres, dx, gab, invS, dy_scale=None, nxt=None):
+    def _ln_bwd(t, dy, dres, dx, gab, invS, dy_scale=None, nxt=None, mc=0):
         """nxt = (dx16, bias_grad) of the sublayer processed next: the LayerNorm kernel also emits the f16 copy of
         the updated residual gradient (that sublayer's GEMM operand) and its column sums (its output-bias gradient)."""
         ln = t["ln"]
         _lib.layernorm_bwd(t["x_in"], ln[0], ln[2], dy, dx, dres=dres, da_2=gab[0], db_2=gab[1], dy_scale=dy_scale,
                            param_alpha=invS, dx_f16=None if nxt is None else nxt[0],
-                           dx_colsum=None if nxt is None else nxt[1], drop=None if nxt is None else nxt[2])
+                           dx_colsum=None if nxt is None else nxt[1], drop=None if nxt is None else nxt[2], mc=mc)
 
     def _flush(self, bk, wq):
         """Launch the collected weight-gradient GEMMs on the wgrad stream, after everything issued so far on the
@@ -456,7 +461,7 @@ class DecoderTrainer(object):
         """dx: [rows, d] f32 scaled residual-stream gradient at the site's OUTPUT; updated in place to the
         gradient at its input.  dkv: (dk view, dv view) f16 destination for cross sites (hoisted columns).
         dx16: f16 copy of dx if the previous LayerNorm backward already produced it (and the b_o gradient)."""
-        G, invS, wq = bk["G"], bk["invS"], []
+        G, invS, wq, mc = bk["G"], bk["invS"], [], bk["mc"]
         A = t["A"]
         B, Lq, Lk, h, dk_ = t["B"], t["Lq"], t["Lk"], A["h"], A["d_k"]
         rows, d = dx.shape
@@ -467,10 +472,10 @@ class DecoderTrainer(object):
         # ---- output projection (mtn.py:267) + residual (mtn.py:127)
         if dx16 is None:
             dx16 = torch.empty(rows, d, dtype=f16, device=dev)
-            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS, drop=t["drop_o"])
+            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "bo")], alpha=invS, drop=t["drop_o"], mc=mc)
         do16 = torch.empty(rows, d, dtype=f16, device=dev)
         _lib.linear_dgrad(dx16, A["w_o"], out_f16=do16)
-        wq.append(lambda: _lib.linear_wgrad(dx16, t["o16"], G[(gk, l, "wo")], alpha=invS))
+        wq.append(lambda: _lib.linear_wgrad(dx16, t["o16"], G[(gk, l, "wo")], alpha=invS, mc=mc))
         # ---- attention core
         delta = torch.empty(B, h, Lq, dtype=torch.float32, device=dev)
         _lib.attn_delta(do16, t["o16"], B, Lq, h, dk_, delta)
@@ -492,20 +497,20 @@ class DecoderTrainer(object):
             if not one_tile:
                 _lib.cast_colsum(dq32, dst_f16=dq16)
             _lib.linear_dgrad(dqkv, A["w_qkv"], out_f32=dxn)
-            wq.append(lambda: _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS, dbias=G[(gk, l, "bqkv")]))
+            wq.append(lambda: _lib.linear_wgrad(dqkv, t["xn16"], G[(gk, l, "wqkv")], alpha=invS, dbias=G[(gk, l, "bqkv")], mc=mc))
         else:
             wq_key, bq_key = ("wq", "bq") if (gk, l, "wq") in G else ("wqkv", "bqkv")
             gw, gb = G[(gk, l, wq_key)], G[(gk, l, bq_key)]
             if not one_tile:
                 _lib.cast_colsum(dq32, dst_f16=dq16)
             _lib.linear_dgrad(dq16, A["w_qkv"][:d], out_f32=dxn)
-            wq.append(lambda: _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS, dbias=gb[:d]))
+            wq.append(lambda: _lib.linear_wgrad(dq16, t["xn16"], gw[:d], alpha=invS, dbias=gb[:d], mc=mc))
         self._flush(bk, wq)
-        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS, nxt=nxt)
+        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS, nxt=nxt, mc=mc)
         bk["keep"].append((dq32, delta, do16, dxn))
 
     def _ffn_bwd(self, bk, t, dx, dx16=None, nxt=None):
-        G, invS, wq = bk["G"], bk["invS"], []
+        G, invS, wq, mc = bk["G"], bk["invS"], [], bk["mc"]
         Fw = t["Fw"]
         rows, d = dx.shape
         dev = dx.device
@@ -514,24 +519,24 @@ class DecoderTrainer(object):
         gk = (key, i)
         if dx16 is None:
             dx16 = torch.empty(rows, d, dtype=f16, device=dev)
-            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS, drop=t["drop_o"])
+            _lib.cast_colsum(dx, dst_f16=dx16, colsum=G[(gk, l, "b2")], alpha=invS, drop=t["drop_o"], mc=mc)
         dhid = torch.empty(rows, Fw["w_1"].shape[0], dtype=f16, device=dev)
         # through the ReLU and the hidden dropout (mtn.py:280): the saved hidden activation is > 0 exactly where the
         # unit was active AND kept; kept gradients are scaled by 1/(1-p)
         ms = 1.0 / (1.0 - t["drop_h"][2] / 65536.0) if t["drop_h"] is not None else 0.0
         _lib.linear_dgrad(dx16, Fw["w_2"], relu_mask=t["hid"], out_f16=dhid, mask_scale=ms)
-        wq.append(lambda: _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS))
-        wq.append(lambda: _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS, dbias=G[(gk, l, "b1")]))
+        wq.append(lambda: _lib.linear_wgrad(dx16, t["hid"], G[(gk, l, "w2")], alpha=invS, mc=mc))
+        wq.append(lambda: _lib.linear_wgrad(dhid, t["xn16"], G[(gk, l, "w1")], alpha=invS, dbias=G[(gk, l, "b1")], mc=mc))
         self._flush(bk, wq)
         dxn = torch.empty(rows, d, dtype=torch.float32, device=dev)
         _lib.linear_dgrad(dhid, Fw["w_1"], out_f32=dxn)
-        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS, nxt=nxt)
+        self._ln_bwd(t, dxn, dx, dx, G[("ln", l, c)], invS, nxt=nxt, mc=mc)
         bk["keep"].append(dxn)
 
     def _mem_bwd(self, bk, dkv, mem16, w_kv, gw, gb):
         """Backward of a hoisted memory K/V projection: bias gradient, weight gradient, memory gradient."""
         invS = bk["invS"]
-        wq = [lambda: _lib.linear_wgrad(dkv, mem16, gw, alpha=invS, dbias=gb)]
+        wq = [lambda: _lib.linear_wgrad(dkv, mem16, gw, alpha=invS, dbias=gb, mc=bk["mc"])]
         self._flush(bk, wq)
         dmem = torch.empty(mem16.shape[0], mem16.shape[1], dtype=torch.float32, device=dkv.device)
         _lib.linear_dgrad(dkv, w_kv, alpha=invS, out_f32=dmem)
@@ -564,7 +569,7 @@ class DecoderTrainer(object):
         g_ae = [g.contiguous().float() for g in g_ae]
         S2 = _lib.grad_scale([g_out] + g_ae)
         S, invS = S2[0:1], S2[1:2]
-        bk = {"G": G, "invS": invS, "ws": ws, "keep": []}
+        bk = {"G": G, "invS": invS, "ws": ws, "keep": [], "mc": self._mc if direct else 0}
 
         # hoisted dK/dV destinations, one per memory: every layer fills its own columns
         rows_mem = {k: v.shape[0] for k, v in ctx["mem16"].items()}
@@ -591,7 +596,7 @@ class DecoderTrainer(object):
         seq = list(reversed(tape[:-1]))
         dx = torch.empty(B * T, d, dtype=torch.float32, device=dev)
         nxt = handoff(seq, -1, B * T)
-        self._ln_bwd(t, g_out.view(B * T, d), None, dx, G[("norm",)], invS, dy_scale=S, nxt=nxt)        # mtn.py:164
+        self._ln_bwd(t, g_out.view(B * T, d), None, dx, G[("norm",)], invS, dy_scale=S, nxt=nxt, mc=bk["mc"])   # mtn.py:164
         for k, (kind, t) in enumerate(seq):
             dx16, nxt = (nxt[0] if nxt is not None else None), handoff(seq, k, B * T)
             if kind == "ffn":
@@ -626,7 +631,7 @@ class DecoderTrainer(object):
                 not_ffn = lambda entry: entry[0] != "ffn"    # an FFN's input gradient gets the K/V term added first
                 dae = torch.empty(B * La, d, dtype=torch.float32, device=dev)
                 nxt = None
-                self._ln_bwd(t, g_ae[i].view(B * La, d), None, dae, G[("ae_norm", i)], invS, dy_scale=S)   # mtn.py:162-163
+                self._ln_bwd(t, g_ae[i].view(B * La, d), None, dae, G[("ae_norm", i)], invS, dy_scale=S, mc=bk["mc"])   # mtn.py:162-163
                 for k, (kind, t) in enumerate(seq):
                     dx16, nxt = (nxt[0] if nxt is not None else None), handoff(seq, k, B * La, not_ffn)
                     key, l, _, c = t["names"]
@@ -639,7 +644,8 @@ class DecoderTrainer(object):
                         buf, a16 = dkv_ae[i][l], ctx["ae16"][i][l]
                         gw, gb = G[(gk, l, "wqkv")][d:], G[(gk, l, "bqkv")][d:]
                         _lib.linear_dgrad(buf, A2["w_qkv"][d:], addend=dae, out_f32=dae)
-                        self._flush(bk, [lambda buf=buf, a16=a16, gw=gw, gb=gb: _lib.linear_wgrad(buf, a16, gw, alpha=invS, dbias=gb)])
+                        self._flush(bk, [lambda buf=buf, a16=a16, gw=gw, gb=gb: _lib.linear_wgrad(buf, a16, gw, alpha=invS, dbias=gb,
+                                                                                             mc=bk["mc"])])
                         self._ffn_bwd(bk, t, dae, None, nxt)
                     elif key == "ae_vid":
                         buf = dkv_vid[i]
