@@ -314,7 +314,12 @@ def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over
         res.update({"tokens_per_s": tokens / (ms * 1e-3), "ms_per_step": ms, "steps": args.train_steps,
                     "mode": "eager launches" if args.train_eager else "CUDA graph replay (one launch per step)",
                     "launches_per_step": n_launches, "launches_by_kernel": per, "params": n_params,
-                    "allreduce_bytes_per_step": ts.flat.numel() * 4 if world > 1 else 0,
+                    "allreduce_bytes_per_step": (0 if world == 1 else (ts.flat.numel() - ts.n_dec) * 4 if ts.nvls is not None
+                                                 else ts.flat.numel() * 4),
+                    "grad_reduction": ("none (1 GPU)" if world == 1 else
+                                       "NVLS multimem.red fused into the weight-gradient / LayerNorm / bias epilogues "
+                                       "(%d MB decoder segment) + NCCL all-reduce of the rest" % (ts.n_dec * 4 >> 20)
+                                       if ts.nvls is not None else "one NCCL all-reduce of the flat gradient buffer"),
                     "loss": float(loss), "model_tflops": 3 * flops_forward(args.batch, args.tgt_len) * world / (ms * 1e-3) / 1e12,
                     "normaliser_note": "loss normalised by the global token counts of rotation slot 0 (fixed in the "
                                        "captured graph); slots differ by < 1 %"})

@@ -36,12 +36,13 @@ struct AttnCfg {
   static constexpr int ROWB = DK * 2;  // bytes per smem row of Q/K/V == swizzle span
   static constexpr int Q_BYTES = ATT_QT * ROWB;
   static constexpr int KV_BYTES = ATT_KT * ROWB;
-  static constexpr int P_PANELS = (ATT_KT + 63) / 64;
-  static constexpr int P_BYTES = P_PANELS * ATT_QT * 128;  // [128 x 64] f16 panels, K-major, 128B swizzle
+  // P: [128 x 64-key] f16 panels, K-major, 128B swizzle; a 32-key remainder (KT = 96) is a [128 x 32] panel
+  // with 64-byte rows and the 64B swizzle
+  static constexpr int P_BYTES = (ATT_KT / 64) * ATT_QT * 128 + ((ATT_KT % 64) ? ATT_QT * 64 : 0);
   static constexpr int OFF_Q = 0;                       // two Q buffers (next work item's queries)
-  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;     // two K buffers (next tile's keys)
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
+  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;     // two K buffers (keys of the next two tiles)
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;    // two V buffers
+  static constexpr int OFF_P = (OFF_V + 2 * KV_BYTES + 1023) / 1024 * 1024;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   // At most TWO CTAs may share an SM (2 x 256 TMEM columns): the request is padded above a third of the
   // shared memory so a third CTA can never be co-resident and sit in tcgen05.alloc behind a persistent peer.
@@ -52,6 +53,7 @@ struct AttnCfg {
   static constexpr uint32_t TMEM_COLS = 256;  // S0: [0,KT)  S1: [KT,2KT)  O: [2KT, 2KT+DK)
   static constexpr uint32_t O_COL = 2 * ATT_KT;
   static_assert(2 * ATT_KT + DK <= 256, "TMEM budget");
+  static_assert(ATT_KT % 64 == 0 || ATT_KT % 64 == 32, "P panels");
   static_assert((KV_BYTES % 1024) == 0 || DK == 32, "K/V buffers must stay swizzle-atom aligned");
 };
 
@@ -71,7 +73,8 @@ struct AttnParams {
 
 enum {  // "+1": two barriers, one per buffer
   BAR_Q_FULL = 0 /* +1 */, BAR_Q_EMPTY = 2 /* +1 */, BAR_K_FULL = 4 /* +1 */, BAR_K_EMPTY = 6 /* +1 */,
-  BAR_V_FULL = 8, BAR_V_EMPTY, BAR_S_FULL = 10 /* +1 */, BAR_S_FREE = 12 /* +1 */, BAR_P_FULL = 14, BAR_PV_DONE,
+  BAR_V_FULL = 8 /* +1 */, BAR_V_EMPTY = 10 /* +1 */, BAR_S_FULL = 12 /* +1 */, BAR_S_FREE = 14 /* +1 */, BAR_P_FULL = 16,
+  BAR_PV_DONE,
   BAR_COUNT
 };
 
@@ -84,7 +87,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int DK, int ATT_KT, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
     attn_core_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                        const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                        const AttnParams p) {
   using C = AttnCfg<DK, ATT_KT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
     for (int i = 0; i < BAR_COUNT; ++i)
       mbar_init(bar(i), (i == BAR_S_FREE || i == BAR_S_FREE + 1 || i == BAR_P_FULL) ? 128u : 1u);
     mbar_fence_init();
@@ -122,23 +127,42 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 
   if (warp == 0) {
     // -------------------------------------------------------------- TMA producer
+    // Loads are issued in the order their buffers come free (Q K^T runs a tile ahead of P V):
+    // K(0); then K(g+1), V(g) for every tile g -- the keys of a tile are requested two softmax periods
+    // before its Q K^T, the values two periods before its P V, across work-item boundaries.
     if (lane == 0) {
-      uint32_t n = 0, g = 0;
-      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++n) {
-        const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
-        const uint32_t qb = n & 1;
-        mbar_wait(bar(BAR_Q_EMPTY + qb), ((n >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(bar(BAR_Q_FULL + qb), C::Q_BYTES);
-        tma_load_3d(sQ + qb * C::Q_BYTES, &tmQ, bar(BAR_Q_FULL + qb), hd * DK, qt * ATT_QT, b);
-        for (int j = 0; j < nt; ++j, ++g) {
-          const uint32_t ph = g & 1, kb = g & 1, kph = (g >> 1) & 1;
-          mbar_wait(bar(BAR_K_EMPTY + kb), kph ^ 1);
-          mbar_arrive_expect_tx(bar(BAR_K_FULL + kb), C::KV_BYTES);
-          tma_load_3d(sK + kb * C::KV_BYTES, &tmK, bar(BAR_K_FULL + kb), hd * DK, j * ATT_KT, b);
-          mbar_wait(bar(BAR_V_EMPTY), ph ^ 1);
-          mbar_arrive_expect_tx(bar(BAR_V_FULL), C::KV_BYTES);
-          tma_load_3d(sV, &tmV, bar(BAR_V_FULL), hd * DK, j * ATT_KT, b);
+      const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t total = (uint32_t)my_items * (uint32_t)nt;
+      auto coords = [&](uint32_t n, int& qt, int& hd, int& b) {
+        const int it = blockIdx.x + (int)n * gridDim.x;
+        qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
+      };
+      auto load_k = [&](uint32_t g) {
+        const uint32_t n = g / nt, j = g % nt, kb = g & 1, kph = (g >> 1) & 1;
+        int qt, hd, b;
+        coords(n, qt, hd, b);
+        if (j == 0) {
+          const uint32_t qb = n & 1;
+          mbar_wait(bar(BAR_Q_EMPTY + qb), ((n >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar(BAR_Q_FULL + qb), C::Q_BYTES);
+          tma_load_3d(sQ + qb * C::Q_BYTES, &tmQ, bar(BAR_Q_FULL + qb), hd * DK, qt * ATT_QT, b);
         }
+        mbar_wait(bar(BAR_K_EMPTY + kb), kph ^ 1);
+        mbar_arrive_expect_tx(bar(BAR_K_FULL + kb), C::KV_BYTES);
+        tma_load_3d(sK + kb * C::KV_BYTES, &tmK, bar(BAR_K_FULL + kb), hd * DK, j * ATT_KT, b);
+      };
+      auto load_v = [&](uint32_t g) {
+        const uint32_t n = g / nt, j = g % nt, vb = g & 1, vph = (g >> 1) & 1;
+        int qt, hd, b;
+        coords(n, qt, hd, b);
+        mbar_wait(bar(BAR_V_EMPTY + vb), vph ^ 1);
+        mbar_arrive_expect_tx(bar(BAR_V_FULL + vb), C::KV_BYTES);
+        tma_load_3d(sV + vb * C::KV_BYTES, &tmV, bar(BAR_V_FULL + vb), hd * DK, j * ATT_KT, b);
+      };
+      if (total > 0) load_k(0);
+      for (uint32_t g = 0; g < total; ++g) {
+        if (g + 1 < total) load_k(g + 1);
+        load_v(g);
       }
     }
   } else if (warp == 1) {
@@ -171,19 +195,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     for (uint32_t g = 0; g < total; ++g) {
       if (g + 1 < total) issue_qk(g + 1);
       const uint32_t ph = g & 1, j = g % nt;
-      mbar_wait(bar(BAR_V_FULL), ph);
+      mbar_wait(bar(BAR_V_FULL + ph), (g >> 1) & 1);
       mbar_wait(bar(BAR_P_FULL), ph);  // P_g is in shared memory, O has been rescaled
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
         for (int kk = 0; kk < ATT_KT / 16; ++kk) {
-          // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row
-          const uint64_t dp = make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
+          // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row; the 32-key
+          // remainder panel of KT = 96 has 64-B rows (64B swizzle, 512-B atoms)
+          const bool rem = (ATT_KT % 64) != 0 && kk >= (ATT_KT / 64) * 4;
+          const uint64_t dp = rem ? make_smem_desc(sP + (ATT_KT / 64) * (ATT_QT * 128) + (kk & 3) * 32, 16, 512, SWZ_64B)
+                                  : make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
           // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
-          const uint64_t dv = make_smem_desc(sV + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
+          const uint64_t dv = make_smem_desc(sV + ph * C::KV_BYTES + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
           tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
         }
-        tc_commit(bar(BAR_V_EMPTY));
+        tc_commit(bar(BAR_V_EMPTY + ph));
         tc_commit(bar(BAR_PV_DONE));
       }
       __syncwarp();
@@ -204,14 +231,30 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     uint32_t g = 0;
     const unsigned long long dseed = (DROP && p.drop.seed != nullptr) ? __ldg(p.drop.seed) : 0ull;
 
+    // The mask words of a tile are requested one tile ahead (the first tile of the next work item during the
+    // last tile of the current one): their latency would otherwise sit at the head of every tile.
+    auto mask_row = [&](int it) -> const uint32_t* {
+      if (p.mask_bits == nullptr || it >= p.n_items) return nullptr;
+      const int qt = it % p.nqt, b = it / (p.nqt * p.h);
+      const int mq = (p.mask_rows_q == 1) ? 0 : min(qt * ATT_QT + row, p.Lq - 1);
+      return p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
+    };
+    uint32_t mw_pref[NCH];
+    auto fetch_mask = [&](const uint32_t* mr, int jn) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int k0 = jn * ATT_KT + c * 32;
+        mw_pref[c] = (mr != nullptr && k0 < p.Lk) ? __ldg(mr + (k0 >> 5)) : 0xffffffffu;
+      }
+    };
+    const uint32_t* mrow = mask_row(blockIdx.x);
+    fetch_mask(mrow, 0);
+    bool staged = false;  // this warp's TMA store of the previous item's output rows may still be reading the P buffer
+
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
       const int qi = qt * ATT_QT + row;
-      const uint32_t* mrow = nullptr;
-      if (p.mask_bits != nullptr) {
-        const int mq = (p.mask_rows_q == 1) ? 0 : min(qi, p.Lq - 1);
-        mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
-      }
+      const uint32_t* mrow_next = mask_row(it + gridDim.x);
       float m_run = -CUDART_INF_F, l_run = 0.f;
       if (qt * ATT_QT + q4 * 32 >= p.Lq) {
         // every query row of this warp is padding (Lq <= 64 sites use half of the 128-row tile): skip the
@@ -225,130 +268,220 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           mbar_arrive(bar(BAR_P_FULL));
         }
         mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
+        mrow = mrow_next;
+        fetch_mask(mrow, 0);
         continue;
       }
 
       for (int j = 0; j < nt; ++j, ++g) {
         const uint32_t ph = g & 1;
         const uint32_t tS = tmem_base + ph * ATT_KT;  // S buffer of this tile
+        // A tile is "plain" when every key of it is inside the sequence and kept for every row of the warp (the
+        // common case): select-free straight-line code on a register-resident score row.  Everything else
+        // (ragged end of the sequence, padding tail, causal diagonal) takes the general chunk loop.
+        uint32_t mwv[NCH];
+        bool plain = (j + 1) * ATT_KT <= p.Lk;
+        {
+          uint32_t w = 0xffffffffu;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            mwv[c] = mw_pref[c];
+            w &= mwv[c];
+          }
+          if (mrow != nullptr) plain = plain && __all_sync(0xffffffffu, w == 0xffffffffu);
+        }
+        if (j + 1 < nt) fetch_mask(mrow, j + 1);
+        else fetch_mask(mrow_next, 0);
         mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
         tc_fence_after();
-        // ---- pass 1: row maximum of the masked, scaled scores
-        float m_tile = -CUDART_INF_F;
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          const int k0 = j * ATT_KT + c * 32;
-          const int nvalid = p.Lk - k0;  // keys of this chunk inside the sequence (warp-uniform)
-          if (nvalid <= 0) break;
-          const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-          const uint32_t mw = (mrow != nullptr) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
-          // chunk with no kept key for ANY row of the warp (padding tail of a key-padding mask):
-          // every in-range score is the constant -1e9, nothing to read from TMEM
-          if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
-            m_tile = fmaxf(m_tile, t_masked);
-            continue;
-          }
-          uint32_t r[32];
-          tc_ld32(tS + lane_off + c * 32, r);
-          tc_wait_ld();
-          if ((mw & inb) == 0xffffffffu) {
-            float mx[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
+        auto store_chunk = [&](int c, const uint32_t(&e)[32]) {  // f16 P chunk -> swizzled K-major panel
+          const bool rem = (ATT_KT % 64) != 0 && c == NCH - 1;     // 32-key remainder panel: 64-B rows
+          const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * (rem ? 64 : 128);
 #pragma unroll
-            for (int i = 4; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));  // 4 independent chains
-            m_tile = fmaxf(m_tile, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
-          } else {
+          for (int t = 0; t < 4; ++t) {
+            // 128B swizzle: 16-B chunk ^= row % 8;  64B swizzle: 16-B chunk ^= (row / 2) % 4
+            const uint32_t chunk = rem ? ((uint32_t)t ^ ((uint32_t)(row >> 1) & 3u)) : ((uint32_t)((c & 1) * 4 + t) ^ sw);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + chunk * 16),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t]), __uint_as_float(e[8 * t + 1]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 2]), __uint_as_float(e[8 * t + 3]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 4]), __uint_as_float(e[8 * t + 5]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 6]), __uint_as_float(e[8 * t + 7])))
+                         : "memory");
+          }
+        };
+        auto store_chunk_dyn = [&](int c, const uint32_t(&e)[32]) {  // same, chunk index known at run time
+          const bool rem = (ATT_KT % 64) != 0 && c == NCH - 1;
+          const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * (rem ? 64 : 128);
+          const uint32_t x = rem ? ((uint32_t)(row >> 1) & 3u) : sw, c4 = rem ? 0u : (uint32_t)(c & 1) * 4u;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + ((c4 + t) ^ x) * 16),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t]), __uint_as_float(e[8 * t + 1]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 2]), __uint_as_float(e[8 * t + 3]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 4]), __uint_as_float(e[8 * t + 5]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 6]), __uint_as_float(e[8 * t + 7])))
+                         : "memory");
+          }
+        };
+        auto drop_chunk = [&](int c, uint32_t(&e)[32]) {
+          // dropout AFTER the softmax: the row sum keeps every key, only the P V operand is thinned
+          const int k0 = j * ATT_KT + c * 32;
+          const unsigned long long e0 =
+              ((((unsigned long long)b * p.h + hd) * p.Lq + min(qi, p.Lq - 1)) * p.Lk32 + k0) >> 3;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t kb = drop_keep8(p.drop, dseed, e0 + t);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              e[8 * t + u] = ((kb >> u) & 1u) ? __float_as_uint(__uint_as_float(e[8 * t + u]) * p.drop.inv_keep) : 0u;
+          }
+        };
+        // P buffer and O accumulator are in use by PV of the previous tile of this item until it retires; across
+        // items the P buffer stages the previous item's output tile until its TMA store has read it
+        auto wait_p_buffer = [&]() {
+          if (j > 0) {
+            mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
+            tc_fence_after();
+          } else if (staged) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+        };
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent partial row sums
+        float m_new;
+        bool rescale = false;
+        // lazy rescale: the running maximum only follows the tile maximum when some row of the warp grew by
+        // more than 2^8 (p <= 256 stays far inside f16 / f32 range and the common factor cancels in O / l);
+        // otherwise the O accumulator in tensor memory is left alone.
+        auto pick_max = [&](float m_tile) {
+          m_new = fmaxf(m_run, m_tile);
+          if (j > 0) {
+            rescale = __any_sync(0xffffffffu, m_new - m_run > 8.f);
+            if (!rescale) m_new = m_run;
+          }
+        };
+        if (plain) {
+          // ---- the whole score row of the tile goes to registers with ONE TMEM round trip (all chunk loads in
+          // flight, one wait) and the S buffer is released to Q K^T of tile g+2 right away
+          uint32_t r[NCH][32];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tc_ld32(tS + lane_off + c * 32, r[c]);
+          tc_wait_ld();
+          tc_fence_before();
+          mbar_arrive(bar(BAR_S_FREE + ph));
+          float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[c][i]));  // 4 independent chains
+          }
+          pick_max(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float t = __uint_as_float(r[i]) * c1;
-              t = ((mw >> i) & 1u) ? t : t_masked;
-              t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-              m_tile = fmaxf(m_tile, t);
+              const float e = ex2_approx(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
+              l4[i & 3] += e;
+              r[c][i] = __float_as_uint(e);
             }
+            if (DROP && p.drop.seed != nullptr) drop_chunk(c, r[c]);
           }
-        }
-        const float m_new = fmaxf(m_run, m_tile);
-        // P buffer and O accumulator are in use by PV of the previous tile of this item until it
-        // retires (across items the epilogue below has already waited for the last PV)
-        if (j > 0) {
-          mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
-          tc_fence_after();
-        }
-        // ---- pass 2: p = 2^(t - m), row sum, f16 P tile to shared memory
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent partial row sums
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          const int k0 = j * ATT_KT + c * 32;
-          const int nvalid = p.Lk - k0;
-          const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-          const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
-          float e[32];
-          if (nvalid > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
-            // all in-range keys masked for every row of the warp: p = 2^(-1e9 log2e - m) is one value
-            // per row (0 unless the whole row has been masked so far, then 1 -> uniform average)
-            const float pm = ex2_approx(t_masked - m_new);
+          wait_p_buffer();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) e[i] = ((inb >> i) & 1u) ? pm : 0.f;
-            l4[0] += pm * (float)__popc(inb);
-          } else if (nvalid > 0) {  // warp-uniform
+          for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
+        } else {
+          // ---- general tile: two passes over the S buffer, one 32-key chunk at a time.  Per chunk (warp-uniform):
+          // beyond the sequence -> zeros; no kept key for ANY row of the warp (padding tail of a key-padding mask)
+          // -> every in-range score is the constant -1e9, nothing to read from TMEM; otherwise per-key selects.
+          float m_tile = -CUDART_INF_F;
+          auto chunk_mask = [&](int c) { return c == 0 ? mwv[0] : (c == 1 ? mwv[1] : mwv[NCH - 1]); };
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int nvalid = p.Lk - (j * ATT_KT + c * 32);  // keys of this chunk inside the sequence (warp-uniform)
+            if (nvalid <= 0) break;
+            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+            const uint32_t mw = chunk_mask(c);
+            if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
+              m_tile = fmaxf(m_tile, t_masked);
+              continue;
+            }
             uint32_t r[32];
             tc_ld32(tS + lane_off + c * 32, r);
             tc_wait_ld();
-            if ((mw & inb) == 0xffffffffu) {
+            if (__all_sync(0xffffffffu, (mw & inb) == 0xffffffffu)) {  // every row keeps every key of the chunk
+              float mx[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c1, -m_new));
-                l4[i & 3] += e[i];
-              }
+              for (int i = 4; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+              m_tile = fmaxf(m_tile, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 float t = __uint_as_float(r[i]) * c1;
                 t = ((mw >> i) & 1u) ? t : t_masked;
                 t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-                e[i] = ex2_approx(t - m_new);
-                l4[i & 3] += e[i];
+                m_tile = fmaxf(m_tile, t);
               }
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) e[i] = 0.f;
           }
-          if (DROP && p.drop.seed != nullptr && nvalid > 0) {
-            // dropout AFTER the softmax: the row sum above keeps every key, only the P V operand is thinned
-            const unsigned long long e0 =
-                ((((unsigned long long)b * p.h + hd) * p.Lq + min(qi, p.Lq - 1)) * p.Lk32 + k0) >> 3;
+          pick_max(m_tile);
+          wait_p_buffer();
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int nvalid = p.Lk - (j * ATT_KT + c * 32);
+            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+            const uint32_t mw = chunk_mask(c);
+            uint32_t e[32];
+            if (nvalid > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
+              // p = 2^(-1e9 log2e - m) is one value per row (0 unless the whole row has been masked so far,
+              // then 1 -> uniform average)
+              const float pm = ex2_approx(t_masked - m_new);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const uint32_t kb = drop_keep8(p.drop, dseed, e0 + t);
+              for (int i = 0; i < 32; ++i) e[i] = ((inb >> i) & 1u) ? __float_as_uint(pm) : 0u;
+              l4[0] += pm * (float)__popc(inb);
+            } else if (nvalid > 0) {
+              tc_ld32(tS + lane_off + c * 32, e);
+              tc_wait_ld();
+              if (__all_sync(0xffffffffu, (mw & inb) == 0xffffffffu)) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) e[8 * t + u] = ((kb >> u) & 1u) ? e[8 * t + u] * p.drop.inv_keep : 0.f;
+                for (int i = 0; i < 32; ++i) {
+                  const float x = ex2_approx(fmaf(__uint_as_float(e[i]), c1, -m_new));
+                  l4[i & 3] += x;
+                  e[i] = __float_as_uint(x);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  float t = __uint_as_float(e[i]) * c1;
+                  t = ((mw >> i) & 1u) ? t : t_masked;
+                  t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+                  const float x = ex2_approx(t - m_new);
+                  l4[i & 3] += x;
+                  e[i] = __float_as_uint(x);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = 0u;
             }
+            if (DROP && p.drop.seed != nullptr && nvalid > 0) drop_chunk(c, e);
+            store_chunk_dyn(c, e);
           }
-          const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * 128;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t chunk = (uint32_t)((c & 1) * 4 + t) ^ sw;  // 128B swizzle: 16-B chunk ^= row % 8
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + chunk * 16),
-                         "r"(pack_f16x2_sat(e[8 * t], e[8 * t + 1])), "r"(pack_f16x2_sat(e[8 * t + 2], e[8 * t + 3])),
-                         "r"(pack_f16x2_sat(e[8 * t + 4], e[8 * t + 5])), "r"(pack_f16x2_sat(e[8 * t + 6], e[8 * t + 7]))
-                         : "memory");
-          }
+          tc_fence_before();
+          mbar_arrive(bar(BAR_S_FREE + ph));  // this S buffer may be overwritten by Q K^T of tile g+2
         }
-        tc_fence_before();
-        mbar_arrive(bar(BAR_S_FREE + ph));  // this S buffer may be overwritten by Q K^T of tile g+2
-        const float alpha = ex2_approx(m_run - m_new);
+        const float alpha = ex2_approx(m_run - m_new);  // 1 when the maximum was kept; 0 for j == 0 (l_run is 0)
         l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
-        if (j > 0) {
-          // rescale the running O accumulator in tensor memory
+        if (rescale) {
+          // rescale the running O accumulator in tensor memory (warp-uniform branch)
 #pragma unroll
           for (int c = 0; c < DK / 32; ++c) {
-            uint32_t r[32];
-            tc_ld32(tO + lane_off + c * 32, r);
+            uint32_t o[32];
+            tc_ld32(tO + lane_off + c * 32, o);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tc_st32(tO + lane_off + c * 32, r);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc_st32(tO + lane_off + c * 32, o);
           }
           tc_wait_st();
         }
@@ -356,7 +489,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         tc_fence_before();
         mbar_arrive(bar(BAR_P_FULL));
       }
-      // ---- epilogue: O / l  -> f16, head hd's column slice of the output
+      // ---- epilogue: O / l -> f16 -> this warp's 32 rows of the (now idle) P buffer in the TMA tile layout -> one
+      // TMA store per warp into head hd's column slice of the output (rows beyond Lq are clipped by the tensor
+      // map); no CTA-wide synchronisation
       mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.f / l_run;
@@ -366,17 +501,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         uint32_t r[32];
         tc_ld32(tO + lane_off + c * 32, r);
         tc_wait_ld();
-        if (qi < p.Lq) {
-          uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qi) * p.ldo + hd * DK + c * 32);
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            o[t] = make_uint4(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l),
-                              pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l),
-                              pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l),
-                              pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l));
+        for (int t = 0; t < 4; ++t) {
+          // 128B swizzle (d_k = 64): 16-B chunk ^= row % 8;  64B swizzle (d_k = 32): chunk ^= (row / 2) % 4
+          const uint32_t chunk = DK == 64 ? ((uint32_t)(c * 4 + t) ^ sw) : ((uint32_t)t ^ ((uint32_t)(row >> 1) & 3u));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + row * C::ROWB + chunk * 16),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l))
+                       : "memory");
         }
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmO, sP + q4 * 32 * C::ROWB, hd * DK, qt * ATT_QT + q4 * 32, b);
+        tma_store_commit();
+      }
+      staged = true;
+      mrow = mrow_next;
     }
+    if (lane == 0) tma_store_wait_read();  // (the kernel boundary completes the writes)
     tc_fence_before();
   }
   __syncthreads();
@@ -404,6 +550,9 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_3d_f16(&tv, a.v, cols, a.Lk, a.B, a.ldv, (uint64_t)a.Lk * a.ldv, DK, ATT_KT, swz);
   if (rc) return rc;
+  CUtensorMap to;
+  rc = make_tmap_3d_f16(&to, a.out, cols, a.Lq, a.B, a.ldo, (uint64_t)a.Lq * a.ldo, DK, 32, swz);
+  if (rc) return rc;
   const int nqt = (a.Lq + ATT_QT - 1) / ATT_QT;
   const int n_items = nqt * a.h * a.B;
   AttnParams p{n_items, nqt, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
@@ -419,7 +568,7 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
     slots = 2 * n;
   }
   dim3 grid(n_items < slots ? n_items : slots);
-  MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT, DROP>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, p));
+  MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT, DROP>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, to, p));
   return MTN_OK;
 }
 
