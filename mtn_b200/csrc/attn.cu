@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         // common case): select-free straight-line code on a register-resident score row.  Everything else
         // (ragged end of the sequence, padding tail, causal diagonal) takes the general chunk loop.
         uint32_t mwv[NCH];
-        bool plain = (j + 1) * ATT_KT <= p.Lk;
+        bool plain = !DROP && (j + 1) * ATT_KT <= p.Lk;  // (training-mode dropout: the chunk loop leaves registers for Philox)
         {
           uint32_t w = 0xffffffffu;
 #pragma unroll
@@ -384,11 +384,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
               l4[i & 3] += e;
               r[c][i] = __float_as_uint(e);
             }
-            if (DROP && p.drop.seed != nullptr) drop_chunk(c, r[c]);
           }
           wait_p_buffer();
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
+          for (int c = 0; c < NCH; ++c) {
+            if (DROP && p.drop.seed != nullptr) drop_chunk(c, r[c]);
+            store_chunk(c, r[c]);
+          }
         } else {
           // ---- general tile: two passes over the S buffer, one 32-key chunk at a time.  Per chunk (warp-uniform):
           // beyond the sequence -> zeros; no kept key for ANY row of the warp (padding tail of a key-padding mask)

@@ -187,6 +187,9 @@ ATT_CASES = [
     (2, 4, 8, 16, 32, "keypad"),
     (2, 4, 8, 8, 32, "causal"),
     (3, 4, 70, 200, 32, "keypad"),
+    (2, 2, 200, 400, 64, "holes"),
+    (2, 2, 300, 300, 64, "causal"),
+    (2, 2, 130, 513, 64, "holes"),
 ]
 
 
@@ -203,6 +206,12 @@ def test_attn_core(L, B, h, Lq, Lk, dk, kind):
         mask[B - 1, 0, Lk // 2:] = False
         if B > 1:
             mask[0, 0, :] = False                     # fully masked -> uniform average (mtn.py:227)
+    elif kind == "holes":
+        # random holes, a padding tail behind which key tiles are skipped, and one query row that keeps nothing
+        mask = torch.rand(B, Lq, Lk, generator=g) > 0.3
+        mask[:, :, Lk // 2 + 5:] = False
+        mask[B - 1, :, Lk // 4:] = False
+        mask[0, Lq // 2, :] = False
     elif kind == "causal":
         mask = O.subsequent_mask(Lq).expand(B, Lq, Lk).clone()
         mask[B - 1, :, Lk - 3:] = False
