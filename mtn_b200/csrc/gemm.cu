@@ -626,7 +626,7 @@ static int run_gemm(const MtnGemmArgs* a, void* stream) {
   static int big_pct = -1;  // 128x256 tiles once they fill this percentage of the SMs
   if (big_pct < 0) {
     const char* e = getenv("MTN_B200_BIG_PCT");
-    big_pct = e ? atoi(e) : 40;
+    big_pct = e ? atoi(e) : 45;
   }
   // split-K launches fill the machine through their slices; small outputs take 128x128 tiles (half the red.add
   // bytes per slice, twice the slices' length), large ones the wide tile
