@@ -236,6 +236,30 @@ def site_roofline(dev, peak_tf):
                     "DESIGN.md section 4"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU runs: pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE the
+    pinned staging buffers are allocated, so that they are first-touched on the GPU's own NUMA node -- with all ranks
+    uploading features every step, cross-socket traffic is what caps the end-to-end leg.  Best effort: returns the
+    number of CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = os.sched_getaffinity(0)
+        if not after or (len(after) < 4 and len(before) >= 4):     # never starve the rank
+            os.sched_setaffinity(0, before)
+            return None
+        return len(after)
+    except Exception:
+        return None
+
+
 def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over_ranks, sum_over_ranks):
     """Tokens/s of one TRAINING step on the same workload: forward (train.py:33), label-smoothed loss on the decoder
     and both auto-encoder streams normalised by the global token counts (train.py:37-39), backward through the
@@ -375,6 +399,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("MTN_B200_NO_NUMA_BIND") != "1" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from mtn_b200 import _lib, mtn
@@ -648,7 +673,8 @@ def main():
                              "residual stream; 4-6e-4 normwise vs the f32 reference (bar 1e-3)",
                 "data": "synthetic", "config": workload_config(args, B),
                 "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps, "f16_features": e2e16},
+                        "ms_per_step": ms_e2e / args.steps, "f16_features": e2e16,
+                        "host_threads_bound_to_gpu_numa_cpus": numa},
                 "gpu_launches": launches * args.steps, "launches_per_step": launches,
                 "roofline": roofline, "attn_site_roofline": site, "cpu_baseline": cpu, "clocks": clocks,
                 "tokens_per_step_per_gpu": sum(ntok) / len(ntok),
