@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MTN_B200_ABI_VERSION 3
+#define MTN_B200_ABI_VERSION 4   /* v4: `multimem` members (NVLS multicast gradient reductions) in the backward structs */
 
 enum {
   MTN_OK = 0,

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ACT_NONE, ACT_RELU = 0, 1
 
