@@ -19,15 +19,12 @@
 // own full/empty barriers so the next K tile streams in while softmax / PV run.
 #include <math_constants.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 #include "host.h"
 
 namespace mtn {
 
 constexpr int ATT_THREADS = 192;
-constexpr int ATT2_THREADS = 320;  // two-threads-per-row variant: 8 softmax warps
 constexpr int ATT_QT = 128;  // queries per CTA (UMMA M)
 
 // KT = keys per tile (UMMA N of the S MMA): 96, or 64 for short memories (Lk <= 64: caption / query /
@@ -49,7 +46,7 @@ struct AttnCfg {
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   // At most TWO CTAs may share an SM (2 x 256 TMEM columns): the request is padded above a third of the
   // shared memory so a third CTA can never be co-resident and sit in tcgen05.alloc behind a persistent peer.
-  static constexpr int NEEDED = OFF_BAR + 192 + 3072 + 1024;  // barriers, row max / sum exchange slots (split kernel), alignment slack
+  static constexpr int NEEDED = OFF_BAR + 192 + 1024;
   static constexpr int TOTAL = NEEDED > 78 * 1024 ? NEEDED : 78 * 1024;
   static constexpr uint64_t SWZ = (DK == 64) ? SWZ_128B : SWZ_64B;
   static constexpr uint32_t SBO = 8 * ROWB;  // 8-row swizzle atom
@@ -537,401 +534,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   }
 }
 
-// Same pipeline with TWO threads per query row (warps w and w + 4 share a TMEM lane quarter and split the key columns
-// of every tile): 8 softmax warps per CTA, i.e. 4 per scheduler with two CTAs per SM, so that one warp's TMEM / barrier /
-// shared-memory latencies are covered by the others' exponentials.  The pair exchanges its partial row maximum
-// through shared memory (one 64-thread named barrier per tile) and its partial row sums once per item.
-// Inference variant only (no dropout), d_k = 64.
-template <int DK, int ATT_KT>
-__global__ void __launch_bounds__(ATT2_THREADS, 2)
-    attn_core_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                        const AttnParams p) {
-  using C = AttnCfg<DK, ATT_KT>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t sQ = base + C::OFF_Q, sK = base + C::OFF_K, sV = base + C::OFF_V, sP = base + C::OFF_P;
-  const uint32_t bars = base + C::OFF_BAR;
-  auto bar = [&](int i) { return bars + 8u * i; };
-  const uint32_t tmem_slot = bars + 8u * BAR_COUNT;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_BAR + 8 * BAR_COUNT);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nt = (p.Lk + ATT_KT - 1) / ATT_KT;
-  // Persistent CTA: work items it = blockIdx.x, += gridDim.x.  All barrier phases run on global
-  // counters (item counter `n` for the Q buffers, tile counter `g` for everything else), so the
-  // producer streams the next item's Q / K / V while the current item is still in softmax / PV.
-
-  pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    tma_prefetch_desc(&tmO);
-    for (int i = 0; i < BAR_COUNT; ++i)
-      mbar_init(bar(i), (i == BAR_S_FREE || i == BAR_S_FREE + 1 || i == BAR_P_FULL) ? 256u : 1u);
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tO = tmem_base + C::O_COL;  // S buffers: tmem_base + (g & 1) * KT
-  pdl_wait();
-
-  if (warp == 0) {
-    // -------------------------------------------------------------- TMA producer
-    // Loads are issued in the order their buffers come free (Q K^T runs a tile ahead of P V):
-    // K(0); then K(g+1), V(g) for every tile g -- the keys of a tile are requested two softmax periods
-    // before its Q K^T, the values two periods before its P V, across work-item boundaries.
-    if (lane == 0) {
-      const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      const uint32_t total = (uint32_t)my_items * (uint32_t)nt;
-      auto coords = [&](uint32_t n, int& qt, int& hd, int& b) {
-        const int it = blockIdx.x + (int)n * gridDim.x;
-        qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
-      };
-      auto load_k = [&](uint32_t g) {
-        const uint32_t n = g / nt, j = g % nt, kb = g & 1, kph = (g >> 1) & 1;
-        int qt, hd, b;
-        coords(n, qt, hd, b);
-        if (j == 0) {
-          const uint32_t qb = n & 1;
-          mbar_wait(bar(BAR_Q_EMPTY + qb), ((n >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar(BAR_Q_FULL + qb), C::Q_BYTES);
-          tma_load_3d(sQ + qb * C::Q_BYTES, &tmQ, bar(BAR_Q_FULL + qb), hd * DK, qt * ATT_QT, b);
-        }
-        mbar_wait(bar(BAR_K_EMPTY + kb), kph ^ 1);
-        mbar_arrive_expect_tx(bar(BAR_K_FULL + kb), C::KV_BYTES);
-        tma_load_3d(sK + kb * C::KV_BYTES, &tmK, bar(BAR_K_FULL + kb), hd * DK, j * ATT_KT, b);
-      };
-      auto load_v = [&](uint32_t g) {
-        const uint32_t n = g / nt, j = g % nt, vb = g & 1, vph = (g >> 1) & 1;
-        int qt, hd, b;
-        coords(n, qt, hd, b);
-        mbar_wait(bar(BAR_V_EMPTY + vb), vph ^ 1);
-        mbar_arrive_expect_tx(bar(BAR_V_FULL + vb), C::KV_BYTES);
-        tma_load_3d(sV + vb * C::KV_BYTES, &tmV, bar(BAR_V_FULL + vb), hd * DK, j * ATT_KT, b);
-      };
-      if (total > 0) load_k(0);
-      for (uint32_t g = 0; g < total; ++g) {
-        if (g + 1 < total) load_k(g + 1);
-        load_v(g);
-      }
-    }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc_s = make_idesc_f16(ATT_QT, ATT_KT, 0, 0);  // S = Q K^T, both K-major
-    constexpr uint32_t idesc_o = make_idesc_f16(ATT_QT, DK, 0, 1);      // O += P V,  V is MN-major
-    const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t total = (uint32_t)my_items * (uint32_t)nt;  // tiles of this CTA, all items
-    // Q K^T runs ONE tile ahead of P V (it only needs the keys and a free S buffer), so the scores of
-    // tile g+1 -- possibly the first tile of the next work item -- are ready when the softmax warps
-    // finish tile g.
-    auto issue_qk = [&](uint32_t g) {
-      const uint32_t n = g / nt, j = g % nt, qb = n & 1, sb = g & 1, ph2 = (g >> 1) & 1;
-      if (j == 0) mbar_wait(bar(BAR_Q_FULL + qb), (n >> 1) & 1);
-      mbar_wait(bar(BAR_K_FULL + sb), ph2);
-      mbar_wait(bar(BAR_S_FREE + sb), ph2 ^ 1);  // softmax has finished reading this S buffer (tile g-2)
-      tc_fence_after();
-      if (lane == 0) {
-        const uint64_t dq = make_smem_desc(sQ + qb * C::Q_BYTES, 16, C::SBO, C::SWZ);
-        const uint64_t dk = make_smem_desc(sK + sb * C::KV_BYTES, 16, C::SBO, C::SWZ);
-#pragma unroll
-        for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tmem_base + sb * ATT_KT, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        tc_commit(bar(BAR_K_EMPTY + sb));
-        tc_commit(bar(BAR_S_FULL + sb));
-        if (j == (uint32_t)nt - 1) tc_commit(bar(BAR_Q_EMPTY + qb));  // last use of this item's queries
-      }
-      __syncwarp();
-    };
-    if (total > 0) issue_qk(0);
-    for (uint32_t g = 0; g < total; ++g) {
-      if (g + 1 < total) issue_qk(g + 1);
-      const uint32_t ph = g & 1, j = g % nt;
-      mbar_wait(bar(BAR_V_FULL + ph), (g >> 1) & 1);
-      mbar_wait(bar(BAR_P_FULL), ph);  // P_g is in shared memory, O has been rescaled
-      tc_fence_after();
-      if (lane == 0) {
-#pragma unroll
-        for (int kk = 0; kk < ATT_KT / 16; ++kk) {
-          // A: P panel kk/4 (64 keys per 128-B swizzled row), +32 B per 16 keys inside the row; the 32-key
-          // remainder panel of KT = 96 has 64-B rows (64B swizzle, 512-B atoms)
-          const bool rem = (ATT_KT % 64) != 0 && kk >= (ATT_KT / 64) * 4;
-          const uint64_t dp = rem ? make_smem_desc(sP + (ATT_KT / 64) * (ATT_QT * 128) + (kk & 3) * 32, 16, 512, SWZ_64B)
-                                  : make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
-          // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
-          const uint64_t dv = make_smem_desc(sV + ph * C::KV_BYTES + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
-          tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
-        }
-        tc_commit(bar(BAR_V_EMPTY + ph));
-        tc_commit(bar(BAR_PV_DONE));
-      }
-      __syncwarp();
-    }
-  } else {
-    // -------------------------------------------------------------- softmax + epilogue (two threads per row)
-    const int q4 = warp & 3, half = (warp - 2) >> 2;
-    const int row = q4 * 32 + lane;  // row inside the tile == TMEM lane
-    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-    constexpr float LOG2E = 1.4426950408889634f;
-    const float c1 = p.scale * LOG2E;
-    const float t_masked = -1e9f * LOG2E;
-    const uint32_t sw = (uint32_t)(row & 7);
-    constexpr int NW = ATT_KT / 32;   // mask words per tile
-    constexpr int CH = ATT_KT / 2;    // key columns per thread (48 / 32)
-    constexpr int NS = CH / 16;       // 16-column sub-chunks per thread
-    constexpr unsigned long long FULL = (CH == 48) ? 0xFFFFFFFFFFFFull : 0xFFFFFFFFull;
-    const uint32_t col0 = (uint32_t)half * CH;
-    const int bar_id = 1 + q4;        // named barrier of the pair (64 threads)
-    float* xch = reinterpret_cast<float*>(smem + C::OFF_BAR + 192);  // [3 slots][2 halves][128 rows]
-    auto xslot = [&](int slot, int h) { return xch + (slot * 2 + h) * 128 + row; };
-    uint32_t g = 0;
-
-    auto mask_row = [&](int it) -> const uint32_t* {
-      if (p.mask_bits == nullptr || it >= p.n_items) return nullptr;
-      const int qt = it % p.nqt, b = it / (p.nqt * p.h);
-      const int mq = (p.mask_rows_q == 1) ? 0 : min(qt * ATT_QT + row, p.Lq - 1);
-      return p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
-    };
-    uint32_t mw_pref[NW];
-    auto fetch_mask = [&](const uint32_t* mr, int jn) {
-#pragma unroll
-      for (int c = 0; c < NW; ++c) {
-        const int k0 = jn * ATT_KT + c * 32;
-        mw_pref[c] = (mr != nullptr && k0 < p.Lk) ? __ldg(mr + (k0 >> 5)) : 0xffffffffu;
-      }
-    };
-    const uint32_t* mrow = mask_row(blockIdx.x);
-    fetch_mask(mrow, 0);
-    bool staged = false;  // the pair's TMA store of the previous item's output rows may still be reading the P buffer
-
-    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
-      const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
-      const int qi = qt * ATT_QT + row;
-      const uint32_t* mrow_next = mask_row(it + gridDim.x);
-      float m_run = -CUDART_INF_F, l_run = 0.f;  // l_run: partial sum over this thread's columns
-      if (qt * ATT_QT + q4 * 32 >= p.Lq) {
-        // every query row of this pair of warps is padding: keep the barrier protocol alive
-        for (int j = 0; j < nt; ++j, ++g) {
-          const uint32_t ph = g & 1;
-          mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
-          if (j > 0) mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
-          mbar_arrive(bar(BAR_S_FREE + ph));
-          mbar_arrive(bar(BAR_P_FULL));
-        }
-        mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
-        mrow = mrow_next;
-        fetch_mask(mrow, 0);
-        continue;
-      }
-
-      for (int j = 0; j < nt; ++j, ++g) {
-        const uint32_t ph = g & 1;
-        const uint32_t tS = tmem_base + ph * ATT_KT + col0;  // this thread's columns of the tile's S buffer
-        // kept-key bits of this thread's CH columns
-        unsigned long long bits;
-        if (ATT_KT == 96) {
-          const unsigned long long lo = (unsigned long long)mw_pref[0] | ((unsigned long long)mw_pref[1] << 32);
-          bits = half == 0 ? (lo & FULL) : ((lo >> 48) | ((unsigned long long)mw_pref[NW - 1] << 16));
-        } else {
-          bits = half == 0 ? mw_pref[0] : mw_pref[NW - 1];
-        }
-        const int nvalid = p.Lk - (j * ATT_KT + (int)col0);  // this thread's columns inside the sequence (warp-uniform)
-        bool plain = nvalid >= CH;
-        if (mrow != nullptr) plain = plain && __all_sync(0xffffffffu, bits == FULL);
-        if (j + 1 < nt) fetch_mask(mrow, j + 1);
-        else fetch_mask(mrow_next, 0);
-        mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
-        tc_fence_after();
-        // 16 keys = two 16-byte chunks of the P row: chunk gc of the tile row; chunks 0..7 live in the 128-byte-row
-        // SW128 panel, 8..11 (KT = 96) in the 64-byte-row SW64 remainder panel
-        auto store_sub = [&](int s_, const uint32_t(&e)[16]) {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const uint32_t gc = (col0 >> 3) + 2u * (uint32_t)s_ + (uint32_t)t;
-            const uint32_t addr = gc < 8u ? sP + row * 128 + ((gc ^ sw) << 4)
-                                          : sP + (ATT_QT * 128) + row * 64 + (((gc - 8u) ^ ((uint32_t)(row >> 1) & 3u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t]), __uint_as_float(e[8 * t + 1]))),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 2]), __uint_as_float(e[8 * t + 3]))),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 4]), __uint_as_float(e[8 * t + 5]))),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 6]), __uint_as_float(e[8 * t + 7])))
-                         : "memory");
-          }
-        };
-        auto wait_p_buffer = [&]() {
-          if (j > 0) {
-            mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
-            tc_fence_after();
-          } else if (staged) {
-            if (half == 0 && lane == 0) tma_store_wait_read();
-            named_bar_sync(bar_id, 64);
-          }
-        };
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        float m_new;
-        bool rescale = false;
-        // the pair's row maximum: partial maxima through shared memory (slot = tile parity), then the lazy
-        // rescale rule of the one-thread-per-row kernel -- both threads see identical values and decide alike
-        auto pick_max = [&](float m_loc) {
-          *xslot((int)ph, half) = m_loc;
-          named_bar_sync(bar_id, 64);
-          const float m_tile = fmaxf(m_loc, *xslot((int)ph, half ^ 1));
-          m_new = fmaxf(m_run, m_tile);
-          if (j > 0) {
-            rescale = __any_sync(0xffffffffu, m_new - m_run > 8.f);
-            if (!rescale) m_new = m_run;
-          }
-        };
-        if (plain) {
-          uint32_t r[NS][16];
-#pragma unroll
-          for (int s_ = 0; s_ < NS; ++s_) tc_ld16(tS + lane_off + s_ * 16, r[s_]);
-          tc_wait_ld();
-          tc_fence_before();
-          mbar_arrive(bar(BAR_S_FREE + ph));
-          float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-#pragma unroll
-          for (int s_ = 0; s_ < NS; ++s_) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[s_][i]));
-          }
-          pick_max(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
-#pragma unroll
-          for (int s_ = 0; s_ < NS; ++s_) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float e = ex2_approx(fmaf(__uint_as_float(r[s_][i]), c1, -m_new));
-              l4[i & 3] += e;
-              r[s_][i] = __float_as_uint(e);
-            }
-          }
-          wait_p_buffer();
-#pragma unroll
-          for (int s_ = 0; s_ < NS; ++s_) store_sub(s_, r[s_]);
-        } else {
-          float m_loc = -CUDART_INF_F;
-#pragma unroll 1
-          for (int s_ = 0; s_ < NS; ++s_) {
-            const int nv = nvalid - s_ * 16;
-            if (nv <= 0) break;
-            const uint32_t inb = nv >= 16 ? 0xffffu : ((1u << nv) - 1u);
-            const uint32_t mw = (uint32_t)(bits >> (16 * s_)) & 0xffffu;
-            if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
-              m_loc = fmaxf(m_loc, t_masked);
-              continue;
-            }
-            uint32_t r[16];
-            tc_ld16(tS + lane_off + s_ * 16, r);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float t = __uint_as_float(r[i]) * c1;
-              t = ((mw >> i) & 1u) ? t : t_masked;
-              t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-              m_loc = fmaxf(m_loc, t);
-            }
-          }
-          pick_max(m_loc);
-          wait_p_buffer();
-#pragma unroll 1
-          for (int s_ = 0; s_ < NS; ++s_) {
-            const int nv = nvalid - s_ * 16;
-            const uint32_t inb = nv >= 16 ? 0xffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
-            const uint32_t mw = (uint32_t)(bits >> (16 * s_)) & 0xffffu;
-            uint32_t e[16];
-            if (nv > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
-              const float pm = ex2_approx(t_masked - m_new);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) e[i] = ((inb >> i) & 1u) ? __float_as_uint(pm) : 0u;
-              l4[0] += pm * (float)__popc(inb);
-            } else if (nv > 0) {
-              tc_ld16(tS + lane_off + s_ * 16, e);
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float t = __uint_as_float(e[i]) * c1;
-                t = ((mw >> i) & 1u) ? t : t_masked;
-                t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-                const float x = ex2_approx(t - m_new);
-                l4[i & 3] += x;
-                e[i] = __float_as_uint(x);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) e[i] = 0u;
-            }
-            store_sub(s_, e);
-          }
-          tc_fence_before();
-          mbar_arrive(bar(BAR_S_FREE + ph));
-        }
-        const float alpha = ex2_approx(m_run - m_new);  // 1 when the maximum was kept; 0 for j == 0 (l_run is 0)
-        l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
-        m_run = m_new;
-        if (rescale) {
-          // each thread of the pair rescales its half of the O columns (warp-uniform branch, same for both warps)
-          uint32_t o[32];
-          tc_ld32(tO + lane_off + half * 32, o);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tc_st32(tO + lane_off + half * 32, o);
-          tc_wait_st();
-        }
-        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
-        tc_fence_before();
-        mbar_arrive(bar(BAR_P_FULL));
-      }
-      // ---- epilogue: the pair adds its partial row sums; each thread scales and stages 32 of the 64 output columns
-      // of its row in the (now idle) P buffer; one TMA store per pair of warps
-      mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
-      tc_fence_after();
-      *xslot(2, half) = l_run;
-      named_bar_sync(bar_id, 64);
-      const float inv_l = 1.f / (l_run + *xslot(2, half ^ 1));
-      if (half == 0 && p.stats != nullptr && qi < p.Lq)
-        p.stats[((size_t)b * p.h + hd) * p.Lq + qi] = make_float2(m_run, inv_l);
-      {
-        uint32_t r[32];
-        tc_ld32(tO + lane_off + half * 32, r);
-        tc_wait_ld();
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t chunk = (uint32_t)(half * 4 + t) ^ sw;  // 128B swizzle: 16-B chunk ^= row % 8
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + row * 128 + chunk * 16),
-                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l)),
-                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l)),
-                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l)),
-                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l))
-                       : "memory");
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(bar_id, 64);
-      if (half == 0 && lane == 0) {
-        tma_store_3d(&tmO, sP + q4 * 32 * 128, hd * DK, qt * ATT_QT + q4 * 32, b);
-        tma_store_commit();
-      }
-      staged = true;
-      mrow = mrow_next;
-    }
-    if (half == 0 && lane == 0) tma_store_wait_read();  // (the kernel boundary completes the writes)
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-
 template <int DK, int ATT_KT, bool DROP>
 static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   using C = AttnCfg<DK, ATT_KT>;
@@ -965,52 +567,10 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
     int dev = 0, n = 0;
     MTN_CHECK_CUDA(cudaGetDevice(&dev));
     MTN_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    const char* e = getenv("MTN_B200_ATTN_CTAS_PER_SM");  // experiments: 1 = one persistent CTA per SM
-    slots = (e && atoi(e) == 1 ? 1 : 2) * n;
+    slots = 2 * n;
   }
   dim3 grid(n_items < slots ? n_items : slots);
   MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT, DROP>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, to, p));
-  return MTN_OK;
-}
-
-template <int DK, int ATT_KT>
-static int launch_attn_split(const MtnAttnCoreArgs& a, cudaStream_t st) {
-  using C = AttnCfg<DK, ATT_KT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_split_kernel<DK, ATT_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        C::TOTAL));
-    attr_set = true;
-  }
-  const TmSwizzle swz = DK == 64 ? TM_SWZ_128 : TM_SWZ_64;
-  const uint64_t cols = (uint64_t)a.h * DK;
-  CUtensorMap tq, tk, tv;
-  int rc = make_tmap_3d_f16(&tq, a.q, cols, a.Lq, a.B, a.ldq, (uint64_t)a.Lq * a.ldq, DK, ATT_QT, swz);
-  if (rc) return rc;
-  rc = make_tmap_3d_f16(&tk, a.k, cols, a.Lk, a.B, a.ldk, (uint64_t)a.Lk * a.ldk, DK, ATT_KT, swz);
-  if (rc) return rc;
-  rc = make_tmap_3d_f16(&tv, a.v, cols, a.Lk, a.B, a.ldv, (uint64_t)a.Lk * a.ldv, DK, ATT_KT, swz);
-  if (rc) return rc;
-  CUtensorMap to;
-  rc = make_tmap_3d_f16(&to, a.out, cols, a.Lq, a.B, a.ldo, (uint64_t)a.Lq * a.ldo, DK, 32, swz);
-  if (rc) return rc;
-  const int nqt = (a.Lq + ATT_QT - 1) / ATT_QT;
-  const int n_items = nqt * a.h * a.B;
-  AttnParams p{n_items, nqt, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk), a.B, a.h, a.Lq, a.Lk,
-               1.0f / sqrtf((float)DK), reinterpret_cast<__half*>(a.out), a.ldo, reinterpret_cast<float2*>(a.stats),
-               DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
-                       a.drop_seed ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
-               (a.Lk + 31) / 32 * 32};
-  static int slots = 0;  // resident CTAs: 2 per SM
-  if (slots == 0) {
-    int dev = 0, n = 0;
-    MTN_CHECK_CUDA(cudaGetDevice(&dev));
-    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    const char* e = getenv("MTN_B200_ATTN_CTAS_PER_SM");  // experiments: 1 = one persistent CTA per SM
-    slots = (e && atoi(e) == 1 ? 1 : 2) * n;
-  }
-  dim3 grid(n_items < slots ? n_items : slots);
-  MTN_CHECK_CUDA(launch_kernel(attn_core_split_kernel<DK, ATT_KT>, grid, dim3(ATT2_THREADS), C::TOTAL, st, tq, tk, tv, to, p));
   return MTN_OK;
 }
 
@@ -1083,13 +643,6 @@ extern "C" int mtn_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
     return a->d_k == 64 ? mtn::launch_attn<64, 96, true>(*a, st) : mtn::launch_attn<32, 96, true>(*a, st);
   }
   if (a->Lk <= 64) return a->d_k == 64 ? mtn::launch_attn<64, 64, false>(*a, st) : mtn::launch_attn<32, 64, false>(*a, st);
-  // long memories, d_k = 64: two threads per query row (8 softmax warps per CTA); MTN_B200_ATTN_SPLIT=0 disables
-  static int split = -1;
-  if (split < 0) {
-    const char* e = getenv("MTN_B200_ATTN_SPLIT");
-    split = e ? atoi(e) : 1;
-  }
-  if (split && a->d_k == 64) return mtn::launch_attn_split<64, 96>(*a, st);
   return a->d_k == 64 ? mtn::launch_attn<64, 96, false>(*a, st) : mtn::launch_attn<32, 96, false>(*a, st);
 }
 
