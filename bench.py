@@ -108,18 +108,18 @@ class ClockSampler(object):
 
 
 def traffic_from_profiles(n_launches, train=False):
-    """DRAM bytes per launch of the linear kernel from the committed ncu capture of the same step
+    """(DRAM bytes per launch of the linear kernel, provenance dict) from the committed ncu capture of the same step
     (profiles/rNN_gemm_traffic.json for the forward, rNN_train_gemm_traffic.json for the training step, written by
-    tools/summarize_profiles.py); None if absent."""
+    tools/summarize_profiles.py); (None, None) if absent."""
     import glob
     files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json"))
                    if ("_train_" in os.path.basename(f)) == train)
     if not files:
-        return None
+        return None, None
     t = json.load(open(files[-1]))
     per_launch = (t["dram_bytes_read"] + t["dram_bytes_write"]) / max(1, t["launches"])
-    return {"dram_bytes_per_launch_avg": per_launch, "launches_in_capture": t["launches"],
-            "launches_in_this_run": n_launches, "source": t["source"]}
+    return per_launch, {"launches_in_capture": t["launches"], "launches_in_this_run": n_launches,
+                        "source": t["source"], "unit": "bytes per launch (average over the capture)"}
 
 
 def synth(O, B, T, seed):
@@ -323,7 +323,8 @@ def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over
                            "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
                            "frac": gemm_fl / (gemm_ms * 1e-3) / 1e12 / pk, "launches": sum(kt[k]["launches"] for k in
                                                                                           ("linear", "linear_dgrad", "linear_wgrad") if k in kt)}
-        res["roofline"]["traffic"] = traffic_from_profiles(res["roofline"]["launches"], train=True)
+        res["roofline"]["traffic"], res["roofline"]["traffic_source"] = \
+            traffic_from_profiles(res["roofline"]["launches"], train=True)
         n_launches = len(rec)
         del rec
         for i in range(3):
@@ -572,7 +573,7 @@ def main():
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (f16 and bf16 share the tensor rate)"
                 if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
-                "traffic": traffic_from_profiles(lin["n"]),
+                "traffic": traffic_from_profiles(lin["n"])[0], "traffic_source": traffic_from_profiles(lin["n"])[1],
                 "flops_per_launch_avg": lin["flops"] / lin["n"], "us_per_launch_avg": lin["ms"] * 1e3 / lin["n"],
                 "note": "algorithmic 2MNK of the step's linear launches / CUDA-event time of those launches "
                         "replayed back to back in one CUDA graph"}

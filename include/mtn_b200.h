@@ -162,6 +162,19 @@ typedef struct MtnLinearArgs {
 } MtnLinearArgs;
 int mtn_linear_fwd(const MtnLinearArgs *args, void *stream);
 
+/* ---- LayerNorm fused into the projection that consumes it (inference) ----------------
+ * Replaces SublayerConnection's norm (mtn.py:126) TOGETHER with the first nn.Linear of the sublayer
+ * (mtn.py:256 Q projection or packed Q|K|V, mtn.py:280 w_1) in one launch:
+ *     out_f16[M, N] = act( LN(x)[M, d] W[N, d]^T + bias )
+ * x: [M, d] f32 contiguous rows; LN as mtn_layernorm_fwd (unbiased std, eps added to std), rounded to
+ * f16 exactly like its y_f16 output, so the result is bit-identical to mtn_layernorm_fwd +
+ * mtn_linear_fwd.  W: f16 [N, d] row-major (leading dimension ldw).  d in {128, 256, 512}
+ * (mtn_ln_linear_supported); other sizes take the two-call form.                                  */
+int mtn_ln_linear_supported(int d);
+int mtn_ln_linear_fwd(const float *x, const float *a_2, const float *b_2, float eps, int M, int d,
+                      const void *W, int ldw, const float *bias, int N, int act, void *out_f16,
+                      int ld16, void *stream);
+
 /* ---- attention core ------------------------------------------------------------
  * Replaces attention() (mtn.py:221-231) plus the head split / concat views around
  * it (mtn.py:257, 265-266) for all B*h heads in one launch:

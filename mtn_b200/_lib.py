@@ -146,6 +146,9 @@ SYMBOLS = {
     "mtn_mask_words": (C.c_int, [C.c_int]),
     "mtn_mask_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mtn_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "mtn_ln_linear_supported": (C.c_int, [C.c_int]),
+    "mtn_ln_linear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mtn_attn_core_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
     "mtn_attn_site_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "mtn_attn_site_fwd": (C.c_int, [C.POINTER(AttnSiteArgs), C.c_void_p]),
@@ -357,6 +360,27 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
                                                         (4 if addend is not None else 0))
     _launch("linear", 2 * a.M * a.N * a.K, nbytes, lambda: fn(C.byref(a), stream_ptr()),
             keep=(A, W, bias, addend, out_f32, out_f16, drop))
+
+
+def ln_linear_supported(d):
+    return bool(lib().mtn_ln_linear_supported(int(d)))
+
+
+def ln_linear(x, a_2, b_2, eps, W, bias=None, act=ACT_NONE, out_f16=None):
+    """out_f16 = act(LN(x) W^T + bias) in ONE launch (LayerNorm fused into the projection's operand staging).
+    x: [M, d] f32 contiguous, W: [N, d] f16 (row stride allowed), out_f16: [M, N] f16 (row stride allowed).
+    Bit-identical to layernorm(out_f16=...) + linear(out_f16=...)."""
+    _req(x, torch.float32, "x"); _req(a_2, torch.float32, "a_2"); _req(b_2, torch.float32, "b_2")
+    _req(W, torch.float16, "W"); _req(bias, torch.float32, "bias"); _req(out_f16, torch.float16, "out_f16")
+    assert x.dim() == 2 and x.is_contiguous() and W.dim() == 2 and W.shape[1] == x.shape[1]
+    M, d = x.shape
+    N = W.shape[0]
+    assert out_f16.dim() == 2 and tuple(out_f16.shape) == (M, N)
+    assert a_2.is_contiguous() and b_2.is_contiguous() and a_2.numel() >= d and b_2.numel() >= d
+    _launch("ln_linear", 2 * M * N * d, M * d * 4 + N * d * 2 + M * N * 2,
+            lambda: lib().mtn_ln_linear_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), M, d, ptr(W), W.stride(0), ptr(bias), N,
+                                            int(act), ptr(out_f16), out_f16.stride(0), stream_ptr()),
+            keep=(x, a_2, b_2, W, bias, out_f16))
 
 
 def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False, stats=None, drop=None):

@@ -18,6 +18,8 @@ self-attention, and LN -> Q GEMM -> core (hoisted K/V) -> out-proj(+residual) fo
 memory, then the fused FFN; the residual stream stays f32, every tensor-core operand
 is f16 (see DESIGN.md "Precision").
 """
+import os
+
 import torch
 
 from . import _lib
@@ -34,6 +36,29 @@ def ensure_inference(module, x):
         raise NotImplementedError(
             "mtn_b200: backward / training-mode dropout of the fused path is not implemented in "
             "this round; call model.eval() and run under torch.no_grad()")
+
+
+def _ln_fused_max_rows():
+    """Row-count threshold of the fused LayerNorm + projection kernel (csrc/ln_gemm.cu); MTN_B200_LN_FUSED=0
+    disables it, =N overrides the threshold.  Above the threshold the row blocks alone fill the machine and the
+    two-launch form (wide 128x256 tiles on all SMs) has the higher throughput; below it the chain is bound by
+    launch boundaries and one kernel beats two."""
+    e = os.environ.get("MTN_B200_LN_FUSED")
+    return LN_FUSED_MAX_ROWS if e is None else int(e)
+
+
+LN_FUSED_MAX_ROWS = 0
+
+
+def _ln_linear(x, ln, w, b, act, xn16, out16):
+    """out16 = act(LN(x) w^T + b): one fused launch when the shape qualifies, else LayerNorm -> xn16 -> linear
+    (bit-identical results either way, tests/test_gpu_ln_linear.py)."""
+    rows, d = x.shape
+    if rows <= _ln_fused_max_rows() and _lib.ln_linear_supported(d):
+        _lib.ln_linear(x, ln[0], ln[1], ln[2], w, bias=b, act=act, out_f16=out16)
+        return
+    _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
+    _lib.linear(xn16, w, b, act=act, out_f16=out16)
 
 
 class PackedWeights(object):
@@ -164,8 +189,7 @@ class DecoderEngine(object):
         """One pre-norm residual attention site, in place on the f32 stream ``x`` [B*Lq, d].
         kv=None -> self-attention (q_w is the [3d, d] pack, K/V come out of the same GEMM)."""
         d = x.shape[1]
-        _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
-        _lib.linear(xn16, q_w, q_b, out_f16=qbuf)
+        _ln_linear(x, ln, q_w, q_b, _lib.ACT_NONE, xn16, qbuf)
         if kv is None:
             q, k, v = qbuf[:, :d], qbuf[:, d:2 * d], qbuf[:, 2 * d:]
         else:
@@ -175,8 +199,7 @@ class DecoderEngine(object):
 
     @staticmethod
     def _ffn_block(x, ln, Fw, xn16, hid, out16=None):
-        _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
-        _lib.linear(xn16, Fw["w_1"], Fw["b_1"], act=_lib.ACT_RELU, out_f16=hid)
+        _ln_linear(x, ln, Fw["w_1"], Fw["b_1"], _lib.ACT_RELU, xn16, hid)
         _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x, out_f32=x, out_f16=out16)
 
     # ------------------------------------------------------------------ memory stage
