@@ -171,6 +171,8 @@ int mtn_linear_fwd(const MtnLinearArgs *args, void *stream);
  * mtn_linear_fwd.  W: f16 [N, d] row-major (leading dimension ldw).  d in {128, 256, 512}
  * (mtn_ln_linear_supported); other sizes take the two-call form.                                  */
 int mtn_ln_linear_supported(int d);
+/* tools only: later launches make CTA (0,0) write 8 clock64() phase stamps to dev_buf8 (NULL: off). */
+int mtn_ln_linear_debug_timestamps(void *dev_buf8);
 int mtn_ln_linear_fwd(const float *x, const float *a_2, const float *b_2, float eps, int M, int d,
                       const void *W, int ldw, const float *bias, int N, int act, void *out_f16,
                       int ld16, void *stream);

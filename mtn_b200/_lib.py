@@ -147,6 +147,7 @@ SYMBOLS = {
     "mtn_mask_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mtn_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "mtn_ln_linear_supported": (C.c_int, [C.c_int]),
+    "mtn_ln_linear_debug_timestamps": (C.c_int, [C.c_void_p]),
     "mtn_ln_linear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mtn_attn_core_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
     ln_gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x,
                           const float* __restrict__ a2, const float* __restrict__ b2, float eps,
                           const float* __restrict__ bias, int act, __half* __restrict__ out16, int ld16, int M, int N,
-                          int tiles_n) {
+                          int tiles_n, long long* __restrict__ ts) {
   using L = LnGemmSmem<VPL>;
   constexpr int D = L::D, NKB = L::NKB;
   extern __shared__ uint8_t smem_raw[];
@@ -77,6 +77,9 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
   const int first_tile = blockIdx.y, tile_stride = gridDim.y;
   constexpr uint32_t TMEM_COLS = 2u * LG_BN;
 
+  // phase timestamps of CTA (0, 0) for tools/ln_linear_bench.py --phases (ts == NULL in production)
+  const bool stamp = ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  if (stamp && warp == 0) ts[0] = clock64();
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
+  if (stamp && warp == 0) ts[1] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (W tiles)
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
     constexpr uint32_t idesc = make_idesc_f16(LG_BM, LG_BN, 0, 0);
     mbar_wait(bar_a_ready, 0);  // the normalised rows are in shared memory (generic writes fenced by the workers)
     tc_fence_after();
+    if (stamp) ts[3] = clock64();
     uint32_t it = 0, lt = 0;
     for (int t = first_tile; t < tiles_n; t += tile_stride, ++lt) {
       const uint32_t buf = lt & 1u;
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
           for (int k = 0; k < LG_BK / 16; ++k) tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           tc_commit(bar_empty(s));
           if (kb == NKB - 1) tc_commit(bar_acc_full(buf));
+          if (stamp && kb == NKB - 1 && lt == 0) ts[4] = clock64();
         }
         __syncwarp();
       }
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
+      if (stamp && ew == 0) ts[2] = clock64();
       if (lane == 0) mbar_arrive(bar_a_ready);
     }
     // ------------------------------------------------------------ workers: epilogue
@@ -235,6 +242,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
       }
       mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
       tc_fence_after();
+      if (stamp && ew == 0 && lt == 0) ts[5] = clock64();
       const uint32_t t_acc = tmem_base + buf * LG_BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
@@ -283,14 +291,18 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
           if (row_ok[i] && colh < N) *reinterpret_cast<uint4*>(out16 + off16[i] + colh) = hv[i];
       }
     }
+    if (stamp && ew == 0) ts[6] = clock64();
     tc_fence_before();
   }
   __syncthreads();
+  if (stamp && warp == 0) ts[7] = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
+
+static long long* g_ln_gemm_ts = nullptr;  // tools only: device buffer of 8 phase timestamps
 
 template <int VPL>
 static int launch_ln_gemm(const float* x, const float* a2, const float* b2, float eps, int M, const void* W, int ldw,
@@ -309,11 +321,16 @@ static int launch_ln_gemm(const float* x, const float* a2, const float* b2, floa
   if (nsplit < 1) nsplit = 1;
   if (nsplit > tiles_n) nsplit = tiles_n;
   MTN_CHECK_CUDA(launch_kernel(ln_gemm_f16_tc_kernel<VPL>, dim3(tiles_m, nsplit), dim3(LG_THREADS), L::TOTAL, st, tmW, x, a2,
-                               b2, eps, bias, act, reinterpret_cast<__half*>(out16), ld16, M, N, tiles_n));
+                               b2, eps, bias, act, reinterpret_cast<__half*>(out16), ld16, M, N, tiles_n, g_ln_gemm_ts));
   return MTN_OK;
 }
 
 }  // namespace mtn
+
+extern "C" int mtn_ln_linear_debug_timestamps(void* dev_buf8) {  // tools only; NULL switches the stamps off
+  mtn::g_ln_gemm_ts = static_cast<long long*>(dev_buf8);
+  return MTN_OK;
+}
 
 extern "C" int mtn_ln_linear_supported(int d) { return d == 128 || d == 256 || d == 512; }
 

@@ -34,15 +34,14 @@ def ensure_inference(module, x):
                                     (module is not None and module.training and
                                      any(p.requires_grad for p in module.parameters()))):
         raise NotImplementedError(
-            "mtn_b200: backward / training-mode dropout of the fused path is not implemented in "
-            "this round; call model.eval() and run under torch.no_grad()")
+            "mtn_b200: this entry point is the inference form (no autograd graph, no dropout); training goes "
+            "through train_engine.DecoderTrainer / trainer.TrainStep -- or call model.eval() under torch.no_grad()")
 
 
 def _ln_fused_max_rows():
-    """Row-count threshold of the fused LayerNorm + projection kernel (csrc/ln_gemm.cu); MTN_B200_LN_FUSED=0
-    disables it, =N overrides the threshold.  Above the threshold the row blocks alone fill the machine and the
-    two-launch form (wide 128x256 tiles on all SMs) has the higher throughput; below it the chain is bound by
-    launch boundaries and one kernel beats two."""
+    """Largest row count that takes the fused LayerNorm + projection kernel (csrc/ln_gemm.cu).  Default 0 = never:
+    measured 3.5-5 us slower per sublayer than the two launches at every shape of the decoder
+    (profiles/r01d_ln_linear.txt).  MTN_B200_LN_FUSED=<rows> opts in (results are the same either way)."""
     e = os.environ.get("MTN_B200_LN_FUSED")
     return LN_FUSED_MAX_ROWS if e is None else int(e)
 

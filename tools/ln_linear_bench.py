@@ -46,8 +46,35 @@ def timed(fn, reps):
     return best
 
 
+def phases(out):
+    """clock64() stamps of CTA (0, 0): where one launch spends its time (cycles of the SM clock)."""
+    import ctypes as C
+    ts = torch.zeros(8, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().mtn_ln_linear_debug_timestamps(C.c_void_p(ts.data_ptr())))
+    names = ["entry", "after griddepcontrol.wait", "LayerNorm done (worker warp 0)", "MMA warp passes a_ready",
+             "last MMA of n-tile 0 issued", "epilogue sees accumulator 0", "epilogue done (worker warp 0)", "exit"]
+    for M, N, d in ((8192, 512, 512), (64, 512, 512), (8192, 2048, 512), (2048, 512, 512)):
+        x = torch.randn(M, d, device="cuda")
+        a, b = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
+        W = (torch.randn(N, d, device="cuda") / d ** 0.5).half()
+        bias = torch.randn(N, device="cuda")
+        y = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        for _ in range(3):
+            _lib.ln_linear(x, a, b, 1e-6, W, bias=bias, out_f16=y)
+        torch.cuda.synchronize()
+        t = ts.cpu().tolist()
+        print("phases M=%d N=%d d=%d (cycles since entry):" % (M, N, d), file=out)
+        for n, v in zip(names, t):
+            print("   %-36s %8d" % (n, v - t[0]), file=out)
+    _lib.check(_lib.lib().mtn_ln_linear_debug_timestamps(None))
+
+
 def main():
     _lib.lib()
+    if len(sys.argv) > 2 and sys.argv[2] == "--phases":
+        with open(sys.argv[1], "w") as f:
+            phases(f)
+        return
     out = open(sys.argv[1], "w") if len(sys.argv) > 1 else sys.stdout
     reps = 20
     print("%-48s %6s %5s | %9s %9s %9s  (us per dependent round; back = the residual projection alone)" %
