@@ -134,7 +134,7 @@ def cpu_forward_seconds(O, sd, inp, reps):
         t0 = time.perf_counter()
         O.forward(sd, CFG, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["fts"])
         ts.append(time.perf_counter() - t0)
-    return statistics.median(ts)
+    return statistics.median(ts) if ts else None
 
 
 def run_reference(args, rank, world):
@@ -642,12 +642,16 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        sub = {k: (v[:args.cpu_batch].clone() if torch.is_tensor(v) else [f[:args.cpu_batch].clone() for f in v])
-               for k, v in host[0].items()}
-        sec = cpu_forward_seconds(O, sd, sub, reps=5)
+        # bounded sample: whole batch 0 (the same 32 dialogues the GPU step processes), repeated for ~10 s of CPU work
+        sub = {k: (v.clone() if torch.is_tensor(v) else [f.clone() for f in v]) for k, v in host[0].items()}
+        t0 = time.perf_counter()
+        cpu_forward_seconds(O, sd, sub, reps=0)                      # warm-up forward, also sizes the sample
+        t_one = time.perf_counter() - t0
+        reps = max(3, min(10, int(10.0 / max(t_one, 1e-3))))
+        sec = cpu_forward_seconds(O, sd, sub, reps=reps)
         cpu = {"value": int((sub["trg_y"] != 1).sum()) / sec, "unit": "tokens/s", "cores": torch.get_num_threads(),
-               "kind": "port", "sample": "oracle forward on the first %d dialogues of batch 0, median of 5 (%.2f s each)"
-               % (args.cpu_batch, sec)}
+               "kind": "port", "sample": "oracle forward on all %d dialogues of batch 0, median of %d (%.2f s each)"
+               % (sub["query"].shape[0], reps, sec)}
         # context only: the same port (stock PyTorch eager ops, f32, what the reference would run on a GPU) on
         # this B200, full batch -- the reference ships no GPU kernels of its own.
         try:
