@@ -380,6 +380,8 @@ def main():
     ap.add_argument("--train-steps", type=int, default=30)
     ap.add_argument("--train-eager", action="store_true", help="time the training step without CUDA-graph capture")
     ap.add_argument("--decode-batch", type=int, default=64)
+    ap.add_argument("--decode-in-flight", type=int, default=2,
+                    help="dialogue batches decoded concurrently (own stream + graphs each) in the decode leg's second measurement")
     ap.add_argument("--decode-len", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -459,6 +461,38 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     tokens = sum_over_ranks(sum(ntok[i % args.rot] for i in range(args.steps)))
     value = tokens / (ms * 1e-3)
+
+    # Context: the same K steps with TWO independent batches in flight (graphs of even / odd rotation slots on two
+    # streams).  The headline stays the one-batch-at-a-time number above; this shows how much of the step is
+    # dependent-launch latency that a second batch can hide.
+    in_flight = None
+    rot2 = args.rot - args.rot % 2
+    if rot2 >= 2:
+        try:
+            sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+
+            def conc(n):
+                for st in (sa, sb):
+                    st.wait_stream(cur)
+                for i in range(n):
+                    with torch.cuda.stream(sa if i % 2 == 0 else sb):
+                        graphs[i % rot2].replay()
+                for st in (sa, sb):
+                    cur.wait_stream(st)
+
+            conc(4)
+            barrier()
+            e0.record()
+            conc(args.steps)
+            e1.record()
+            barrier()
+            ms2 = max_over_ranks(e0.elapsed_time(e1))
+            tok2 = sum_over_ranks(sum(ntok[i % rot2] for i in range(args.steps)))
+            in_flight = {"batches_in_flight": 2, "value": tok2 / (ms2 * 1e-3), "unit": "tokens/s",
+                         "ms_per_step_amortised": ms2 / args.steps}
+        except Exception as e:
+            in_flight = {"error": repr(e)[:300]}
 
     # ------------------------------------------------------------- end to end (host buffers)
     # Public API with HOST inputs, every step: pinned-host -> device copy of ids + features, the
@@ -628,6 +662,61 @@ def main():
                   "generated_tokens_per_s": sum_over_ranks(Bd * (Ld - 1)) / (ms_dec * 1e-3), "ms_per_batch": ms_dec,
                   "includes": "H2D of ids+features (pipelined with the previous batch's decoding), encode, memory stage, "
                               "all steps, D2H of tokens"}
+        # Several dialogue batches in flight: a decoding step is a chain of small dependent kernels (<= 40 CTAs each on
+        # 148 SMs), so independent batches on their own streams fill the idle SMs -- same per-batch work, same tokens.
+        if args.decode_in_flight > 1:
+            try:
+                K = args.decode_in_flight
+                dev0 = {k: (v.to(dev) if torch.is_tensor(v) else [f.to(dev) for f in v]) for k, v in dh[0].items()}
+                decs = [dec] + [GraphedGreedyDecoder(model, dev0, Ld) for _ in range(K - 1)]
+                streams = [torch.cuda.Stream() for _ in range(K)]
+                outs = [torch.empty(Bd, Ld, dtype=torch.int64).pin_memory() for _ in range(K)]
+                main = torch.cuda.current_stream()
+
+                def one(i):          # dialogue batch i on decoder / stream i % K (its round i // K decodes dh[round % 2])
+                    j = i % K
+                    with torch.cuda.stream(streams[j]):
+                        t = decs[j].decode(staged=True)
+                        decs[j].upload(dh[(i // K + 1) % 2])
+                        outs[j].copy_(t, non_blocking=True)
+
+                for st_ in streams:
+                    st_.wait_stream(main)
+                for j in range(K):
+                    with torch.cuda.stream(streams[j]):
+                        decs[j].upload(dh[0])
+                for i in range(2 * K):
+                    one(i)
+                torch.cuda.synchronize()
+                # every decoder decoded dh[1] last, with the other batches in flight: compare with the same decoder
+                # decoding dh[1] ALONE (tools/concurrency_check.py does the same for the forward graphs)
+                same = True
+                for j in range(K):
+                    with torch.cuda.stream(streams[j]):
+                        decs[j].upload(dh[1])
+                        solo = decs[j].decode(staged=True).clone()
+                        decs[j].upload(dh[0])
+                    torch.cuda.synchronize()
+                    same = same and bool((solo.cpu() == outs[j]).all())
+                barrier()
+                e0.record()
+                for st_ in streams:
+                    st_.wait_stream(main)
+                nb = reps * K
+                for i in range(nb):
+                    one(i)
+                for st_ in streams:
+                    main.wait_stream(st_)
+                e1.record()
+                barrier()
+                ms_k = max_over_ranks(e0.elapsed_time(e1)) / nb
+                decode["in_flight"] = {"batches_in_flight": K, "generated_tokens_per_s": sum_over_ranks(Bd * (Ld - 1)) / (ms_k * 1e-3),
+                                       "ms_per_batch_amortised": ms_k, "tokens_equal_solo_decoding": same,
+                                       "note": "K independent dialogue batches of %d, each on its own stream with its own "
+                                               "CUDA graphs and staging buffers; H2D / D2H inside the timed region" % Bd}
+                del decs
+            except Exception as e:
+                decode["in_flight"] = {"error": repr(e)[:300]}
         del dec
 
     # ------------------------------------------------------------- training step (forward + loss + backward +
@@ -682,6 +771,7 @@ def main():
                         "host_threads_bound_to_gpu_numa_cpus": numa},
                 "gpu_launches": launches * args.steps, "launches_per_step": launches,
                 "roofline": roofline, "attn_site_roofline": site, "cpu_baseline": cpu, "clocks": clocks,
+                "two_batches_in_flight": in_flight,
                 "tokens_per_step_per_gpu": sum(ntok) / len(ntok),
                 "model_tflops": fl * world / (ms / args.steps * 1e-3) / 1e12, "gflop_per_step_per_gpu": fl / 1e9,
                 "kernel_breakdown_one_step": breakdown, "decode": decode, "train": train}

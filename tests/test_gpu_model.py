@@ -277,6 +277,31 @@ def test_cfg4_decode_graphs_token_exact(M, cfg2_model):
         model.generator.proj.weight.data.copy_(w0)
 
 
+@pytest.mark.xfail(strict=False, reason="OPEN (found at the end of round 1, profiles/r01d_concurrency.txt): at batch 64 two decoder "
+                                        "instances and the eager decoder disagree from position ~10 on (each one deterministic); "
+                                        "tools/concurrency_check.py / tools/stale_memory_check.py reproduce and localise it")
+def test_cfg4_decoder_instances_agree_at_batch_64(M, cfg2_model):
+    """BASELINE configs[3] at its full batch (64 dialogues, 20 tokens): two GraphedGreedyDecoder instances captured
+    from the same model must produce the same tokens on the same input, and the same as the eager decoder -- the
+    kernels are pure functions of their operands.  (The B=8 case above holds; at B=64 the step buffers cross the
+    caching allocator's 1 MB small/large-pool boundary at prefix length 9-10, which is where the runs part.)"""
+    mtn, du = M
+    from mtn_b200.graph import GraphedGreedyDecoder
+    cfg, model = cfg2_model
+    inp = O.synth_inputs(cfg, B=64, Q=64, C=64, H=256, T=4, Lv=[512, 256], seed=5001)
+    d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
+         if k in ("query", "his", "cap", "fts")}
+    d0, d1 = GraphedGreedyDecoder(model, d, 20), GraphedGreedyDecoder(model, d, 20)
+    t0, t1 = d0.decode().clone(), d1.decode().clone()
+    b = du.Batch(d["query"], d["his"], None, [f.permute(1, 0, 2) for f in d["fts"]], d["cap"], None, None, 1)
+    with torch.no_grad():
+        te = du.greedy_decode(model, b, 20, 2)
+    torch.cuda.synchronize()
+    n01, n0e = int((t0 != t1).any(1).sum()), int((t0 != te).any(1).sum())
+    print("decoder instances differ in %d of 64 sequences; instance 0 vs eager: %d" % (n01, n0e))
+    assert n01 == 0 and n0e == 0, (n01, n0e)
+
+
 def test_cfg5_family_d1024_h16(M):
     """BASELINE configs[4] architecture family (d_model=1024, h=16 -> d_k=64, d_ff=4096, video_len=1024) at
     N=1 and a small batch so the CPU oracle finishes in seconds."""
