@@ -370,7 +370,7 @@ def ln_linear_supported(d):
 def ln_linear(x, a_2, b_2, eps, W, bias=None, act=ACT_NONE, out_f16=None):
     """out_f16 = act(LN(x) W^T + bias) in ONE launch (LayerNorm fused into the projection's operand staging).
     x: [M, d] f32 contiguous, W: [N, d] f16 (row stride allowed), out_f16: [M, N] f16 (row stride allowed).
-    Bit-identical to layernorm(out_f16=...) + linear(out_f16=...)."""
+    Same result as layernorm(out_f16=...) + linear(out_f16=...) (bit-identical at d = 256 / 512)."""
     _req(x, torch.float32, "x"); _req(a_2, torch.float32, "a_2"); _req(b_2, torch.float32, "b_2")
     _req(W, torch.float16, "W"); _req(bias, torch.float32, "bias"); _req(out_f16, torch.float16, "out_f16")
     assert x.dim() == 2 and x.is_contiguous() and W.dim() == 2 and W.shape[1] == x.shape[1]

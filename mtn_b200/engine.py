@@ -51,7 +51,7 @@ LN_FUSED_MAX_ROWS = 0
 
 def _ln_linear(x, ln, w, b, act, xn16, out16):
     """out16 = act(LN(x) w^T + b): one fused launch when the shape qualifies, else LayerNorm -> xn16 -> linear
-    (bit-identical results either way, tests/test_gpu_ln_linear.py)."""
+    (same results either way, tests/test_gpu_ln_linear.py)."""
     rows, d = x.shape
     if rows <= _ln_fused_max_rows() and _lib.ln_linear_supported(d):
         _lib.ln_linear(x, ln[0], ln[1], ln[2], w, bias=b, act=act, out_f16=out16)
