@@ -239,6 +239,66 @@ def test_attn_core(L, B, h, Lq, Lk, dk, kind):
         assert G.rel_err(o[0], mean_v) < 2e-3
 
 
+ATT_MANY = [
+    # B, h, Lq, Lk, dk, mask kind -- more work items than resident CTAs (2 per SM = 296): every persistent CTA takes
+    # 2-4 items, with partially filled query tiles (the shapes of batched greedy decoding, BASELINE configs[3])
+    (64, 8, 12, 12, 64, "causal"),      # target self-attention at prefix length 12, batch 64: 512 items
+    (64, 8, 12, 256, 64, "keypad"),     # target -> history: 3 key tiles per item
+    (64, 8, 19, 64, 64, "keypad"),      # target -> caption / query
+    (128, 8, 64, 64, 64, "keypad"),     # QAE self-attention of both modalities at batch 64: 1024 items
+    (40, 8, 200, 300, 64, "holes"),     # 640 items, second query tile partially filled
+]
+
+
+@pytest.mark.xfail(strict=False, reason="added at the end of round 1 without a GPU run (profiles/r01d_concurrency.txt, DESIGN.md "
+                                        "section 7: open item); an XPASS clears the attention core of the batch-64 decode discrepancy")
+@pytest.mark.parametrize("B,h,Lq,Lk,dk,kind", ATT_MANY)
+def test_attn_core_many_items(L, B, h, Lq, Lk, dk, kind):
+    """Multi-item persistent CTAs with partial query tiles against the oracle arithmetic, PER batch element (items
+    beyond the first wave belong to the later batch elements), plus purity: the same operands at different
+    addresses, and a second run, give bit-identical outputs."""
+    g = torch.Generator().manual_seed(B * 1000 + Lq * 10 + Lk + dk)
+    d = h * dk
+    q = (torch.randn(B, Lq, d, generator=g) * 1.5).half()
+    k = (torch.randn(B, Lk, d, generator=g) * 1.5).half()
+    v = torch.randn(B, Lk, d, generator=g).half()
+    if kind == "keypad":
+        mask = torch.ones(B, 1, Lk, dtype=torch.bool)
+        lens = torch.randint(Lk // 2, Lk + 1, (B,), generator=g)
+        for b in range(B):
+            mask[b, 0, int(lens[b]):] = False
+    elif kind == "holes":
+        mask = torch.rand(B, Lq, Lk, generator=g) > 0.3
+        mask[:, :, Lk // 2 + 5:] = False
+    else:
+        mask = O.subsequent_mask(Lq).expand(B, Lq, Lk).clone()
+    ref = _attn_ref(q, k, v, mask, h, dk)
+    bits = L.mask_pack(dev(mask))
+
+    def run(pad_rows):
+        # a fresh set of buffers (different addresses: `pad_rows` shifts every allocation), packed [Q|K|V]-style
+        _shift = torch.empty(pad_rows * 1024 + 16, device="cuda", dtype=torch.float16)
+        qd = torch.zeros(B * Lq, d + 64, device="cuda", dtype=torch.float16); qd[:, :d] = dev(q).view(-1, d)
+        kvd = torch.zeros(B * Lk, 2 * d, device="cuda", dtype=torch.float16)
+        kvd[:, :d] = dev(k).view(-1, d); kvd[:, d:] = dev(v).view(-1, d)
+        out = torch.full((B * Lq, d), float("nan"), device="cuda", dtype=torch.float16)
+        L.attn_core(qd[:, :d], kvd[:, :d], kvd[:, d:], B, h, Lq, Lk, dk, out, mask_bits=bits)
+        torch.cuda.synchronize()
+        return out, (_shift, qd, kvd)
+
+    o1, keep1 = run(0)
+    o2, keep2 = run(777)
+    o3, _ = run(0)
+    assert torch.equal(o1, o2) and torch.equal(o1, o3), "attention core output depends on buffer addresses / run"
+    o = o1.float().cpu().view(B, Lq, d)
+    assert torch.isfinite(o).all()
+    errs = [G.rel_err(o[b], ref[b]) for b in range(B)]
+    worst = max(range(B), key=lambda b: errs[b])
+    print("attn many items %s: worst batch element %d err %.3e (first wave holds batch elements < %d)" %
+          ((B, h, Lq, Lk, dk, kind), worst, errs[worst], 296 // (h * ((Lq + 127) // 128))))
+    assert errs[worst] < 1e-3, (worst, errs[worst])
+
+
 def test_attn_kat(L):
     """SURVEY 8c known answers, embedded in a d_k=32 head (extra dims zero)."""
     z = G.load("kat.npz")

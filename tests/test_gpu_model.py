@@ -302,6 +302,33 @@ def test_cfg4_decoder_instances_agree_at_batch_64(M, cfg2_model):
     assert n01 == 0 and n0e == 0, (n01, n0e)
 
 
+@pytest.mark.xfail(strict=False, reason="added at the end of round 1 without a GPU run (DESIGN.md section 7, open item): checks the "
+                                        "batch-64 shapes of configs[3] -- 512 / 1024 attention work items, i.e. several per persistent "
+                                        "CTA -- against the CPU oracle on batch elements of the LATER waves")
+@pytest.mark.parametrize("T", [12, 19])
+def test_cfg4_batch_64_step_vs_oracle(M, cfg2_model, T):
+    """One full-prefix decode step at BASELINE configs[3]'s batch (64 dialogues, prefix length T) against the CPU
+    oracle on dialogues 0, 40 and 63 (the target-path attention launches have 512 work items on 296 resident CTAs:
+    dialogues >= 37 are second items; the QAE launches have 1024), for the decoder output and both QAE outputs."""
+    mtn, du = M
+    cfg, model = cfg2_model
+    inp = O.synth_inputs(cfg, B=64, Q=64, C=64, H=256, T=T, Lv=[512, 256], seed=4242)
+    b = make_batch(du, inp)
+    with torch.no_grad():
+        out, ae = model.forward(b)
+        out2, _ = model.forward(b)
+    assert torch.isfinite(out).all() and torch.equal(out, out2)
+    sel = [0, 40, 63]
+    sub = {k: (v[sel] if torch.is_tensor(v) else [f[sel] for f in v]) for k, v in inp.items()}
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref_out, ref_ae = O.forward(sd, cfg, sub["query"], sub["his"], sub["cap"], sub["trg"], sub["fts"])
+    e = {"out": [G.rel_err(out[i].cpu(), ref_out[j]) for j, i in enumerate(sel)],
+         "ae0": [G.rel_err(ae[0][i].cpu(), ref_ae[0][j]) for j, i in enumerate(sel)],
+         "ae1": [G.rel_err(ae[1][i].cpu(), ref_ae[1][j]) for j, i in enumerate(sel)]}
+    print("cfg4 batch 64, T=%d vs oracle (dialogues %s): %s" % (T, sel, e))
+    assert max(max(v) for v in e.values()) <= TOL, e
+
+
 def test_cfg5_family_d1024_h16(M):
     """BASELINE configs[4] architecture family (d_model=1024, h=16 -> d_k=64, d_ff=4096, video_len=1024) at
     N=1 and a small batch so the CPU oracle finishes in seconds."""
