@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     const uint32_t sw = (uint32_t)(row & 7);
     constexpr int NCH = ATT_KT / 32;
     uint32_t g = 0;
-    const unsigned long long dseed = (DROP && p.drop.seed != nullptr) ? __ldg(p.drop.seed) : 0ull;
+    const unsigned long long dseed = (DROP && p.drop.seed != nullptr) ? __ldcg(p.drop.seed) : 0ull;
 
     // The mask words of a tile are requested one tile ahead (the first tile of the next work item during the
     // last tile of the current one): their latency would otherwise sit at the head of every tile.
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int k0 = jn * ATT_KT + c * 32;
-        mw_pref[c] = (mr != nullptr && k0 < p.Lk) ? __ldg(mr + (k0 >> 5)) : 0xffffffffu;
+        mw_pref[c] = (mr != nullptr && k0 < p.Lk) ? __ldcg(mr + (k0 >> 5)) : 0xffffffffu;  // coherent load (PDL, common.cuh)
       }
     };
     const uint32_t* mrow = mask_row(blockIdx.x);

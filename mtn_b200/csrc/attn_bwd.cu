@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const float c1 = p.scale * LOG2E;
     const float t_masked = -1e9f * LOG2E;
     const uint32_t sw = (uint32_t)(row & 7);
-    const unsigned long long dseed = p.drop.seed != nullptr ? __ldg(p.drop.seed) : 0ull;
+    const unsigned long long dseed = p.drop.seed != nullptr ? __ldcg(p.drop.seed) : 0ull;
     uint32_t g = 0;  // query tiles processed so far by this CTA (all items): barrier phases and the dQ buffer index
 
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       const bool valid = qi < p.Lq;
       float m_row = 0.f, inv_l = 0.f, delta = 0.f;
       if (valid) {
-        const float2 st = __ldg(p.stats + bh * p.Lq + qi);
+        const float2 st = __ldcg(p.stats + bh * p.Lq + qi);
         m_row = st.x;
         inv_l = st.y;
-        delta = __ldg(p.delta + bh * p.Lq + qi);
+        delta = __ldcg(p.delta + bh * p.Lq + qi);  // written by the predecessor (attn_delta): coherent load, common.cuh
       }
       const uint32_t* mrow = nullptr;
       if (p.mask_bits != nullptr) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         const int k0 = kt * AB_T + c * 32;
         const int nvalid = p.Lk - k0;
         const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldg(mrow + (k0 >> 5)) : 0xffffffffu;
+        const uint32_t mw = (mrow != nullptr && nvalid > 0) ? __ldcg(mrow + (k0 >> 5)) : 0xffffffffu;
         uint32_t pk_p[16], pk_d[16];
         if (nvalid > 0) {  // warp-uniform
           uint32_t s[32], d[32];

@@ -65,6 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // of its CTAs are resident the next kernel of the stream may start and run its prologue (barrier
 // init, TMEM allocation, descriptor prefetch) -- and pdl_wait() before its first global-memory
 // access, which blocks until the preceding kernel has completed and its writes are visible.
+// Loads of data that the PREDECESSOR kernel produced (the residual stream, logits, mask words ...) must not take the
+// non-coherent path (ld.global.nc, what `const T* __restrict__` / __ldg compile to): this kernel's lifetime starts
+// before its griddepcontrol.wait, i.e. while the producer is still writing, and .nc data has to be read-only for the
+// whole lifetime of the kernel.  Such loads use __ldcg (ld.global.cg: L2, the coherence point); parameters and
+// weights, which no kernel of the same pass writes, stay on __ldg.
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }

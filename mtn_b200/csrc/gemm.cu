@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     constexpr bool MASKED = (A_MN == 0 && B_MN == 1);  // only the data-gradient form carries the ReLU-mask epilogue
     const bool f16_only = epi0.out16 != nullptr && epi0.out32 == nullptr && epi0.addend == nullptr &&
                           !(MASKED && epi0.relu_mask != nullptr);
-    const float alpha = epi0.alpha != nullptr ? __ldg(epi0.alpha) : 1.f;
-    const unsigned long long drop_seed = (DROP && epi0.drop.seed != nullptr) ? __ldg(epi0.drop.seed) : 0ull;
+    const float alpha = epi0.alpha != nullptr ? __ldcg(epi0.alpha) : 1.f;  // written by a recent kernel (gradient scale): coherent load
+    const unsigned long long drop_seed = (DROP && epi0.drop.seed != nullptr) ? __ldcg(epi0.drop.seed) : 0ull;
     const float mscale = epi0.mask_scale != 0.f ? epi0.mask_scale : 1.f;
     const int sub_r = lane >> 2, c8 = lane & 3;  // coalesced phase: 4 lanes x 8 columns per row, 8 rows per pass
     constexpr int NCHUNK = BN / 32;

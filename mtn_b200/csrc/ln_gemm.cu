@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
           const int g = m0 + ew + 8 * (b * RB + j);
           const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(g < M ? g : 0) * D);
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) dst[j][i] = (g < M) ? xr[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < VPL; ++i) dst[j][i] = (g < M) ? __ldcg(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
       load_batch(0, v[0]);

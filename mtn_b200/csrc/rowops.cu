@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256)
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    v[i] = xr[lane + 32 * i];
+    v[i] = __ldcg(xr + lane + 32 * i);  // coherent (L2) load: x is written by the PDL-overlapped predecessor, see common.cuh
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
 #pragma unroll
@@ -75,18 +75,18 @@ __global__ void layernorm_generic_kernel(const float* __restrict__ x, const floa
   const int lane = threadIdx.x & 31;
   const float* xr = x + (size_t)row * d;
   float s = 0.f;
-  for (int i = lane; i < d; i += 32) s += xr[i];
+  for (int i = lane; i < d; i += 32) s += __ldcg(xr + i);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / d;
   float ss = 0.f;
   for (int i = lane; i < d; i += 32) {
-    const float t = xr[i] - mean;
+    const float t = __ldcg(xr + i) - mean;
     ss += t * t;
   }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float inv = 1.f / (sqrtf(ss / (d - 1)) + eps);
   for (int i = lane; i < d; i += 32) {
-    const float o = a2[i] * (xr[i] - mean) * inv + b2[i];
+    const float o = a2[i] * (__ldcg(xr + i) - mean) * inv + b2[i];
     if (y32) y32[(size_t)row * d + i] = o;
     if (y16) {
       const uint32_t p = pack_f16x2_sat(o, 0.f);
@@ -105,8 +105,8 @@ __global__ void cast_f16_vec8_kernel(const float* __restrict__ src, int ld_src, 
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * cols8) return;
   const int r = (int)(i / cols8), c = (int)(i % cols8) * 8;
-  const float4 lo = *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c);
-  const float4 hi = *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c + 4);
+  const float4 lo = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c));
+  const float4 hi = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c + 4));
   *reinterpret_cast<uint4*>(dst + (size_t)r * ld_dst + c) =
       make_uint4(pack_f16x2_sat(lo.x, lo.y), pack_f16x2_sat(lo.z, lo.w), pack_f16x2_sat(hi.x, hi.y),
                  pack_f16x2_sat(hi.z, hi.w));
@@ -118,7 +118,7 @@ __global__ void cast_f16_scalar_kernel(const float* __restrict__ src, int ld_src
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * cols) return;
   const int r = (int)(i / cols), c = (int)(i % cols);
-  const uint32_t p = pack_f16x2_sat(src[(size_t)r * ld_src + c], 0.f);
+  const uint32_t p = pack_f16x2_sat(__ldcg(src + (size_t)r * ld_src + c), 0.f);
   dst[(size_t)r * ld_dst + c] = __ushort_as_half((unsigned short)(p & 0xffff));
 }
 
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128)
   float mx = -3.4e38f;
   int mi = 0;
   for (int i = threadIdx.x; i < V; i += 128) {
-    const float v = xr[i];
+    const float v = __ldcg(xr + i);
     if (v > mx) { mx = v; mi = i; }
   }
   if (argmax != nullptr) {  // first maximal index, like torch.max / argmax
@@ -312,10 +312,10 @@ __global__ void __launch_bounds__(128)
   const float m = block_reduce_128(mx, true, sh);
   if (y == nullptr) return;
   float s = 0.f;
-  for (int i = threadIdx.x; i < V; i += 128) s += __expf(xr[i] - m);
+  for (int i = threadIdx.x; i < V; i += 128) s += __expf(__ldcg(xr + i) - m);
   const float lse = m + __logf(block_reduce_128(s, false, sh));
   float* yr = y + (size_t)blockIdx.x * ldy;
-  for (int i = threadIdx.x; i < V; i += 128) yr[i] = xr[i] - lse;
+  for (int i = threadIdx.x; i < V; i += 128) yr[i] = __ldcg(xr + i) - lse;
 }
 
 }  // namespace mtn
@@ -424,23 +424,23 @@ __global__ void __launch_bounds__(128)
   const long long y = tgt[r];
   float mx = -3.4e38f, sum = 0.f;
   for (int i = threadIdx.x; i < V; i += 128) {
-    const float v = zr[i];
+    const float v = __ldcg(zr + i);
     mx = fmaxf(mx, v);
     sum += v;
   }
   const float m = block_reduce_128(mx, true, sh);
   const float zsum = block_reduce_128(sum, false, sh);
   float se = 0.f;
-  for (int i = threadIdx.x; i < V; i += 128) se += __expf(zr[i] - m);
+  for (int i = threadIdx.x; i < V; i += 128) se += __expf(__ldcg(zr + i) - m);
   const float lse = m + __logf(block_reduce_128(se, false, sh));
   if (threadIdx.x != 0) return;
   const float s = smoothing / (float)(V - 2), conf = 1.f - smoothing;
   const float sum_logp = zsum - (float)V * lse;
-  const float logp_p = zr[pad] - lse;
+  const float logp_p = __ldcg(zr + pad) - lse;
   const float s_log_s = s > 0.f ? __logf(s) : 0.f;
   float loss;
   if (y != pad) {
-    const float logp_y = zr[y] - lse;
+    const float logp_y = __ldcg(zr + y) - lse;
     loss = (conf > 0.f ? conf * (__logf(conf) - logp_y) : 0.f) +
            (s > 0.f ? s * ((float)(V - 2) * s_log_s - (sum_logp - logp_y - logp_p)) : 0.f);
   } else if (*pad_index_sum > 0ull) {
