@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(128)
     const float logp_y = __ldcg(zr + y) - lse;
     loss = (conf > 0.f ? conf * (__logf(conf) - logp_y) : 0.f) +
            (s > 0.f ? s * ((float)(V - 2) * s_log_s - (sum_logp - logp_y - logp_p)) : 0.f);
-  } else if (*pad_index_sum > 0ull) {
+  } else if (__ldcg(pad_index_sum) > 0ull) {  // written by the predecessor kernel: coherent load
     loss = 0.f;
   } else {
     loss = s > 0.f ? s * ((float)(V - 1) * s_log_s - (sum_logp - logp_p)) : 0.f;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(1024) sum_scaled_kernel(const float* __restric
   pdl_launch_dependents();
   pdl_wait();
   float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += 1024) acc += x[i];
+  for (int i = threadIdx.x; i < n; i += 1024) acc += __ldcg(x + i);  // row losses of the predecessor kernel
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
   __syncthreads();
