@@ -9,6 +9,11 @@
 // chosen on the device from its magnitude (mtn_grad_scale_*), keeps every intermediate scaled, and multiplies
 // each RESULT (parameter / input gradient) by 1/S in the producing kernel.  `scale` / `alpha` arguments below
 // are pointers to those device scalars (NULL = 1).
+//
+// Input pointers are `const T*` WITHOUT __restrict__, and device scalars are read with __ldcg: nearly every input
+// here is produced by the kernel launched just before, whose writes overlap this kernel's lifetime under
+// programmatic dependent launch, so the non-coherent load path is off limits (rule in common.cuh).  Only weights
+// (embedding table, positional table, a_2) keep __ldg.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -56,9 +61,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float dys = p.dy_scale ? __ldg(p.dy_scale) : 1.f;
-  const float pal = p.param_alpha ? __ldg(p.param_alpha) : 1.f;
-  const unsigned long long dseed = p.drop.seed ? __ldg(p.drop.seed) : 0ull;
+  const float dys = p.dy_scale ? __ldcg(p.dy_scale) : 1.f;
+  const float pal = p.param_alpha ? __ldcg(p.param_alpha) : 1.f;
+  const unsigned long long dseed = p.drop.seed ? __ldcg(p.drop.seed) : 0ull;
   // keep decisions of this lane's float4 number i of `row` (columns 4*(lane+32i) .. +3): 4 bits
   auto keep4 = [&](int row, int i) -> uint32_t {
     if (p.drop.seed == nullptr) return 0xfu;
@@ -255,16 +260,16 @@ __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
 
 template <typename TIn>
 __global__ void __launch_bounds__(256)
-    cast_colsum_kernel(const TIn* __restrict__ src, int ld_src, __half* __restrict__ dst, int ld_dst,
-                       const __half* __restrict__ relu_mask, int ld_mask, int rows, int vcols, int rows_per_block,
-                       const float* __restrict__ scale, const float* __restrict__ alpha, float* __restrict__ colsum,
+    cast_colsum_kernel(const TIn* src, int ld_src, __half* __restrict__ dst, int ld_dst,
+                       const __half* relu_mask, int ld_mask, int rows, int vcols, int rows_per_block,
+                       const float* scale, const float* alpha, float* __restrict__ colsum,
                        const DropCfg drop, int multimem) {
   pdl_launch_dependents();
   pdl_wait();
-  const unsigned long long dseed = drop.seed ? __ldg(drop.seed) : 0ull;
+  const unsigned long long dseed = drop.seed ? __ldcg(drop.seed) : 0ull;
   const int vc = blockIdx.x * 32 + threadIdx.x;
   const bool active = vc < vcols;
-  const float sc = scale ? __ldg(scale) : 1.f;
+  const float sc = scale ? __ldcg(scale) : 1.f;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int r_end = active ? min(rows, (int)(blockIdx.y + 1) * rows_per_block) : 0;
   const int r0 = blockIdx.y * rows_per_block + threadIdx.y;
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(256)
   }
   }
   if (colsum != nullptr) {
-    const float al = alpha ? __ldg(alpha) : 1.f;
+    const float al = alpha ? __ldcg(alpha) : 1.f;
     // the 8 row lanes of a block share columns: combine them through shared memory first
     __shared__ float sh[8][32][9];
 #pragma unroll
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(256)
 // Gradient scale: S = 2^k with absmax * S in [2^7, 2^8); out = {S, 1/S}.  absmax is collected into a
 // self-resetting slot (uint bits of a non-negative float order like the float).
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n4, unsigned* __restrict__ slot) {
+__global__ void __launch_bounds__(256) absmax_kernel(const float* x, size_t n4, unsigned* __restrict__ slot) {
   __shared__ float sh[8];
   pdl_launch_dependents();
   pdl_wait();
@@ -378,11 +383,11 @@ __global__ void adam_advance_kernel(float* st, float noam_factor, float model_si
 
 __global__ void __launch_bounds__(256)
     adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                     __half* __restrict__ p16, size_t n4, const float* __restrict__ st, int zero_grad) {
+                     __half* __restrict__ p16, size_t n4, const float* st, int zero_grad) {
   pdl_launch_dependents();
   pdl_wait();
-  const float lr = __ldg(st), b1 = __ldg(st + 1), b2 = __ldg(st + 2), eps = __ldg(st + 3);
-  const float step_size = lr / __ldg(st + 4), inv_sqrt_bc2 = rsqrtf(__ldg(st + 5));
+  const float lr = __ldcg(st), b1 = __ldcg(st + 1), b2 = __ldcg(st + 2), eps = __ldcg(st + 3);
+  const float step_size = lr / __ldcg(st + 4), inv_sqrt_bc2 = rsqrtf(__ldcg(st + 5));
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     float4 P = reinterpret_cast<float4*>(p)[i];
     const float4 Gv = reinterpret_cast<const float4*>(g)[i];
@@ -409,11 +414,11 @@ __global__ void seed_bump_kernel(unsigned long long* seed) {
 }
 
 // y = (accumulate ? y : 0) + x * alpha: un-scaling of an input gradient that leaves the backward pass
-__global__ void __launch_bounds__(256) scale_f32_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+__global__ void __launch_bounds__(256) scale_f32_kernel(const float* x, const float* alpha,
                                                         float* __restrict__ y, size_t n4, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
-  const float a = alpha ? __ldg(alpha) : 1.f;
+  const float a = alpha ? __ldcg(alpha) : 1.f;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
     v = make_float4(v.x * a, v.y * a, v.z * a, v.w * a);
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(256) scale_f32_kernel(const float* __restrict_
 // f32 result): the softmax-backward row term of attention (dS = P * (dP - delta)).  One warp per row.
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    attn_delta_kernel(const __half* __restrict__ dO, int lddo, const __half* __restrict__ O, int ldo, int B, int Lq, int h,
+    attn_delta_kernel(const __half* dO, int lddo, const __half* O, int ldo, int B, int Lq, int h,
                       int dk, float* __restrict__ delta) {
   pdl_launch_dependents();
   pdl_wait();
@@ -473,7 +478,7 @@ __device__ __forceinline__ float block_max_128(float v, float* sh) {
 }
 
 __global__ void __launch_bounds__(128)
-    log_softmax_bwd_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ dy, int lddy, int V,
+    log_softmax_bwd_kernel(const float* y, int ldy, const float* dy, int lddy, int V,
                            float* __restrict__ dz, int lddz) {
   __shared__ float sh[4];
   pdl_launch_dependents();
@@ -493,9 +498,9 @@ __global__ void __launch_bounds__(128)
 //   dz_v = g * (T_r softmax(z)_v - t_v),  t = smoothed target row, T_r = sum_v t_v.
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-    label_smoothing_bwd_kernel(const float* __restrict__ z, int ldz, int V, const long long* __restrict__ tgt, long long pad,
-                               float smoothing, const unsigned long long* __restrict__ pad_index_sum, float gscale,
-                               const float* __restrict__ gout, float* __restrict__ dz, int lddz) {
+    label_smoothing_bwd_kernel(const float* z, int ldz, int V, const long long* tgt, long long pad,
+                               float smoothing, const unsigned long long* pad_index_sum, float gscale,
+                               const float* gout, float* __restrict__ dz, int lddz) {
   __shared__ float sh[4];
   pdl_launch_dependents();
   pdl_wait();
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__(128)
   const float* zr = z + (size_t)r * ldz;
   float* dzr = dz + (size_t)r * lddz;
   const long long y = tgt[r];
-  const float g = gscale * (gout ? __ldg(gout) : 1.f);
+  const float g = gscale * (gout ? __ldcg(gout) : 1.f);
   const float s = smoothing / (float)(V - 2), conf = 1.f - smoothing;
   const bool is_pad = (y == pad);
   if (is_pad && *pad_index_sum > 0ull) {  // zeroed padding row
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // sum of the indices of the padding rows (label_smoothing.py:26-30 quirk; same as the forward's kernel)
-__global__ void __launch_bounds__(1024) pad_index_sum_bwd_kernel(const long long* __restrict__ tgt, int rows, long long pad,
+__global__ void __launch_bounds__(1024) pad_index_sum_bwd_kernel(const long long* tgt, int rows, long long pad,
                                                                  unsigned long long* __restrict__ out) {
   __shared__ unsigned long long sh[32];
   pdl_launch_dependents();
