@@ -170,3 +170,29 @@ def test_shard_range_partitions():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
     assert parallel.shard_range(256, 3, 8) == (96, 128)             # cfg3: rows [32r, 32r+32)
+
+
+def test_ln_linear_dispatch(monkeypatch):
+    """engine._ln_linear: the fused LayerNorm + projection launch is taken only when MTN_B200_LN_FUSED opts in, the
+    row count is under the threshold and d is supported; otherwise LayerNorm -> f16 -> linear (the shipped default,
+    DESIGN.md section 4).  No kernel runs: the binding functions are replaced by recorders."""
+    calls = []
+    monkeypatch.setattr(_lib, "ln_linear_supported", lambda d: d in (128, 256, 512))
+    monkeypatch.setattr(_lib, "ln_linear", lambda *a, **k: calls.append("fused"))
+    monkeypatch.setattr(_lib, "layernorm", lambda *a, **k: calls.append("ln"))
+    monkeypatch.setattr(_lib, "linear", lambda *a, **k: calls.append("linear"))
+    ln = (torch.ones(512), torch.zeros(512), 1e-6)
+    x = torch.zeros(640, 512)
+    monkeypatch.delenv("MTN_B200_LN_FUSED", raising=False)
+    engine._ln_linear(x, ln, None, None, 0, None, None)
+    assert calls == ["ln", "linear"]                      # default: never fused
+    del calls[:]
+    monkeypatch.setenv("MTN_B200_LN_FUSED", "1000")
+    engine._ln_linear(x, ln, None, None, 0, None, None)
+    assert calls == ["fused"]
+    del calls[:]
+    engine._ln_linear(torch.zeros(2048, 512), ln, None, None, 0, None, None)      # above the threshold
+    assert calls == ["ln", "linear"]
+    del calls[:]
+    engine._ln_linear(torch.zeros(64, 1024), (torch.ones(1024), torch.zeros(1024), 1e-6), None, None, 0, None, None)
+    assert calls == ["ln", "linear"]                      # d = 1024: the row block's panels do not fit shared memory
