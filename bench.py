@@ -467,7 +467,7 @@ def main():
     # dependent-launch latency that a second batch can hide.
     in_flight = None
     rot2 = args.rot - args.rot % 2
-    if rot2 >= 2:
+    if rot2 >= 2 and world == 1:      # context only; single-process so that a failure cannot desynchronise ranks
         try:
             sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
             cur = torch.cuda.current_stream()
@@ -664,7 +664,7 @@ def main():
                               "all steps, D2H of tokens"}
         # Several dialogue batches in flight: a decoding step is a chain of small dependent kernels (<= 40 CTAs each on
         # 148 SMs), so independent batches on their own streams fill the idle SMs -- same per-batch work, same tokens.
-        if args.decode_in_flight > 1:
+        if args.decode_in_flight > 1 and world == 1:
             try:
                 K = args.decode_in_flight
                 dev0 = {k: (v.to(dev) if torch.is_tensor(v) else [f.to(dev) for f in v]) for k, v in dh[0].items()}
