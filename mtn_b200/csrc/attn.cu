@@ -250,6 +250,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     const uint32_t* mrow = mask_row(blockIdx.x);
     fetch_mask(mrow, 0);
     bool staged = false;  // this warp's TMA store of the previous item's output rows may still be reading the P buffer
+    // Output staging tile of this warp (32 rows x d_k f16, TMA box layout): the first bytes of the warp's OWN 32 rows of
+    // P panel 0 (128 B per row = 4 KB per warp), so that only the owning warp -- which waits for its TMA store to have
+    // read the tile before it writes the next item's P -- ever touches it.  (For d_k = 64 the tile fills those 4 KB
+    // exactly; for d_k = 32 it is their first half: a dense [row * 64 B] layout would alias other warps' P rows.)
+    const uint32_t sO = sP + (uint32_t)q4 * (32u * 128u);
 
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const int qt = it % p.nqt, hd = (it / p.nqt) % p.h, b = it / (p.nqt * p.h);
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         for (int t = 0; t < 4; ++t) {
           // 128B swizzle (d_k = 64): 16-B chunk ^= row % 8;  64B swizzle (d_k = 32): chunk ^= (row / 2) % 4
           const uint32_t chunk = DK == 64 ? ((uint32_t)(c * 4 + t) ^ sw) : ((uint32_t)t ^ ((uint32_t)(row >> 1) & 3u));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + row * C::ROWB + chunk * 16),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sO + lane * C::ROWB + chunk * 16),
                        "r"(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l)),
                        "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l)),
                        "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l)),
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&tmO, sP + q4 * 32 * C::ROWB, hd * DK, qt * ATT_QT + q4 * 32, b);
+        tma_store_3d(&tmO, sO, hd * DK, qt * ATT_QT + q4 * 32, b);
         tma_store_commit();
       }
       staged = true;

@@ -111,17 +111,23 @@ class SimpleLossCompute:
         self.generator, self.ae_generator, self.criterion, self.opt, self.l = generator, ae_generator, criterion, opt, l
 
     def loss(self, x, y, norm, ae_x=None, ae_y=None, ae_norm=None):
-        """The normalised loss as a 0-d tensor (differentiable when autograd is recording); no host sync when
-        ``norm`` / ``ae_norm`` are Python numbers."""
+        """The normalised loss as a 0-d tensor (differentiable when autograd is recording).  No host sync: ``norm`` /
+        ``ae_norm`` may be Python numbers (folded into the kernels' scale) or 0-d DEVICE tensors (the counts of the batch
+        in flight, e.g. inside a captured step: the division then happens on the device, per replay)."""
+        def scaled(logits, V, target, weight, n):
+            if torch.is_tensor(n) and n.is_cuda:
+                return self.criterion.from_logits(logits, V, target, scale=float(weight)) / n.to(torch.float32)
+            return self.criterion.from_logits(logits, V, target, scale=float(weight) / float(n))
+
         logits, V = self.generator._logits(x)
-        total = self.criterion.from_logits(logits, V, y, scale=1.0 / float(norm))
+        total = scaled(logits, V, y, 1.0, norm)
         if ae_x is not None:
             streams = ae_x if isinstance(ae_x, (list, tuple)) else [ae_x]
             for i, ae_in in enumerate(streams):
                 gen = self.generator if self.ae_generator is None else (
                     self.ae_generator[i] if isinstance(ae_x, (list, tuple)) else self.ae_generator)
                 lg, Vg = gen._logits(ae_in)
-                total = total + self.criterion.from_logits(lg, Vg, ae_y, scale=self.l / float(ae_norm))
+                total = total + scaled(lg, Vg, ae_y, self.l, ae_norm)
         return total
 
     def __call__(self, x, y, norm, ae_x=None, ae_y=None, ae_norm=None):

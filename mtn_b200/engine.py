@@ -49,6 +49,18 @@ def _ln_fused_max_rows():
 LN_FUSED_MAX_ROWS = 0
 
 
+# Debug taps (tools/bisect_decode.py): when TAP is a list, the target path appends (label, clone) of every
+# intermediate -- also inside CUDA-graph capture, where the clones live in the graph's pool and are refreshed by
+# every replay.  None in production: no extra work.
+TAP = None
+TAP_PREFIX = [""]
+
+
+def _tap(label, t):
+    if TAP is not None:
+        TAP.append((TAP_PREFIX[0] + label, t.clone()))
+
+
 def _ln_linear(x, ln, w, b, act, xn16, out16):
     """out16 = act(LN(x) w^T + b): one fused launch when the shape qualifies, else LayerNorm -> xn16 -> linear
     (same results either way, tests/test_gpu_ln_linear.py)."""
@@ -57,18 +69,33 @@ def _ln_linear(x, ln, w, b, act, xn16, out16):
         _lib.ln_linear(x, ln[0], ln[1], ln[2], w, bias=b, act=act, out_f16=out16)
         return
     _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
+    _tap("xn16", xn16)
     _lib.linear(xn16, w, b, act=act, out_f16=out16)
+
+
+_GENERATION = [0]
+
+
+def invalidate_weight_caches():
+    """Public hook: call after modifying parameters in a way autograd's version counters do not see --
+    writes through ``p.data`` (``p.data.mul_(2)`` leaves ``p._version`` unchanged), raw-pointer kernel updates
+    (the fused arena Adam), ``p.data = new_tensor`` with a recycled address.  Every f16 weight pack and every cached
+    memory stage (their keys carry this generation) is rebuilt on its next use."""
+    _GENERATION[0] += 1
 
 
 class PackedWeights(object):
     """Cache of tensor-core-ready (f16, concatenated) copies of nn.Parameters, rebuilt
-    when any source parameter is modified in place (``_version``) or re-assigned."""
+    when any source parameter is modified in place (``_version``), re-assigned, or after
+    ``invalidate_weight_caches()`` (writes the version counters cannot see)."""
 
-    def __init__(self):
-        self._key, self._val = None, None
+    def __init__(self, follow_generation=True):
+        # follow_generation=False: the owner refreshes the pack itself when the raw-pointer writer runs (the training
+        # arena, whose f16 copy the fused Adam kernel rewrites in the same pass)
+        self._key, self._val, self._gen = None, None, follow_generation
 
     def get(self, params, build):
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (_GENERATION[0] if self._gen else 0,) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self._key:
             self._val, self._key = build(), key
         return self._val
@@ -80,7 +107,7 @@ class PackedWeights(object):
         return {}
 
     def __setstate__(self, st):
-        self._key, self._val = None, None
+        self._key, self._val, self._gen = None, None, True
 
 
 class _MemoryKey(object):
@@ -193,13 +220,18 @@ class DecoderEngine(object):
             q, k, v = qbuf[:, :d], qbuf[:, d:2 * d], qbuf[:, 2 * d:]
         else:
             q, k, v = qbuf, kv[:, k_col:k_col + d], kv[:, v_col:v_col + d]
+        _tap("q", qbuf)
         _lib.attn_core(q, k, v, B, A["h"], Lq, Lk, A["d_k"], obuf, mask_bits=bits)
+        _tap("o", obuf)
         _lib.linear(obuf, A["w_o"], A["b_o"], addend=x, out_f32=x)
+        _tap("x", x)
 
     @staticmethod
     def _ffn_block(x, ln, Fw, xn16, hid, out16=None):
         _ln_linear(x, ln, Fw["w_1"], Fw["b_1"], _lib.ACT_RELU, xn16, hid)
+        _tap("hid", hid)
         _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x, out_f32=x, out_f16=out16)
+        _tap("x", x)
 
     # ------------------------------------------------------------------ memory stage
     def _streams(self, M, dev):
@@ -405,30 +437,40 @@ class DecoderEngine(object):
         if tm is not None and tm.shape[0] != B:
             tm = tm.expand(B, -1, -1)
         bits_t = _lib.mask_pack(tm) if tm is not None else None
+        if bits_t is not None:
+            _tap("bits_t", bits_t)
         order = (("src", "kv_q", "bits_q", "Q"), ("cap", "kv_cap", "bits_cap", "C")) \
             if ae_features in ("caption", "summary") else \
             (("cap", "kv_cap", "bits_cap", "C"), ("src", "kv_q", "bits_q", "Q"))
+        _tap("embed.x", xs)
         for l in range(N):
             Lw = W["layers"][l]
             A = Lw["self"]
+            TAP_PREFIX[0] = "L%d.self." % l
             self._attn_block(xs, Lw["ln"][0], A, B, T, T, A["w_qkv"], A["b_qkv"], None, 0, 0, bits_t, xn16, qkv, obuf)
             kc, vc = l * 2 * d, l * 2 * d + d
             A = Lw["his"]
+            TAP_PREFIX[0] = "L%d.his." % l
             self._attn_block(xs, Lw["ln"][1], A, B, T, S["H"], A["w_qkv"][:d], A["b_qkv"][:d], S["kv_his"], kc, vc,
                              S["bits_his"], xn16, qkv[:, :d], obuf)
             for c, (name, kvn, bn, Ln) in enumerate(order):
                 A = Lw[name]
+                TAP_PREFIX[0] = "L%d.%s." % (l, name)
                 self._attn_block(xs, Lw["ln"][2 + c], A, B, T, S[Ln], A["w_qkv"][:d], A["b_qkv"][:d], S[kvn], kc, vc,
                                  S[bn], xn16, qkv[:, :d], obuf)
             for i in range(M):
                 if fresh:
                     main.wait_event(S["ev"][l][i])          # layer l's K/V of ae_i (side stream i)
                 A = Lw["ae_attn"][i]
+                TAP_PREFIX[0] = "L%d.ae%d." % (l, i)
                 self._attn_block(xs, Lw["ln"][7 + 4 * i], A, B, T, S["La"], A["w_qkv"][:d], A["b_qkv"][:d],
                                  S["kv_ae"][l][i], 0, d, S["bits_ae"], xn16, qkv[:, :d], obuf)
+            TAP_PREFIX[0] = "L%d.ffn." % l
             self._ffn_block(xs, Lw["ln"][4 + 4 * M], Lw["ffn"], xn16, hid)
         out = torch.empty(rows, d, dtype=torch.float32, device=dev)
         _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=out)   # mtn.py:164
+        TAP_PREFIX[0] = ""
+        _tap("final.out", out)
         if fresh:
             for st in S["side"]:                                 # join (also required for graph capture)
                 main.wait_stream(st)

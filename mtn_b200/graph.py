@@ -75,7 +75,11 @@ class GraphedGreedyDecoder(object):
         self.ys = torch.full((B, max_len), pad, dtype=torch.int64, device=dev)
         self.ys[:, 0] = sos
         self._sos = sos
-        masks = [subsequent_mask(t, dev) for t in range(max_len)]      # built outside capture
+        # Built outside capture and read by every replay: they MUST stay referenced for the lifetime of the graphs.
+        # (Round 1 kept them in a local only: once __init__ returned the caching allocator recycled their memory and the
+        # replayed steps read whatever the next small allocation wrote there -- the "batch-64 decoder instances
+        # disagree" item: row 0 of the causal mask gained a stray key.  tools/bisect_decode.py found it.)
+        masks = self.masks = [subsequent_mask(t, dev) for t in range(max_len)]
 
         def prefill():
             st = self.static

@@ -54,7 +54,7 @@ class _Arena(object):
 class DecoderTrainer(object):
     def __init__(self, decoder):
         self.dec = decoder
-        self._packed = PackedWeights()
+        self._packed = PackedWeights(follow_generation=False)
         self._arena = None          # flat f32 parameter arena + f16 operand arena (same layout)
         self._grad = None           # optional persistent gradient arena (same layout) backing every .grad
         self._mc = 0                # byte offset local -> NVLS multicast mapping of that arena (0: local accumulation)

@@ -247,11 +247,14 @@ ATT_MANY = [
     (64, 8, 19, 64, 64, "keypad"),      # target -> caption / query
     (128, 8, 64, 64, 64, "keypad"),     # QAE self-attention of both modalities at batch 64: 1024 items
     (40, 8, 200, 300, 64, "holes"),     # 640 items, second query tile partially filled
+    # d_k = 32 with several items per CTA and Lq < 128 (the epilogue's output staging tile used to alias
+    # OTHER warps' P rows for d_k = 32; it now lives in the warp's own rows)
+    (96, 8, 100, 64, 32, "keypad"),     # 768 items, all four softmax warps live
+    (80, 8, 120, 200, 32, "holes"),     # 640 items, three key tiles
+    (100, 4, 40, 40, 32, "causal"),     # 400 items, two live warps
 ]
 
 
-@pytest.mark.xfail(strict=False, reason="added at the end of round 1 without a GPU run (profiles/r01d_concurrency.txt, DESIGN.md "
-                                        "section 7: open item); an XPASS clears the attention core of the batch-64 decode discrepancy")
 @pytest.mark.parametrize("B,h,Lq,Lk,dk,kind", ATT_MANY)
 def test_attn_core_many_items(L, B, h, Lq, Lk, dk, kind):
     """Multi-item persistent CTAs with partial query tiles against the oracle arithmetic, PER batch element (items
