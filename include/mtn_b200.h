@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MTN_B200_ABI_VERSION 4   /* v4: `multimem` members (NVLS multicast gradient reductions) in the backward structs */
+#define MTN_B200_ABI_VERSION 5   /* v5: batch strides in MtnAttnCoreArgs (KV-cached decoding); v4: `multimem` members in the backward structs */
 
 enum {
   MTN_OK = 0,
@@ -205,6 +205,10 @@ typedef struct MtnAttnCoreArgs {
    * Lk rounded up to 32, assigns to it are >= drop_thresh; kept probabilities are multiplied by
    * 1/(1 - drop_thresh/65536).  The softmax normalisation is unaffected.  drop_seed NULL = no dropout.        */
   const void *drop_seed; uint32_t drop_site, drop_thresh;
+  /* ABI v5 (KV-cached decoding): element strides between consecutive batch elements of q / k / v / out.
+   * 0 = dense (Lq*ldq, Lk*ldk, Lk*ldv, Lq*ldo).  A self-attention cache [B, T_max, 3d] is then addressed in place:
+   * q = row t of every dialogue (Lq = 1, q_batch_stride = T_max*3d), k / v = its first t+1 rows.  Multiples of 8. */
+  long long q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride;
 } MtnAttnCoreArgs;
 int mtn_attn_core_fwd(const MtnAttnCoreArgs *args, void *stream);
 

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -100,7 +100,9 @@ class AttnCoreArgs(C.Structure):
                 ("v", C.c_void_p), ("ldv", C.c_int), ("mask_bits", C.c_void_p),
                 ("mask_rows_q", C.c_int), ("B", C.c_int), ("h", C.c_int), ("Lq", C.c_int),
                 ("Lk", C.c_int), ("d_k", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int), ("stats", C.c_void_p),
-                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32)]
+                ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thresh", C.c_uint32),
+                ("q_batch_stride", C.c_longlong), ("k_batch_stride", C.c_longlong), ("v_batch_stride", C.c_longlong),
+                ("o_batch_stride", C.c_longlong)]
 
 
 class AttnSiteArgs(C.Structure):
@@ -386,19 +388,27 @@ def ln_linear(x, a_2, b_2, eps, W, bias=None, act=ACT_NONE, out_f16=None):
 
 def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=False, stats=None, drop=None):
     """q: [B*Lq, >=h*d_k] f16 view (row stride = leading dimension), k/v: [B*Lk, ...];
-    out: [B*Lq, >=h*d_k] f16.  mask_bits: output of mask_pack or None."""
+    out: [B*Lq, >=h*d_k] f16.  mask_bits: output of mask_pack or None.
+    Any of q / k / v / out may instead be 3-D [B, >=L, >=h*d_k] views (KV-cached decoding: strides (batch, row, 1);
+    the first Lq / Lk rows of every batch element are used)."""
+    a = AttnCoreArgs()
+    strides = {}
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _req(t, torch.float16, n)
-        assert t.dim() == 2
-    a = AttnCoreArgs()
-    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = (q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
-                                         v.data_ptr(), v.stride(0))
+        assert t.dim() in (2, 3)
+        strides[n] = (t.stride(0), 0) if t.dim() == 2 else (t.stride(1), t.stride(0))
+        if t.dim() == 3:
+            assert t.shape[0] == B and t.shape[1] >= (Lq if n in ("q", "out") else Lk)
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = (q.data_ptr(), strides["q"][0], k.data_ptr(), strides["k"][0],
+                                         v.data_ptr(), strides["v"][0])
+    a.q_batch_stride, a.k_batch_stride, a.v_batch_stride, a.o_batch_stride = (strides["q"][1], strides["k"][1],
+                                                                              strides["v"][1], strides["out"][1])
     if mask_bits is not None:
         assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == B
         assert mask_bits.shape[2] == mask_words(Lk)
         a.mask_bits, a.mask_rows_q = mask_bits.data_ptr(), mask_bits.shape[1]
     a.B, a.h, a.Lq, a.Lk, a.d_k = B, h, Lq, Lk, d_k
-    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.out, a.ldo = out.data_ptr(), strides["out"][0]
     if stats is not None:      # [B, h, Lq, 2] f32 softmax statistics for the backward pass
         _req(stats, torch.float32, "stats")
         assert stats.is_contiguous() and stats.numel() == B * h * Lq * 2

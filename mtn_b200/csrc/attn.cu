@@ -551,14 +551,15 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
   const TmSwizzle swz = DK == 64 ? TM_SWZ_128 : TM_SWZ_64;
   const uint64_t cols = (uint64_t)a.h * DK;
   CUtensorMap tq, tk, tv;
-  int rc = make_tmap_3d_f16(&tq, a.q, cols, a.Lq, a.B, a.ldq, (uint64_t)a.Lq * a.ldq, DK, ATT_QT, swz);
+  auto bstride = [](long long given, int L, int ld) { return given > 0 ? (uint64_t)given : (uint64_t)L * ld; };
+  int rc = make_tmap_3d_f16(&tq, a.q, cols, a.Lq, a.B, a.ldq, bstride(a.q_batch_stride, a.Lq, a.ldq), DK, ATT_QT, swz);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tk, a.k, cols, a.Lk, a.B, a.ldk, (uint64_t)a.Lk * a.ldk, DK, ATT_KT, swz);
+  rc = make_tmap_3d_f16(&tk, a.k, cols, a.Lk, a.B, a.ldk, bstride(a.k_batch_stride, a.Lk, a.ldk), DK, ATT_KT, swz);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tv, a.v, cols, a.Lk, a.B, a.ldv, (uint64_t)a.Lk * a.ldv, DK, ATT_KT, swz);
+  rc = make_tmap_3d_f16(&tv, a.v, cols, a.Lk, a.B, a.ldv, bstride(a.v_batch_stride, a.Lk, a.ldv), DK, ATT_KT, swz);
   if (rc) return rc;
   CUtensorMap to;
-  rc = make_tmap_3d_f16(&to, a.out, cols, a.Lq, a.B, a.ldo, (uint64_t)a.Lq * a.ldo, DK, 32, swz);
+  rc = make_tmap_3d_f16(&to, a.out, cols, a.Lq, a.B, a.ldo, bstride(a.o_batch_stride, a.Lq, a.ldo), DK, 32, swz);
   if (rc) return rc;
   const int nqt = (a.Lq + ATT_QT - 1) / ATT_QT;
   const int n_items = nqt * a.h * a.B;
@@ -594,6 +595,12 @@ static int validate_attn(const MtnAttnCoreArgs* a) {
   MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,
               "attn_core: mask_rows_q=%d must be 1 or Lq=%d", a->mask_rows_q, a->Lq);
   MTN_REQUIRE(a->drop_thresh < 65536u, MTN_E_ARG, "attn_core: drop_thresh=%u", a->drop_thresh);
+  MTN_REQUIRE(a->q_batch_stride >= 0 && a->k_batch_stride >= 0 && a->v_batch_stride >= 0 && a->o_batch_stride >= 0 &&
+                  a->q_batch_stride % 8 == 0 && a->k_batch_stride % 8 == 0 && a->v_batch_stride % 8 == 0 &&
+                  a->o_batch_stride % 8 == 0,
+              MTN_E_ALIGN, "attn_core: batch strides must be non-negative multiples of 8 elements");
+  MTN_REQUIRE(a->stats == nullptr || (a->q_batch_stride == 0 && a->o_batch_stride == 0), MTN_E_ARG,
+              "attn_core: saved statistics (training) need the dense batch layout");
   return MTN_OK;
 }
 
@@ -602,16 +609,16 @@ static int validate_attn(const MtnAttnCoreArgs* a) {
 // arithmetic contract (f16 operands, f32 scores/softmax, P rounded to f16 for PV).
 // ----------------------------------------------------------------------------
 __global__ void attn_core_check_kernel(const __half* q, int ldq, const __half* k, int ldk, const __half* v,
-                                       int ldv, AttnParams p, int dk) {
+                                       int ldv, AttnParams p, int dk, size_t sq, size_t sk, size_t sv, size_t so) {
   extern __shared__ float sc[];  // Lk scores
   const int qi = blockIdx.x, hd = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x;
-  const __half* qr = q + ((size_t)b * p.Lq + qi) * ldq + hd * dk;
+  const __half* qr = q + (size_t)b * sq + (size_t)qi * ldq + hd * dk;
   const uint32_t* mrow = nullptr;
   if (p.mask_bits) mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + (p.mask_rows_q == 1 ? 0 : qi)) * p.mask_words;
   float mx = -CUDART_INF_F;
   for (int j = lane; j < p.Lk; j += 32) {
-    const __half* kr = k + ((size_t)b * p.Lk + j) * ldk + hd * dk;
+    const __half* kr = k + (size_t)b * sk + (size_t)j * ldk + hd * dk;
     float s = 0.f;
     for (int c = 0; c < dk; ++c) s = fmaf(__half2float(qr[c]), __half2float(kr[c]), s);
     s *= p.scale;
@@ -631,9 +638,9 @@ __global__ void attn_core_check_kernel(const __half* q, int ldq, const __half* k
   for (int c = lane; c < dk; c += 32) {
     float acc = 0.f;
     for (int j = 0; j < p.Lk; ++j)
-      acc = fmaf(sc[j], __half2float(v[((size_t)b * p.Lk + j) * ldv + hd * dk + c]), acc);
+      acc = fmaf(sc[j], __half2float(v[(size_t)b * sv + (size_t)j * ldv + hd * dk + c]), acc);
     const uint32_t pk = pack_f16x2_sat(acc / sum, 0.f);
-    p.out[((size_t)b * p.Lq + qi) * p.ldo + hd * dk + c] = __ushort_as_half((unsigned short)(pk & 0xffff));
+    p.out[(size_t)b * so + (size_t)qi * p.ldo + hd * dk + c] = __ushort_as_half((unsigned short)(pk & 0xffff));
   }
 }
 
@@ -658,9 +665,11 @@ extern "C" int mtn_check_attn_core_fwd(const MtnAttnCoreArgs* a, void* stream) {
                     1.0f / sqrtf((float)a->d_k), reinterpret_cast<__half*>(a->out), a->ldo, nullptr,
                     mtn::DropCfg{nullptr, 0, 0, 1.f}, 0};
   dim3 grid(a->Lq, a->h, a->B);
+  auto bs = [](long long given, int L, int ld) { return given > 0 ? (size_t)given : (size_t)L * ld; };
   mtn::attn_core_check_kernel<<<grid, 32, a->Lk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(a->q), a->ldq, reinterpret_cast<const __half*>(a->k), a->ldk,
-      reinterpret_cast<const __half*>(a->v), a->ldv, p, a->d_k);
+      reinterpret_cast<const __half*>(a->v), a->ldv, p, a->d_k, bs(a->q_batch_stride, a->Lq, a->ldq),
+      bs(a->k_batch_stride, a->Lk, a->ldk), bs(a->v_batch_stride, a->Lk, a->ldv), bs(a->o_batch_stride, a->Lq, a->ldo));
   MTN_CHECK_CUDA(cudaGetLastError());
   return MTN_OK;
 }

@@ -151,13 +151,27 @@ def _encode_batch(model, batch):
                   batch.query_mask, batch.fts, batch.fts_mask)
 
 
-def greedy_decode(model, batch, max_len, start_symbol, pad_symbol=None):
-    """ys = [sos]; repeat max_len-1 times: decode the whole prefix, take the argmax of the
-    last position (no EOS stop, as in the reference).  Works for any batch size (the
-    reference is batch-1; rows are independent).  The memory stage (hoisted K/V, QAE
-    branch) is computed once and reused by every step through the engine's cache."""
+def greedy_decode(model, batch, max_len, start_symbol, pad_symbol=None, cached=None):
+    """ys = [sos]; repeat max_len-1 times: decode, take the argmax of the last position (no EOS stop, as in the
+    reference).  Works for any batch size (the reference is batch-1; rows are independent).  The memory stage
+    (hoisted K/V, QAE branch) is computed once per dialogue batch.
+
+    cached=True (default where the model offers ``decode_begin`` / ``decode_step``): KV-cached decoding -- every
+    step computes ONLY the new position (self-attention over the per-layer cache, 1-row cross-attention queries);
+    cached=False: the reference's call form, the whole prefix is decoded again at every step (data_utils.py:202-210).
+    Both produce the same tokens (tests/test_gpu_model.py)."""
     his_mem, cap_mem, q_mem, vid_mem, ae_ft = _encode_batch(model, batch)
     B = batch.query.shape[0]
+    if cached is None:
+        cached = hasattr(model, "decode_begin") and getattr(model, "_fused_embed_ok", lambda: False)()
+    if cached:
+        st = model.decode_begin(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask, batch.cap_mask,
+                                batch.query_mask, ae_ft, max_len)
+        ys = torch.full((B, max_len), start_symbol, dtype=batch.query.dtype, device=batch.query.device)
+        for t in range(max_len - 1):
+            last = model.decode_step(st, ys[:, t], t)
+            ys[:, t + 1] = model.generator.argmax(last)
+        return ys
     ys = torch.full((B, 1), start_symbol, dtype=batch.query.dtype, device=batch.query.device)
     for _ in range(max_len - 1):
         out = model.decode(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask,
@@ -197,13 +211,83 @@ class _BeamPool(object):
         return False
 
 
+def beam_search_decode_batched(model, batch, max_len, start_symbol, unk_symbol, end_symbol, pad_symbol, beam=5,
+                               penalty=1.0, nbest=5, min_len=1):
+    """The reference's beam search (data_utils.py:188-242, the path generate.py:56 calls) for a batch of D dialogues
+    at once: returns a list of D results ``(nbest hypotheses [(tokens, score)], best finished score)``, each identical
+    to what the reference's batch-of-one search returns for that dialogue.
+
+    All live hypotheses of all dialogues advance in ONE KV-cached ``model.decode_step`` per position (rows ordered
+    dialogue-major, ``beam`` rows per dialogue), the generator's log-probabilities stay on the device, and ONE
+    device-to-host copy per step brings back what the selection rules can possibly use: per hypothesis the best
+    ``beam + 2`` continuations (at most ``beam`` can enter a pool of ``beam`` entries; <unk> and <eos> are skipped)
+    and the <eos> log-probability.  The pool rules themselves (grow to ``beam``, then replace the current worst,
+    first rejected candidate ends a hypothesis' expansion, data_utils.py:219-234) run on the host per dialogue."""
+    his_mem, cap_mem, q_mem, vid_mem, ae_ft = _encode_batch(model, batch)
+    ids = batch.query
+    D, dev = ids.shape[0], ids.device
+    R = int(beam)
+    st = model.decode_begin(vid_mem, his_mem, cap_mem, q_mem, batch.fts_mask, batch.his_mask, batch.cap_mask,
+                            batch.query_mask, ae_ft, max_len, rows_per_dialogue=R)
+    tokens = torch.full((D * R,), start_symbol, dtype=ids.dtype, device=dev)
+    # per dialogue: live hypotheses [(tokens, score, row of this step's batch)]
+    live = [[([], 0., d * R)] for d in range(D)]
+    finished = [[] for _ in range(D)]
+    best = [None] * D
+    K = R + 2
+    for step in range(max_len):
+        logp = model.generator(model.decode_step(st, tokens, step))             # [D*R, V] log-probabilities
+        top_v, top_i = torch.topk(logp, min(K, logp.shape[1]), dim=1)           # sorted, best first
+        pack = torch.cat([top_v, top_i.to(top_v.dtype), logp[:, end_symbol:end_symbol + 1]], dim=1).cpu().numpy()
+        kk = top_v.shape[1]
+        parents = np.arange(D * R, dtype=np.int64)
+        nxt = np.full(D * R, int(pad_symbol if pad_symbol is not None else start_symbol), dtype=np.int64)
+        for d in range(D):
+            pool = _BeamPool(R)
+            for toks, score, row in live[d]:
+                vals, idxs, lp_eos = pack[row, :kk] + score, pack[row, kk:2 * kk].astype(np.int64), pack[row, 2 * kk] + score
+                if step >= min_len:
+                    done = lp_eos + penalty * (len(toks) + 1)
+                    finished[d].append((toks, done))
+                    if best[d] is None or best[d] < done:
+                        best[d] = done
+                for v, tok in zip(vals, idxs):
+                    if tok == unk_symbol or tok == end_symbol:
+                        continue
+                    if not pool.offer((toks + [int(tok)], float(v), row)):
+                        break
+            live[d] = []
+            for j, (toks, score, parent) in enumerate(pool.entries):
+                row = d * R + j
+                parents[row], nxt[row] = parent, toks[-1]
+                live[d].append((toks, score, row))
+        if step + 1 < max_len:
+            model.decode_reorder(st, torch.from_numpy(parents).to(dev))
+            tokens = torch.from_numpy(nxt).to(dev).to(ids.dtype)
+    res = []
+    for d in range(D):
+        if finished[d]:
+            res.append((sorted(finished[d], key=lambda h: -h[1])[:nbest], best[d]))
+        else:
+            res.append(([([], 0)], None))
+    return res
+
+
 def beam_search_decode(model, batch, max_len, start_symbol, unk_symbol, end_symbol, pad_symbol, beam=5,
                        penalty=1.0, nbest=5, min_len=1):
     """Beam search with the reference's rules (data_utils.py:188-242): batch of one dialogue; each live
     hypothesis is expanded best-token-first, never with <unk> or <eos>; from step ``min_len`` on every live
     hypothesis also contributes a finished candidate scored ``logp[eos] + penalty * (len + 1)``; the n-best
-    finished candidates and the best finished score are returned.  Every ``model.decode`` call after the
-    first reuses the engine's cached memory stage (hoisted K/V, QAE branch)."""
+    finished candidates and the best finished score are returned.
+
+    On the CUDA model this is ``beam_search_decode_batched`` for D = 1 (all hypotheses in one KV-cached step, one
+    D2H per position).  A model without ``decode_begin`` (or MTN_B200_BEAM_SERIAL=1) takes the reference's own call
+    form below: one ``model.decode`` of the whole prefix per hypothesis per step."""
+    import os
+    if (hasattr(model, "decode_begin") and getattr(model, "_fused_embed_ok", lambda: False)() and
+            os.environ.get("MTN_B200_BEAM_SERIAL") != "1" and batch.query.shape[0] == 1):
+        return beam_search_decode_batched(model, batch, max_len, start_symbol, unk_symbol, end_symbol, pad_symbol, beam,
+                                          penalty, nbest, min_len)[0]
     his_mem, cap_mem, q_mem, vid_mem, ae_ft = _encode_batch(model, batch)
     ids = batch.query
 

@@ -406,13 +406,10 @@ class DecoderEngine(object):
         S["_keep"] = mods
         return S
 
-    # ------------------------------------------------------------------ forward
-    def forward(self, vid_ft, vid_mask, x, his, his_mask, cap, cap_mask, qm, q_mask, tgt_mask, ae_ft,
-                ae_features):
-        W = self.weights()
-        d, N, M = W["d"], W["N"], W["M"]
-        B, T, _ = x.shape
-        dev = x.device
+    # ------------------------------------------------------------------ memory stage, cached by tensor identity
+    def memory(self, W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask, ae_ft, ae_features):
+        """(S, fresh): the memory stage of this memory set -- computed now (fresh: its side streams are still running;
+        the caller waits on S["ev"] / joins S["side"]) or found cached from an earlier call with the same tensors."""
         key = _MemoryKey(self._packed._key, ae_features,
                          list(vid_ft) + list(vid_mask) + [his, his_mask, cap, cap_mask, qm, q_mask] +
                          (list(ae_ft) if isinstance(ae_ft, (list, tuple)) else [ae_ft]))
@@ -422,7 +419,98 @@ class DecoderEngine(object):
             self._mem = self._memory_stage(W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask,
                                            ae_ft, ae_features)
             self._mem_key = key
-        S = self._mem
+        return self._mem, fresh
+
+    @staticmethod
+    def _site_order(ae_features):
+        return (("src", "kv_q", "bits_q", "Q"), ("cap", "kv_cap", "bits_cap", "C")) \
+            if ae_features in ("caption", "summary") else \
+            (("cap", "kv_cap", "bits_cap", "C"), ("src", "kv_q", "bits_q", "Q"))
+
+    # ------------------------------------------------------------------ KV-cached, last-token-only decoding
+    def decode_begin(self, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask, ae_ft, ae_features, max_len,
+                     rows_per_dialogue=1):
+        """Start incremental decoding of one dialogue batch (reference call form data_utils.py:202-210
+        without its full-prefix recompute): runs (or finds cached) the memory stage and allocates, per layer, the
+        self-attention cache [B, max_len, 3d] f16 that holds the [Q|K|V] projection of every target position seen so
+        far.  Exact by SURVEY 8a invariant (ii): row t of a full-prefix decode only depends on rows <= t.
+        rows_per_dialogue = R > 1 (beam search): R hypotheses per dialogue decode in lockstep; target rows are ordered
+        dialogue-major (row = dialogue * R + hypothesis).  Self-attention caches are per hypothesis; the cross sites
+        treat the R hypotheses of a dialogue as R query rows of ONE batch element, so the memory stage (hoisted K/V,
+        QAE branch) is computed and stored once per dialogue, not per hypothesis."""
+        W = self.weights()
+        d, N = W["d"], W["N"]
+        R = int(rows_per_dialogue)
+        B = qm.shape[0] * R
+        S, fresh = self.memory(W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask, ae_ft, ae_features)
+        main = torch.cuda.current_stream()
+        if fresh:                                            # the per-step path has no event waits: join here
+            for st in S["side"]:
+                main.wait_stream(st)
+        dev = qm.device
+        f16 = torch.float16
+        dff = W["layers"][0]["ffn"]["w_1"].shape[0]
+        return {"S": S, "W": W, "B": B, "R": R, "t": 0, "max_len": int(max_len), "ae_features": ae_features,
+                "cache": [torch.zeros(B, int(max_len), 3 * d, dtype=f16, device=dev) for _ in range(N)],
+                "xs": torch.empty(B, d, dtype=torch.float32, device=dev), "xn16": torch.empty(B, d, dtype=f16, device=dev),
+                "q": torch.empty(B, d, dtype=f16, device=dev), "obuf": torch.empty(B, d, dtype=f16, device=dev),
+                "hid": torch.empty(B, dff, dtype=f16, device=dev), "out": torch.empty(B, d, dtype=torch.float32, device=dev)}
+
+    def decode_step(self, st, x_t, t=None):
+        """One target position for every dialogue of the batch: x_t [B, d] f32 = embedding (+ positional encoding) of the
+        token at position t (default: the next one).  Returns the decoder output row [B, d] (final LayerNorm applied;
+        a buffer of `st`, overwritten by the next step).  Per layer: LayerNorm -> [Q|K|V] projection of the ONE new row
+        straight into the cache -> attention of that row over cache rows 0..t (no mask needed: every cached key is in
+        the causal past) -> output projection + residual; then the cross sites with a 1-row query over the hoisted
+        K/V of the memory stage; then the FFN.  M = B rows per GEMM instead of B*(t+1)."""
+        S, W, B, R = st["S"], st["W"], st["B"], st["R"]
+        D = B // R                                           # dialogues; the cross sites see [D, R] query rows
+        d, N, M = W["d"], W["N"], W["M"]
+        t = st["t"] if t is None else int(t)
+        assert 0 <= t < st["max_len"], "decode_step: position %d outside the cache (max_len %d)" % (t, st["max_len"])
+        xs, xn16, qb, obuf, hid = st["xs"], st["xn16"], st["q"], st["obuf"], st["hid"]
+        xs.copy_(x_t.reshape(B, d))
+        order = self._site_order(st["ae_features"])
+        for l in range(N):
+            Lw = W["layers"][l]
+            A = Lw["self"]
+            cache = st["cache"][l]
+            row = cache[:, t]                                            # [B, 3d], row stride max_len * 3d
+            _ln_linear(xs, Lw["ln"][0], A["w_qkv"], A["b_qkv"], _lib.ACT_NONE, xn16, row)
+            _lib.attn_core(cache[:, t:t + 1, :d], cache[:, :, d:2 * d], cache[:, :, 2 * d:], B, A["h"], 1, t + 1, A["d_k"],
+                           obuf, mask_bits=None)
+            _lib.linear(obuf, A["w_o"], A["b_o"], addend=xs, out_f32=xs)
+            kc, vc = l * 2 * d, l * 2 * d + d
+            A = Lw["his"]
+            self._attn_block(xs, Lw["ln"][1], A, D, R, S["H"], A["w_qkv"][:d], A["b_qkv"][:d], S["kv_his"], kc, vc,
+                             S["bits_his"], xn16, qb, obuf)
+            for c, (name, kvn, bn, Ln) in enumerate(order):
+                A = Lw[name]
+                self._attn_block(xs, Lw["ln"][2 + c], A, D, R, S[Ln], A["w_qkv"][:d], A["b_qkv"][:d], S[kvn], kc, vc,
+                                 S[bn], xn16, qb, obuf)
+            for i in range(M):
+                A = Lw["ae_attn"][i]
+                self._attn_block(xs, Lw["ln"][7 + 4 * i], A, D, R, S["La"], A["w_qkv"][:d], A["b_qkv"][:d],
+                                 S["kv_ae"][l][i], 0, d, S["bits_ae"], xn16, qb, obuf)
+            self._ffn_block(xs, Lw["ln"][4 + 4 * M], Lw["ffn"], xn16, hid)
+        _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=st["out"])   # mtn.py:164
+        st["t"] = t + 1
+        return st["out"]
+
+    @staticmethod
+    def decode_reorder(st, parents):
+        """Beam search: target row i continues the hypothesis that was row parents[i] (int64 [B], device) -- gathers
+        the self-attention caches accordingly (the cross-attention side has no per-hypothesis state)."""
+        st["cache"] = [c.index_select(0, parents) for c in st["cache"]]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, vid_ft, vid_mask, x, his, his_mask, cap, cap_mask, qm, q_mask, tgt_mask, ae_ft,
+                ae_features):
+        W = self.weights()
+        d, N, M = W["d"], W["N"], W["M"]
+        B, T, _ = x.shape
+        dev = x.device
+        S, fresh = self.memory(W, vid_ft, vid_mask, his, his_mask, cap, cap_mask, qm, q_mask, ae_ft, ae_features)
         main = torch.cuda.current_stream()
 
         rows = B * T
@@ -439,9 +527,7 @@ class DecoderEngine(object):
         bits_t = _lib.mask_pack(tm) if tm is not None else None
         if bits_t is not None:
             _tap("bits_t", bits_t)
-        order = (("src", "kv_q", "bits_q", "Q"), ("cap", "kv_cap", "bits_cap", "C")) \
-            if ae_features in ("caption", "summary") else \
-            (("cap", "kv_cap", "bits_cap", "C"), ("src", "kv_q", "bits_q", "Q"))
+        order = self._site_order(ae_features)
         _tap("embed.x", xs)
         for l in range(N):
             Lw = W["layers"][l]

@@ -66,9 +66,11 @@ class GraphedGreedyDecoder(object):
     Inputs: dict with int64 ``query, his, cap`` (B, L) and ``fts`` [(B, Lv, F) f32] on the GPU.
     """
 
-    def __init__(self, model, inputs, max_len, sos=2, pad=1):
+    def __init__(self, model, inputs, max_len, sos=2, pad=1, cached=True):
+        """cached=True: KV-cached steps (only the new position is computed; ``model.decode_begin`` / ``decode_step``);
+        cached=False: every step decodes the whole prefix again (the reference's call form)."""
         from .data_utils import subsequent_mask
-        self.model, self.max_len = model, max_len
+        self.model, self.max_len, self.cached = model, max_len, cached
         dev = inputs["query"].device
         self.static = {k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v]) for k, v in inputs.items()}
         B = inputs["query"].shape[0]
@@ -86,11 +88,18 @@ class GraphedGreedyDecoder(object):
             b = Batch(st["query"], st["his"], None, [f.permute(1, 0, 2) for f in st["fts"]], st["cap"], None, None, pad)
             self.b = b
             self.mem = model.encode(b.query, b.query_mask, b.his, b.his_mask, b.cap, b.cap_mask, b.fts, b.fts_mask)
+            if cached:
+                q, vid, cap, his, ae = self.mem
+                self.state = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae,
+                                                max_len)
             step(1)
 
-        def step(t):
+        def step(t):      # produces ys[:, t] from the prefix ys[:, :t]
             q, vid, cap, his, ae = self.mem
             b = self.b
+            if cached:
+                self.ys[:, t] = model.generator.argmax(model.decode_step(self.state, self.ys[:, t - 1], t - 1))
+                return
             out = model.decode(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask,
                                self.ys[:, :t], masks[t], ae)
             self.ys[:, t] = model.generator.argmax(out[0][:, -1])

@@ -581,6 +581,33 @@ class EncoderDecoder(nn.Module):
                             auto_encoded_ft, self.auto_encoder_ft)
 
 
+    # ---- KV-cached, last-token-only decoding (extension of the reference API) ----------------
+    def decode_begin(self, encoded_vid_features, his_memory, cap_memory, query_memory, vid_features_mask,
+                     his_mask, cap_mask, query_mask, auto_encoded_ft, max_len, rows_per_dialogue=1):
+        """Same memories / masks as ``decode`` (data_utils.py:202-210), no target yet: returns the incremental
+        decoding state (memory stage + per-layer self-attention caches for ``max_len`` positions).
+        rows_per_dialogue > 1: that many hypotheses per dialogue (beam search), rows ordered dialogue-major."""
+        ensure_inference(self, query_memory)
+        return self.decoder.engine.decode_begin(encoded_vid_features, vid_features_mask, his_memory, his_mask,
+                                                cap_memory, cap_mask, query_memory, query_mask, auto_encoded_ft,
+                                                self.auto_encoder_ft, max_len, rows_per_dialogue)
+
+    def decode_reorder(self, state, parents):
+        """Beam search bookkeeping: row i of the next step continues the hypothesis of row parents[i]."""
+        self.decoder.engine.decode_reorder(state, parents)
+
+    def decode_step(self, state, tokens, t=None):
+        """tokens: [B] int64 = the target token at position t (default: the next position of ``state``).  Returns the
+        decoder output row of that position, [B, d] -- equal to ``decode(..., ys[:, :t+1], ...)[0][:, -1]`` of the
+        full-prefix form (the causal mask makes row t independent of later rows; SURVEY 8a invariant ii)."""
+        t = state["t"] if t is None else int(t)
+        emb, pos = self.tgt_embed[0], self.tgt_embed[1]
+        B = tokens.shape[0]
+        x = torch.empty(B, 1, emb.d_model, dtype=torch.float32, device=tokens.device)
+        _lib.embed(tokens.reshape(B, 1), emb.lut.weight.data, pos.pe[0][t:], math.sqrt(emb.d_model), out_f32=x)
+        return self.decoder.engine.decode_step(state, x, t)
+
+
 def make_model(src_vocab, tgt_vocab, N=6, d_model=512, d_ff=2048, h=8, dropout=0.1,
                separate_his_embed=False, separate_cap_embed=False, ft_sizes=None, diff_encoder=False,
                diff_embed=False, diff_gen=False, auto_encoder_ft=None, auto_encoder_attn=False):

@@ -27,8 +27,18 @@ import torch
 _REF = None
 
 
-def ref_dir():
-    for cand in (os.environ.get("MTN_REF_DIR"), "/root/reference"):
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ref_dir(allow_build_container_path=True):
+    """SURVEY 8c lookup order: $MTN_REF_DIR -> /root/reference (the build container only; bench.py passes
+    allow_build_container_path=False because nothing it runs on the GPU box may read that path) -> baseline/_ref/
+    (a driver-installed copy that travels with the repo snapshot)."""
+    cands = [os.environ.get("MTN_REF_DIR")]
+    if allow_build_container_path:
+        cands.append("/root/reference")
+    cands.append(os.path.join(_REPO, "baseline", "_ref"))
+    for cand in cands:
         if cand and os.path.isfile(os.path.join(cand, "mtn.py")):
             return cand
     return None
@@ -38,12 +48,12 @@ def available():
     return ref_dir() is not None
 
 
-def load():
-    """Return (mtn, data_utils) modules of the reference."""
+def load(d=None):
+    """Return (mtn, data_utils) modules of the reference (from `d`, default: ref_dir())."""
     global _REF
     if _REF is not None:
         return _REF
-    d = ref_dir()
+    d = d or ref_dir()
     if d is None:
         raise RuntimeError("reference checkout not found (set MTN_REF_DIR)")
     if "torchtext" not in sys.modules:

@@ -302,6 +302,33 @@ def test_attn_core_many_items(L, B, h, Lq, Lk, dk, kind):
     assert errs[worst] < 1e-3, (worst, errs[worst])
 
 
+@pytest.mark.parametrize("B,h,t,Tmax,dk", [(64, 8, 0, 20, 64), (64, 8, 11, 20, 64), (5, 8, 19, 20, 64), (7, 4, 130, 160, 32)])
+def test_attn_core_kv_cache_layout(L, B, h, t, Tmax, dk):
+    """KV-cached decoding (ABI v5 batch strides): q = row t of a [B, Tmax, 3d] cache (Lq = 1), k / v = its first t + 1
+    rows, no mask; rows > t of the cache hold NaN poison and must not be read."""
+    g = torch.Generator().manual_seed(B * 100 + t)
+    d = h * dk
+    qkv = torch.randn(B, Tmax, 3 * d, generator=g).half()
+    ref = _attn_ref(qkv[:, t:t + 1, :d].contiguous(), qkv[:, :t + 1, d:2 * d].contiguous(),
+                    qkv[:, :t + 1, 2 * d:].contiguous(), None, h, dk)
+    cache = dev(qkv).clone()
+    cache[:, t + 1:] = float("nan")
+    out = torch.full((B, d), float("nan"), device="cuda", dtype=torch.float16)
+    chk = torch.full((B, d), float("nan"), device="cuda", dtype=torch.float16)
+    args = (cache[:, t:t + 1, :d], cache[:, :, d:2 * d], cache[:, :, 2 * d:], B, h, 1, t + 1, dk)
+    L.attn_core(*args, chk, _check_kernel=True)
+    L.attn_core(*args, out)
+    torch.cuda.synchronize()
+    o, c = out.float().cpu().view(B, 1, d), chk.float().cpu().view(B, 1, d)
+    assert torch.isfinite(o).all()
+    assert G.rel_err(c, ref) < 1e-3 and G.rel_err(o, ref) < 1e-3, (G.rel_err(c, ref), G.rel_err(o, ref))
+    # strided output too: the row lands inside a [B, Tmax, d] buffer
+    obuf = torch.zeros(B, Tmax, d, device="cuda", dtype=torch.float16)
+    L.attn_core(*args, obuf[:, t:t + 1])
+    torch.cuda.synchronize()
+    assert torch.equal(obuf[:, t], out) and float(obuf.float().abs().sum() - out.float().abs().sum()) == 0.0
+
+
 def test_attn_kat(L):
     """SURVEY 8c known answers, embedded in a d_k=32 head (extra dims zero)."""
     z = G.load("kat.npz")

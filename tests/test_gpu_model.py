@@ -280,6 +280,84 @@ def test_cfg4_decode_graphs_token_exact(M, cfg2_model):
         invalidate_weight_caches()
 
 
+def test_kv_cached_decode_equals_full_prefix(M, cfg2_model):
+    """SURVEY 8f row f3 / 8a invariant (ii): the KV-cached, last-token-only step produces the row the full-prefix
+    decode produces (f32 reduction-order noise only), and cached greedy decoding generates the same tokens as the
+    reference's full-recompute call form -- eager and as CUDA graphs."""
+    mtn, du = M
+    from mtn_b200.graph import GraphedGreedyDecoder
+    from mtn_b200.engine import invalidate_weight_caches
+    cfg, model = cfg2_model
+    w0 = model.generator.proj.weight.data.clone()
+    model.generator.proj.weight.data.mul_(8.0)
+    invalidate_weight_caches()
+    try:
+        B, T = 12, 20
+        inp = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=T, Lv=[512, 256], seed=91)
+        b = make_batch(du, inp)
+        with torch.no_grad():
+            q, vid, cap, his, ae = model.encode(b.query, b.query_mask, b.his, b.his_mask, b.cap, b.cap_mask, b.fts, b.fts_mask)
+            causal = du.subsequent_mask(T, b.trg.device)           # greedy decoding's mask: no target padding
+            full = model.decode(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, b.trg, causal, ae)[0]
+            st = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae, T)
+            errs = []
+            for t in range(T):
+                row = model.decode_step(st, b.trg[:, t])
+                errs.append(G.rel_err(row.cpu(), full[:, t].cpu()))
+        print("KV-cached rows vs full-prefix decode, worst position: %.2e" % max(errs))
+        assert max(errs) < 2e-4, errs
+        d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
+             if k in ("query", "his", "cap", "fts")}
+        bd = du.Batch(d["query"], d["his"], None, [f.permute(1, 0, 2) for f in d["fts"]], d["cap"], None, None, 1)
+        with torch.no_grad():
+            y_full = du.greedy_decode(model, bd, T, 2, cached=False)
+            y_kv = du.greedy_decode(model, bd, T, 2, cached=True)
+        y_g = GraphedGreedyDecoder(model, d, T, cached=True).decode().clone()
+        y_gf = GraphedGreedyDecoder(model, d, T, cached=False).decode().clone()
+        torch.cuda.synchronize()
+        assert torch.equal(y_full, y_gf)
+        assert torch.equal(y_kv, y_g)
+        nbad = int((y_full != y_kv).any(1).sum())
+        print("greedy tokens, cached vs full recompute: %d of %d sequences differ" % (nbad, B))
+        assert nbad == 0
+    finally:
+        model.generator.proj.weight.data.copy_(w0)
+        invalidate_weight_caches()
+
+
+def test_batched_beam_search_on_the_kernels(M, cfg2_model, monkeypatch):
+    """generate.py's path (data_utils.py:188-242): the batched, KV-cached beam search over 3 dialogues returns, per
+    dialogue, the hypotheses of the serial search in the reference's call form (one full-prefix ``model.decode`` per
+    hypothesis per step) -- same token lists, scores to f16-operand noise."""
+    mtn, du = M
+    from mtn_b200.engine import invalidate_weight_caches
+    cfg, model = cfg2_model
+    w0 = model.generator.proj.weight.data.clone()
+    model.generator.proj.weight.data.mul_(8.0)
+    invalidate_weight_caches()
+    try:
+        D, steps = 3, 8
+        inp = O.synth_inputs(cfg, B=D, Q=64, C=64, H=256, T=4, Lv=[512, 256], seed=313)
+        d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
+             if k in ("query", "his", "cap", "fts")}
+        mk = lambda sl: du.Batch(d["query"][sl], d["his"][sl], None, [f[sl].permute(1, 0, 2) for f in d["fts"]],
+                                 d["cap"][sl], None, None, 1)
+        with torch.no_grad():
+            got = du.beam_search_decode_batched(model, mk(slice(0, D)), steps, 2, 0, 3, 1, beam=5, penalty=1.0, nbest=5)
+            monkeypatch.setenv("MTN_B200_BEAM_SERIAL", "1")
+            for i in range(D):
+                ref = du.beam_search_decode(model, mk(slice(i, i + 1)), steps, 2, 0, 3, 1, beam=5, penalty=1.0, nbest=5)
+                assert [list(map(int, h)) for h, _ in ref[0]] == [list(map(int, h)) for h, _ in got[i][0]], i
+                assert np.allclose([s for _, s in ref[0]], [s for _, s in got[i][0]], rtol=0, atol=5e-3)
+                assert abs(ref[1] - got[i][1]) < 5e-3
+            monkeypatch.delenv("MTN_B200_BEAM_SERIAL")
+            one = du.beam_search_decode(model, mk(slice(1, 2)), steps, 2, 0, 3, 1, beam=5, penalty=1.0, nbest=5)
+            assert [list(map(int, h)) for h, _ in one[0]] == [list(map(int, h)) for h, _ in got[1][0]]
+    finally:
+        model.generator.proj.weight.data.copy_(w0)
+        invalidate_weight_caches()
+
+
 def test_cfg4_decoder_instances_agree_at_batch_64(M, cfg2_model):
     """BASELINE configs[3] at its full batch (64 dialogues, 20 tokens): two GraphedGreedyDecoder instances captured
     from the same model must produce the same tokens on the same input, the same as the eager decoder, and -- with

@@ -152,6 +152,71 @@ def test_beam_search_matches_reference_rules():
         assert np.isclose(ref[1], mine[1])
 
 
+class FakeModelD(FakeModel):
+    """FakeModel whose distribution also depends on a dialogue number (batch-of-one protocol)."""
+
+    def __init__(self, dialogue):
+        self.dialogue = dialogue
+
+    def decode(self, vid, his, cap, q, fm, hm, cm, qm, tgt, tgt_mask, ae):
+        g = torch.Generator().manual_seed(int((tgt[0] * torch.arange(1, tgt.shape[1] + 1)).sum()) + 7919 * self.dialogue)
+        return (torch.randn(tgt.shape[0], tgt.shape[1], self.V, generator=g), [])
+
+
+class FakeCachedModel(FakeModel):
+    """The same distributions behind the incremental protocol (decode_begin / decode_step / decode_reorder): D dialogues
+    x R hypotheses in lockstep, rows dialogue-major -- what beam_search_decode_batched drives on the CUDA model."""
+
+    def _fused_embed_ok(self):
+        return True
+
+    def decode_begin(self, vid, his, cap, q, fm, hm, cm, qm, ae, max_len, rows_per_dialogue=1):
+        return {"hist": torch.zeros(self.D * rows_per_dialogue, max_len, dtype=torch.long), "R": rows_per_dialogue, "calls": 0}
+
+    def decode_step(self, st, tokens, t=None):
+        st["hist"][:, t] = tokens
+        st["calls"] += 1
+        rows = []
+        for r in range(st["hist"].shape[0]):
+            m = FakeModelD(r // st["R"])
+            rows.append(m.decode(*[None] * 8, st["hist"][r:r + 1, :t + 1], None, None)[0][:, -1])
+        return torch.cat(rows, 0)
+
+    def decode_reorder(self, st, parents):
+        st["hist"] = st["hist"][parents]
+
+
+def test_batched_beam_search_equals_the_reference_per_dialogue():
+    """all live hypotheses of several dialogues in one step, one host round trip per position --
+    hypotheses and scores identical to the reference's batch-of-one search run per dialogue."""
+    import ref_loader
+    D = 3
+    m = FakeCachedModel()
+    m.D = D
+
+    class B3(FakeBatch):
+        query = torch.zeros(D, 3, dtype=torch.long)
+    got = data_utils.beam_search_decode_batched(m, B3(), 7, 2, 0, 3, 1, beam=3, penalty=1.0, nbest=3)
+    assert len(got) == D
+    for d in range(D):
+        # this repo's own serial search (the reference's call form) on the dialogue alone
+        mine = data_utils.beam_search_decode(FakeModelD(d), FakeBatch(), 7, 2, 0, 3, 1, beam=3, penalty=1.0, nbest=3)
+        assert [list(map(int, h)) for h, _ in mine[0]] == [list(map(int, h)) for h, _ in got[d][0]]
+        assert np.allclose([s for _, s in mine[0]], [s for _, s in got[d][0]], rtol=0, atol=1e-6)
+        assert np.isclose(mine[1], got[d][1])
+        if ref_loader.available():
+            warnings.simplefilter("ignore")
+            _, ref_du = ref_loader.load()
+            ref = ref_du.beam_search_decode(FakeModelD(d), FakeBatch(), 7, 2, 0, 3, 1, beam=3, penalty=1.0, nbest=3)
+            assert [list(map(int, h)) for h, _ in ref[0]] == [list(map(int, h)) for h, _ in got[d][0]]
+            assert np.allclose([s for _, s in ref[0]], [s for _, s in got[d][0]], rtol=0, atol=1e-6)
+            assert np.isclose(ref[1], got[d][1])
+    # a batch of one through the reference signature takes the batched path on a model with the incremental protocol
+    m1 = FakeCachedModel(); m1.D = 1
+    one = data_utils.beam_search_decode(m1, FakeBatch(), 7, 2, 0, 3, 1, beam=3, penalty=1.0, nbest=3)
+    assert [list(map(int, h)) for h, _ in one[0]] == [list(map(int, h)) for h, _ in got[0][0]]
+
+
 def test_greedy_decode_semantics():
     ys = data_utils.greedy_decode(FakeModel(), FakeBatch(), 5, 2)
     assert ys.shape == (1, 5) and int(ys[0, 0]) == 2
