@@ -238,6 +238,26 @@ typedef struct MtnAttnSiteArgs {
 size_t mtn_attn_site_workspace_bytes(int B, int Lq, int Lk, int d);
 int mtn_attn_site_fwd(const MtnAttnSiteArgs *args, void *stream);
 
+/* ---- one attention site, ONE kernel (hoisted K/V) ----------------------------------
+ * The same sublayer as mtn_attn_site_fwd for a site whose K / V projections already exist (static memories: `kv`),
+ * taking xn = LayerNorm(x) in f16 (mtn_layernorm_fwd) and updating the f32 residual stream IN PLACE:
+ *     x += Wo . concat_h softmax(mask((xn Wq_h^T + bq_h) K_h^T / sqrt(d_k))) V_h + bo
+ * One launch: a cluster of two CTAs per (batch element, 128-query tile) keeps the Q projection, the attention and the
+ * output projection on chip (csrc/site_fused.cu); the two CTAs exchange their heads' outputs through distributed
+ * shared memory.  d_k = 64 with d in {256, 512} (mtn_attn_site_fused_supported); other shapes: mtn_attn_site_fwd.
+ * ld_wq / ld_wo: row pitch of the weights in elements (0 = d), so w_q may be the first d rows of a [3d, d] pack. */
+typedef struct MtnAttnSiteFusedArgs {
+  int B, Lq, Lk, d, h;
+  const void *xn_f16; int ld_xn;            /* [B*Lq, d] f16 */
+  float *x; int ld_x;                       /* [B*Lq, d] f32, updated in place */
+  const void *w_q; int ld_wq; const float *b_q;
+  const void *w_o; int ld_wo; const float *b_o;
+  const void *kv; int ld_kv, kv_k_col, kv_v_col;   /* f16 [B*Lk, ld_kv]; K at column kv_k_col, V at kv_v_col */
+  const uint32_t *mask_bits; int mask_rows_q;
+} MtnAttnSiteFusedArgs;
+int mtn_attn_site_fused_supported(int d, int h);
+int mtn_attn_site_fused_fwd(const MtnAttnSiteFusedArgs *args, void *stream);
+
 /* ---- feed-forward sublayer -----------------------------------------------------
  * Replaces  SublayerConnection.forward(x, PositionwiseFeedForward)  (mtn.py:125-127
  * around mtn.py:279-280):   x_out = x + W2 relu(W1 LN(x) + b1) + b2

@@ -118,6 +118,15 @@ class AttnSiteArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class AttnSiteFusedArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("d", C.c_int), ("h", C.c_int),
+                ("xn_f16", C.c_void_p), ("ld_xn", C.c_int), ("x", C.c_void_p), ("ld_x", C.c_int),
+                ("w_q", C.c_void_p), ("ld_wq", C.c_int), ("b_q", C.c_void_p),
+                ("w_o", C.c_void_p), ("ld_wo", C.c_int), ("b_o", C.c_void_p),
+                ("kv", C.c_void_p), ("ld_kv", C.c_int), ("kv_k_col", C.c_int), ("kv_v_col", C.c_int),
+                ("mask_bits", C.c_void_p), ("mask_rows_q", C.c_int)]
+
+
 class FfnArgs(C.Structure):
     _fields_ = [("rows", C.c_int), ("d", C.c_int), ("d_ff", C.c_int),
                 ("x", C.c_void_p), ("x_out", C.c_void_p),
@@ -155,6 +164,8 @@ SYMBOLS = {
     "mtn_attn_core_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
     "mtn_attn_site_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "mtn_attn_site_fwd": (C.c_int, [C.POINTER(AttnSiteArgs), C.c_void_p]),
+    "mtn_attn_site_fused_supported": (C.c_int, [C.c_int, C.c_int]),
+    "mtn_attn_site_fused_fwd": (C.c_int, [C.POINTER(AttnSiteFusedArgs), C.c_void_p]),
     "mtn_ffn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "mtn_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), C.c_void_p]),
     "mtn_check_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
@@ -417,6 +428,37 @@ def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=Fal
     fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
     _launch("attn_core", 4 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (2 * Lq + 2 * Lk),
             lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits, stats, drop))
+
+
+def attn_site_fused_supported(d, h):
+    return bool(lib().mtn_attn_site_fused_supported(int(d), int(h)))
+
+
+def attn_site_fused(xn16, x, w_q, b_q, w_o, b_o, kv, k_col, v_col, B, h, Lq, Lk, mask_bits=None):
+    """x [B*Lq, d] f32 += Wo . attention(xn16 Wq^T + bq, K, V) + bo in ONE launch (csrc/site_fused.cu).
+    xn16: [B*Lq, d] f16 = LayerNorm(x); kv: f16 [B*Lk, ld] with K at columns [k_col, k_col+d), V at [v_col, v_col+d);
+    w_q / w_o: [d, d] f16 (row stride allowed); mask_bits: output of mask_pack or None."""
+    for t, n in ((xn16, "xn16"), (w_q, "w_q"), (w_o, "w_o"), (kv, "kv")):
+        _req(t, torch.float16, n)
+        assert t.dim() == 2
+    _req(x, torch.float32, "x"); _req(b_q, torch.float32, "b_q"); _req(b_o, torch.float32, "b_o")
+    d = x.shape[1]
+    assert x.dim() == 2 and x.shape[0] == B * Lq and tuple(xn16.shape) == (B * Lq, d) and kv.shape[0] == B * Lk
+    assert tuple(w_q.shape) == (d, d) and tuple(w_o.shape) == (d, d) and b_q.numel() == d and b_o.numel() == d
+    a = AttnSiteFusedArgs()
+    a.B, a.Lq, a.Lk, a.d, a.h = B, Lq, Lk, d, h
+    a.xn_f16, a.ld_xn, a.x, a.ld_x = xn16.data_ptr(), xn16.stride(0), x.data_ptr(), x.stride(0)
+    a.w_q, a.ld_wq, a.b_q = w_q.data_ptr(), w_q.stride(0), b_q.data_ptr()
+    a.w_o, a.ld_wo, a.b_o = w_o.data_ptr(), w_o.stride(0), b_o.data_ptr()
+    a.kv, a.ld_kv, a.kv_k_col, a.kv_v_col = kv.data_ptr(), kv.stride(0), int(k_col), int(v_col)
+    if mask_bits is not None:
+        assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == B
+        assert mask_bits.shape[2] == mask_words(Lk)
+        a.mask_bits, a.mask_rows_q = mask_bits.data_ptr(), mask_bits.shape[1]
+    rows = B * Lq
+    _launch("attn_site_fused", 4 * rows * d * d + 4 * B * Lq * Lk * d, rows * d * (2 + 8) + 2 * B * Lk * 2 * d + 4 * d * d,
+            lambda: lib().mtn_attn_site_fused_fwd(C.byref(a), stream_ptr()),
+            keep=(xn16, x, w_q, b_q, w_o, b_o, kv, mask_bits))
 
 
 def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None, drop=None):

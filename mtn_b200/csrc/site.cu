@@ -58,20 +58,49 @@ extern "C" int mtn_attn_site_fwd(const MtnAttnSiteArgs* a, void* stream) {
               "attn_site: workspace of %zu bytes too small (need %zu)", a->workspace_bytes,
               mtn_attn_site_workspace_bytes(a->B, a->Lq, Lk, d));
 
-  int rc = mtn_layernorm_fwd(a->x, a->ln_a, a->ln_b, a->ln_eps, (int)rq, d, nullptr, xn, stream);
-  if (rc) return rc;
+  // Cross site with its own (not hoisted) memory: the K/V projection of the memory does not depend on x, so it runs on
+  // an internal side stream CONCURRENTLY with LayerNorm + Q projection (fork / join by events: stream-ordered for the
+  // caller and legal inside CUDA-graph capture) -- it is half of the site's FLOPs and used to sit in front of the core.
+  const bool own_kv = !self && a->kv == nullptr;
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t main_st = static_cast<cudaStream_t>(stream);
+  if (own_kv) {
+    MTN_REQUIRE(a->w_kv != nullptr && a->mem_f16 != nullptr, MTN_E_ARG, "attn_site: w_kv / mem_f16 is NULL for a non-hoisted cross site");
+    if (side == nullptr) {
+      MTN_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      MTN_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      MTN_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    MTN_CHECK_CUDA(cudaEventRecord(ev_fork, main_st));
+    MTN_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    MtnLinearArgs kvl = {};
+    kvl.A = a->mem_f16; kvl.lda = d; kvl.W = a->w_kv; kvl.ldw = d; kvl.bias = a->b_kv;
+    kvl.M = (int)rk; kvl.N = 2 * d; kvl.K = d; kvl.act = MTN_ACT_NONE;
+    kvl.out_f16 = kvbuf; kvl.ld16 = 2 * d;
+    int rck = mtn_linear_fwd(&kvl, side);
+    MTN_CHECK_CUDA(cudaEventRecord(ev_join, side));     // always joined, also on error, so capture stays well-formed
+    if (rck) {
+      cudaStreamWaitEvent(main_st, ev_join, 0);
+      return rck;
+    }
+  }
 
-  MtnLinearArgs lin = {};
-  lin.A = xn; lin.lda = d; lin.W = a->w_q; lin.ldw = d; lin.bias = a->b_q;
-  lin.M = (int)rq; lin.N = self ? 3 * d : d; lin.K = d; lin.act = MTN_ACT_NONE;
-  lin.out_f16 = qbuf; lin.ld16 = lin.N;
-  rc = mtn_linear_fwd(&lin, stream);
+  int rc = mtn_layernorm_fwd(a->x, a->ln_a, a->ln_b, a->ln_eps, (int)rq, d, nullptr, xn, stream);
+  if (rc == 0) {
+    MtnLinearArgs lin0 = {};
+    lin0.A = xn; lin0.lda = d; lin0.W = a->w_q; lin0.ldw = d; lin0.bias = a->b_q;
+    lin0.M = (int)rq; lin0.N = self ? 3 * d : d; lin0.K = d; lin0.act = MTN_ACT_NONE;
+    lin0.out_f16 = qbuf; lin0.ld16 = lin0.N;
+    rc = mtn_linear_fwd(&lin0, stream);
+  }
+  if (own_kv) MTN_CHECK_CUDA(cudaStreamWaitEvent(main_st, ev_join, 0));
   if (rc) return rc;
 
   MtnAttnCoreArgs core = {};
   core.B = a->B; core.h = a->h; core.Lq = a->Lq; core.Lk = Lk; core.d_k = dk;
   core.mask_bits = a->mask_bits; core.mask_rows_q = a->mask_rows_q;
-  core.q = qbuf; core.ldq = lin.N;
+  core.q = qbuf; core.ldq = self ? 3 * d : d;
   core.out = obuf; core.ldo = d;
   if (self) {
     core.k = static_cast<const uint8_t*>(qbuf) + (size_t)d * 2; core.ldk = 3 * d;
@@ -80,13 +109,6 @@ extern "C" int mtn_attn_site_fwd(const MtnAttnSiteArgs* a, void* stream) {
     core.k = static_cast<const uint8_t*>(a->kv) + (size_t)a->kv_k_col * 2; core.ldk = a->ld_kv;
     core.v = static_cast<const uint8_t*>(a->kv) + (size_t)a->kv_v_col * 2; core.ldv = a->ld_kv;
   } else {
-    MTN_REQUIRE(a->w_kv != nullptr, MTN_E_ARG, "attn_site: w_kv is NULL for a non-hoisted cross site");
-    MtnLinearArgs kvl = {};
-    kvl.A = a->mem_f16; kvl.lda = d; kvl.W = a->w_kv; kvl.ldw = d; kvl.bias = a->b_kv;
-    kvl.M = (int)rk; kvl.N = 2 * d; kvl.K = d; kvl.act = MTN_ACT_NONE;
-    kvl.out_f16 = kvbuf; kvl.ld16 = 2 * d;
-    rc = mtn_linear_fwd(&kvl, stream);
-    if (rc) return rc;
     core.k = kvbuf; core.ldk = 2 * d;
     core.v = static_cast<const uint8_t*>(kvbuf) + (size_t)d * 2; core.ldv = 2 * d;
   }

@@ -1,0 +1,650 @@
+// One attention SITE in one kernel (hoisted K/V):
+//     x += Wo . concat_h softmax(mask((xn Wq_h^T + bq_h) K_h^T / sqrt(d_k))) V_h + bo
+// i.e. SublayerConnection.forward (mtn.py:125-127) around MultiHeadedAttention.forward (mtn.py:248-267) around
+// attention() (mtn.py:221-231), for a site whose K / V projections already exist (static memories: their K/V for all
+// layers come out of one hoisted GEMM; engine.py).  xn = LayerNorm(x) in f16 is the input (mtn_layernorm_fwd).
+//
+// Work decomposition: one CLUSTER OF TWO CTAs per (batch element, 128-query tile).  CTA `rank` owns half of the heads
+// (HH = h / 2) and half of the output columns (NH = HH * 64 = d / 2); everything between the LayerNorm output and the
+// residual stream stays on chip:
+//   phase 1  Q[128, NH] = xn[128, d] Wq[rank half]^T on the tensor core (TMA ring, tcgen05.mma into TMEM), drained
+//            (+ bias, -> f16) into shared memory as HH K-major 128B-swizzled [128 x 64] head tiles -- the A operand
+//            layout of Q K^T.  The Q projection never goes to HBM.
+//   phase 2  per head: S = Q_h K_h^T, online softmax (f32, log2 domain, the reference's FINITE -1e9 mask value), P V
+//            -- the pipeline of csrc/attn.cu (K/V by 3-D TMA out of the hoisted buffer, two S accumulators, P through
+//            shared memory).  O_h / l overwrites the head's Q tile (f16): after the last head the CTA holds its half
+//            of concat_h O as the A operand of the output projection.  Each finished tile is also pushed into the
+//            PEER CTA's shared memory by one bulk async copy (cp.async.bulk shared::cta -> shared::cluster) that
+//            completes on the peer's mbarrier.
+//   phase 3  Y[128, NH] = O[128, d] Wo[rank half]^T: A = the 2 HH head tiles (own + received), B = Wo rows by TMA;
+//            epilogue: + bias, transposed through shared memory, added to the f32 residual stream with coalesced
+//            red.global.add.v4.f32 (one f32 add per element; the CTA pair covers every column exactly once).
+// Versus the launch sequence LayerNorm -> Q GEMM -> core -> out-proj GEMM this removes two launches and the HBM/L2 round
+// trips of Q and O per site.
+//
+// Shared memory (HH = 4, 96-key tiles): Q/O tiles 64 KB + peer tiles 64 KB + a 96 KB region that is, in turn, the
+// phase-1 operand ring (2 x 48 KB), the K/V/P buffers of phase 2 (72 KB), the phase-3 Wo ring (3 x 32 KB) and the
+// epilogue's transpose tiles.  TMEM: 512 columns = Q / Y accumulator (NH) + two S buffers + O.  One CTA per SM.
+//
+// Warp roles (224 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 softmax / drains / epilogue
+// (TMEM lane quarter = warp % 4), warp 6 sends finished O tiles to the peer.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mtn {
+
+constexpr int SF_THREADS = 224;
+constexpr int SF_QT = 128;
+
+template <int HH, int KT>
+struct SfCfg {
+  static constexpr int DK = 64;
+  static constexpr int NH = HH * DK;        // columns of Q / of the output owned by one CTA
+  static constexpr int D = 2 * NH;          // model width
+  static constexpr int NKB = D / 64;        // 64-wide k-blocks of the two projections
+  static constexpr int TILE = SF_QT * 128;  // one [128 x 64] f16 tile, K-major, 128B swizzle: 16 KB
+  static constexpr int OFF_QO = 0;
+  static constexpr int OFF_PEER = OFF_QO + HH * TILE;
+  static constexpr int OFF_RING = OFF_PEER + HH * TILE;
+  static constexpr int A_BYTES = TILE;      // xn k-block [128 x 64]
+  static constexpr int B_BYTES = NH * 128;  // weight k-block [NH x 64]
+  static constexpr int ST1 = 2, ST3 = 3;
+  static constexpr int RING1 = ST1 * (A_BYTES + B_BYTES);
+  static constexpr int RING3 = ST3 * B_BYTES;
+  static constexpr int KV_BYTES = KT * 128;
+  static constexpr int P_BYTES = (KT / 64) * SF_QT * 128 + ((KT % 64) ? SF_QT * 64 : 0);
+  static constexpr int OFF_K = 0, OFF_V = 2 * KV_BYTES, OFF_P = (4 * KV_BYTES + 1023) / 1024 * 1024;
+  static constexpr int RING2 = OFF_P + P_BYTES;
+  static constexpr int XPOSE = 4 * 4096;
+  static constexpr int RING_A = RING1 > RING2 ? RING1 : RING2;
+  static constexpr int RING_B = RING3 > XPOSE ? RING3 : XPOSE;
+  static constexpr int RING = RING_A > RING_B ? RING_A : RING_B;
+  static constexpr int OFF_BAR = OFF_RING + RING;
+  static constexpr int TOTAL = OFF_BAR + 512 + 1024;  // barriers + 1 KB alignment slack
+  static constexpr uint32_t D_COL = 0, S_COL = NH, O_COL = NH + 2 * KT;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(NH + 2 * KT + DK <= 512, "TMEM budget");
+  static_assert(KV_BYTES % 1024 == 0, "K/V buffers must stay swizzle-atom aligned");
+  static_assert(NH <= 256 && NH % 16 == 0, "UMMA N");
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+enum {
+  SB_R1_FULL = 0 /* +1 */, SB_R1_EMPTY = 2 /* +1 */, SB_D1_FULL = 4, SB_Q_READY = 5,
+  SB_K_FULL = 6 /* +1 */, SB_K_EMPTY = 8 /* +1 */, SB_V_FULL = 10 /* +1 */, SB_V_EMPTY = 12 /* +1 */,
+  SB_S_FULL = 14 /* +1 */, SB_S_FREE = 16 /* +1 */, SB_P_FULL = 18, SB_PV_DONE = 19, SB_ATT_DONE = 20,
+  SB_OWN_O = 21 /* +3 */, SB_PEER_O = 25, SB_R3_FULL = 26 /* +2 */, SB_R3_EMPTY = 29 /* +2 */, SB_D3_FULL = 32,
+  SB_COUNT = 33
+};
+
+struct SfParams {
+  int B, h, Lq, Lk, nqt;
+  const float* b_q;
+  const float* b_o;
+  float* x;
+  int ld_x;
+  const uint32_t* mask_bits;
+  int mask_rows_q, mask_words;
+  float scale;
+};
+
+__device__ __forceinline__ float sf_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t sf_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// bulk async copy local shared memory -> a peer CTA's shared memory; completes `bytes` on the PEER's mbarrier
+__device__ __forceinline__ void sf_dsmem_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+
+template <int HH, int KT>
+__global__ void __launch_bounds__(SF_THREADS, 1)
+    attn_site_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
+                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                           const __grid_constant__ CUtensorMap tmWo, const SfParams p) {
+  using C = SfCfg<HH, KT>;
+  constexpr int DK = C::DK;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sQO = base + C::OFF_QO, sPEER = base + C::OFF_PEER, sRING = base + C::OFF_RING;
+  const uint32_t sK = sRING + C::OFF_K, sV = sRING + C::OFF_V, sP = sRING + C::OFF_P;
+  const uint32_t bars = base + C::OFF_BAR;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const uint32_t tmem_slot = bars + 8u * SB_COUNT;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_BAR + 8 * SB_COUNT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int item = blockIdx.x >> 1;  // (batch element, query tile) of this cluster
+  const int qt = item % p.nqt, b = item / p.nqt;
+  const int nt = (p.Lk + KT - 1) / KT;
+  const uint32_t total = (uint32_t)HH * (uint32_t)nt;  // key tiles of this CTA, all heads
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWq);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmWo);
+    for (int i = 0; i < SB_COUNT; ++i) {
+      const bool all128 = (i == SB_Q_READY || i == SB_S_FREE || i == SB_S_FREE + 1 || i == SB_P_FULL ||
+                           (i >= SB_OWN_O && i < SB_OWN_O + 4));
+      mbar_init(bar(i), all128 ? 128u : 1u);
+    }
+    // the peer's HH finished head tiles land here (armed before the cluster barrier below, i.e. before any send)
+    mbar_arrive_expect_tx(bar(SB_PEER_O), (uint32_t)(HH * C::TILE));
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers exist before either can signal the other
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tD = tmem_base + C::D_COL, tO = tmem_base + C::O_COL;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      // ---- phase 1: xn k-blocks + Wq k-blocks
+      for (int kb = 0; kb < C::NKB; ++kb) {
+        const int s = kb % C::ST1;
+        mbar_wait(bar(SB_R1_EMPTY + s), ((kb / C::ST1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar(SB_R1_FULL + s), C::A_BYTES + C::B_BYTES);
+        const uint32_t st = sRING + s * (C::A_BYTES + C::B_BYTES);
+        tma_load_3d(st, &tmX, bar(SB_R1_FULL + s), kb * 64, qt * SF_QT, b);
+        tma_load_2d(st + C::A_BYTES, &tmWq, bar(SB_R1_FULL + s), kb * 64, (int)rank * C::NH);
+      }
+      // ---- phase 2: K / V tiles of my heads (the ring region is free once the projection MMAs have retired)
+      mbar_wait(bar(SB_D1_FULL), 0);
+      auto load_k = [&](uint32_t g) {
+        const uint32_t hh = g / nt, j = g % nt, kb = g & 1, kph = (g >> 1) & 1;
+        mbar_wait(bar(SB_K_EMPTY + kb), kph ^ 1);
+        mbar_arrive_expect_tx(bar(SB_K_FULL + kb), C::KV_BYTES);
+        tma_load_3d(sK + kb * C::KV_BYTES, &tmK, bar(SB_K_FULL + kb), ((int)rank * HH + (int)hh) * DK, j * KT, b);
+      };
+      auto load_v = [&](uint32_t g) {
+        const uint32_t hh = g / nt, j = g % nt, vb = g & 1, vph = (g >> 1) & 1;
+        mbar_wait(bar(SB_V_EMPTY + vb), vph ^ 1);
+        mbar_arrive_expect_tx(bar(SB_V_FULL + vb), C::KV_BYTES);
+        tma_load_3d(sV + vb * C::KV_BYTES, &tmV, bar(SB_V_FULL + vb), ((int)rank * HH + (int)hh) * DK, j * KT, b);
+      };
+      load_k(0);
+      for (uint32_t g = 0; g < total; ++g) {
+        if (g + 1 < total) load_k(g + 1);
+        load_v(g);
+      }
+      // ---- phase 3: Wo k-blocks (the region is free once the last P V has retired)
+      mbar_wait(bar(SB_ATT_DONE), 0);
+      for (int kc = 0; kc < C::NKB; ++kc) {
+        const int s = kc % C::ST3;
+        mbar_wait(bar(SB_R3_EMPTY + s), ((kc / C::ST3) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar(SB_R3_FULL + s), C::B_BYTES);
+        tma_load_2d(sRING + s * C::B_BYTES, &tmWo, bar(SB_R3_FULL + s), kc * 64, (int)rank * C::NH);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    constexpr uint32_t idesc_p = make_idesc_f16(SF_QT, C::NH, 0, 0);  // both projections: K-major x K-major
+    constexpr uint32_t idesc_s = make_idesc_f16(SF_QT, KT, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_f16(SF_QT, DK, 0, 1);     // V is MN-major
+    // ---- phase 1
+    for (int kb = 0; kb < C::NKB; ++kb) {
+      const int s = kb % C::ST1;
+      mbar_wait(bar(SB_R1_FULL + s), (kb / C::ST1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = sRING + s * (C::A_BYTES + C::B_BYTES);
+        const uint64_t da = make_smem_desc(st, 16, 1024, SWZ_128B);
+        const uint64_t db = make_smem_desc(st + C::A_BYTES, 16, 1024, SWZ_128B);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tD, da + 2 * k, db + 2 * k, idesc_p, (kb | k) != 0);
+        tc_commit(bar(SB_R1_EMPTY + s));
+        if (kb == C::NKB - 1) tc_commit(bar(SB_D1_FULL));
+      }
+      __syncwarp();
+    }
+    // ---- phase 2
+    mbar_wait(bar(SB_Q_READY), 0);  // the Q head tiles are in shared memory
+    tc_fence_after();
+    auto issue_qk = [&](uint32_t g) {
+      const uint32_t hh = g / nt, sb = g & 1, ph2 = (g >> 1) & 1;
+      mbar_wait(bar(SB_K_FULL + sb), ph2);
+      mbar_wait(bar(SB_S_FREE + sb), ph2 ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dq = make_smem_desc(sQO + hh * C::TILE, 16, 1024, SWZ_128B);
+        const uint64_t dk = make_smem_desc(sK + sb * C::KV_BYTES, 16, 1024, SWZ_128B);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k)
+          tc_mma_f16(tmem_base + C::S_COL + sb * KT, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(bar(SB_K_EMPTY + sb));
+        tc_commit(bar(SB_S_FULL + sb));
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (uint32_t g = 0; g < total; ++g) {
+      if (g + 1 < total) issue_qk(g + 1);
+      const uint32_t ph = g & 1, j = g % nt;
+      mbar_wait(bar(SB_V_FULL + ph), (g >> 1) & 1);
+      mbar_wait(bar(SB_P_FULL), ph);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const bool rem = (KT % 64) != 0 && kk >= (KT / 64) * 4;
+          const uint64_t dp = rem ? make_smem_desc(sP + (KT / 64) * (SF_QT * 128) + (kk & 3) * 32, 16, 512, SWZ_64B)
+                                  : make_smem_desc(sP + (kk >> 2) * (SF_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
+          const uint64_t dv = make_smem_desc(sV + ph * C::KV_BYTES + kk * 16 * 128, KT * 128, 1024, SWZ_128B);
+          tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
+        }
+        tc_commit(bar(SB_V_EMPTY + ph));
+        tc_commit(bar(SB_PV_DONE));
+        if (g == total - 1) tc_commit(bar(SB_ATT_DONE));
+      }
+      __syncwarp();
+    }
+    // ---- phase 3: Y = [O own | O peer] Wo^T, head tiles in global head order
+    for (int hh = 0; hh < HH; ++hh) mbar_wait(bar(SB_OWN_O + hh), 0);
+    mbar_wait(bar(SB_PEER_O), 0);
+    tc_fence_after();
+    for (int kc = 0; kc < C::NKB; ++kc) {
+      const int s = kc % C::ST3;
+      mbar_wait(bar(SB_R3_FULL + s), (kc / C::ST3) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_tile = ((uint32_t)(kc / HH) == rank ? sQO : sPEER) + (uint32_t)(kc % HH) * C::TILE;
+        const uint64_t da = make_smem_desc(a_tile, 16, 1024, SWZ_128B);
+        const uint64_t db = make_smem_desc(sRING + s * C::B_BYTES, 16, 1024, SWZ_128B);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tD, da + 2 * k, db + 2 * k, idesc_p, (kc | k) != 0);
+        tc_commit(bar(SB_R3_EMPTY + s));
+        if (kc == C::NKB - 1) tc_commit(bar(SB_D3_FULL));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 6) {
+    // ================================================================ DSMEM sender: my finished head tiles -> the peer
+    if (lane == 0) {
+      const uint32_t peer = rank ^ 1u;
+      const uint32_t peer_bar = sf_mapa(bar(SB_PEER_O), peer);
+      for (int hh = 0; hh < HH; ++hh) {
+        mbar_wait(bar(SB_OWN_O + hh), 0);  // all 128 rows written and fenced for the async proxy
+        sf_dsmem_copy(sf_mapa(sPEER + hh * C::TILE, peer), sQO + hh * C::TILE, (uint32_t)C::TILE, peer_bar);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ softmax warps: Q drain, softmax, O drain, epilogue
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;  // row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t sw = (uint32_t)(row & 7);
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float c1 = p.scale * LOG2E;
+    const float t_masked = -1e9f * LOG2E;
+    constexpr int NCH = KT / 32;
+
+    // ---- phase 1 drain: Q = acc + bias -> f16 -> HH K-major swizzled head tiles
+    mbar_wait(bar(SB_D1_FULL), 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < C::NH / 32; ++c) {
+      uint32_t r[32];
+      tc_ld32(tD + lane_off + c * 32, r);
+      const float* bq = p.b_q + rank * C::NH + c * 32;
+      float4 bb[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) bb[t] = __ldg(reinterpret_cast<const float4*>(bq) + t);
+      tc_wait_ld();
+      const uint32_t tile = sQO + (uint32_t)(c >> 1) * C::TILE + row * 128;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t chunk = ((uint32_t)((c & 1) * 4 + t)) ^ sw;
+        const float4 b0 = bb[2 * t], b1 = bb[2 * t + 1];
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + chunk * 16),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t]) + b0.x, __uint_as_float(r[8 * t + 1]) + b0.y)),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) + b0.z, __uint_as_float(r[8 * t + 3]) + b0.w)),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) + b1.x, __uint_as_float(r[8 * t + 5]) + b1.y)),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) + b1.z, __uint_as_float(r[8 * t + 7]) + b1.w))
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar(SB_Q_READY));
+
+    // ---- phase 2: softmax over the key tiles of each head (the per-tile code of csrc/attn.cu)
+    const bool live = qt * SF_QT + q4 * 32 < p.Lq;  // some query row of this warp exists
+    const uint32_t* mrow = nullptr;
+    if (p.mask_bits != nullptr) {
+      const int mq = (p.mask_rows_q == 1) ? 0 : min(qt * SF_QT + row, p.Lq - 1);
+      mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
+    }
+    uint32_t mw_pref[NCH];
+    auto fetch_mask = [&](int jn) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int k0 = jn * KT + c * 32;
+        mw_pref[c] = (mrow != nullptr && k0 < p.Lk) ? __ldcg(mrow + (k0 >> 5)) : 0xffffffffu;
+      }
+    };
+    fetch_mask(0);
+    uint32_t g = 0;
+    for (int hh = 0; hh < HH; ++hh) {
+      float m_run = -CUDART_INF_F, l_run = 0.f;
+      if (!live) {
+        // every query row of this warp is padding: keep the barrier protocol alive, skip the arithmetic (these rows of
+        // P / O hold whatever shared / tensor memory holds; rows are independent and never stored)
+        for (int j = 0; j < nt; ++j, ++g) {
+          const uint32_t ph = g & 1;
+          mbar_wait(bar(SB_S_FULL + ph), (g >> 1) & 1);
+          if (j > 0) mbar_wait(bar(SB_PV_DONE), ph ^ 1);
+          mbar_arrive(bar(SB_S_FREE + ph));
+          mbar_arrive(bar(SB_P_FULL));
+        }
+        mbar_wait(bar(SB_PV_DONE), (g - 1) & 1);
+        mbar_arrive(bar(SB_OWN_O + hh));
+        continue;
+      }
+      for (int j = 0; j < nt; ++j, ++g) {
+        const uint32_t ph = g & 1;
+        const uint32_t tS = tmem_base + C::S_COL + ph * KT;
+        uint32_t mwv[NCH];
+        bool plain = (j + 1) * KT <= p.Lk;
+        {
+          uint32_t w = 0xffffffffu;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            mwv[c] = mw_pref[c];
+            w &= mwv[c];
+          }
+          if (mrow != nullptr) plain = plain && __all_sync(0xffffffffu, w == 0xffffffffu);
+        }
+        fetch_mask(j + 1 < nt ? j + 1 : 0);  // the mask does not depend on the head
+        mbar_wait(bar(SB_S_FULL + ph), (g >> 1) & 1);
+        tc_fence_after();
+        auto store_chunk = [&](int c, const uint32_t(&e)[32]) {
+          const bool rem = (KT % 64) != 0 && c == NCH - 1;
+          const uint32_t panel = sP + (c >> 1) * (SF_QT * 128) + row * (rem ? 64 : 128);
+          const uint32_t x = rem ? ((uint32_t)(row >> 1) & 3u) : sw, c4 = rem ? 0u : (uint32_t)(c & 1) * 4u;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + ((c4 + t) ^ x) * 16),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t]), __uint_as_float(e[8 * t + 1]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 2]), __uint_as_float(e[8 * t + 3]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 4]), __uint_as_float(e[8 * t + 5]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 6]), __uint_as_float(e[8 * t + 7])))
+                         : "memory");
+          }
+        };
+        // the P buffer and the O accumulator are in use by P V of the previous tile until it retires (across heads the
+        // previous head's epilogue has already waited for its last P V)
+        auto wait_p_buffer = [&]() {
+          if (j > 0) {
+            mbar_wait(bar(SB_PV_DONE), ph ^ 1);
+            tc_fence_after();
+          }
+        };
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        float m_new;
+        bool rescale = false;
+        auto pick_max = [&](float m_tile) {
+          m_new = fmaxf(m_run, m_tile);
+          if (j > 0) {
+            rescale = __any_sync(0xffffffffu, m_new - m_run > 8.f);
+            if (!rescale) m_new = m_run;
+          }
+        };
+        if (plain) {
+          uint32_t r[NCH][32];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tc_ld32(tS + lane_off + c * 32, r[c]);
+          tc_wait_ld();
+          tc_fence_before();
+          mbar_arrive(bar(SB_S_FREE + ph));
+          float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[c][i]));
+          }
+          pick_max(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float e = sf_ex2(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
+              l4[i & 3] += e;
+              r[c][i] = __float_as_uint(e);
+            }
+          }
+          wait_p_buffer();
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
+        } else {
+          float m_tile = -CUDART_INF_F;
+          auto chunk_mask = [&](int c) { return c == 0 ? mwv[0] : (c == 1 ? mwv[1] : mwv[NCH - 1]); };
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int nvalid = p.Lk - (j * KT + c * 32);
+            if (nvalid <= 0) break;
+            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+            const uint32_t mw = chunk_mask(c);
+            if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
+              m_tile = fmaxf(m_tile, t_masked);
+              continue;
+            }
+            uint32_t r[32];
+            tc_ld32(tS + lane_off + c * 32, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float t = __uint_as_float(r[i]) * c1;
+              t = ((mw >> i) & 1u) ? t : t_masked;
+              t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+              m_tile = fmaxf(m_tile, t);
+            }
+          }
+          pick_max(m_tile);
+          wait_p_buffer();
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int nvalid = p.Lk - (j * KT + c * 32);
+            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+            const uint32_t mw = chunk_mask(c);
+            uint32_t e[32];
+            if (nvalid > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
+              const float pm = sf_ex2(t_masked - m_new);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = ((inb >> i) & 1u) ? __float_as_uint(pm) : 0u;
+              l4[0] += pm * (float)__popc(inb);
+            } else if (nvalid > 0) {
+              tc_ld32(tS + lane_off + c * 32, e);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float t = __uint_as_float(e[i]) * c1;
+                t = ((mw >> i) & 1u) ? t : t_masked;
+                t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+                const float x = sf_ex2(t - m_new);
+                l4[i & 3] += x;
+                e[i] = __float_as_uint(x);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = 0u;
+            }
+            store_chunk(c, e);
+          }
+          tc_fence_before();
+          mbar_arrive(bar(SB_S_FREE + ph));
+        }
+        const float alpha = sf_ex2(m_run - m_new);
+        l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+        m_run = m_new;
+        if (rescale) {
+#pragma unroll
+          for (int c = 0; c < DK / 32; ++c) {
+            uint32_t o[32];
+            tc_ld32(tO + lane_off + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc_st32(tO + lane_off + c * 32, o);
+          }
+          tc_wait_st();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar(SB_P_FULL));
+      }
+      // ---- head epilogue: O / l -> f16 -> the head's (now idle) Q tile: the A operand of the output projection
+      mbar_wait(bar(SB_PV_DONE), (g - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const uint32_t tile = sQO + (uint32_t)hh * C::TILE + row * 128;
+#pragma unroll
+      for (int c = 0; c < DK / 32; ++c) {
+        uint32_t r[32];
+        tc_ld32(tO + lane_off + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t chunk = (uint32_t)(c * 4 + t) ^ sw;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + chunk * 16),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l))
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar(SB_OWN_O + hh));
+    }
+
+    // ---- phase 3 epilogue: Y + bias, transposed through shared memory, added to the residual stream (coalesced red.add)
+    mbar_wait(bar(SB_D3_FULL), 0);
+    tc_fence_after();
+    float4* xp = reinterpret_cast<float4*>(smem + C::OFF_RING + (warp - 2) * 4096);
+    const int sub_r = lane >> 2, c8 = lane & 3;
+    const int wr_base = lane * 8, wr_sw = lane & 7;
+    const int rd0 = sub_r * 8 + ((2 * c8) ^ sub_r), rd1 = sub_r * 8 + ((2 * c8 + 1) ^ sub_r);
+    const int rows_valid = min(SF_QT, p.Lq - qt * SF_QT);
+    const size_t grow0 = (size_t)b * p.Lq + (size_t)qt * SF_QT;
+#pragma unroll 1
+    for (int c = 0; c < C::NH / 32; ++c) {
+      const int col = (int)rank * C::NH + c * 32 + c8 * 8;
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b_o + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b_o + col + 4));
+      uint32_t acc[32];
+      tc_ld32(tD + lane_off + c * 32, acc);
+      tc_wait_ld();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        xp[wr_base + (jj ^ wr_sw)] = make_float4(__uint_as_float(acc[4 * jj]), __uint_as_float(acc[4 * jj + 1]),
+                                                 __uint_as_float(acc[4 * jj + 2]), __uint_as_float(acc[4 * jj + 3]));
+      __syncwarp();
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] = xp[i * 64 + rd0];
+        v[2 * i + 1] = xp[i * 64 + rd1];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = q4 * 32 + sub_r + i * 8;
+        if (rl < rows_valid) {
+          float* o = p.x + (grow0 + rl) * p.ld_x + col;
+          grad_red_v4(o, v[2 * i].x + b0.x, v[2 * i].y + b0.y, v[2 * i].z + b0.z, v[2 * i].w + b0.w, 0);
+          grad_red_v4(o + 4, v[2 * i + 1].x + b1.x, v[2 * i + 1].y + b1.y, v[2 * i + 1].z + b1.z, v[2 * i + 1].w + b1.w, 0);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  // nobody leaves while the peer may still copy into / out of its shared memory or signal its barriers
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int HH, int KT>
+static int launch_site_fused(const MtnAttnSiteFusedArgs& a, cudaStream_t st) {
+  using C = SfCfg<HH, KT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_site_fused_kernel<HH, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    attr_set = true;
+  }
+  const int d = a.d;
+  CUtensorMap tx, twq, tk, tv, two;
+  int rc = make_tmap_3d_f16(&tx, a.xn_f16, d, a.Lq, a.B, a.ld_xn, (uint64_t)a.Lq * a.ld_xn, 64, SF_QT, TM_SWZ_128);
+  if (rc) return rc;
+  rc = make_tmap_2d_f16(&twq, a.w_q, d, d, a.ld_wq > 0 ? a.ld_wq : d, 64, C::NH, TM_SWZ_128);
+  if (rc) return rc;
+  rc = make_tmap_2d_f16(&two, a.w_o, d, d, a.ld_wo > 0 ? a.ld_wo : d, 64, C::NH, TM_SWZ_128);
+  if (rc) return rc;
+  const uint8_t* kp = static_cast<const uint8_t*>(a.kv) + (size_t)a.kv_k_col * 2;
+  const uint8_t* vp = static_cast<const uint8_t*>(a.kv) + (size_t)a.kv_v_col * 2;
+  rc = make_tmap_3d_f16(&tk, kp, d, a.Lk, a.B, a.ld_kv, (uint64_t)a.Lk * a.ld_kv, 64, KT, TM_SWZ_128);
+  if (rc) return rc;
+  rc = make_tmap_3d_f16(&tv, vp, d, a.Lk, a.B, a.ld_kv, (uint64_t)a.Lk * a.ld_kv, 64, KT, TM_SWZ_128);
+  if (rc) return rc;
+  const int nqt = (a.Lq + SF_QT - 1) / SF_QT;
+  SfParams p{a.B, a.h, a.Lq, a.Lk, nqt, a.b_q, a.b_o, a.x, a.ld_x, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk),
+             1.0f / sqrtf(64.f)};
+  dim3 grid(2u * (unsigned)(a.B * nqt));
+  MTN_CHECK_CUDA(launch_kernel_cluster(attn_site_fused_kernel<HH, KT>, grid, dim3(SF_THREADS), C::TOTAL, st, 2u, tx, twq, tk, tv,
+                                       two, p));
+  return MTN_OK;
+}
+
+}  // namespace mtn
+
+extern "C" int mtn_attn_site_fused_supported(int d, int h) {
+  return (h > 0 && d == h * 64 && (d == 512 || d == 256)) ? 1 : 0;
+}
+
+extern "C" int mtn_attn_site_fused_fwd(const MtnAttnSiteFusedArgs* a, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(a && a->xn_f16 && a->x && a->w_q && a->b_q && a->w_o && a->b_o && a->kv, MTN_E_ARG, "attn_site_fused: NULL pointer");
+  MTN_REQUIRE(a->B > 0 && a->Lq > 0 && a->Lk > 0, MTN_E_SHAPE, "attn_site_fused: B=%d Lq=%d Lk=%d", a->B, a->Lq, a->Lk);
+  MTN_REQUIRE(mtn_attn_site_fused_supported(a->d, a->h), MTN_E_SHAPE,
+              "attn_site_fused: d=%d h=%d (supported: d_k = 64 with d in {256, 512}; other shapes take mtn_attn_site_fwd)", a->d, a->h);
+  MTN_REQUIRE(a->ld_xn >= a->d && a->ld_xn % 8 == 0 && a->ld_kv % 8 == 0 && a->ld_x >= a->d && a->ld_x % 4 == 0 &&
+                  a->kv_k_col % 8 == 0 && a->kv_v_col % 8 == 0 && a->kv_k_col >= 0 && a->kv_v_col >= 0 &&
+                  a->ld_kv >= a->kv_k_col + a->d && a->ld_kv >= a->kv_v_col + a->d,
+              MTN_E_ALIGN, "attn_site_fused: leading dimensions / K,V columns");
+  MTN_REQUIRE(aligned16(a->xn_f16) && aligned16(a->x) && aligned16(a->w_q) && aligned16(a->w_o) && aligned16(a->kv) &&
+                  aligned16(a->b_q) && aligned16(a->b_o),
+              MTN_E_ALIGN, "attn_site_fused: pointers must be 16-byte aligned");
+  MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,
+              "attn_site_fused: mask_rows_q=%d must be 1 or Lq=%d", a->mask_rows_q, a->Lq);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->d == 512) return a->Lk <= 64 ? launch_site_fused<4, 64>(*a, st) : launch_site_fused<4, 96>(*a, st);
+  return a->Lk <= 64 ? launch_site_fused<2, 64>(*a, st) : launch_site_fused<2, 96>(*a, st);
+}

@@ -84,6 +84,18 @@ def invalidate_weight_caches():
     _GENERATION[0] += 1
 
 
+def _site_fused_ok(d, h, B, Lq, Lk):
+    """Does this hoisted-K/V site take the ONE-kernel path (csrc/site_fused.cu)?  MTN_B200_SITE_FUSED = 1: whenever the
+    shape is supported; 0: never; default "auto": where it measured at least as fast as the launch sequence Q GEMM ->
+    core -> out-proj GEMM (profiles/r02_site_bench.txt): full query tiles on short memories."""
+    mode = os.environ.get("MTN_B200_SITE_FUSED", "auto")
+    if mode == "0" or not _lib.attn_site_fused_supported(d, h):
+        return False
+    if mode == "1":
+        return True
+    return Lq >= 128 and Lk <= 64
+
+
 class PackedWeights(object):
     """Cache of tensor-core-ready (f16, concatenated) copies of nn.Parameters, rebuilt
     when any source parameter is modified in place (``_version``), re-assigned, or after
@@ -215,6 +227,12 @@ class DecoderEngine(object):
         """One pre-norm residual attention site, in place on the f32 stream ``x`` [B*Lq, d].
         kv=None -> self-attention (q_w is the [3d, d] pack, K/V come out of the same GEMM)."""
         d = x.shape[1]
+        if kv is not None and _site_fused_ok(d, A["h"], B, Lq, Lk):
+            _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
+            _tap("xn16", xn16)
+            _lib.attn_site_fused(xn16, x, q_w, q_b, A["w_o"], A["b_o"], kv, k_col, v_col, B, A["h"], Lq, Lk, mask_bits=bits)
+            _tap("x", x)
+            return
         _ln_linear(x, ln, q_w, q_b, _lib.ACT_NONE, xn16, qbuf)
         if kv is None:
             q, k, v = qbuf[:, :d], qbuf[:, d:2 * d], qbuf[:, 2 * d:]

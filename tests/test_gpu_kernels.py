@@ -468,3 +468,82 @@ def test_linear_batched_and_grouped_layernorm(L):
     torch.cuda.synchronize()
     ref_ln = torch.cat([O.layer_norm(xd[i].cpu(), a2[i], b2[i], 1e-6) for i in range(b)])
     assert G.rel_err(y.float().cpu(), ref_ln) < 6e-4
+
+
+# ------------------------------------------------------------------ one attention site in one kernel (csrc/site_fused.cu)
+SITE_FUSED = [
+    # B, Lq, Lk, d, h, mask kind
+    (2, 128, 64, 512, 8, "keypad"),
+    (3, 256, 64, 512, 8, "keypad"),
+    (2, 200, 300, 512, 8, "keypad"),     # partial second query tile, 4 key tiles
+    (5, 1, 256, 512, 8, "keypad"),       # KV-cached decoding: one query row per dialogue
+    (4, 64, 512, 512, 8, "none"),        # QAE ae -> video
+    (2, 100, 64, 256, 4, "keypad"),      # d = 256: two heads per CTA
+    (3, 70, 130, 256, 4, "dense"),       # per-query mask rows
+    (32, 256, 64, 512, 8, "keypad"),     # cfg2 target -> caption: 64 clusters
+]
+
+
+@pytest.mark.parametrize("B,Lq,Lk,d,h,kind", SITE_FUSED)
+def test_attn_site_fused(L, B, Lq, Lk, d, h, kind):
+    """x += Wo . attention(xn Wq^T + bq, K, V) + bo in ONE launch against (a) the CPU oracle arithmetic on the
+    f16-rounded operands and (b) the launch sequence linear -> attn_core -> linear(+residual), which runs the same
+    arithmetic in the same order: bit-identical."""
+    assert L.attn_site_fused_supported(d, h)
+    g = torch.Generator().manual_seed(B * 1000 + Lq * 7 + Lk + d)
+    dk = d // h
+    xn = torch.randn(B * Lq, d, generator=g).half()
+    x = torch.randn(B * Lq, d, generator=g) * 2
+    mem_kv = (torch.randn(B * Lk, 2 * d + 64, generator=g) * 1.2).half()      # [K | V | pad] with a leading dimension
+    wq, wo = (torch.randn(d, d, generator=g) * 0.05).half(), (torch.randn(d, d, generator=g) * 0.05).half()
+    bq, bo = torch.randn(d, generator=g) * 0.1, torch.randn(d, generator=g) * 0.1
+    if kind == "keypad":
+        mask = torch.ones(B, 1, Lk, dtype=torch.bool)
+        lens = torch.randint(max(1, Lk // 2), Lk + 1, (B,), generator=g)
+        for b in range(B):
+            mask[b, 0, int(lens[b]):] = False
+        mask[0] = False                                   # fully masked batch element: uniform average (mtn.py:227)
+    elif kind == "dense":
+        mask = torch.rand(B, Lq, Lk, generator=g) > 0.3
+    else:
+        mask = None
+    # (a) oracle arithmetic with the kernels' roundings (Q and O to f16)
+    q = (xn.float() @ wq.float().t() + bq).half()
+    k, v = mem_kv[:, :d], mem_kv[:, d:2 * d]
+    o = _attn_ref(q.view(B, Lq, d), k.reshape(B, Lk, d), v.reshape(B, Lk, d), mask, h, dk).reshape(B * Lq, d).half()
+    ref_delta = o.float() @ wo.float().t() + bo
+    # (b) launch sequence
+    xd, xn_d, kv_d = dev(x), dev(xn), dev(mem_kv)
+    bits = L.mask_pack(dev(mask)) if mask is not None else None
+    qb = torch.empty(B * Lq, d, device="cuda", dtype=torch.float16)
+    ob = torch.empty(B * Lq, d, device="cuda", dtype=torch.float16)
+    x_seq = xd.clone()
+    L.linear(xn_d, dev(wq), dev(bq), out_f16=qb)
+    L.attn_core(qb, kv_d[:, :d], kv_d[:, d:2 * d], B, h, Lq, Lk, dk, ob, mask_bits=bits)
+    L.linear(ob, dev(wo), dev(bo), addend=x_seq, out_f32=x_seq)
+    # fused
+    x_f = xd.clone()
+    L.attn_site_fused(xn_d, x_f, dev(wq), dev(bq), dev(wo), dev(bo), kv_d, 0, d, B, h, Lq, Lk, mask_bits=bits)
+    torch.cuda.synchronize()
+    assert torch.isfinite(x_f).all()
+    e_ref = G.rel_err((x_f - xd).cpu(), ref_delta)
+    e_seq = G.rel_err((x_seq - xd).cpu(), ref_delta)
+    same = bool(torch.equal(x_f, x_seq))
+    print("site fused %s: vs oracle %.2e (launch sequence %.2e), bit-identical to the launch sequence: %s"
+          % ((B, Lq, Lk, d, h, kind), e_ref, e_seq, same))
+    if not (e_ref < 2e-3):
+        _dump("fail_site_fused_%d_%d_%d_%d.npz" % (B, Lq, Lk, d), fused=x_f - xd, seq=x_seq - xd, ref=ref_delta)
+    assert e_ref < 2e-3, (e_ref, e_seq)
+    # same arithmetic in the same order: identical up to a handful of f16 roundings of O (measured: <= 3 of 131072
+    # elements differ by one f16 ulp, tools/site_fused_debug.py), i.e. far below the error against the oracle
+    assert G.rel_err((x_f - xd).cpu(), (x_seq - xd).cpu()) < 2e-5, float((x_f - x_seq).abs().max())
+    # run-to-run determinism, and a second call on the same buffers (cluster / barrier state is per launch)
+    x_g = xd.clone()
+    L.attn_site_fused(xn_d, x_g, dev(wq), dev(bq), dev(wo), dev(bo), kv_d, 0, d, B, h, Lq, Lk, mask_bits=bits)
+    L.attn_site_fused(xn_d, x_f, dev(wq), dev(bq), dev(wo), dev(bo), kv_d, 0, d, B, h, Lq, Lk, mask_bits=bits)
+    torch.cuda.synchronize()
+    assert torch.equal(x_g + (x_g - xd), x_f) or G.rel_err((x_f - x_g).cpu(), ref_delta) < 2e-3
+    x_h = xd.clone()
+    L.attn_site_fused(xn_d, x_h, dev(wq), dev(bq), dev(wo), dev(bo), kv_d, 0, d, B, h, Lq, Lk, mask_bits=bits)
+    torch.cuda.synchronize()
+    assert torch.equal(x_g, x_h), "fused site kernel is not deterministic run to run"
