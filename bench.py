@@ -394,6 +394,28 @@ def train_leg(args, model, devb, ntok, host, dev, rank, world, barrier, max_over
                     "normaliser_note": "ntokens / ntokens_query are counted on the device inside the captured step and "
                                        "summed over the ranks (one 2-element all-reduce); `loss` is summed over the ranks",
                     "normalisers_last_step": [float(x) for x in ts.norms] if ts.norms is not None else None})
+        # how much of the gradient exchange is exposed: the same captured step WITHOUT its collectives (measurement only)
+        if world > 1 and not args.train_eager:
+            try:
+                ts.allreduce = False
+                ts.capture(devb[0])
+                for i in range(3):
+                    ts.replay(devb[i % args.rot])
+                barrier()
+                e0.record()
+                for i in range(args.train_steps):
+                    ts.replay(devb[i % args.rot])
+                e1.record()
+                barrier()
+                ms0 = max_over_ranks(e0.elapsed_time(e1)) / args.train_steps
+                res["ms_per_step_without_allreduce"] = ms0
+                res["allreduce_exposed_ms"] = ms - ms0
+                res["allreduce_overlap"] = ("prefix of %d MB (target path's modules) all-reduced on a communication stream during "
+                                            "the auto-encoder chains' backward, then the remaining %d MB"
+                                            % (ts.n_prefix * 4 >> 20, (ts.flat.numel() - ts.n_prefix) * 4 >> 20)) \
+                    if ts.n_prefix else "none (one all-reduce after the backward)"
+            except Exception as e:
+                res["allreduce_exposed_error"] = repr(e)[:300]
         del ts
     except Exception as e:           # the forward headline must survive a failing auxiliary leg
         import traceback
@@ -869,10 +891,28 @@ def main():
                 "kernel_breakdown_one_step": breakdown, "decode": decode, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # every rank has finished its legs (the line above is out): leave without NCCL's teardown -- with captured
+        # graphs that hold collectives, destroy_process_group() was seen to hang a finished run until the caller's timeout
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def _watchdog(limit_s):
+    """A bench run that exceeds its wall-clock budget is killed from inside (exit code 3) instead of holding the GPU
+    box until the caller's timeout: MTN_B200_BENCH_LIMIT_S, default 900 s."""
+    def run():
+        time.sleep(limit_s)
+        sys.stderr.write("bench.py: wall-clock limit of %d s exceeded -- aborting\n" % limit_s)
+        sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=run, daemon=True).start()
 
 
 if __name__ == "__main__":
+    _watchdog(int(os.environ.get("MTN_B200_BENCH_LIMIT_S", "900")))
     # The contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its version
     # banner there) are pointed at stderr for the duration of the run; print() keeps the real stdout.
     sys.stdout.flush()

@@ -55,6 +55,8 @@ class DecoderTrainer(object):
     def __init__(self, decoder):
         self.dec = decoder
         self._packed = PackedWeights(follow_generation=False)
+        self.on_target_grads_ready = None   # callable(event on the wgrad stream) or None, see _carve
+        self._prefix_numel = 0
         self._arena = None          # flat f32 parameter arena + f16 operand arena (same layout)
         self._grad = None           # optional persistent gradient arena (same layout) backing every .grad
         self._mc = 0                # byte offset local -> NVLS multicast mapping of that arena (0: local accumulation)
@@ -412,6 +414,11 @@ class DecoderTrainer(object):
         hoisted(("cap", 0), [(l, L.cap_attn) for l, L in enumerate(layers)])
         hoisted(("src", 0), [(l, L.src_attn) for l, L in enumerate(layers)])
         ffn(("ffn", 0), [(l, L.feed_forward) for l, L in enumerate(layers)])
+        # Everything carved so far belongs to the TARGET path's own modules (self / his / cap / src sites, FFN): these
+        # gradients are final once the target path and the text memories' K/V projections have been differentiated --
+        # while the Query-Aware Auto-Encoder chains still run on their side streams.  A data-parallel trainer starts
+        # the all-reduce of this prefix then (trainer.TrainStep, `on_target_grads_ready`).
+        self._prefix_numel = ar.off
         for i in range(M):
             packed_qkv(("ae_self", i), [(l, L.auto_encoder_self_attn[i]) for l, L in enumerate(layers)])
             hoisted(("ae_vid", i), [(l, L.auto_encoder_vid_attn[i]) for l, L in enumerate(layers)])
@@ -620,6 +627,12 @@ class DecoderTrainer(object):
             grads[name] = self._mem_bwd(bk, dkv_mem[name], ctx["mem16"][name],
                                         W["kv_" + ("q" if name == "src" else name)][0], G[(gk, "wkv")],
                                         G[(gk, "bkv")]).view(ctx["mem_shape"][name])
+
+        hook = getattr(self, "on_target_grads_ready", None)
+        if hook is not None and direct:
+            ev_w = torch.cuda.Event()
+            ev_w.record(ws)                 # the weight-gradient GEMMs issued so far (all of the prefix's)
+            hook(ev_w)
 
         # ---- Query-Aware Auto-Encoder branch: one side stream per modality
         grads["ae"], grads["vid"] = [], []

@@ -88,16 +88,20 @@ def test_two_rank_gradient_allreduce_equals_single_process_oracle():
     assert err <= 1e-5, err                                          # SURVEY 8e equivalence bar
 
 
-def _dp_gpu_worker(rank, world, port, q):
+def _dp_gpu_worker(rank, world, port, q, backend="gloo", batch=4, overlap=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if backend == "nccl":                   # one rank per GPU, the production arrangement
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:                                   # gloo: both ranks share GPU 0 (gradient buffer staged through the host)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.cuda.set_device(0)
     import mtn_oracle as O
     from mtn_b200 import mtn, parallel
     from mtn_b200.trainer import TrainStep
-    torch.cuda.set_device(0)
     sd = O.init_state_dict(CFG_DP, 11)
-    full = O.synth_inputs(CFG_DP, B=4, Q=8, C=8, H=16, T=8, Lv=[16, 8], seed=5)
+    full = O.synth_inputs(CFG_DP, B=batch, Q=8, C=8, H=16, T=8, Lv=[16, 8], seed=5)
 
     def grads_of(batch, ntok, nq, use_dist):
         model = mtn.make_model(100, 100, N=1, d_model=128, d_ff=512, h=4, dropout=0.0, ft_sizes=[2048, 128],
@@ -107,7 +111,7 @@ def _dp_gpu_worker(rank, world, port, q):
         for m in model.modules():
             if isinstance(m, torch.nn.Dropout):
                 m.p = 0.0
-        ts = TrainStep(model, 100, graph=False, optimizer=_NoOpt())
+        ts = TrainStep(model, 100, graph=False, optimizer=_NoOpt(), overlap=overlap and use_dist)
         if not use_dist:
             ts.world = 1
         snap = {}
@@ -116,9 +120,15 @@ def _dp_gpu_worker(rank, world, port, q):
         return snap["flat"].cpu()
 
     mine = parallel.shard_batch(full, rank, world)
-    ntok = parallel.global_tokens(mine["trg_y"], 1)
-    nq = parallel.all_sum(int((mine["query"] != 1).sum()))
-    g_dp = grads_of(mine, ntok, nq, True)
+    dev = "cuda" if backend == "nccl" else "cpu"
+    if backend == "nccl":
+        # normalisers counted ON THE DEVICE inside the step (summed over the ranks by TrainStep), prefix all-reduce
+        # overlapped with the rest of the backward: the production path
+        g_dp = grads_of(mine, None, None, True)
+    else:
+        ntok = parallel.global_tokens(mine["trg_y"], 1, dev)
+        nq = parallel.all_sum(int((mine["query"] != 1).sum()), dev)
+        g_dp = grads_of(mine, ntok, nq, True)
     if rank == 0:
         g_one = grads_of(full, int((full["trg_y"] != 1).sum()), int((full["query"] != 1).sum()), False)
         q.put(float((g_dp - g_one).norm() / g_one.norm()))
@@ -149,3 +159,26 @@ def test_two_process_trainstep_allreduce_equals_single_process_gpu():
     [p.join(120) for p in ps]
     assert all(p.exitcode == 0 for p in ps)
     assert err <= 2e-3, err          # two f16-operand passes over different batch splits: rounding noise only
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("overlap", [False, True])
+def test_nccl_ranks_trainstep_equals_single_process(overlap):
+    """SURVEY 8e on hardware: N ranks, one per GPU, NCCL -- shards of one global batch, token counts summed on the
+    device, the gradient exchanged in one all-reduce (default) or in two overlapped ones (overlap=True) -- must give
+    the single-process gradient of the whole batch (f16-operand rounding noise only).  Needs >= 2 GPUs (the driver's
+    1-GPU box skips it)."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs, found %d" % n)
+    world = min(n, 8)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 29) % 500
+    ps = [ctx.Process(target=_dp_gpu_worker, args=(r, world, port + int(overlap), q, "nccl", 2 * world, overlap)) for r in range(world)]
+    [p.start() for p in ps]
+    err = q.get(timeout=600)
+    [p.join(180) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    print("NCCL %d-rank gradient vs single process: %.2e" % (world, err))
+    assert err <= 2e-3, err
