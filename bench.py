@@ -446,7 +446,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=30)
     ap.add_argument("--train-eager", action="store_true", help="time the training step without CUDA-graph capture")
     ap.add_argument("--decode-batch", type=int, default=64)
-    ap.add_argument("--decode-in-flight", type=int, default=2,
+    ap.add_argument("--decode-in-flight", type=int, default=4,
                     help="dialogue batches decoded concurrently (own stream + graphs each) in the decode leg's second measurement")
     ap.add_argument("--decode-len", type=int, default=20)
     args = ap.parse_args()

@@ -212,6 +212,19 @@ typedef struct MtnAttnCoreArgs {
 } MtnAttnCoreArgs;
 int mtn_attn_core_fwd(const MtnAttnCoreArgs *args, void *stream);
 
+/* ---- few-row variants for KV-cached decoding (csrc/decode_rows.cu) -----------------
+ * At one target position per dialogue every kernel of a decoding step works on M = B rows; the tcgen05 kernels pay
+ * ~6 us of fixed cost per launch there.  Same contracts, same arithmetic (f16 operands, f32 accumulate, the same
+ * softmax formulas), no tensor-memory / TMA setup:
+ *   mtn_rows_linear_fwd  = mtn_linear_fwd for M <= 128 (N % 8 == 0, K % 32 == 0); `addend`, if given, must be the f32
+ *                          output itself (in-place residual).  mma.sync, one CTA per 8 output columns.
+ *   mtn_decode_attn_fwd  = mtn_attn_core_fwd for Lq <= 8 query rows per batch element, d_k = 64 (batch strides
+ *                          honoured: the self-attention cache is addressed in place).  One warp per (batch, head).  */
+int mtn_rows_linear_supported(int M, int N, int K);
+int mtn_rows_linear_fwd(const MtnLinearArgs *args, void *stream);
+int mtn_decode_attn_supported(int Lq, int d_k);
+int mtn_decode_attn_fwd(const MtnAttnCoreArgs *args, void *stream);
+
 /* ---- one attention site --------------------------------------------------------
  * Replaces  SublayerConnection.forward(x, lambda x: attn(x, mem, mem, mask))
  * (mtn.py:125-127 around mtn.py:248-267):

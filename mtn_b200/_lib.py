@@ -164,6 +164,10 @@ SYMBOLS = {
     "mtn_attn_core_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
     "mtn_attn_site_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "mtn_attn_site_fwd": (C.c_int, [C.POINTER(AttnSiteArgs), C.c_void_p]),
+    "mtn_rows_linear_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "mtn_rows_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "mtn_decode_attn_supported": (C.c_int, [C.c_int, C.c_int]),
+    "mtn_decode_attn_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
     "mtn_attn_site_fused_supported": (C.c_int, [C.c_int, C.c_int]),
     "mtn_attn_site_fused_fwd": (C.c_int, [C.POINTER(AttnSiteFusedArgs), C.c_void_p]),
     "mtn_ffn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -345,6 +349,17 @@ def mask_pack(mask):
     return bits
 
 
+# few-row dispatch (KV-cached decoding): linear() / attn_core() take the small-M kernels of csrc/decode_rows.cu when
+# the shape qualifies and ROWS_KERNELS is on (engine.decode_step switches it on for its launches)
+ROWS_KERNELS = False
+
+
+def rows_linear_ok(M, N, K, addend, out_f32, add_period, drop, out16_pre_add):
+    return (ROWS_KERNELS and M <= 128 and N % 8 == 0 and K % 32 == 0 and drop is None and not out16_pre_add and
+            (addend is None or (out_f32 is not None and addend.data_ptr() == out_f32.data_ptr() and add_period == 0 and
+                                addend.stride(0) == out_f32.stride(0))))
+
+
 def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=None, out_f16=None,
            _check_kernel=False, out16_pre_add=False, drop=None, drop_after_add=False):
     """C = act(A W^T + bias) + addend.  A: [M, K] f16 (row stride allowed), W: [N, K] f16."""
@@ -369,6 +384,8 @@ def linear(A, W, bias=None, act=ACT_NONE, addend=None, add_period=0, out_f32=Non
     _set_drop(a, drop)
     a.drop_after_add = 1 if drop_after_add else 0
     fn = lib().mtn_check_linear_fwd if _check_kernel else lib().mtn_linear_fwd
+    if not _check_kernel and rows_linear_ok(a.M, a.N, a.K, addend, out_f32, add_period, drop, out16_pre_add):
+        fn = lib().mtn_rows_linear_fwd
     nbytes = 2 * (a.M * a.K + a.N * a.K) + a.M * a.N * ((4 if out_f32 is not None else 0) +
                                                         (2 if out_f16 is not None else 0) +
                                                         (4 if addend is not None else 0))
@@ -426,6 +443,8 @@ def attn_core(q, k, v, B, h, Lq, Lk, d_k, out, mask_bits=None, _check_kernel=Fal
         a.stats = stats.data_ptr()
     _set_drop(a, drop)
     fn = lib().mtn_check_attn_core_fwd if _check_kernel else lib().mtn_attn_core_fwd
+    if not _check_kernel and ROWS_KERNELS and Lq <= 8 and d_k == 64 and stats is None and drop is None:
+        fn = lib().mtn_decode_attn_fwd
     _launch("attn_core", 4 * B * h * Lq * Lk * d_k, 2 * h * d_k * B * (2 * Lq + 2 * Lk),
             lambda: fn(C.byref(a), stream_ptr()), keep=(q, k, v, out, mask_bits, stats, drop))
 

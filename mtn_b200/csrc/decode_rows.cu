@@ -1,0 +1,267 @@
+// Small-M kernels for KV-cached, last-token-only decoding (reference call form
+// data_utils.py:202-210): at one target position per dialogue a decoding step is ~170 dependent launches over M = B
+// (<= 128) rows.  The tcgen05 kernels pay their fixed costs (TMEM allocation, TMA pipeline fill, 128-row tiles that are
+// mostly padding) on every one of them -- ~6 us per launch for microseconds of work.  These two kernels do the same
+// arithmetic (f16 operands, f32 accumulate, the same softmax formulas) for few rows with nothing to set up:
+//
+//   rows_linear_kernel   out[M, N] = act(A[M, K] W[N, K]^T + bias) (+ residual):  one CTA per 8 output columns, one warp
+//                        per 16 rows, mma.sync.m16n8k16 with both operands read straight from global memory by 16-byte
+//                        loads (a k-permutation that A and B share makes the fragments line up without shared memory);
+//                        the weight matrix is spread over N/8 CTAs, i.e. streamed by the whole machine.
+//   decode_attn_kernel   O = softmax(mask(Q K^T / sqrt(d_k))) V for R <= 8 query rows per batch element and d_k = 64:
+//                        one warp per (batch element, head); keys across lanes for the scores, dims across lanes for
+//                        P V; online softmax in the log2 domain with the reference's FINITE -1e9 (mtn.py:227).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mtn {
+
+struct RowsLinearParams {
+  const __half* A; int lda;
+  const __half* W; int ldw;
+  const float* bias;
+  int M, N, K, act;
+  float* x32; int ld32;      // optional f32 output; with `residual` it is updated in place: x32 += result
+  int residual;
+  __half* out16; int ld16;   // optional f16 output
+};
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// grid = N / 8, block = 32 * ceil(M / 16).  K % 32 == 0.
+__global__ void __launch_bounds__(256) rows_linear_kernel(const RowsLinearParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int n0 = blockIdx.x * 8;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;  // the two rows of this thread's fragments
+  // rows beyond M read row M-1 (valid memory) and are not stored
+  const __half* a_lo = p.A + (size_t)min(r0, p.M - 1) * p.lda + 8 * q;
+  const __half* a_hi = p.A + (size_t)min(r1, p.M - 1) * p.lda + 8 * q;
+  const __half* w_row = p.W + (size_t)(n0 + g) * p.ldw + 8 * q;
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  // Per 32-wide k chunk a thread loads 8 consecutive k of its rows (A: rows g / g + 8; W: output column g) with one
+  // 16-byte load each.  Both mma k16 steps then use the SAME mapping logical-k -> actual-k for A and B
+  // (logical 2q+j -> 8q+j, logical 2q+8+j -> 8q+2+j; second step: +4), so the products pair up correctly.
+#pragma unroll 4
+  for (int kc = 0; kc < p.K; kc += 32) {
+    const uint4 xa = __ldcg(reinterpret_cast<const uint4*>(a_lo + kc));   // activations: written by the predecessor kernel
+    const uint4 xb = __ldcg(reinterpret_cast<const uint4*>(a_hi + kc));
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(w_row + kc));     // weights: read-only
+    mma_16816(c, xa.x, xb.x, xa.y, xb.y, w.x, w.y);
+    mma_16816(c, xa.z, xb.z, xa.w, xb.w, w.z, w.w);
+  }
+  const int col = n0 + 2 * q;
+  float b0 = 0.f, b1 = 0.f;
+  if (p.bias != nullptr) {
+    b0 = __ldg(p.bias + col);
+    b1 = __ldg(p.bias + col + 1);
+  }
+  float v[4] = {c[0] + b0, c[1] + b1, c[2] + b0, c[3] + b1};
+  if (p.act == MTN_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = hh == 0 ? r0 : r1;
+    if (r >= p.M) continue;
+    float y0 = v[2 * hh], y1 = v[2 * hh + 1];
+    if (p.x32 != nullptr) {
+      float2* o = reinterpret_cast<float2*>(p.x32 + (size_t)r * p.ld32 + col);
+      if (p.residual) {  // every element has exactly one owner thread: a plain read-modify-write, deterministic
+        const float2 old = __ldcg(o);
+        y0 += old.x;
+        y1 += old.y;
+      }
+      *o = make_float2(y0, y1);
+    }
+    if (p.out16 != nullptr) *reinterpret_cast<uint32_t*>(p.out16 + (size_t)r * p.ld16 + col) = pack_f16x2_sat(y0, y1);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+struct DecodeAttnParams {
+  const __half *q, *k, *v;
+  __half* out;
+  int ldq, ldk, ldv, ldo;
+  long long sq, sk, sv, so;  // batch strides (elements)
+  const uint32_t* mask_bits;
+  int mask_rows_q, mask_words;
+  int B, h, R, Lk;
+  float scale;
+};
+
+__device__ __forceinline__ float da_ex2(float x) {   // the tensor-core path's exponential (csrc/attn.cu)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int DA_MAXR = 8;
+constexpr int DA_WARPS = 4;
+
+// one warp per (batch element, head); d_k = 64; R <= 8 query rows
+template <int R>
+__global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const DecodeAttnParams p) {
+  __shared__ float sq_[DA_WARPS][R][64];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * DA_WARPS + warp;
+  if (item >= p.B * p.h) return;
+  const int b = item / p.h, hd = item % p.h;
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float c1 = p.scale * LOG2E, t_masked = -1e9f * LOG2E;
+  // queries -> shared memory as f32 (lane holds dims 2*lane, 2*lane+1)
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const __half2 qv = __ldcg(reinterpret_cast<const __half2*>(p.q + (size_t)b * p.sq + (size_t)r * p.ldq + hd * 64) + lane);
+    const float2 f = __half22float2(qv);
+    sq_[warp][r][2 * lane] = f.x;
+    sq_[warp][r][2 * lane + 1] = f.y;
+  }
+  __syncwarp();
+  float m_run[R], l_run[R], o0[R], o1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) m_run[r] = -CUDART_INF_F, l_run[r] = 0.f, o0[r] = 0.f, o1[r] = 0.f;
+  const __half* kb = p.k + (size_t)b * p.sk + hd * 64;
+  const __half* vb = p.v + (size_t)b * p.sv + hd * 64;
+  for (int k0 = 0; k0 < p.Lk; k0 += 32) {
+    const int key = k0 + lane;
+    const bool inb = key < p.Lk;
+    // ---- scores of this lane's key against the R queries
+    float s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[r] = 0.f;
+    if (inb) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)key * p.ldk);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 kv = __ldcg(kr + c);
+        const __half2* hp = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 kf = __half22float2(hp[j]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) s[r] = fmaf(sq_[warp][r][8 * c + 2 * j], kf.x, fmaf(sq_[warp][r][8 * c + 2 * j + 1], kf.y, s[r]));
+        }
+      }
+    }
+    // ---- masks, online softmax (log2 domain)
+    float pr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bool keep = true;
+      if (p.mask_bits != nullptr && inb) {
+        const int mq = p.mask_rows_q == 1 ? 0 : r;
+        const uint32_t w = __ldcg(p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words + (k0 >> 5));
+        keep = (w >> lane) & 1u;
+      }
+      float t = inb ? (keep ? s[r] * c1 : t_masked) : -CUDART_INF_F;
+      float mx = t;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_new = fmaxf(m_run[r], mx);
+      const float e = da_ex2(t - m_new);     // 0 for keys beyond Lk
+      float sum = e;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float alpha = da_ex2(m_run[r] - m_new);  // 0 on the first chunk (m_run = -inf)
+      l_run[r] = l_run[r] * alpha + sum;
+      o0[r] *= alpha;
+      o1[r] *= alpha;
+      m_run[r] = m_new;
+      pr[r] = __half2float(__float2half_rn(e));     // P is rounded to f16 before P V, like the tensor-core path
+    }
+    // ---- P V: lane owns dims 2*lane, 2*lane+1
+    const int nk = min(32, p.Lk - k0);
+    for (int kk = 0; kk < nk; ++kk) {
+      const float2 vf = __half22float2(__ldcg(reinterpret_cast<const __half2*>(vb + (size_t)(k0 + kk) * p.ldv) + lane));
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float pk = __shfl_sync(0xffffffffu, pr[r], kk);
+        o0[r] = fmaf(pk, vf.x, o0[r]);
+        o1[r] = fmaf(pk, vf.y, o1[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float inv = 1.f / l_run[r];
+    *reinterpret_cast<uint32_t*>(p.out + (size_t)b * p.so + (size_t)r * p.ldo + hd * 64 + 2 * lane) = pack_f16x2_sat(o0[r] * inv, o1[r] * inv);
+  }
+}
+
+}  // namespace mtn
+
+extern "C" int mtn_rows_linear_supported(int M, int N, int K) { return (M > 0 && M <= 128 && N % 8 == 0 && K % 32 == 0) ? 1 : 0; }
+
+// Same contract as mtn_linear_fwd for few rows (M <= 128): A f16 [M, K], W f16 [N, K], optional bias / ReLU, f16 and/or
+// f32 outputs; addend must be the f32 output itself (in-place residual, x += ...) or NULL.
+extern "C" int mtn_rows_linear_fwd(const MtnLinearArgs* a, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(a && a->A && a->W && (a->out_f32 || a->out_f16), MTN_E_ARG, "rows_linear: NULL pointer");
+  MTN_REQUIRE(mtn_rows_linear_supported(a->M, a->N, a->K), MTN_E_SHAPE, "rows_linear: M=%d N=%d K=%d (M <= 128, N %% 8 == 0, K %% 32 == 0)",
+              a->M, a->N, a->K);
+  MTN_REQUIRE(a->addend == nullptr || (a->addend == a->out_f32 && a->ld_add == a->ld32 && a->add_period == 0), MTN_E_ARG,
+              "rows_linear: the addend must be the f32 output itself (in-place residual)");
+  MTN_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0 && aligned16(a->A) && aligned16(a->W) && a->batch <= 1 && a->drop_seed == nullptr &&
+                  !a->out16_pre_add,
+              MTN_E_ALIGN, "rows_linear: alignment / unsupported option");
+  MTN_REQUIRE((!a->out_f32 || (a->ld32 % 2 == 0 && (reinterpret_cast<uintptr_t>(a->out_f32) & 7) == 0)) &&
+                  (!a->out_f16 || (a->ld16 % 2 == 0 && (reinterpret_cast<uintptr_t>(a->out_f16) & 3) == 0)),
+              MTN_E_ALIGN, "rows_linear: output alignment");
+  RowsLinearParams p{reinterpret_cast<const __half*>(a->A), a->lda, reinterpret_cast<const __half*>(a->W), a->ldw, a->bias,
+                     a->M, a->N, a->K, a->act, a->out_f32, a->ld32, a->addend != nullptr ? 1 : 0,
+                     reinterpret_cast<__half*>(a->out_f16), a->ld16};
+  const int warps = (a->M + 15) / 16;
+  MTN_CHECK_CUDA(launch_kernel(rows_linear_kernel, dim3(a->N / 8), dim3(32 * warps), 0, static_cast<cudaStream_t>(stream), p));
+  return MTN_OK;
+}
+
+extern "C" int mtn_decode_attn_supported(int Lq, int d_k) { return (Lq >= 1 && Lq <= mtn::DA_MAXR && d_k == 64) ? 1 : 0; }
+
+// Same contract as mtn_attn_core_fwd for Lq <= 8 query rows per batch element and d_k = 64.
+extern "C" int mtn_decode_attn_fwd(const MtnAttnCoreArgs* a, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(a && a->q && a->k && a->v && a->out, MTN_E_ARG, "decode_attn: NULL pointer");
+  MTN_REQUIRE(a->B > 0 && a->h > 0 && a->Lk > 0 && mtn_decode_attn_supported(a->Lq, a->d_k), MTN_E_SHAPE,
+              "decode_attn: B=%d h=%d Lq=%d Lk=%d d_k=%d (Lq <= 8, d_k = 64)", a->B, a->h, a->Lq, a->Lk, a->d_k);
+  MTN_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0 && aligned16(a->q) && aligned16(a->k) &&
+                  aligned16(a->v) && aligned16(a->out) && a->q_batch_stride % 8 == 0 && a->k_batch_stride % 8 == 0 &&
+                  a->v_batch_stride % 8 == 0 && a->o_batch_stride % 8 == 0,
+              MTN_E_ALIGN, "decode_attn: leading dimensions / strides must be multiples of 8 elements, pointers 16-byte aligned");
+  MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,
+              "decode_attn: mask_rows_q=%d must be 1 or Lq=%d", a->mask_rows_q, a->Lq);
+  MTN_REQUIRE(a->stats == nullptr && a->drop_seed == nullptr, MTN_E_ARG, "decode_attn: inference only");
+  auto bs = [](long long given, int L, int ld) { return given > 0 ? given : (long long)L * ld; };
+  DecodeAttnParams p{reinterpret_cast<const __half*>(a->q), reinterpret_cast<const __half*>(a->k), reinterpret_cast<const __half*>(a->v),
+                     reinterpret_cast<__half*>(a->out), a->ldq, a->ldk, a->ldv, a->ldo,
+                     bs(a->q_batch_stride, a->Lq, a->ldq), bs(a->k_batch_stride, a->Lk, a->ldk), bs(a->v_batch_stride, a->Lk, a->ldv),
+                     bs(a->o_batch_stride, a->Lq, a->ldo), a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
+                     1.0f / sqrtf(64.f)};
+  const int items = a->B * a->h;
+  dim3 grid((items + DA_WARPS - 1) / DA_WARPS), block(32 * DA_WARPS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MTN_DA(RR) MTN_CHECK_CUDA(launch_kernel(decode_attn_kernel<RR>, grid, block, 0, st, p))
+  switch (a->Lq) {
+    case 1: MTN_DA(1); break;
+    case 2: MTN_DA(2); break;
+    case 3: MTN_DA(3); break;
+    case 4: MTN_DA(4); break;
+    case 5: MTN_DA(5); break;
+    case 6: MTN_DA(6); break;
+    case 7: MTN_DA(7); break;
+    default: MTN_DA(8); break;
+  }
+#undef MTN_DA
+  return MTN_OK;
+}

@@ -481,6 +481,14 @@ class DecoderEngine(object):
         straight into the cache -> attention of that row over cache rows 0..t (no mask needed: every cached key is in
         the causal past) -> output projection + residual; then the cross sites with a 1-row query over the hoisted
         K/V of the memory stage; then the FFN.  M = B rows per GEMM instead of B*(t+1)."""
+        prev_rows = _lib.ROWS_KERNELS
+        _lib.ROWS_KERNELS = os.environ.get("MTN_B200_DECODE_ROWS", "1") != "0"      # few-row kernels (csrc/decode_rows.cu)
+        try:
+            return self._decode_step(st, x_t, t)
+        finally:
+            _lib.ROWS_KERNELS = prev_rows
+
+    def _decode_step(self, st, x_t, t):
         S, W, B, R = st["S"], st["W"], st["B"], st["R"]
         D = B // R                                           # dialogues; the cross sites see [D, R] query rows
         d, N, M = W["d"], W["N"], W["M"]

@@ -547,3 +547,103 @@ def test_attn_site_fused(L, B, Lq, Lk, d, h, kind):
     L.attn_site_fused(xn_d, x_h, dev(wq), dev(bq), dev(wo), dev(bo), kv_d, 0, d, B, h, Lq, Lk, mask_bits=bits)
     torch.cuda.synchronize()
     assert torch.equal(x_g, x_h), "fused site kernel is not deterministic run to run"
+
+
+# ------------------------------------------------------------------ few-row kernels of KV-cached decoding (csrc/decode_rows.cu)
+@pytest.fixture
+def rows_kernels(L):
+    prev, L.ROWS_KERNELS = L.ROWS_KERNELS, True
+    yield L
+    L.ROWS_KERNELS = prev
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(64, 512, 512, "f16"), (64, 1536, 512, "f16"), (64, 2048, 512, "relu"),
+                                        (64, 512, 2048, "residual"), (5, 3000, 512, "f32"), (128, 512, 512, "residual"),
+                                        (1, 8, 32, "f32"), (100, 64, 96, "both"), (320 // 5, 512, 512, "strided")])
+def test_rows_linear(rows_kernels, M, N, K, mode):
+    """mtn_rows_linear_fwd (mma.sync, operands straight from global memory) against the tcgen05 linear kernel and the
+    f32 oracle arithmetic on the f16-rounded operands."""
+    L = rows_kernels
+    g = torch.Generator().manual_seed(M * 31 + N + K)
+    A = torch.randn(M, K, generator=g).half()
+    W = (torch.randn(N, K, generator=g) * 0.05).half()
+    b = torch.randn(N, generator=g) * 0.1
+    x0 = torch.randn(M, N, generator=g)
+    ref = A.float() @ W.float().t() + b
+    if mode == "relu":
+        ref = ref.relu()
+    Ad, Wd, bd = dev(A), dev(W), dev(b)
+
+    def run(rows):
+        L.ROWS_KERNELS = rows
+        o32 = dev(x0).clone() if mode in ("residual", "both") else torch.full((M, N), float("nan"), device="cuda")
+        big = torch.full((M, 3 * N + 8), float("nan"), device="cuda", dtype=torch.float16)
+        o16 = big[:, N:2 * N] if mode == "strided" else torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+        kw = {}
+        if mode in ("f16", "relu", "strided"):
+            kw = dict(out_f16=o16)
+        elif mode == "f32":
+            kw = dict(out_f32=o32)
+        elif mode == "residual":
+            kw = dict(addend=o32, out_f32=o32)
+        else:
+            kw = dict(addend=o32, out_f32=o32, out_f16=o16)
+        L.linear(Ad, Wd, bd, act=L.ACT_RELU if mode == "relu" else L.ACT_NONE, **kw)
+        torch.cuda.synchronize()
+        if mode == "strided":
+            assert torch.isnan(big[:, :N].float()).all() and torch.isnan(big[:, 2 * N:].float()).all()
+        return o32, o16
+    r32, r16 = run(True)
+    t32, t16 = run(False)
+    want = ref + (x0 if mode in ("residual", "both") else 0)
+    if mode in ("f32", "residual", "both"):
+        assert G.rel_err(r32.cpu(), want) < 2e-5 and G.rel_err(r32.cpu(), t32.cpu()) < 2e-5
+    if mode in ("f16", "relu", "strided", "both"):
+        assert G.rel_err(r16.float().cpu(), want) < 6e-4 and G.rel_err(r16.float().cpu(), t16.float().cpu()) < 6e-4
+
+
+@pytest.mark.parametrize("B,h,R,Lk,kind", [(64, 8, 1, 256, "keypad"), (64, 8, 1, 12, "none"), (16, 8, 5, 64, "keypad"),
+                                           (3, 8, 5, 300, "keypad"), (7, 4, 8, 33, "dense"), (2, 8, 1, 1, "none")])
+def test_decode_attn(rows_kernels, B, h, R, Lk, kind):
+    """mtn_decode_attn_fwd (one warp per (batch element, head)) against the oracle arithmetic and the tcgen05 core."""
+    L = rows_kernels
+    g = torch.Generator().manual_seed(B * 100 + R * 10 + Lk)
+    d = h * 64
+    q = (torch.randn(B, R, d, generator=g) * 1.5).half()
+    k = (torch.randn(B, Lk, d, generator=g) * 1.5).half()
+    v = torch.randn(B, Lk, d, generator=g).half()
+    if kind == "keypad":
+        mask = torch.ones(B, 1, Lk, dtype=torch.bool)
+        lens = torch.randint(max(1, Lk // 2), Lk + 1, (B,), generator=g)
+        for i in range(B):
+            mask[i, 0, int(lens[i]):] = False
+        mask[0] = False                                   # fully masked: uniform average over all Lk keys
+    elif kind == "dense":
+        mask = torch.rand(B, R, Lk, generator=g) > 0.3
+    else:
+        mask = None
+    ref = _attn_ref(q, k, v, mask, h, 64)
+    bits = L.mask_pack(dev(mask)) if mask is not None else None
+    kvd = torch.zeros(B * Lk, 2 * d + 64, device="cuda", dtype=torch.float16)
+    kvd[:, :d] = dev(k).view(-1, d); kvd[:, d:2 * d] = dev(v).view(-1, d)
+    qd = dev(q).view(B * R, d)
+    outs = []
+    for rows in (True, False):
+        L.ROWS_KERNELS = rows
+        out = torch.full((B * R, d), float("nan"), device="cuda", dtype=torch.float16)
+        L.attn_core(qd, kvd[:, :d], kvd[:, d:2 * d], B, h, R, Lk, 64, out, mask_bits=bits)
+        torch.cuda.synchronize()
+        outs.append(out.float().cpu().view(B, R, d))
+    assert torch.isfinite(outs[0]).all()
+    e_ref, e_tc = G.rel_err(outs[0], ref), G.rel_err(outs[0], outs[1])
+    print("decode attn %s: vs oracle %.2e, vs tcgen05 core %.2e" % ((B, h, R, Lk, kind), e_ref, e_tc))
+    assert e_ref < 1e-3 and e_tc < 1e-3, (e_ref, e_tc)
+    if R == 1 and kind == "none":        # the self-attention cache layout (batch strides), rows > t poisoned
+        Tmax = Lk + 3
+        cache = torch.full((B, Tmax, 3 * d), float("nan"), device="cuda", dtype=torch.float16)
+        cache[:, :Lk, d:2 * d] = dev(k); cache[:, :Lk, 2 * d:] = dev(v); cache[:, Lk - 1, :d] = dev(q)[:, 0]
+        L.ROWS_KERNELS = True
+        o2 = torch.full((B, d), float("nan"), device="cuda", dtype=torch.float16)
+        L.attn_core(cache[:, Lk - 1:Lk, :d], cache[:, :, d:2 * d], cache[:, :, 2 * d:], B, h, 1, Lk, 64, o2)
+        torch.cuda.synchronize()
+        assert torch.equal(o2.float().cpu().view(B, 1, d), outs[0])

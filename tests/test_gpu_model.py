@@ -305,7 +305,7 @@ def test_kv_cached_decode_equals_full_prefix(M, cfg2_model):
                 row = model.decode_step(st, b.trg[:, t])
                 errs.append(G.rel_err(row.cpu(), full[:, t].cpu()))
         print("KV-cached rows vs full-prefix decode, worst position: %.2e" % max(errs))
-        assert max(errs) < 2e-4, errs
+        assert max(errs) < 5e-4, errs        # few-row kernels (mma.sync / CUDA-core softmax): same arithmetic, other summation order
         d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
              if k in ("query", "his", "cap", "fts")}
         bd = du.Batch(d["query"], d["his"], None, [f.permute(1, 0, 2) for f in d["fts"]], d["cap"], None, None, 1)

@@ -22,7 +22,13 @@ from mtn_b200.data_utils import Batch  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--tgt-len", type=int, default=256)
 ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--preset", default="cfg2", choices=["cfg2", "cfg5"])
 args = ap.parse_args()
+if args.preset == "cfg5":          # BASELINE configs[4]: N=12 d=1024 h=16, video_len=1024, batch 4 per GPU
+    bench.CFG.update({"N": 12, "d_model": 1024, "d_ff": 4096, "h": 16})
+    bench.SHAPE.update({"B": 4, "Lv": [1024, 256]})
+    if args.batch == 32:
+        args.batch = 4
 torch.manual_seed(7)
 C = bench.CFG
 model = mtn.make_model(C["vocab"], C["vocab"], N=C["N"], d_model=C["d_model"], d_ff=C["d_ff"], h=C["h"],
