@@ -355,7 +355,7 @@ ROWS_KERNELS = False
 
 
 def rows_linear_ok(M, N, K, addend, out_f32, add_period, drop, out16_pre_add):
-    return (ROWS_KERNELS and M <= 128 and N % 8 == 0 and K % 32 == 0 and drop is None and not out16_pre_add and
+    return (ROWS_KERNELS and bool(lib().mtn_rows_linear_supported(int(M), int(N), int(K))) and drop is None and not out16_pre_add and
             (addend is None or (out_f32 is not None and addend.data_ptr() == out_f32.data_ptr() and add_period == 0 and
                                 addend.stride(0) == out_f32.stride(0))))
 

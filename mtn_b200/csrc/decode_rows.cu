@@ -26,6 +26,7 @@ struct RowsLinearParams {
   float* x32; int ld32;      // optional f32 output; with `residual` it is updated in place: x32 += result
   int residual;
   __half* out16; int ld16;   // optional f16 output
+  uint32_t zero;             // always 0 (see the load-scheduling note in the kernel)
 };
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -34,29 +35,72 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// grid = N / 8, block = 32 * ceil(M / 16).  K % 32 == 0.
-__global__ void __launch_bounds__(256) rows_linear_kernel(const RowsLinearParams p) {
+// volatile 16-byte loads: the compiler keeps them in program order ahead of the (volatile) mma sequence, i.e. ALL of a
+// warp's loads are in flight at once instead of being sunk next to their uses to save registers
+__device__ __forceinline__ uint4 ld_cg_v4(const void* ptr) {    // L2 (coherent): activations written by the predecessor kernel
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const void* ptr) {    // read-only path: weights
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+
+// grid = (N / 8, ceil(M / 16)), block = 32 * KS warps: CTA = 16 rows x 8 output columns, the contraction split over its
+// KS warps (each issues ALL of its 16-byte loads before the first mma: one memory round trip per warp), partial sums
+// combined through shared memory in a fixed order (deterministic).  K % (32 * KS) == 0.
+constexpr int RL_MAX_KS = 8;
+template <int CPW>   // 32-wide k chunks per warp
+__global__ void __launch_bounds__(32 * RL_MAX_KS) rows_linear_kernel(const RowsLinearParams p) {
+  __shared__ float part[RL_MAX_KS][32][4];
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int n0 = blockIdx.x * 8;
-  const int r0 = warp * 16 + g, r1 = r0 + 8;  // the two rows of this thread's fragments
+  const int r0 = blockIdx.y * 16 + g, r1 = r0 + 8;  // the two rows of this thread's fragments
+  const int kbase = warp * CPW * 32;
   // rows beyond M read row M-1 (valid memory) and are not stored
-  const __half* a_lo = p.A + (size_t)min(r0, p.M - 1) * p.lda + 8 * q;
-  const __half* a_hi = p.A + (size_t)min(r1, p.M - 1) * p.lda + 8 * q;
-  const __half* w_row = p.W + (size_t)(n0 + g) * p.ldw + 8 * q;
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  const __half* a_lo = p.A + (size_t)min(r0, p.M - 1) * p.lda + 8 * q + kbase;
+  const __half* a_hi = p.A + (size_t)min(r1, p.M - 1) * p.lda + 8 * q + kbase;
+  const __half* w_row = p.W + (size_t)(n0 + g) * p.ldw + 8 * q + kbase;
   // Per 32-wide k chunk a thread loads 8 consecutive k of its rows (A: rows g / g + 8; W: output column g) with one
   // 16-byte load each.  Both mma k16 steps then use the SAME mapping logical-k -> actual-k for A and B
   // (logical 2q+j -> 8q+j, logical 2q+8+j -> 8q+2+j; second step: +4), so the products pair up correctly.
-#pragma unroll 4
-  for (int kc = 0; kc < p.K; kc += 32) {
-    const uint4 xa = __ldcg(reinterpret_cast<const uint4*>(a_lo + kc));   // activations: written by the predecessor kernel
-    const uint4 xb = __ldcg(reinterpret_cast<const uint4*>(a_hi + kc));
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(w_row + kc));     // weights: read-only
-    mma_16816(c, xa.x, xb.x, xa.y, xb.y, w.x, w.y);
-    mma_16816(c, xa.z, xb.z, xa.w, xb.w, w.z, w.w);
+  uint4 xa[CPW], xb[CPW], w[CPW];
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+    xa[c] = ld_cg_v4(a_lo + 32 * c);
+    xb[c] = ld_cg_v4(a_hi + 32 * c);
+    w[c] = ld_nc_v4(w_row + 32 * c);
+  }
+  // The accumulator's initial value is made to DEPEND on every loaded register (their XOR, masked with a run-time
+  // zero the compiler cannot see through): ptxas must then complete all loads before the first mma instead of sinking
+  // each load next to its use to save registers (load -> mma -> load ...: one memory round trip per chunk).
+  uint32_t fold = 0u;
+#pragma unroll
+  for (int c = 0; c < CPW; ++c)
+    fold ^= (xa[c].x ^ xa[c].y ^ xa[c].z ^ xa[c].w) ^ (xb[c].x ^ xb[c].y ^ xb[c].z ^ xb[c].w) ^ (w[c].x ^ w[c].y ^ w[c].z ^ w[c].w);
+  float c4[4] = {__uint_as_float(fold & p.zero), 0.f, 0.f, 0.f};   // p.zero == 0: exactly 0.0f
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+    mma_16816(c4, xa[c].x, xb[c].x, xa[c].y, xb[c].y, w[c].x, w[c].y);
+    mma_16816(c4, xa[c].z, xb[c].z, xa[c].w, xb[c].w, w[c].z, w[c].w);
+  }
+  const int KS = blockDim.x >> 5;
+  if (KS > 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) part[warp][lane][i] = c4[i];
+    __syncthreads();
+    if (warp != 0) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float acc = part[0][lane][i];
+      for (int ws = 1; ws < KS; ++ws) acc += part[ws][lane][i];   // fixed order
+      c4[i] = acc;
+    }
   }
   const int col = n0 + 2 * q;
   float b0 = 0.f, b1 = 0.f;
@@ -64,7 +108,7 @@ __global__ void __launch_bounds__(256) rows_linear_kernel(const RowsLinearParams
     b0 = __ldg(p.bias + col);
     b1 = __ldg(p.bias + col + 1);
   }
-  float v[4] = {c[0] + b0, c[1] + b1, c[2] + b0, c[3] + b1};
+  float v[4] = {c4[0] + b0, c4[1] + b1, c4[2] + b0, c4[3] + b1};
   if (p.act == MTN_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -108,64 +152,69 @@ __device__ __forceinline__ float da_ex2(float x) {   // the tensor-core path's e
 constexpr int DA_MAXR = 8;
 constexpr int DA_WARPS = 4;
 
-// one warp per (batch element, head); d_k = 64; R <= 8 query rows
+// One CTA per (batch element, head), d_k = 64, R <= 8 query rows.  The keys are dealt to the CTA's 4 warps in chunks
+// of 32 (warp w takes chunks w, w + 4, ...): every warp runs an online softmax over its keys (lane = key for the
+// scores, lane = two output dims for P V), then the partial (max, sum, O) triples are merged through shared memory in
+// a fixed order.  All loads of a chunk are issued before its arithmetic.
 template <int R>
 __global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const DecodeAttnParams p) {
-  __shared__ float sq_[DA_WARPS][R][64];
+  __shared__ float sq_[R][64];
+  __shared__ float sm_[DA_WARPS][R], sl_[DA_WARPS][R], so_[DA_WARPS][R][64];
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * DA_WARPS + warp;
-  if (item >= p.B * p.h) return;
-  const int b = item / p.h, hd = item % p.h;
+  const int b = blockIdx.x / p.h, hd = blockIdx.x % p.h;
   constexpr float LOG2E = 1.4426950408889634f;
   const float c1 = p.scale * LOG2E, t_masked = -1e9f * LOG2E;
-  // queries -> shared memory as f32 (lane holds dims 2*lane, 2*lane+1)
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const __half2 qv = __ldcg(reinterpret_cast<const __half2*>(p.q + (size_t)b * p.sq + (size_t)r * p.ldq + hd * 64) + lane);
-    const float2 f = __half22float2(qv);
-    sq_[warp][r][2 * lane] = f.x;
-    sq_[warp][r][2 * lane + 1] = f.y;
+  // queries -> shared memory as f32
+  for (int i = threadIdx.x; i < R * 32; i += 32 * DA_WARPS) {
+    const int r = i >> 5, l2 = i & 31;
+    const float2 f = __half22float2(__ldcg(reinterpret_cast<const __half2*>(p.q + (size_t)b * p.sq + (size_t)r * p.ldq + hd * 64) + l2));
+    sq_[r][2 * l2] = f.x;
+    sq_[r][2 * l2 + 1] = f.y;
   }
-  __syncwarp();
+  __syncthreads();
   float m_run[R], l_run[R], o0[R], o1[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) m_run[r] = -CUDART_INF_F, l_run[r] = 0.f, o0[r] = 0.f, o1[r] = 0.f;
   const __half* kb = p.k + (size_t)b * p.sk + hd * 64;
   const __half* vb = p.v + (size_t)b * p.sv + hd * 64;
-  for (int k0 = 0; k0 < p.Lk; k0 += 32) {
+  for (int k0 = warp * 32; k0 < p.Lk; k0 += 32 * DA_WARPS) {
     const int key = k0 + lane;
     const bool inb = key < p.Lk;
-    // ---- scores of this lane's key against the R queries
+    // ---- this lane's key row (128 B) and the chunk's mask words, requested together
+    uint4 kv[8];
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)min(key, p.Lk - 1) * p.ldk);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kv[c] = ld_cg_v4(kr + c);
+    uint32_t mw[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mw[r] = 0xffffffffu;
+      if (p.mask_bits != nullptr) {
+        const int mq = p.mask_rows_q == 1 ? 0 : r;
+        mw[r] = __ldcg(p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words + (k0 >> 5));
+      }
+    }
     float s[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) s[r] = 0.f;
-    if (inb) {
-      const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)key * p.ldk);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 kv = __ldcg(kr + c);
-        const __half2* hp = reinterpret_cast<const __half2*>(&kv);
+    for (int c = 0; c < 8; ++c) {
+      const __half2* hp = reinterpret_cast<const __half2*>(&kv[c]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 kf = __half22float2(hp[j]);
+      for (int j = 0; j < 4; ++j) {
+        const float2 kf = __half22float2(hp[j]);
 #pragma unroll
-          for (int r = 0; r < R; ++r) s[r] = fmaf(sq_[warp][r][8 * c + 2 * j], kf.x, fmaf(sq_[warp][r][8 * c + 2 * j + 1], kf.y, s[r]));
-        }
+        for (int r = 0; r < R; ++r) s[r] = fmaf(sq_[r][8 * c + 2 * j], kf.x, fmaf(sq_[r][8 * c + 2 * j + 1], kf.y, s[r]));
       }
     }
-    // ---- masks, online softmax (log2 domain)
+    // ---- online softmax (log2 domain)
     float pr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      bool keep = true;
-      if (p.mask_bits != nullptr && inb) {
-        const int mq = p.mask_rows_q == 1 ? 0 : r;
-        const uint32_t w = __ldcg(p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words + (k0 >> 5));
-        keep = (w >> lane) & 1u;
-      }
-      float t = inb ? (keep ? s[r] * c1 : t_masked) : -CUDART_INF_F;
+      const bool keep = (mw[r] >> lane) & 1u;
+      const float t = inb ? (keep ? s[r] * c1 : t_masked) : -CUDART_INF_F;
       float mx = t;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -181,28 +230,62 @@ __global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const Decode
       m_run[r] = m_new;
       pr[r] = __half2float(__float2half_rn(e));     // P is rounded to f16 before P V, like the tensor-core path
     }
-    // ---- P V: lane owns dims 2*lane, 2*lane+1
+    // ---- P V: lane owns dims 2*lane, 2*lane+1; the chunk's 32 value rows are requested 8 at a time
     const int nk = min(32, p.Lk - k0);
-    for (int kk = 0; kk < nk; ++kk) {
-      const float2 vf = __half22float2(__ldcg(reinterpret_cast<const __half2*>(vb + (size_t)(k0 + kk) * p.ldv) + lane));
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float pk = __shfl_sync(0xffffffffu, pr[r], kk);
-        o0[r] = fmaf(pk, vf.x, o0[r]);
-        o1[r] = fmaf(pk, vf.y, o1[r]);
+    for (int k8 = 0; k8 < 32; k8 += 8) {
+      if (k8 >= nk) break;
+      __half2 vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        vv[u] = __ldcg(reinterpret_cast<const __half2*>(vb + (size_t)min(k0 + k8 + u, p.Lk - 1) * p.ldv) + lane);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float2 vf = __half22float2(vv[u]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float pk = __shfl_sync(0xffffffffu, pr[r], k8 + u);   // 0 for keys beyond Lk
+          o0[r] = fmaf(pk, vf.x, o0[r]);
+          o1[r] = fmaf(pk, vf.y, o1[r]);
+        }
       }
     }
   }
+  // ---- merge the warps' partial results (fixed order)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const float inv = 1.f / l_run[r];
-    *reinterpret_cast<uint32_t*>(p.out + (size_t)b * p.so + (size_t)r * p.ldo + hd * 64 + 2 * lane) = pack_f16x2_sat(o0[r] * inv, o1[r] * inv);
+    if (lane == 0) sm_[warp][r] = m_run[r], sl_[warp][r] = l_run[r];
+    so_[warp][r][2 * lane] = o0[r];
+    so_[warp][r][2 * lane + 1] = o1[r];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * 32; i += 32 * DA_WARPS) {
+    const int r = i >> 5, l2 = i & 31;
+    float m = sm_[0][r];
+#pragma unroll
+    for (int w = 1; w < DA_WARPS; ++w) m = fmaxf(m, sm_[w][r]);
+    float l = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) {
+      const float f = da_ex2(sm_[w][r] - m);   // 0 for a warp that saw no key (its max is -inf)
+      l = fmaf(sl_[w][r], f, l);
+      a0 = fmaf(so_[w][r][2 * l2], f, a0);
+      a1 = fmaf(so_[w][r][2 * l2 + 1], f, a1);
+    }
+    const float inv = 1.f / l;
+    *reinterpret_cast<uint32_t*>(p.out + (size_t)b * p.so + (size_t)r * p.ldo + hd * 64 + 2 * l2) = pack_f16x2_sat(a0 * inv, a1 * inv);
   }
 }
 
 }  // namespace mtn
 
-extern "C" int mtn_rows_linear_supported(int M, int N, int K) { return (M > 0 && M <= 128 && N % 8 == 0 && K % 32 == 0) ? 1 : 0; }
+extern "C" int mtn_rows_linear_supported(int M, int N, int K) {
+  if (!(M > 0 && M <= 128 && N > 0 && N % 8 == 0 && K > 0 && K % 32 == 0)) return 0;
+  const int chunks = K / 32;
+  for (int ks = 1; ks <= mtn::RL_MAX_KS; ++ks)
+    if (chunks % ks == 0 && chunks / ks <= 8) return 1;
+  return 0;
+}
 
 // Same contract as mtn_linear_fwd for few rows (M <= 128): A f16 [M, K], W f16 [N, K], optional bias / ReLU, f16 and/or
 // f32 outputs; addend must be the f32 output itself (in-place residual, x += ...) or NULL.
@@ -221,9 +304,30 @@ extern "C" int mtn_rows_linear_fwd(const MtnLinearArgs* a, void* stream) {
               MTN_E_ALIGN, "rows_linear: output alignment");
   RowsLinearParams p{reinterpret_cast<const __half*>(a->A), a->lda, reinterpret_cast<const __half*>(a->W), a->ldw, a->bias,
                      a->M, a->N, a->K, a->act, a->out_f32, a->ld32, a->addend != nullptr ? 1 : 0,
-                     reinterpret_cast<__half*>(a->out_f16), a->ld16};
-  const int warps = (a->M + 15) / 16;
-  MTN_CHECK_CUDA(launch_kernel(rows_linear_kernel, dim3(a->N / 8), dim3(32 * warps), 0, static_cast<cudaStream_t>(stream), p));
+                     reinterpret_cast<__half*>(a->out_f16), a->ld16, 0u};
+  // contraction split: at most 8 warps, at most 8 chunks (of 32) per warp in flight; K = 512 -> 4 warps x 4 chunks,
+  // K = 2048 -> 8 warps x 8 chunks; other K: the largest split that divides it
+  const int chunks = a->K / 32;
+  int ks = 0;
+  for (int c = RL_MAX_KS; c >= 1 && ks == 0; --c)
+    if (chunks % c == 0 && chunks / c <= 8) ks = c;
+  if (ks == 0) ks = RL_MAX_KS + 1;
+  MTN_REQUIRE(ks <= RL_MAX_KS && chunks % ks == 0, MTN_E_SHAPE, "rows_linear: K=%d has no supported split (K / 32 must factor into <= 8 warps x <= 8 chunks)", a->K);
+  const int cpw = chunks / ks;
+  dim3 grid(a->N / 8, (a->M + 15) / 16), block(32 * ks);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MTN_RL(C) MTN_CHECK_CUDA(launch_kernel(rows_linear_kernel<C>, grid, block, 0, st, p))
+  switch (cpw) {
+    case 1: MTN_RL(1); break;
+    case 2: MTN_RL(2); break;
+    case 3: MTN_RL(3); break;
+    case 4: MTN_RL(4); break;
+    case 5: MTN_RL(5); break;
+    case 6: MTN_RL(6); break;
+    case 7: MTN_RL(7); break;
+    default: MTN_RL(8); break;
+  }
+#undef MTN_RL
   return MTN_OK;
 }
 
@@ -248,8 +352,7 @@ extern "C" int mtn_decode_attn_fwd(const MtnAttnCoreArgs* a, void* stream) {
                      bs(a->q_batch_stride, a->Lq, a->ldq), bs(a->k_batch_stride, a->Lk, a->ldk), bs(a->v_batch_stride, a->Lk, a->ldv),
                      bs(a->o_batch_stride, a->Lq, a->ldo), a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
                      1.0f / sqrtf(64.f)};
-  const int items = a->B * a->h;
-  dim3 grid((items + DA_WARPS - 1) / DA_WARPS), block(32 * DA_WARPS);
+  dim3 grid(a->B * a->h), block(32 * DA_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MTN_DA(RR) MTN_CHECK_CUDA(launch_kernel(decode_attn_kernel<RR>, grid, block, 0, st, p))
   switch (a->Lq) {

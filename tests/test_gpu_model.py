@@ -348,8 +348,9 @@ def test_batched_beam_search_on_the_kernels(M, cfg2_model, monkeypatch):
             for i in range(D):
                 ref = du.beam_search_decode(model, mk(slice(i, i + 1)), steps, 2, 0, 3, 1, beam=5, penalty=1.0, nbest=5)
                 assert [list(map(int, h)) for h, _ in ref[0]] == [list(map(int, h)) for h, _ in got[i][0]], i
-                assert np.allclose([s for _, s in ref[0]], [s for _, s in got[i][0]], rtol=0, atol=5e-3)
-                assert abs(ref[1] - got[i][1]) < 5e-3
+                # cumulative log-probabilities over 8 steps through a generator scaled x8: f16-operand noise x8 per step
+                assert np.allclose([s for _, s in ref[0]], [s for _, s in got[i][0]], rtol=0, atol=2e-2)
+                assert abs(ref[1] - got[i][1]) < 2e-2
             monkeypatch.delenv("MTN_B200_BEAM_SERIAL")
             one = du.beam_search_decode(model, mk(slice(1, 2)), steps, 2, 0, 3, 1, beam=5, penalty=1.0, nbest=5)
             assert [list(map(int, h)) for h, _ in one[0]] == [list(map(int, h)) for h, _ in got[1][0]]
