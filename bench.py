@@ -757,12 +757,29 @@ def main():
             e1.record(); torch.cuda.synchronize()
             us_step = e0.elapsed_time(e1) * 1e3 / (3 * (len(dec.graphs) - 1))
             hbm_pk = peaks.get("hbm_gbs", 6650.0)
+            # launches of one cached step (eager, untimed): our kernels by name
+            try:
+                _lib.RECORD = []
+                with torch.no_grad():
+                    model.decode_step(dec.state, dec.ys[:, 3], 3)
+                torch.cuda.synchronize()
+                rec_d, _lib.RECORD = _lib.RECORD, None
+                by = {}
+                for r_ in rec_d:
+                    by[r_[0]] = by.get(r_[0], 0) + 1
+                decode["launches_per_step"] = len(rec_d)
+                decode["launches_by_kernel"] = by
+                del rec_d
+            except Exception as e:
+                _lib.RECORD = None
+                decode["launches_per_step_error"] = repr(e)[:200]
             decode["roofline"] = {"bound": "hbm", "achieved": step_bytes / (us_step * 1e-6) / 1e9, "peak": hbm_pk, "unit": "GB/s",
                                   "frac": step_bytes / (us_step * 1e-6) / 1e9 / hbm_pk, "us_per_step": us_step,
                                   "bytes_per_step": step_bytes,
                                   "note": "algorithmic bytes of one cached step (f16 weights %.0f MB + memory K/V %.0f MB + "
                                           "self cache %.1f MB) / CUDA-event time of the step graphs; the step is a chain of "
-                                          "~170 dependent launches, i.e. launch-latency bound, not bandwidth bound"
+                                          "~130 dependent few-row launches (csrc/decode_rows.cu), each one memory round trip "
+                                          "deep: latency bound, not bandwidth bound"
                                           % (w_bytes / 1e6, kv_mem / 1e6, kv_self / 1e6)}
         except Exception as e:
             decode["roofline"] = {"error": repr(e)[:300]}

@@ -222,6 +222,12 @@ int mtn_attn_core_fwd(const MtnAttnCoreArgs *args, void *stream);
  *                          honoured: the self-attention cache is addressed in place).  One warp per (batch, head).  */
 int mtn_rows_linear_supported(int M, int N, int K);
 int mtn_rows_linear_fwd(const MtnLinearArgs *args, void *stream);
+/*   mtn_rows_ln_linear_fwd = mtn_layernorm_fwd + mtn_rows_linear_fwd in ONE launch (bit-identical): out_f16 = act(LN(x) W^T + b),
+ *                          x f32 [M, d] with row pitch ldx, d in {128, 256, 512, 1024}, M <= 128.                          */
+int mtn_rows_ln_linear_supported(int M, int N, int d);
+int mtn_rows_ln_linear_fwd(const float *x, int ldx, const float *a_2, const float *b_2, float eps, int M, int d,
+                           const void *W, int ldw, const float *bias, int N, int act, void *out_f16, int ld16,
+                           void *stream);
 int mtn_decode_attn_supported(int Lq, int d_k);
 int mtn_decode_attn_fwd(const MtnAttnCoreArgs *args, void *stream);
 

@@ -166,6 +166,9 @@ SYMBOLS = {
     "mtn_attn_site_fwd": (C.c_int, [C.POINTER(AttnSiteArgs), C.c_void_p]),
     "mtn_rows_linear_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "mtn_rows_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "mtn_rows_ln_linear_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "mtn_rows_ln_linear_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mtn_decode_attn_supported": (C.c_int, [C.c_int, C.c_int]),
     "mtn_decode_attn_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
     "mtn_attn_site_fused_supported": (C.c_int, [C.c_int, C.c_int]),
@@ -411,6 +414,27 @@ def ln_linear(x, a_2, b_2, eps, W, bias=None, act=ACT_NONE, out_f16=None):
     _launch("ln_linear", 2 * M * N * d, M * d * 4 + N * d * 2 + M * N * 2,
             lambda: lib().mtn_ln_linear_fwd(ptr(x), ptr(a_2), ptr(b_2), float(eps), M, d, ptr(W), W.stride(0), ptr(bias), N,
                                             int(act), ptr(out_f16), out_f16.stride(0), stream_ptr()),
+            keep=(x, a_2, b_2, W, bias, out_f16))
+
+
+def rows_ln_linear_ok(M, N, d):
+    # every CTA of a row block (N / 8 of them) recomputes the block's LayerNorm statistics: worth it for N <= 512
+    # (3.9 us vs 1.8 + 3.3 us as two launches), not for wide outputs (N = 2048: 13 us vs 7.7; profiles/r02_decode_kernels.txt)
+    return ROWS_KERNELS and N <= 512 and bool(lib().mtn_rows_ln_linear_supported(int(M), int(N), int(d)))
+
+
+def rows_ln_linear(x, a_2, b_2, eps, W, bias=None, act=ACT_NONE, out_f16=None):
+    """out_f16 [M, N] = act(LN(x) W^T + bias) for M <= 128 in ONE launch (csrc/decode_rows.cu); bit-identical to
+    layernorm(out_f16=...) + linear(out_f16=...).  x: [M, d] f32 (row stride allowed), out_f16: row stride allowed."""
+    _req(x, torch.float32, "x"); _req(a_2, torch.float32, "a_2"); _req(b_2, torch.float32, "b_2")
+    _req(W, torch.float16, "W"); _req(bias, torch.float32, "bias"); _req(out_f16, torch.float16, "out_f16")
+    assert x.dim() == 2 and W.dim() == 2 and W.shape[1] == x.shape[1] and out_f16.dim() == 2
+    M, d = x.shape
+    N = W.shape[0]
+    assert tuple(out_f16.shape) == (M, N) and a_2.is_contiguous() and b_2.is_contiguous()
+    _launch("rows_ln_linear", 2 * M * N * d, M * d * 4 + N * d * 2 + M * N * 2,
+            lambda: lib().mtn_rows_ln_linear_fwd(ptr(x), x.stride(0), ptr(a_2), ptr(b_2), float(eps), M, d, ptr(W), W.stride(0),
+                                                 ptr(bias), N, int(act), ptr(out_f16), out_f16.stride(0), stream_ptr()),
             keep=(x, a_2, b_2, W, bias, out_f16))
 
 

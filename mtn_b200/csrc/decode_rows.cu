@@ -132,6 +132,126 @@ __global__ void __launch_bounds__(32 * RL_MAX_KS) rows_linear_kernel(const RowsL
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// The same with the reference's LayerNorm (mtn.py:111-114) in front:  out16[M, N] = act(LN(x)[M, K] W[N, K]^T + bias),
+// x f32.  A CTA (16 rows x 8 output columns, KS warps over the contraction) first requests everything it will need --
+// the raw x values of its mma fragments, a_2 / b_2, its weights -- then its warps compute mean / 1/(std + eps) of the 16
+// rows with exactly the arithmetic (and summation order) of layernorm_rows_kernel, and the fragments are normalised and
+// rounded to f16 in registers: bit-identical to mtn_layernorm_fwd + mtn_rows_linear_fwd, one launch, one memory round
+// trip.  The statistics are recomputed by every CTA of a row block (N / 8 of them): 2 KB per row out of L2.
+struct RowsLnLinearParams {
+  const float* x; int ldx;
+  const float* a2; const float* b2; float eps;
+  const __half* W; int ldw;
+  const float* bias;
+  int M, N, act;
+  __half* out16; int ld16;
+  uint32_t zero;
+};
+
+template <int VPL>   // K = 128 * VPL
+__global__ void __launch_bounds__(256) rows_ln_linear_kernel(const RowsLnLinearParams p) {
+  constexpr int K = 128 * VPL;
+  constexpr int KS = (K / 32 >= 8) ? 8 : K / 32;   // warps over the contraction
+  constexpr int CPW = K / (32 * KS);              // 32-wide chunks per warp
+  constexpr int RPW = 16 / KS;                    // rows whose statistics a warp computes
+  __shared__ float part[KS][32][4];
+  __shared__ float2 stats[16];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int n0 = blockIdx.x * 8;
+  const int rb = blockIdx.y * 16;
+  const int r0 = rb + g, r1 = r0 + 8;
+  const int kbase = warp * CPW * 32 + 8 * q;
+  const float* x_lo = p.x + (size_t)min(r0, p.M - 1) * p.ldx + kbase;
+  const float* x_hi = p.x + (size_t)min(r1, p.M - 1) * p.ldx + kbase;
+  // (1) everything the mma phase needs, requested now
+  float4 xl[CPW][2], xh[CPW][2], ga[CPW][2], gb[CPW][2];
+  uint4 w[CPW];
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      xl[c][u] = __ldcg(reinterpret_cast<const float4*>(x_lo + 32 * c) + u);
+      xh[c][u] = __ldcg(reinterpret_cast<const float4*>(x_hi + 32 * c) + u);
+      ga[c][u] = __ldg(reinterpret_cast<const float4*>(p.a2 + kbase + 32 * c) + u);
+      gb[c][u] = __ldg(reinterpret_cast<const float4*>(p.b2 + kbase + 32 * c) + u);
+    }
+    w[c] = ld_nc_v4(p.W + (size_t)(n0 + g) * p.ldw + kbase + 32 * c);
+  }
+  // (2) row statistics: the arithmetic of layernorm_rows_kernel<VPL> (lane l holds float4 l + 32 i of the row)
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int rl = warp * RPW + rr;
+    const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)min(rb + rl, p.M - 1) * p.ldx);
+    float4 v[VPL];
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i] = __ldcg(xr + lane + 32 * i);
+      sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    const float mean = sm * (1.f / K);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) stats[rl] = make_float2(mean, 1.f / (sqrtf(ss * (1.f / (K - 1))) + p.eps));
+  }
+  __syncthreads();
+  // (3) normalise the fragments: a_2 * (x - mean) * inv + b_2, rounded to f16 like the LayerNorm kernel's y_f16
+  const float2 sl = stats[g], sh = stats[g + 8];
+  float c4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+    uint32_t al[4], ah[4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float4 a = ga[c][u], bq = gb[c][u], l4 = xl[c][u], h4 = xh[c][u];
+      al[2 * u] = pack_f16x2_sat(a.x * (l4.x - sl.x) * sl.y + bq.x, a.y * (l4.y - sl.x) * sl.y + bq.y);
+      al[2 * u + 1] = pack_f16x2_sat(a.z * (l4.z - sl.x) * sl.y + bq.z, a.w * (l4.w - sl.x) * sl.y + bq.w);
+      ah[2 * u] = pack_f16x2_sat(a.x * (h4.x - sh.x) * sh.y + bq.x, a.y * (h4.y - sh.x) * sh.y + bq.y);
+      ah[2 * u + 1] = pack_f16x2_sat(a.z * (h4.z - sh.x) * sh.y + bq.z, a.w * (h4.w - sh.x) * sh.y + bq.w);
+    }
+    mma_16816(c4, al[0], ah[0], al[1], ah[1], w[c].x, w[c].y);
+    mma_16816(c4, al[2], ah[2], al[3], ah[3], w[c].z, w[c].w);
+  }
+  if (KS > 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) part[warp][lane][i] = c4[i];
+    __syncthreads();
+    if (warp != 0) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float acc = part[0][lane][i];
+#pragma unroll
+      for (int ws = 1; ws < KS; ++ws) acc += part[ws][lane][i];
+      c4[i] = acc;
+    }
+  }
+  const int col = n0 + 2 * q;
+  float b0 = 0.f, b1 = 0.f;
+  if (p.bias != nullptr) {
+    b0 = __ldg(p.bias + col);
+    b1 = __ldg(p.bias + col + 1);
+  }
+  float v[4] = {c4[0] + b0, c4[1] + b1, c4[2] + b0, c4[3] + b1};
+  if (p.act == MTN_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (r0 < p.M) *reinterpret_cast<uint32_t*>(p.out16 + (size_t)r0 * p.ld16 + col) = pack_f16x2_sat(v[0], v[1]);
+  if (r1 < p.M) *reinterpret_cast<uint32_t*>(p.out16 + (size_t)r1 * p.ld16 + col) = pack_f16x2_sat(v[2], v[3]);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 struct DecodeAttnParams {
   const __half *q, *k, *v;
   __half* out;
@@ -150,12 +270,20 @@ __device__ __forceinline__ float da_ex2(float x) {   // the tensor-core path's e
 }
 
 constexpr int DA_MAXR = 8;
-constexpr int DA_WARPS = 4;
+constexpr int DA_WARPS = 8;
 
-// One CTA per (batch element, head), d_k = 64, R <= 8 query rows.  The keys are dealt to the CTA's 4 warps in chunks
-// of 32 (warp w takes chunks w, w + 4, ...): every warp runs an online softmax over its keys (lane = key for the
-// scores, lane = two output dims for P V), then the partial (max, sum, O) triples are merged through shared memory in
-// a fixed order.  All loads of a chunk are issued before its arithmetic.
+__device__ __forceinline__ uint32_t ld_cg_b32(const void* ptr) {
+  uint32_t r;
+  asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(r) : "l"(ptr));
+  return r;
+}
+
+// One CTA (8 warps) per (batch element, head), d_k = 64, R <= 8 query rows.  The keys are dealt to the warps in chunks
+// of 32 (warp w takes chunks w, w + 8, ...; up to 256 keys in one pass).  Per chunk a warp requests EVERYTHING first --
+// its lane's key row (128 B) and, for P V, its two output dims of all 32 value rows -- so a launch is one memory round
+// trip deep (the K / V caches of a decoding step do not fit the L2: this kernel is HBM-latency bound otherwise); then an
+// online softmax (lane = key for the scores, lane = two dims for P V) and a fixed-order merge of the warps' partial
+// (max, sum, O) triples through shared memory.
 template <int R>
 __global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const DecodeAttnParams p) {
   __shared__ float sq_[R][64];
@@ -166,36 +294,46 @@ __global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const Decode
   const int b = blockIdx.x / p.h, hd = blockIdx.x % p.h;
   constexpr float LOG2E = 1.4426950408889634f;
   const float c1 = p.scale * LOG2E, t_masked = -1e9f * LOG2E;
-  // queries -> shared memory as f32
-  for (int i = threadIdx.x; i < R * 32; i += 32 * DA_WARPS) {
-    const int r = i >> 5, l2 = i & 31;
-    const float2 f = __half22float2(__ldcg(reinterpret_cast<const __half2*>(p.q + (size_t)b * p.sq + (size_t)r * p.ldq + hd * 64) + l2));
-    sq_[r][2 * l2] = f.x;
-    sq_[r][2 * l2 + 1] = f.y;
-  }
-  __syncthreads();
+  const __half* kb = p.k + (size_t)b * p.sk + hd * 64;
+  const __half* vb = p.v + (size_t)b * p.sv + hd * 64;
   float m_run[R], l_run[R], o0[R], o1[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) m_run[r] = -CUDART_INF_F, l_run[r] = 0.f, o0[r] = 0.f, o1[r] = 0.f;
-  const __half* kb = p.k + (size_t)b * p.sk + hd * 64;
-  const __half* vb = p.v + (size_t)b * p.sv + hd * 64;
-  for (int k0 = warp * 32; k0 < p.Lk; k0 += 32 * DA_WARPS) {
+  bool have_q = false;
+  for (int k0 = warp * 32; k0 < p.Lk || !have_q; k0 += 32 * DA_WARPS) {
+    const bool active = k0 < p.Lk;            // (a warp without keys still takes part in the query staging below)
     const int key = k0 + lane;
     const bool inb = key < p.Lk;
-    // ---- this lane's key row (128 B) and the chunk's mask words, requested together
+    // ---- request the chunk: key row of this lane, value rows (this lane's two dims), mask words
     uint4 kv[8];
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)min(key, p.Lk - 1) * p.ldk);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) kv[c] = ld_cg_v4(kr + c);
+    uint32_t vv[32];
     uint32_t mw[R];
+    if (active) {
+      const uint8_t* kr = reinterpret_cast<const uint8_t*>(kb + (size_t)min(key, p.Lk - 1) * p.ldk);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      mw[r] = 0xffffffffu;
-      if (p.mask_bits != nullptr) {
-        const int mq = p.mask_rows_q == 1 ? 0 : r;
-        mw[r] = __ldcg(p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words + (k0 >> 5));
+      for (int c = 0; c < 8; ++c) kv[c] = ld_cg_v4(kr + 16 * c);
+#pragma unroll
+      for (int u = 0; u < 32; ++u) vv[u] = ld_cg_b32(vb + (size_t)min(k0 + u, p.Lk - 1) * p.ldv + 2 * lane);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        mw[r] = 0xffffffffu;
+        if (p.mask_bits != nullptr) {
+          const int mq = p.mask_rows_q == 1 ? 0 : r;
+          mw[r] = __ldcg(p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words + (k0 >> 5));
+        }
       }
     }
+    if (!have_q) {   // queries -> shared memory as f32 (requested after the chunk's loads, used after the barrier)
+      for (int i = threadIdx.x; i < R * 32; i += 32 * DA_WARPS) {
+        const int r = i >> 5, l2 = i & 31;
+        const float2 f = __half22float2(__ldcg(reinterpret_cast<const __half2*>(p.q + (size_t)b * p.sq + (size_t)r * p.ldq + hd * 64) + l2));
+        sq_[r][2 * l2] = f.x;
+        sq_[r][2 * l2 + 1] = f.y;
+      }
+      __syncthreads();
+      have_q = true;
+    }
+    if (!active) break;
     float s[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) s[r] = 0.f;
@@ -230,24 +368,15 @@ __global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const Decode
       m_run[r] = m_new;
       pr[r] = __half2float(__float2half_rn(e));     // P is rounded to f16 before P V, like the tensor-core path
     }
-    // ---- P V: lane owns dims 2*lane, 2*lane+1; the chunk's 32 value rows are requested 8 at a time
-    const int nk = min(32, p.Lk - k0);
+    // ---- P V: lane owns dims 2*lane, 2*lane+1 (rows beyond Lk were clamped to a valid row; their P is 0)
 #pragma unroll
-    for (int k8 = 0; k8 < 32; k8 += 8) {
-      if (k8 >= nk) break;
-      __half2 vv[8];
+    for (int u = 0; u < 32; ++u) {
+      const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vv[u]));
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        vv[u] = __ldcg(reinterpret_cast<const __half2*>(vb + (size_t)min(k0 + k8 + u, p.Lk - 1) * p.ldv) + lane);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float2 vf = __half22float2(vv[u]);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float pk = __shfl_sync(0xffffffffu, pr[r], k8 + u);   // 0 for keys beyond Lk
-          o0[r] = fmaf(pk, vf.x, o0[r]);
-          o1[r] = fmaf(pk, vf.y, o1[r]);
-        }
+      for (int r = 0; r < R; ++r) {
+        const float pk = __shfl_sync(0xffffffffu, pr[r], u);
+        o0[r] = fmaf(pk, vf.x, o0[r]);
+        o1[r] = fmaf(pk, vf.y, o1[r]);
       }
     }
   }
@@ -328,6 +457,34 @@ extern "C" int mtn_rows_linear_fwd(const MtnLinearArgs* a, void* stream) {
     default: MTN_RL(8); break;
   }
 #undef MTN_RL
+  return MTN_OK;
+}
+
+extern "C" int mtn_rows_ln_linear_supported(int M, int N, int d) {
+  return (M > 0 && M <= 128 && N > 0 && N % 8 == 0 && (d == 128 || d == 256 || d == 512 || d == 1024)) ? 1 : 0;
+}
+
+// out_f16[M, N] = act(LN(x)[M, d] W[N, d]^T + bias) for M <= 128: the contract of mtn_ln_linear_fwd (and bit-identical to
+// mtn_layernorm_fwd + mtn_rows_linear_fwd), one launch.
+extern "C" int mtn_rows_ln_linear_fwd(const float* x, int ldx, const float* a_2, const float* b_2, float eps, int M, int d,
+                                      const void* W, int ldw, const float* bias, int N, int act, void* out_f16, int ld16,
+                                      void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(x && a_2 && b_2 && W && out_f16, MTN_E_ARG, "rows_ln_linear: NULL pointer");
+  MTN_REQUIRE(mtn_rows_ln_linear_supported(M, N, d), MTN_E_SHAPE, "rows_ln_linear: M=%d N=%d d=%d", M, N, d);
+  MTN_REQUIRE(ldx >= d && ldx % 4 == 0 && ldw >= d && ldw % 8 == 0 && ld16 >= N && ld16 % 2 == 0 && aligned16(x) && aligned16(a_2) &&
+                  aligned16(b_2) && aligned16(W) && (reinterpret_cast<uintptr_t>(out_f16) & 3) == 0,
+              MTN_E_ALIGN, "rows_ln_linear: alignment / leading dimensions");
+  MTN_REQUIRE(act == MTN_ACT_NONE || act == MTN_ACT_RELU, MTN_E_ARG, "rows_ln_linear: act=%d", act);
+  RowsLnLinearParams p{x, ldx, a_2, b_2, eps, reinterpret_cast<const __half*>(W), ldw, bias, M, N, act,
+                       reinterpret_cast<__half*>(out_f16), ld16, 0u};
+  dim3 grid(N / 8, (M + 15) / 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ks = d / 32 >= 8 ? 8 : d / 32;
+  if (d == 128) MTN_CHECK_CUDA(launch_kernel(rows_ln_linear_kernel<1>, grid, dim3(32 * ks), 0, st, p));
+  else if (d == 256) MTN_CHECK_CUDA(launch_kernel(rows_ln_linear_kernel<2>, grid, dim3(32 * ks), 0, st, p));
+  else if (d == 512) MTN_CHECK_CUDA(launch_kernel(rows_ln_linear_kernel<4>, grid, dim3(32 * ks), 0, st, p));
+  else MTN_CHECK_CUDA(launch_kernel(rows_ln_linear_kernel<8>, grid, dim3(32 * ks), 0, st, p));
   return MTN_OK;
 }
 

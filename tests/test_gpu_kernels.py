@@ -647,3 +647,34 @@ def test_decode_attn(rows_kernels, B, h, R, Lk, kind):
         L.attn_core(cache[:, Lk - 1:Lk, :d], cache[:, :, d:2 * d], cache[:, :, 2 * d:], B, h, 1, Lk, 64, o2)
         torch.cuda.synchronize()
         assert torch.equal(o2.float().cpu().view(B, 1, d), outs[0])
+
+
+@pytest.mark.parametrize("M,N,d,act", [(64, 512, 512, 0), (64, 1536, 512, 0), (64, 2048, 512, 1), (5, 8, 128, 0),
+                                       (100, 256, 256, 1), (17, 1024, 1024, 0)])
+def test_rows_ln_linear(rows_kernels, M, N, d, act):
+    """LayerNorm fused into the few-row projection: bit-identical to mtn_layernorm_fwd + mtn_rows_linear_fwd, and
+    within f16-operand noise of the f32 oracle arithmetic."""
+    L = rows_kernels
+    g = torch.Generator().manual_seed(M * 7 + N + d)
+    x = torch.randn(M, d, generator=g) * 3 + 0.5
+    a2, b2 = 1 + 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g)
+    W = (torch.randn(N, d, generator=g) * 0.05).half()
+    b = torch.randn(N, generator=g) * 0.1
+    ref = O.layer_norm(x, a2, b2, 1e-6) @ W.float().t() + b
+    if act:
+        ref = ref.relu()
+    big = torch.zeros(M, 2 * d + 16, device="cuda")          # x lives inside a wider buffer: row pitch != d
+    big[:, 8:8 + d] = dev(x)
+    xd = dev(x)
+    xn = torch.empty(M, d, device="cuda", dtype=torch.float16)
+    o_seq = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    L.layernorm(xd, dev(a2), dev(b2), 1e-6, out_f16=xn)
+    L.linear(xn, dev(W), dev(b), act=act, out_f16=o_seq)
+    o_f = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    L.rows_ln_linear(xd, dev(a2), dev(b2), 1e-6, dev(W), bias=dev(b), act=act, out_f16=o_f)
+    cache = torch.full((M, 3, N + 8), float("nan"), device="cuda", dtype=torch.float16)
+    L.rows_ln_linear(xd, dev(a2), dev(b2), 1e-6, dev(W), bias=dev(b), act=act, out_f16=cache[:, 1, :N])   # strided rows
+    torch.cuda.synchronize()
+    assert G.rel_err(o_f.float().cpu(), ref) < 1.5e-3
+    assert torch.equal(o_f, o_seq), float((o_f.float() - o_seq.float()).abs().max())
+    assert torch.equal(cache[:, 1, :N], o_f) and torch.isnan(cache[:, 0].float()).all()
