@@ -274,12 +274,13 @@ def site_roofline(dev, peak_tf):
     proj, core = 4 * B * d * d * (Lq + Lk), 4 * B * Lq * Lk * d
     tf = (proj + core) / (us * 1e-6) / 1e12
     return {"workload": "mtn_attn_site_fwd: B=32 Lq=256 Lk=512 d=512 h=8, key-padding mask, memory K/V projected in the call "
-                        "(5 kernels: LayerNorm, Q GEMM, K/V GEMM, attention core, out-proj GEMM + residual)",
+                        "(3 kernels: LayerNorm || K/V GEMM of the memory on an internal side stream, then ONE fused kernel: "
+                        "Q projection + attention + out-projection + residual, csrc/site_fused.cu)",
             "gflop": (proj + core) / 1e9, "us_per_site": us, "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": tf / peak_tf, "bound": "tensor",
-            "note": "north_star target 0.70; the site is five dependent launches (fixed latency each) and the attention "
-                    "core is bound by the serial per-row softmax chain (ncu: XU pipe ~26 % busy, tensor pipe ~15 %), see "
-                    "DESIGN.md section 4"}
+            "note": "north_star target 0.70; round 1: five dependent launches, 79.1 us (0.31).  Half of the FLOPs are the "
+                    "K/V projection (a plain GEMM near the GEMM ceiling); the fused kernel's attention phase is bound by the "
+                    "per-row softmax latency chain (two engines per CTA), see DESIGN.md section 4"}
 
 
 def bind_to_gpu_numa_node(local):

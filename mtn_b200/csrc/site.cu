@@ -3,6 +3,8 @@
 // kernels.  These are the units SublayerConnection.forward wraps in the reference
 // (mtn.py:125-127 around :248-267 and :279-280).  All scratch lives in the caller's
 // workspace; the launch sequence is stream-ordered and graph-capturable.
+#include <stdlib.h>
+
 #include "host.h"
 
 namespace mtn {
@@ -84,6 +86,31 @@ extern "C" int mtn_attn_site_fwd(const MtnAttnSiteArgs* a, void* stream) {
       cudaStreamWaitEvent(main_st, ev_join, 0);
       return rck;
     }
+  }
+
+  // Cross sites with full query tiles take the ONE-kernel form (csrc/site_fused.cu: Q projection + attention + output
+  // projection + residual; measured 1.06-1.13x the launch sequence at Lq = 256, profiles/r02_site_bench_v2.txt):
+  // LayerNorm -> fused kernel, the residual stream updated in place (x_out is seeded with x when they differ).
+  static int fused_mode = -1;   // MTN_B200_SITE_FUSED: 0 never, 1 whenever supported, default: Lq >= 128
+  if (fused_mode < 0) {
+    const char* e = getenv("MTN_B200_SITE_FUSED");
+    fused_mode = (e == nullptr || e[0] == 'a') ? 2 : (e[0] == '0' ? 0 : 1);
+  }
+  if (!self && fused_mode != 0 && mtn_attn_site_fused_supported(d, a->h) && (fused_mode == 1 || a->Lq >= 128)) {
+    int rcf = mtn_layernorm_fwd(a->x, a->ln_a, a->ln_b, a->ln_eps, (int)rq, d, nullptr, xn, stream);
+    if (rcf == 0 && a->x_out != a->x)
+      rcf = cudaMemcpyAsync(a->x_out, a->x, rq * d * sizeof(float), cudaMemcpyDeviceToDevice, main_st) == cudaSuccess
+                ? 0 : set_error(MTN_E_CUDA, "attn_site: cudaMemcpyAsync failed");
+    if (own_kv) MTN_CHECK_CUDA(cudaStreamWaitEvent(main_st, ev_join, 0));
+    if (rcf) return rcf;
+    MtnAttnSiteFusedArgs f = {};
+    f.B = a->B; f.Lq = a->Lq; f.Lk = Lk; f.d = d; f.h = a->h;
+    f.xn_f16 = xn; f.ld_xn = d; f.x = a->x_out; f.ld_x = d;
+    f.w_q = a->w_q; f.ld_wq = d; f.b_q = a->b_q; f.w_o = a->w_o; f.ld_wo = d; f.b_o = a->b_o;
+    if (own_kv) { f.kv = kvbuf; f.ld_kv = 2 * d; f.kv_k_col = 0; f.kv_v_col = d; }
+    else { f.kv = a->kv; f.ld_kv = a->ld_kv; f.kv_k_col = a->kv_k_col; f.kv_v_col = a->kv_v_col; }
+    f.mask_bits = a->mask_bits; f.mask_rows_q = a->mask_rows_q;
+    return mtn_attn_site_fused_fwd(&f, stream);
   }
 
   int rc = mtn_layernorm_fwd(a->x, a->ln_a, a->ln_b, a->ln_eps, (int)rq, d, nullptr, xn, stream);

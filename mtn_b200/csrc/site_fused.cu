@@ -29,6 +29,7 @@
 // Warp roles (224 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 softmax / drains / epilogue
 // (TMEM lane quarter = warp % 4), warp 6 sends finished O tiles to the peer.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host.h"
@@ -592,6 +593,581 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   }
 }
 
+// ================================================================================================================
+// v2: TWO attention engines per CTA.  v1 runs the HH heads of a CTA one after the other on one softmax warpgroup; the
+// attention phase is a per-row latency chain (TMEM load -> max -> exp -> P store -> P V -> O drain), so the tensor
+// pipe idles and phase 2 is ~40 % of the kernel.  Here the CTA carries two complete engines -- K/V producer warp, MMA
+// warp, four softmax warps, own barriers, own K/V/P buffers (64-key tiles: 48 KB each, together the 96 KB ring region),
+// own S/O columns of tensor memory -- that work on different heads at the same time; the two softmax warpgroups also
+// split the Q drain and the epilogue's columns.  416 threads (13 warps): 0 producer A, 1 MMA A, 2..5 softmax 0,
+// 6 sender, 7 producer B, 8 MMA B, 9..12 softmax 1.  Everything else is v1.
+// ================================================================================================================
+constexpr int SF2_THREADS = 416;
+
+template <int HH>
+struct Sf2Cfg {
+  static constexpr int DK = 64, KT = 64;
+  static constexpr int NH = HH * DK;
+  static constexpr int D = 2 * NH;
+  static constexpr int NKB = D / 64;
+  static constexpr int TILE = SF_QT * 128;
+  static constexpr int OFF_QO = 0;
+  static constexpr int OFF_PEER = OFF_QO + HH * TILE;
+  static constexpr int OFF_RING = OFF_PEER + HH * TILE;
+  static constexpr int A_BYTES = TILE;
+  static constexpr int B_BYTES = NH * 128;
+  static constexpr int ST1 = 2, ST3 = 3;
+  static constexpr int RING1 = ST1 * (A_BYTES + B_BYTES);
+  static constexpr int RING3 = ST3 * B_BYTES;
+  static constexpr int KV_BYTES = KT * 128;            // 8 KB
+  static constexpr int P_BYTES = SF_QT * 128;          // 16 KB: one [128 x 64] K-major panel
+  static constexpr int ENG_BYTES = 4 * KV_BYTES + P_BYTES;   // K0 K1 V0 V1 P = 48 KB
+  static constexpr int RING2 = 2 * ENG_BYTES;
+  static constexpr int XPOSE = 8 * 4096;
+  static constexpr int RING_A = RING1 > RING2 ? RING1 : RING2;
+  static constexpr int RING_B = RING3 > XPOSE ? RING3 : XPOSE;
+  static constexpr int RING = RING_A > RING_B ? RING_A : RING_B;
+  static constexpr int OFF_BAR = OFF_RING + RING;
+  static constexpr int TOTAL = OFF_BAR + 640 + 1024;
+  static constexpr uint32_t ENG_COLS = 2 * KT + DK;    // S0 S1 O = 192 columns per engine
+  static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(2 * ENG_COLS <= 512 && NH <= 256, "TMEM budget");
+  static_assert(TOTAL <= 232448, "shared memory budget");
+  static_assert(HH % 2 == 0, "heads are split over two engines");
+};
+
+enum {
+  S2_R1_FULL = 0 /* +1 */, S2_R1_EMPTY = 2 /* +1 */, S2_D1_FULL = 4, S2_Q_READY = 5, S2_OWN_O = 6 /* +3 */, S2_PEER_O = 10,
+  S2_R3_FULL = 11 /* +2 */, S2_R3_EMPTY = 14 /* +2 */, S2_D3_FULL = 17,
+  S2_ENG = 18,   // per engine (+15 each): K_FULL 0,1  K_EMPTY 2,3  V_FULL 4,5  V_EMPTY 6,7  S_FULL 8,9  S_FREE 10,11  P_FULL 12  PV_DONE 13  ATT_DONE 14
+  S2_COUNT = 18 + 30
+};
+enum { E_K_FULL = 0, E_K_EMPTY = 2, E_V_FULL = 4, E_V_EMPTY = 6, E_S_FULL = 8, E_S_FREE = 10, E_P_FULL = 12, E_PV_DONE = 13, E_ATT_DONE = 14 };
+
+template <int HH>
+__global__ void __launch_bounds__(SF2_THREADS, 1)
+    attn_site_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
+                            const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                            const __grid_constant__ CUtensorMap tmWo, const SfParams p) {
+  using C = Sf2Cfg<HH>;
+  constexpr int DK = C::DK, KT = C::KT, HE = HH / 2;   // heads per engine
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sQO = base + C::OFF_QO, sPEER = base + C::OFF_PEER, sRING = base + C::OFF_RING;
+  const uint32_t bars = base + C::OFF_BAR;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const uint32_t tmem_slot = bars + 8u * S2_COUNT;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_BAR + 8 * S2_COUNT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int item = blockIdx.x >> 1;
+  const int qt = item % p.nqt, b = item / p.nqt;
+  const int nt = (p.Lk + KT - 1) / KT;
+  const uint32_t total = (uint32_t)HE * (uint32_t)nt;  // key tiles of one engine, all its heads
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWq);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmWo);
+    for (int i = 0; i < S2_COUNT; ++i) {
+      uint32_t cnt = 1u;
+      if (i == S2_Q_READY) cnt = 256u;
+      if (i >= S2_OWN_O && i < S2_OWN_O + 4) cnt = 128u;
+      if (i >= S2_ENG) {
+        const int k = (i - S2_ENG) % 15;
+        if (k == E_S_FREE || k == E_S_FREE + 1 || k == E_P_FULL) cnt = 128u;
+      }
+      mbar_init(bar(i), cnt);
+    }
+    mbar_arrive_expect_tx(bar(S2_PEER_O), (uint32_t)(HH * C::TILE));
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tD = tmem_base;   // Q / Y accumulator: columns [0, NH); the engines reuse columns [0, 384) in phase 2
+  pdl_wait();
+
+  // which engine this warp serves (producer / MMA / softmax warps), or -1
+  const int eng = (warp == 0 || warp == 1 || (warp >= 2 && warp <= 5)) ? 0 : ((warp == 7 || warp == 8 || warp >= 9) ? 1 : -1);
+  const int EB = S2_ENG + 15 * (eng < 0 ? 0 : eng);
+  const uint32_t sE = sRING + (uint32_t)(eng < 0 ? 0 : eng) * C::ENG_BYTES;
+  const uint32_t sK = sE, sV = sE + 2 * C::KV_BYTES, sP = sE + 4 * C::KV_BYTES;
+  const uint32_t tS = tmem_base + (uint32_t)(eng < 0 ? 0 : eng) * C::ENG_COLS;   // S0 S1 at +0 / +KT, O at +2 KT
+  const uint32_t tO = tS + 2 * KT;
+  const int head0 = (eng < 0 ? 0 : eng) * HE;   // first local head of this engine
+
+  if (warp == 0 || warp == 7) {
+    // ================================================================ TMA producers
+    if (lane == 0) {
+      if (warp == 0) {
+        for (int kb = 0; kb < C::NKB; ++kb) {
+          const int s = kb % C::ST1;
+          mbar_wait(bar(S2_R1_EMPTY + s), ((kb / C::ST1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar(S2_R1_FULL + s), C::A_BYTES + C::B_BYTES);
+          const uint32_t st = sRING + s * (C::A_BYTES + C::B_BYTES);
+          tma_load_3d(st, &tmX, bar(S2_R1_FULL + s), kb * 64, qt * SF_QT, b);
+          tma_load_2d(st + C::A_BYTES, &tmWq, bar(S2_R1_FULL + s), kb * 64, (int)rank * C::NH);
+        }
+      }
+      mbar_wait(bar(S2_D1_FULL), 0);   // the ring region is free once the projection MMAs have retired
+      auto load_k = [&](uint32_t g) {
+        const uint32_t hh = g / nt, j = g % nt, kb = g & 1, kph = (g >> 1) & 1;
+        mbar_wait(bar(EB + E_K_EMPTY + kb), kph ^ 1);
+        mbar_arrive_expect_tx(bar(EB + E_K_FULL + kb), C::KV_BYTES);
+        tma_load_3d(sK + kb * C::KV_BYTES, &tmK, bar(EB + E_K_FULL + kb), ((int)rank * HH + head0 + (int)hh) * DK, j * KT, b);
+      };
+      auto load_v = [&](uint32_t g) {
+        const uint32_t hh = g / nt, j = g % nt, vb = g & 1, vph = (g >> 1) & 1;
+        mbar_wait(bar(EB + E_V_EMPTY + vb), vph ^ 1);
+        mbar_arrive_expect_tx(bar(EB + E_V_FULL + vb), C::KV_BYTES);
+        tma_load_3d(sV + vb * C::KV_BYTES, &tmV, bar(EB + E_V_FULL + vb), ((int)rank * HH + head0 + (int)hh) * DK, j * KT, b);
+      };
+      load_k(0);
+      for (uint32_t g = 0; g < total; ++g) {
+        if (g + 1 < total) load_k(g + 1);
+        load_v(g);
+      }
+      if (warp == 0) {
+        mbar_wait(bar(S2_ENG + E_ATT_DONE), 0);        // both engines have retired their last P V
+        mbar_wait(bar(S2_ENG + 15 + E_ATT_DONE), 0);
+        for (int kc = 0; kc < C::NKB; ++kc) {
+          const int s = kc % C::ST3;
+          mbar_wait(bar(S2_R3_EMPTY + s), ((kc / C::ST3) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar(S2_R3_FULL + s), C::B_BYTES);
+          tma_load_2d(sRING + s * C::B_BYTES, &tmWo, bar(S2_R3_FULL + s), kc * 64, (int)rank * C::NH);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 8) {
+    // ================================================================ MMA issuers
+    constexpr uint32_t idesc_p = make_idesc_f16(SF_QT, C::NH, 0, 0);
+    constexpr uint32_t idesc_s = make_idesc_f16(SF_QT, KT, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_f16(SF_QT, DK, 0, 1);
+    if (warp == 1) {
+      for (int kb = 0; kb < C::NKB; ++kb) {
+        const int s = kb % C::ST1;
+        mbar_wait(bar(S2_R1_FULL + s), (kb / C::ST1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = sRING + s * (C::A_BYTES + C::B_BYTES);
+          const uint64_t da = make_smem_desc(st, 16, 1024, SWZ_128B);
+          const uint64_t db = make_smem_desc(st + C::A_BYTES, 16, 1024, SWZ_128B);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_f16(tD, da + 2 * k, db + 2 * k, idesc_p, (kb | k) != 0);
+          tc_commit(bar(S2_R1_EMPTY + s));
+          if (kb == C::NKB - 1) tc_commit(bar(S2_D1_FULL));
+        }
+        __syncwarp();
+      }
+    }
+    mbar_wait(bar(S2_Q_READY), 0);   // every Q tile is in shared memory AND the whole Q accumulator has been read
+    tc_fence_after();
+    auto issue_qk = [&](uint32_t g) {
+      const uint32_t hh = g / nt, sb = g & 1, ph2 = (g >> 1) & 1;
+      mbar_wait(bar(EB + E_K_FULL + sb), ph2);
+      mbar_wait(bar(EB + E_S_FREE + sb), ph2 ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dq = make_smem_desc(sQO + (uint32_t)(head0 + (int)hh) * C::TILE, 16, 1024, SWZ_128B);
+        const uint64_t dk = make_smem_desc(sK + sb * C::KV_BYTES, 16, 1024, SWZ_128B);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) tc_mma_f16(tS + sb * KT, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(bar(EB + E_K_EMPTY + sb));
+        tc_commit(bar(EB + E_S_FULL + sb));
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (uint32_t g = 0; g < total; ++g) {
+      if (g + 1 < total) issue_qk(g + 1);
+      const uint32_t ph = g & 1, j = g % nt;
+      mbar_wait(bar(EB + E_V_FULL + ph), (g >> 1) & 1);
+      mbar_wait(bar(EB + E_P_FULL), ph);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint64_t dp = make_smem_desc(sP + kk * 32, 16, 1024, SWZ_128B);
+          const uint64_t dv = make_smem_desc(sV + ph * C::KV_BYTES + kk * 16 * 128, KT * 128, 1024, SWZ_128B);
+          tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
+        }
+        tc_commit(bar(EB + E_V_EMPTY + ph));
+        tc_commit(bar(EB + E_PV_DONE));
+        if (g == total - 1) tc_commit(bar(EB + E_ATT_DONE));
+      }
+      __syncwarp();
+    }
+    if (warp == 1) {
+      // ---- phase 3 (after BOTH engines: their tensor-memory columns become the Y accumulator)
+      for (int hh = 0; hh < HH; ++hh) mbar_wait(bar(S2_OWN_O + hh), 0);
+      mbar_wait(bar(S2_ENG + 15 + E_ATT_DONE), 0);
+      mbar_wait(bar(S2_PEER_O), 0);
+      tc_fence_after();
+      for (int kc = 0; kc < C::NKB; ++kc) {
+        const int s = kc % C::ST3;
+        mbar_wait(bar(S2_R3_FULL + s), (kc / C::ST3) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_tile = ((uint32_t)(kc / HH) == rank ? sQO : sPEER) + (uint32_t)(kc % HH) * C::TILE;
+          const uint64_t da = make_smem_desc(a_tile, 16, 1024, SWZ_128B);
+          const uint64_t db = make_smem_desc(sRING + s * C::B_BYTES, 16, 1024, SWZ_128B);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_f16(tD, da + 2 * k, db + 2 * k, idesc_p, (kc | k) != 0);
+          tc_commit(bar(S2_R3_EMPTY + s));
+          if (kc == C::NKB - 1) tc_commit(bar(S2_D3_FULL));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 6) {
+    // ================================================================ DSMEM sender
+    if (lane == 0) {
+      const uint32_t peer = rank ^ 1u;
+      const uint32_t peer_bar = sf_mapa(bar(S2_PEER_O), peer);
+      for (int hh = 0; hh < HH; ++hh) {
+        mbar_wait(bar(S2_OWN_O + hh), 0);
+        sf_dsmem_copy(sf_mapa(sPEER + hh * C::TILE, peer), sQO + hh * C::TILE, (uint32_t)C::TILE, peer_bar);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ softmax warpgroups (engine 0: warps 2..5, engine 1: 9..12)
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t sw = (uint32_t)(row & 7);
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float c1 = p.scale * LOG2E;
+    const float t_masked = -1e9f * LOG2E;
+    constexpr int NCH = KT / 32;
+    constexpr int CH = C::NH / 64;   // 32-column chunks of the Q / Y accumulator per warpgroup
+
+    // ---- phase 1 drain of this group's heads: columns [eng * NH/2, (eng+1) * NH/2)
+    mbar_wait(bar(S2_D1_FULL), 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = eng * CH; c < (eng + 1) * CH; ++c) {
+      uint32_t r[32];
+      tc_ld32(tD + lane_off + c * 32, r);
+      const float* bq = p.b_q + rank * C::NH + c * 32;
+      float4 bb[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) bb[t] = __ldg(reinterpret_cast<const float4*>(bq) + t);
+      tc_wait_ld();
+      const uint32_t tile = sQO + (uint32_t)(c >> 1) * C::TILE + row * 128;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t chunk = ((uint32_t)((c & 1) * 4 + t)) ^ sw;
+        const float4 b0 = bb[2 * t], b1 = bb[2 * t + 1];
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + chunk * 16),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t]) + b0.x, __uint_as_float(r[8 * t + 1]) + b0.y)),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) + b0.z, __uint_as_float(r[8 * t + 3]) + b0.w)),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) + b1.x, __uint_as_float(r[8 * t + 5]) + b1.y)),
+                     "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) + b1.z, __uint_as_float(r[8 * t + 7]) + b1.w))
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar(S2_Q_READY));
+
+    // ---- phase 2
+    const bool live = qt * SF_QT + q4 * 32 < p.Lq;
+    const uint32_t* mrow = nullptr;
+    if (p.mask_bits != nullptr) {
+      const int mq = (p.mask_rows_q == 1) ? 0 : min(qt * SF_QT + row, p.Lq - 1);
+      mrow = p.mask_bits + ((size_t)b * p.mask_rows_q + mq) * p.mask_words;
+    }
+    uint32_t mw_pref[NCH];
+    auto fetch_mask = [&](int jn) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int k0 = jn * KT + c * 32;
+        mw_pref[c] = (mrow != nullptr && k0 < p.Lk) ? __ldcg(mrow + (k0 >> 5)) : 0xffffffffu;
+      }
+    };
+    fetch_mask(0);
+    uint32_t g = 0;
+    for (int hh = 0; hh < HE; ++hh) {
+      const int hl = head0 + hh;   // local head index (tile / OWN_O barrier)
+      float m_run = -CUDART_INF_F, l_run = 0.f;
+      if (!live) {
+        for (int j = 0; j < nt; ++j, ++g) {
+          const uint32_t ph = g & 1;
+          mbar_wait(bar(EB + E_S_FULL + ph), (g >> 1) & 1);
+          if (j > 0) mbar_wait(bar(EB + E_PV_DONE), ph ^ 1);
+          mbar_arrive(bar(EB + E_S_FREE + ph));
+          mbar_arrive(bar(EB + E_P_FULL));
+        }
+        mbar_wait(bar(EB + E_PV_DONE), (g - 1) & 1);
+        mbar_arrive(bar(S2_OWN_O + hl));
+        continue;
+      }
+      for (int j = 0; j < nt; ++j, ++g) {
+        const uint32_t ph = g & 1;
+        const uint32_t tSb = tS + ph * KT;
+        uint32_t mwv[NCH];
+        bool plain = (j + 1) * KT <= p.Lk;
+        {
+          uint32_t w = 0xffffffffu;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            mwv[c] = mw_pref[c];
+            w &= mwv[c];
+          }
+          if (mrow != nullptr) plain = plain && __all_sync(0xffffffffu, w == 0xffffffffu);
+        }
+        fetch_mask(j + 1 < nt ? j + 1 : 0);
+        mbar_wait(bar(EB + E_S_FULL + ph), (g >> 1) & 1);
+        tc_fence_after();
+        auto store_chunk = [&](int c, const uint32_t(&e)[32]) {
+          const uint32_t panel = sP + row * 128;
+          const uint32_t c4 = (uint32_t)(c & 1) * 4u;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + ((c4 + t) ^ sw) * 16),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t]), __uint_as_float(e[8 * t + 1]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 2]), __uint_as_float(e[8 * t + 3]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 4]), __uint_as_float(e[8 * t + 5]))),
+                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 6]), __uint_as_float(e[8 * t + 7])))
+                         : "memory");
+          }
+        };
+        auto wait_p_buffer = [&]() {
+          if (j > 0) {
+            mbar_wait(bar(EB + E_PV_DONE), ph ^ 1);
+            tc_fence_after();
+          }
+        };
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        float m_new;
+        bool rescale = false;
+        auto pick_max = [&](float m_tile) {
+          m_new = fmaxf(m_run, m_tile);
+          if (j > 0) {
+            rescale = __any_sync(0xffffffffu, m_new - m_run > 8.f);
+            if (!rescale) m_new = m_run;
+          }
+        };
+        if (plain) {
+          uint32_t r[NCH][32];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tc_ld32(tSb + lane_off + c * 32, r[c]);
+          tc_wait_ld();
+          tc_fence_before();
+          mbar_arrive(bar(EB + E_S_FREE + ph));
+          float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[c][i]));
+          }
+          pick_max(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float e = sf_ex2(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
+              l4[i & 3] += e;
+              r[c][i] = __float_as_uint(e);
+            }
+          }
+          wait_p_buffer();
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
+        } else {
+          float m_tile = -CUDART_INF_F;
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int nvalid = p.Lk - (j * KT + c * 32);
+            if (nvalid <= 0) break;
+            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+            const uint32_t mw = c == 0 ? mwv[0] : mwv[NCH - 1];
+            if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
+              m_tile = fmaxf(m_tile, t_masked);
+              continue;
+            }
+            uint32_t r[32];
+            tc_ld32(tSb + lane_off + c * 32, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float t = __uint_as_float(r[i]) * c1;
+              t = ((mw >> i) & 1u) ? t : t_masked;
+              t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+              m_tile = fmaxf(m_tile, t);
+            }
+          }
+          pick_max(m_tile);
+          wait_p_buffer();
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int nvalid = p.Lk - (j * KT + c * 32);
+            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+            const uint32_t mw = c == 0 ? mwv[0] : mwv[NCH - 1];
+            uint32_t e[32];
+            if (nvalid > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
+              const float pm = sf_ex2(t_masked - m_new);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = ((inb >> i) & 1u) ? __float_as_uint(pm) : 0u;
+              l4[0] += pm * (float)__popc(inb);
+            } else if (nvalid > 0) {
+              tc_ld32(tSb + lane_off + c * 32, e);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float t = __uint_as_float(e[i]) * c1;
+                t = ((mw >> i) & 1u) ? t : t_masked;
+                t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
+                const float x = sf_ex2(t - m_new);
+                l4[i & 3] += x;
+                e[i] = __float_as_uint(x);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = 0u;
+            }
+            store_chunk(c, e);
+          }
+          tc_fence_before();
+          mbar_arrive(bar(EB + E_S_FREE + ph));
+        }
+        const float alpha = sf_ex2(m_run - m_new);
+        l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+        m_run = m_new;
+        if (rescale) {
+#pragma unroll
+          for (int c = 0; c < DK / 32; ++c) {
+            uint32_t o[32];
+            tc_ld32(tO + lane_off + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc_st32(tO + lane_off + c * 32, o);
+          }
+          tc_wait_st();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar(EB + E_P_FULL));
+      }
+      mbar_wait(bar(EB + E_PV_DONE), (g - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const uint32_t tile = sQO + (uint32_t)hl * C::TILE + row * 128;
+#pragma unroll
+      for (int c = 0; c < DK / 32; ++c) {
+        uint32_t r[32];
+        tc_ld32(tO + lane_off + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t chunk = (uint32_t)(c * 4 + t) ^ sw;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + chunk * 16),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t]) * inv_l, __uint_as_float(r[8 * t + 1]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 2]) * inv_l, __uint_as_float(r[8 * t + 3]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 4]) * inv_l, __uint_as_float(r[8 * t + 5]) * inv_l)),
+                       "r"(pack_f16x2_sat(__uint_as_float(r[8 * t + 6]) * inv_l, __uint_as_float(r[8 * t + 7]) * inv_l))
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar(S2_OWN_O + hl));
+    }
+
+    // ---- phase 3 epilogue: this group's half of the CTA's output columns
+    mbar_wait(bar(S2_D3_FULL), 0);
+    tc_fence_after();
+    const int ew = eng * 4 + q4;   // transpose tile of this warp
+    float4* xp = reinterpret_cast<float4*>(smem + C::OFF_RING + ew * 4096);
+    const int sub_r = lane >> 2, c8 = lane & 3;
+    const int wr_base = lane * 8, wr_sw = lane & 7;
+    const int rd0 = sub_r * 8 + ((2 * c8) ^ sub_r), rd1 = sub_r * 8 + ((2 * c8 + 1) ^ sub_r);
+    const int rows_valid = min(SF_QT, p.Lq - qt * SF_QT);
+    const size_t grow0 = (size_t)b * p.Lq + (size_t)qt * SF_QT;
+#pragma unroll 1
+    for (int c = eng * CH; c < (eng + 1) * CH; ++c) {
+      const int col = (int)rank * C::NH + c * 32 + c8 * 8;
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b_o + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b_o + col + 4));
+      uint32_t acc[32];
+      tc_ld32(tD + lane_off + c * 32, acc);
+      tc_wait_ld();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        xp[wr_base + (jj ^ wr_sw)] = make_float4(__uint_as_float(acc[4 * jj]), __uint_as_float(acc[4 * jj + 1]),
+                                                 __uint_as_float(acc[4 * jj + 2]), __uint_as_float(acc[4 * jj + 3]));
+      __syncwarp();
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] = xp[i * 64 + rd0];
+        v[2 * i + 1] = xp[i * 64 + rd1];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = q4 * 32 + sub_r + i * 8;
+        if (rl < rows_valid) {
+          float* o = p.x + (grow0 + rl) * p.ld_x + col;
+          grad_red_v4(o, v[2 * i].x + b0.x, v[2 * i].y + b0.y, v[2 * i].z + b0.z, v[2 * i].w + b0.w, 0);
+          grad_red_v4(o + 4, v[2 * i + 1].x + b1.x, v[2 * i + 1].y + b1.y, v[2 * i + 1].z + b1.z, v[2 * i + 1].w + b1.w, 0);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int HH>
+static int launch_site_fused2(const MtnAttnSiteFusedArgs& a, cudaStream_t st) {
+  using C = Sf2Cfg<HH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_site_fused2_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    attr_set = true;
+  }
+  const int d = a.d;
+  CUtensorMap tx, twq, tk, tv, two;
+  int rc = make_tmap_3d_f16(&tx, a.xn_f16, d, a.Lq, a.B, a.ld_xn, (uint64_t)a.Lq * a.ld_xn, 64, SF_QT, TM_SWZ_128);
+  if (rc) return rc;
+  rc = make_tmap_2d_f16(&twq, a.w_q, d, d, a.ld_wq > 0 ? a.ld_wq : d, 64, C::NH, TM_SWZ_128);
+  if (rc) return rc;
+  rc = make_tmap_2d_f16(&two, a.w_o, d, d, a.ld_wo > 0 ? a.ld_wo : d, 64, C::NH, TM_SWZ_128);
+  if (rc) return rc;
+  const uint8_t* kp = static_cast<const uint8_t*>(a.kv) + (size_t)a.kv_k_col * 2;
+  const uint8_t* vp = static_cast<const uint8_t*>(a.kv) + (size_t)a.kv_v_col * 2;
+  rc = make_tmap_3d_f16(&tk, kp, d, a.Lk, a.B, a.ld_kv, (uint64_t)a.Lk * a.ld_kv, 64, C::KT, TM_SWZ_128);
+  if (rc) return rc;
+  rc = make_tmap_3d_f16(&tv, vp, d, a.Lk, a.B, a.ld_kv, (uint64_t)a.Lk * a.ld_kv, 64, C::KT, TM_SWZ_128);
+  if (rc) return rc;
+  const int nqt = (a.Lq + SF_QT - 1) / SF_QT;
+  SfParams p{a.B, a.h, a.Lq, a.Lk, nqt, a.b_q, a.b_o, a.x, a.ld_x, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk),
+             1.0f / sqrtf(64.f)};
+  dim3 grid(2u * (unsigned)(a.B * nqt));
+  MTN_CHECK_CUDA(launch_kernel_cluster(attn_site_fused2_kernel<HH>, grid, dim3(SF2_THREADS), C::TOTAL, st, 2u, tx, twq, tk, tv,
+                                       two, p));
+  return MTN_OK;
+}
+
 template <int HH, int KT>
 static int launch_site_fused(const MtnAttnSiteFusedArgs& a, cudaStream_t st) {
   using C = SfCfg<HH, KT>;
@@ -645,6 +1221,12 @@ extern "C" int mtn_attn_site_fused_fwd(const MtnAttnSiteFusedArgs* a, void* stre
   MTN_REQUIRE(a->mask_bits == nullptr || a->mask_rows_q == 1 || a->mask_rows_q == a->Lq, MTN_E_SHAPE,
               "attn_site_fused: mask_rows_q=%d must be 1 or Lq=%d", a->mask_rows_q, a->Lq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int version = 0;   // MTN_B200_SITE_FUSED_V=1: the single-engine kernel (v1); default: two engines per CTA (v2)
+  if (version == 0) {
+    const char* e = getenv("MTN_B200_SITE_FUSED_V");
+    version = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  if (version == 2) return a->d == 512 ? launch_site_fused2<4>(*a, st) : launch_site_fused2<2>(*a, st);
   if (a->d == 512) return a->Lk <= 64 ? launch_site_fused<4, 64>(*a, st) : launch_site_fused<4, 96>(*a, st);
   return a->Lk <= 64 ? launch_site_fused<2, 64>(*a, st) : launch_site_fused<2, 96>(*a, st);
 }

@@ -89,14 +89,14 @@ def invalidate_weight_caches():
 
 def _site_fused_ok(d, h, B, Lq, Lk):
     """Does this hoisted-K/V site take the ONE-kernel path (csrc/site_fused.cu)?  MTN_B200_SITE_FUSED = 1: whenever the
-    shape is supported; 0: never; default "auto": where it measured at least as fast as the launch sequence Q GEMM ->
-    core -> out-proj GEMM (profiles/r02_site_bench.txt): full query tiles on short memories."""
+    shape is supported; 0: never; default "auto": where it measured faster than the launch sequence Q GEMM -> core ->
+    out-proj GEMM (profiles/r02_site_bench_v2.txt: 1.06-1.13x at Lq = 256, parity or below at Lq <= 64): full query tiles."""
     mode = os.environ.get("MTN_B200_SITE_FUSED", "auto")
     if mode == "0" or not _lib.attn_site_fused_supported(d, h):
         return False
     if mode == "1":
         return True
-    return Lq >= 128 and Lk <= 64
+    return Lq >= 128
 
 
 class PackedWeights(object):

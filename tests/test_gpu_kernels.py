@@ -534,9 +534,10 @@ def test_attn_site_fused(L, B, Lq, Lk, d, h, kind):
     if not (e_ref < 2e-3):
         _dump("fail_site_fused_%d_%d_%d_%d.npz" % (B, Lq, Lk, d), fused=x_f - xd, seq=x_seq - xd, ref=ref_delta)
     assert e_ref < 2e-3, (e_ref, e_seq)
-    # same arithmetic in the same order: identical up to a handful of f16 roundings of O (measured: <= 3 of 131072
-    # elements differ by one f16 ulp, tools/site_fused_debug.py), i.e. far below the error against the oracle
-    assert G.rel_err((x_f - xd).cpu(), (x_seq - xd).cpu()) < 2e-5, float((x_f - x_seq).abs().max())
+    # same arithmetic; with one key tile (Lk <= 64) also the same order: identical up to a handful of f16 roundings of O
+    # (<= 3 of 131072 elements differ by one f16 ulp, tools/site_fused_debug.py).  Longer memories: the fused kernel
+    # walks 64-key tiles, the attention core 96-key tiles -- the online softmax rounds P against other running maxima
+    assert G.rel_err((x_f - xd).cpu(), (x_seq - xd).cpu()) < (2e-5 if Lk <= 64 else 5e-4), float((x_f - x_seq).abs().max())
     # run-to-run determinism, and a second call on the same buffers (cluster / barrier state is per launch)
     x_g = xd.clone()
     L.attn_site_fused(xn_d, x_g, dev(wq), dev(bq), dev(wo), dev(bo), kv_d, 0, d, B, h, Lq, Lk, mask_bits=bits)

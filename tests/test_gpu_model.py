@@ -443,6 +443,31 @@ def test_cfg5_family_d1024_h16(M):
     assert max(e) <= TOL, e
 
 
+def test_cfg5_full_depth_spot_check(M):
+    """BASELINE configs[4] as written -- N=12, d_model=1024, h=16, d_ff=4096, video_len=1024, the per-GPU batch of 4 --
+    with ONE of the 4 dialogues checked against the CPU oracle (12 layers of d=1024 take the oracle ~10 s per
+    dialogue), plus the size-independent property that a dialogue's outputs do not depend on its batch neighbours."""
+    mtn, du = M
+    cfg = {"N": 12, "d_model": 1024, "d_ff": 4096, "h": 16, "vocab": 3000, "ft_sizes": [2048, 128],
+           "auto_encoder_ft": "query", "diff_encoder": True}
+    sd = O.init_state_dict(cfg, 77)
+    model = build(mtn, cfg, sd)
+    inp = O.synth_inputs(cfg, B=4, Q=64, C=64, H=256, T=32, Lv=[1024, 256], seed=12)
+    with torch.no_grad():
+        out, ae = model.forward(make_batch(du, inp))
+    sel = [2]
+    sub = {k: (v[sel] if torch.is_tensor(v) else [f[sel] for f in v]) for k, v in inp.items()}
+    ref_out, ref_ae = O.forward(sd, cfg, sub["query"], sub["his"], sub["cap"], sub["trg"], sub["fts"])
+    e = [G.rel_err(out[2].cpu(), ref_out[0]), G.rel_err(ae[0][2].cpu(), ref_ae[0][0]), G.rel_err(ae[1][2].cpu(), ref_ae[1][0])]
+    print("cfg5 N=12 d=1024, dialogue 2 of 4 vs oracle:", e)
+    assert max(e) <= TOL, e
+    with torch.no_grad():
+        out1, ae1 = model.forward(make_batch(du, sub))
+    assert G.rel_err(out1[0].cpu(), out[2].cpu()) < 1e-4 and G.rel_err(ae1[0][0].cpu(), ae[0][2].cpu()) < 1e-4
+    del model
+    torch.cuda.empty_cache()
+
+
 def test_edge_shapes(M):
     """Edge cases of the domain: batch 1; a first-turn dialogue whose history is the single <blank> token
     (data_handler.py:113-114 -> fully masked keys -> uniform softmax); target length 1 (first decode step);
