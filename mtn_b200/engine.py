@@ -65,7 +65,7 @@ def _ln_linear(x, ln, w, b, act, xn16, out16):
     """out16 = act(LN(x) w^T + b): one fused launch when the shape qualifies, else LayerNorm -> xn16 -> linear
     (same results either way, tests/test_gpu_ln_linear.py)."""
     rows, d = x.shape
-    if _lib.rows_ln_linear_ok(rows, w.shape[0], d):          # KV-cached decoding: few rows, one mma.sync launch
+    if _lib.ROWS_KERNELS and _lib.rows_ln_linear_ok(rows, w.shape[0], d):   # KV-cached decoding: few rows, one mma.sync launch
         _lib.rows_ln_linear(x, ln[0], ln[1], ln[2], w, bias=b, act=act, out_f16=out16)
         return
     if rows <= _ln_fused_max_rows() and _lib.ln_linear_supported(d):

@@ -261,3 +261,25 @@ def test_ln_linear_dispatch(monkeypatch):
     del calls[:]
     engine._ln_linear(torch.zeros(64, 1024), (torch.ones(1024), torch.zeros(1024), 1e-6), None, None, 0, None, None)
     assert calls == ["ln", "linear"]                      # d = 1024: the row block's panels do not fit shared memory
+
+
+def test_device_feature_cache_lru_and_gather():
+    """mtn_b200/feature_cache.py on CPU tensors: resident lookup, device-side batch assembly, LRU eviction, loud miss."""
+    from mtn_b200.feature_cache import DeviceFeatureCache
+    c = DeviceFeatureCache(3, [(4, 8), (2, 4)], "cpu", dtype=torch.float32)
+    f = lambda v: [torch.full((4, 8), float(v)), torch.full((2, 4), float(v) + 0.5)]
+    for v in (10, 11, 12):
+        c.put(v, f(v), non_blocking=False)
+    g = c.gather([12, 10])
+    assert g[0].shape == (2, 4, 8) and float(g[0][0, 0, 0]) == 12 and float(g[1][1, 0, 0]) == 10.5
+    c.put(13, f(13), non_blocking=False)            # evicts the least recently used video: 11
+    assert 11 not in c and 10 in c and 12 in c and 13 in c
+    with pytest.raises(KeyError):
+        c.gather([11])
+    out = [torch.empty(2, 4, 8), torch.empty(2, 2, 4)]
+    c.gather([13, 12], out=out, index_buffer=torch.empty(4, dtype=torch.int64))
+    assert float(out[0][0, 0, 0]) == 13 and float(out[1][1, 0, 0]) == 12.5
+    c.invalidate(12)
+    assert 12 not in c and c.bytes_per_video() == (4 * 8 + 2 * 4) * 4
+    c.put(10, f(99), non_blocking=False)            # re-upload of a resident video reuses its slot
+    assert float(c.gather([10])[0][0, 0, 0]) == 99
