@@ -134,10 +134,15 @@ class GraphedGreedyDecoder(object):
                 for dst, src in zip(self.static[k], v):
                     dst.copy_(src, non_blocking=non_blocking)
 
-    def upload(self, inputs):
+    def upload(self, inputs, cache=None, video_ids=None, new_videos=(), index_buffer=None):
         """Asynchronous host -> device copy of the NEXT dialogue batch into staging buffers on a copy stream, so the
-        PCIe transfer (277 MB of features at BASELINE configs[3]) overlaps the decoding of the current batch.
-        ``decode(staged=True)`` then starts from the staged batch."""
+        PCIe transfer (277 MB of f32 features at BASELINE configs[3]) overlaps the decoding of the current batch.
+        ``decode(staged=True)`` then starts from the staged batch.
+
+        With ``cache`` (feature_cache.DeviceFeatureCache): ``inputs`` carries only the token ids; the features of the
+        batch's ``video_ids`` are gathered ON THE DEVICE from the cache after the ``new_videos`` -- [(video id, [host
+        feature tensors])], the videos not yet resident -- have been uploaded.  generate.py decodes the ten turns of a
+        dialogue one after the other: nine of ten samples find their video resident."""
         if getattr(self, "_stage", None) is None:
             self._stage = {k: (torch.empty_like(v) if torch.is_tensor(v) else [torch.empty_like(t) for t in v])
                            for k, v in self.static.items()}
@@ -147,13 +152,17 @@ class GraphedGreedyDecoder(object):
         self._copy.wait_event(self._ev_used)            # the previous staged batch has been moved into the static buffers
         with torch.cuda.stream(self._copy):
             for k, v in inputs.items():
-                if k not in self._stage:
+                if k not in self._stage or (cache is not None and k == "fts"):
                     continue
                 if torch.is_tensor(v):
                     self._stage[k].copy_(v, non_blocking=True)
                 else:
                     for dst, src in zip(self._stage[k], v):
                         dst.copy_(src, non_blocking=True)
+            if cache is not None:
+                for vid, feats in new_videos:
+                    cache.put(vid, feats)
+                cache.gather(video_ids, out=self._stage["fts"], index_buffer=index_buffer)
             self._ev_up.record(self._copy)
 
     def decode(self, staged=False):
