@@ -917,6 +917,35 @@ def main():
             except Exception as e:
                 decode["in_flight"] = {"error": repr(e)[:300]}
         del dec
+        # ---- beam search (generate.py's actual path, data_utils.py:188-242): all hypotheses of all dialogues in one
+        # KV-cached step and one D2H per position, next to the reference's call form (one full-prefix decode and one
+        # D2H per hypothesis per step) on the same dialogues.  Context numbers, rank 0 of a 1-GPU run only.
+        if world == 1:
+            try:
+                from mtn_b200 import data_utils as du
+                Db, beam_w, blen = 8, 5, Ld
+                dvb = {k: (v[:Db].to(dev) if torch.is_tensor(v) else [f[:Db].to(dev) for f in v]) for k, v in dh[0].items()}
+                mkb = lambda sl: du.Batch(dvb["query"][sl], dvb["his"][sl], None, [f[sl].permute(1, 0, 2) for f in dvb["fts"]],
+                                          dvb["cap"][sl], None, None, 1)
+                with torch.no_grad():
+                    du.beam_search_decode_batched(model, mkb(slice(0, Db)), blen, 2, 0, 3, 1, beam=beam_w)      # warm-up
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    got = du.beam_search_decode_batched(model, mkb(slice(0, Db)), blen, 2, 0, 3, 1, beam=beam_w)
+                    torch.cuda.synchronize(); t_b = time.perf_counter() - t0
+                    os.environ["MTN_B200_BEAM_SERIAL"] = "1"
+                    du.beam_search_decode(model, mkb(slice(0, 1)), blen, 2, 0, 3, 1, beam=beam_w)               # warm-up
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    ref1 = du.beam_search_decode(model, mkb(slice(0, 1)), blen, 2, 0, 3, 1, beam=beam_w)
+                    torch.cuda.synchronize(); t_s = time.perf_counter() - t0
+                    os.environ.pop("MTN_B200_BEAM_SERIAL", None)
+                decode["beam_search"] = {
+                    "workload": "beam %d, %d positions, %d dialogues at once (eager launches, host-side pool rules)" % (beam_w, blen, Db),
+                    "batched_ms_per_dialogue": t_b * 1e3 / Db, "serial_reference_call_form_ms_per_dialogue": t_s * 1e3,
+                    "speedup": t_s / (t_b / Db),
+                    "same_best_hypothesis_as_serial": [int(t) for t in got[0][0][0][0]] == [int(t) for t in ref1[0][0][0]]}
+            except Exception as e:
+                os.environ.pop("MTN_B200_BEAM_SERIAL", None)
+                decode["beam_search"] = {"error": repr(e)[:300]}
 
     # ------------------------------------------------------------- training step (forward + loss + backward +
     # ONE NCCL gradient all-reduce + Adam), BASELINE configs[1] / [2]
