@@ -4,8 +4,10 @@ path's boundary: ``Batch`` (masks, data_utils.py:21-54), ``subsequent_mask``
 WORKING ``greedy_decode`` (the reference's, :162-186, raises TypeError -- SURVEY 8a
 row G; this one implements its intended semantics with the call form of :202-210).
 
-Optimiser / loss / torchtext leftovers of the reference file are out of scope
- and are not mirrored.
+Torchtext leftovers of the reference file are out of scope and are not mirrored.  ``Batch``'s field
+block and ``NoamOpt`` are interface mirrors: they follow the reference's ``data_utils.py:21-46`` and ``:92-117`` almost
+line for line on purpose (``train.py`` / ``generate.py`` read these attributes and drive this schedule); everything that
+computes -- masks on the device, the fused loss, greedy / beam decoding -- is this repo's own code.
 """
 import numpy as np
 import torch

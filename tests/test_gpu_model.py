@@ -228,6 +228,34 @@ def test_cfg2_full_size_properties(M, cfg2_model):
     assert G.rel_err(pre.cpu(), full[:, :7].cpu()) <= 2e-5
 
 
+def test_cfg2_bench_configuration_T256_vs_oracle(M, cfg2_model, monkeypatch):
+    """The configuration bench.py measures -- BASELINE configs[1] with target length 256, batch 32 -- against the CPU
+    oracle on 3 of the 32 dialogues (first, middle, last cluster of the fused site kernel's grid), with the fused
+    one-kernel sites on (the default at full query tiles) and off: both within the parity bar, and within f16-operand
+    rounding of each other."""
+    mtn, du = M
+    cfg, model = cfg2_model
+    inp = O.synth_inputs(cfg, B=32, Q=64, C=64, H=256, T=256, Lv=[512, 256], seed=1000)
+    b = make_batch(du, inp)
+    outs = {}
+    for mode in ("auto", "0"):
+        monkeypatch.setenv("MTN_B200_SITE_FUSED", mode)
+        with torch.no_grad():
+            out, ae = model.forward(b)
+        torch.cuda.synchronize()
+        outs[mode] = (out.cpu(), [a.cpu() for a in ae])
+    monkeypatch.delenv("MTN_B200_SITE_FUSED")
+    sel = [0, 17, 31]
+    sub = {k: (v[sel] if torch.is_tensor(v) else [f[sel] for f in v]) for k, v in inp.items()}
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref_out, ref_ae = O.forward(sd, cfg, sub["query"], sub["his"], sub["cap"], sub["trg"], sub["fts"])
+    for mode, (out, ae) in outs.items():
+        e = [G.rel_err(out[sel], ref_out), G.rel_err(ae[0][sel], ref_ae[0]), G.rel_err(ae[1][sel], ref_ae[1])]
+        print("cfg2 T=256 B=32, fused sites %s, dialogues %s vs oracle: %s" % (mode, sel, e))
+        assert max(e) <= TOL, (mode, e)
+    assert G.rel_err(outs["auto"][0], outs["0"][0]) <= 5e-4
+
+
 def test_loud_failures(M):
     mtn, _ = M
     ln = mtn.LayerNorm(128)
