@@ -483,3 +483,49 @@ def test_training_step_variants_vs_oracle(cfg, shape):
     print("   variant-specific tensors:", {k: round(errs[k], 4) for k in key[:8]})
     assert max(errs[k] for k in key) < 2.5e-2, {k: errs[k] for k in key}
     assert max(errs.values()) < 8e-2 and float(np.median(list(errs.values()))) < 1.5e-2, worst
+
+
+class _RecordingOpt(object):
+    """Optimizer stand-in: snapshots the gradients TrainStep hands to the optimizer instead of updating."""
+
+    def __init__(self, model):
+        self.model, self.grads = model, None
+
+    def step(self):
+        self.grads = {k: p.grad.detach().clone() for k, p in self.model.named_parameters()}
+
+
+def test_trainstep_caption_variant_device_normalisers():
+    """TrainStep must take the auto-encoder target and normaliser from auto_encoder_ft (b.cap / ntokens_cap
+    for 'caption', train.py:34-36) -- caption and query lengths differ here, so the old hard-wired b.query would not even
+    have matched the row count -- and count the normalisers on the device; loss and gradients vs the oracle's step."""
+    from mtn_b200 import mtn
+    from mtn_b200.trainer import TrainStep
+    cfg, shape = VARIANTS[0]
+    assert cfg["auto_encoder_ft"] == "caption" and shape["C"] != shape["Q"]
+    sd = O.init_state_dict(cfg, 8)
+    inp = O.synth_inputs(cfg, seed=9, **shape)
+    model = mtn.make_model(cfg["vocab"], cfg["vocab"], N=cfg["N"], d_model=cfg["d_model"], d_ff=cfg["d_ff"], h=cfg["h"],
+                           dropout=0.0, ft_sizes=cfg["ft_sizes"], diff_encoder=cfg["diff_encoder"],
+                           auto_encoder_ft=cfg["auto_encoder_ft"])
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    for m in model.modules():                       # (MultiHeadedAttention keeps the reference's default p = 0.1)
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    rec = _RecordingOpt(model)
+    ts = TrainStep(model, cfg["vocab"], graph=False, optimizer=rec)
+    batch = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()}
+    loss = float(ts.eager(batch))                      # normalisers: None -> counted on the device
+    oloss, og = O.loss_and_grads(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["trg"], inp["trg_y"], inp["fts"])
+    assert [float(x) for x in ts.norms] == [float((inp["trg_y"] != 1).sum()), float((inp["cap"] != 1).sum())]
+    errs = grad_errors(rec.grads, og)
+    print("TrainStep caption variant: loss %.5f vs %.5f, gradient median %.2e max %.2e"
+          % (loss, oloss, float(np.median(list(errs.values()))), max(errs.values())))
+    assert abs(loss - oloss) <= 5e-3 * abs(oloss)
+    assert max(errs.values()) < 8e-2 and float(np.median(list(errs.values()))) < 1.5e-2
+    # a second batch with other token counts through the same object: its own normalisers
+    inp2 = O.synth_inputs(cfg, seed=10, **shape)
+    batch2 = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp2.items()}
+    ts.eager(batch2)
+    assert [float(x) for x in ts.norms] == [float((inp2["trg_y"] != 1).sum()), float((inp2["cap"] != 1).sum())]
