@@ -10,14 +10,20 @@
 //   * softmax is f32 with one thread per query row (TMEM lane == row): masked
 //     scores become the FINITE -1e9 of mtn.py:227, so a fully masked row yields the
 //     uniform average the reference produces; keys beyond Lk get -inf (weight 0).
-//   * P is rounded to f16, written to shared memory in the UMMA K-major 128B-swizzle
-//     layout and multiplied with V (MN-major operand) by the tensor core; the running
-//     max/sum rescale of O is done in TMEM (online softmax).
+//   * P is rounded to f16 and handed to the tensor core THROUGH TENSOR MEMORY (PT, the default): the softmax
+//     warps overwrite the first KT/2 columns of the tile's S buffer with the packed probabilities (tcgen05.st)
+//     and P V is the TS form of tcgen05.mma (A operand in TMEM, V as MN-major shared-memory operand) -- no
+//     swizzled shared-memory stores, no generic->async proxy fence, and no wait for the previous tile's P V
+//     before P is written (each tile's P lives in its own S buffer).  The S buffer is recycled by issue order:
+//     Q K^T of tile g+2 is issued after P V of tile g, and the tensor pipe executes in issue order.
+//     (PT = false keeps the round-1 form: P through a swizzled shared-memory panel; MTN_B200_ATTN_PTMEM=0.)
+//     The running max/sum rescale of O is done in TMEM (online softmax).
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
 // warps 2..5 softmax / epilogue.  K and V use separate single-slot buffers with their
 // own full/empty barriers so the next K tile streams in while softmax / PV run.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host.h"
@@ -73,9 +79,9 @@ struct AttnParams {
 
 enum {  // "+1": two barriers, one per buffer
   BAR_Q_FULL = 0 /* +1 */, BAR_Q_EMPTY = 2 /* +1 */, BAR_K_FULL = 4 /* +1 */, BAR_K_EMPTY = 6 /* +1 */,
-  BAR_V_FULL = 8 /* +1 */, BAR_V_EMPTY = 10 /* +1 */, BAR_S_FULL = 12 /* +1 */, BAR_S_FREE = 14 /* +1 */, BAR_P_FULL = 16,
-  BAR_PV_DONE,
-  BAR_COUNT
+  BAR_V_FULL = 8 /* +1 */, BAR_V_EMPTY = 10 /* +1 */, BAR_S_FULL = 12 /* +1 */, BAR_S_FREE = 14 /* +1 */, BAR_P_FULL = 16 /* +1 */,
+  BAR_PV_DONE = 18 /* +1 */,
+  BAR_COUNT = 20
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -84,7 +90,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DK, int ATT_KT, bool DROP>
+template <int DK, int ATT_KT, bool DROP, bool PT>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
     attn_core_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -97,6 +103,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   const uint32_t sQ = base + C::OFF_Q, sK = base + C::OFF_K, sV = base + C::OFF_V, sP = base + C::OFF_P;
   const uint32_t bars = base + C::OFF_BAR;
   auto bar = [&](int i) { return bars + 8u * i; };
+  // P V of (global) tile t has completed.  One barrier per tile parity: a waiter may lag the tensor core by a whole
+  // tile (Q K^T runs one tile ahead, so a fast softmax warp can finish tile t while a slow one still holds up P V of
+  // tile t-1); with a single barrier its parity test would then be satisfied by the phase of tile t-2.
+  auto wait_pv = [&](uint32_t t) { mbar_wait(bar(BAR_PV_DONE + (t & 1)), (t >> 1) & 1); };
   const uint32_t tmem_slot = bars + 8u * BAR_COUNT;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_BAR + 8 * BAR_COUNT);
 
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < BAR_COUNT; ++i)
-      mbar_init(bar(i), (i == BAR_S_FREE || i == BAR_S_FREE + 1 || i == BAR_P_FULL) ? 128u : 1u);
+      mbar_init(bar(i), (i == BAR_S_FREE || i == BAR_S_FREE + 1 || i == BAR_P_FULL || i == BAR_P_FULL + 1) ? 128u : 1u);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -178,7 +188,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       const uint32_t n = g / nt, j = g % nt, qb = n & 1, sb = g & 1, ph2 = (g >> 1) & 1;
       if (j == 0) mbar_wait(bar(BAR_Q_FULL + qb), (n >> 1) & 1);
       mbar_wait(bar(BAR_K_FULL + sb), ph2);
-      mbar_wait(bar(BAR_S_FREE + sb), ph2 ^ 1);  // softmax has finished reading this S buffer (tile g-2)
+      // softmax has finished reading this S buffer (tile g-2).  PT: the buffer also holds P of tile g-2; its P V was
+      // issued before this Q K^T (after P_FULL of tile g-2, i.e. after the softmax warps' last access) and the
+      // tensor pipe executes in issue order -- no barrier needed.
+      if (!PT) mbar_wait(bar(BAR_S_FREE + sb), ph2 ^ 1);
+      // ... and P V of tile g-2 has COMPLETED: a later MMA's accumulator write is not ordered behind an earlier MMA's
+      // read of a tensor-memory A operand (measured: without this wait P is occasionally overwritten under the P V
+      // that reads it).  P V of tile g-2 retired long ago in steady state -- the wait is free.
+      if (PT && g >= 2) wait_pv(g - 2);
       tc_fence_after();
       if (lane == 0) {
         const uint64_t dq = make_smem_desc(sQ + qb * C::Q_BYTES, 16, C::SBO, C::SWZ);
@@ -196,7 +213,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       if (g + 1 < total) issue_qk(g + 1);
       const uint32_t ph = g & 1, j = g % nt;
       mbar_wait(bar(BAR_V_FULL + ph), (g >> 1) & 1);
-      mbar_wait(bar(BAR_P_FULL), ph);  // P_g is in shared memory, O has been rescaled
+      // P_g is in place, O has been rescaled.  One barrier per S buffer: a softmax warp can run at most two tiles ahead
+      // of the slowest one (S of tile g+2 exists only after P V of tile g was issued, i.e. after this phase completed),
+      // so its arrival for tile g+2 can never be counted in the phase of tile g.
+      mbar_wait(bar(BAR_P_FULL + ph), (g >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -208,10 +228,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
                                   : make_smem_desc(sP + (kk >> 2) * (ATT_QT * 128) + (kk & 3) * 32, 16, 1024, SWZ_128B);
           // B: V rows [16 kk, 16 kk + 16): two 8-row swizzle atoms, d_k contiguous (MN-major)
           const uint64_t dv = make_smem_desc(sV + ph * C::KV_BYTES + kk * 16 * C::ROWB, ATT_KT * C::ROWB, C::SBO, C::SWZ);
-          tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
+          if (PT) tc_mma_f16_ts(tO, tmem_base + ph * ATT_KT + kk * 8, dv, idesc_o, (j | (uint32_t)kk) != 0);  // P: 16 keys = 8 columns
+          else tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
         }
         tc_commit(bar(BAR_V_EMPTY + ph));
-        tc_commit(bar(BAR_PV_DONE));
+        tc_commit(bar(BAR_PV_DONE + ph));
       }
       __syncwarp();
     }
@@ -268,11 +289,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         for (int j = 0; j < nt; ++j, ++g) {
           const uint32_t ph = g & 1;
           mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
-          if (j > 0) mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
-          mbar_arrive(bar(BAR_S_FREE + ph));
-          mbar_arrive(bar(BAR_P_FULL));
+          if (!PT) {
+            if (j > 0) wait_pv(g - 1);
+            mbar_arrive(bar(BAR_S_FREE + ph));
+          }
+          mbar_arrive(bar(BAR_P_FULL + ph));
         }
-        mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
+        wait_pv(g - 1);
         mrow = mrow_next;
         fetch_mask(mrow, 0);
         continue;
@@ -299,7 +322,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         else fetch_mask(mrow_next, 0);
         mbar_wait(bar(BAR_S_FULL + ph), (g >> 1) & 1);
         tc_fence_after();
-        auto store_chunk = [&](int c, const uint32_t(&e)[32]) {  // f16 P chunk -> swizzled K-major panel
+        auto store_chunk = [&](int c, const uint32_t(&e)[32]) {  // f16 P chunk -> tensor memory / swizzled K-major panel
+          if (PT) {  // keys 32 c .. 32 c + 31 of this row -> columns [16 c, 16 c + 16) of the tile's S buffer
+            uint32_t pk[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2_sat(__uint_as_float(e[2 * t]), __uint_as_float(e[2 * t + 1]));
+            tc_st16(tS + lane_off + c * 16, pk);
+            return;
+          }
           const bool rem = (ATT_KT % 64) != 0 && c == NCH - 1;     // 32-key remainder panel: 64-B rows
           const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * (rem ? 64 : 128);
 #pragma unroll
@@ -315,6 +345,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           }
         };
         auto store_chunk_dyn = [&](int c, const uint32_t(&e)[32]) {  // same, chunk index known at run time
+          if (PT) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2_sat(__uint_as_float(e[2 * t]), __uint_as_float(e[2 * t + 1]));
+            tc_st16(tS + lane_off + c * 16, pk);
+            return;
+          }
           const bool rem = (ATT_KT % 64) != 0 && c == NCH - 1;
           const uint32_t panel = sP + (c >> 1) * (ATT_QT * 128) + row * (rem ? 64 : 128);
           const uint32_t x = rem ? ((uint32_t)(row >> 1) & 3u) : sw, c4 = rem ? 0u : (uint32_t)(c & 1) * 4u;
@@ -344,8 +381,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         // P buffer and O accumulator are in use by PV of the previous tile of this item until it retires; across
         // items the P buffer stages the previous item's output tile until its TMA store has read it
         auto wait_p_buffer = [&]() {
+          if (PT) return;  // P of this tile goes to its own S buffer; the staging tile is waited for in the epilogue
           if (j > 0) {
-            mbar_wait(bar(BAR_PV_DONE), ph ^ 1);
+            wait_pv(g - 1);
             tc_fence_after();
           } else if (staged) {
             if (lane == 0) tma_store_wait_read();
@@ -372,8 +410,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 #pragma unroll
           for (int c = 0; c < NCH; ++c) tc_ld32(tS + lane_off + c * 32, r[c]);
           tc_wait_ld();
-          tc_fence_before();
-          mbar_arrive(bar(BAR_S_FREE + ph));
+          if (!PT) {
+            tc_fence_before();
+            mbar_arrive(bar(BAR_S_FREE + ph));
+          }
           float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -473,14 +513,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
             if (DROP && p.drop.seed != nullptr && nvalid > 0) drop_chunk(c, e);
             store_chunk_dyn(c, e);
           }
-          tc_fence_before();
-          mbar_arrive(bar(BAR_S_FREE + ph));  // this S buffer may be overwritten by Q K^T of tile g+2
+          if (!PT) {
+            tc_fence_before();
+            mbar_arrive(bar(BAR_S_FREE + ph));  // this S buffer may be overwritten by Q K^T of tile g+2
+          }
         }
         const float alpha = ex2_approx(m_run - m_new);  // 1 when the maximum was kept; 0 for j == 0 (l_run is 0)
         l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
         if (rescale) {
           // rescale the running O accumulator in tensor memory (warp-uniform branch)
+          if (PT) {  // (without PT every tile has already waited for the previous P V before writing P)
+            wait_pv(g - 1);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int c = 0; c < DK / 32; ++c) {
             uint32_t o[32];
@@ -492,16 +538,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           }
           tc_wait_st();
         }
-        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+        if (PT) tc_wait_st();               // P (and a rescaled O) have landed in tensor memory
+        else fence_proxy_async_smem();      // P (generic-proxy stores) -> visible to the tensor core
         tc_fence_before();
-        mbar_arrive(bar(BAR_P_FULL));
+        mbar_arrive(bar(BAR_P_FULL + ph));
       }
       // ---- epilogue: O / l -> f16 -> this warp's 32 rows of the (now idle) P buffer in the TMA tile layout -> one
       // TMA store per warp into head hd's column slice of the output (rows beyond Lq are clipped by the tensor
       // map); no CTA-wide synchronisation
-      mbar_wait(bar(BAR_PV_DONE), (g - 1) & 1);
+      wait_pv(g - 1);
       tc_fence_after();
       const float inv_l = 1.f / l_run;
+      if (PT && staged) {  // this warp's previous output tile must have left the staging buffer
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
       if (p.stats != nullptr && qi < p.Lq) p.stats[((size_t)b * p.h + hd) * p.Lq + qi] = make_float2(m_run, inv_l);
 #pragma unroll
       for (int c = 0; c < DK / 32; ++c) {
@@ -539,12 +590,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   }
 }
 
-template <int DK, int ATT_KT, bool DROP>
-static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
+template <int DK, int ATT_KT, bool DROP, bool PT>
+static int launch_attn_v(const MtnAttnCoreArgs& a, cudaStream_t st) {
   using C = AttnCfg<DK, ATT_KT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tc_kernel<DK, ATT_KT, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MTN_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tc_kernel<DK, ATT_KT, DROP, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::TOTAL));
     attr_set = true;
   }
@@ -576,8 +627,18 @@ static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
     slots = 2 * n;
   }
   dim3 grid(n_items < slots ? n_items : slots);
-  MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT, DROP>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, to, p));
+  MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT, DROP, PT>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, to, p));
   return MTN_OK;
+}
+
+template <int DK, int ATT_KT, bool DROP>
+static int launch_attn(const MtnAttnCoreArgs& a, cudaStream_t st) {
+  static int pt = -1;  // MTN_B200_ATTN_PTMEM=0: P through shared memory (round-1 form)
+  if (pt < 0) {
+    const char* e = getenv("MTN_B200_ATTN_PTMEM");
+    pt = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return pt ? launch_attn_v<DK, ATT_KT, DROP, true>(a, st) : launch_attn_v<DK, ATT_KT, DROP, false>(a, st);
 }
 
 static int validate_attn(const MtnAttnCoreArgs* a) {
