@@ -601,6 +601,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
 // own S/O columns of tensor memory -- that work on different heads at the same time; the two softmax warpgroups also
 // split the Q drain and the epilogue's columns.  416 threads (13 warps): 0 producer A, 1 MMA A, 2..5 softmax 0,
 // 6 sender, 7 producer B, 8 MMA B, 9..12 softmax 1.  Everything else is v1.
+// P goes to the tensor core THROUGH TENSOR MEMORY as in csrc/attn.cu (packed f16 over the first KT/2 columns of the
+// tile's S buffer, TS-form tcgen05.mma): the engines keep no P panel in shared memory, and the 32 KB that frees hold
+// the first W_o stage of phase 3, requested while the attention phase still runs.
 // ================================================================================================================
 constexpr int SF2_THREADS = 416;
 
@@ -620,12 +623,16 @@ struct Sf2Cfg {
   static constexpr int RING1 = ST1 * (A_BYTES + B_BYTES);
   static constexpr int RING3 = ST3 * B_BYTES;
   static constexpr int KV_BYTES = KT * 128;            // 8 KB
-  static constexpr int P_BYTES = SF_QT * 128;          // 16 KB: one [128 x 64] K-major panel
-  static constexpr int ENG_BYTES = 4 * KV_BYTES + P_BYTES;   // K0 K1 V0 V1 P = 48 KB
-  static constexpr int RING2 = 2 * ENG_BYTES;
+  static constexpr int ENG_BYTES = 4 * KV_BYTES;       // K0 K1 V0 V1 = 32 KB (P lives in tensor memory)
+  static constexpr int RING2 = 2 * ENG_BYTES;          // the engines use ring bytes [0, 64 KB)
+  // W_o stage ST3-1 of phase 3 sits behind the engines' buffers, so its first k-block can be requested while the
+  // attention phase still runs; the other stages start at the ring base
+  static constexpr int OFF_WO_LAST = RING2 > (ST3 - 1) * B_BYTES ? RING2 : (ST3 - 1) * B_BYTES;
   static constexpr int XPOSE = 8 * 4096;
   static constexpr int RING_A = RING1 > RING2 ? RING1 : RING2;
-  static constexpr int RING_B = RING3 > XPOSE ? RING3 : XPOSE;
+  static constexpr int RING3B = OFF_WO_LAST + B_BYTES;
+  static constexpr int RING_B0 = RING3 > XPOSE ? RING3 : XPOSE;
+  static constexpr int RING_B = RING_B0 > RING3B ? RING_B0 : RING3B;
   static constexpr int RING = RING_A > RING_B ? RING_A : RING_B;
   static constexpr int OFF_BAR = OFF_RING + RING;
   static constexpr int TOTAL = OFF_BAR + 640 + 1024;
@@ -639,10 +646,10 @@ struct Sf2Cfg {
 enum {
   S2_R1_FULL = 0 /* +1 */, S2_R1_EMPTY = 2 /* +1 */, S2_D1_FULL = 4, S2_Q_READY = 5, S2_OWN_O = 6 /* +3 */, S2_PEER_O = 10,
   S2_R3_FULL = 11 /* +2 */, S2_R3_EMPTY = 14 /* +2 */, S2_D3_FULL = 17,
-  S2_ENG = 18,   // per engine (+15 each): K_FULL 0,1  K_EMPTY 2,3  V_FULL 4,5  V_EMPTY 6,7  S_FULL 8,9  S_FREE 10,11  P_FULL 12  PV_DONE 13  ATT_DONE 14
+  S2_ENG = 18,   // per engine (+E_COUNT each): K_FULL 0,1  K_EMPTY 2,3  V_FULL 4,5  V_EMPTY 6,7  S_FULL 8,9  P_FULL 10,11  PV_DONE 12,13  ATT_DONE 14
   S2_COUNT = 18 + 30
 };
-enum { E_K_FULL = 0, E_K_EMPTY = 2, E_V_FULL = 4, E_V_EMPTY = 6, E_S_FULL = 8, E_S_FREE = 10, E_P_FULL = 12, E_PV_DONE = 13, E_ATT_DONE = 14 };
+enum { E_K_FULL = 0, E_K_EMPTY = 2, E_V_FULL = 4, E_V_EMPTY = 6, E_S_FULL = 8, E_P_FULL = 10, E_PV_DONE = 12, E_ATT_DONE = 14, E_COUNT = 15 };
 
 template <int HH>
 __global__ void __launch_bounds__(SF2_THREADS, 1)
@@ -681,8 +688,8 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
       if (i == S2_Q_READY) cnt = 256u;
       if (i >= S2_OWN_O && i < S2_OWN_O + 4) cnt = 128u;
       if (i >= S2_ENG) {
-        const int k = (i - S2_ENG) % 15;
-        if (k == E_S_FREE || k == E_S_FREE + 1 || k == E_P_FULL) cnt = 128u;
+        const int k = (i - S2_ENG) % E_COUNT;
+        if (k == E_P_FULL || k == E_P_FULL + 1) cnt = 128u;
       }
       mbar_init(bar(i), cnt);
     }
@@ -700,9 +707,12 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
 
   // which engine this warp serves (producer / MMA / softmax warps), or -1
   const int eng = (warp == 0 || warp == 1 || (warp >= 2 && warp <= 5)) ? 0 : ((warp == 7 || warp == 8 || warp >= 9) ? 1 : -1);
-  const int EB = S2_ENG + 15 * (eng < 0 ? 0 : eng);
+  const int EB = S2_ENG + E_COUNT * (eng < 0 ? 0 : eng);
+  auto wo_stage = [&](int st) { return sRING + (uint32_t)(st == C::ST3 - 1 ? C::OFF_WO_LAST : st * C::B_BYTES); };
+  // P V of this engine's (global) tile t has completed: one barrier per tile parity (see csrc/attn.cu)
+  auto wait_pv = [&](uint32_t t) { mbar_wait(bar(EB + E_PV_DONE + (t & 1)), (t >> 1) & 1); };
   const uint32_t sE = sRING + (uint32_t)(eng < 0 ? 0 : eng) * C::ENG_BYTES;
-  const uint32_t sK = sE, sV = sE + 2 * C::KV_BYTES, sP = sE + 4 * C::KV_BYTES;
+  const uint32_t sK = sE, sV = sE + 2 * C::KV_BYTES;
   const uint32_t tS = tmem_base + (uint32_t)(eng < 0 ? 0 : eng) * C::ENG_COLS;   // S0 S1 at +0 / +KT, O at +2 KT
   const uint32_t tO = tS + 2 * KT;
   const int head0 = (eng < 0 ? 0 : eng) * HE;   // first local head of this engine
@@ -721,6 +731,12 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
         }
       }
       mbar_wait(bar(S2_D1_FULL), 0);   // the ring region is free once the projection MMAs have retired
+      if (warp == 0) {
+        // first W_o k-block of phase 3 -> the ring bytes the engines do not use (stage ST3-1); k-block kc lives in
+        // stage (kc + ST3 - 1) % ST3, so the stage-reuse parity of k-block kc is (kc / ST3) & 1 as before
+        mbar_arrive_expect_tx(bar(S2_R3_FULL + C::ST3 - 1), C::B_BYTES);
+        tma_load_2d(wo_stage(C::ST3 - 1), &tmWo, bar(S2_R3_FULL + C::ST3 - 1), 0, (int)rank * C::NH);
+      }
       auto load_k = [&](uint32_t g) {
         const uint32_t hh = g / nt, j = g % nt, kb = g & 1, kph = (g >> 1) & 1;
         mbar_wait(bar(EB + E_K_EMPTY + kb), kph ^ 1);
@@ -740,12 +756,12 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
       }
       if (warp == 0) {
         mbar_wait(bar(S2_ENG + E_ATT_DONE), 0);        // both engines have retired their last P V
-        mbar_wait(bar(S2_ENG + 15 + E_ATT_DONE), 0);
-        for (int kc = 0; kc < C::NKB; ++kc) {
-          const int s = kc % C::ST3;
+        mbar_wait(bar(S2_ENG + E_COUNT + E_ATT_DONE), 0);
+        for (int kc = 1; kc < C::NKB; ++kc) {          // (k-block 0 was requested before the attention phase, below)
+          const int s = (kc + C::ST3 - 1) % C::ST3;
           mbar_wait(bar(S2_R3_EMPTY + s), ((kc / C::ST3) & 1) ^ 1);
           mbar_arrive_expect_tx(bar(S2_R3_FULL + s), C::B_BYTES);
-          tma_load_2d(sRING + s * C::B_BYTES, &tmWo, bar(S2_R3_FULL + s), kc * 64, (int)rank * C::NH);
+          tma_load_2d(wo_stage(s), &tmWo, bar(S2_R3_FULL + s), kc * 64, (int)rank * C::NH);
         }
       }
     }
@@ -777,7 +793,7 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
     auto issue_qk = [&](uint32_t g) {
       const uint32_t hh = g / nt, sb = g & 1, ph2 = (g >> 1) & 1;
       mbar_wait(bar(EB + E_K_FULL + sb), ph2);
-      mbar_wait(bar(EB + E_S_FREE + sb), ph2 ^ 1);
+      if (g >= 2) wait_pv(g - 2);   // this S buffer held P of tile g-2: its P V must have COMPLETED (csrc/attn.cu)
       tc_fence_after();
       if (lane == 0) {
         const uint64_t dq = make_smem_desc(sQO + (uint32_t)(head0 + (int)hh) * C::TILE, 16, 1024, SWZ_128B);
@@ -794,17 +810,16 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
       if (g + 1 < total) issue_qk(g + 1);
       const uint32_t ph = g & 1, j = g % nt;
       mbar_wait(bar(EB + E_V_FULL + ph), (g >> 1) & 1);
-      mbar_wait(bar(EB + E_P_FULL), ph);
+      mbar_wait(bar(EB + E_P_FULL + ph), (g >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
         for (int kk = 0; kk < KT / 16; ++kk) {
-          const uint64_t dp = make_smem_desc(sP + kk * 32, 16, 1024, SWZ_128B);
           const uint64_t dv = make_smem_desc(sV + ph * C::KV_BYTES + kk * 16 * 128, KT * 128, 1024, SWZ_128B);
-          tc_mma_f16(tO, dp, dv, idesc_o, (j | (uint32_t)kk) != 0);
+          tc_mma_f16_ts(tO, tS + ph * KT + kk * 8, dv, idesc_o, (j | (uint32_t)kk) != 0);   // P: 16 keys = 8 columns of S buffer ph
         }
         tc_commit(bar(EB + E_V_EMPTY + ph));
-        tc_commit(bar(EB + E_PV_DONE));
+        tc_commit(bar(EB + E_PV_DONE + ph));
         if (g == total - 1) tc_commit(bar(EB + E_ATT_DONE));
       }
       __syncwarp();
@@ -812,17 +827,17 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
     if (warp == 1) {
       // ---- phase 3 (after BOTH engines: their tensor-memory columns become the Y accumulator)
       for (int hh = 0; hh < HH; ++hh) mbar_wait(bar(S2_OWN_O + hh), 0);
-      mbar_wait(bar(S2_ENG + 15 + E_ATT_DONE), 0);
+      mbar_wait(bar(S2_ENG + E_COUNT + E_ATT_DONE), 0);
       mbar_wait(bar(S2_PEER_O), 0);
       tc_fence_after();
       for (int kc = 0; kc < C::NKB; ++kc) {
-        const int s = kc % C::ST3;
+        const int s = (kc + C::ST3 - 1) % C::ST3;
         mbar_wait(bar(S2_R3_FULL + s), (kc / C::ST3) & 1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_tile = ((uint32_t)(kc / HH) == rank ? sQO : sPEER) + (uint32_t)(kc % HH) * C::TILE;
           const uint64_t da = make_smem_desc(a_tile, 16, 1024, SWZ_128B);
-          const uint64_t db = make_smem_desc(sRING + s * C::B_BYTES, 16, 1024, SWZ_128B);
+          const uint64_t db = make_smem_desc(wo_stage(s), 16, 1024, SWZ_128B);
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_f16(tD, da + 2 * k, db + 2 * k, idesc_p, (kc | k) != 0);
           tc_commit(bar(S2_R3_EMPTY + s));
@@ -907,11 +922,9 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
         for (int j = 0; j < nt; ++j, ++g) {
           const uint32_t ph = g & 1;
           mbar_wait(bar(EB + E_S_FULL + ph), (g >> 1) & 1);
-          if (j > 0) mbar_wait(bar(EB + E_PV_DONE), ph ^ 1);
-          mbar_arrive(bar(EB + E_S_FREE + ph));
-          mbar_arrive(bar(EB + E_P_FULL));
+          mbar_arrive(bar(EB + E_P_FULL + ph));
         }
-        mbar_wait(bar(EB + E_PV_DONE), (g - 1) & 1);
+        wait_pv(g - 1);
         mbar_arrive(bar(S2_OWN_O + hl));
         continue;
       }
@@ -932,24 +945,11 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
         fetch_mask(j + 1 < nt ? j + 1 : 0);
         mbar_wait(bar(EB + E_S_FULL + ph), (g >> 1) & 1);
         tc_fence_after();
-        auto store_chunk = [&](int c, const uint32_t(&e)[32]) {
-          const uint32_t panel = sP + row * 128;
-          const uint32_t c4 = (uint32_t)(c & 1) * 4u;
+        auto store_chunk = [&](int c, const uint32_t(&e)[32]) {   // keys 32 c .. +31 of this row -> columns [16 c, 16 c + 16) of the S buffer
+          uint32_t pk[16];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + ((c4 + t) ^ sw) * 16),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t]), __uint_as_float(e[8 * t + 1]))),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 2]), __uint_as_float(e[8 * t + 3]))),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 4]), __uint_as_float(e[8 * t + 5]))),
-                         "r"(pack_f16x2_sat(__uint_as_float(e[8 * t + 6]), __uint_as_float(e[8 * t + 7])))
-                         : "memory");
-          }
-        };
-        auto wait_p_buffer = [&]() {
-          if (j > 0) {
-            mbar_wait(bar(EB + E_PV_DONE), ph ^ 1);
-            tc_fence_after();
-          }
+          for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2_sat(__uint_as_float(e[2 * t]), __uint_as_float(e[2 * t + 1]));
+          tc_st16(tSb + lane_off + c * 16, pk);
         };
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         float m_new;
@@ -966,8 +966,6 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
 #pragma unroll
           for (int c = 0; c < NCH; ++c) tc_ld32(tSb + lane_off + c * 32, r[c]);
           tc_wait_ld();
-          tc_fence_before();
-          mbar_arrive(bar(EB + E_S_FREE + ph));
           float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -984,7 +982,6 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
               r[c][i] = __float_as_uint(e);
             }
           }
-          wait_p_buffer();
 #pragma unroll
           for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
         } else {
@@ -1011,7 +1008,6 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
             }
           }
           pick_max(m_tile);
-          wait_p_buffer();
 #pragma unroll 1
           for (int c = 0; c < NCH; ++c) {
             const int nvalid = p.Lk - (j * KT + c * 32);
@@ -1041,13 +1037,13 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
             }
             store_chunk(c, e);
           }
-          tc_fence_before();
-          mbar_arrive(bar(EB + E_S_FREE + ph));
         }
         const float alpha = sf_ex2(m_run - m_new);
         l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
         if (rescale) {
+          wait_pv(g - 1);   // (rescale implies j > 0) the accumulator is idle once the previous tile's P V has retired
+          tc_fence_after();
 #pragma unroll
           for (int c = 0; c < DK / 32; ++c) {
             uint32_t o[32];
@@ -1059,11 +1055,11 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
           }
           tc_wait_st();
         }
-        fence_proxy_async_smem();
+        tc_wait_st();   // P (and a rescaled O) have landed in tensor memory
         tc_fence_before();
-        mbar_arrive(bar(EB + E_P_FULL));
+        mbar_arrive(bar(EB + E_P_FULL + ph));
       }
-      mbar_wait(bar(EB + E_PV_DONE), (g - 1) & 1);
+      wait_pv(g - 1);
       tc_fence_after();
       const float inv_l = 1.f / l_run;
       const uint32_t tile = sQO + (uint32_t)hl * C::TILE + row * 128;
