@@ -436,8 +436,76 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
             if (DROP && p.drop.seed != nullptr) drop_chunk(c, r[c]);
             store_chunk(c, r[c]);
           }
+        } else if (!DROP && ATT_KT == 64) {
+          // (64-key tiles only, i.e. the single-tile sites of short memories: measured 8.4 -> 7.5 us there, but with three
+          // chunks per tile the unrolled code of this path costs more in instruction-cache misses than it saves --
+          // causal self-attention 16.1 -> 22.1 us -- so 96-key tiles keep the compact chunk loop below.)
+          // ---- masked / ragged tile (padding tail, end of the sequence, causal diagonal, holes), still register-resident:
+          // ONE TMEM round trip, then per 32-key chunk a warp-uniform choice between the select-free code of a plain tile
+          // (every row keeps every key), a constant (no row keeps any key: every in-range score is the -1e9 of
+          // mtn.py:227, keys beyond Lk weigh 0) and per-key selects.
+          uint32_t r[NCH][32];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tc_ld32(tS + lane_off + c * 32, r[c]);
+          uint32_t inbv[NCH], kmv[NCH];
+          int kind[NCH];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const int nvalid = p.Lk - (j * ATT_KT + c * 32);  // keys of this chunk inside the sequence (warp-uniform)
+            inbv[c] = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+            kmv[c] = mwv[c] & inbv[c];
+            kind[c] = __all_sync(0xffffffffu, kmv[c] == 0xffffffffu) ? 0 : (__all_sync(0xffffffffu, kmv[c] == 0u) ? 1 : 2);
+          }
+          tc_wait_ld();
+          if (!PT) {
+            tc_fence_before();
+            mbar_arrive(bar(BAR_S_FREE + ph));
+          }
+          float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+          uint32_t masked_any = 0u;  // some in-range key of this row is masked
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            masked_any |= inbv[c] & ~mwv[c];
+            if (kind[c] == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[c][i]));
+            } else if (kind[c] == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                mx[i & 3] = fmaxf(mx[i & 3], ((kmv[c] >> i) & 1u) ? __uint_as_float(r[c][i]) : -CUDART_INF_F);
+            }
+          }
+          pick_max(fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1, masked_any ? t_masked : -CUDART_INF_F));
+          const float pm = ex2_approx(t_masked - m_new);  // weight of a masked key: 0 unless the whole row is masked so far
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (kind[c] == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float e = ex2_approx(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
+                l4[i & 3] += e;
+                r[c][i] = __float_as_uint(e);
+              }
+            } else if (kind[c] == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[c][i] = ((inbv[c] >> i) & 1u) ? __float_as_uint(pm) : 0u;
+              l4[0] += pm * (float)__popc(inbv[c]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = ex2_approx(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
+                const float e = ((kmv[c] >> i) & 1u) ? x : (((inbv[c] >> i) & 1u) ? pm : 0.f);
+                l4[i & 3] += e;
+                r[c][i] = __float_as_uint(e);
+              }
+            }
+          }
+          wait_p_buffer();
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
         } else {
-          // ---- general tile: two passes over the S buffer, one 32-key chunk at a time.  Per chunk (warp-uniform):
+          // ---- general tile (96-key tiles, and training-mode dropout: Philox needs the registers): two passes over the S
+          // buffer, one 32-key chunk at a time, compact code.  Per chunk (warp-uniform):
           // beyond the sequence -> zeros; no kept key for ANY row of the warp (padding tail of a key-padding mask)
           // -> every in-range score is the constant -1e9, nothing to read from TMEM; otherwise per-key selects.
           float m_tile = -CUDART_INF_F;

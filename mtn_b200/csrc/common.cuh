@@ -121,6 +121,15 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// TMA reduce-add store: global[tile] += shared tile (element type of the tensor map; f32 here), clipped like a store.
+// One bulk operation replaces the per-lane red.global.add instructions of an epilogue (~1 lane per clock per SM).
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the committed stores have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

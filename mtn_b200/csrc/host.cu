@@ -45,7 +45,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides_bytes, const cuuint32_t* box, TmSwizzle swz) {
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, TmSwizzle swz,
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   EncodeTiledFn fn = encode_fn();
   MTN_REQUIRE(fn != nullptr, MTN_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   MTN_REQUIRE(aligned16(base), MTN_E_ALIGN, "TMA base pointer %p is not 16-byte aligned", base);
@@ -53,7 +54,7 @@ static int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuin
     MTN_REQUIRE(strides_bytes[i] % 16 == 0, MTN_E_ALIGN, "TMA stride %llu B is not a multiple of 16",
                 (unsigned long long)strides_bytes[i]);
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims,
+  CUresult r = fn(out, dtype, rank, const_cast<void*>(base), dims,
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swz == TM_SWZ_128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -76,6 +77,15 @@ int make_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
   cuuint64_t strides[2] = {ld * 2, batch_stride * 2};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   return encode(out, base, 3, dims, strides, box, swz);
+}
+
+int make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
+                     uint64_t ld, uint64_t batch_stride, uint32_t box_cols, uint32_t box_rows,
+                     TmSwizzle swz) {
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld * 4, batch_stride * 4};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  return encode(out, base, 3, dims, strides, box, swz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 }  // namespace mtn

@@ -73,4 +73,9 @@ int make_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
                      uint64_t ld, uint64_t batch_stride, uint32_t box_cols, uint32_t box_rows,
                      TmSwizzle swz);
 
+// f32, rank 3 (the residual stream as the target of TMA reduce-add stores): strides in elements
+int make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
+                     uint64_t ld, uint64_t batch_stride, uint32_t box_cols, uint32_t box_rows,
+                     TmSwizzle swz);
+
 }  // namespace mtn

@@ -594,6 +594,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
 }
 
 // ================================================================================================================
+// Debug instrument (tools/site_phases.py): when a stamp buffer is registered, a few role-leader threads of the v2 kernel
+// record clock64() at phase boundaries: stamps[blockIdx.x * 16 + i].  NULL (the default) costs one load per CTA.
+__device__ unsigned long long* g_sf_stamps = nullptr;
+#define SF_STAMP(i) do { if (stamps != nullptr) stamps[blockIdx.x * 16 + (i)] = (unsigned long long)clock64(); } while (0)
+
 // v2: TWO attention engines per CTA.  v1 runs the HH heads of a CTA one after the other on one softmax warpgroup; the
 // attention phase is a per-row latency chain (TMEM load -> max -> exp -> P store -> P V -> O drain), so the tensor
 // pipe idles and phase 2 is ~40 % of the kernel.  Here the CTA carries two complete engines -- K/V producer warp, MMA
@@ -619,8 +624,11 @@ struct Sf2Cfg {
   static constexpr int OFF_RING = OFF_PEER + HH * TILE;
   static constexpr int A_BYTES = TILE;
   static constexpr int B_BYTES = NH * 128;
-  static constexpr int ST1 = 2, ST3 = 3;
-  static constexpr int RING1 = ST1 * (A_BYTES + B_BYTES);
+  // phase 1: two stages in the ring region plus one in the (still unused) Q/O tile region -- the projection is bound by
+  // the latency of its operand loads, not by their bandwidth
+  static constexpr int ST1 = 3, ST3 = 3;
+  static constexpr int RING1 = (ST1 - 1) * (A_BYTES + B_BYTES);
+  static_assert(A_BYTES + B_BYTES <= HH * TILE, "third phase-1 stage lives in the Q/O tile region");
   static constexpr int RING3 = ST3 * B_BYTES;
   static constexpr int KV_BYTES = KT * 128;            // 8 KB
   static constexpr int ENG_BYTES = 4 * KV_BYTES;       // K0 K1 V0 V1 = 32 KB (P lives in tensor memory)
@@ -628,14 +636,15 @@ struct Sf2Cfg {
   // W_o stage ST3-1 of phase 3 sits behind the engines' buffers, so its first k-block can be requested while the
   // attention phase still runs; the other stages start at the ring base
   static constexpr int OFF_WO_LAST = RING2 > (ST3 - 1) * B_BYTES ? RING2 : (ST3 - 1) * B_BYTES;
-  static constexpr int XPOSE = 8 * 4096;
+  static constexpr int XPOSE = 8 * 8192;   // epilogue staging: two 4 KB tiles per softmax warp
   static constexpr int RING_A = RING1 > RING2 ? RING1 : RING2;
   static constexpr int RING3B = OFF_WO_LAST + B_BYTES;
   static constexpr int RING_B0 = RING3 > XPOSE ? RING3 : XPOSE;
   static constexpr int RING_B = RING_B0 > RING3B ? RING_B0 : RING3B;
   static constexpr int RING = RING_A > RING_B ? RING_A : RING_B;
   static constexpr int OFF_BAR = OFF_RING + RING;
-  static constexpr int TOTAL = OFF_BAR + 640 + 1024;
+  static constexpr int OFF_BIAS = OFF_BAR + 448;        // b_q of this CTA's NH columns (f32)
+  static constexpr int TOTAL = OFF_BIAS + NH * 4 + 1024;
   static constexpr uint32_t ENG_COLS = 2 * KT + DK;    // S0 S1 O = 192 columns per engine
   static constexpr uint32_t TMEM_COLS = 512;
   static_assert(2 * ENG_COLS <= 512 && NH <= 256, "TMEM budget");
@@ -644,18 +653,20 @@ struct Sf2Cfg {
 };
 
 enum {
-  S2_R1_FULL = 0 /* +1 */, S2_R1_EMPTY = 2 /* +1 */, S2_D1_FULL = 4, S2_Q_READY = 5, S2_OWN_O = 6 /* +3 */, S2_PEER_O = 10,
-  S2_R3_FULL = 11 /* +2 */, S2_R3_EMPTY = 14 /* +2 */, S2_D3_FULL = 17,
-  S2_ENG = 18,   // per engine (+E_COUNT each): K_FULL 0,1  K_EMPTY 2,3  V_FULL 4,5  V_EMPTY 6,7  S_FULL 8,9  P_FULL 10,11  PV_DONE 12,13  ATT_DONE 14
-  S2_COUNT = 18 + 30
+  S2_R1_FULL = 0 /* +2 */, S2_R1_EMPTY = 3 /* +2 */, S2_D1_FULL = 6, S2_Q_READY = 7, S2_OWN_O = 8 /* +3 */, S2_PEER_O = 12,
+  S2_R3_FULL = 13 /* +2 */, S2_R3_EMPTY = 16 /* +2 */, S2_D3_FULL = 19,
+  S2_ENG = 20,   // per engine (+E_COUNT each): K_FULL 0,1  K_EMPTY 2,3  V_FULL 4,5  V_EMPTY 6,7  S_FULL 8,9  P_FULL 10,11  PV_DONE 12,13  ATT_DONE 14
+  S2_COUNT = 20 + 30
 };
+static_assert(8 * S2_COUNT + 8 <= 448, "barrier area");
 enum { E_K_FULL = 0, E_K_EMPTY = 2, E_V_FULL = 4, E_V_EMPTY = 6, E_S_FULL = 8, E_P_FULL = 10, E_PV_DONE = 12, E_ATT_DONE = 14, E_COUNT = 15 };
 
 template <int HH>
 __global__ void __launch_bounds__(SF2_THREADS, 1)
     attn_site_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
                             const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                            const __grid_constant__ CUtensorMap tmWo, const SfParams p) {
+                            const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmXo,
+                            const SfParams p) {
   using C = Sf2Cfg<HH>;
   constexpr int DK = C::DK, KT = C::KT, HE = HH / 2;   // heads per engine
   extern __shared__ uint8_t smem_raw[];
@@ -683,6 +694,7 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmWo);
+    tma_prefetch_desc(&tmXo);
     for (int i = 0; i < S2_COUNT; ++i) {
       uint32_t cnt = 1u;
       if (i == S2_Q_READY) cnt = 256u;
@@ -703,11 +715,22 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tD = tmem_base;   // Q / Y accumulator: columns [0, NH); the engines reuse columns [0, 384) in phase 2
+  unsigned long long* const stamps = (lane == 0) ? g_sf_stamps : nullptr;
+  float* const s_bq = reinterpret_cast<float*>(smem + C::OFF_BIAS);
+  if (warp >= 2 && warp != 6 && warp != 7 && warp != 8) {   // the 8 softmax warps: b_q (a parameter, not produced upstream) -> shared memory
+    const int t = ((warp >= 9 ? warp - 5 : warp - 2) << 5) + lane;   // 0 .. 255
+    if (t < C::NH) s_bq[t] = __ldg(p.b_q + rank * C::NH + t);
+    named_bar_sync(1, 256);
+  }
   pdl_wait();
+  if (warp == 0) SF_STAMP(0);
 
   // which engine this warp serves (producer / MMA / softmax warps), or -1
   const int eng = (warp == 0 || warp == 1 || (warp >= 2 && warp <= 5)) ? 0 : ((warp == 7 || warp == 8 || warp >= 9) ? 1 : -1);
   const int EB = S2_ENG + E_COUNT * (eng < 0 ? 0 : eng);
+  auto r1_stage = [&](int st) { return st < C::ST1 - 1 ? sRING + (uint32_t)st * (C::A_BYTES + C::B_BYTES) : sQO; };
+  // phase 3 walks the output projection's contraction OWN heads first, then the peer's: step i is k-block k3(i)
+  auto k3 = [&](int i) { return (int)((rank * HH + (uint32_t)i) % (uint32_t)C::NKB); };
   auto wo_stage = [&](int st) { return sRING + (uint32_t)(st == C::ST3 - 1 ? C::OFF_WO_LAST : st * C::B_BYTES); };
   // P V of this engine's (global) tile t has completed: one barrier per tile parity (see csrc/attn.cu)
   auto wait_pv = [&](uint32_t t) { mbar_wait(bar(EB + E_PV_DONE + (t & 1)), (t >> 1) & 1); };
@@ -725,17 +748,18 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
           const int s = kb % C::ST1;
           mbar_wait(bar(S2_R1_EMPTY + s), ((kb / C::ST1) & 1) ^ 1);
           mbar_arrive_expect_tx(bar(S2_R1_FULL + s), C::A_BYTES + C::B_BYTES);
-          const uint32_t st = sRING + s * (C::A_BYTES + C::B_BYTES);
+          const uint32_t st = r1_stage(s);
           tma_load_3d(st, &tmX, bar(S2_R1_FULL + s), kb * 64, qt * SF_QT, b);
           tma_load_2d(st + C::A_BYTES, &tmWq, bar(S2_R1_FULL + s), kb * 64, (int)rank * C::NH);
         }
+        SF_STAMP(1);
       }
       mbar_wait(bar(S2_D1_FULL), 0);   // the ring region is free once the projection MMAs have retired
       if (warp == 0) {
         // first W_o k-block of phase 3 -> the ring bytes the engines do not use (stage ST3-1); k-block kc lives in
         // stage (kc + ST3 - 1) % ST3, so the stage-reuse parity of k-block kc is (kc / ST3) & 1 as before
         mbar_arrive_expect_tx(bar(S2_R3_FULL + C::ST3 - 1), C::B_BYTES);
-        tma_load_2d(wo_stage(C::ST3 - 1), &tmWo, bar(S2_R3_FULL + C::ST3 - 1), 0, (int)rank * C::NH);
+        tma_load_2d(wo_stage(C::ST3 - 1), &tmWo, bar(S2_R3_FULL + C::ST3 - 1), k3(0) * 64, (int)rank * C::NH);
       }
       auto load_k = [&](uint32_t g) {
         const uint32_t hh = g / nt, j = g % nt, kb = g & 1, kph = (g >> 1) & 1;
@@ -761,7 +785,7 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
           const int s = (kc + C::ST3 - 1) % C::ST3;
           mbar_wait(bar(S2_R3_EMPTY + s), ((kc / C::ST3) & 1) ^ 1);
           mbar_arrive_expect_tx(bar(S2_R3_FULL + s), C::B_BYTES);
-          tma_load_2d(wo_stage(s), &tmWo, bar(S2_R3_FULL + s), kc * 64, (int)rank * C::NH);
+          tma_load_2d(wo_stage(s), &tmWo, bar(S2_R3_FULL + s), k3(kc) * 64, (int)rank * C::NH);
         }
       }
     }
@@ -777,7 +801,7 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
         mbar_wait(bar(S2_R1_FULL + s), (kb / C::ST1) & 1);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t st = sRING + s * (C::A_BYTES + C::B_BYTES);
+          const uint32_t st = r1_stage(s);
           const uint64_t da = make_smem_desc(st, 16, 1024, SWZ_128B);
           const uint64_t db = make_smem_desc(st + C::A_BYTES, 16, 1024, SWZ_128B);
 #pragma unroll
@@ -787,6 +811,7 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
         }
         __syncwarp();
       }
+      SF_STAMP(2);
     }
     mbar_wait(bar(S2_Q_READY), 0);   // every Q tile is in shared memory AND the whole Q accumulator has been read
     tc_fence_after();
@@ -828,14 +853,18 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
       // ---- phase 3 (after BOTH engines: their tensor-memory columns become the Y accumulator)
       for (int hh = 0; hh < HH; ++hh) mbar_wait(bar(S2_OWN_O + hh), 0);
       mbar_wait(bar(S2_ENG + E_COUNT + E_ATT_DONE), 0);
-      mbar_wait(bar(S2_PEER_O), 0);
+      SF_STAMP(11);
       tc_fence_after();
-      for (int kc = 0; kc < C::NKB; ++kc) {
+      for (int kc = 0; kc < C::NKB; ++kc) {   // step kc: k-block k3(kc) -- own O tiles first, the peer's arrive meanwhile
         const int s = (kc + C::ST3 - 1) % C::ST3;
+        if (kc == HH) {
+          mbar_wait(bar(S2_PEER_O), 0);
+          SF_STAMP(7);
+        }
         mbar_wait(bar(S2_R3_FULL + s), (kc / C::ST3) & 1);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_tile = ((uint32_t)(kc / HH) == rank ? sQO : sPEER) + (uint32_t)(kc % HH) * C::TILE;
+          const uint32_t a_tile = (kc < HH ? sQO : sPEER) + (uint32_t)(kc % HH) * C::TILE;
           const uint64_t da = make_smem_desc(a_tile, 16, 1024, SWZ_128B);
           const uint64_t db = make_smem_desc(wo_stage(s), 16, 1024, SWZ_128B);
 #pragma unroll
@@ -872,14 +901,14 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
     // ---- phase 1 drain of this group's heads: columns [eng * NH/2, (eng+1) * NH/2)
     mbar_wait(bar(S2_D1_FULL), 0);
     tc_fence_after();
+    if (warp == 2) SF_STAMP(3);
 #pragma unroll 1
     for (int c = eng * CH; c < (eng + 1) * CH; ++c) {
       uint32_t r[32];
       tc_ld32(tD + lane_off + c * 32, r);
-      const float* bq = p.b_q + rank * C::NH + c * 32;
       float4 bb[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) bb[t] = __ldg(reinterpret_cast<const float4*>(bq) + t);
+      for (int t = 0; t < 8; ++t) bb[t] = reinterpret_cast<const float4*>(s_bq + c * 32)[t];   // broadcast reads
       tc_wait_ld();
       const uint32_t tile = sQO + (uint32_t)(c >> 1) * C::TILE + row * 128;
 #pragma unroll
@@ -897,6 +926,7 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar(S2_Q_READY));
+    if (warp == 2) SF_STAMP(4);
 
     // ---- phase 2
     const bool live = qt * SF_QT + q4 * 32 < p.Lq;
@@ -945,6 +975,8 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
         fetch_mask(j + 1 < nt ? j + 1 : 0);
         mbar_wait(bar(EB + E_S_FULL + ph), (g >> 1) & 1);
         tc_fence_after();
+        if (warp == 2 && g == 0) SF_STAMP(5);
+        if (warp == 2 && g == 1) SF_STAMP(15);
         auto store_chunk = [&](int c, const uint32_t(&e)[32]) {   // keys 32 c .. +31 of this row -> columns [16 c, 16 c + 16) of the S buffer
           uint32_t pk[16];
 #pragma unroll
@@ -985,58 +1017,62 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
 #pragma unroll
           for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
         } else {
-          float m_tile = -CUDART_INF_F;
-#pragma unroll 1
+          // masked / ragged tile, register-resident like a plain one (csrc/attn.cu): per 32-key chunk a warp-uniform choice
+          // between select-free code (every row keeps every key), a constant (no row keeps any key) and per-key selects
+          uint32_t r[NCH][32];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tc_ld32(tSb + lane_off + c * 32, r[c]);
+          uint32_t inbv[NCH], kmv[NCH];
+          int kind[NCH];
+#pragma unroll
           for (int c = 0; c < NCH; ++c) {
             const int nvalid = p.Lk - (j * KT + c * 32);
-            if (nvalid <= 0) break;
-            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-            const uint32_t mw = c == 0 ? mwv[0] : mwv[NCH - 1];
-            if (__all_sync(0xffffffffu, (mw & inb) == 0u)) {
-              m_tile = fmaxf(m_tile, t_masked);
-              continue;
-            }
-            uint32_t r[32];
-            tc_ld32(tSb + lane_off + c * 32, r);
-            tc_wait_ld();
+            inbv[c] = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+            kmv[c] = mwv[c] & inbv[c];
+            kind[c] = __all_sync(0xffffffffu, kmv[c] == 0xffffffffu) ? 0 : (__all_sync(0xffffffffu, kmv[c] == 0u) ? 1 : 2);
+          }
+          tc_wait_ld();
+          float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+          uint32_t masked_any = 0u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float t = __uint_as_float(r[i]) * c1;
-              t = ((mw >> i) & 1u) ? t : t_masked;
-              t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-              m_tile = fmaxf(m_tile, t);
+          for (int c = 0; c < NCH; ++c) {
+            masked_any |= inbv[c] & ~mwv[c];
+            if (kind[c] == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[c][i]));
+            } else if (kind[c] == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                mx[i & 3] = fmaxf(mx[i & 3], ((kmv[c] >> i) & 1u) ? __uint_as_float(r[c][i]) : -CUDART_INF_F);
             }
           }
-          pick_max(m_tile);
-#pragma unroll 1
-          for (int c = 0; c < NCH; ++c) {
-            const int nvalid = p.Lk - (j * KT + c * 32);
-            const uint32_t inb = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-            const uint32_t mw = c == 0 ? mwv[0] : mwv[NCH - 1];
-            uint32_t e[32];
-            if (nvalid > 0 && __all_sync(0xffffffffu, (mw & inb) == 0u)) {
-              const float pm = sf_ex2(t_masked - m_new);
+          pick_max(fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c1, masked_any ? t_masked : -CUDART_INF_F));
+          const float pm = sf_ex2(t_masked - m_new);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) e[i] = ((inb >> i) & 1u) ? __float_as_uint(pm) : 0u;
-              l4[0] += pm * (float)__popc(inb);
-            } else if (nvalid > 0) {
-              tc_ld32(tSb + lane_off + c * 32, e);
-              tc_wait_ld();
+          for (int c = 0; c < NCH; ++c) {
+            if (kind[c] == 0) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                float t = __uint_as_float(e[i]) * c1;
-                t = ((mw >> i) & 1u) ? t : t_masked;
-                t = ((inb >> i) & 1u) ? t : -CUDART_INF_F;
-                const float x = sf_ex2(t - m_new);
-                l4[i & 3] += x;
-                e[i] = __float_as_uint(x);
+                const float e = sf_ex2(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
+                l4[i & 3] += e;
+                r[c][i] = __float_as_uint(e);
               }
+            } else if (kind[c] == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[c][i] = ((inbv[c] >> i) & 1u) ? __float_as_uint(pm) : 0u;
+              l4[0] += pm * (float)__popc(inbv[c]);
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) e[i] = 0u;
+              for (int i = 0; i < 32; ++i) {
+                const float x = sf_ex2(fmaf(__uint_as_float(r[c][i]), c1, -m_new));
+                const float e = ((kmv[c] >> i) & 1u) ? x : (((inbv[c] >> i) & 1u) ? pm : 0.f);
+                l4[i & 3] += e;
+                r[c][i] = __float_as_uint(e);
+              }
             }
-            store_chunk(c, e);
           }
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) store_chunk(c, r[c]);
         }
         const float alpha = sf_ex2(m_run - m_new);
         l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
@@ -1058,9 +1094,11 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
         tc_wait_st();   // P (and a rescaled O) have landed in tensor memory
         tc_fence_before();
         mbar_arrive(bar(EB + E_P_FULL + ph));
+        if (warp == 2 && g == 0) SF_STAMP(12);
       }
       wait_pv(g - 1);
       tc_fence_after();
+      if (warp == 2 && hh == 0) SF_STAMP(13);
       const float inv_l = 1.f / l_run;
       const uint32_t tile = sQO + (uint32_t)hl * C::TILE + row * 128;
 #pragma unroll
@@ -1082,49 +1120,57 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar(S2_OWN_O + hl));
+      if (warp == 2 && hh == 0) SF_STAMP(14);
     }
+    if (warp == 2) SF_STAMP(6);
+    if (warp == 9) SF_STAMP(10);
 
-    // ---- phase 3 epilogue: this group's half of the CTA's output columns
+    // ---- phase 3 epilogue: this group's half of the CTA's output columns.  The residual add x += Y + b_o goes out as
+    // TMA REDUCE-ADD stores: per warp and 32-column chunk, the [32 rows x 32 cols] f32 tile is staged in shared memory
+    // (row per thread, 128B-swizzled like the tensor map) and one bulk operation adds it into the residual stream.
+    // (Per-lane red.global.add retires ~1 lane per clock per SM: 128 KB per CTA took ~8.5 k cycles, the longest
+    // phase of the kernel; tools/site_phases.py.)  Rows beyond Lq are clipped by the tensor map.
+    const int t256 = ((warp >= 9 ? warp - 5 : warp - 2) << 5) + lane;
+    const float bo_mine = t256 < C::NH ? __ldg(p.b_o + rank * C::NH + t256) : 0.f;   // requested while phase 3 still runs
+    mbar_wait(bar(S2_Q_READY), 0);          // (long complete) every warp has finished reading b_q from shared memory
+    if (t256 < C::NH) s_bq[t256] = bo_mine;   // the bias area now holds b_o of this CTA's columns
+    named_bar_sync(1, 256);
     mbar_wait(bar(S2_D3_FULL), 0);
     tc_fence_after();
-    const int ew = eng * 4 + q4;   // transpose tile of this warp
-    float4* xp = reinterpret_cast<float4*>(smem + C::OFF_RING + ew * 4096);
-    const int sub_r = lane >> 2, c8 = lane & 3;
-    const int wr_base = lane * 8, wr_sw = lane & 7;
-    const int rd0 = sub_r * 8 + ((2 * c8) ^ sub_r), rd1 = sub_r * 8 + ((2 * c8 + 1) ^ sub_r);
-    const int rows_valid = min(SF_QT, p.Lq - qt * SF_QT);
-    const size_t grow0 = (size_t)b * p.Lq + (size_t)qt * SF_QT;
+    if (warp == 2) SF_STAMP(8);
+    const int ew = eng * 4 + q4;
+    const uint32_t tiles = sRING + (uint32_t)ew * 8192u;   // two 4 KB staging tiles per warp
 #pragma unroll 1
-    for (int c = eng * CH; c < (eng + 1) * CH; ++c) {
-      const int col = (int)rank * C::NH + c * 32 + c8 * 8;
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b_o + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b_o + col + 4));
+    for (int cc = 0; cc < CH; ++cc) {   // (sw == row % 8 == lane % 8: the 16-byte chunk XOR of the 128B swizzle)
+      const int c = eng * CH + cc;
+      const uint32_t tile = tiles + (uint32_t)(cc & 1) * 4096u;
       uint32_t acc[32];
       tc_ld32(tD + lane_off + c * 32, acc);
+      if (cc >= 2) {   // the reduce-add that last used this tile has read it
+        if (lane == 0) tma_store_wait_read1();
+        __syncwarp();
+      }
+      float4 bb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bb[j] = reinterpret_cast<const float4*>(s_bq + c * 32)[j];
       tc_wait_ld();
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj)
-        xp[wr_base + (jj ^ wr_sw)] = make_float4(__uint_as_float(acc[4 * jj]), __uint_as_float(acc[4 * jj + 1]),
-                                                 __uint_as_float(acc[4 * jj + 2]), __uint_as_float(acc[4 * jj + 3]));
-      __syncwarp();
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[2 * i] = xp[i * 64 + rd0];
-        v[2 * i + 1] = xp[i * 64 + rd1];
+      for (int j = 0; j < 8; ++j) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + lane * 128 + (((uint32_t)j ^ sw) << 4)),
+                     "f"(__uint_as_float(acc[4 * j]) + bb[j].x), "f"(__uint_as_float(acc[4 * j + 1]) + bb[j].y),
+                     "f"(__uint_as_float(acc[4 * j + 2]) + bb[j].z), "f"(__uint_as_float(acc[4 * j + 3]) + bb[j].w)
+                     : "memory");
       }
+      fence_proxy_async_smem();
       __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rl = q4 * 32 + sub_r + i * 8;
-        if (rl < rows_valid) {
-          float* o = p.x + (grow0 + rl) * p.ld_x + col;
-          grad_red_v4(o, v[2 * i].x + b0.x, v[2 * i].y + b0.y, v[2 * i].z + b0.z, v[2 * i].w + b0.w, 0);
-          grad_red_v4(o + 4, v[2 * i + 1].x + b1.x, v[2 * i + 1].y + b1.y, v[2 * i + 1].z + b1.z, v[2 * i + 1].w + b1.w, 0);
-        }
+      if (lane == 0) {
+        tma_reduce_add_3d(&tmXo, tile, (int)rank * C::NH + c * 32, qt * SF_QT + q4 * 32, b);
+        tma_store_commit();
       }
     }
+    if (lane == 0) tma_store_wait_read();   // (the kernel boundary completes the writes)
     tc_fence_before();
+    if (warp == 2) SF_STAMP(9);
   }
   cluster_sync_all();
   if (warp == 1) {
@@ -1159,8 +1205,11 @@ static int launch_site_fused2(const MtnAttnSiteFusedArgs& a, cudaStream_t st) {
   SfParams p{a.B, a.h, a.Lq, a.Lk, nqt, a.b_q, a.b_o, a.x, a.ld_x, a.mask_bits, a.mask_rows_q, mtn_mask_words(a.Lk),
              1.0f / sqrtf(64.f)};
   dim3 grid(2u * (unsigned)(a.B * nqt));
+  CUtensorMap txo;   // the f32 residual stream, target of the epilogue's reduce-add stores
+  rc = make_tmap_3d_f32(&txo, a.x, d, a.Lq, a.B, a.ld_x, (uint64_t)a.Lq * a.ld_x, 32, 32, TM_SWZ_128);
+  if (rc) return rc;
   MTN_CHECK_CUDA(launch_kernel_cluster(attn_site_fused2_kernel<HH>, grid, dim3(SF2_THREADS), C::TOTAL, st, 2u, tx, twq, tk, tv,
-                                       two, p));
+                                       two, txo, p));
   return MTN_OK;
 }
 
@@ -1196,6 +1245,13 @@ static int launch_site_fused(const MtnAttnSiteFusedArgs& a, cudaStream_t st) {
 }
 
 }  // namespace mtn
+
+// Debug (not part of include/mtn_b200.h): register / clear the phase-stamp buffer of the v2 kernel, [grid * 16] u64.
+extern "C" int mtn_debug_site_stamps(void* dev_ptr) {
+  unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+  MTN_CHECK_CUDA(cudaMemcpyToSymbol(mtn::g_sf_stamps, &p, sizeof(p)));
+  return MTN_OK;
+}
 
 extern "C" int mtn_attn_site_fused_supported(int d, int h) {
   return (h > 0 && d == h * 64 && (d == 512 || d == 256)) ? 1 : 0;
