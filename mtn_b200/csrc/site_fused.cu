@@ -636,7 +636,7 @@ struct Sf2Cfg {
   // W_o stage ST3-1 of phase 3 sits behind the engines' buffers, so its first k-block can be requested while the
   // attention phase still runs; the other stages start at the ring base
   static constexpr int OFF_WO_LAST = RING2 > (ST3 - 1) * B_BYTES ? RING2 : (ST3 - 1) * B_BYTES;
-  static constexpr int XPOSE = 8 * 8192;   // epilogue staging: two 4 KB tiles per softmax warp
+  static constexpr int XPOSE = 0;           // (the epilogue stages in the O tile regions)
   static constexpr int RING_A = RING1 > RING2 ? RING1 : RING2;
   static constexpr int RING3B = OFF_WO_LAST + B_BYTES;
   static constexpr int RING_B0 = RING3 > XPOSE ? RING3 : XPOSE;
@@ -1138,18 +1138,19 @@ __global__ void __launch_bounds__(SF2_THREADS, 1)
     mbar_wait(bar(S2_D3_FULL), 0);
     tc_fence_after();
     if (warp == 2) SF_STAMP(8);
+    // Staging: one 4 KB tile per (warp, chunk) in the Q/O and peer-O tile regions, which are dead once the phase-3 MMAs
+    // have retired (D3_FULL): no tile is reused, every chunk is issued as soon as it is staged.  What bounds this phase is
+    // the SM's write path into L2 (128 KB per CTA at ~26 B per clock measured, whatever the box size: 16 KB boxes issued
+    // by one thread per group were no faster), so the bulk operations should start as early as possible.
     const int ew = eng * 4 + q4;
-    const uint32_t tiles = sRING + (uint32_t)ew * 8192u;   // two 4 KB staging tiles per warp
+    const uint32_t tiles = sQO + (uint32_t)ew * (uint32_t)(CH * 4096);
+    static_assert(8 * CH * 4096 <= 2 * HH * C::TILE, "epilogue staging fits the O tile regions");
 #pragma unroll 1
     for (int cc = 0; cc < CH; ++cc) {   // (sw == row % 8 == lane % 8: the 16-byte chunk XOR of the 128B swizzle)
       const int c = eng * CH + cc;
-      const uint32_t tile = tiles + (uint32_t)(cc & 1) * 4096u;
+      const uint32_t tile = tiles + (uint32_t)cc * 4096u;
       uint32_t acc[32];
       tc_ld32(tD + lane_off + c * 32, acc);
-      if (cc >= 2) {   // the reduce-add that last used this tile has read it
-        if (lane == 0) tma_store_wait_read1();
-        __syncwarp();
-      }
       float4 bb[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) bb[j] = reinterpret_cast<const float4*>(s_bq + c * 32)[j];
