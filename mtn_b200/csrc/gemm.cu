@@ -47,6 +47,7 @@ struct GemmEpi {
   int drop_after_add;      // 0: before the addend (SublayerConnection, mtn.py:127)  1: after it (PositionalEncoding, mtn.py:309)
   // strided batch (element strides between consecutive problems; batch == 1: unused)
   long long s_bias, s_add, s_out32, s_out16;
+  int tma_red;             // in-place residual / accumulating f32 output goes out as TMA reduce-add stores (tmC)
 };
 
 constexpr int BM = 128;
@@ -90,7 +91,7 @@ struct GemmSmem {
 template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP, int BIAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmEpi epi0, int M, int N, int K, int tiles_n, int tiles_per_batch, int num_tiles,
+                       const __grid_constant__ CUtensorMap tmC, const GemmEpi epi0, int M, int N, int K, int tiles_n, int tiles_per_batch, int num_tiles,
                        int tiles_mn, int kb_per_split) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (epi0.tma_red) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full(s), 1);   // producer arrive + tx bytes
       mbar_init(bar_empty(s), CL);  // tcgen05.commit of every CTA in the cluster
@@ -305,6 +307,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
+        if (epi0.tma_red) {
+          // x += A W^T + b (in-place residual) or a split-K partial tile: the [32 rows x 32 cols] f32 block of this warp
+          // is staged row-per-thread (the TMEM layout: no transpose) in its 128B-swizzled shared-memory tile and ONE TMA
+          // reduce-add operation adds it into the output; rows >= M / columns >= N are clipped by the tensor map.
+          // Per-lane red.global.add retires ~16 B per clock per SM, the bulk form ~26 B (the SM's L2 write path):
+          // single-tile launches (N = d residual projections) spend most of their time in this epilogue.
+          const int cb = n0 + c * 32;
+          float4 bb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (epi.bias != nullptr && cb + 4 * j < N) bb[j] = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4 * j));
+          }
+          uint32_t acc[32];
+          tc_ld32(t_acc + c * 32, acc);
+          tc_wait_ld();
+          if (c + 2 >= NCHUNK) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+          }
+          if (lane == 0) tma_store_wait_read();   // this warp's previous block has left the staging tile
+          __syncwarp();
+          const uint32_t tile = base + L::XPOSE_OFF + ew * STAGE_TILE_BYTES + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v0 = fmaf(__uint_as_float(acc[4 * j]), alpha, bb[j].x), v1 = fmaf(__uint_as_float(acc[4 * j + 1]), alpha, bb[j].y);
+            float v2 = fmaf(__uint_as_float(acc[4 * j + 2]), alpha, bb[j].z), v3 = fmaf(__uint_as_float(acc[4 * j + 3]), alpha, bb[j].w);
+            if (epi.act == MTN_ACT_RELU) {
+              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (((uint32_t)j ^ (uint32_t)(lane & 7)) << 4)),
+                         "f"(v0), "f"(v1), "f"(v2), "f"(v3)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&tmC, base + L::XPOSE_OFF + ew * STAGE_TILE_BYTES, cb, m0 + q * 32, bt);
+            tma_store_commit();
+          }
+          continue;
+        }
         if (f16_only) {
           // f16-only outputs (Q/K/V projections, FFN hidden: most of the FLOPs): bias + activation in the
           // row-per-thread layout, round to f16 BEFORE the transpose -- half the shared-memory traffic of the
@@ -467,6 +512,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
       }
     }
+    if (epi0.tma_red && lane == 0) tma_store_wait_read();   // (the kernel boundary completes the writes)
     tc_fence_before();
   }
   // no CTA may leave while a peer can still multicast into its shared memory / arrive on its barriers
@@ -533,7 +579,27 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
               a.ld_mask, a.accumulate, a.out16_pre_add, a.multimem, a.colsum_a, a.mask_scale,
               DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
                       a.drop_thresh ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
-              a.drop_after_add, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16};
+              a.drop_after_add, a.stride_bias, a.stride_add, a.stride_out_f32, a.stride_out_f16, 0};
+  // TMA reduce-add epilogue: the result is ADDED into an f32 output and nothing else is written
+  CUtensorMap tmC = tmA;
+  {
+    static int tma_red_on = -1;   // MTN_B200_GEMM_TMA_RED=0: per-lane red.global.add (round-1 form)
+    if (tma_red_on < 0) {
+      const char* e = getenv("MTN_B200_GEMM_TMA_RED");
+      tma_red_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const bool inplace = a.addend != nullptr && a.addend == a.out_f32 && a.add_period == 0 && a.ld_add == a.ld32 &&
+                         a.stride_add == a.stride_out_f32;
+    const bool eligible = tma_red_on && a.out_f32 != nullptr && a.out_f16 == nullptr && a.relu_mask == nullptr &&
+                          a.drop_seed == nullptr && !a.multimem && (a.accumulate ? a.addend == nullptr : inplace) &&
+                          a.ld32 % 4 == 0 && aligned16(a.out_f32) && (batch == 1 || a.stride_out_f32 % 4 == 0);
+    if (eligible) {
+      rc = make_tmap_3d_f32(&tmC, a.out_f32, a.N, a.M, batch, a.ld32,
+                            batch > 1 ? (uint64_t)a.stride_out_f32 : (uint64_t)a.M * a.ld32, 32, 32, TM_SWZ_128);
+      if (rc) return rc;
+      epi.tma_red = 1;
+    }
+  }
   const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
   const int tiles_mn = tiles_n * ((tiles_m + CL - 1) / CL);
   // split-K (accumulating outputs only): cut the contraction so that the launch is ONE wave of CTAs -- every slice
@@ -552,7 +618,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   const int num_super = tiles_per_batch * batch;
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
   MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP, BIAS>, dim3(clusters * CL),
-                                       dim3(GEMM_THREADS), L::TOTAL, st, (unsigned)CL, tmA, tmB, epi, a.M, a.N, a.K,
+                                       dim3(GEMM_THREADS), L::TOTAL, st, (unsigned)CL, tmA, tmB, tmC, epi, a.M, a.N, a.K,
                                        tiles_n, tiles_per_batch, num_super, tiles_mn, kb_per_split));
   return MTN_OK;
 }

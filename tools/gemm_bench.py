@@ -45,9 +45,10 @@ def main():
         A = torch.randn(M, K, device="cuda").half()
         W = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
         bias = torch.randn(N, device="cuda")
-        res = torch.randn(M, N, device="cuda") if N == 512 else None
+        # residual shapes update the f32 stream IN PLACE (x += A W^T + b), as the engine does
+        o32 = torch.randn(M, N, device="cuda") if N == 512 else None
+        res = o32
         o16 = torch.empty(M, N, device="cuda", dtype=torch.float16) if res is None else None
-        o32 = torch.empty(M, N, device="cuda") if res is not None else None
 
         def run():
             _lib.linear(A, W, bias, addend=res, out_f32=o32, out_f16=o16)
