@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MTN_B200_ABI_VERSION 5   /* v5: batch strides in MtnAttnCoreArgs (KV-cached decoding); v4: `multimem` members in the backward structs */
+#define MTN_B200_ABI_VERSION 6   /* v6: mtn_ffn_fused_fwd; v5: batch strides in MtnAttnCoreArgs (KV-cached decoding); v4: `multimem` members in the backward structs */
 
 enum {
   MTN_OK = 0,
@@ -291,6 +291,14 @@ typedef struct MtnFfnArgs {
 } MtnFfnArgs;
 size_t mtn_ffn_workspace_bytes(int rows, int d, int d_ff);
 int mtn_ffn_fwd(const MtnFfnArgs *args, void *stream);
+
+/* The same sublayer behind the LayerNorm in ONE kernel, the [rows, d_ff] hidden activation never written to HBM
+ * (csrc/ffn_fused.cu; ABI v6):   x += W2 relu(W1 xn + b1) + b2,   xn = LayerNorm(x) as f16 (mtn_layernorm_fwd).
+ * xn_f16: [rows, ld_xn] f16; x: [rows, ld_x] f32 updated in place; w_1: [d_ff, d] f16; w_2: [d, d_ff] f16 (mtn.py:276-277).
+ * Supported: d = 512, d_ff a multiple of 128.  Results are bit-identical to the two mtn_linear_fwd launches of mtn_ffn_fwd. */
+int mtn_ffn_fused_supported(int rows, int d, int d_ff);
+int mtn_ffn_fused_fwd(const void *xn_f16, int ld_xn, float *x, int ld_x, int rows, int d, int d_ff,
+                      const void *w_1, const float *b_1, const void *w_2, const float *b_2, void *stream);
 
 
 /* =====================================================================================================

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -173,6 +173,9 @@ SYMBOLS = {
     "mtn_decode_attn_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
     "mtn_attn_site_fused_supported": (C.c_int, [C.c_int, C.c_int]),
     "mtn_attn_site_fused_fwd": (C.c_int, [C.POINTER(AttnSiteFusedArgs), C.c_void_p]),
+    "mtn_ffn_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "mtn_ffn_fused_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtn_ffn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "mtn_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), C.c_void_p]),
     "mtn_check_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
@@ -502,6 +505,27 @@ def attn_site_fused(xn16, x, w_q, b_q, w_o, b_o, kv, k_col, v_col, B, h, Lq, Lk,
     _launch("attn_site_fused", 4 * rows * d * d + 4 * B * Lq * Lk * d, rows * d * (2 + 8) + 2 * B * Lk * 2 * d + 4 * d * d,
             lambda: lib().mtn_attn_site_fused_fwd(C.byref(a), stream_ptr()),
             keep=(xn16, x, w_q, b_q, w_o, b_o, kv, mask_bits))
+
+
+def ffn_fused_supported(rows, d, d_ff):
+    return bool(lib().mtn_ffn_fused_supported(int(rows), int(d), int(d_ff)))
+
+
+def ffn_fused(xn16, x, w_1, b_1, w_2, b_2):
+    """x [rows, d] f32 += relu(xn16 W1^T + b1) W2^T + b2 in ONE launch, the hidden activation stays on chip
+    (csrc/ffn_fused.cu).  xn16: [rows, d] f16 = LayerNorm(x); w_1: [d_ff, d] f16; w_2: [d, d_ff] f16 (contiguous)."""
+    for t, n in ((xn16, "xn16"), (w_1, "w_1"), (w_2, "w_2")):
+        _req(t, torch.float16, n)
+        assert t.dim() == 2
+    _req(x, torch.float32, "x"); _req(b_1, torch.float32, "b_1"); _req(b_2, torch.float32, "b_2")
+    rows, d = x.shape
+    d_ff = w_1.shape[0]
+    assert tuple(xn16.shape) == (rows, d) and tuple(w_1.shape) == (d_ff, d) and tuple(w_2.shape) == (d, d_ff)
+    assert w_1.is_contiguous() and w_2.is_contiguous() and b_1.numel() == d_ff and b_2.numel() == d
+    _launch("ffn_fused", 4 * rows * d * d_ff, rows * d * (2 + 8) + 4 * d * d_ff,
+            lambda: lib().mtn_ffn_fused_fwd(xn16.data_ptr(), xn16.stride(0), x.data_ptr(), x.stride(0), rows, d, d_ff,
+                                            w_1.data_ptr(), b_1.data_ptr(), w_2.data_ptr(), b_2.data_ptr(), stream_ptr()),
+            keep=(xn16, x, w_1, b_1, w_2, b_2))
 
 
 def embed(ids, lut, pe, scale, ln=None, out_f32=None, out_f16=None, drop=None):

@@ -89,14 +89,14 @@ extern "C" int mtn_attn_site_fwd(const MtnAttnSiteArgs* a, void* stream) {
   }
 
   // Cross sites with full query tiles take the ONE-kernel form (csrc/site_fused.cu: Q projection + attention + output
-  // projection + residual; measured 1.06-1.13x the launch sequence at Lq = 256, profiles/r02_site_bench_v2.txt):
+  // projection + residual; measured 1.23-1.33x the launch sequence at Lq = 256, profiles/r02c_site_bench.txt):
   // LayerNorm -> fused kernel, the residual stream updated in place (x_out is seeded with x when they differ).
-  static int fused_mode = -1;   // MTN_B200_SITE_FUSED: 0 never, 1 whenever supported, default: Lq >= 128
+  static int fused_mode = -1;   // MTN_B200_SITE_FUSED: 0 never, 1 whenever supported, default: Lq >= 64 or Lk <= 64
   if (fused_mode < 0) {
     const char* e = getenv("MTN_B200_SITE_FUSED");
     fused_mode = (e == nullptr || e[0] == 'a') ? 2 : (e[0] == '0' ? 0 : 1);
   }
-  if (!self && fused_mode != 0 && mtn_attn_site_fused_supported(d, a->h) && (fused_mode == 1 || a->Lq >= 128)) {
+  if (!self && fused_mode != 0 && mtn_attn_site_fused_supported(d, a->h) && (fused_mode == 1 || a->Lq >= 64 || Lk <= 64)) {
     int rcf = mtn_layernorm_fwd(a->x, a->ln_a, a->ln_b, a->ln_eps, (int)rq, d, nullptr, xn, stream);
     if (rcf == 0 && a->x_out != a->x)
       rcf = cudaMemcpyAsync(a->x_out, a->x, rq * d * sizeof(float), cudaMemcpyDeviceToDevice, main_st) == cudaSuccess

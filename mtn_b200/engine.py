@@ -90,13 +90,28 @@ def invalidate_weight_caches():
 def _site_fused_ok(d, h, B, Lq, Lk):
     """Does this hoisted-K/V site take the ONE-kernel path (csrc/site_fused.cu)?  MTN_B200_SITE_FUSED = 1: whenever the
     shape is supported; 0: never; default "auto": where it measured faster than the launch sequence Q GEMM -> core ->
-    out-proj GEMM (profiles/r02_site_bench_v2.txt: 1.06-1.13x at Lq = 256, parity or below at Lq <= 64): full query tiles."""
+    out-proj GEMM (profiles/r02c_site_bench.txt: 1.23-1.33x at Lq = 256, 1.06-1.12x at Lq = 64, 1.09-1.16x for few query
+    rows over a short memory, 0.97x for few rows over a long one)."""
     mode = os.environ.get("MTN_B200_SITE_FUSED", "auto")
     if mode == "0" or not _lib.attn_site_fused_supported(d, h):
         return False
     if mode == "1":
         return True
-    return Lq >= 128
+    return Lq >= 64 or Lk <= 64
+
+
+def _ffn_fused_ok(rows, d, d_ff):
+    """Does this feed-forward sublayer take the ONE-kernel path (csrc/ffn_fused.cu)?  MTN_B200_FFN_FUSED = 1: whenever the
+    shape is supported; 0 (default): never -- see DESIGN.md section 4 for the measurement behind the default."""
+    mode = os.environ.get("MTN_B200_FFN_FUSED", FFN_FUSED_DEFAULT)
+    if mode == "0" or not _lib.ffn_fused_supported(rows, d, d_ff):
+        return False
+    if mode == "1":
+        return True
+    return rows >= 4096          # "auto": full machine
+
+
+FFN_FUSED_DEFAULT = "0"
 
 
 class PackedWeights(object):
@@ -249,6 +264,12 @@ class DecoderEngine(object):
 
     @staticmethod
     def _ffn_block(x, ln, Fw, xn16, hid, out16=None):
+        if out16 is None and _ffn_fused_ok(x.shape[0], x.shape[1], Fw["w_1"].shape[0]):
+            # LayerNorm -> ONE kernel: both projections, the [rows, d_ff] hidden activation stays on the SM (csrc/ffn_fused.cu)
+            _lib.layernorm(x, ln[0], ln[1], ln[2], out_f16=xn16)
+            _lib.ffn_fused(xn16, x, Fw["w_1"], Fw["b_1"], Fw["w_2"], Fw["b_2"])
+            _tap("x", x)
+            return
         _ln_linear(x, ln, Fw["w_1"], Fw["b_1"], _lib.ACT_RELU, xn16, hid)
         _tap("hid", hid)
         _lib.linear(hid, Fw["w_2"], Fw["b_2"], addend=x, out_f32=x, out_f16=out16)

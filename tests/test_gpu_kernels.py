@@ -550,6 +550,43 @@ def test_attn_site_fused(L, B, Lq, Lk, d, h, kind):
     assert torch.equal(x_g, x_h), "fused site kernel is not deterministic run to run"
 
 
+# ------------------------------------------------------------------ feed-forward sublayer in one kernel (csrc/ffn_fused.cu)
+@pytest.mark.parametrize("rows,d_ff", [(128, 2048), (300, 2048), (8192, 2048), (70, 256), (1000, 1024)])
+def test_ffn_fused(L, rows, d_ff):
+    """x += relu(xn W1^T + b1) W2^T + b2 in ONE launch (the hidden activation never reaches HBM) against (a) the oracle
+    arithmetic with the kernels' roundings (hidden activation to f16) and (b) the two-launch form linear(ReLU) ->
+    linear(+residual), which runs the same MMAs in the same order: bit-identical."""
+    d = 512
+    assert L.ffn_fused_supported(rows, d, d_ff)
+    g = torch.Generator().manual_seed(rows * 7 + d_ff)
+    xn = torch.randn(rows, d, generator=g).half()
+    x = torch.randn(rows, d, generator=g) * 2
+    w1, w2 = (torch.randn(d_ff, d, generator=g) * 0.05).half(), (torch.randn(d, d_ff, generator=g) * 0.03).half()
+    b1, b2 = torch.randn(d_ff, generator=g) * 0.1, torch.randn(d, generator=g) * 0.1
+    hid_ref = torch.relu(xn.float() @ w1.float().t() + b1).half()
+    ref_delta = hid_ref.float() @ w2.float().t() + b2
+    xd, xn_d, w1d, w2d, b1d, b2d = dev(x), dev(xn), dev(w1), dev(w2), dev(b1), dev(b2)
+    hid = torch.empty(rows, d_ff, device="cuda", dtype=torch.float16)
+    x_seq = xd.clone()
+    L.linear(xn_d, w1d, b1d, act=L.ACT_RELU, out_f16=hid)
+    L.linear(hid, w2d, b2d, addend=x_seq, out_f32=x_seq)
+    x_f = xd.clone()
+    L.ffn_fused(xn_d, x_f, w1d, b1d, w2d, b2d)
+    torch.cuda.synchronize()
+    assert torch.isfinite(x_f).all()
+    e_ref = G.rel_err((x_f - xd).cpu(), ref_delta)
+    e_seq = G.rel_err((x_seq - xd).cpu(), ref_delta)
+    same = bool(torch.equal(x_f, x_seq))
+    print("ffn fused rows=%d d_ff=%d: vs oracle %.2e (two launches %.2e), bit-identical to the two launches: %s"
+          % (rows, d_ff, e_ref, e_seq, same))
+    assert e_ref < 1e-3, (e_ref, e_seq)
+    assert G.rel_err((x_f - xd).cpu(), (x_seq - xd).cpu()) < 2e-6, float((x_f - x_seq).abs().max())
+    x_g = xd.clone()                                      # run-to-run determinism
+    L.ffn_fused(xn_d, x_g, w1d, b1d, w2d, b2d)
+    torch.cuda.synchronize()
+    assert torch.equal(x_f, x_g)
+
+
 # ------------------------------------------------------------------ few-row kernels of KV-cached decoding (csrc/decode_rows.cu)
 @pytest.fixture
 def rows_kernels(L):
