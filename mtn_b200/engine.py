@@ -97,6 +97,8 @@ def _site_fused_ok(d, h, B, Lq, Lk):
         return False
     if mode == "1":
         return True
+    if _lib.ROWS_KERNELS and Lq <= 8 and B * Lq <= 128:
+        return False                 # KV-cached decoding: the few-row kernels (csrc/decode_rows.cu) are faster still
     return Lq >= 64 or Lk <= 64
 
 
