@@ -231,6 +231,20 @@ int mtn_rows_ln_linear_fwd(const float *x, int ldx, const float *a_2, const floa
 int mtn_decode_attn_supported(int Lq, int d_k);
 int mtn_decode_attn_fwd(const MtnAttnCoreArgs *args, void *stream);
 
+/* ---- one KV-cached decoding step as ONE persistent kernel (ABI v6; csrc/decode_rows.cu) ----------------------------
+ * Between mtn_prog_begin and mtn_prog_end, mtn_rows_linear_fwd, mtn_rows_ln_linear_fwd, mtn_decode_attn_fwd (Lq = 1) and
+ * mtn_layernorm_fwd (d = 512) RECORD their launch as a stage instead of launching (every other entry point fails with
+ * MTN_E_CUDA: it would run out of order).  mtn_prog_end copies the stage list (mtn_prog_stage_bytes() bytes per stage)
+ * into host memory supplied by the caller (NULL: discard); after the caller has copied it to the device,
+ * mtn_prog_launch runs the stages in order inside one cooperative kernel, a grid barrier between consecutive stages
+ * (same device functions as the stand-alone kernels: bit-identical results).  `counter`: 4 bytes of device memory.
+ * Graph-capturable; recording is thread-local and touches no CUDA state.                                              */
+int mtn_prog_begin(void);
+int mtn_prog_recording(void);
+int mtn_prog_stage_bytes(void);
+int mtn_prog_end(void *host_dst, size_t capacity, int *n_stages);
+int mtn_prog_launch(const void *dev_prog, int n_stages, void *counter, void *stream);
+
 /* ---- one attention site --------------------------------------------------------
  * Replaces  SublayerConnection.forward(x, lambda x: attn(x, mem, mem, mask))
  * (mtn.py:125-127 around mtn.py:248-267):

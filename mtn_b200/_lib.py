@@ -173,6 +173,11 @@ SYMBOLS = {
     "mtn_decode_attn_fwd": (C.c_int, [C.POINTER(AttnCoreArgs), C.c_void_p]),
     "mtn_attn_site_fused_supported": (C.c_int, [C.c_int, C.c_int]),
     "mtn_attn_site_fused_fwd": (C.c_int, [C.POINTER(AttnSiteFusedArgs), C.c_void_p]),
+    "mtn_prog_begin": (C.c_int, []),
+    "mtn_prog_recording": (C.c_int, []),
+    "mtn_prog_stage_bytes": (C.c_int, []),
+    "mtn_prog_end": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "mtn_prog_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mtn_ffn_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "mtn_ffn_fused_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -505,6 +510,58 @@ def attn_site_fused(xn16, x, w_q, b_q, w_o, b_o, kv, k_col, v_col, B, h, Lq, Lk,
     _launch("attn_site_fused", 4 * rows * d * d + 4 * B * Lq * Lk * d, rows * d * (2 + 8) + 2 * B * Lk * 2 * d + 4 * d * d,
             lambda: lib().mtn_attn_site_fused_fwd(C.byref(a), stream_ptr()),
             keep=(xn16, x, w_q, b_q, w_o, b_o, kv, mask_bits))
+
+
+class StepProgram(object):
+    """A decoding-step program (csrc/decode_rows.cu): the few-row launches of one KV-cached step as the stage list of ONE
+    persistent cooperative kernel.  ``with prog.record():`` runs the step's Python code -- the few-row entry points and
+    ``layernorm`` append stages instead of launching (host-side only: legal during CUDA-graph capture); ``prog.launch()``
+    then runs them (graph-capturable: the stage list is uploaded from pinned memory with a stream-ordered copy).
+    The constructor allocates (pinned host + device buffers): construct OUTSIDE graph capture."""
+
+    MAX_STAGES = 256
+
+    def __init__(self):
+        self.n = 0
+        nbytes = self.MAX_STAGES * int(lib().mtn_prog_stage_bytes())
+        self.host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        self.counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+        self.keep = []
+        self._uploaded = False
+
+    class _Rec(object):
+        def __init__(self, prog):
+            self.prog = prog
+
+        def __enter__(self):
+            global RECORD
+            check(lib().mtn_prog_begin())
+            self.prev, RECORD = RECORD, []        # RECORD pins the operand tensors of every recorded call
+            return self.prog
+
+        def __exit__(self, et, ev, tb):
+            global RECORD
+            rec, RECORD = RECORD, self.prev
+            n = C.c_int(0)
+            if et is not None:
+                lib().mtn_prog_end(None, 0, C.byref(n))
+                return False
+            p = self.prog
+            check(lib().mtn_prog_end(p.host.data_ptr(), p.host.numel(), C.byref(n)))
+            p.n, p._uploaded = int(n.value), False
+            p.keep = [r[4] for r in rec]
+            return False
+
+    def record(self):
+        return self._Rec(self)
+
+    def launch(self):
+        if not self._uploaded:
+            nbytes = self.n * int(lib().mtn_prog_stage_bytes())
+            self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
+            self._uploaded = True
+        check(lib().mtn_prog_launch(self.dev.data_ptr(), self.n, self.counter.data_ptr(), stream_ptr()))
 
 
 def ffn_fused_supported(rows, d, d_ff):

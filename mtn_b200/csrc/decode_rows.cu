@@ -12,6 +12,9 @@
 //                        one warp per (batch element, head); keys across lanes for the scores, dims across lanes for
 //                        P V; online softmax in the log2 domain with the reference's FINITE -1e9 (mtn.py:227).
 #include <math_constants.h>
+#include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "host.h"
@@ -52,15 +55,14 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* ptr) {    // read-only pat
 // KS warps (each issues ALL of its 16-byte loads before the first mma: one memory round trip per warp), partial sums
 // combined through shared memory in a fixed order (deterministic).  K % (32 * KS) == 0.
 constexpr int RL_MAX_KS = 8;
+// The kernels' bodies are device functions of a VIRTUAL block index (bx, by): the stand-alone kernels pass blockIdx, the
+// persistent decoding-step kernel at the end of this file walks the virtual blocks of one launch after the other.
 template <int CPW>   // 32-wide k chunks per warp
-__global__ void __launch_bounds__(32 * RL_MAX_KS) rows_linear_kernel(const RowsLinearParams p) {
-  __shared__ float part[RL_MAX_KS][32][4];
-  pdl_launch_dependents();
-  pdl_wait();
+__device__ __forceinline__ void rows_linear_body(const RowsLinearParams& p, int bx, int by, int KS, float (*part)[32][4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int n0 = blockIdx.x * 8;
-  const int r0 = blockIdx.y * 16 + g, r1 = r0 + 8;  // the two rows of this thread's fragments
+  const int n0 = bx * 8;
+  const int r0 = by * 16 + g, r1 = r0 + 8;  // the two rows of this thread's fragments
   const int kbase = warp * CPW * 32;
   // rows beyond M read row M-1 (valid memory) and are not stored
   const __half* a_lo = p.A + (size_t)min(r0, p.M - 1) * p.lda + 8 * q + kbase;
@@ -89,7 +91,6 @@ __global__ void __launch_bounds__(32 * RL_MAX_KS) rows_linear_kernel(const RowsL
     mma_16816(c4, xa[c].x, xb[c].x, xa[c].y, xb[c].y, w[c].x, w[c].y);
     mma_16816(c4, xa[c].z, xb[c].z, xa[c].w, xb[c].w, w[c].z, w[c].w);
   }
-  const int KS = blockDim.x >> 5;
   if (KS > 1) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) part[warp][lane][i] = c4[i];
@@ -131,6 +132,14 @@ __global__ void __launch_bounds__(32 * RL_MAX_KS) rows_linear_kernel(const RowsL
   }
 }
 
+template <int CPW>
+__global__ void __launch_bounds__(32 * RL_MAX_KS) rows_linear_kernel(const RowsLinearParams p) {
+  __shared__ float part[RL_MAX_KS][32][4];
+  pdl_launch_dependents();
+  pdl_wait();
+  rows_linear_body<CPW>(p, blockIdx.x, blockIdx.y, blockDim.x >> 5, part);
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // The same with the reference's LayerNorm (mtn.py:111-114) in front:  out16[M, N] = act(LN(x)[M, K] W[N, K]^T + bias),
 // x f32.  A CTA (16 rows x 8 output columns, KS warps over the contraction) first requests everything it will need --
@@ -149,19 +158,15 @@ struct RowsLnLinearParams {
 };
 
 template <int VPL>   // K = 128 * VPL
-__global__ void __launch_bounds__(256) rows_ln_linear_kernel(const RowsLnLinearParams p) {
+__device__ __forceinline__ void rows_ln_linear_body(const RowsLnLinearParams& p, int bx, int by, float (*part)[32][4], float2* stats) {
   constexpr int K = 128 * VPL;
   constexpr int KS = (K / 32 >= 8) ? 8 : K / 32;   // warps over the contraction
   constexpr int CPW = K / (32 * KS);              // 32-wide chunks per warp
   constexpr int RPW = 16 / KS;                    // rows whose statistics a warp computes
-  __shared__ float part[KS][32][4];
-  __shared__ float2 stats[16];
-  pdl_launch_dependents();
-  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int n0 = blockIdx.x * 8;
-  const int rb = blockIdx.y * 16;
+  const int n0 = bx * 8;
+  const int rb = by * 16;
   const int r0 = rb + g, r1 = r0 + 8;
   const int kbase = warp * CPW * 32 + 8 * q;
   const float* x_lo = p.x + (size_t)min(r0, p.M - 1) * p.ldx + kbase;
@@ -251,6 +256,16 @@ __global__ void __launch_bounds__(256) rows_ln_linear_kernel(const RowsLnLinearP
   if (r1 < p.M) *reinterpret_cast<uint32_t*>(p.out16 + (size_t)r1 * p.ld16 + col) = pack_f16x2_sat(v[2], v[3]);
 }
 
+template <int VPL>
+__global__ void __launch_bounds__(256) rows_ln_linear_kernel(const RowsLnLinearParams p) {
+  constexpr int KS = (128 * VPL / 32 >= 8) ? 8 : 128 * VPL / 32;
+  __shared__ float part[KS][32][4];
+  __shared__ float2 stats[16];
+  pdl_launch_dependents();
+  pdl_wait();
+  rows_ln_linear_body<VPL>(p, blockIdx.x, blockIdx.y, part, stats);
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 struct DecodeAttnParams {
   const __half *q, *k, *v;
@@ -285,13 +300,19 @@ __device__ __forceinline__ uint32_t ld_cg_b32(const void* ptr) {
 // online softmax (lane = key for the scores, lane = two dims for P V) and a fixed-order merge of the warps' partial
 // (max, sum, O) triples through shared memory.
 template <int R>
-__global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const DecodeAttnParams p) {
-  __shared__ float sq_[R][64];
-  __shared__ float sm_[DA_WARPS][R], sl_[DA_WARPS][R], so_[DA_WARPS][R][64];
-  pdl_launch_dependents();
-  pdl_wait();
+struct DecodeAttnShared {
+  float sq_[R][64];
+  float sm_[DA_WARPS][R], sl_[DA_WARPS][R], so_[DA_WARPS][R][64];
+};
+
+template <int R>
+__device__ __forceinline__ void decode_attn_body(const DecodeAttnParams& p, int bx, DecodeAttnShared<R>& sh) {
+  float (&sq_)[R][64] = sh.sq_;
+  float (&sm_)[DA_WARPS][R] = sh.sm_;
+  float (&sl_)[DA_WARPS][R] = sh.sl_;
+  float (&so_)[DA_WARPS][R][64] = sh.so_;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / p.h, hd = blockIdx.x % p.h;
+  const int b = bx / p.h, hd = bx % p.h;
   constexpr float LOG2E = 1.4426950408889634f;
   const float c1 = p.scale * LOG2E, t_masked = -1e9f * LOG2E;
   const __half* kb = p.k + (size_t)b * p.sk + hd * 64;
@@ -406,7 +427,236 @@ __global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const Decode
   }
 }
 
+template <int R>
+__global__ void __launch_bounds__(32 * DA_WARPS) decode_attn_kernel(const DecodeAttnParams p) {
+  __shared__ DecodeAttnShared<R> sh;
+  pdl_launch_dependents();
+  pdl_wait();
+  decode_attn_body<R>(p, blockIdx.x, sh);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// One decoding step as ONE persistent kernel.  A KV-cached step is ~130 dependent few-row launches (above); inside a CUDA
+// graph each still costs a kernel boundary (~3 us) for ~1 us of work.  While a program is being RECORDED
+// (mtn_prog_begin), the few-row entry points below and mtn_layernorm_fwd append their launch -- kernel kind, grid, the
+// parameter struct they would have launched with -- to a stage list instead of launching; mtn_prog_launch then runs
+// the list in one cooperative kernel: every CTA walks the virtual blocks of stage s (the same device functions as the
+// stand-alone kernels: identical arithmetic, bit-identical results), then all CTAs meet at a grid barrier (one atomic
+// per CTA + acquire polling) before stage s+1.  The next stage's descriptor is fetched under the current stage's work.
+// ----------------------------------------------------------------------------------------------------------------
+enum { PK_LINEAR = 1, PK_LN_LINEAR = 2, PK_ATTN = 3, PK_LN = 4 };
+
+struct LnStageParams {
+  const float* x; const float* a2; const float* b2;
+  float eps; int rows, rpg;
+  float* y32; __half* y16;
+};
+
+constexpr int PROG_PARAM_BYTES = 128;
+struct ProgStage {
+  int kind, tparam, gx, gy;
+  alignas(8) unsigned char params[PROG_PARAM_BYTES];
+};
+static_assert(sizeof(RowsLinearParams) <= PROG_PARAM_BYTES && sizeof(RowsLnLinearParams) <= PROG_PARAM_BYTES &&
+                  sizeof(DecodeAttnParams) <= PROG_PARAM_BYTES && sizeof(LnStageParams) <= PROG_PARAM_BYTES,
+              "stage parameter area");
+constexpr int PROG_STAGE_WORDS = sizeof(ProgStage) / 4;
+static_assert(sizeof(ProgStage) % 4 == 0 && PROG_STAGE_WORDS <= 64, "stage descriptor");
+
+// LayerNorm of 8 rows per virtual block, d = 512: the arithmetic (and summation order) of layernorm_rows_kernel<4>
+__device__ __forceinline__ void ln_rows_body(const LnStageParams& p, int bx) {
+  constexpr int VPL = 4, D = 512;
+  const int row = bx * 8 + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const float* a2 = p.a2 + (size_t)(row / p.rpg) * D;
+  const float* b2 = p.b2 + (size_t)(row / p.rpg) * D;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)row * D);
+  float4 v[VPL];
+  float sm = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = __ldcg(xr + lane + 32 * i);
+    sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  const float mean = sm * (1.f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / (sqrtf(ss * (1.f / (D - 1))) + p.eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(a2) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(b2) + c4);
+    float4 o;
+    o.x = a.x * v[i].x * inv + b.x;
+    o.y = a.y * v[i].y * inv + b.y;
+    o.z = a.z * v[i].z * inv + b.z;
+    o.w = a.w * v[i].w * inv + b.w;
+    if (p.y32) reinterpret_cast<float4*>(p.y32 + (size_t)row * D)[c4] = o;
+    if (p.y16) reinterpret_cast<uint2*>(p.y16 + (size_t)row * D)[c4] = make_uint2(pack_f16x2_sat(o.x, o.y), pack_f16x2_sat(o.z, o.w));
+  }
+}
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* ptr) {
+  uint32_t r;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* ptr) {
+  uint32_t r;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(ptr) : "memory");
+  return r;
+}
+
+// All CTAs of the (co-resident, cooperative) grid have finished the stage: the writes of every CTA are visible to every
+// CTA afterwards.  `target` = arrivals expected so far (monotonic counter, zeroed before the launch).  Bounded: a
+// protocol error traps instead of hanging the GPU.
+__device__ __forceinline__ void prog_grid_sync(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+      if (++spins > (1u << 27)) {
+        printf("mtn_b200: decode program grid barrier timeout, block %d target %u\n", blockIdx.x, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 2) decode_prog_kernel(const ProgStage* prog, int n_stages, unsigned* counter) {
+  __shared__ ProgStage sst[2];
+  __shared__ float part[RL_MAX_KS][32][4];
+  __shared__ float2 stats[16];
+  __shared__ DecodeAttnShared<1> ash;
+  if (threadIdx.x < PROG_STAGE_WORDS)
+    reinterpret_cast<uint32_t*>(&sst[0])[threadIdx.x] = ld_cg_u32(reinterpret_cast<const uint32_t*>(prog) + threadIdx.x);
+  __syncthreads();
+  for (int s = 0; s < n_stages; ++s) {
+    uint32_t nextw = 0u;   // the next stage's descriptor, in flight under this stage's work
+    if (s + 1 < n_stages && threadIdx.x < PROG_STAGE_WORDS)
+      nextw = ld_cg_u32(reinterpret_cast<const uint32_t*>(prog + s + 1) + threadIdx.x);
+    const ProgStage& st = sst[s & 1];
+    const int kind = st.kind, tparam = st.tparam, gx = st.gx, nvb = st.gx * st.gy;
+    for (int vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
+      const int bx = vb % gx, by = vb / gx;
+      if (kind == PK_LINEAR) {
+        const RowsLinearParams p = *reinterpret_cast<const RowsLinearParams*>(st.params);
+        if (tparam == 2) rows_linear_body<2>(p, bx, by, RL_MAX_KS, part);
+        else rows_linear_body<8>(p, bx, by, RL_MAX_KS, part);
+      } else if (kind == PK_LN_LINEAR) {
+        const RowsLnLinearParams p = *reinterpret_cast<const RowsLnLinearParams*>(st.params);
+        rows_ln_linear_body<4>(p, bx, by, part, stats);
+      } else if (kind == PK_ATTN) {
+        const DecodeAttnParams p = *reinterpret_cast<const DecodeAttnParams*>(st.params);
+        decode_attn_body<1>(p, bx, ash);
+      } else {
+        const LnStageParams p = *reinterpret_cast<const LnStageParams*>(st.params);
+        ln_rows_body(p, bx);
+      }
+      __syncthreads();   // the shared scratch is reused by the next virtual block
+    }
+    if (s + 1 < n_stages) {
+      if (threadIdx.x < PROG_STAGE_WORDS) reinterpret_cast<uint32_t*>(&sst[(s + 1) & 1])[threadIdx.x] = nextw;
+      prog_grid_sync(counter, (unsigned)(s + 1) * gridDim.x);
+    }
+  }
+}
+
+// ---- recorder (host side; one recording at a time per thread)
+static thread_local std::vector<ProgStage>* g_prog = nullptr;
+
+bool prog_recording() { return g_prog != nullptr; }
+
+static int prog_push(int kind, int tparam, dim3 grid, const void* params, size_t bytes) {
+  ProgStage st;
+  memset(&st, 0, sizeof(st));
+  st.kind = kind; st.tparam = tparam; st.gx = (int)grid.x; st.gy = (int)grid.y;
+  memcpy(st.params, params, bytes);
+  g_prog->push_back(st);
+  return MTN_OK;
+}
+
+int prog_push_layernorm(const float* x, const float* a2, const float* b2, float eps, int rows, int d, int rows_per_group,
+                        float* y32, void* y16) {
+  MTN_REQUIRE(d == 512 && aligned16(x) && aligned16(a2) && aligned16(b2) && (!y32 || aligned16(y32)) && (!y16 || aligned16(y16)),
+              MTN_E_SHAPE, "decode program: LayerNorm stage needs d = 512 and 16-byte aligned pointers (d = %d)", d);
+  LnStageParams p{x, a2, b2, eps, rows, rows_per_group, y32, reinterpret_cast<__half*>(y16)};
+  return prog_push(PK_LN, 4, dim3((rows + 7) / 8, 1), &p, sizeof(p));
+}
+
 }  // namespace mtn
+
+extern "C" int mtn_prog_begin(void) {
+  using namespace mtn;
+  MTN_REQUIRE(g_prog == nullptr, MTN_E_ARG, "prog_begin: a program is already being recorded");
+  g_prog = new std::vector<ProgStage>();
+  return MTN_OK;
+}
+extern "C" int mtn_prog_recording(void) { return mtn::g_prog != nullptr ? 1 : 0; }
+extern "C" int mtn_prog_stage_bytes(void) { return (int)sizeof(mtn::ProgStage); }
+// Ends the recording.  host_dst (capacity bytes; pinned memory if it is to be uploaded asynchronously) receives the stage
+// list; returns the number of stages through *n_stages.  host_dst == NULL: the recording is discarded.
+extern "C" int mtn_prog_end(void* host_dst, size_t capacity, int* n_stages) {
+  using namespace mtn;
+  MTN_REQUIRE(g_prog != nullptr, MTN_E_ARG, "prog_end: no program is being recorded");
+  std::vector<ProgStage>* v = g_prog;
+  g_prog = nullptr;
+  const size_t n = v->size(), bytes = n * sizeof(ProgStage);
+  int rc = MTN_OK;
+  if (host_dst != nullptr) {
+    if (bytes > capacity) rc = set_error(MTN_E_WORKSPACE, "prog_end: %zu stages need %zu bytes, buffer has %zu", n, bytes, capacity);
+    else if (n > 0) memcpy(host_dst, v->data(), bytes);
+  }
+  if (n_stages != nullptr) *n_stages = (int)n;
+  delete v;
+  return rc;
+}
+// Runs a recorded program (device copy of the stage list) as one cooperative kernel on `stream`; `counter`: 4 bytes of
+// device memory for the grid barrier (zeroed here, stream-ordered).  Graph-capturable.
+extern "C" int mtn_prog_launch(const void* dev_prog, int n_stages, void* counter, void* stream) {
+  using namespace mtn;
+  MTN_REQUIRE(dev_prog && counter && n_stages > 0, MTN_E_ARG, "prog_launch: NULL pointer / empty program");
+  MTN_REQUIRE(!prog_recording(), MTN_E_ARG, "prog_launch: a program is being recorded");
+  static int grid = 0;
+  if (grid == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    MTN_CHECK_CUDA(cudaGetDevice(&dev));
+    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MTN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_prog_kernel, 256, 0));
+    MTN_REQUIRE(per_sm > 0, MTN_E_CUDA, "prog_launch: the program kernel does not fit an SM");
+    grid = sms * (per_sm > 2 ? 2 : per_sm);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MTN_CHECK_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const ProgStage* pp = static_cast<const ProgStage*>(dev_prog);
+  unsigned* cc = static_cast<unsigned*>(counter);
+  MTN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_prog_kernel, pp, n_stages, cc));
+  return MTN_OK;
+}
 
 extern "C" int mtn_rows_linear_supported(int M, int N, int K) {
   if (!(M > 0 && M <= 128 && N > 0 && N % 8 == 0 && K > 0 && K % 32 == 0)) return 0;
@@ -444,6 +694,11 @@ extern "C" int mtn_rows_linear_fwd(const MtnLinearArgs* a, void* stream) {
   MTN_REQUIRE(ks <= RL_MAX_KS && chunks % ks == 0, MTN_E_SHAPE, "rows_linear: K=%d has no supported split (K / 32 must factor into <= 8 warps x <= 8 chunks)", a->K);
   const int cpw = chunks / ks;
   dim3 grid(a->N / 8, (a->M + 15) / 16), block(32 * ks);
+  if (prog_recording()) {
+    MTN_REQUIRE(ks == RL_MAX_KS && (cpw == 2 || cpw == 8), MTN_E_SHAPE,
+                "decode program: linear stage needs K = 512 or 2048 (K = %d)", a->K);
+    return prog_push(PK_LINEAR, cpw, grid, &p, sizeof(p));
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MTN_RL(C) MTN_CHECK_CUDA(launch_kernel(rows_linear_kernel<C>, grid, block, 0, st, p))
   switch (cpw) {
@@ -479,6 +734,10 @@ extern "C" int mtn_rows_ln_linear_fwd(const float* x, int ldx, const float* a_2,
   RowsLnLinearParams p{x, ldx, a_2, b_2, eps, reinterpret_cast<const __half*>(W), ldw, bias, M, N, act,
                        reinterpret_cast<__half*>(out_f16), ld16, 0u};
   dim3 grid(N / 8, (M + 15) / 16);
+  if (prog_recording()) {
+    MTN_REQUIRE(d == 512, MTN_E_SHAPE, "decode program: LayerNorm + linear stage needs d = 512 (d = %d)", d);
+    return prog_push(PK_LN_LINEAR, 4, grid, &p, sizeof(p));
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ks = d / 32 >= 8 ? 8 : d / 32;
   if (d == 128) MTN_CHECK_CUDA(launch_kernel(rows_ln_linear_kernel<1>, grid, dim3(32 * ks), 0, st, p));
@@ -510,6 +769,10 @@ extern "C" int mtn_decode_attn_fwd(const MtnAttnCoreArgs* a, void* stream) {
                      bs(a->o_batch_stride, a->Lq, a->ldo), a->mask_bits, a->mask_rows_q, mtn_mask_words(a->Lk), a->B, a->h, a->Lq, a->Lk,
                      1.0f / sqrtf(64.f)};
   dim3 grid(a->B * a->h), block(32 * DA_WARPS);
+  if (prog_recording()) {
+    MTN_REQUIRE(a->Lq == 1, MTN_E_SHAPE, "decode program: attention stage needs one query row per batch element (Lq = %d)", a->Lq);
+    return prog_push(PK_ATTN, 1, dim3(grid.x, 1), &p, sizeof(p));
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MTN_DA(RR) MTN_CHECK_CUDA(launch_kernel(decode_attn_kernel<RR>, grid, block, 0, st, p))
   switch (a->Lq) {

@@ -27,11 +27,18 @@ const char* last_error();
     if (!(cond)) return ::mtn::set_error(code, __VA_ARGS__);       \
   } while (0)
 
+// Decoding-step programs (csrc/decode_rows.cu): while one is being recorded the few-row entry points and
+// mtn_layernorm_fwd append stages instead of launching; every other launch is an error (it would run out of order).
+bool prog_recording();
+int prog_push_layernorm(const float* x, const float* a2, const float* b2, float eps, int rows, int d, int rows_per_group,
+                        float* y32, void* y16);
+
 // Launch with the programmatic-stream-serialization attribute (PDL) unless MTN_B200_PDL=0.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                          cudaStream_t st, unsigned cluster_x, Args&&... args) {
+  if (prog_recording()) return cudaErrorNotPermitted;   // this kernel cannot be a stage of a decoding-step program
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

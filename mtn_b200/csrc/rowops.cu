@@ -331,6 +331,8 @@ extern "C" int mtn_layernorm_grouped_fwd(const float* x, const float* a_2, const
   MTN_REQUIRE(x && a_2 && b_2 && (y_f32 || y_f16), MTN_E_ARG, "layernorm: NULL pointer");
   MTN_REQUIRE(rows > 0 && d > 1 && rows_per_group > 0, MTN_E_SHAPE, "layernorm: rows=%d d=%d rows_per_group=%d", rows, d,
               rows_per_group);
+  if (prog_recording())   // a stage of a decoding-step program (csrc/decode_rows.cu) instead of a launch
+    return prog_push_layernorm(x, a_2, b_2, eps, rows, d, rows_per_group, y_f32, y_f16);
   const bool grouped = rows_per_group < rows;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __half* y16 = reinterpret_cast<__half*>(y_f16);

@@ -102,6 +102,11 @@ def _site_fused_ok(d, h, B, Lq, Lk):
     return Lq >= 64 or Lk <= 64
 
 
+# Pre-allocated _lib.StepProgram objects for decode_step calls made during CUDA-graph capture (graph.GraphedGreedyDecoder
+# fills it before capturing: a program's pinned / device buffers cannot be allocated inside a capture)
+PROGRAM_POOL = []
+
+
 def _ffn_fused_ok(rows, d, d_ff):
     """Does this feed-forward sublayer take the ONE-kernel path (csrc/ffn_fused.cu)?  MTN_B200_FFN_FUSED = 1: whenever the
     shape is supported; 0 (default): never -- see DESIGN.md section 4 for the measurement behind the default."""
@@ -515,13 +520,44 @@ class DecoderEngine(object):
             _lib.ROWS_KERNELS = prev_rows
 
     def _decode_step(self, st, x_t, t):
+        B, d = st["B"], st["W"]["d"]
+        t = st["t"] if t is None else int(t)
+        assert 0 <= t < st["max_len"], "decode_step: position %d outside the cache (max_len %d)" % (t, st["max_len"])
+        st["xs"].copy_(x_t.reshape(B, d))
+        prog = self._step_program(st, t)
+        if prog is not None:
+            prog.launch()          # the whole step: ONE persistent kernel (csrc/decode_rows.cu, decode_prog_kernel)
+        else:
+            self._decode_step_body(st, t)
+        st["t"] = t + 1
+        return st["out"]
+
+    def _step_program(self, st, t):
+        """The recorded program of position t of this state (greedy decoding, few-row kernels, d = 512), or None.  The stage
+        list depends on t (cache row, number of cached keys) and on the state's buffers only, so it is recorded once per
+        (state, t).  MTN_B200_DECODE_PROG=0: always the launch sequence."""
+        if (not _lib.ROWS_KERNELS or st["R"] != 1 or st["W"]["d"] != 512 or st["B"] > 128 or
+                os.environ.get("MTN_B200_DECODE_PROG", "1") == "0" or TAP is not None):
+            return None
+        progs = st.setdefault("progs", {})
+        prog = progs.get(t)
+        if prog is None:
+            if PROGRAM_POOL:
+                prog = PROGRAM_POOL.pop()
+            elif torch.cuda.is_current_stream_capturing():
+                return None                     # (buffers cannot be allocated during capture: fill PROGRAM_POOL before)
+            else:
+                prog = _lib.StepProgram()
+            with prog.record():
+                self._decode_step_body(st, t)
+            progs[t] = prog
+        return prog
+
+    def _decode_step_body(self, st, t):
         S, W, B, R = st["S"], st["W"], st["B"], st["R"]
         D = B // R                                           # dialogues; the cross sites see [D, R] query rows
         d, N, M = W["d"], W["N"], W["M"]
-        t = st["t"] if t is None else int(t)
-        assert 0 <= t < st["max_len"], "decode_step: position %d outside the cache (max_len %d)" % (t, st["max_len"])
         xs, xn16, qb, obuf, hid = st["xs"], st["xn16"], st["q"], st["obuf"], st["hid"]
-        xs.copy_(x_t.reshape(B, d))
         order = self._site_order(st["ae_features"])
         for l in range(N):
             Lw = W["layers"][l]
@@ -546,8 +582,6 @@ class DecoderEngine(object):
                                  S["kv_ae"][l][i], 0, d, S["bits_ae"], xn16, qb, obuf)
             self._ffn_block(xs, Lw["ln"][4 + 4 * M], Lw["ffn"], xn16, hid)
         _lib.layernorm(xs, W["norm"][0], W["norm"][1], W["norm"][2], out_f32=st["out"])   # mtn.py:164
-        st["t"] = t + 1
-        return st["out"]
 
     @staticmethod
     def decode_reorder(st, parents):

@@ -6,6 +6,8 @@ bottleneck (ctypes + launch latency >> kernel time).  ``GraphedForward`` capture
 static input buffers and replays it with a single launch per step -- the B200-native
 replacement for a tracing compiler: streams + graphs, no code generation.
 """
+import os
+
 import torch
 
 from .data_utils import Batch
@@ -104,6 +106,14 @@ class GraphedGreedyDecoder(object):
                                self.ys[:, :t], masks[t], ae)
             self.ys[:, t] = model.generator.argmax(out[0][:, -1])
 
+        if cached:
+            # KV-cached steps run as ONE persistent kernel each (engine._step_program); the captured prefill creates a
+            # fresh decoding state, whose step programs are recorded during capture -- their buffers must exist already
+            from . import engine as _engine
+            from . import _lib
+            _lib.lib()
+            if os.environ.get("MTN_B200_DECODE_PROG", "1") != "0":
+                _engine.PROGRAM_POOL.extend(_lib.StepProgram() for _ in range(max_len))
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s), torch.no_grad():
@@ -112,6 +122,8 @@ class GraphedGreedyDecoder(object):
                 step(t)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if cached:                                      # the warm-up state's step programs go back to the pool
+            _engine.PROGRAM_POOL.extend(self.state.pop("progs", {}).values())
         self.graphs = []
         g = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(g):

@@ -353,6 +353,42 @@ def test_kv_cached_decode_equals_full_prefix(M, cfg2_model):
         invalidate_weight_caches()
 
 
+def test_decode_step_program_equals_launch_sequence(M, cfg2_model, monkeypatch):
+    """One KV-cached decoding step as ONE persistent kernel (recorded program, csrc/decode_rows.cu decode_prog_kernel)
+    runs the device functions of the stand-alone few-row kernels stage by stage: its rows are BIT-IDENTICAL to the
+    launch sequence's at every position, at batch 64 (configs[3]) and at a ragged batch, and so are the greedy tokens of
+    the graphed decoder."""
+    mtn, du = M
+    from mtn_b200.graph import GraphedGreedyDecoder
+    cfg, model = cfg2_model
+    for B in (64, 5):
+        T = 20
+        inp = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=T, Lv=[512, 256], seed=17 + B)
+        b = make_batch(du, inp)
+        rows = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("MTN_B200_DECODE_PROG", mode)
+            with torch.no_grad():
+                q, vid, cap, his, ae = model.encode(b.query, b.query_mask, b.his, b.his_mask, b.cap, b.cap_mask, b.fts, b.fts_mask)
+                st = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae, T)
+                rows[mode] = [model.decode_step(st, b.trg[:, t]).clone() for t in range(T)]
+            assert ("progs" in st) == (mode == "1"), "the step program path was %staken" % ("not " if mode == "1" else "")
+        torch.cuda.synchronize()
+        for t in range(T):
+            assert torch.isfinite(rows["1"][t]).all()
+            assert torch.equal(rows["0"][t], rows["1"][t]), (B, t, float((rows["0"][t] - rows["1"][t]).abs().max()))
+    d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
+         if k in ("query", "his", "cap", "fts")}
+    ys = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MTN_B200_DECODE_PROG", mode)
+        dec = GraphedGreedyDecoder(model, d, T, cached=True)
+        ys[mode] = dec.decode().clone()
+        ys[mode + "b"] = dec.decode().clone()          # a second replay of the same graphs
+        torch.cuda.synchronize()
+    assert torch.equal(ys["0"], ys["1"]) and torch.equal(ys["1"], ys["1b"])
+
+
 def test_batched_beam_search_on_the_kernels(M, cfg2_model, monkeypatch):
     """generate.py's path (data_utils.py:188-242): the batched, KV-cached beam search over 3 dialogues returns, per
     dialogue, the hypotheses of the serial search in the reference's call form (one full-prefix ``model.decode`` per
