@@ -523,8 +523,8 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* ptr) {
 __device__ __forceinline__ void prog_grid_sync(unsigned* counter, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release: the CTA's writes (ordered before this thread by the barrier above) become visible before the arrival
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned spins = 0;
     while (ld_acquire_u32(counter) < target) {
       if (++spins > (1u << 27)) {
@@ -532,7 +532,6 @@ __device__ __forceinline__ void prog_grid_sync(unsigned* counter, unsigned targe
         __trap();
       }
     }
-    __threadfence();
   }
   __syncthreads();
 }

@@ -535,9 +535,13 @@ class DecoderEngine(object):
     def _step_program(self, st, t):
         """The recorded program of position t of this state (greedy decoding, few-row kernels, d = 512), or None.  The stage
         list depends on t (cache row, number of cached keys) and on the state's buffers only, so it is recorded once per
-        (state, t).  MTN_B200_DECODE_PROG=0: always the launch sequence."""
+        (state, t).  OPT-IN (MTN_B200_DECODE_PROG=1): measured SLOWER than the launch sequence (907 vs 650 us per step at batch
+        64): a stage costs >= 2.3 us (three dependent L2 round trips: operands, release-arrive, acquire-poll), no less than
+        a kernel boundary under programmatic dependent launch, and the persistent grid holds 2 CTAs per SM (registers of
+        the widest stage) where the stand-alone kernels run 8 -- the stages with 512-1024 virtual blocks take several
+        rounds."""
         if (not _lib.ROWS_KERNELS or st["R"] != 1 or st["W"]["d"] != 512 or st["B"] > 128 or
-                os.environ.get("MTN_B200_DECODE_PROG", "1") == "0" or TAP is not None):
+                os.environ.get("MTN_B200_DECODE_PROG", "0") != "1" or TAP is not None):
             return None
         progs = st.setdefault("progs", {})
         prog = progs.get(t)

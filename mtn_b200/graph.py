@@ -112,7 +112,7 @@ class GraphedGreedyDecoder(object):
             from . import engine as _engine
             from . import _lib
             _lib.lib()
-            if os.environ.get("MTN_B200_DECODE_PROG", "1") != "0":
+            if os.environ.get("MTN_B200_DECODE_PROG", "0") == "1":
                 _engine.PROGRAM_POOL.extend(_lib.StepProgram() for _ in range(max_len))
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
