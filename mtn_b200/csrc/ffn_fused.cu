@@ -9,11 +9,12 @@
 // so a CTA cannot hold the output tile and a hidden-chunk accumulator at once.  Here a CTA owns 128 rows and HALF of the
 // output columns (256 TMEM columns) and walks the hidden dimension in chunks of 128: chunk c of the hidden activation
 // H_c[128, 128] = relu(xn W1_c^T + b1_c) is accumulated in one of two 128-column TMEM buffers, drained by the epilogue
-// warps (bias, ReLU, f16) into a K-major 128B-swizzled shared-memory tile, and immediately consumed as the A operand of
-// Y[128, 256] += H_c W2[cols, c]^T.  The two CTAs of a row block (one per column half) each compute the full hidden
+// warps (bias, ReLU, f16) and written BACK over the first 64 columns of the same buffer as packed f16 (like the attention
+// probabilities of csrc/attn.cu), and immediately consumed from tensor memory as the A operand (TS-form tcgen05.mma) of
+// Y[128, 256] += H_c W2[cols, c]^T -- the hidden activation touches neither HBM nor shared memory.  The two CTAs of a row block (one per column half) each compute the full hidden
 // activation: 1.5x the FLOPs of the two-GEMM form, in exchange for no cluster, no exchange and no HBM round trip of the
 // hidden activation (2 x rows x d_ff x 2 bytes).  xn stays resident in shared memory (128 KB); W1 / W2 stream through a
-// ring of [128 x 64] f16 tiles (16 KB each); every MMA is 128 x 128 x 16.
+// ring of six [128 x 64] f16 tiles (16 KB each: everything that is left); every MMA is 128 x 128 x 16.
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..9 epilogue (two per TMEM lane
 // quarter).  Tensor-pipe program order: G1(0), G1(1), G2(0), G1(2), G2(1), ... so the hidden chunk c+1 is being
@@ -30,19 +31,18 @@ constexpr int FF_ROWS = 128;    // rows per CTA (UMMA M)
 constexpr int FF_D = 512;       // model width (contraction of the first GEMM)
 constexpr int FF_NCOL = 256;    // output columns per CTA
 constexpr int FF_HC = 128;      // hidden units per chunk
-constexpr int FF_STAGES = 4;
+constexpr int FF_STAGES = 6;
 
 struct FfCfg {
   static constexpr int TILE = 128 * 128;                  // one [128 x 64] f16 tile: 16 KB
   static constexpr int OFF_XN = 0;                        // 8 k-panels of xn: 128 KB
-  static constexpr int OFF_HS = OFF_XN + (FF_D / 64) * TILE;   // 2 k-panels of the hidden chunk: 32 KB
-  static constexpr int OFF_RING = OFF_HS + (FF_HC / 64) * TILE;
+  static constexpr int OFF_RING = OFF_XN + (FF_D / 64) * TILE;
   static constexpr int OFF_BAR = OFF_RING + FF_STAGES * TILE;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-enum { FB_FULL = 0 /* +3 */, FB_EMPTY = 4 /* +3 */, FB_XN = 8, FB_D1_FULL = 9 /* +1 */, FB_HS_FULL = 11, FB_HS_FREE = 12, FB_Y_FULL = 13, FB_COUNT = 14 };
+enum { FB_FULL = 0 /* +5 */, FB_EMPTY = 6 /* +5 */, FB_XN = 12, FB_D1_FULL = 13 /* +1 */, FB_HS_FULL = 15 /* +1 */, FB_G2_DONE = 17 /* +1 */, FB_Y_FULL = 19, FB_COUNT = 20 };
 
 struct FfParams {
   int rows, d_ff;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t sXN = base + C::OFF_XN, sHS = base + C::OFF_HS, sRING = base + C::OFF_RING;
+  const uint32_t sXN = base + C::OFF_XN, sRING = base + C::OFF_RING;
   const uint32_t bars = base + C::OFF_BAR;
   auto bar = [&](int i) { return bars + 8u * i; };
   const uint32_t tmem_slot = bars + 8u * FB_COUNT;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmOut);
-    for (int i = 0; i < FB_COUNT; ++i) mbar_init(bar(i), i == FB_HS_FULL ? 256u : 1u);
+    for (int i = 0; i < FB_COUNT; ++i) mbar_init(bar(i), (i == FB_HS_FULL || i == FB_HS_FULL + 1) ? 256u : 1u);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -122,6 +122,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
     mbar_wait(bar(FB_XN), 0);
     auto g1 = [&](int c) {              // D1[c & 1] = xn W1_c^T
       const uint32_t d = tD1 + (uint32_t)(c & 1) * FF_HC;
+      // the buffer still holds the hidden chunk c-2 as the A operand of its second GEMM: that GEMM must have COMPLETED (the
+      // tensor pipe does not order an accumulator write behind an earlier MMA's read of a TMEM operand, csrc/attn.cu)
+      if (c >= 2) mbar_wait(bar(FB_G2_DONE + (c & 1)), ((c - 2) >> 1) & 1);
       for (int kp = 0; kp < FF_D / 64; ++kp, ++it) {
         const uint32_t s = it % FF_STAGES;
         mbar_wait(bar(FB_FULL + s), (it / FF_STAGES) & 1);
@@ -137,31 +140,32 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
         __syncwarp();
       }
     };
-    auto g2 = [&](int c) {              // Y += H_c W2[cols, c]^T
-      mbar_wait(bar(FB_HS_FULL), c & 1);   // the hidden chunk is in shared memory (and D1[c & 1] has been read)
+    auto g2 = [&](int c) {              // Y += H_c W2[cols, c]^T, H_c from tensor memory
+      mbar_wait(bar(FB_HS_FULL + (c & 1)), (c >> 1) & 1);   // the packed hidden chunk is in D1[c & 1]
+      const uint32_t th = tD1 + (uint32_t)(c & 1) * FF_HC;
       for (int kp = 0; kp < FF_HC / 64; ++kp)
         for (int nh = 0; nh < FF_NCOL / 128; ++nh, ++it) {
           const uint32_t s = it % FF_STAGES;
           mbar_wait(bar(FB_FULL + s), (it / FF_STAGES) & 1);
           tc_fence_after();
           if (lane == 0) {
-            const uint64_t da = make_smem_desc(sHS + kp * C::TILE, 16, 1024, SWZ_128B);
             const uint64_t db = make_smem_desc(sRING + s * C::TILE, 16, 1024, SWZ_128B);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_f16(tY + nh * 128, da + 2 * k, db + 2 * k, idesc, (c | kp | k) != 0);
+            for (int k = 0; k < 4; ++k)   // 16 hidden units = 8 packed columns per k-step
+              tc_mma_f16_ts(tY + nh * 128, th + (uint32_t)(kp * 4 + k) * 8, db + 2 * k, idesc, (c | kp | k) != 0);
             tc_commit(bar(FB_EMPTY + s));
           }
           __syncwarp();
         }
       if (lane == 0) {
-        tc_commit(bar(FB_HS_FREE));       // the hidden tile may be overwritten
+        tc_commit(bar(FB_G2_DONE + (c & 1)));   // D1[c & 1] may be overwritten by the first GEMM of chunk c+2
         if (c == nch - 1) tc_commit(bar(FB_Y_FULL));
       }
       __syncwarp();
     };
     g1(0);
     for (int c = 0; c < nch; ++c) {
-      if (c + 1 < nch) g1(c + 1);   // (D1[(c+1) & 1] was drained before HS_FULL of chunk c-1, waited for by g2(c-1))
+      if (c + 1 < nch) g1(c + 1);
       g2(c);
     }
   } else {
@@ -171,7 +175,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
     const int half = ew >> 2;     // hidden 64-block of the chunk (drain) / output 128-column half (final epilogue)
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t sw = (uint32_t)(row & 7);
     // b1 of this warp's 64 hidden units of the next chunk: lane l holds units l and 32 + l, broadcast by shuffles
     float bA = __ldg(p.b1 + half * 64 + lane), bB = __ldg(p.b1 + half * 64 + 32 + lane);
     for (int c = 0; c < nch; ++c) {
@@ -198,16 +201,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
         const float b0 = __shfl_sync(0xffffffffu, cB, 2 * i), b1v = __shfl_sync(0xffffffffu, cB, 2 * i + 1);
         pk[16 + i] = pack_f16x2_sat(fmaxf(__uint_as_float(r1[2 * i]) + b0, 0.f), fmaxf(__uint_as_float(r1[2 * i + 1]) + b1v, 0.f));
       }
-      if (c > 0) mbar_wait(bar(FB_HS_FREE), (c - 1) & 1);   // Y += H_{c-1} ... has retired: the hidden tile is free
-      const uint32_t dst = sHS + half * C::TILE + row * 128;   // k-panel `half`, this row: 8 x 16 B, 128B swizzle
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ sw) << 4)), "r"(pk[4 * j]),
-                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                     : "memory");
-      fence_proxy_async_smem();
+      // Both warps of this lane quarter have read their f32 columns before either overwrites them: the packed hidden
+      // units of warp `half` go to columns [32 half, 32 half + 32) of the buffer, inside the f32 columns of warp 0.
+      named_bar_sync(1 + q, 64);
+      tc_st32(tD1 + (uint32_t)(c & 1) * FF_HC + lane_off + half * 32, pk);
+      tc_wait_st();
       tc_fence_before();
-      mbar_arrive(bar(FB_HS_FULL));
+      mbar_arrive(bar(FB_HS_FULL + (c & 1)));
     }
     // ---- final epilogue: x[rows, col0 + 128 half ..] += Y + b2, as TMA reduce-add stores from the (dead) xn region
     float b2v[4];
