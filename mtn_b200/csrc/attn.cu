@@ -687,13 +687,7 @@ static int launch_attn_v(const MtnAttnCoreArgs& a, cudaStream_t st) {
                DropCfg{reinterpret_cast<const unsigned long long*>(a.drop_seed), a.drop_site, a.drop_thresh,
                        a.drop_seed ? 1.f / (1.f - a.drop_thresh / 65536.f) : 1.f},
                (a.Lk + 31) / 32 * 32};
-  static int slots = 0;  // resident CTAs: 2 per SM
-  if (slots == 0) {
-    int dev = 0, n = 0;
-    MTN_CHECK_CUDA(cudaGetDevice(&dev));
-    MTN_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    slots = 2 * n;
-  }
+  const int slots = 2 * stream_sm_count(st);  // resident CTAs: 2 per SM of the stream's SM partition
   dim3 grid(n_items < slots ? n_items : slots);
   MTN_CHECK_CUDA(launch_kernel(attn_core_tc_kernel<DK, ATT_KT, DROP, PT>, grid, dim3(ATT_THREADS), C::TOTAL, st, tq, tk, tv, to, p));
   return MTN_OK;

@@ -547,7 +547,8 @@ static int make_operand_map(CUtensorMap* tm, const void* p, int mn_major, int MN
 template <int BN, int STAGES, int CL, int A_MN, int B_MN, int DROP = 0, int BIAS = 0>
 static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
-  static int max_clusters = 0;  // co-resident clusters (1 CTA per SM)
+  static int max_clusters_dev = 0;  // co-resident clusters on the whole device (1 CTA per SM)
+  int& max_clusters = max_clusters_dev;
   if (max_clusters == 0) {
     MTN_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP, BIAS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -568,6 +569,12 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
       max_clusters = n;
     }
   }
+  // a stream of an SM partition (green context, mtn_b200/parallel.py): the grid follows the partition's SM count
+  const int part_sms = stream_sm_count(st);
+  int max_clusters_here = max_clusters_dev;
+  if (part_sms < g_num_sms) max_clusters_here = (part_sms / CL) < max_clusters_dev ? (part_sms / CL) : max_clusters_dev;
+  if (max_clusters_here < 1) max_clusters_here = 1;
+#define max_clusters max_clusters_here
   const int batch = a.batch > 1 ? a.batch : 1;
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, a.A, A_MN, a.M, a.K, a.lda, batch, a.stride_A, BM);
@@ -620,6 +627,7 @@ static int launch_gemm(const MtnGemmArgs& a, cudaStream_t st) {
   MTN_CHECK_CUDA(launch_kernel_cluster(gemm_f16_tc_kernel<BN, STAGES, CL, A_MN, B_MN, DROP, BIAS>, dim3(clusters * CL),
                                        dim3(GEMM_THREADS), L::TOTAL, st, (unsigned)CL, tmA, tmB, tmC, epi, a.M, a.N, a.K,
                                        tiles_n, tiles_per_batch, num_super, tiles_mn, kb_per_split));
+#undef max_clusters
   return MTN_OK;
 }
 

@@ -3,6 +3,8 @@
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
+#include <vector>
 
 namespace mtn {
 
@@ -60,6 +62,41 @@ static int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuin
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MTN_REQUIRE(r == CUDA_SUCCESS, MTN_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return MTN_OK;
+}
+
+typedef CUresult (*StreamGetGreenCtxFn)(CUstream, CUgreenCtx*);
+typedef CUresult (*GreenCtxGetDevResourceFn)(CUgreenCtx, CUdevResource*, CUdevResourceType);
+
+int stream_sm_count(cudaStream_t st) {
+  static int dev_sms = 0;
+  static StreamGetGreenCtxFn get_ctx = nullptr;
+  static GreenCtxGetDevResourceFn get_res = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev);
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamGetGreenCtx", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      get_ctx = reinterpret_cast<StreamGetGreenCtxFn>(p);
+    if (cudaGetDriverEntryPoint("cuGreenCtxGetDevResource", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      get_res = reinterpret_cast<GreenCtxGetDevResourceFn>(p);
+  });
+  if (st == nullptr || get_ctx == nullptr || get_res == nullptr) return dev_sms;
+  static std::mutex mu;
+  static std::vector<std::pair<cudaStream_t, int>> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& e : cache)
+    if (e.first == st) return e.second;
+  int n = dev_sms;
+  CUgreenCtx g = nullptr;
+  if (get_ctx(reinterpret_cast<CUstream>(st), &g) == CUDA_SUCCESS && g != nullptr) {
+    CUdevResource res;
+    if (get_res(g, &res, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS && res.sm.smCount > 0) n = (int)res.sm.smCount;
+  }
+  if (cache.size() < 64) cache.emplace_back(st, n);
+  return n;
 }
 
 int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,

@@ -68,6 +68,11 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return launch_kernel_cluster(kernel, grid, block, smem, st, 1u, static_cast<Args&&>(args)...);
 }
 
+// SMs a kernel launched on `st` can use: the SM count of the stream's green context (CUDA SM partitioning: the engine
+// may run its side chains on a small partition, mtn_b200/parallel.py) or of the device.  Persistent kernels size their
+// grids with it.  Cached per stream handle.
+int stream_sm_count(cudaStream_t st);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 enum TmSwizzle { TM_SWZ_64 = 64, TM_SWZ_128 = 128 };

@@ -102,6 +102,10 @@ def _site_fused_ok(d, h, B, Lq, Lk):
     return Lq >= 64 or Lk <= 64
 
 
+# parallel.SmPartition or None: see DecoderEngine._streams
+SM_PARTITION = None
+
+
 # Pre-allocated _lib.StepProgram objects for decode_step calls made during CUDA-graph capture (graph.GraphedGreedyDecoder
 # fills it before capturing: a program's pinned / device buffers cannot be allocated inside a capture)
 PROGRAM_POOL = []
@@ -284,6 +288,11 @@ class DecoderEngine(object):
 
     # ------------------------------------------------------------------ memory stage
     def _streams(self, M, dev):
+        if SM_PARTITION is not None:
+            # SM partitioning (parallel.SmPartition): the side chain (side[0]: the batched Query-Aware Auto-Encoder branch)
+            # runs on the small SM group, concurrently with the target path on the big group (the caller runs the forward
+            # on SM_PARTITION.main); the other side streams (hoisted video K/V: wide GEMMs) stay on the big group
+            return [SM_PARTITION.side] + [SM_PARTITION.extra(i) for i in range(M - 1)]
         if getattr(self, "_side", None) is None or len(self._side) != M or self._side_dev != dev:
             self._side = [torch.cuda.Stream(device=dev) for _ in range(M)]
             self._side_dev = dev

@@ -19,20 +19,28 @@ class GraphedForward(object):
     into ``self.static`` directly) + ``replay()`` run one forward; results are in ``self.out`` /
     ``self.ae`` (static output buffers, overwritten by the next replay)."""
 
-    def __init__(self, model, inputs, pad=1, warmup=2):
+    def __init__(self, model, inputs, pad=1, warmup=2, partition=None):
+        """partition: a parallel.SmPartition -- the forward is captured on the big SM group's stream and the engine's side
+        chain on the small group's (engine.SM_PARTITION), so the two run concurrently on disjoint SMs."""
+        from . import engine as _engine
         self.model, self.pad = model, pad
         self.static = {k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v])
                        for k, v in inputs.items()}
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s), torch.no_grad():
-            for _ in range(warmup):                 # first-launch work (func attributes, weight packing)
-                self._run()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.out, self.ae, self.ntokens = self._run()
+        prev, _engine.SM_PARTITION = _engine.SM_PARTITION, partition
+        try:
+            s = torch.cuda.Stream() if partition is None else partition.main
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(warmup):                 # first-launch work (func attributes, weight packing)
+                    self._run()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            kw = {} if partition is None else {"stream": partition.main}
+            with torch.no_grad(), torch.cuda.graph(self.graph, **kw):
+                self.out, self.ae, self.ntokens = self._run()
+        finally:
+            _engine.SM_PARTITION = prev
 
     def _run(self):
         st = self.static
