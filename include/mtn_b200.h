@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MTN_B200_ABI_VERSION 6   /* v6: mtn_ffn_fused_fwd; v5: batch strides in MtnAttnCoreArgs (KV-cached decoding); v4: `multimem` members in the backward structs */
+#define MTN_B200_ABI_VERSION 7   /* v7: mtn_decode_cluster_fwd; v6: mtn_ffn_fused_fwd; v5: batch strides in MtnAttnCoreArgs (KV-cached decoding); v4: `multimem` members in the backward structs */
 
 enum {
   MTN_OK = 0,
@@ -244,6 +244,48 @@ int mtn_prog_recording(void);
 int mtn_prog_stage_bytes(void);
 int mtn_prog_end(void *host_dst, size_t capacity, int *n_stages);
 int mtn_prog_launch(const void *dev_prog, int n_stages, void *counter, void *stream);
+
+/* ---- one KV-cached decoding step, ONE kernel, one thread-block cluster per dialogue group (ABI v7;
+ * csrc/decode_cluster.cu) ---------------------------------------------------------------------------------------
+ * The whole target path of one new position per dialogue -- reference call form data_utils.py:202-210 restricted to
+ * the last position, i.e. for every DecoderLayer (mtn.py:181-218) its self-attention over the layer's cache, its
+ * cross-attention sublayers over static (already projected) memories and its feed-forward sublayer, each a pre-norm
+ * residual sublayer (mtn.py:125-127), then Decoder.norm (mtn.py:164) -- described as a flat list of sublayers
+ * ("sites") in execution order.  A cluster of 8 CTAs owns ceil(B / #clusters) dialogues for the whole step; CTA r owns
+ * head r.  d = 512, h = 8 (d_k = 64), d_ff = 2048, B <= 128, n_sites <= mtn_decode_cluster_max_sites().
+ *   kind 0  self-attention:  w_in = [Wq;Wk;Wv] f16 [3d, d], b_in [3d];  q_cache / k / v = column 0 / d / 2d of row 0,
+ *           dialogue 0 of the layer's cache (f16 [B, T_max, 3d]: ld_kv = 3d, kv_batch_stride = T_max * 3d).  The new
+ *           position's [Q|K|V] is written to cache row t; keys / values are cache rows 0..t (no mask: causal past).
+ *   kind 1  cross-attention: w_in = Wq f16 [d, d], b_in [d];  k / v = head 0 of key 0 of dialogue 0 (f16, row pitch
+ *           ld_kv, dialogue pitch kv_batch_stride, Lk keys);  mask_bits: bit-packed key mask (mtn_mask_pack) with ONE
+ *           query row per dialogue, [B, mask_words] words, or NULL.  Masked scores take the reference's finite -1e9.
+ *   kind 2  feed-forward:    w_in = w_1 f16 [d_ff, d], b_in [d_ff];  w_out = w_2 f16 [d, d_ff], b_out [d].
+ * Attention sites: w_out = Wo f16 [d, d], b_out [d].  All weights contiguous (row pitch = their K).
+ * `sites` is a HOST array (copied into the kernel's parameter space: graph-capturable, nothing to upload);
+ * x_in: [B, d] f32 embedding (+ positional encoding) of the new position; out: [B, d] f32; taps: optional
+ * [n_sites, B, d] f32 debug output (the residual rows after every sublayer) or NULL.                              */
+typedef struct MtnDecodeSite {
+  int kind; float ln_eps;
+  const float *ln_a; const float *ln_b;
+  const void *w_in;  const float *b_in;
+  const void *w_out; const float *b_out;
+  const void *k; const void *v; void *q_cache;
+  int ld_kv, Lk;
+  long long kv_batch_stride;
+  const uint32_t *mask_bits; int mask_words;
+} MtnDecodeSite;
+typedef struct MtnDecodeClusterArgs {
+  const MtnDecodeSite *sites; int n_sites;
+  int B, d, h, d_ff;
+  int t;
+  const float *x_in; float *out;
+  const float *norm_a; const float *norm_b; float norm_eps;
+  float *taps;
+  long long *stamps;   /* optional debug output [n_sites, 8]: clock64 at the phase boundaries of every sublayer (CTA 0) or NULL */
+} MtnDecodeClusterArgs;
+int mtn_decode_cluster_supported(int B, int d, int h, int d_ff);
+int mtn_decode_cluster_max_sites(void);
+int mtn_decode_cluster_fwd(const MtnDecodeClusterArgs *args, void *stream);
 
 /* ---- one attention site --------------------------------------------------------
  * Replaces  SublayerConnection.forward(x, lambda x: attn(x, mem, mem, mask))

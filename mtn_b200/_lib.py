@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -135,6 +135,22 @@ class FfnArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class DecodeSite(C.Structure):
+    _fields_ = [("kind", C.c_int), ("ln_eps", C.c_float), ("ln_a", C.c_void_p), ("ln_b", C.c_void_p),
+                ("w_in", C.c_void_p), ("b_in", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+                ("k", C.c_void_p), ("v", C.c_void_p), ("q_cache", C.c_void_p),
+                ("ld_kv", C.c_int), ("Lk", C.c_int), ("kv_batch_stride", C.c_longlong),
+                ("mask_bits", C.c_void_p), ("mask_words", C.c_int)]
+
+
+class DecodeClusterArgs(C.Structure):
+    _fields_ = [("sites", C.POINTER(DecodeSite)), ("n_sites", C.c_int),
+                ("B", C.c_int), ("d", C.c_int), ("h", C.c_int), ("d_ff", C.c_int), ("t", C.c_int),
+                ("x_in", C.c_void_p), ("out", C.c_void_p),
+                ("norm_a", C.c_void_p), ("norm_b", C.c_void_p), ("norm_eps", C.c_float),
+                ("taps", C.c_void_p), ("stamps", C.c_void_p)]
+
+
 # every symbol include/mtn_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mtn_abi_version": (C.c_int, []),
@@ -178,6 +194,9 @@ SYMBOLS = {
     "mtn_prog_stage_bytes": (C.c_int, []),
     "mtn_prog_end": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "mtn_prog_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mtn_decode_cluster_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mtn_decode_cluster_max_sites": (C.c_int, []),
+    "mtn_decode_cluster_fwd": (C.c_int, [C.POINTER(DecodeClusterArgs), C.c_void_p]),
     "mtn_ffn_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "mtn_ffn_fused_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -562,6 +581,95 @@ class StepProgram(object):
             self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
             self._uploaded = True
         check(lib().mtn_prog_launch(self.dev.data_ptr(), self.n, self.counter.data_ptr(), stream_ptr()))
+
+
+def decode_cluster_supported(B, d, h, d_ff, n_sites):
+    L = lib()
+    return bool(L.mtn_decode_cluster_supported(int(B), int(d), int(h), int(d_ff))) and n_sites <= L.mtn_decode_cluster_max_sites()
+
+
+class DecodeClusterPlan(object):
+    """The sublayer list of one decoding state for ``mtn_decode_cluster_fwd`` (csrc/decode_cluster.cu: one KV-cached step
+    = ONE kernel, one thread-block cluster per dialogue group).  Built once per state by engine.DecoderEngine; holds the
+    host-side ``MtnDecodeSite`` array (passed by value into the kernel's parameter space at every launch, so nothing is
+    uploaded and the launch is graph-capturable) and keeps every referenced tensor alive."""
+
+    def __init__(self, B, d, h, d_ff):
+        self.B, self.d, self.h, self.d_ff = int(B), int(d), int(h), int(d_ff)
+        self.sites, self.keep = [], []
+
+    def _site(self, kind, ln, w_in, b_in, w_out, b_out):
+        for t, n in ((w_in, "w_in"), (w_out, "w_out")):
+            _req(t, torch.float16, n)
+            assert t.is_contiguous(), n
+        for t, n in ((ln[0], "a_2"), (ln[1], "b_2"), (b_in, "b_in"), (b_out, "b_out")):
+            _req(t, torch.float32, n)
+            assert t.is_contiguous(), n
+        s = DecodeSite()
+        s.kind, s.ln_eps, s.ln_a, s.ln_b = kind, float(ln[2]), ln[0].data_ptr(), ln[1].data_ptr()
+        s.w_in, s.b_in, s.w_out, s.b_out = w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(), b_out.data_ptr()
+        self.keep += [ln[0], ln[1], w_in, b_in, w_out, b_out]
+        self.sites.append(s)
+        return s
+
+    def self_attention(self, ln, w_qkv, b_qkv, w_o, b_o, cache):
+        """cache: f16 [B, T_max, 3d] holding [Q|K|V] of every position decoded so far."""
+        d = self.d
+        _req(cache, torch.float16, "cache")
+        assert cache.dim() == 3 and cache.shape[0] == self.B and cache.shape[2] == 3 * d and cache.is_contiguous()
+        assert tuple(w_qkv.shape) == (3 * d, d) and tuple(w_o.shape) == (d, d) and b_qkv.numel() == 3 * d and b_o.numel() == d
+        s = self._site(0, ln, w_qkv, b_qkv, w_o, b_o)
+        s.q_cache, s.k, s.v = cache.data_ptr(), cache.data_ptr() + 2 * d, cache.data_ptr() + 4 * d
+        s.ld_kv, s.Lk, s.kv_batch_stride = 3 * d, 0, cache.stride(0)
+        self.keep.append(cache)
+
+    def cross_attention(self, ln, w_q, b_q, w_o, b_o, kv, k_col, v_col, Lk, mask_bits=None):
+        """kv: f16 [B*Lk, ld] with K at columns [k_col, k_col + d), V at [v_col, v_col + d) (the memory stage's hoisted
+        projections); mask_bits: mask_pack output [B, 1, words] or None."""
+        d = self.d
+        _req(kv, torch.float16, "kv")
+        assert kv.dim() == 2 and kv.shape[0] == self.B * Lk and kv.stride(1) == 1
+        assert tuple(w_q.shape) == (d, d) and tuple(w_o.shape) == (d, d) and b_q.numel() == d and b_o.numel() == d
+        s = self._site(1, ln, w_q, b_q, w_o, b_o)
+        s.k, s.v = kv.data_ptr() + 2 * int(k_col), kv.data_ptr() + 2 * int(v_col)
+        s.ld_kv, s.Lk, s.kv_batch_stride = kv.stride(0), int(Lk), int(Lk) * kv.stride(0)
+        if mask_bits is not None:
+            assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == self.B
+            assert mask_bits.shape[1] == 1 and mask_bits.shape[2] == mask_words(Lk)
+            s.mask_bits, s.mask_words = mask_bits.data_ptr(), mask_bits.shape[2]
+            self.keep.append(mask_bits)
+        self.keep.append(kv)
+
+    def feed_forward(self, ln, w_1, b_1, w_2, b_2):
+        d, dff = self.d, self.d_ff
+        assert tuple(w_1.shape) == (dff, d) and tuple(w_2.shape) == (d, dff) and b_1.numel() == dff and b_2.numel() == d
+        self._site(2, ln, w_1, b_1, w_2, b_2)
+
+    def finish(self, norm):
+        self.arr = (DecodeSite * len(self.sites))(*self.sites)
+        self.norm = norm
+        self.keep += [norm[0], norm[1]]
+        return self
+
+    def step(self, t, x_in, out, taps=None, stamps=None):
+        """One position: x_in [B, d] f32 -> out [B, d] f32 (Decoder.norm applied); cache rows t are written."""
+        _req(x_in, torch.float32, "x_in"); _req(out, torch.float32, "out")
+        assert tuple(x_in.shape) == (self.B, self.d) and tuple(out.shape) == (self.B, self.d)
+        assert x_in.is_contiguous() and out.is_contiguous()
+        a = DecodeClusterArgs()
+        a.sites, a.n_sites = self.arr, len(self.sites)
+        a.B, a.d, a.h, a.d_ff, a.t = self.B, self.d, self.h, self.d_ff, int(t)
+        a.x_in, a.out = x_in.data_ptr(), out.data_ptr()
+        a.norm_a, a.norm_b, a.norm_eps = self.norm[0].data_ptr(), self.norm[1].data_ptr(), float(self.norm[2])
+        if taps is not None:
+            _req(taps, torch.float32, "taps")
+            assert taps.is_contiguous() and taps.numel() == len(self.sites) * self.B * self.d
+            a.taps = taps.data_ptr()
+        if stamps is not None:
+            assert stamps.dtype == torch.int64 and stamps.is_cuda and stamps.numel() >= 8 * len(self.sites)
+            a.stamps = stamps.data_ptr()
+        _launch("decode_cluster", 0, 0, lambda: lib().mtn_decode_cluster_fwd(C.byref(a), stream_ptr()),
+                keep=(self, x_in, out, taps, stamps))
 
 
 def ffn_fused_supported(rows, d, d_ff):

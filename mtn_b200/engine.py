@@ -123,6 +123,7 @@ def _ffn_fused_ok(rows, d, d_ff):
 
 
 FFN_FUSED_DEFAULT = "0"
+DECODE_CLUSTER_DEFAULT = "1"
 
 
 class PackedWeights(object):
@@ -532,6 +533,15 @@ class DecoderEngine(object):
         B, d = st["B"], st["W"]["d"]
         t = st["t"] if t is None else int(t)
         assert 0 <= t < st["max_len"], "decode_step: position %d outside the cache (max_len %d)" % (t, st["max_len"])
+        plan = self._cluster_plan(st)
+        if plan is not None:
+            # the whole step: ONE kernel, one thread-block cluster per dialogue group (csrc/decode_cluster.cu)
+            x = x_t.reshape(B, d)
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = st["xs"].copy_(x)
+            plan.step(t, x, st["out"], taps=st.get("cluster_taps"), stamps=st.get("cluster_stamps"))
+            st["t"] = t + 1
+            return st["out"]
         st["xs"].copy_(x_t.reshape(B, d))
         prog = self._step_program(st, t)
         if prog is not None:
@@ -540,6 +550,52 @@ class DecoderEngine(object):
             self._decode_step_body(st, t)
         st["t"] = t + 1
         return st["out"]
+
+    def _cluster_plan(self, st):
+        """The _lib.DecodeClusterPlan of this decoding state, or None when the step takes the launch sequence.  Default on
+        (MTN_B200_DECODE_CLUSTER=0: off) for greedy decoding (one row per dialogue) at d = 512, h = 8, d_ff = 2048,
+        B <= 128: a decoding step's dependency chain is per dialogue, so a cluster of 8 CTAs (one per head) takes a group
+        of dialogues through all sublayers of the step with cluster barriers only, streaming its weights and K / V ahead
+        of the chain -- ONE launch instead of ~135."""
+        if (os.environ.get("MTN_B200_DECODE_CLUSTER", DECODE_CLUSTER_DEFAULT) == "0" or not _lib.ROWS_KERNELS or
+                st["R"] != 1 or TAP is not None or os.environ.get("MTN_B200_DECODE_PROG", "0") == "1"):
+            return None
+        plan = st.get("cluster_plan", False)
+        if plan is False:
+            plan = st["cluster_plan"] = self._build_cluster_plan(st)
+        return plan
+
+    def _build_cluster_plan(self, st):
+        S, W, B = st["S"], st["W"], st["B"]
+        d, N, M = W["d"], W["N"], W["M"]
+        L0 = W["layers"][0]
+        h, dff = L0["self"]["h"], L0["ffn"]["w_1"].shape[0]
+        if not _lib.decode_cluster_supported(B, d, h, dff, N * (5 + M)):
+            return None
+        bits = [S["bits_his"], S["bits_cap"], S["bits_q"], S["bits_ae"]]
+        if any(b is not None and b.shape[1] != 1 for b in bits) or max(S["H"], S["C"], S["Q"], S["La"]) > 1024:
+            return None
+        plan = _lib.DecodeClusterPlan(B, d, h, dff)
+        order = self._site_order(st["ae_features"])
+        for l in range(N):
+            Lw = W["layers"][l]
+            A = Lw["self"]
+            plan.self_attention(Lw["ln"][0], A["w_qkv"], A["b_qkv"], A["w_o"], A["b_o"], st["cache"][l])
+            kc, vc = l * 2 * d, l * 2 * d + d
+            A = Lw["his"]
+            plan.cross_attention(Lw["ln"][1], A["w_qkv"][:d], A["b_qkv"][:d], A["w_o"], A["b_o"], S["kv_his"], kc, vc, S["H"],
+                                 S["bits_his"])
+            for c, (name, kvn, bn, Ln) in enumerate(order):
+                A = Lw[name]
+                plan.cross_attention(Lw["ln"][2 + c], A["w_qkv"][:d], A["b_qkv"][:d], A["w_o"], A["b_o"], S[kvn], kc, vc, S[Ln],
+                                     S[bn])
+            for i in range(M):
+                A = Lw["ae_attn"][i]
+                plan.cross_attention(Lw["ln"][7 + 4 * i], A["w_qkv"][:d], A["b_qkv"][:d], A["w_o"], A["b_o"], S["kv_ae"][l][i],
+                                     0, d, S["La"], S["bits_ae"])
+            F = Lw["ffn"]
+            plan.feed_forward(Lw["ln"][4 + 4 * M], F["w_1"], F["b_1"], F["w_2"], F["b_2"])
+        return plan.finish(W["norm"])
 
     def _step_program(self, st, t):
         """The recorded program of position t of this state (greedy decoding, few-row kernels, d = 512), or None.  The stage
@@ -581,6 +637,7 @@ class DecoderEngine(object):
             _lib.attn_core(cache[:, t:t + 1, :d], cache[:, :, d:2 * d], cache[:, :, 2 * d:], B, A["h"], 1, t + 1, A["d_k"],
                            obuf, mask_bits=None)
             _lib.linear(obuf, A["w_o"], A["b_o"], addend=xs, out_f32=xs)
+            _tap("x", xs)
             kc, vc = l * 2 * d, l * 2 * d + d
             A = Lw["his"]
             self._attn_block(xs, Lw["ln"][1], A, D, R, S["H"], A["w_qkv"][:d], A["b_qkv"][:d], S["kv_his"], kc, vc,
@@ -601,6 +658,7 @@ class DecoderEngine(object):
         """Beam search: target row i continues the hypothesis that was row parents[i] (int64 [B], device) -- gathers
         the self-attention caches accordingly (the cross-attention side has no per-hypothesis state)."""
         st["cache"] = [c.index_select(0, parents) for c in st["cache"]]
+        st.pop("cluster_plan", None)                           # (its sites point into the old caches)
 
     # ------------------------------------------------------------------ forward
     def forward(self, vid_ft, vid_mask, x, his, his_mask, cap, cap_mask, qm, q_mask, tgt_mask, ae_ft,

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libmtn_b200.so does not export %s" % n
     assert sorted(_lib.SYMBOLS) == names, "ctypes binding and header disagree"
-    assert L.mtn_abi_version() == _lib.ABI_VERSION == 6
+    assert L.mtn_abi_version() == _lib.ABI_VERSION == 7
     assert L.mtn_mask_words(1) == 4 and L.mtn_mask_words(128) == 4 and L.mtn_mask_words(129) == 8
     assert L.mtn_attn_site_workspace_bytes(32, 256, 512, 512) > 32 * 256 * 512 * 2 * 5
     assert L.mtn_ffn_workspace_bytes(100, 512, 2048) >= 100 * (512 + 2048) * 2
@@ -39,7 +39,9 @@ def test_header_is_plain_c_and_struct_layouts_match(tmp_path):
                "MtnAttnSiteArgs": _lib.AttnSiteArgs, "MtnFfnArgs": _lib.FfnArgs,
                "MtnGemmArgs": _lib.GemmArgs, "MtnLinearDgradArgs": _lib.LinearDgradArgs,
                "MtnLinearWgradArgs": _lib.LinearWgradArgs, "MtnLayerNormBwdArgs": _lib.LayerNormBwdArgs,
-               "MtnEmbedBwdArgs": _lib.EmbedBwdArgs, "MtnAttnCoreBwdArgs": _lib.AttnCoreBwdArgs}
+               "MtnEmbedBwdArgs": _lib.EmbedBwdArgs, "MtnAttnCoreBwdArgs": _lib.AttnCoreBwdArgs,
+               "MtnDecodeSite": _lib.DecodeSite, "MtnDecodeClusterArgs": _lib.DecodeClusterArgs,
+               "MtnAttnSiteFusedArgs": _lib.AttnSiteFusedArgs}
     prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "mtn_b200.h"', 'int main(void){']
     for cname, cls in structs.items():
         prog.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

@@ -389,6 +389,73 @@ def test_decode_step_program_equals_launch_sequence(M, cfg2_model, monkeypatch):
     assert torch.equal(ys["0"], ys["1"]) and torch.equal(ys["1"], ys["1b"])
 
 
+def test_decode_cluster_step_equals_launch_sequence(M, cfg2_model, monkeypatch):
+    """One KV-cached decoding step as ONE kernel with one thread-block cluster per dialogue group
+    (csrc/decode_cluster.cu, the default for greedy decoding) against the launch sequence of the few-row kernels: same
+    arithmetic, another summation order in the projections -- the residual rows after EVERY sublayer (the kernel's
+    debug taps vs engine.TAP), the cache rows it appends and the step's output rows agree to f32 / f16 rounding at every
+    position; at batch 64 (configs[3]: 16 clusters x 4 dialogues), at a ragged batch (5: one dialogue per cluster) and at
+    a batch whose last cluster is partly empty (37: 3 rows per cluster, the last one holds 1); and the graphed greedy
+    decoders produce the same tokens with the generator scaled x8."""
+    mtn, du = M
+    from mtn_b200 import engine
+    from mtn_b200.graph import GraphedGreedyDecoder
+    cfg, model = cfg2_model
+    nsite = cfg["N"] * 7
+    for B in (64, 5, 37):
+        T = 20 if B == 64 else 6
+        inp = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=T, Lv=[512, 256], seed=17 + B)
+        b = make_batch(du, inp)
+        with torch.no_grad():
+            q, vid, cap, his, ae = model.encode(b.query, b.query_mask, b.his, b.his_mask, b.cap, b.cap_mask, b.fts, b.fts_mask)
+            monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "0")
+            st0 = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae, T)
+            monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "1")
+            st1 = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae, T)
+            st1["cluster_taps"] = torch.zeros(nsite, B, 512, device="cuda")
+            worst = [0.0, 0.0, 0.0]
+            for t in range(T):
+                monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "0")
+                engine.TAP = []
+                try:
+                    r0 = model.decode_step(st0, b.trg[:, t]).clone()
+                    taps0 = [x for (n, x) in engine.TAP if n.endswith("x")]
+                finally:
+                    engine.TAP = None
+                monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "1")
+                r1 = model.decode_step(st1, b.trg[:, t]).clone()
+                torch.cuda.synchronize()
+                assert st1.get("cluster_plan") is not None and "cluster_plan" not in st0
+                assert len(taps0) == nsite and torch.isfinite(r1).all()
+                es = max(G.rel_err(st1["cluster_taps"][s].cpu(), taps0[s].cpu()) for s in range(nsite))
+                ec = max(G.rel_err(c1[:, t].cpu(), c0[:, t].cpu()) for c0, c1 in zip(st0["cache"], st1["cache"]))
+                worst = [max(worst[0], G.rel_err(r1.cpu(), r0.cpu())), max(worst[1], es), max(worst[2], ec)]
+        print("decode cluster step vs launch sequence, B=%d: rows %.2e, worst sublayer %.2e, cache rows %.2e" % (B, *worst))
+        assert worst[0] < 2e-4 and worst[1] < 2e-4 and worst[2] < 1e-3, (B, worst)
+    from mtn_b200.engine import invalidate_weight_caches
+    w0 = model.generator.proj.weight.data.clone()
+    model.generator.proj.weight.data.mul_(8.0)
+    invalidate_weight_caches()
+    try:
+        B, T = 64, 20
+        inp = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=4, Lv=[512, 256], seed=401)
+        d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
+             if k in ("query", "his", "cap", "fts")}
+        ys = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", mode)
+            dec = GraphedGreedyDecoder(model, d, T, cached=True)
+            ys[mode] = dec.decode().clone()
+            ys[mode + "b"] = dec.decode().clone()      # a second replay of the same graphs
+            torch.cuda.synchronize()
+        nbad = int((ys["0"] != ys["1"]).any(1).sum())
+        print("graphed greedy decoding, cluster step vs launch sequence: %d of %d sequences differ" % (nbad, B))
+        assert nbad == 0 and torch.equal(ys["1"], ys["1b"])
+    finally:
+        model.generator.proj.weight.data.copy_(w0)
+        invalidate_weight_caches()
+
+
 def test_batched_beam_search_on_the_kernels(M, cfg2_model, monkeypatch):
     """generate.py's path (data_utils.py:188-242): the batched, KV-cached beam search over 3 dialogues returns, per
     dialogue, the hypotheses of the serial search in the reference's call form (one full-prefix ``model.decode`` per
