@@ -36,10 +36,15 @@
 namespace mtn {
 
 constexpr int DC_CS = 8;            // CTAs per cluster = heads
-constexpr int DC_WARPS = 8, DC_THREADS = 32 * DC_WARPS;
+constexpr int DC_CWARPS = 8;        // compute warps; warp DC_CWARPS + w streams the operands of compute warp w
+constexpr int DC_CTHREADS = 32 * DC_CWARPS, DC_THREADS = 2 * DC_CTHREADS;
 constexpr int DC_G = 8;             // dialogues (rows) per cluster, at most: the m16n8k16 fragments carry rows 0..7
 constexpr int DC_D = 512, DC_DFF = 2048, DC_DK = 64;
-constexpr int DC_NSLOT = 4, DC_SLOT = 4096;
+// ring slots: a WEIGHT chunk is 8 weight rows x 256 k (row pitch 576 B); a K or V chunk is 32 keys x 64 dims (row pitch
+// 144 B).  The pitches make the fragment / lane-per-key reads conflict-free.
+constexpr int DC_NSLOT = 4, DC_SLOT = 4608;
+constexpr int DC_WPITCH = 576, DC_KPITCH = 144;
+static_assert(8 * DC_WPITCH <= DC_SLOT && 32 * DC_KPITCH <= DC_SLOT, "slot size");
 constexpr int DC_MAX_SITES = 64;
 
 // shared memory (bytes).  The f16 A operands (LayerNorm output, gathered attention output, gathered hidden activation)
@@ -51,15 +56,21 @@ constexpr int DC_OFF_XS = 0;                                      // f32 [8][512
 constexpr int DC_OFF_XN = DC_OFF_XS + DC_G * DC_D * 4;            // f16 [8][LDA]  LayerNorm(x)
 constexpr int DC_OFF_OB = DC_OFF_XN + DC_G * DC_LDA;              // f16 [8][LDA]  attention output, all heads
 constexpr int DC_OFF_HID = DC_OFF_OB + DC_G * DC_LDA;             // f16 [8][LDH]  hidden activation, all columns
+constexpr int DC_OFF_PO = DC_OFF_HID;                             // f32 [8 warps][8][64] partial attention outputs (alias: hid is
+                                                                  // dead between the feed-forward sublayers)
 constexpr int DC_OFF_QS = DC_OFF_HID + DC_G * DC_LDH;             // f32 [3][8][64] q, new k, new v of this head (f16-rounded)
 constexpr int DC_OFF_PM = DC_OFF_QS + 3 * DC_G * DC_DK * 4;       // f32 [8 warps][8]      partial row maxima
-constexpr int DC_OFF_PL = DC_OFF_PM + DC_WARPS * DC_G * 4;        // f32 [8 warps][8]      partial row sums
-constexpr int DC_OFF_PO = DC_OFF_PL + DC_WARPS * DC_G * 4;        // f32 [8 warps][8][64]  partial outputs
-constexpr int DC_OFF_SITES = DC_OFF_PO + DC_WARPS * DC_G * DC_DK * 4;
-constexpr int DC_OFF_RING = (DC_OFF_SITES + DC_MAX_SITES * (int)sizeof(MtnDecodeSite) + 1023) / 1024 * 1024;
-constexpr int DC_SMEM = DC_OFF_RING + DC_WARPS * DC_NSLOT * DC_SLOT;
+constexpr int DC_OFF_PL = DC_OFF_PM + DC_CWARPS * DC_G * 4;       // f32 [8 warps][8]      partial row sums
+constexpr int DC_OFF_BAR = DC_OFF_PL + DC_CWARPS * DC_G * 4;      // mbarriers
+constexpr int DC_OFF_RING = (DC_OFF_BAR + 1024 + 1023) / 1024 * 1024;
+constexpr int DC_SMEM = DC_OFF_RING + DC_CWARPS * DC_NSLOT * DC_SLOT;
 static_assert(DC_SMEM <= 232448, "shared memory budget");
-static_assert(sizeof(MtnDecodeSite) % 8 == 0, "site descriptors are copied word-wise");
+static_assert(DC_CWARPS * DC_G * DC_DK * 4 <= DC_G * DC_LDH, "partial outputs fit the hidden-activation buffer");
+// mbarriers: FULL / EMPTY per (compute warp, ring slot); O / X / H: the cluster-wide exchanges (attention outputs,
+// residual rows, hidden activation) complete their bytes on the RECEIVER's barrier
+constexpr int DC_BAR_FULL = 0, DC_BAR_EMPTY = DC_CWARPS * DC_NSLOT, DC_BAR_O = 2 * DC_CWARPS * DC_NSLOT, DC_BAR_X = DC_BAR_O + 1,
+              DC_BAR_H = DC_BAR_O + 2, DC_BAR_COUNT = DC_BAR_O + 3;
+static_assert(DC_BAR_COUNT * 8 <= 1024, "barrier area");
 
 struct DcTable {
   MtnDecodeSite s[DC_MAX_SITES];
@@ -73,26 +84,18 @@ struct DcParams {
   const float* norm_b;
   float norm_eps;
   float* taps;
-  long long* stamps;   // optional [n_sites][8] clock64 stamps of CTA 0, warp 0 (debug: where a sublayer spends its time)
+  long long* stamps;   // optional [n_sites][8] clock64 stamps of CTA 0, thread 0 (debug: where a sublayer spends its time)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dc_cp16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void dc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void dc_cp_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ uint4 dc_lds128(uint32_t a) {
   uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
   return r;
 }
 __device__ __forceinline__ uint32_t dc_lds32(uint32_t a) {
   uint32_t r;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
   return r;
 }
 __device__ __forceinline__ uint32_t dc_mapa(uint32_t saddr, uint32_t rank) {
@@ -100,14 +103,16 @@ __device__ __forceinline__ uint32_t dc_mapa(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void dc_st_cluster_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+// remote (or local) shared-memory store that completes its bytes on the mbarrier `bar` of the SAME CTA as `addr`: the
+// receiver waits on its own barrier -- no fence, no cluster barrier
+__device__ __forceinline__ void dc_st_async_u32(uint32_t addr, uint32_t v, uint32_t bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void dc_st_cluster_v2f32(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void dc_st_async_v2f32(uint32_t addr, float a, float b, uint32_t bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(a), "f"(b), "r"(bar)
+               : "memory");
 }
-__device__ __forceinline__ void dc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void dc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void dc_cbar() { named_bar_sync(1, DC_CTHREADS); }   // the compute warps
 __device__ __forceinline__ float dc_ex2(float x) {   // the exponential of the other attention kernels
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -121,20 +126,16 @@ __device__ __forceinline__ void dc_mma(float (&c)[4], uint32_t a0, uint32_t a2, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The operand stream of one warp.  Its chunk sequence is a pure function of (site list, t, rows of the cluster, CTA
-// rank, warp): per attention sublayer [w_in: 2 chunks per projection] [per attention unit: K chunk, V chunk] [w_out: 2],
-// per feed-forward sublayer [w_1: 4 column groups x 2] [w_2: 8].  A weight chunk is 8 weight rows x 256 k (4 KB), a K / V
-// chunk 32 keys x 64 dims of the CTA's head.  An attention UNIT is (row of the cluster, 32-key chunk); the units of a
-// sublayer are dealt round-robin to the warps (unit u -> warp u % 8).  The consumer code below takes chunks in exactly
-// this order; dc_phase_count is the single source of truth for how many chunks a phase has.
+// The operand stream of one compute warp.  Its chunk sequence is a pure function of (site list, t, rows of the cluster,
+// CTA rank, warp): per attention sublayer [w_in: 2 chunks per projection] [per attention unit: K chunk, V chunk]
+// [w_out: 2], per feed-forward sublayer [w_1: 4 column groups x 2] [w_2: 8].  A weight chunk is 8 weight rows x 256 k
+// (4 KB), a K / V chunk 32 keys x 64 dims of the CTA's head.  An attention UNIT is (row of the cluster, 32-key chunk);
+// the units of a sublayer are dealt round-robin to the warps (unit u -> warp u % 8).  The PRODUCER warp of the pair walks
+// this sequence (dc_produce) as far ahead as the ring allows -- across sublayer boundaries and while the compute warp
+// waits for the cluster -- and the compute warp takes the chunks in exactly the same order (dc_acquire / dc_release).
 struct DcCtx {
-  const MtnDecodeSite* sites;   // shared-memory copy
-  int n_sites, t, nrows, row0, rank, warp, lane;
-  uint32_t ring;                // shared-memory address of this warp's ring
-};
-struct DcStream {
-  int s, ph, i;                 // producer cursor: site, phase, chunk inside the phase
-  uint32_t issued, taken;
+  int n_sites, t, nrows, row0, rank, warp, lane;   // warp: index of the COMPUTE warp of the pair
+  uint32_t ring, bars;                             // shared-memory addresses: this pair's ring, the barrier area
 };
 
 __device__ __forceinline__ int dc_site_lk(const DcCtx& c, const MtnDecodeSite& d) { return d.kind == 0 ? c.t : d.Lk; }
@@ -142,104 +143,133 @@ __device__ __forceinline__ int dc_units(const DcCtx& c, int Lk) {
   const int total = c.nrows * ((Lk + 31) >> 5);
   return total > c.warp ? (total - c.warp + 7) >> 3 : 0;
 }
-__device__ __forceinline__ int dc_phases(const MtnDecodeSite& d) { return d.kind == 2 ? 2 : (d.kind == 0 ? 5 : 3); }
-__device__ __forceinline__ int dc_phase_count(const DcCtx& c, const MtnDecodeSite& d, int ph) {
-  if (d.kind == 2) return 8;
-  const int nin = d.kind == 0 ? 3 : 1;
-  if (ph == nin) return 2 * dc_units(c, dc_site_lk(c, d));
-  return 2;
+__device__ __forceinline__ void dc_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+template <int DOFF, int SOFF>
+__device__ __forceinline__ void dc_cp16i(uint32_t dst, const void* src) {   // immediate offsets: no address arithmetic per copy
+  asm volatile("cp.async.cg.shared.global [%0 + %2], [%1 + %3], 16;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all of its cp.async issued so far have landed
+__device__ __forceinline__ void dc_cp_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dc_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// 8 weight rows x 256 k -> slot: lane l copies 16-byte segment l of every row.  ROWB = bytes between rows.
+template <int ROWB>
+__device__ __forceinline__ void dc_issue_w(uint32_t dst, const uint8_t* src) {
+#define DC_W1(R) dc_cp16i<(R) * DC_WPITCH, (R) * ROWB>(dst, src);
+  DC_W1(0) DC_W1(1) DC_W1(2) DC_W1(3) DC_W1(4) DC_W1(5) DC_W1(6) DC_W1(7)
+#undef DC_W1
 }
 
-__device__ __forceinline__ void dc_issue(const DcCtx& c, DcStream& st) {
-  if (st.s < c.n_sites) {
-    const MtnDecodeSite& d = c.sites[st.s];
-    const uint32_t slot = c.ring + (st.issued % DC_NSLOT) * DC_SLOT;
-    const int lane = c.lane;
+// producer warp: the whole chunk sequence of its compute warp, slot by slot (cp.async, 16 bytes per lane and copy; the
+// slot's FULL barrier collects one deferred arrival per lane)
+__device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab) {
+  uint32_t n = 0;
+  const int lane = c.lane;
+  const uint32_t full0 = c.bars + 8u * (DC_BAR_FULL + c.warp * DC_NSLOT), empty0 = c.bars + 8u * (DC_BAR_EMPTY + c.warp * DC_NSLOT);
+  auto slot_wait = [&]() -> uint32_t {   // index of the next slot, free
+    const uint32_t sl = n % DC_NSLOT;
+    if (n >= DC_NSLOT) mbar_wait(empty0 + 8u * sl, ((n / DC_NSLOT) - 1u) & 1u);
+    ++n;
+    return sl;
+  };
+  auto weights = [&](const void* W, int K, int row, int nchunks) {   // rows [row, row + 8), nchunks k-blocks of 256
+    const uint8_t* src = static_cast<const uint8_t*>(W) + (size_t)row * K * 2 + lane * 16;
+#pragma unroll 1
+    for (int kp = 0; kp < nchunks; ++kp) {
+      const uint32_t sl = slot_wait();
+      const uint32_t dst = c.ring + sl * DC_SLOT + lane * 16;
+      if (K == DC_D) dc_issue_w<DC_D * 2>(dst, src + kp * 512);
+      else dc_issue_w<DC_DFF * 2>(dst, src + kp * 512);
+      dc_cp_arrive(full0 + 8u * sl);
+    }
+  };
+#pragma unroll 1
+  for (int s = 0; s < c.n_sites; ++s) {
+    const MtnDecodeSite& d = tab.s[s];
+    if (d.kind == 2) {
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) weights(d.w_in, DC_D, c.rank * 256 + (j * 8 + c.warp) * 8, 2);
+      weights(d.w_out, DC_DFF, c.rank * 64 + c.warp * 8, 8);
+      continue;
+    }
     const int nin = d.kind == 0 ? 3 : 1;
-    if (d.kind == 2 || st.ph != nin) {
-      // ---- weight chunk: rows [row, row + 8) x k [256 kp, 256 kp + 256); lane l copies 16-byte segment l of each row.
-      // Row i lands at i * 512 with its segment index XORed by 4 for odd rows (conflict-free fragment loads).
-      const __half* W;
-      int K, row, kp;
-      if (d.kind == 2) {
-        if (st.ph == 0) { W = static_cast<const __half*>(d.w_in); K = DC_D; row = c.rank * 256 + ((st.i >> 1) * 8 + c.warp) * 8; kp = st.i & 1; }
-        else { W = static_cast<const __half*>(d.w_out); K = DC_DFF; row = c.rank * 64 + c.warp * 8; kp = st.i; }
-      } else if (st.ph < nin) {
-        W = static_cast<const __half*>(d.w_in); K = DC_D; row = st.ph * DC_D + c.rank * 64 + c.warp * 8; kp = st.i;
-      } else {
-        W = static_cast<const __half*>(d.w_out); K = DC_D; row = c.rank * 64 + c.warp * 8; kp = st.i;
-      }
-      const __half* src = W + (size_t)row * K + kp * 256 + lane * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dc_cp16(slot + i * 512 + (((uint32_t)lane ^ ((uint32_t)(i & 1) << 2)) << 4), src + (size_t)i * K);
-    } else {
-      // ---- K (even i) or V (odd i) chunk of attention unit st.i / 2: 32 keys x 128 bytes of head `rank`.  K rows are
-      // stored with their 16-byte segment index XORed by (key % 8): lane = key reads are conflict-free.
-      const int Lk = dc_site_lk(c, d);
-      const int nck = (Lk + 31) >> 5;
-      const int u = c.warp + 8 * (st.i >> 1);
+#pragma unroll 1
+    for (int pj = 0; pj < nin; ++pj) weights(d.w_in, DC_D, pj * DC_D + c.rank * 64 + c.warp * 8, 2);
+    const int Lk = dc_site_lk(c, d);
+    const int nck = (Lk + 31) >> 5;
+    const int nun = dc_units(c, Lk);
+    const long long vdelta = static_cast<const uint8_t*>(d.v) - static_cast<const uint8_t*>(d.k);
+    const int seg = lane & 7;
+#pragma unroll 1
+    for (int j = 0; j < nun; ++j) {
+      // attention unit (row g, keys [32 ck, 32 ck + 32)): 128 bytes of head `rank` per key, K then V; lane l copies
+      // segment l % 8 of keys l / 8 + 4 it
+      const int u = c.warp + 8 * j;
       const int g = u / nck, ck = u - g * nck;
-      const bool isv = (st.i & 1) != 0;
-      const int seg = lane & 7;
-      const __half* base = static_cast<const __half*>(isv ? d.v : d.k) + (size_t)(c.row0 + g) * d.kv_batch_stride + c.rank * DC_DK + seg * 8;
+      const uint8_t* base = static_cast<const uint8_t*>(d.k) + ((size_t)(c.row0 + g) * d.kv_batch_stride + c.rank * DC_DK + seg * 8) * 2;
+      const uint8_t* src[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = 4 * i + (lane >> 3);
-        const int key = min(ck * 32 + r, Lk - 1);
-        const uint32_t sg = isv ? (uint32_t)seg : ((uint32_t)seg ^ (uint32_t)(r & 7));
-        dc_cp16(slot + r * 128 + (sg << 4), base + (size_t)key * d.ld_kv);
-      }
+      for (int it = 0; it < 8; ++it) src[it] = base + (size_t)min(ck * 32 + 4 * it + (lane >> 3), Lk - 1) * d.ld_kv * 2;
+      uint32_t sl = slot_wait();
+      uint32_t dst = c.ring + sl * DC_SLOT + (lane >> 3) * DC_KPITCH + seg * 16;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) dc_cp16(dst + it * 4 * DC_KPITCH, src[it]);
+      dc_cp_arrive(full0 + 8u * sl);
+      sl = slot_wait();
+      dst = c.ring + sl * DC_SLOT + (lane >> 3) * DC_KPITCH + seg * 16;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) dc_cp16(dst + it * 4 * DC_KPITCH, src[it] + vdelta);
+      dc_cp_arrive(full0 + 8u * sl);
     }
-    ++st.i;
-    while (st.s < c.n_sites && st.i >= dc_phase_count(c, c.sites[st.s], st.ph)) {
-      st.i = 0;
-      if (++st.ph >= dc_phases(c.sites[st.s])) { st.ph = 0; ++st.s; }
-    }
+    weights(d.w_out, DC_D, c.rank * 64 + c.warp * 8, 2);
   }
-  dc_cp_commit();   // (an empty group past the end keeps the group arithmetic of dc_acquire uniform)
-  ++st.issued;
+  dc_cp_wait_all();
 }
 
-// The next chunk of this warp's stream: waits for it, refills the slot consumed BEFORE it (so the caller holds exactly
-// one chunk at a time) and returns its shared-memory address.
-__device__ __forceinline__ uint32_t dc_acquire(const DcCtx& c, DcStream& st) {
-  dc_cp_wait<DC_NSLOT - 2>();
+// compute warp: the next chunk of its stream (shared-memory address) / hand its slot back to the producer
+__device__ __forceinline__ uint32_t dc_acquire(const DcCtx& c, uint32_t& taken) {
+  const uint32_t sl = taken % DC_NSLOT;
+  mbar_wait(c.bars + 8u * (DC_BAR_FULL + c.warp * DC_NSLOT + sl), (taken / DC_NSLOT) & 1u);
+  return c.ring + sl * DC_SLOT;
+}
+__device__ __forceinline__ void dc_release(const DcCtx& c, uint32_t& taken) {
   __syncwarp();
-  dc_issue(c, st);
-  const uint32_t slot = c.ring + (st.taken % DC_NSLOT) * DC_SLOT;
-  ++st.taken;
-  return slot;
+  if (c.lane == 0) mbar_arrive(c.bars + 8u * (DC_BAR_EMPTY + c.warp * DC_NSLOT + (taken % DC_NSLOT)));
+  ++taken;
 }
 
 // One 8-column group of a projection over K = 256 * KCH: A rows from shared memory (byte offset a_off, row stride lda),
 // the group's weight rows from the stream.  Per 32-wide k chunk a thread takes 8 consecutive k of its row (A: row
 // lane / 4; W: output column lane / 4) with one 16-byte load each; both mma k16 steps use the same logical -> actual k
-// mapping for A and B (csrc/decode_rows.cu), so the products pair up.  Returns this thread's two outputs: row lane / 4,
-// columns 2 (lane % 4), + 1 of the group.
-template <int KCH>
-__device__ __forceinline__ float2 dc_proj(const DcCtx& c, DcStream& st, uint32_t smem_base, int a_off, int lda) {
+// mapping for A and B (csrc/decode_rows.cu), so the products pair up.  Four independent accumulators.  Returns this
+// thread's two outputs: row lane / 4, columns 2 (lane % 4), + 1 of the group.
+template <int KCH>   // K = 256 * KCH
+__device__ __forceinline__ float2 dc_proj(const DcCtx& c, uint32_t& taken, uint32_t smem_base, int a_off, int lda) {
   const int g = c.lane >> 2, q = c.lane & 3;
-  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-  const uint32_t wsw = (uint32_t)(g & 1) << 2;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll 1
   for (int kp = 0; kp < KCH; ++kp) {
-    const uint32_t slot = dc_acquire(c, st);
     const uint32_t arow = smem_base + a_off + g * lda + (kp * 256 + 8 * q) * 2;
-    const uint32_t wrow = slot + g * 512;
+    uint4 a[8], w[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) a[cc] = dc_lds128(arow + cc * 64);
+    const uint32_t wrow = dc_acquire(c, taken) + g * DC_WPITCH + (q << 4);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) w[cc] = dc_lds128(wrow + cc * 64);
+    dc_release(c, taken);
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
-      const uint4 w = dc_lds128(wrow + ((((uint32_t)(4 * cc + q)) ^ wsw) << 4));
-      const uint4 a = dc_lds128(arow + cc * 64);
-      if (cc & 1) {
-        dc_mma(acc1, a.x, a.y, w.x, w.y);
-        dc_mma(acc1, a.z, a.w, w.z, w.w);
-      } else {
-        dc_mma(acc0, a.x, a.y, w.x, w.y);
-        dc_mma(acc0, a.z, a.w, w.z, w.w);
-      }
+      dc_mma(acc[cc & 3], a[cc].x, a[cc].y, w[cc].x, w[cc].y);
+      dc_mma(acc[cc & 3], a[cc].z, a[cc].w, w[cc].z, w[cc].w);
     }
   }
-  return make_float2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
+  return make_float2((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]), (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]));
 }
 
 // LayerNorm parameters of one row pass: lane l holds float4 (l + 32 i) of a_2 / b_2
@@ -300,22 +330,28 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
   float* pm = reinterpret_cast<float*>(smem + DC_OFF_PM);
   float* pl = reinterpret_cast<float*>(smem + DC_OFF_PL);
   float* po = reinterpret_cast<float*>(smem + DC_OFF_PO);
-  MtnDecodeSite* sites = reinterpret_cast<MtnDecodeSite*>(smem + DC_OFF_SITES);
+  const uint32_t bars = sbase + DC_OFF_BAR;
   constexpr float LOG2E = 1.4426950408889634f;
   const float c1 = 0.125f * LOG2E, t_masked = -1e9f * LOG2E;   // 1 / sqrt(d_k), d_k = 64
 
   pdl_launch_dependents();
-  // ---- site table -> shared memory; A operand buffers zeroed (rows >= nrows stay zero: their products are never stored)
+  // ---- barriers; A operand buffers zeroed (rows >= nrows stay zero: their products are never stored)
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DC_CWARPS * DC_NSLOT; ++i) {
+      mbar_init(bars + 8u * (DC_BAR_FULL + i), 32u);    // one deferred arrival per producer lane (cp.async.mbarrier.arrive.noinc)
+      mbar_init(bars + 8u * (DC_BAR_EMPTY + i), 1u);
+    }
+    mbar_init(bars + 8u * DC_BAR_O, 1u);
+    mbar_init(bars + 8u * DC_BAR_X, 1u);
+    mbar_init(bars + 8u * DC_BAR_H, 1u);
+    mbar_fence_init();
+  }
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&tab);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sites);
-    const int words = p.n_sites * (int)(sizeof(MtnDecodeSite) / 4);
-    for (int i = threadIdx.x; i < words; i += DC_THREADS) dst[i] = src[i];
     uint4* z = reinterpret_cast<uint4*>(smem + DC_OFF_XN);
     for (int i = threadIdx.x; i < (DC_OFF_QS - DC_OFF_XN) / 16; i += DC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   pdl_wait();   // the embedding rows and the caches are written by preceding kernels
-  {
+  if (warp < DC_CWARPS) {
     // residual rows: warp w loads row w (zeros beyond the cluster's rows)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -325,237 +361,265 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
     }
   }
   __syncthreads();
-  dc_cluster_arrive();   // every CTA of the cluster is running and initialised before anyone writes into a peer
-  dc_cluster_wait();
+  cluster_sync_all();   // every CTA of the cluster is running, its barriers initialised, before anyone writes into a peer
 
   DcCtx ctx;
-  ctx.sites = sites; ctx.n_sites = p.n_sites; ctx.t = p.t; ctx.nrows = nrows; ctx.row0 = row0;
-  ctx.rank = (int)rank; ctx.warp = warp; ctx.lane = lane;
-  ctx.ring = sbase + DC_OFF_RING + warp * (DC_NSLOT * DC_SLOT);
-  DcStream st = {0, 0, 0, 0u, 0u};
-#pragma unroll 1
-  for (int i = 0; i < DC_NSLOT - 1; ++i) dc_issue(ctx, st);
+  ctx.n_sites = p.n_sites; ctx.t = p.t; ctx.nrows = nrows; ctx.row0 = row0;
+  ctx.rank = (int)rank; ctx.warp = warp & (DC_CWARPS - 1); ctx.lane = lane;
+  ctx.ring = sbase + DC_OFF_RING + ctx.warp * (DC_NSLOT * DC_SLOT);
+  ctx.bars = bars;
 
-  const int col = (int)rank * 64 + warp * 8 + 2 * q;   // this thread's output columns of a d-wide projection
-  const uint32_t xs_s = sbase + DC_OFF_XS, ob_s = sbase + DC_OFF_OB, hid_s = sbase + DC_OFF_HID;
-  DcLn ln;
-  dc_ln_load(ln, sites[0].ln_a, sites[0].ln_b, sites[0].ln_eps, lane);
-
-  const bool stamping = p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (warp >= DC_CWARPS) {
+    dc_produce(ctx, tab);
+  } else {
+    uint32_t taken = 0;
+    const int col = (int)rank * 64 + warp * 8 + 2 * q;   // this thread's output columns of a d-wide projection
+    const uint32_t xs_s = sbase + DC_OFF_XS, ob_s = sbase + DC_OFF_OB, hid_s = sbase + DC_OFF_HID;
+    // bytes every exchange delivers into one CTA: 8 CTAs x its rows x their 64 (256) columns
+    const uint32_t o_bytes = (uint32_t)nrows * DC_D * 2, x_bytes = (uint32_t)nrows * DC_D * 4, h_bytes = (uint32_t)nrows * DC_DFF * 2;
+    uint32_t n_o = 0, n_x = 0, n_h = 0;   // completed phases of the exchange barriers
+    DcLn ln;
+    dc_ln_load(ln, tab.s[0].ln_a, tab.s[0].ln_b, tab.s[0].ln_eps, lane);
+    const bool stamping = p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 #define DC_STAMP(k) do { if (stamping) p.stamps[s * 8 + (k)] = clock64(); } while (0)
+
 #pragma unroll 1
-  for (int s = 0; s < p.n_sites; ++s) {
-    const MtnDecodeSite& d = sites[s];
-    DC_STAMP(0);
-    // ---- LayerNorm: warp w normalises row w -> f16 A operand
-    {
-      float4 o[4];
-      dc_ln_row(xs + warp * DC_D, ln, lane, o);
-      uint8_t* xr = smem + DC_OFF_XN + warp * DC_LDA;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        reinterpret_cast<uint2*>(xr)[lane + 32 * i] = make_uint2(pack_f16x2_sat(o[i].x, o[i].y), pack_f16x2_sat(o[i].z, o[i].w));
-    }
-    __syncthreads();
-    DC_STAMP(1);
-    float2 bo;
-    if (d.kind == 2) {
-      // ================================================================ feed-forward sublayer
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int hc = (int)rank * 256 + (j * 8 + warp) * 8 + 2 * q;
-        const float2 b1 = __ldg(reinterpret_cast<const float2*>(d.b_in + hc));
-        float2 y = dc_proj<2>(ctx, st, sbase, DC_OFF_XN, DC_LDA);
-        const uint32_t h2 = pack_f16x2_sat(fmaxf(y.x + b1.x, 0.f), fmaxf(y.y + b1.y, 0.f));
-        if (g < nrows) {
-          const uint32_t a = hid_s + g * DC_LDH + hc * 2;
-#pragma unroll
-          for (uint32_t r = 0; r < DC_CS; ++r) dc_st_cluster_u32(dc_mapa(a, r), h2);
-        }
+    for (int s = 0; s < p.n_sites; ++s) {
+      const MtnDecodeSite& d = tab.s[s];
+      const int kind = d.kind;
+      DC_STAMP(0);
+      // ---- everything of this sublayer whose address is known now is requested before the LayerNorm: biases, mask words
+      const float2 bo = __ldg(reinterpret_cast<const float2*>(d.b_out + col));
+      float2 bi[3];
+      bi[0] = __ldg(reinterpret_cast<const float2*>(d.b_in + (kind == 2 ? (int)rank * 256 + warp * 8 + 2 * q : col)));
+      bi[1] = bi[2] = bi[0];
+      if (kind == 0) {
+        bi[1] = __ldg(reinterpret_cast<const float2*>(d.b_in + DC_D + col));
+        bi[2] = __ldg(reinterpret_cast<const float2*>(d.b_in + 2 * DC_D + col));
       }
-      DC_STAMP(4);
-      dc_cluster_arrive();
-      bo = __ldg(reinterpret_cast<const float2*>(d.b_out + col));
-      dc_cluster_wait();
-    } else {
-      // ================================================================ attention sublayer
-      const int nin = d.kind == 0 ? 3 : 1;
-#pragma unroll 1
-      for (int pj = 0; pj < nin; ++pj) {
-        const float2 bi = __ldg(reinterpret_cast<const float2*>(d.b_in + pj * DC_D + col));
-        float2 y = dc_proj<2>(ctx, st, sbase, DC_OFF_XN, DC_LDA);
-        const uint32_t h2 = pack_f16x2_sat(y.x + bi.x, y.y + bi.y);
-        if (g < nrows) {
-          const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&h2));
-          *reinterpret_cast<float2*>(qs + (pj * DC_G + g) * DC_DK + warp * 8 + 2 * q) = r;
-          if (d.kind == 0) {   // the new row of the self-attention cache: [Q | K | V] of position t
-            __half* base = pj == 0 ? static_cast<__half*>(d.q_cache)
-                                   : const_cast<__half*>(static_cast<const __half*>(pj == 1 ? d.k : d.v));
-            if (base != nullptr)
-              *reinterpret_cast<uint32_t*>(base + (size_t)(row0 + g) * d.kv_batch_stride + (size_t)p.t * d.ld_kv + col) = h2;
-          }
-        }
-      }
-      const int Lk = dc_site_lk(ctx, d);
+      const int Lk = kind == 2 ? 0 : dc_site_lk(ctx, d);
       const int nck = (Lk + 31) >> 5;
-      const int nun = dc_units(ctx, Lk);
-      // mask word of unit j in lane j (key padding mask, one query row per dialogue; NULL: all keys kept)
+      const int nun = kind == 2 ? 0 : dc_units(ctx, Lk);
+      // mask word of attention unit j in lane j (key padding mask, one query row per dialogue; NULL: all keys kept)
       uint32_t mwords = 0xffffffffu;
-      if (d.mask_bits != nullptr && lane < nun) {
+      if (kind == 1 && d.mask_bits != nullptr && lane < nun) {
         const int u = warp + 8 * lane;
         const int gu = u / nck;
         mwords = __ldg(d.mask_bits + (size_t)(row0 + gu) * d.mask_words + (u - gu * nck));
       }
       if (lane < DC_G) pm[warp * DC_G + lane] = -CUDART_INF_F;
-      __syncthreads();   // q (new k, v) of every warp's columns are in shared memory
-      DC_STAMP(2);
+      // ---- LayerNorm: warp w normalises row w -> f16 A operand
       {
-        int gcur = -1;
-        float m_run = -CUDART_INF_F, l_run = 0.f, o0 = 0.f, o1 = 0.f;
+        float4 o[4];
+        dc_ln_row(xs + warp * DC_D, ln, lane, o);
+        uint8_t* xr = smem + DC_OFF_XN + warp * DC_LDA;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<uint2*>(xr)[lane + 32 * i] = make_uint2(pack_f16x2_sat(o[i].x, o[i].y), pack_f16x2_sat(o[i].z, o[i].w));
+      }
+      dc_cbar();
+      DC_STAMP(1);
+      if (kind == 2) {
+        // ================================================================ feed-forward sublayer
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bars + 8u * DC_BAR_H, h_bytes);
 #pragma unroll 1
-        for (int j = 0; j < nun; ++j) {
-          const int u = warp + 8 * j;
-          const int gu = u / nck, ck = u - gu * nck;
-          if (gu != gcur) {
-            if (gcur >= 0) {
-              if (lane == 0) pm[warp * DC_G + gcur] = m_run, pl[warp * DC_G + gcur] = l_run;
-              *reinterpret_cast<float2*>(po + (warp * DC_G + gcur) * DC_DK + 2 * lane) = make_float2(o0, o1);
+        for (int j = 0; j < 4; ++j) {
+          const int hc = (int)rank * 256 + (j * 8 + warp) * 8 + 2 * q;
+          const float2 b1 = j == 0 ? bi[0] : __ldg(reinterpret_cast<const float2*>(d.b_in + hc));
+          const float2 y = dc_proj<2>(ctx, taken, sbase, DC_OFF_XN, DC_LDA);
+          const uint32_t h2 = pack_f16x2_sat(fmaxf(y.x + b1.x, 0.f), fmaxf(y.y + b1.y, 0.f));
+          if (g < nrows) {
+            const uint32_t a = hid_s + g * DC_LDH + hc * 2;
+#pragma unroll
+            for (uint32_t r = 0; r < DC_CS; ++r) dc_st_async_u32(dc_mapa(a, r), h2, dc_mapa(bars + 8u * DC_BAR_H, r));
+          }
+        }
+        DC_STAMP(4);
+        mbar_wait(bars + 8u * DC_BAR_H, n_h & 1u);
+        ++n_h;
+      } else {
+        // ================================================================ attention sublayer
+        const int nin = kind == 0 ? 3 : 1;
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bars + 8u * DC_BAR_O, o_bytes);
+#pragma unroll 1
+        for (int pj = 0; pj < nin; ++pj) {
+          const float2 y = dc_proj<2>(ctx, taken, sbase, DC_OFF_XN, DC_LDA);
+          const float2 bb = pj == 0 ? bi[0] : (pj == 1 ? bi[1] : bi[2]);
+          const uint32_t h2 = pack_f16x2_sat(y.x + bb.x, y.y + bb.y);
+          if (g < nrows) {
+            const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+            *reinterpret_cast<float2*>(qs + (pj * DC_G + g) * DC_DK + warp * 8 + 2 * q) = r;
+            if (kind == 0) {   // the new row of the self-attention cache: [Q | K | V] of position t
+              __half* base = pj == 0 ? static_cast<__half*>(d.q_cache)
+                                     : const_cast<__half*>(static_cast<const __half*>(pj == 1 ? d.k : d.v));
+              if (base != nullptr)
+                *reinterpret_cast<uint32_t*>(base + (size_t)(row0 + g) * d.kv_batch_stride + (size_t)p.t * d.ld_kv + col) = h2;
             }
-            gcur = gu; m_run = -CUDART_INF_F; l_run = 0.f; o0 = 0.f; o1 = 0.f;
-          }
-          const uint32_t mw = __shfl_sync(0xffffffffu, mwords, j);
-          const int key = ck * 32 + lane;
-          // ---- scores: lane = key
-          const uint32_t ks = dc_acquire(ctx, st);
-          float sc = 0.f;
-          const float4* q4 = reinterpret_cast<const float4*>(qs + gu * DC_DK);
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const uint4 kv = dc_lds128(ks + lane * 128 + (((uint32_t)cc ^ (uint32_t)(lane & 7)) << 4));
-            const float4 qa = q4[2 * cc], qb = q4[2 * cc + 1];
-            const __half2* hp = reinterpret_cast<const __half2*>(&kv);
-            const float2 k0 = __half22float2(hp[0]), k1 = __half22float2(hp[1]), k2 = __half22float2(hp[2]), k3 = __half22float2(hp[3]);
-            sc = fmaf(qa.x, k0.x, fmaf(qa.y, k0.y, sc));
-            sc = fmaf(qa.z, k1.x, fmaf(qa.w, k1.y, sc));
-            sc = fmaf(qb.x, k2.x, fmaf(qb.y, k2.y, sc));
-            sc = fmaf(qb.z, k3.x, fmaf(qb.w, k3.y, sc));
-          }
-          const bool keep = (mw >> lane) & 1u;
-          const float tt = key < Lk ? (keep ? sc * c1 : t_masked) : -CUDART_INF_F;
-          float mx = tt;
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-          const float m_new = fmaxf(m_run, mx);
-          const float e = dc_ex2(tt - m_new);
-          float sum = e;
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-          const float alpha = dc_ex2(m_run - m_new);
-          l_run = l_run * alpha + sum;
-          o0 *= alpha;
-          o1 *= alpha;
-          m_run = m_new;
-          const float pr = __half2float(__float2half_rn(e));   // P rounded to f16 before P V, like the tensor-core path
-          // ---- P V: lane = two output dims
-          const uint32_t vs = dc_acquire(ctx, st);
-#pragma unroll
-          for (int uu = 0; uu < 32; ++uu) {
-            const uint32_t vv = dc_lds32(vs + uu * 128 + lane * 4);
-            const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vv));
-            const float pk = __shfl_sync(0xffffffffu, pr, uu);
-            o0 = fmaf(pk, vf.x, o0);
-            o1 = fmaf(pk, vf.y, o1);
           }
         }
-        if (gcur >= 0) {
-          if (lane == 0) pm[warp * DC_G + gcur] = m_run, pl[warp * DC_G + gcur] = l_run;
-          *reinterpret_cast<float2*>(po + (warp * DC_G + gcur) * DC_DK + 2 * lane) = make_float2(o0, o1);
+        dc_cbar();   // q (new k, v) of every warp's columns are in shared memory
+        DC_STAMP(2);
+        {
+          int gcur = -1;
+          float m_run = -CUDART_INF_F, l_run = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll 1
+          for (int j = 0; j < nun; ++j) {
+            const int u = warp + 8 * j;
+            const int gu = u / nck, ck = u - gu * nck;
+            if (gu != gcur) {
+              if (gcur >= 0) {
+                if (lane == 0) pm[warp * DC_G + gcur] = m_run, pl[warp * DC_G + gcur] = l_run;
+                *reinterpret_cast<float2*>(po + (warp * DC_G + gcur) * DC_DK + 2 * lane) = make_float2(o0, o1);
+              }
+              gcur = gu; m_run = -CUDART_INF_F; l_run = 0.f; o0 = 0.f; o1 = 0.f;
+            }
+            const uint32_t mw = __shfl_sync(0xffffffffu, mwords, j);
+            const int key = ck * 32 + lane;
+            // ---- scores: lane = key; four independent partial sums
+            float4 qv[16];
+            const float4* q4 = reinterpret_cast<const float4*>(qs + gu * DC_DK);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) qv[i] = q4[i];
+            const uint32_t ks = dc_acquire(ctx, taken);
+            uint4 kr[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) kr[cc] = dc_lds128(ks + lane * DC_KPITCH + (cc << 4));
+            dc_release(ctx, taken);
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const float4 qa = qv[2 * cc], qb = qv[2 * cc + 1];
+              const __half2* hp = reinterpret_cast<const __half2*>(&kr[cc]);
+              const float2 k0 = __half22float2(hp[0]), k1 = __half22float2(hp[1]), k2 = __half22float2(hp[2]), k3 = __half22float2(hp[3]);
+              sc[0] = fmaf(qa.x, k0.x, fmaf(qa.y, k0.y, sc[0]));
+              sc[1] = fmaf(qa.z, k1.x, fmaf(qa.w, k1.y, sc[1]));
+              sc[2] = fmaf(qb.x, k2.x, fmaf(qb.y, k2.y, sc[2]));
+              sc[3] = fmaf(qb.z, k3.x, fmaf(qb.w, k3.y, sc[3]));
+            }
+            const float sdot = (sc[0] + sc[1]) + (sc[2] + sc[3]);
+            const bool keep = (mw >> lane) & 1u;
+            const float tt = key < Lk ? (keep ? sdot * c1 : t_masked) : -CUDART_INF_F;
+            float mx = tt;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float m_new = fmaxf(m_run, mx);
+            const float e = dc_ex2(tt - m_new);
+            float sum = e;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            const float alpha = dc_ex2(m_run - m_new);
+            l_run = l_run * alpha + sum;
+            m_run = m_new;
+            const float pr = __half2float(__float2half_rn(e));   // P rounded to f16 before P V, like the tensor-core path
+            // ---- P V: lane = two output dims; two independent partial sums per dim
+            const uint32_t vs = dc_acquire(ctx, taken);
+            uint32_t vv[32];
+#pragma unroll
+            for (int uu = 0; uu < 32; ++uu) vv[uu] = dc_lds32(vs + uu * DC_KPITCH + lane * 4);
+            dc_release(ctx, taken);
+            float oa0 = o0 * alpha, oa1 = o1 * alpha, ob0 = 0.f, ob1 = 0.f;
+#pragma unroll
+            for (int uu = 0; uu < 32; uu += 2) {
+              const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&vv[uu]));
+              const float2 vb = __half22float2(*reinterpret_cast<const __half2*>(&vv[uu + 1]));
+              const float pa = __shfl_sync(0xffffffffu, pr, uu), pb = __shfl_sync(0xffffffffu, pr, uu + 1);
+              oa0 = fmaf(pa, va.x, oa0);
+              oa1 = fmaf(pa, va.y, oa1);
+              ob0 = fmaf(pb, vb.x, ob0);
+              ob1 = fmaf(pb, vb.y, ob1);
+            }
+            o0 = oa0 + ob0;
+            o1 = oa1 + ob1;
+          }
+          if (gcur >= 0) {
+            if (lane == 0) pm[warp * DC_G + gcur] = m_run, pl[warp * DC_G + gcur] = l_run;
+            *reinterpret_cast<float2*>(po + (warp * DC_G + gcur) * DC_DK + 2 * lane) = make_float2(o0, o1);
+          }
+        }
+        dc_cbar();
+        DC_STAMP(3);
+        // ---- merge the warps' partial (max, sum, O) of row `warp` in a fixed order; self-attention adds the new key
+        if (warp < nrows) {
+          const int gr = warp;
+          float m = -CUDART_INF_F;
+#pragma unroll
+          for (int w = 0; w < DC_CWARPS; ++w) m = fmaxf(m, pm[w * DC_G + gr]);
+          float m_new = -CUDART_INF_F;
+          float2 vnew = make_float2(0.f, 0.f);
+          if (kind == 0) {
+            const float2 qq = *reinterpret_cast<const float2*>(qs + (0 * DC_G + gr) * DC_DK + 2 * lane);
+            const float2 kk = *reinterpret_cast<const float2*>(qs + (1 * DC_G + gr) * DC_DK + 2 * lane);
+            vnew = *reinterpret_cast<const float2*>(qs + (2 * DC_G + gr) * DC_DK + 2 * lane);
+            float sn = fmaf(qq.x, kk.x, qq.y * kk.y);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sn += __shfl_xor_sync(0xffffffffu, sn, off);
+            m_new = sn * c1;
+            m = fmaxf(m, m_new);
+          }
+          float l = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int w = 0; w < DC_CWARPS; ++w) {
+            const float pmw = pm[w * DC_G + gr];
+            if (pmw > -CUDART_INF_F) {
+              const float f = dc_ex2(pmw - m);
+              const float2 ov = *reinterpret_cast<const float2*>(po + (w * DC_G + gr) * DC_DK + 2 * lane);
+              l = fmaf(pl[w * DC_G + gr], f, l);
+              a0 = fmaf(ov.x, f, a0);
+              a1 = fmaf(ov.y, f, a1);
+            }
+          }
+          if (kind == 0) {
+            const float f = dc_ex2(m_new - m);
+            l += f;
+            a0 = fmaf(vnew.x, f, a0);
+            a1 = fmaf(vnew.y, f, a1);
+          }
+          const float inv = 1.f / l;
+          const uint32_t h2 = pack_f16x2_sat(a0 * inv, a1 * inv);
+          const uint32_t a = ob_s + gr * DC_LDA + ((int)rank * DC_DK + 2 * lane) * 2;
+#pragma unroll
+          for (uint32_t r = 0; r < DC_CS; ++r) dc_st_async_u32(dc_mapa(a, r), h2, dc_mapa(bars + 8u * DC_BAR_O, r));
+        }
+        DC_STAMP(4);
+        mbar_wait(bars + 8u * DC_BAR_O, n_o & 1u);
+        ++n_o;
+      }
+      DC_STAMP(5);
+      // ---- output projection (attention: A = all heads' outputs; feed-forward: A = hidden activation) + residual
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(bars + 8u * DC_BAR_X, x_bytes);
+      {
+        const float2 y = kind == 2 ? dc_proj<8>(ctx, taken, sbase, DC_OFF_HID, DC_LDH) : dc_proj<2>(ctx, taken, sbase, DC_OFF_OB, DC_LDA);
+        if (g < nrows) {
+          const float2 xo = *reinterpret_cast<const float2*>(xs + g * DC_D + col);
+          const float x0 = xo.x + (y.x + bo.x), x1 = xo.y + (y.y + bo.y);
+          const uint32_t a = xs_s + (g * DC_D + col) * 4;
+#pragma unroll
+          for (uint32_t r = 0; r < DC_CS; ++r) dc_st_async_v2f32(dc_mapa(a, r), x0, x1, dc_mapa(bars + 8u * DC_BAR_X, r));
         }
       }
-      __syncthreads();
-      DC_STAMP(3);
-      // ---- merge the warps' partial (max, sum, O) of row `warp` in a fixed order; self-attention adds the new key
-      if (warp < nrows) {
-        const int gr = warp;
-        float m = -CUDART_INF_F;
+      DC_STAMP(6);
+      if (s + 1 < p.n_sites) dc_ln_load(ln, tab.s[s + 1].ln_a, tab.s[s + 1].ln_b, tab.s[s + 1].ln_eps, lane);
+      else dc_ln_load(ln, p.norm_a, p.norm_b, p.norm_eps, lane);
+      mbar_wait(bars + 8u * DC_BAR_X, n_x & 1u);
+      ++n_x;
+      DC_STAMP(7);
+      if (p.taps != nullptr && rank == 0 && warp < nrows) {
+        float4* tp = reinterpret_cast<float4*>(p.taps + ((size_t)s * p.B + row0 + warp) * DC_D);
 #pragma unroll
-        for (int w = 0; w < DC_WARPS; ++w) m = fmaxf(m, pm[w * DC_G + gr]);
-        float m_new = -CUDART_INF_F;
-        float2 vnew = make_float2(0.f, 0.f);
-        if (d.kind == 0) {
-          const float2 qq = *reinterpret_cast<const float2*>(qs + (0 * DC_G + gr) * DC_DK + 2 * lane);
-          const float2 kk = *reinterpret_cast<const float2*>(qs + (1 * DC_G + gr) * DC_DK + 2 * lane);
-          vnew = *reinterpret_cast<const float2*>(qs + (2 * DC_G + gr) * DC_DK + 2 * lane);
-          float sn = fmaf(qq.x, kk.x, qq.y * kk.y);
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) sn += __shfl_xor_sync(0xffffffffu, sn, off);
-          m_new = sn * c1;
-          m = fmaxf(m, m_new);
-        }
-        float l = 0.f, a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int w = 0; w < DC_WARPS; ++w) {
-          const float pmw = pm[w * DC_G + gr];
-          if (pmw > -CUDART_INF_F) {
-            const float f = dc_ex2(pmw - m);
-            const float2 ov = *reinterpret_cast<const float2*>(po + (w * DC_G + gr) * DC_DK + 2 * lane);
-            l = fmaf(pl[w * DC_G + gr], f, l);
-            a0 = fmaf(ov.x, f, a0);
-            a1 = fmaf(ov.y, f, a1);
-          }
-        }
-        if (d.kind == 0) {
-          const float f = dc_ex2(m_new - m);
-          l += f;
-          a0 = fmaf(vnew.x, f, a0);
-          a1 = fmaf(vnew.y, f, a1);
-        }
-        const float inv = 1.f / l;
-        const uint32_t h2 = pack_f16x2_sat(a0 * inv, a1 * inv);
-        const uint32_t a = ob_s + gr * DC_LDA + ((int)rank * DC_DK + 2 * lane) * 2;
-#pragma unroll
-        for (uint32_t r = 0; r < DC_CS; ++r) dc_st_cluster_u32(dc_mapa(a, r), h2);
+        for (int i = 0; i < 4; ++i) tp[lane + 32 * i] = reinterpret_cast<const float4*>(xs + warp * DC_D)[lane + 32 * i];
       }
-      DC_STAMP(4);
-      dc_cluster_arrive();
-      bo = __ldg(reinterpret_cast<const float2*>(d.b_out + col));
-      dc_cluster_wait();
     }
-    DC_STAMP(5);
-    // ---- output projection (attention: A = all heads' outputs; feed-forward: A = hidden activation) + residual
-    {
-      const float2 y = d.kind == 2 ? dc_proj<8>(ctx, st, sbase, DC_OFF_HID, DC_LDH) : dc_proj<2>(ctx, st, sbase, DC_OFF_OB, DC_LDA);
-      if (g < nrows) {
-        const float2 xo = *reinterpret_cast<const float2*>(xs + g * DC_D + col);
-        const float x0 = xo.x + (y.x + bo.x), x1 = xo.y + (y.y + bo.y);
-        const uint32_t a = xs_s + (g * DC_D + col) * 4;
+    // ---- final LayerNorm (mtn.py:164) -> out
+    if (rank == 0 && warp < nrows) {
+      float4 o[4];
+      dc_ln_row(xs + warp * DC_D, ln, lane, o);
+      float4* op = reinterpret_cast<float4*>(p.out + (size_t)(row0 + warp) * DC_D);
 #pragma unroll
-        for (uint32_t r = 0; r < DC_CS; ++r) dc_st_cluster_v2f32(dc_mapa(a, r), x0, x1);
-      }
-    }
-    DC_STAMP(6);
-    dc_cluster_arrive();
-    if (s + 1 < p.n_sites) dc_ln_load(ln, sites[s + 1].ln_a, sites[s + 1].ln_b, sites[s + 1].ln_eps, lane);
-    else dc_ln_load(ln, p.norm_a, p.norm_b, p.norm_eps, lane);
-    dc_cluster_wait();
-    DC_STAMP(7);
-    if (p.taps != nullptr && rank == 0 && warp < nrows) {
-      float4* tp = reinterpret_cast<float4*>(p.taps + ((size_t)s * p.B + row0 + warp) * DC_D);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) tp[lane + 32 * i] = reinterpret_cast<const float4*>(xs + warp * DC_D)[lane + 32 * i];
+      for (int i = 0; i < 4; ++i) op[lane + 32 * i] = o[i];
     }
   }
-  // ---- final LayerNorm (mtn.py:164) -> out
-  if (rank == 0 && warp < nrows) {
-    float4 o[4];
-    dc_ln_row(xs + warp * DC_D, ln, lane, o);
-    float4* op = reinterpret_cast<float4*>(p.out + (size_t)(row0 + warp) * DC_D);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) op[lane + 32 * i] = o[i];
-  }
-  dc_cp_wait<0>();
-  dc_cluster_arrive();   // no CTA leaves while a peer could still address its shared memory
-  dc_cluster_wait();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
 }
 
 static int dc_max_clusters(int* out) {

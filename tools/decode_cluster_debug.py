@@ -68,7 +68,7 @@ def main():
         print("worst output error over %d positions: %.2e" % (T, worst))
         if a.stamps:
             st1.pop("cluster_taps")
-            st1["cluster_stamps"] = torch.zeros(nsite, 8, dtype=torch.int64, device="cuda")
+            st1["cluster_stamps"] = torch.zeros(nsite + 8, 8, dtype=torch.int64, device="cuda")
             for _ in range(3):
                 model.decode_step(st1, b.trg[:, T - 1], T - 1)
             torch.cuda.synchronize()
@@ -88,6 +88,13 @@ def main():
                     seg.append(r[k] - last); last = r[k]
                 print("%3d  %-5s  " % (s_, kinds[s_ % 7]) + "  ".join("%10d" % v for v in seg) + "  %10d" % (r[7] - r[0]))
             print("whole step: %d cycles" % (sm[nsite - 1, 7].item() - sm[0, 0].item()))
+            f = sm[nsite:].reshape(-1).tolist()
+            if f[15]:
+                t0 = f[15]
+                print("site 2 in-proj detail (cycles after entering dc_proj): chunk0 A-loaded %d acquired %d W-loaded+released %d mma done %d | "
+                      "chunk1 %d %d %d %d | returned %d | before cbar %d | stamp1->entry %d, cbar done %d" %
+                      (f[0] - t0, f[1] - t0, f[2] - t0, f[3] - t0, f[4] - t0, f[5] - t0, f[6] - t0, f[7] - t0, f[8] - t0, f[9] - t0,
+                       t0 - sm[2, 1].item(), sm[2, 2].item() - t0))
     if a.time:
         from mtn_b200.graph import GraphedGreedyDecoder
         d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items() if k in ("query", "his", "cap", "fts")}
