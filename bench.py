@@ -833,7 +833,7 @@ def main():
                 for g_ in dec.graphs[1:]:
                     g_.replay()
             e1.record(); torch.cuda.synchronize()
-            us_step = e0.elapsed_time(e1) * 1e3 / (3 * (len(dec.graphs) - 1))
+            us_step = e0.elapsed_time(e1) * 1e3 / (3 * sum(dec.steps_in_graph[1:]))
             hbm_pk = peaks.get("hbm_gbs", 6650.0)
             # launches of one cached step (eager, untimed): our kernels by name
             try:
@@ -855,10 +855,15 @@ def main():
                                   "frac": step_bytes / (us_step * 1e-6) / 1e9 / hbm_pk, "us_per_step": us_step,
                                   "bytes_per_step": step_bytes,
                                   "note": "algorithmic bytes of one cached step (f16 weights %.0f MB + memory K/V %.0f MB + "
-                                          "self cache %.1f MB) / CUDA-event time of the step graphs; the step is a chain of "
-                                          "~130 dependent few-row launches (csrc/decode_rows.cu), each one memory round trip "
-                                          "deep: latency bound, not bandwidth bound"
-                                          % (w_bytes / 1e6, kv_mem / 1e6, kv_self / 1e6)}
+                                          "self cache %.1f MB) / CUDA-event time of the step graph; %s"
+                                          % (w_bytes / 1e6, kv_mem / 1e6, kv_self / 1e6,
+                                             "the target path of a step is ONE kernel (csrc/decode_cluster.cu): a cluster of 8 CTAs "
+                                             "per dialogue group, one head per CTA, operands streamed ahead of the per-dialogue "
+                                             "dependency chain; bound by that chain's latency (LayerNorm -> projection -> attention "
+                                             "-> exchange per sublayer), not by bandwidth"
+                                             if "decode_cluster" in decode.get("launches_by_kernel", {}) else
+                                             "the step is a chain of ~130 dependent few-row launches (csrc/decode_rows.cu), each one "
+                                             "memory round trip deep: latency bound, not bandwidth bound")}
         except Exception as e:
             decode["roofline"] = {"error": repr(e)[:300]}
         # Several dialogue batches in flight: a decoding step is a chain of small dependent kernels (<= 40 CTAs each on

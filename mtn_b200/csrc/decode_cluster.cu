@@ -40,11 +40,12 @@ constexpr int DC_CWARPS = 8;        // compute warps; warp DC_CWARPS + w streams
 constexpr int DC_CTHREADS = 32 * DC_CWARPS, DC_THREADS = 2 * DC_CTHREADS;
 constexpr int DC_G = 8;             // dialogues (rows) per cluster, at most: the m16n8k16 fragments carry rows 0..7
 constexpr int DC_D = 512, DC_DFF = 2048, DC_DK = 64;
-// ring slots: a WEIGHT chunk is 8 weight rows x 256 k (row pitch 576 B); a K or V chunk is 32 keys x 64 dims (row pitch
-// 144 B).  The pitches make the fragment / lane-per-key reads conflict-free.
-constexpr int DC_NSLOT = 4, DC_SLOT = 4608;
-constexpr int DC_WPITCH = 576, DC_KPITCH = 144;
-static_assert(8 * DC_WPITCH <= DC_SLOT && 32 * DC_KPITCH <= DC_SLOT, "slot size");
+// ring slots: a WEIGHT chunk is 8 weight rows x 512 k (row pitch 1088 B); an attention-UNIT chunk is 32 keys x 64 dims of K
+// (row pitch 144 B) followed, at DC_VOFF, by the same of V.  The pitches make the fragment / lane-per-key reads
+// conflict-free.  Two slots per warp: with everything else the step keeps on chip, shared memory has room for no more.
+constexpr int DC_NSLOT = 2, DC_SLOT = 9216;
+constexpr int DC_WPITCH = 1088, DC_KPITCH = 144, DC_VOFF = 32 * DC_KPITCH;
+static_assert(8 * DC_WPITCH <= DC_SLOT && 2 * DC_VOFF <= DC_SLOT, "slot size");
 constexpr int DC_MAX_SITES = 64;
 
 // shared memory (bytes).  The f16 A operands (LayerNorm output, gathered attention output, gathered hidden activation)
@@ -156,12 +157,12 @@ __device__ __forceinline__ void dc_cp_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void dc_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// 8 weight rows x 256 k -> slot: lane l copies 16-byte segment l of every row.  ROWB = bytes between rows.
+// 8 weight rows x 512 k -> slot: lane l copies 16-byte segments l and l + 32 of every row.  ROWB = bytes between rows.
 template <int ROWB>
 __device__ __forceinline__ void dc_issue_w(uint32_t dst, const uint8_t* src) {
-#define DC_W1(R) dc_cp16i<(R) * DC_WPITCH, (R) * ROWB>(dst, src);
-  DC_W1(0) DC_W1(1) DC_W1(2) DC_W1(3) DC_W1(4) DC_W1(5) DC_W1(6) DC_W1(7)
-#undef DC_W1
+#define DC_W2(R) dc_cp16i<(R) * DC_WPITCH, (R) * ROWB>(dst, src); dc_cp16i<(R) * DC_WPITCH + 512, (R) * ROWB + 512>(dst, src);
+  DC_W2(0) DC_W2(1) DC_W2(2) DC_W2(3) DC_W2(4) DC_W2(5) DC_W2(6) DC_W2(7)
+#undef DC_W2
 }
 
 // producer warp: the whole chunk sequence of its compute warp, slot by slot (cp.async, 16 bytes per lane and copy; the
@@ -176,14 +177,14 @@ __device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab) {
     ++n;
     return sl;
   };
-  auto weights = [&](const void* W, int K, int row, int nchunks) {   // rows [row, row + 8), nchunks k-blocks of 256
+  auto weights = [&](const void* W, int K, int row, int nchunks) {   // rows [row, row + 8), nchunks k-blocks of 512
     const uint8_t* src = static_cast<const uint8_t*>(W) + (size_t)row * K * 2 + lane * 16;
 #pragma unroll 1
     for (int kp = 0; kp < nchunks; ++kp) {
       const uint32_t sl = slot_wait();
       const uint32_t dst = c.ring + sl * DC_SLOT + lane * 16;
-      if (K == DC_D) dc_issue_w<DC_D * 2>(dst, src + kp * 512);
-      else dc_issue_w<DC_DFF * 2>(dst, src + kp * 512);
+      if (K == DC_D) dc_issue_w<DC_D * 2>(dst, src + kp * 1024);
+      else dc_issue_w<DC_DFF * 2>(dst, src + kp * 1024);
       dc_cp_arrive(full0 + 8u * sl);
     }
   };
@@ -192,13 +193,13 @@ __device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab) {
     const MtnDecodeSite& d = tab.s[s];
     if (d.kind == 2) {
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) weights(d.w_in, DC_D, c.rank * 256 + (j * 8 + c.warp) * 8, 2);
-      weights(d.w_out, DC_DFF, c.rank * 64 + c.warp * 8, 8);
+      for (int j = 0; j < 4; ++j) weights(d.w_in, DC_D, c.rank * 256 + (j * 8 + c.warp) * 8, 1);
+      weights(d.w_out, DC_DFF, c.rank * 64 + c.warp * 8, 4);
       continue;
     }
     const int nin = d.kind == 0 ? 3 : 1;
 #pragma unroll 1
-    for (int pj = 0; pj < nin; ++pj) weights(d.w_in, DC_D, pj * DC_D + c.rank * 64 + c.warp * 8, 2);
+    for (int pj = 0; pj < nin; ++pj) weights(d.w_in, DC_D, pj * DC_D + c.rank * 64 + c.warp * 8, 1);
     const int Lk = dc_site_lk(c, d);
     const int nck = (Lk + 31) >> 5;
     const int nun = dc_units(c, Lk);
@@ -211,21 +212,17 @@ __device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab) {
       const int u = c.warp + 8 * j;
       const int g = u / nck, ck = u - g * nck;
       const uint8_t* base = static_cast<const uint8_t*>(d.k) + ((size_t)(c.row0 + g) * d.kv_batch_stride + c.rank * DC_DK + seg * 8) * 2;
-      const uint8_t* src[8];
+      const uint32_t sl = slot_wait();
+      const uint32_t dst = c.ring + sl * DC_SLOT + (lane >> 3) * DC_KPITCH + seg * 16;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) src[it] = base + (size_t)min(ck * 32 + 4 * it + (lane >> 3), Lk - 1) * d.ld_kv * 2;
-      uint32_t sl = slot_wait();
-      uint32_t dst = c.ring + sl * DC_SLOT + (lane >> 3) * DC_KPITCH + seg * 16;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) dc_cp16(dst + it * 4 * DC_KPITCH, src[it]);
-      dc_cp_arrive(full0 + 8u * sl);
-      sl = slot_wait();
-      dst = c.ring + sl * DC_SLOT + (lane >> 3) * DC_KPITCH + seg * 16;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) dc_cp16(dst + it * 4 * DC_KPITCH, src[it] + vdelta);
+      for (int it = 0; it < 8; ++it) {
+        const uint8_t* src = base + (size_t)min(ck * 32 + 4 * it + (lane >> 3), Lk - 1) * d.ld_kv * 2;
+        dc_cp16(dst + it * 4 * DC_KPITCH, src);
+        dc_cp16(dst + it * 4 * DC_KPITCH + DC_VOFF, src + vdelta);
+      }
       dc_cp_arrive(full0 + 8u * sl);
     }
-    weights(d.w_out, DC_D, c.rank * 64 + c.warp * 8, 2);
+    weights(d.w_out, DC_D, c.rank * 64 + c.warp * 8, 1);
   }
   dc_cp_wait_all();
 }
@@ -247,7 +244,7 @@ __device__ __forceinline__ void dc_release(const DcCtx& c, uint32_t& taken) {
 // lane / 4; W: output column lane / 4) with one 16-byte load each; both mma k16 steps use the same logical -> actual k
 // mapping for A and B (csrc/decode_rows.cu), so the products pair up.  Four independent accumulators.  Returns this
 // thread's two outputs: row lane / 4, columns 2 (lane % 4), + 1 of the group.
-template <int KCH>   // K = 256 * KCH
+template <int KCH>   // K = 512 * KCH
 __device__ __forceinline__ float2 dc_proj(const DcCtx& c, uint32_t& taken, uint32_t smem_base, int a_off, int lda) {
   const int g = c.lane >> 2, q = c.lane & 3;
   float acc[4][4];
@@ -255,13 +252,22 @@ __device__ __forceinline__ float2 dc_proj(const DcCtx& c, uint32_t& taken, uint3
   for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll 1
   for (int kp = 0; kp < KCH; ++kp) {
-    const uint32_t arow = smem_base + a_off + g * lda + (kp * 256 + 8 * q) * 2;
+    const uint32_t arow = smem_base + a_off + g * lda + (kp * 512 + 8 * q) * 2;
     uint4 a[8], w[8];
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) a[cc] = dc_lds128(arow + cc * 64);
     const uint32_t wrow = dc_acquire(c, taken) + g * DC_WPITCH + (q << 4);
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) w[cc] = dc_lds128(wrow + cc * 64);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      dc_mma(acc[cc & 3], a[cc].x, a[cc].y, w[cc].x, w[cc].y);
+      dc_mma(acc[cc & 3], a[cc].z, a[cc].w, w[cc].z, w[cc].w);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) a[cc] = dc_lds128(arow + 512 + cc * 64);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) w[cc] = dc_lds128(wrow + 512 + cc * 64);
     dc_release(c, taken);
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
         for (int j = 0; j < 4; ++j) {
           const int hc = (int)rank * 256 + (j * 8 + warp) * 8 + 2 * q;
           const float2 b1 = j == 0 ? bi[0] : __ldg(reinterpret_cast<const float2*>(d.b_in + hc));
-          const float2 y = dc_proj<2>(ctx, taken, sbase, DC_OFF_XN, DC_LDA);
+          const float2 y = dc_proj<1>(ctx, taken, sbase, DC_OFF_XN, DC_LDA);
           const uint32_t h2 = pack_f16x2_sat(fmaxf(y.x + b1.x, 0.f), fmaxf(y.y + b1.y, 0.f));
           if (g < nrows) {
             const uint32_t a = hid_s + g * DC_LDH + hc * 2;
@@ -443,7 +449,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
         if (threadIdx.x == 0) mbar_arrive_expect_tx(bars + 8u * DC_BAR_O, o_bytes);
 #pragma unroll 1
         for (int pj = 0; pj < nin; ++pj) {
-          const float2 y = dc_proj<2>(ctx, taken, sbase, DC_OFF_XN, DC_LDA);
+          const float2 y = dc_proj<1>(ctx, taken, sbase, DC_OFF_XN, DC_LDA);
           const float2 bb = pj == 0 ? bi[0] : (pj == 1 ? bi[1] : bi[2]);
           const uint32_t h2 = pack_f16x2_sat(y.x + bb.x, y.y + bb.y);
           if (g < nrows) {
@@ -484,7 +490,6 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
             uint4 kr[8];
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) kr[cc] = dc_lds128(ks + lane * DC_KPITCH + (cc << 4));
-            dc_release(ctx, taken);
             float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
@@ -512,10 +517,9 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
             m_run = m_new;
             const float pr = __half2float(__float2half_rn(e));   // P rounded to f16 before P V, like the tensor-core path
             // ---- P V: lane = two output dims; two independent partial sums per dim
-            const uint32_t vs = dc_acquire(ctx, taken);
             uint32_t vv[32];
 #pragma unroll
-            for (int uu = 0; uu < 32; ++uu) vv[uu] = dc_lds32(vs + uu * DC_KPITCH + lane * 4);
+            for (int uu = 0; uu < 32; ++uu) vv[uu] = dc_lds32(ks + DC_VOFF + uu * DC_KPITCH + lane * 4);
             dc_release(ctx, taken);
             float oa0 = o0 * alpha, oa1 = o1 * alpha, ob0 = 0.f, ob1 = 0.f;
 #pragma unroll
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
       // ---- output projection (attention: A = all heads' outputs; feed-forward: A = hidden activation) + residual
       if (threadIdx.x == 0) mbar_arrive_expect_tx(bars + 8u * DC_BAR_X, x_bytes);
       {
-        const float2 y = kind == 2 ? dc_proj<8>(ctx, taken, sbase, DC_OFF_HID, DC_LDH) : dc_proj<2>(ctx, taken, sbase, DC_OFF_OB, DC_LDA);
+        const float2 y = kind == 2 ? dc_proj<4>(ctx, taken, sbase, DC_OFF_HID, DC_LDH) : dc_proj<1>(ctx, taken, sbase, DC_OFF_OB, DC_LDA);
         if (g < nrows) {
           const float2 xo = *reinterpret_cast<const float2*>(xs + g * DC_D + col);
           const float x0 = xo.x + (y.x + bo.x), x1 = xo.y + (y.y + bo.y);

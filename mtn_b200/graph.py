@@ -138,11 +138,24 @@ class GraphedGreedyDecoder(object):
             prefill()
         self.graphs.append(g)
         pool = g.pool()
-        for t in range(2, max_len):
+        # cached decoding: ALL later positions in ONE graph (a step is a handful of launches -- embedding, the cluster
+        # kernel, generator + arg-max: a graph per step would pay a graph launch for each); full-prefix mode keeps one
+        # graph per position.  ``steps_in_graph[i]`` = positions graph i decodes.
+        self.steps_in_graph = [1]
+        if cached and max_len > 2 and os.environ.get("MTN_B200_DECODE_ONE_GRAPH", "1") != "0":
             g = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(g, pool=pool):
-                step(t)
+                for t in range(2, max_len):
+                    step(t)
             self.graphs.append(g)
+            self.steps_in_graph.append(max_len - 2)
+        else:
+            for t in range(2, max_len):
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g, pool=pool):
+                    step(t)
+                self.graphs.append(g)
+                self.steps_in_graph.append(1)
 
     def copy_inputs(self, inputs, non_blocking=True):
         for k, v in inputs.items():

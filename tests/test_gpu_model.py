@@ -361,6 +361,7 @@ def test_decode_step_program_equals_launch_sequence(M, cfg2_model, monkeypatch):
     mtn, du = M
     from mtn_b200.graph import GraphedGreedyDecoder
     cfg, model = cfg2_model
+    monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "0")      # (the default step is the cluster kernel: another summation order)
     for B in (64, 5):
         T = 20
         inp = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=T, Lv=[512, 256], seed=17 + B)
@@ -431,7 +432,8 @@ def test_decode_cluster_step_equals_launch_sequence(M, cfg2_model, monkeypatch):
                 ec = max(G.rel_err(c1[:, t].cpu(), c0[:, t].cpu()) for c0, c1 in zip(st0["cache"], st1["cache"]))
                 worst = [max(worst[0], G.rel_err(r1.cpu(), r0.cpu())), max(worst[1], es), max(worst[2], ec)]
         print("decode cluster step vs launch sequence, B=%d: rows %.2e, worst sublayer %.2e, cache rows %.2e" % (B, *worst))
-        assert worst[0] < 2e-4 and worst[1] < 2e-4 and worst[2] < 1e-3, (B, worst)
+        # (two schedules of the same f16-operand arithmetic: the bar of test_kv_cached_decode_equals_full_prefix)
+        assert worst[0] < 5e-4 and worst[1] < 5e-4 and worst[2] < 1e-3, (B, worst)
     from mtn_b200.engine import invalidate_weight_caches
     w0 = model.generator.proj.weight.data.clone()
     model.generator.proj.weight.data.mul_(8.0)
@@ -441,16 +443,42 @@ def test_decode_cluster_step_equals_launch_sequence(M, cfg2_model, monkeypatch):
         inp = O.synth_inputs(cfg, B=B, Q=64, C=64, H=256, T=4, Lv=[512, 256], seed=401)
         d = {k: (v.cuda() if torch.is_tensor(v) else [f.cuda() for f in v]) for k, v in inp.items()
              if k in ("query", "his", "cap", "fts")}
-        ys = {}
-        for mode in ("0", "1"):
-            monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", mode)
-            dec = GraphedGreedyDecoder(model, d, T, cached=True)
-            ys[mode] = dec.decode().clone()
-            ys[mode + "b"] = dec.decode().clone()      # a second replay of the same graphs
-            torch.cuda.synchronize()
-        nbad = int((ys["0"] != ys["1"]).any(1).sum())
-        print("graphed greedy decoding, cluster step vs launch sequence: %d of %d sequences differ" % (nbad, B))
-        assert nbad == 0 and torch.equal(ys["1"], ys["1b"])
+        # (1) both schedules decode the SAME prefix in lockstep (the launch sequence's greedy tokens): their arg-max tokens
+        # agree at every position of every dialogue, except where the two best log-probabilities are a near-tie
+        b = du.Batch(d["query"], d["his"], None, [f.permute(1, 0, 2) for f in d["fts"]], d["cap"], None, None, 1)
+        with torch.no_grad():
+            q, vid, cap, his, ae = model.encode(b.query, b.query_mask, b.his, b.his_mask, b.cap, b.cap_mask, b.fts, b.fts_mask)
+            monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "0")
+            st0 = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae, T)
+            monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "1")
+            st1 = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae, T)
+            tok = torch.full((B,), 2, dtype=torch.int64, device="cuda")
+            ndiff, worst_margin = 0, 0.0
+            for t in range(T - 1):
+                monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "0")
+                lp0 = model.generator(model.decode_step(st0, tok, t)).float().clone()
+                monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "1")
+                lp1 = model.generator(model.decode_step(st1, tok, t)).float().clone()
+                a0, a1 = lp0.argmax(-1), lp1.argmax(-1)
+                bad = a0 != a1
+                if bool(bad.any()):
+                    top2 = lp0.topk(2, dim=-1).values
+                    ndiff += int(bad.sum())
+                    worst_margin = max(worst_margin, float((top2[:, 0] - top2[:, 1])[bad].max()))
+                tok = a0
+        print("greedy arg-max, cluster step vs launch sequence on the same prefixes: %d of %d decisions differ, widest margin "
+              "among them %.2e (log-probability)" % (ndiff, B * (T - 1), worst_margin))
+        assert ndiff <= 0.005 * B * (T - 1) and worst_margin < 2e-2, (ndiff, worst_margin)
+        # (2) the graphed decoder on the cluster step: replays are deterministic and equal to eager cached greedy decoding
+        monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "1")
+        dec = GraphedGreedyDecoder(model, d, T, cached=True)
+        y1 = dec.decode().clone()
+        y1b = dec.decode().clone()
+        with torch.no_grad():
+            y_e = du.greedy_decode(model, b, T, 2, cached=True)
+        torch.cuda.synchronize()
+        assert len(dec.graphs) == 2 and dec.steps_in_graph == [1, T - 2]       # prefill + ONE graph for all later positions
+        assert torch.equal(y1, y1b) and torch.equal(y1, y_e)
     finally:
         model.generator.proj.weight.data.copy_(w0)
         invalidate_weight_caches()

@@ -118,7 +118,7 @@ def main():
                     gph.replay()
             ev[1].record()
             torch.cuda.synchronize()
-            us = ev[0].elapsed_time(ev[1]) / 10 / max(1, len(dec.graphs) - 1) * 1e3
+            us = ev[0].elapsed_time(ev[1]) / 10 / max(1, sum(dec.steps_in_graph[1:])) * 1e3
             print("cluster=%s: %.3f ms per batch of %d dialogues x %d tokens = %.1f k tokens/s; %.1f us per cached step" %
                   (mode, ms, B, T, B * T / ms, us))
         print("tokens equal: %s (%d of %d sequences differ)" % (bool(torch.equal(ys["0"], ys["1"])),
