@@ -282,6 +282,11 @@ typedef struct MtnDecodeClusterArgs {
   const float *norm_a; const float *norm_b; float norm_eps;
   float *taps;
   long long *stamps;   /* optional debug output [n_sites, 8]: clock64 at the phase boundaries of every sublayer (CTA 0) or NULL */
+  /* optional last stage in the same kernel (greedy decoding, data_utils.py:180-184): tokens[r * tokens_stride] =
+   * argmax_v (out[r] . gen_w[v] + gen_b[v]), v < gen_V (first maximal index) -- Generator.forward (mtn.py:68-69) followed by
+   * the arg-max; gen_w: f16 [gen_V8, d] (rows >= gen_V zero, gen_V8 a multiple of 8), gen_b: [gen_V8].  gen_w NULL: off. */
+  const void *gen_w; const float *gen_b; int gen_V, gen_V8;
+  int64_t *tokens; long long tokens_stride;
 } MtnDecodeClusterArgs;
 int mtn_decode_cluster_supported(int B, int d, int h, int d_ff);
 int mtn_decode_cluster_max_sites(void);

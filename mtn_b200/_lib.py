@@ -148,7 +148,9 @@ class DecodeClusterArgs(C.Structure):
                 ("B", C.c_int), ("d", C.c_int), ("h", C.c_int), ("d_ff", C.c_int), ("t", C.c_int),
                 ("x_in", C.c_void_p), ("out", C.c_void_p),
                 ("norm_a", C.c_void_p), ("norm_b", C.c_void_p), ("norm_eps", C.c_float),
-                ("taps", C.c_void_p), ("stamps", C.c_void_p)]
+                ("taps", C.c_void_p), ("stamps", C.c_void_p),
+                ("gen_w", C.c_void_p), ("gen_b", C.c_void_p), ("gen_V", C.c_int), ("gen_V8", C.c_int),
+                ("tokens", C.c_void_p), ("tokens_stride", C.c_longlong)]
 
 
 # every symbol include/mtn_b200.h declares: name -> (restype, argtypes)
@@ -651,8 +653,10 @@ class DecodeClusterPlan(object):
         self.keep += [norm[0], norm[1]]
         return self
 
-    def step(self, t, x_in, out, taps=None, stamps=None):
-        """One position: x_in [B, d] f32 -> out [B, d] f32 (Decoder.norm applied); cache rows t are written."""
+    def step(self, t, x_in, out, taps=None, stamps=None, gen=None, tokens=None):
+        """One position: x_in [B, d] f32 -> out [B, d] f32 (Decoder.norm applied); cache rows t are written.
+        gen = (w f16 [V8, d], b f32 [V8], V) + tokens (int64 [B], any stride): the arg-max of the generator's logits of the
+        output rows is taken in the same kernel (greedy decoding)."""
         _req(x_in, torch.float32, "x_in"); _req(out, torch.float32, "out")
         assert tuple(x_in.shape) == (self.B, self.d) and tuple(out.shape) == (self.B, self.d)
         assert x_in.is_contiguous() and out.is_contiguous()
@@ -668,8 +672,15 @@ class DecodeClusterPlan(object):
         if stamps is not None:
             assert stamps.dtype == torch.int64 and stamps.is_cuda and stamps.numel() >= 8 * len(self.sites)
             a.stamps = stamps.data_ptr()
+        if gen is not None:
+            gw, gb, V = gen
+            _req(gw, torch.float16, "gen_w"); _req(gb, torch.float32, "gen_b")
+            assert gw.is_contiguous() and gw.shape[1] == self.d and gw.shape[0] % 8 == 0 and gb.numel() == gw.shape[0] >= V
+            assert tokens is not None and tokens.dtype == torch.int64 and tokens.is_cuda and tokens.dim() == 1 and tokens.numel() == self.B
+            a.gen_w, a.gen_b, a.gen_V, a.gen_V8 = gw.data_ptr(), gb.data_ptr(), int(V), gw.shape[0]
+            a.tokens, a.tokens_stride = tokens.data_ptr(), tokens.stride(0)
         _launch("decode_cluster", 0, 0, lambda: lib().mtn_decode_cluster_fwd(C.byref(a), stream_ptr()),
-                keep=(self, x_in, out, taps, stamps))
+                keep=(self, x_in, out, taps, stamps, gen, tokens))
 
 
 def ffn_fused_supported(rows, d, d_ff):

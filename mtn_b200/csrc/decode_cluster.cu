@@ -6,23 +6,35 @@
 // round trips) per stage instead and is no faster.  But the dependency chain of a decoding step is PER DIALOGUE: nothing
 // in DecoderLayer.forward (mtn.py:181-218) mixes dialogues.  So a cluster of 8 CTAs takes G = ceil(B / #clusters)
 // dialogues through the whole N-layer step; CTA `rank` owns head `rank` (d_k = 64) and the matching 64 output columns of
-// every projection (256 of the feed-forward hidden layer), and the only synchronisation is the hardware cluster barrier:
+// every projection (256 of the feed-forward hidden layer), and nothing in the step synchronises wider than the cluster:
 //
 //   per attention sublayer (mtn.py:125-127 around :248-267 around :221-231)
 //     LayerNorm of the G residual rows (every CTA holds the full rows, f32, in shared memory)
 //     q (self: q, k, v) of head `rank`:  mma.sync over the CTA's 64 weight rows (8 per warp)
 //     attention of head `rank`: the static memory's K / V (or the self-attention cache rows 0..t-1 plus the new row,
 //       which is also appended to the cache), online softmax in the log2 domain with the reference's FINITE -1e9
-//     the head's output -> every CTA of the cluster (st.shared::cluster), cluster barrier
-//     output projection of the CTA's 64 columns + residual -> every CTA's copy of the rows, cluster barrier
-//   feed-forward sublayer (mtn.py:279-280): LayerNorm, w_1 + ReLU (256 hidden columns per CTA) -> every CTA, barrier,
-//     w_2 (64 columns, K = 2048) + residual -> every CTA, barrier.
+//     the head's output -> every CTA of the cluster (st.async into distributed shared memory)
+//     output projection of the CTA's 64 columns + residual -> every CTA's copy of the rows (st.async)
+//   feed-forward sublayer (mtn.py:279-280): LayerNorm, w_1 + ReLU (256 hidden columns per CTA) -> every CTA,
+//     w_2 (64 columns, K = 2048) + residual -> every CTA
+//   last: Decoder.norm (mtn.py:164) and, for greedy decoding, the generator's projection + arg-max (mtn.py:68-69,
+//     data_utils.py:183) over vocabulary slices, the per-CTA winners gathered in CTA 0.
 //
-// Everything a CTA reads from global memory inside the step -- its weight rows and its head's K / V rows -- has an
-// address that does not depend on computed data, so each WARP streams its own operands through a private ring of
-// cp.async buffers (4 x 4 KB), running up to three chunks ahead ACROSS sublayer boundaries: the weights of the next
-// sublayer arrive while the current one waits at its barriers.  No kernel boundary, no grid barrier, no exposed memory
-// round trip on the chain; HBM sees each K / V byte once, the f16 weights (72 MB) come out of L2 once per cluster.
+// EXCHANGES.  A value another CTA needs is stored straight into that CTA's shared memory with st.async, which completes
+// its bytes on an mbarrier of the RECEIVER; the receiver arms the barrier with the byte count of the exchange (8 CTAs x
+// its rows x 64 columns) and waits on it -- no fence, no cluster barrier inside the step (a barrier.cluster.arrive.release
+// costs ~1300 cycles here, the st.async hand-off ~400).  Single buffers suffice: a CTA can only send sublayer s + 1 data
+// after it has received every CTA's sublayer-s data, i.e. after every reader of the old contents is done.
+//
+// OPERAND STREAM.  Everything a CTA reads from global memory inside the step -- its weight rows and its head's K / V rows
+// -- has an address that does not depend on computed data.  Warps 8..15 are PRODUCERS: producer w walks the chunk sequence
+// of compute warp w (weight chunk = the 8 rows x 512 k of one projection job; attention-unit chunk = 32 keys of K and of
+// V) and copies it with cp.async (16 bytes per lane: full 128-byte lines per row) into a two-slot ring, the slot's FULL
+// mbarrier collecting the copies' completions; it runs ahead ACROSS sublayer boundaries and while the compute warp waits
+// for the cluster.  Measured alternatives: the compute warps issuing their own cp.async (the address
+// arithmetic lands on the dependency chain), bulk copies (one per row: serialised by the hardware's one-lane-at-a-time
+// issue), four smaller slots (per-chunk hand-off costs more than the deeper look-ahead returns), operands prefetched
+// straight into registers (64-byte requests: the L1 request rate, not bandwidth, becomes the bound).
 //
 // Arithmetic = the few-row kernels' (f16 operands, f32 accumulate, f16-rounded q / k / v / P / O / hidden, LayerNorm
 // with the summation order of layernorm_rows_kernel); only the summation order of the projections differs (one warp
@@ -70,8 +82,9 @@ static_assert(DC_CWARPS * DC_G * DC_DK * 4 <= DC_G * DC_LDH, "partial outputs fi
 // mbarriers: FULL / EMPTY per (compute warp, ring slot); O / X / H: the cluster-wide exchanges (attention outputs,
 // residual rows, hidden activation) complete their bytes on the RECEIVER's barrier
 constexpr int DC_BAR_FULL = 0, DC_BAR_EMPTY = DC_CWARPS * DC_NSLOT, DC_BAR_O = 2 * DC_CWARPS * DC_NSLOT, DC_BAR_X = DC_BAR_O + 1,
-              DC_BAR_H = DC_BAR_O + 2, DC_BAR_COUNT = DC_BAR_O + 3;
-static_assert(DC_BAR_COUNT * 8 <= 1024, "barrier area");
+              DC_BAR_H = DC_BAR_O + 2, DC_BAR_G = DC_BAR_O + 3, DC_BAR_COUNT = DC_BAR_O + 4;
+constexpr int DC_OFF_GBUF = DC_OFF_BAR + 512;   // u64 [8 CTAs][8 rows]: every CTA's best (logit, column) per row, gathered in CTA 0
+static_assert(DC_BAR_COUNT * 8 <= 512, "barrier area");
 
 struct DcTable {
   MtnDecodeSite s[DC_MAX_SITES];
@@ -86,6 +99,12 @@ struct DcParams {
   float norm_eps;
   float* taps;
   long long* stamps;   // optional [n_sites][8] clock64 stamps of CTA 0, thread 0 (debug: where a sublayer spends its time)
+  // optional last stage: arg-max of the generator's logits (mtn.py:62-69 + data_utils.py:183) of the output rows
+  const __half* gen_w;       // [gen_V8, 512] f16, rows >= gen_V zero
+  const float* gen_b;        // [gen_V8]
+  int gen_V, gen_V8;
+  long long* tokens;         // token of row r -> tokens[r * tokens_stride]
+  long long tokens_stride;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -167,7 +186,7 @@ __device__ __forceinline__ void dc_issue_w(uint32_t dst, const uint8_t* src) {
 
 // producer warp: the whole chunk sequence of its compute warp, slot by slot (cp.async, 16 bytes per lane and copy; the
 // slot's FULL barrier collects one deferred arrival per lane)
-__device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab) {
+__device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab, const void* gen_w, int gen_groups) {
   uint32_t n = 0;
   const int lane = c.lane;
   const uint32_t full0 = c.bars + 8u * (DC_BAR_FULL + c.warp * DC_NSLOT), empty0 = c.bars + 8u * (DC_BAR_EMPTY + c.warp * DC_NSLOT);
@@ -224,6 +243,8 @@ __device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab) {
     }
     weights(d.w_out, DC_D, c.rank * 64 + c.warp * 8, 1);
   }
+  if (gen_w != nullptr)   // generator arg-max: 8-row groups of the vocabulary, group index = rank + 8 (warp + 8 i)
+    for (int gi = c.rank + 8 * c.warp; gi < gen_groups; gi += 64) weights(gen_w, DC_D, gi * 8, 1);
   dc_cp_wait_all();
 }
 
@@ -350,6 +371,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
     mbar_init(bars + 8u * DC_BAR_O, 1u);
     mbar_init(bars + 8u * DC_BAR_X, 1u);
     mbar_init(bars + 8u * DC_BAR_H, 1u);
+    mbar_init(bars + 8u * DC_BAR_G, 1u);
     mbar_fence_init();
   }
   {
@@ -376,7 +398,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
   ctx.bars = bars;
 
   if (warp >= DC_CWARPS) {
-    dc_produce(ctx, tab);
+    dc_produce(ctx, tab, p.gen_w, p.gen_V8 >> 3);
   } else {
     uint32_t taken = 0;
     const int col = (int)rank * 64 + warp * 8 + 2 * q;   // this thread's output columns of a d-wide projection
@@ -613,13 +635,65 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
         for (int i = 0; i < 4; ++i) tp[lane + 32 * i] = reinterpret_cast<const float4*>(xs + warp * DC_D)[lane + 32 * i];
       }
     }
-    // ---- final LayerNorm (mtn.py:164) -> out
-    if (rank == 0 && warp < nrows) {
+    // ---- final LayerNorm (mtn.py:164) -> out (CTA 0) and, for the generator stage, the f16 A operand (every CTA)
+    {
       float4 o[4];
       dc_ln_row(xs + warp * DC_D, ln, lane, o);
-      float4* op = reinterpret_cast<float4*>(p.out + (size_t)(row0 + warp) * DC_D);
+      if (rank == 0 && warp < nrows) {
+        float4* op = reinterpret_cast<float4*>(p.out + (size_t)(row0 + warp) * DC_D);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) op[lane + 32 * i] = o[i];
+        for (int i = 0; i < 4; ++i) op[lane + 32 * i] = o[i];
+      }
+      uint8_t* xr = smem + DC_OFF_XN + warp * DC_LDA;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint2*>(xr)[lane + 32 * i] = make_uint2(pack_f16x2_sat(o[i].x, o[i].y), pack_f16x2_sat(o[i].z, o[i].w));
+    }
+    if (p.gen_w != nullptr) {
+      // ---- generator arg-max (Generator.forward mtn.py:68-69 + the arg-max of data_utils.py:183: log_softmax is monotone,
+      // so the arg-max of the logits): vocabulary groups of 8 dealt over the cluster's 64 warps; a key packs (orderable
+      // logit, ~column) so that the maximum key is the largest logit, the FIRST column among equal ones (torch.argmax)
+      dc_cbar();
+      if (rank == 0 && threadIdx.x == 0) mbar_arrive_expect_tx(bars + 8u * DC_BAR_G, (uint32_t)(DC_CS * nrows * 8));
+      unsigned long long best = 0ull;
+      auto key_of = [](float v, int colx) -> unsigned long long {
+        uint32_t u = __float_as_uint(v);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // monotone map f32 -> u32
+        return ((unsigned long long)u << 32) | (uint32_t)(0x7fffffff - colx);
+      };
+      const int ngroups = p.gen_V8 >> 3;
+#pragma unroll 1
+      for (int gi = (int)rank + 8 * warp; gi < ngroups; gi += 64) {
+        const int c0 = gi * 8 + 2 * q;
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(p.gen_b + c0));
+        const float2 y = dc_proj<1>(ctx, taken, sbase, DC_OFF_XN, DC_LDA);
+        if (c0 < p.gen_V) best = max(best, key_of(y.x + bb.x, c0));
+        if (c0 + 1 < p.gen_V) best = max(best, key_of(y.y + bb.y, c0 + 1));
+      }
+      best = max(best, __shfl_xor_sync(0xffffffffu, best, 1));
+      best = max(best, __shfl_xor_sync(0xffffffffu, best, 2));
+      unsigned long long* wbest = reinterpret_cast<unsigned long long*>(smem + DC_OFF_PM);   // [8 warps][8 rows] (pm / pl are dead)
+      if (q == 0) wbest[warp * DC_G + g] = best;
+      dc_cbar();
+      if (threadIdx.x < nrows) {
+        unsigned long long b8 = 0ull;
+#pragma unroll
+        for (int w = 0; w < DC_CWARPS; ++w) b8 = max(b8, wbest[w * DC_G + threadIdx.x]);
+        const uint32_t a = sbase + DC_OFF_GBUF + ((int)rank * DC_G + threadIdx.x) * 8;
+        asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u64 [%0], %1, [%2];" ::"r"(dc_mapa(a, 0)), "l"(b8),
+                     "r"(dc_mapa(bars + 8u * DC_BAR_G, 0))
+                     : "memory");
+      }
+      if (rank == 0) {
+        mbar_wait(bars + 8u * DC_BAR_G, 0u);
+        if (threadIdx.x < nrows) {
+          const unsigned long long* gb = reinterpret_cast<const unsigned long long*>(smem + DC_OFF_GBUF);
+          unsigned long long b8 = 0ull;
+#pragma unroll
+          for (int r = 0; r < DC_CS; ++r) b8 = max(b8, gb[r * DC_G + threadIdx.x]);
+          p.tokens[(size_t)(row0 + threadIdx.x) * p.tokens_stride] = (long long)(0x7fffffff - (int)(uint32_t)(b8 & 0xffffffffu));
+        }
+      }
     }
   }
   __syncthreads();
@@ -667,6 +741,12 @@ extern "C" int mtn_decode_cluster_fwd(const MtnDecodeClusterArgs* a, void* strea
               DC_MAX_SITES, a->t);
   MTN_REQUIRE(aligned16(a->x_in) && aligned16(a->out) && aligned16(a->norm_a) && aligned16(a->norm_b) && (!a->taps || aligned16(a->taps)),
               MTN_E_ALIGN, "decode_cluster: x_in / out / norm / taps must be 16-byte aligned");
+  if (a->gen_w != nullptr) {
+    MTN_REQUIRE(a->gen_b && a->tokens && a->gen_V >= 1 && a->gen_V8 >= a->gen_V && a->gen_V8 % 8 == 0 && a->tokens_stride >= 1, MTN_E_ARG,
+                "decode_cluster: generator stage: bias / tokens NULL or V=%d V8=%d stride=%lld", a->gen_V, a->gen_V8, a->tokens_stride);
+    MTN_REQUIRE(aligned16(a->gen_w) && (reinterpret_cast<uintptr_t>(a->gen_b) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->tokens) & 7) == 0,
+                MTN_E_ALIGN, "decode_cluster: generator stage: alignment");
+  }
   DcTable tab;
   memset(&tab, 0, sizeof(tab));
   for (int s = 0; s < a->n_sites; ++s) {
@@ -697,7 +777,8 @@ extern "C" int mtn_decode_cluster_fwd(const MtnDecodeClusterArgs* a, void* strea
   const int G = (a->B + max_clusters - 1) / max_clusters;
   MTN_REQUIRE(G <= DC_G, MTN_E_SHAPE, "decode_cluster: B=%d needs %d rows per cluster (%d clusters fit), at most %d", a->B, G, max_clusters, DC_G);
   const int nclusters = (a->B + G - 1) / G;
-  DcParams p{a->n_sites, a->B, G, a->t, a->x_in, a->out, a->norm_a, a->norm_b, a->norm_eps, a->taps, a->stamps};
+  DcParams p{a->n_sites, a->B, G, a->t, a->x_in, a->out, a->norm_a, a->norm_b, a->norm_eps, a->taps, a->stamps,
+             static_cast<const __half*>(a->gen_w), a->gen_b, a->gen_V, a->gen_V8, reinterpret_cast<long long*>(a->tokens), a->tokens_stride};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MTN_CHECK_CUDA(launch_kernel_cluster(decode_cluster_kernel, dim3(nclusters * DC_CS), dim3(DC_THREADS), DC_SMEM, st, DC_CS, tab, p));
   return MTN_OK;

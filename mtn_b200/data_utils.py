@@ -171,8 +171,10 @@ def greedy_decode(model, batch, max_len, start_symbol, pad_symbol=None, cached=N
                                 batch.query_mask, ae_ft, max_len)
         ys = torch.full((B, max_len), start_symbol, dtype=batch.query.dtype, device=batch.query.device)
         for t in range(max_len - 1):
-            last = model.decode_step(st, ys[:, t], t)
-            ys[:, t + 1] = model.generator.argmax(last)
+            if hasattr(model, "decode_step_argmax"):
+                model.decode_step_argmax(st, ys[:, t], t, out=ys[:, t + 1])
+            else:
+                ys[:, t + 1] = model.generator.argmax(model.decode_step(st, ys[:, t], t))
         return ys
     ys = torch.full((B, 1), start_symbol, dtype=batch.query.dtype, device=batch.query.device)
     for _ in range(max_len - 1):

@@ -515,21 +515,23 @@ class DecoderEngine(object):
                 "q": torch.empty(B, d, dtype=f16, device=dev), "obuf": torch.empty(B, d, dtype=f16, device=dev),
                 "hid": torch.empty(B, dff, dtype=f16, device=dev), "out": torch.empty(B, d, dtype=torch.float32, device=dev)}
 
-    def decode_step(self, st, x_t, t=None):
+    def decode_step(self, st, x_t, t=None, generator=None, tokens_out=None):
         """One target position for every dialogue of the batch: x_t [B, d] f32 = embedding (+ positional encoding) of the
         token at position t (default: the next one).  Returns the decoder output row [B, d] (final LayerNorm applied;
-        a buffer of `st`, overwritten by the next step).  Per layer: LayerNorm -> [Q|K|V] projection of the ONE new row
+        a buffer of `st`, overwritten by the next step) -- or, when ``generator`` (mtn.Generator) and ``tokens_out`` (int64
+        [B]) are given AND the step runs as the cluster kernel, ``tokens_out`` filled with the arg-max tokens (the caller
+        checks ``result is tokens_out``).  Per layer: LayerNorm -> [Q|K|V] projection of the ONE new row
         straight into the cache -> attention of that row over cache rows 0..t (no mask needed: every cached key is in
         the causal past) -> output projection + residual; then the cross sites with a 1-row query over the hoisted
         K/V of the memory stage; then the FFN.  M = B rows per GEMM instead of B*(t+1)."""
         prev_rows = _lib.ROWS_KERNELS
         _lib.ROWS_KERNELS = os.environ.get("MTN_B200_DECODE_ROWS", "1") != "0"      # few-row kernels (csrc/decode_rows.cu)
         try:
-            return self._decode_step(st, x_t, t)
+            return self._decode_step(st, x_t, t, generator, tokens_out)
         finally:
             _lib.ROWS_KERNELS = prev_rows
 
-    def _decode_step(self, st, x_t, t):
+    def _decode_step(self, st, x_t, t, generator=None, tokens_out=None):
         B, d = st["B"], st["W"]["d"]
         t = st["t"] if t is None else int(t)
         assert 0 <= t < st["max_len"], "decode_step: position %d outside the cache (max_len %d)" % (t, st["max_len"])
@@ -539,9 +541,14 @@ class DecoderEngine(object):
             x = x_t.reshape(B, d)
             if x.dtype != torch.float32 or not x.is_contiguous():
                 x = st["xs"].copy_(x)
-            plan.step(t, x, st["out"], taps=st.get("cluster_taps"), stamps=st.get("cluster_stamps"))
+            gen = None
+            if generator is not None and tokens_out is not None and os.environ.get("MTN_B200_DECODE_ARGMAX_FUSED", "1") != "0":
+                G = generator.packed()           # greedy decoding: generator projection + arg-max as the kernel's last stage
+                gen = (G["w"], G["b"], generator.proj.weight.shape[0])
+            plan.step(t, x, st["out"], taps=st.get("cluster_taps"), stamps=st.get("cluster_stamps"), gen=gen,
+                      tokens=tokens_out if gen is not None else None)
             st["t"] = t + 1
-            return st["out"]
+            return tokens_out if gen is not None else st["out"]
         st["xs"].copy_(x_t.reshape(B, d))
         prog = self._step_program(st, t)
         if prog is not None:

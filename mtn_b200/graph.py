@@ -108,7 +108,7 @@ class GraphedGreedyDecoder(object):
             q, vid, cap, his, ae = self.mem
             b = self.b
             if cached:
-                self.ys[:, t] = model.generator.argmax(model.decode_step(self.state, self.ys[:, t - 1], t - 1))
+                model.decode_step_argmax(self.state, self.ys[:, t - 1], t - 1, out=self.ys[:, t])
                 return
             out = model.decode(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask,
                                self.ys[:, :t], masks[t], ae)

@@ -388,7 +388,9 @@ class Generator(nn.Module):
         self.proj = nn.Linear(d_model, vocab)
         self._packed = PackedWeights()
 
-    def _logits(self, x, log_probs=False):
+    def packed(self):
+        """{"w": f16 [V8, d] (vocabulary padded to a multiple of 8 rows, padding rows zero), "b": f32 [V8]}, rebuilt when
+        the projection's parameters change."""
         V, d = self.proj.weight.shape
         V8 = (V + 7) // 8 * 8
 
@@ -398,7 +400,12 @@ class Generator(nn.Module):
             b = torch.zeros(V8, dtype=torch.float32, device=w.device)
             b[:V] = self.proj.bias.data
             return {"w": _lib.cast_f16(w), "b": b}
-        W = self._packed.get(list(self.proj.parameters()), build)
+        return self._packed.get(list(self.proj.parameters()), build)
+
+    def _logits(self, x, log_probs=False):
+        V, d = self.proj.weight.shape
+        V8 = (V + 7) // 8 * 8
+        W = self.packed()
         if AG.recording(self, x):       # training: projection (+ log-softmax) with its backward kernels
             return AG.ProjectFn.apply(x, self.proj.weight, self.proj.bias, W["w"], W["b"], V, log_probs), V
         x16 = _lib.cast_f16(x.contiguous().float().view(-1, d))
@@ -606,6 +613,22 @@ class EncoderDecoder(nn.Module):
         x = torch.empty(B, 1, emb.d_model, dtype=torch.float32, device=tokens.device)
         _lib.embed(tokens.reshape(B, 1), emb.lut.weight.data, pos.pe[0][t:], math.sqrt(emb.d_model), out_f32=x)
         return self.decoder.engine.decode_step(state, x, t)
+
+    def decode_step_argmax(self, state, tokens, t=None, out=None):
+        """Greedy decoding's step (data_utils.py:180-184): ``generator.argmax(decode_step(state, tokens, t))`` -> int64 [B]
+        (written into ``out`` when given; any stride).  Where the step runs as the cluster kernel (csrc/decode_cluster.cu)
+        the generator's projection and the arg-max are its last stage: the whole position is embedding + ONE kernel."""
+        t = state["t"] if t is None else int(t)
+        emb, pos = self.tgt_embed[0], self.tgt_embed[1]
+        B = tokens.shape[0]
+        x = torch.empty(B, 1, emb.d_model, dtype=torch.float32, device=tokens.device)
+        _lib.embed(tokens.reshape(B, 1), emb.lut.weight.data, pos.pe[0][t:], math.sqrt(emb.d_model), out_f32=x)
+        if out is None:
+            out = torch.empty(B, dtype=torch.int64, device=tokens.device)
+        res = self.decoder.engine.decode_step(state, x, t, generator=self.generator, tokens_out=out)
+        if res is not out:                       # (launch-sequence step: the generator runs on its own kernels)
+            out.copy_(self.generator.argmax(res))
+        return out
 
 
 def make_model(src_vocab, tgt_vocab, N=6, d_model=512, d_ff=2048, h=8, dropout=0.1,

@@ -479,6 +479,14 @@ def test_decode_cluster_step_equals_launch_sequence(M, cfg2_model, monkeypatch):
         torch.cuda.synchronize()
         assert len(dec.graphs) == 2 and dec.steps_in_graph == [1, T - 2]       # prefill + ONE graph for all later positions
         assert torch.equal(y1, y1b) and torch.equal(y1, y_e)
+        # (3) the generator's projection + arg-max as the kernel's last stage vs the stand-alone generator kernels
+        monkeypatch.setenv("MTN_B200_DECODE_ARGMAX_FUSED", "0")
+        with torch.no_grad():
+            y_u = du.greedy_decode(model, b, T, 2, cached=True)
+        monkeypatch.delenv("MTN_B200_DECODE_ARGMAX_FUSED")
+        nbad = int((y_u != y_e).any(1).sum())
+        print("greedy tokens, arg-max inside the cluster kernel vs generator kernels: %d of %d sequences differ" % (nbad, B))
+        assert nbad == 0 and int(y_e.min()) >= 0 and int(y_e.max()) < cfg["vocab"]
     finally:
         model.generator.proj.weight.data.copy_(w0)
         invalidate_weight_caches()

@@ -26,9 +26,9 @@ with torch.no_grad():
     st = model.decode_begin(vid, his, cap, q, b.fts_mask, b.his_mask, b.cap_mask, b.query_mask, ae, 20)
     tok = torch.full((64,), 2, dtype=torch.int64, device="cuda")
     for t in range(10):
-        tok = model.generator.argmax(model.decode_step(st, tok, t))
+        tok = model.decode_step_argmax(st, tok, t)       # greedy decoding's step: embedding + the cluster kernel
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    tok = model.generator.argmax(model.decode_step(st, tok, 10))
+    tok = model.decode_step_argmax(st, tok, 10)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
