@@ -258,7 +258,7 @@ int mtn_prog_launch(const void *dev_prog, int n_stages, void *counter, void *str
  *           position's [Q|K|V] is written to cache row t; keys / values are cache rows 0..t (no mask: causal past).
  *   kind 1  cross-attention: w_in = Wq f16 [d, d], b_in [d];  k / v = head 0 of key 0 of dialogue 0 (f16, row pitch
  *           ld_kv, dialogue pitch kv_batch_stride, Lk keys);  mask_bits: bit-packed key mask (mtn_mask_pack) with ONE
- *           query row per dialogue, [B, mask_words] words, or NULL.  Masked scores take the reference's finite -1e9.
+ *           query row per dialogue, [D, mask_words] words (D = B / rows_per_dialogue), or NULL.  Masked scores take the reference's finite -1e9.
  *   kind 2  feed-forward:    w_in = w_1 f16 [d_ff, d], b_in [d_ff];  w_out = w_2 f16 [d, d_ff], b_out [d].
  * Attention sites: w_out = Wo f16 [d, d], b_out [d].  All weights contiguous (row pitch = their K).
  * `sites` is a HOST array (copied into the kernel's parameter space: graph-capturable, nothing to upload);
@@ -287,6 +287,10 @@ typedef struct MtnDecodeClusterArgs {
    * the arg-max; gen_w: f16 [gen_V8, d] (rows >= gen_V zero, gen_V8 a multiple of 8), gen_b: [gen_V8].  gen_w NULL: off. */
   const void *gen_w; const float *gen_b; int gen_V, gen_V8;
   int64_t *tokens; long long tokens_stride;
+  /* beam search: R = rows_per_dialogue consecutive target rows are the hypotheses of ONE dialogue (B = D * R): the
+   * cross-attention sites' K / V and mask of row r are those of dialogue r / R (the memory stage is stored once per
+   * dialogue); the self-attention caches stay per row.  0 or 1: one row per dialogue.                              */
+  int rows_per_dialogue;
 } MtnDecodeClusterArgs;
 int mtn_decode_cluster_supported(int B, int d, int h, int d_ff);
 int mtn_decode_cluster_max_sites(void);

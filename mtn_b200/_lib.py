@@ -150,7 +150,7 @@ class DecodeClusterArgs(C.Structure):
                 ("norm_a", C.c_void_p), ("norm_b", C.c_void_p), ("norm_eps", C.c_float),
                 ("taps", C.c_void_p), ("stamps", C.c_void_p),
                 ("gen_w", C.c_void_p), ("gen_b", C.c_void_p), ("gen_V", C.c_int), ("gen_V8", C.c_int),
-                ("tokens", C.c_void_p), ("tokens_stride", C.c_longlong)]
+                ("tokens", C.c_void_p), ("tokens_stride", C.c_longlong), ("rows_per_dialogue", C.c_int)]
 
 
 # every symbol include/mtn_b200.h declares: name -> (restype, argtypes)
@@ -596,8 +596,11 @@ class DecodeClusterPlan(object):
     host-side ``MtnDecodeSite`` array (passed by value into the kernel's parameter space at every launch, so nothing is
     uploaded and the launch is graph-capturable) and keeps every referenced tensor alive."""
 
-    def __init__(self, B, d, h, d_ff):
-        self.B, self.d, self.h, self.d_ff = int(B), int(d), int(h), int(d_ff)
+    def __init__(self, B, d, h, d_ff, rows_per_dialogue=1):
+        """B target rows = D dialogues x rows_per_dialogue hypotheses (beam search; greedy decoding: 1)."""
+        self.B, self.d, self.h, self.d_ff, self.R = int(B), int(d), int(h), int(d_ff), int(rows_per_dialogue)
+        assert self.R >= 1 and self.B % self.R == 0
+        self.D = self.B // self.R
         self.sites, self.keep = [], []
 
     def _site(self, kind, ln, w_in, b_in, w_out, b_out):
@@ -626,17 +629,17 @@ class DecodeClusterPlan(object):
         self.keep.append(cache)
 
     def cross_attention(self, ln, w_q, b_q, w_o, b_o, kv, k_col, v_col, Lk, mask_bits=None):
-        """kv: f16 [B*Lk, ld] with K at columns [k_col, k_col + d), V at [v_col, v_col + d) (the memory stage's hoisted
-        projections); mask_bits: mask_pack output [B, 1, words] or None."""
+        """kv: f16 [D*Lk, ld] with K at columns [k_col, k_col + d), V at [v_col, v_col + d) (the memory stage's hoisted
+        projections, one set per DIALOGUE); mask_bits: mask_pack output [D, 1, words] or None."""
         d = self.d
         _req(kv, torch.float16, "kv")
-        assert kv.dim() == 2 and kv.shape[0] == self.B * Lk and kv.stride(1) == 1
+        assert kv.dim() == 2 and kv.shape[0] == self.D * Lk and kv.stride(1) == 1
         assert tuple(w_q.shape) == (d, d) and tuple(w_o.shape) == (d, d) and b_q.numel() == d and b_o.numel() == d
         s = self._site(1, ln, w_q, b_q, w_o, b_o)
         s.k, s.v = kv.data_ptr() + 2 * int(k_col), kv.data_ptr() + 2 * int(v_col)
         s.ld_kv, s.Lk, s.kv_batch_stride = kv.stride(0), int(Lk), int(Lk) * kv.stride(0)
         if mask_bits is not None:
-            assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == self.B
+            assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.shape[0] == self.D
             assert mask_bits.shape[1] == 1 and mask_bits.shape[2] == mask_words(Lk)
             s.mask_bits, s.mask_words = mask_bits.data_ptr(), mask_bits.shape[2]
             self.keep.append(mask_bits)
@@ -663,6 +666,7 @@ class DecodeClusterPlan(object):
         a = DecodeClusterArgs()
         a.sites, a.n_sites = self.arr, len(self.sites)
         a.B, a.d, a.h, a.d_ff, a.t = self.B, self.d, self.h, self.d_ff, int(t)
+        a.rows_per_dialogue = self.R
         a.x_in, a.out = x_in.data_ptr(), out.data_ptr()
         a.norm_a, a.norm_b, a.norm_eps = self.norm[0].data_ptr(), self.norm[1].data_ptr(), float(self.norm[2])
         if taps is not None:

@@ -92,6 +92,7 @@ struct DcTable {
 
 struct DcParams {
   int n_sites, B, G, t;
+  int R;               // target rows per dialogue (beam search: R hypotheses share their dialogue's memories; greedy: 1)
   const float* x_in;
   float* out;
   const float* norm_a;
@@ -155,6 +156,7 @@ __device__ __forceinline__ void dc_mma(float (&c)[4], uint32_t a0, uint32_t a2, 
 // waits for the cluster -- and the compute warp takes the chunks in exactly the same order (dc_acquire / dc_release).
 struct DcCtx {
   int n_sites, t, nrows, row0, rank, warp, lane;   // warp: index of the COMPUTE warp of the pair
+  int R;                                           // rows per dialogue
   uint32_t ring, bars;                             // shared-memory addresses: this pair's ring, the barrier area
 };
 
@@ -230,7 +232,8 @@ __device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab, c
       // segment l % 8 of keys l / 8 + 4 it
       const int u = c.warp + 8 * j;
       const int g = u / nck, ck = u - g * nck;
-      const uint8_t* base = static_cast<const uint8_t*>(d.k) + ((size_t)(c.row0 + g) * d.kv_batch_stride + c.rank * DC_DK + seg * 8) * 2;
+      const int bidx = d.kind == 1 ? (c.row0 + g) / c.R : c.row0 + g;   // static memories are stored once per dialogue
+      const uint8_t* base = static_cast<const uint8_t*>(d.k) + ((size_t)bidx * d.kv_batch_stride + c.rank * DC_DK + seg * 8) * 2;
       const uint32_t sl = slot_wait();
       const uint32_t dst = c.ring + sl * DC_SLOT + (lane >> 3) * DC_KPITCH + seg * 16;
 #pragma unroll
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
   cluster_sync_all();   // every CTA of the cluster is running, its barriers initialised, before anyone writes into a peer
 
   DcCtx ctx;
-  ctx.n_sites = p.n_sites; ctx.t = p.t; ctx.nrows = nrows; ctx.row0 = row0;
+  ctx.n_sites = p.n_sites; ctx.t = p.t; ctx.nrows = nrows; ctx.row0 = row0; ctx.R = p.R;
   ctx.rank = (int)rank; ctx.warp = warp & (DC_CWARPS - 1); ctx.lane = lane;
   ctx.ring = sbase + DC_OFF_RING + ctx.warp * (DC_NSLOT * DC_SLOT);
   ctx.bars = bars;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
       if (kind == 1 && d.mask_bits != nullptr && lane < nun) {
         const int u = warp + 8 * lane;
         const int gu = u / nck;
-        mwords = __ldg(d.mask_bits + (size_t)(row0 + gu) * d.mask_words + (u - gu * nck));
+        mwords = __ldg(d.mask_bits + (size_t)((row0 + gu) / p.R) * d.mask_words + (u - gu * nck));
       }
       if (lane < DC_G) pm[warp * DC_G + lane] = -CUDART_INF_F;
       // ---- LayerNorm: warp w normalises row w -> f16 A operand
@@ -737,6 +740,8 @@ extern "C" int mtn_decode_cluster_fwd(const MtnDecodeClusterArgs* a, void* strea
   MTN_REQUIRE(a && a->sites && a->x_in && a->out && a->norm_a && a->norm_b, MTN_E_ARG, "decode_cluster: NULL pointer");
   MTN_REQUIRE(mtn_decode_cluster_supported(a->B, a->d, a->h, a->d_ff), MTN_E_SHAPE,
               "decode_cluster: B=%d d=%d h=%d d_ff=%d (d = 512, h = 8, d_ff = 2048, B <= 128)", a->B, a->d, a->h, a->d_ff);
+  MTN_REQUIRE(a->rows_per_dialogue <= 1 || a->B % a->rows_per_dialogue == 0, MTN_E_SHAPE, "decode_cluster: B=%d is not a multiple of rows_per_dialogue=%d",
+              a->B, a->rows_per_dialogue);
   MTN_REQUIRE(a->n_sites >= 1 && a->n_sites <= DC_MAX_SITES && a->t >= 0, MTN_E_SHAPE, "decode_cluster: n_sites=%d (<= %d), t=%d", a->n_sites,
               DC_MAX_SITES, a->t);
   MTN_REQUIRE(aligned16(a->x_in) && aligned16(a->out) && aligned16(a->norm_a) && aligned16(a->norm_b) && (!a->taps || aligned16(a->taps)),
@@ -777,7 +782,7 @@ extern "C" int mtn_decode_cluster_fwd(const MtnDecodeClusterArgs* a, void* strea
   const int G = (a->B + max_clusters - 1) / max_clusters;
   MTN_REQUIRE(G <= DC_G, MTN_E_SHAPE, "decode_cluster: B=%d needs %d rows per cluster (%d clusters fit), at most %d", a->B, G, max_clusters, DC_G);
   const int nclusters = (a->B + G - 1) / G;
-  DcParams p{a->n_sites, a->B, G, a->t, a->x_in, a->out, a->norm_a, a->norm_b, a->norm_eps, a->taps, a->stamps,
+  DcParams p{a->n_sites, a->B, G, a->t, a->rows_per_dialogue > 1 ? a->rows_per_dialogue : 1, a->x_in, a->out, a->norm_a, a->norm_b, a->norm_eps, a->taps, a->stamps,
              static_cast<const __half*>(a->gen_w), a->gen_b, a->gen_V, a->gen_V8, reinterpret_cast<long long*>(a->tokens), a->tokens_stride};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MTN_CHECK_CUDA(launch_kernel_cluster(decode_cluster_kernel, dim3(nclusters * DC_CS), dim3(DC_THREADS), DC_SMEM, st, DC_CS, tab, p));

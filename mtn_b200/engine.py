@@ -560,12 +560,12 @@ class DecoderEngine(object):
 
     def _cluster_plan(self, st):
         """The _lib.DecodeClusterPlan of this decoding state, or None when the step takes the launch sequence.  Default on
-        (MTN_B200_DECODE_CLUSTER=0: off) for greedy decoding (one row per dialogue) at d = 512, h = 8, d_ff = 2048,
-        B <= 128: a decoding step's dependency chain is per dialogue, so a cluster of 8 CTAs (one per head) takes a group
+        (MTN_B200_DECODE_CLUSTER=0: off) for greedy decoding and beam search (R hypotheses per dialogue share its
+        memories) at d = 512, h = 8, d_ff = 2048, at most 128 target rows: a decoding step's dependency chain is per dialogue, so a cluster of 8 CTAs (one per head) takes a group
         of dialogues through all sublayers of the step with cluster barriers only, streaming its weights and K / V ahead
         of the chain -- ONE launch instead of ~135."""
         if (os.environ.get("MTN_B200_DECODE_CLUSTER", DECODE_CLUSTER_DEFAULT) == "0" or not _lib.ROWS_KERNELS or
-                st["R"] != 1 or TAP is not None or os.environ.get("MTN_B200_DECODE_PROG", "0") == "1"):
+                TAP is not None or os.environ.get("MTN_B200_DECODE_PROG", "0") == "1"):
             return None
         plan = st.get("cluster_plan", False)
         if plan is False:
@@ -582,7 +582,7 @@ class DecoderEngine(object):
         bits = [S["bits_his"], S["bits_cap"], S["bits_q"], S["bits_ae"]]
         if any(b is not None and b.shape[1] != 1 for b in bits) or max(S["H"], S["C"], S["Q"], S["La"]) > 1024:
             return None
-        plan = _lib.DecodeClusterPlan(B, d, h, dff)
+        plan = _lib.DecodeClusterPlan(B, d, h, dff, rows_per_dialogue=st["R"])
         order = self._site_order(st["ae_features"])
         for l in range(N):
             Lw = W["layers"][l]

@@ -521,6 +521,14 @@ def test_batched_beam_search_on_the_kernels(M, cfg2_model, monkeypatch):
             monkeypatch.delenv("MTN_B200_BEAM_SERIAL")
             one = du.beam_search_decode(model, mk(slice(1, 2)), steps, 2, 0, 3, 1, beam=5, penalty=1.0, nbest=5)
             assert [list(map(int, h)) for h, _ in one[0]] == [list(map(int, h)) for h, _ in got[1][0]]
+            # the batched search's steps run as the cluster kernel (5 hypotheses per dialogue share its memories); the
+            # launch sequence of the few-row kernels finds the same hypotheses
+            monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", "0")
+            seq = du.beam_search_decode_batched(model, mk(slice(0, D)), steps, 2, 0, 3, 1, beam=5, penalty=1.0, nbest=5)
+            monkeypatch.delenv("MTN_B200_DECODE_CLUSTER")
+            for i in range(D):
+                assert [list(map(int, h)) for h, _ in seq[i][0]] == [list(map(int, h)) for h, _ in got[i][0]], i
+                assert np.allclose([s for _, s in seq[i][0]], [s for _, s in got[i][0]], rtol=0, atol=2e-2)
     finally:
         model.generator.proj.weight.data.copy_(w0)
         invalidate_weight_caches()
