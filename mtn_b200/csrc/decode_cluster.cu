@@ -40,6 +40,7 @@
 // with the summation order of layernorm_rows_kernel); only the summation order of the projections differs (one warp
 // accumulates the whole contraction).  d = 512, h = 8, d_ff = 2048, one query row per dialogue (greedy decoding).
 #include <math_constants.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -106,6 +107,7 @@ struct DcParams {
   int gen_V, gen_V8;
   long long* tokens;         // token of row r -> tokens[r * tokens_stride]
   long long tokens_stride;
+  int kv_prefetch;           // L2 prefetch of the next cross-attention sublayer's K / V (MTN_B200_DECODE_KV_PREFETCH=1; default off)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -188,7 +190,7 @@ __device__ __forceinline__ void dc_issue_w(uint32_t dst, const uint8_t* src) {
 
 // producer warp: the whole chunk sequence of its compute warp, slot by slot (cp.async, 16 bytes per lane and copy; the
 // slot's FULL barrier collects one deferred arrival per lane)
-__device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab, const void* gen_w, int gen_groups) {
+__device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab, const void* gen_w, int gen_groups, int pf_on) {
   uint32_t n = 0;
   const int lane = c.lane;
   const uint32_t full0 = c.bars + 8u * (DC_BAR_FULL + c.warp * DC_NSLOT), empty0 = c.bars + 8u * (DC_BAR_EMPTY + c.warp * DC_NSLOT);
@@ -209,9 +211,31 @@ __device__ __forceinline__ void dc_produce(const DcCtx& c, const DcTable& tab, c
       dc_cp_arrive(full0 + 8u * sl);
     }
   };
+  // (experiment, opt-in) K / V of a cross-attention sublayer -> L2, one sublayer ahead of its use.  Measured without
+  // effect: the step is bound by its dependency chain, not by where the K / V come from.
+  // Line i of the CTA's (row, key, K | V) lines goes to producer lane (i % 256).
+  auto kv_prefetch = [&](const MtnDecodeSite& d) {
+    const int lines = c.nrows * d.Lk * 2;
+    for (int i = c.warp * 32 + lane; i < lines; i += 256) {
+      const int kvsel = i & 1, rk = i >> 1;
+      const int g = rk / d.Lk, key = rk - g * d.Lk;
+      const uint8_t* a = static_cast<const uint8_t*>(kvsel ? d.v : d.k) +
+                         ((size_t)((c.row0 + g) / c.R) * d.kv_batch_stride + (size_t)key * d.ld_kv + c.rank * DC_DK) * 2;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  };
+  const bool pf = pf_on != 0;
 #pragma unroll 1
   for (int s = 0; s < c.n_sites; ++s) {
     const MtnDecodeSite& d = tab.s[s];
+    if (pf) {   // the next cross-attention sublayer after s (s itself if it is the first one)
+      if (s == 0 && d.kind == 1) kv_prefetch(d);
+      for (int s2 = s + 1; s2 < c.n_sites; ++s2)
+        if (tab.s[s2].kind != 2) {
+          if (tab.s[s2].kind == 1) kv_prefetch(tab.s[s2]);
+          break;
+        }
+    }
     if (d.kind == 2) {
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) weights(d.w_in, DC_D, c.rank * 256 + (j * 8 + c.warp) * 8, 1);
@@ -401,7 +425,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
   ctx.bars = bars;
 
   if (warp >= DC_CWARPS) {
-    dc_produce(ctx, tab, p.gen_w, p.gen_V8 >> 3);
+    dc_produce(ctx, tab, p.gen_w, p.gen_V8 >> 3, p.kv_prefetch);
   } else {
     uint32_t taken = 0;
     const int col = (int)rank * 64 + warp * 8 + 2 * q;   // this thread's output columns of a d-wide projection
@@ -703,6 +727,15 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const __g
   cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
 }
 
+static int dc_kv_prefetch_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTN_B200_DECODE_KV_PREFETCH");   // opt-in: measured without effect (380 vs 375 us per step)
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
 static int dc_max_clusters(int* out) {
   static int cached = 0;
   if (cached == 0) {
@@ -783,7 +816,7 @@ extern "C" int mtn_decode_cluster_fwd(const MtnDecodeClusterArgs* a, void* strea
   MTN_REQUIRE(G <= DC_G, MTN_E_SHAPE, "decode_cluster: B=%d needs %d rows per cluster (%d clusters fit), at most %d", a->B, G, max_clusters, DC_G);
   const int nclusters = (a->B + G - 1) / G;
   DcParams p{a->n_sites, a->B, G, a->t, a->rows_per_dialogue > 1 ? a->rows_per_dialogue : 1, a->x_in, a->out, a->norm_a, a->norm_b, a->norm_eps, a->taps, a->stamps,
-             static_cast<const __half*>(a->gen_w), a->gen_b, a->gen_V, a->gen_V8, reinterpret_cast<long long*>(a->tokens), a->tokens_stride};
+             static_cast<const __half*>(a->gen_w), a->gen_b, a->gen_V, a->gen_V8, reinterpret_cast<long long*>(a->tokens), a->tokens_stride, dc_kv_prefetch_enabled()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MTN_CHECK_CUDA(launch_kernel_cluster(decode_cluster_kernel, dim3(nclusters * DC_CS), dim3(DC_THREADS), DC_SMEM, st, DC_CS, tab, p));
   return MTN_OK;
