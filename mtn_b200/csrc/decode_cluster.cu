@@ -295,35 +295,34 @@ __device__ __forceinline__ void dc_release(const DcCtx& c, uint32_t& taken) {
 template <int KCH>   // K = 512 * KCH
 __device__ __forceinline__ float2 dc_proj(const DcCtx& c, uint32_t& taken, uint32_t smem_base, int a_off, int lda) {
   const int g = c.lane >> 2, q = c.lane & 3;
-  float acc[4][4];
+  // A fragment rows beyond the cluster's rows are zero: their quarter-warps (two rows each) do not touch shared memory
+  const bool live = (g & ~1) < c.nrows;
+  // EIGHT independent accumulators: a dependent mma.sync costs ~90 cycles here, and a chunk is 32 of them
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll 1
   for (int kp = 0; kp < KCH; ++kp) {
     const uint32_t arow = smem_base + a_off + g * lda + (kp * 512 + 8 * q) * 2;
-    uint4 a[8], w[8];
+    uint32_t wrow = 0;
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) a[cc] = dc_lds128(arow + cc * 64);
-    const uint32_t wrow = dc_acquire(c, taken) + g * DC_WPITCH + (q << 4);
+    for (int h = 0; h < 4; ++h) {
+      uint4 a[4], w[4];
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) w[cc] = dc_lds128(wrow + cc * 64);
+      for (int cc = 0; cc < 4; ++cc) a[cc] = live ? dc_lds128(arow + (4 * h + cc) * 64) : make_uint4(0u, 0u, 0u, 0u);
+      if (h == 0) wrow = dc_acquire(c, taken) + g * DC_WPITCH + (q << 4);
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      dc_mma(acc[cc & 3], a[cc].x, a[cc].y, w[cc].x, w[cc].y);
-      dc_mma(acc[cc & 3], a[cc].z, a[cc].w, w[cc].z, w[cc].w);
-    }
+      for (int cc = 0; cc < 4; ++cc) w[cc] = dc_lds128(wrow + (4 * h + cc) * 64);
+      if (h == 3) dc_release(c, taken);
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) a[cc] = dc_lds128(arow + 512 + cc * 64);
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) w[cc] = dc_lds128(wrow + 512 + cc * 64);
-    dc_release(c, taken);
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      dc_mma(acc[cc & 3], a[cc].x, a[cc].y, w[cc].x, w[cc].y);
-      dc_mma(acc[cc & 3], a[cc].z, a[cc].w, w[cc].z, w[cc].w);
+      for (int cc = 0; cc < 4; ++cc) {
+        dc_mma(acc[2 * cc], a[cc].x, a[cc].y, w[cc].x, w[cc].y);
+        dc_mma(acc[2 * cc + 1], a[cc].z, a[cc].w, w[cc].z, w[cc].w);
+      }
     }
   }
-  return make_float2((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]), (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]));
+  return make_float2(((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0])) + ((acc[4][0] + acc[5][0]) + (acc[6][0] + acc[7][0])),
+                     ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1])) + ((acc[4][1] + acc[5][1]) + (acc[6][1] + acc[7][1])));
 }
 
 // LayerNorm parameters of one row pass: lane l holds float4 (l + 32 i) of a_2 / b_2
