@@ -76,6 +76,22 @@ def test_argument_validation_without_gpu():
     assert L.mtn_attn_core_fwd(ctypes.byref(c), None) == -1
     assert b"d_k=48" in L.mtn_last_error()
     assert L.mtn_layernorm_fwd(None, None, None, 1e-6, 1, 4, None, None, None) == -5
+    # the cluster decoding step (ABI v7): shape support and argument validation happen on the host
+    assert L.mtn_decode_cluster_supported(64, 512, 8, 2048) == 1 and L.mtn_decode_cluster_supported(128, 512, 8, 2048) == 1
+    assert L.mtn_decode_cluster_supported(129, 512, 8, 2048) == 0 and L.mtn_decode_cluster_supported(64, 1024, 16, 4096) == 0
+    assert L.mtn_decode_cluster_max_sites() >= 42                  # N = 6 layers x (self + 5 cross + feed-forward)
+    d = _lib.DecodeClusterArgs()
+    assert L.mtn_decode_cluster_fwd(ctypes.byref(d), None) == -5  # NULL site list / rows / norm
+    assert b"NULL" in L.mtn_last_error()
+    site = (_lib.DecodeSite * 1)()
+    d.sites, d.n_sites, d.x_in, d.out, d.norm_a, d.norm_b = site, 1, 16, 16, 16, 16
+    d.B, d.d, d.h, d.d_ff = 64, 256, 4, 1024
+    assert L.mtn_decode_cluster_fwd(ctypes.byref(d), None) == -1  # MTN_E_SHAPE
+    assert b"d = 512" in L.mtn_last_error()
+    d.d, d.h, d.d_ff, d.rows_per_dialogue = 512, 8, 2048, 5
+    assert L.mtn_decode_cluster_fwd(ctypes.byref(d), None) == -1 and b"rows_per_dialogue" in L.mtn_last_error()
+    d.rows_per_dialogue = 1
+    assert L.mtn_decode_cluster_fwd(ctypes.byref(d), None) == -5 and b"site 0" in L.mtn_last_error()   # site with NULL pointers
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
