@@ -252,7 +252,8 @@ int mtn_prog_launch(const void *dev_prog, int n_stages, void *counter, void *str
  * cross-attention sublayers over static (already projected) memories and its feed-forward sublayer, each a pre-norm
  * residual sublayer (mtn.py:125-127), then Decoder.norm (mtn.py:164) -- described as a flat list of sublayers
  * ("sites") in execution order.  A cluster of 8 CTAs owns ceil(B / #clusters) dialogues for the whole step; CTA r owns
- * head r.  d = 512, h = 8 (d_k = 64), d_ff = 2048, B <= 128, n_sites <= mtn_decode_cluster_max_sites().
+ * head r.  d = 512, h = 8 (d_k = 64), d_ff = 2048, B <= 8 rows x the clusters the device keeps co-resident (13 on a B200:
+ * 104 rows; mtn_decode_cluster_supported tells), n_sites <= mtn_decode_cluster_max_sites().
  *   kind 0  self-attention:  w_in = [Wq;Wk;Wv] f16 [3d, d], b_in [3d];  q_cache / k / v = column 0 / d / 2d of row 0,
  *           dialogue 0 of the layer's cache (f16 [B, T_max, 3d]: ld_kv = 3d, kv_batch_stride = T_max * 3d).  The new
  *           position's [Q|K|V] is written to cache row t; keys / values are cache rows 0..t (no mask: causal past).

@@ -761,8 +761,17 @@ static int dc_max_clusters(int* out) {
 
 }  // namespace mtn
 
+// B rows fit when ceil(B / co-resident clusters) <= 8 rows per cluster.  The cluster count is a property of the device (13 on
+// the B200s this was measured on: 104 rows); without a usable device (host-only callers, tests) 16 clusters are assumed.
 extern "C" int mtn_decode_cluster_supported(int B, int d, int h, int d_ff) {
-  return (B >= 1 && B <= 16 * mtn::DC_G && d == mtn::DC_D && h == mtn::DC_CS && d_ff == mtn::DC_DFF) ? 1 : 0;
+  if (!(B >= 1 && d == mtn::DC_D && h == mtn::DC_CS && d_ff == mtn::DC_DFF)) return 0;
+  int clusters = 0, ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || mtn::dc_max_clusters(&clusters) != MTN_OK) {
+    cudaGetLastError();
+    clusters = 16;
+  }
+  if (clusters > 16) clusters = 16;
+  return B <= clusters * mtn::DC_G ? 1 : 0;
 }
 
 extern "C" int mtn_decode_cluster_max_sites(void) { return mtn::DC_MAX_SITES; }
@@ -771,7 +780,8 @@ extern "C" int mtn_decode_cluster_fwd(const MtnDecodeClusterArgs* a, void* strea
   using namespace mtn;
   MTN_REQUIRE(a && a->sites && a->x_in && a->out && a->norm_a && a->norm_b, MTN_E_ARG, "decode_cluster: NULL pointer");
   MTN_REQUIRE(mtn_decode_cluster_supported(a->B, a->d, a->h, a->d_ff), MTN_E_SHAPE,
-              "decode_cluster: B=%d d=%d h=%d d_ff=%d (d = 512, h = 8, d_ff = 2048, B <= 128)", a->B, a->d, a->h, a->d_ff);
+              "decode_cluster: B=%d d=%d h=%d d_ff=%d (d = 512, h = 8, d_ff = 2048, B <= 8 rows x co-resident clusters)", a->B, a->d, a->h,
+              a->d_ff);
   MTN_REQUIRE(a->rows_per_dialogue <= 1 || a->B % a->rows_per_dialogue == 0, MTN_E_SHAPE, "decode_cluster: B=%d is not a multiple of rows_per_dialogue=%d",
               a->B, a->rows_per_dialogue);
   MTN_REQUIRE(a->n_sites >= 1 && a->n_sites <= DC_MAX_SITES && a->t >= 0, MTN_E_SHAPE, "decode_cluster: n_sites=%d (<= %d), t=%d", a->n_sites,

@@ -492,6 +492,54 @@ def test_decode_cluster_step_equals_launch_sequence(M, cfg2_model, monkeypatch):
         invalidate_weight_caches()
 
 
+def test_decode_cluster_caption_variant_and_fallback(M, cfg2_model, monkeypatch):
+    """(1) auto_encoder_ft = 'caption' (mtn.py:187-194: the query sublayer comes before the caption sublayer, the
+    auto-encoder memories and their mask come from the caption; ONE modality, ragged lengths) through the cluster
+    decoding step: greedy tokens equal to the CPU oracle's full-recompute greedy decoding and to the launch sequence's.
+    (2) More rows than the device's co-resident clusters hold (8 rows each): ``decode_step`` takes the launch sequence
+    instead of failing, and produces the rows the cluster kernel produces for the first dialogues."""
+    mtn, du = M
+    from mtn_b200 import _lib
+    cfg = {"N": 2, "d_model": 512, "d_ff": 2048, "h": 8, "vocab": 120, "ft_sizes": [2048], "auto_encoder_ft": "caption",
+           "diff_encoder": True}
+    sd = O.init_state_dict(cfg, 21)
+    sd["generator.proj.weight"] = sd["generator.proj.weight"] * 8.0
+    model = build(mtn, cfg, sd)
+    inp = O.synth_inputs(cfg, B=5, Q=9, C=40, H=70, T=4, Lv=[33], seed=12)
+    g = lambda t: t.cuda()
+    b = du.Batch(g(inp["query"]), g(inp["his"]), None, [g(inp["fts"][0]).permute(1, 0, 2).contiguous()], g(inp["cap"]), None, None, 1)
+    ys = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MTN_B200_DECODE_CLUSTER", mode)
+        with torch.no_grad():
+            ys[mode] = du.greedy_decode(model, b, 10, 2, cached=True).cpu()
+    monkeypatch.delenv("MTN_B200_DECODE_CLUSTER")
+    ref = O.greedy_decode(sd, cfg, inp["query"], inp["his"], inp["cap"], inp["fts"], 10)
+    print("caption variant, cluster decoding step:", ys["1"].tolist(), ref.tolist())
+    assert torch.equal(ys["1"], ref) and torch.equal(ys["0"], ref)
+    # (2)
+    cfg2, model2 = cfg2_model
+    B = 8 * 16 + 2            # more than any device's clusters can hold
+    assert not _lib.decode_cluster_supported(B, 512, 8, 2048, 42) and _lib.decode_cluster_supported(64, 512, 8, 2048, 42)
+    inp = O.synth_inputs(cfg2, B=B, Q=64, C=64, H=256, T=3, Lv=[512, 256], seed=77)
+    bb = make_batch(du, inp)
+    with torch.no_grad():
+        q, vid, cap, his, ae = model2.encode(bb.query, bb.query_mask, bb.his, bb.his_mask, bb.cap, bb.cap_mask, bb.fts, bb.fts_mask)
+        st = model2.decode_begin(vid, his, cap, q, bb.fts_mask, bb.his_mask, bb.cap_mask, bb.query_mask, ae, 3)
+        rows = [model2.decode_step(st, bb.trg[:, t]).clone() for t in range(3)]
+        assert st.get("cluster_plan") is None
+        sl = slice(0, 16)
+        sub = make_batch(du, {k: (v[sl] if torch.is_tensor(v) else [f[sl] for f in v]) for k, v in inp.items()})
+        q, vid, cap, his, ae = model2.encode(sub.query, sub.query_mask, sub.his, sub.his_mask, sub.cap, sub.cap_mask, sub.fts, sub.fts_mask)
+        st2 = model2.decode_begin(vid, his, cap, q, sub.fts_mask, sub.his_mask, sub.cap_mask, sub.query_mask, ae, 3)
+        rows2 = [model2.decode_step(st2, bb.trg[sl, t]).clone() for t in range(3)]
+        assert st2.get("cluster_plan") is not None
+    torch.cuda.synchronize()
+    e = max(G.rel_err(rows2[t].cpu(), rows[t][sl].cpu()) for t in range(3))
+    print("launch-sequence fallback at %d rows vs cluster step on the first 16 dialogues: %.2e" % (B, e))
+    assert e < 5e-4
+
+
 def test_batched_beam_search_on_the_kernels(M, cfg2_model, monkeypatch):
     """generate.py's path (data_utils.py:188-242): the batched, KV-cached beam search over 3 dialogues returns, per
     dialogue, the hypotheses of the serial search in the reference's call form (one full-prefix ``model.decode`` per
