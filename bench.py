@@ -952,6 +952,34 @@ def main():
                 os.environ.pop("MTN_B200_BEAM_SERIAL", None)
                 decode["beam_search"] = {"error": repr(e)[:300]}
 
+        # ---- the cluster decoding step at the row capacity of the device (context, rank 0 of a 1-GPU run): a cluster
+        # takes up to 8 dialogues; 75 % of a batch-64 step is the fixed per-cluster chain, so more rows per launch
+        # amortise it
+        if world == 1:
+            try:
+                cap_b = max(b_ for b_ in range(64, 129, 8) if _lib.decode_cluster_supported(b_, CFG["d_model"], CFG["h"], CFG["d_ff"], 7 * CFG["N"]))
+                hb = O.synth_inputs(CFG, B=cap_b, Q=SHAPE["Q"], C=SHAPE["C"], H=SHAPE["H"], T=4, Lv=SHAPE["Lv"], seed=5100)
+                decb = GraphedGreedyDecoder(model, {k: (v.to(dev) if torch.is_tensor(v) else [f.half().to(dev) for f in v])
+                                                    for k, v in hb.items() if k in ("query", "his", "cap", "fts")}, Ld)
+                decb.decode(); torch.cuda.synchronize()
+                e0.record()
+                for _ in range(3):
+                    decb.decode()
+                e1.record(); torch.cuda.synchronize()
+                ms_b = e0.elapsed_time(e1) / 3
+                e0.record()
+                for _ in range(3):
+                    for g_ in decb.graphs[1:]:
+                        g_.replay()
+                e1.record(); torch.cuda.synchronize()
+                decode["at_row_capacity"] = {"batch": cap_b, "generated_tokens_per_s": cap_b * (Ld - 1) / (ms_b * 1e-3), "ms_per_batch": ms_b,
+                                             "us_per_step": e0.elapsed_time(e1) * 1e3 / (3 * sum(decb.steps_in_graph[1:])),
+                                             "note": "device-resident inputs, memory stage + all steps; the largest batch (multiple "
+                                                     "of 8) whose rows fit the co-resident clusters"}
+                del decb, hb
+            except Exception as e:
+                decode["at_row_capacity"] = {"error": repr(e)[:300]}
+
     # ------------------------------------------------------------- training step (forward + loss + backward +
     # ONE NCCL gradient all-reduce + Adam), BASELINE configs[1] / [2]
     train = None
